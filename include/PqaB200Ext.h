@@ -1,0 +1,95 @@
+/* probqa_b200 -- additive C entry points of libPqaCore.so that the reference's one-quiz-per-call ABI cannot express.
+ *
+ * None of these exists in the reference (ProbQA/PqaCore/Interface/PqaCInterop.h); they follow its conventions
+ * (void* = NULL or owned PqaError; plain pointers and sizes; caller owns every buffer). They exist because
+ * BASELINE configs 2-4 are batches of concurrent quizzes sharing one stream over sA/mD (SURVEY.md 8b last row).
+ * All host pointers are ordinary host memory unless the parameter name starts with "d" (device pointer). */
+#ifndef PQA_B200_EXT_H
+#define PQA_B200_EXT_H
+#include "PqaCInterop.h"
+
+#pragma pack(push, 8)
+typedef struct {
+  int32_t _device;           /* CUDA device ordinal; -1 = current device / env PQA_B200_DEVICE */
+  /* Worker count W of the CpuEngine being reproduced (reference: std::thread::hardware_concurrency(),
+   * BaseCpuEngine.cpp:21-22). It fixes the order of the Kahan sums in StartQuiz/RecordAnswer, the run-length
+   * chunking of NextQuestion and the piece split of ListTopTargets, i.e. the bits of the results.
+   * 0 = env PQA_B200_EMULATED_WORKERS, else this host's hardware_concurrency(). */
+  int32_t _emulatedWorkers;
+  uint64_t _rngSeed;         /* seed of the host xorshift128+ used by NextQuestion; 0 = std::random_device */
+  int64_t _initialQuizCapacity; /* quiz slots pre-allocated on the device; 0 = 256 */
+} CiB200Options;
+#pragma pack(pop)
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Same contract as PqaEngineFactory_CreateCpuEngine, with explicit options. */
+PQACORE_API void *PqaB200_CreateEngine(void **ppError, const CiEngineDefinition *pEngDef, const CiB200Options *pOpts);
+PQACORE_API int32_t PqaB200_GetEmulatedWorkers(void *pvEngine);
+PQACORE_API int32_t PqaB200_GetDevice(void *pvEngine);
+PQACORE_API const char *PqaB200_BuildInfo(void); /* static string: arch, build flags */
+
+/* C exports of IPqaEngine::CopyATargets/CopyDTargets/CopyBTargets (Interface/IPqaEngine.h:36-39; C++-only in the
+ * reference). */
+PQACORE_API void *PqaEngine_CopyATargets(void *pvEngine, int64_t iQuestion, int64_t iAnswer, int64_t maxTargets, double *pFreqs);
+PQACORE_API void *PqaEngine_CopyDTargets(void *pvEngine, int64_t iQuestion, int64_t maxTargets, double *pFreqs);
+PQACORE_API void *PqaEngine_CopyBTargets(void *pvEngine, int64_t maxTargets, double *pFreqs);
+
+/* Whole-KB transfer in the reference's file layout (CpuEngine.cpp:664-688): sA[(i*K+k)*T + j], mD[i*T + j], vB[j]. */
+PQACORE_API void *PqaB200_UploadKB(void *pvEngine, const double *sA, const double *mD, const double *vB);
+PQACORE_API void *PqaB200_DownloadKB(void *pvEngine, double *sA, double *mD, double *vB);
+
+/* ---- batches of concurrent quizzes (each quiz id must appear at most once per call) ---- */
+PQACORE_API void *PqaEngine_StartQuizBatch(void *pvEngine, int64_t n, int64_t *pQuizIds);
+/* pRandoms: optional n 64-bit draws replacing the engine RNG (SRDoubleNumber.h:35-39 consumes one per call).
+ * pQuestions[i] = chosen question or -1; ppErrors: optional n slots receiving NULL / owned per-quiz errors. */
+PQACORE_API void *PqaEngine_NextQuestionBatch(void *pvEngine, int64_t n, const int64_t *pQuizIds,
+                                              const uint64_t *pRandoms, int64_t *pQuestions, void **ppErrors);
+PQACORE_API void *PqaEngine_RecordAnswerBatch(void *pvEngine, int64_t n, const int64_t *pQuizIds, const int64_t *pAnswers);
+PQACORE_API void *PqaEngine_SetActiveQuestionBatch(void *pvEngine, int64_t n, const int64_t *pQuizIds, const int64_t *pQuestions);
+/* pDest: n*maxCount items, row i belongs to quiz i; pCounts[i] = number listed. */
+PQACORE_API void *PqaEngine_ListTopTargetsBatch(void *pvEngine, int64_t n, const int64_t *pQuizIds, int64_t maxCount,
+                                                CiRatedTarget *pDest, int64_t *pCounts);
+/* Applied in array order, exactly as n successive PqaEngine_RecordQuizTarget calls would be. pAmounts may be NULL (=1). */
+PQACORE_API void *PqaEngine_RecordQuizTargetBatch(void *pvEngine, int64_t n, const int64_t *pQuizIds,
+                                                  const int64_t *pTargets, const double *pAmounts);
+PQACORE_API void *PqaEngine_ReleaseQuizBatch(void *pvEngine, int64_t n, const int64_t *pQuizIds);
+
+/* ---- inspection (parity tests, diagnostics) ---- */
+PQACORE_API void *PqaB200_CopyQuizPriors(void *pvEngine, int64_t iQuiz, double *pPriors /* nTargets */);
+PQACORE_API void *PqaB200_SetQuizPriors(void *pvEngine, int64_t iQuiz, const double *pPriors /* nTargets */);
+/* Evaluates every question of each quiz without selecting one. Any output may be NULL.
+ * pPriorities[n*Q] (NaN for asked questions), pRunLength[n*Q] (chunk-local Kahan prefixes, CpuEngine.cpp:337-360),
+ * pGrandTotals[n*nChunks] with nChunks = min(Q, 8*W) returned in *pnChunks. */
+PQACORE_API void *PqaB200_EvalQuestions(void *pvEngine, int64_t n, const int64_t *pQuizIds, double *pPriorities,
+                                        double *pRunLength, double *pGrandTotals, int64_t *pnChunks);
+/* Per-answer metrics of one quiz: pW/pH/pV [Q*K], pLack [Q] (CEEvalQsSubtaskConsider.cpp:88,129-132,201). */
+PQACORE_API void *PqaB200_EvalQuestionsDetailed(void *pvEngine, int64_t iQuiz, double *pW, double *pH, double *pV,
+                                                double *pLack, double *pPriorities);
+/* Selects which evaluation kernel the engine uses: 0 auto, 1 generic (direct loads), 2 staged (TMA + shared memory). */
+PQACORE_API void *PqaB200_SetEvalKernel(void *pvEngine, int32_t which);
+
+/* ---- device-resident stepping and timing (bench.py "value" leg: no host<->device traffic inside) ---- */
+/* Binds n quizzes as the resident batch: ids and one random draw per quiz are copied to the device once. */
+PQACORE_API void *PqaB200_ResidentBind(void *pvEngine, int64_t n, const int64_t *pQuizIds, const uint64_t *pRandoms);
+/* One NextQuestion pass (evaluation + selection) over the resident batch, asynchronous on the engine stream;
+ * results stay on the device. */
+PQACORE_API void *PqaB200_ResidentStep(void *pvEngine);
+PQACORE_API void *PqaB200_ResidentFetch(void *pvEngine, int64_t *pQuestions /* n */);
+PQACORE_API void *PqaB200_Synchronize(void *pvEngine);
+PQACORE_API void *PqaB200_EventCreate(void);
+PQACORE_API void PqaB200_EventDestroy(void *pvEvent);
+PQACORE_API void *PqaB200_EventRecord(void *pvEngine, void *pvEvent); /* on the engine's stream */
+PQACORE_API void *PqaB200_EventSynchronize(void *pvEvent);
+PQACORE_API double PqaB200_EventElapsedMs(void *pvStart, void *pvStop);
+/* Number of kernel launches issued by this engine since creation (bench.py "gpu_launches"). */
+PQACORE_API uint64_t PqaB200_KernelLaunchCount(void *pvEngine);
+/* Writes a buffer larger than L2 on the engine's stream (timing hygiene between iterations). */
+PQACORE_API void *PqaB200_FlushL2(void *pvEngine);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PQA_B200_EXT_H */

@@ -1,0 +1,81 @@
+// probqa_b200: device-side data views and kernel launchers (sm_100a).
+// Every launcher cites the reference CPU code whose results it reproduces (paths relative to
+// /root/reference/ProbQA/). No launcher synchronises; all work is enqueued on the given stream.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace pqa {
+
+// Knowledge base resident in HBM. Rows are padded to a multiple of 4 doubles (32 B) like the reference's
+// SRFastArray rows (CpuEngine.decl.h:31-37): sA[(i*K + k)*Tp + j], mD[i*Tp + j], vB[j].
+// Padding lanes hold sA = 0, mD = 1, vB = 0 so that they produce the +0.0 the reference's gap mask produces
+// (GapTracker.h:12-15, SRSimd.h:253-256) without a branch.
+struct DeviceKB {
+  double *sA;
+  double *mD;
+  double *vB;
+  const double *log2tbl;   // 1024-entry table of SRVectMath.cpp:30-44
+  const uint32_t *tgaps;   // target gap bitmap (bit j of word j>>5) or nullptr
+  const uint32_t *qgaps;   // question gap bitmap or nullptr
+  int64_t Q, K, T, Tp;
+  int64_t nValidTargets;   // T - #target gaps (CpuEngine.cpp:351)
+};
+
+// Per-quiz state resident in HBM, addressed by quiz slot.
+struct QuizPool {
+  double *priors;          // [slot][Tp]  normalised posterior (CEQuiz.decl.h _pPriorMants); padding = +0
+  uint64_t *asked;         // [slot][askedWords]  bit i = question i already answered (CEBaseQuiz _isQAsked)
+  int64_t *active;         // [slot] active question or -1 (BaseQuiz.h _activeQuestion)
+  int64_t askedWords;      // ceil(Q/64)
+  int64_t Tp;
+};
+
+struct EvalDetail {        // optional per-answer outputs of the question evaluation (may all be nullptr)
+  double *W, *H, *V;       // [n][Q][K]
+  double *lack;            // [n][Q]
+};
+
+void launch_fill_kb(const DeviceKB &kb, double initSqr, double initMD, double init1, cudaStream_t st);
+// pack flat (stride T) host-layout rows into padded device rows and back
+void launch_pad_rows(double *dst, const double *src, int64_t nRows, int64_t T, int64_t Tp, double padValue, cudaStream_t st);
+void launch_unpad_rows(double *dst, const double *src, int64_t nRows, int64_t T, int64_t Tp, cudaStream_t st);
+
+// CECreateQuizStart::UpdateLikelihoods (CECreateQuizOperation.cpp:22-53): priors = vB / KahanSum_W(vB); asked = 0.
+void launch_start_quiz(const DeviceKB &kb, const QuizPool &qp, int64_t n, const int64_t *dSlots, int W, cudaStream_t st);
+// CEQuiz::RecordAnswer (CEQuiz.h:77-122): uses the quiz' active question, sets its asked bit, clears active.
+// dAnswers[n]; W = loose worker count max(1, hwc-1).
+void launch_record_answer(const DeviceKB &kb, const QuizPool &qp, int64_t n, const int64_t *dSlots,
+                          const int64_t *dAnswers, int W, cudaStream_t st);
+// CEEvalQsSubtaskConsider::Run (CEEvalQsSubtaskConsider.cpp:41-217) for every (quiz, question):
+// dPriority[n*Q] (NaN where asked/gap). which: 1 generic, 2 staged (TMA + smem), 0 auto.
+void launch_eval_questions(const DeviceKB &kb, const QuizPool &qp, int64_t n, const int64_t *dSlots,
+                           double *dPriority, const EvalDetail &det, int which, int smCount, cudaStream_t st);
+// CpuEngine::NextQuestionSpec (CpuEngine.cpp:337-415) after the evaluation: chunk run-lengths, grand totals,
+// weighted draw with dRandoms[n], nearest unasked question; writes dQuestions[n] and the quiz' active question.
+// dRunLength[n*Q] / dGrand[n*nChunks] optional outputs. setActive=0 leaves the quiz untouched.
+void launch_select_question(const DeviceKB &kb, const QuizPool &qp, int64_t n, const int64_t *dSlots,
+                            const double *dPriority, const uint64_t *dRandoms, int W, double *dRunLength,
+                            double *dGrand, int64_t *dQuestions, int setActive, cudaStream_t st);
+int64_t select_chunk_count(int64_t Q, int W);
+// CEListTopTargetsAlgorithm::RunHeapifyBased (CEListTopTargetsAlgorithm.cpp:30-97). dScratch: n*T 16-byte items.
+void launch_list_top_targets(const DeviceKB &kb, const QuizPool &qp, int64_t n, const int64_t *dSlots, int W,
+                             int64_t maxCount, void *dScratch, void *dDest, int64_t *dCounts, cudaStream_t st);
+
+// CETrainOperation (CETrainOperation.cpp:15-83) for a list of pre-paired operations, applied per (question,
+// target) cell group in sequence order. See TrainOp.
+struct TrainOp {
+  int64_t q0, a0, q1, a1;  // q1 = -1 for a single; (q0,a0)==(q1,a1) = the doubled step; q0==q1,a0!=a1 = the 3-add form
+  int64_t target;
+  double amount;
+};
+void launch_train_ops(const DeviceKB &kb, int64_t nOps, const TrainOp *dOps, const int64_t *dOrder,
+                      const int64_t *dGroupStart, int64_t nGroups, cudaStream_t st);
+void launch_add_vb(const DeviceKB &kb, int64_t n, const int64_t *dTargets, const double *dAmounts, cudaStream_t st);
+
+void launch_set_active(const QuizPool &qp, int64_t n, const int64_t *dSlots, const int64_t *dQuestions, cudaStream_t st);
+void launch_flush_l2(void *buf, size_t bytes, cudaStream_t st);
+
+uint64_t kernel_launch_count();
+
+} // namespace pqa
