@@ -68,8 +68,12 @@ PQACORE_API void *PqaB200_EvalQuestions(void *pvEngine, int64_t n, const int64_t
 /* Per-answer metrics of one quiz: pW/pH/pV [Q*K], pLack [Q] (CEEvalQsSubtaskConsider.cpp:88,129-132,201). */
 PQACORE_API void *PqaB200_EvalQuestionsDetailed(void *pvEngine, int64_t iQuiz, double *pW, double *pH, double *pV,
                                                 double *pLack, double *pPriorities);
-/* Selects which evaluation kernel the engine uses: 0 auto, 1 generic (direct loads), 2 staged (TMA + shared memory). */
+/* Selects which evaluation kernel the engine uses: 0 auto (= 2), 1 exact (every rounding of CpuEngine reproduced;
+ * bit-identical W/H/V/lack), 2 staged (TMA + shared memory throughput kernel, tolerance-level parity). */
 PQACORE_API void *PqaB200_SetEvalKernel(void *pvEngine, int32_t which);
+/* Same, plus tuning knobs of the staged kernel (tests force the chunked-targets path on small T with these):
+ * chunkTargets = targets staged per shared-memory chunk (0 auto), quizzesPerCta = quiz tile of one CTA (0 auto). */
+PQACORE_API void *PqaB200_SetEvalTuning(void *pvEngine, int32_t which, int64_t chunkTargets, int64_t quizzesPerCta);
 
 /* ---- device-resident stepping and timing (bench.py "value" leg: no host<->device traffic inside) ---- */
 /* Binds n quizzes as the resident batch: ids and one random draw per quiz are copied to the device once. */
@@ -78,6 +82,9 @@ PQACORE_API void *PqaB200_ResidentBind(void *pvEngine, int64_t n, const int64_t 
  * results stay on the device. */
 PQACORE_API void *PqaB200_ResidentStep(void *pvEngine);
 PQACORE_API void *PqaB200_ResidentFetch(void *pvEngine, int64_t *pQuestions /* n */);
+/* Device time (ms, CUDA events on the engine stream) of the question-evaluation kernel inside the most recent
+ * PqaB200_ResidentStep; waits for that kernel. -1 if no step was issued. */
+PQACORE_API double PqaB200_ResidentLastEvalMs(void *pvEngine);
 PQACORE_API void *PqaB200_Synchronize(void *pvEngine);
 PQACORE_API void *PqaB200_EventCreate(void);
 PQACORE_API void PqaB200_EventDestroy(void *pvEvent);

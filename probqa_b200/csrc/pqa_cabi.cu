@@ -1,0 +1,368 @@
+// probqa_b200: the extern "C" layer of libPqaCore.so. Every PqaCInterop.h symbol of the reference
+// (PqaCore/Interface/PqaCInterop.h:48-108, definitions in PqaCore/PqaCInterop.cpp) is exported with the same
+// signature and error convention; entry points outside the hot-path scope return a NotImplemented error object
+// (the reference's own convention for unimplemented engine features, e.g. CudaEngine.cpp:62-98).
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "../../include/PqaB200Ext.h"
+#include "pqa_engine.h"
+
+using namespace pqa;
+
+namespace {
+
+struct Factory { int unused; };
+Factory g_factory;
+
+inline Engine *E(void *pv) { return static_cast<Engine *>(pv); }
+
+PqaError *NullEngine() { return MakeError(ErrCode::NullArgument, "pvEngine is NULL"); }
+
+// ReturnPqaError (PqaCInterop.cpp:56-61): NULL on success, owned error otherwise.
+inline void *Ret(PqaError *e) { return e; }
+// AssignPqaError (PqaCInterop.cpp:45-54)
+inline void Assign(void **ppError, PqaError *e) {
+  if (ppError) *ppError = e;
+  else if (e) delete e;
+}
+
+template <typename F> PqaError *Guard(F &&f) {
+  try { return f(); }
+  catch (const CudaFail &cf) { return ErrCuda(cf.code, cf.what(), cf.file, cf.line); }
+  catch (const std::exception &ex) { return ErrStd(ex.what()); }
+  catch (...) { return MakeError(ErrCode::Internal, "unknown exception"); }
+}
+
+PqaError *CreateEngineImpl(const CiEngineDefinition *pEngDef, const CiB200Options *pOpts, Engine **out) {
+  *out = nullptr;
+  if (!pEngDef) return MakeError(ErrCode::NullArgument, "pEngDef is NULL");
+  // PqaEngineBaseFactory::CreateCpuEngine (PqaEngineBaseFactory.cpp:16-27): only Double precision;
+  // CheckDimensions (:113-122) with the minimums of PqaEngineBaseFactory.h:15-17.
+  if (pEngDef->_precType != 3)
+    return ErrNotImplemented("B200 engine on precision type other than double (precType must be 3).");
+  if (pEngDef->_nAnswers < 2 || pEngDef->_nQuestions < 1 || pEngDef->_nTargets < 2)
+    return ErrInsufficientDims(pEngDef->_nAnswers, pEngDef->_nQuestions, pEngDef->_nTargets);
+  CiB200Options opts;
+  if (pOpts) opts = *pOpts;
+  else { opts._device = -1; opts._emulatedWorkers = 0; opts._rngSeed = 0; opts._initialQuizCapacity = 0; }
+  return Guard([&]() -> PqaError * { *out = new Engine(*pEngDef, opts); return nullptr; });
+}
+
+} // namespace
+
+extern "C" {
+
+PQACORE_API void CiDebugBreak(void) {}
+
+PQACORE_API uint8_t Logger_Init(void **ppStrErr, const char *baseName) {
+  // the reference opens a file logger (PqaCInterop.cpp:145-172); this library logs to stderr only
+  (void)baseName;
+  if (ppStrErr) *ppStrErr = nullptr;
+  return 1;
+}
+PQACORE_API void CiReleaseString(void *pvString) { delete[] static_cast<char *>(pvString); }
+
+PQACORE_API void *CiGetPqaEngineFactory(void) { return &g_factory; }
+
+PQACORE_API void *PqaEngineFactory_CreateCpuEngine(void *pvFactory, void **ppError, const CiEngineDefinition *pEngDef) {
+  (void)pvFactory;
+  Engine *eng = nullptr;
+  Assign(ppError, CreateEngineImpl(pEngDef, nullptr, &eng));
+  return eng;
+}
+PQACORE_API void *PqaB200_CreateEngine(void **ppError, const CiEngineDefinition *pEngDef, const CiB200Options *pOpts) {
+  Engine *eng = nullptr;
+  Assign(ppError, CreateEngineImpl(pEngDef, pOpts, &eng));
+  return eng;
+}
+PQACORE_API void *PqaEngineFactory_LoadCpuEngine(void *pvFactory, void **ppError, const char *filePath,
+                                                 uint64_t memPoolMaxBytes) {
+  (void)pvFactory; (void)memPoolMaxBytes;
+  CiB200Options opts; opts._device = -1; opts._emulatedWorkers = 0; opts._rngSeed = 0; opts._initialQuizCapacity = 0;
+  PqaError *err = nullptr;
+  Engine *eng = nullptr;
+  PqaError *g = Guard([&]() -> PqaError * { eng = Engine::LoadKB(filePath, opts, &err); return nullptr; });
+  Assign(ppError, g ? g : err);
+  return eng;
+}
+
+PQACORE_API void CiReleasePqaError(void *pvErr) { delete static_cast<PqaError *>(pvErr); }
+PQACORE_API void *PqaError_ToString(void *pvError, const uint8_t withParams) {
+  const std::string s = pvError ? static_cast<PqaError *>(pvError)->ToString(withParams != 0) : std::string("Success");
+  char *out = new char[s.size() + 1];
+  std::memcpy(out, s.c_str(), s.size() + 1);
+  return out;
+}
+
+PQACORE_API void CiReleasePqaEngine(void *pvEngine) { delete E(pvEngine); }
+
+PQACORE_API void *PqaEngine_Train(void *pvEngine, int64_t nQuestions, const CiAnsweredQuestion *const pAQs,
+                                  const int64_t iTarget, const double amount) {
+  if (!pvEngine) return NullEngine();
+  return Ret(Guard([&] { return E(pvEngine)->Train(nQuestions, pAQs, iTarget, amount); }));
+}
+
+// Permanent <-> compact id maps: without maintenance (no removals, no compaction) the two id spaces coincide
+// (PermanentIdManager.cpp: GrowTo assigns perm = comp), so the maps are the identity on valid ids.
+static uint8_t IdentityIds(void *pvEngine, int64_t count, int64_t *pIds, int which) {
+  if (!pvEngine || (count > 0 && !pIds)) return 0;
+  const CiEngineDimensions d = E(pvEngine)->CopyDims();
+  const int64_t lim = which == 0 ? d._nQuestions : which == 1 ? d._nTargets : INT64_MAX;
+  for (int64_t i = 0; i < count; i++)
+    if (pIds[i] < 0 || pIds[i] >= lim) pIds[i] = -1;
+  return 1;
+}
+PQACORE_API uint8_t PqaEngine_QuestionPermFromComp(void *pvEngine, const int64_t count, int64_t *pIds) { return IdentityIds(pvEngine, count, pIds, 0); }
+PQACORE_API uint8_t PqaEngine_QuestionCompFromPerm(void *pvEngine, const int64_t count, int64_t *pIds) { return IdentityIds(pvEngine, count, pIds, 0); }
+PQACORE_API uint8_t PqaEngine_TargetPermFromComp(void *pvEngine, const int64_t count, int64_t *pIds) { return IdentityIds(pvEngine, count, pIds, 1); }
+PQACORE_API uint8_t PqaEngine_TargetCompFromPerm(void *pvEngine, const int64_t count, int64_t *pIds) { return IdentityIds(pvEngine, count, pIds, 1); }
+PQACORE_API uint8_t PqaEngine_QuizPermFromComp(void *pvEngine, const int64_t count, int64_t *pIds) { return IdentityIds(pvEngine, count, pIds, 2); }
+PQACORE_API uint8_t PqaEngine_QuizCompFromPerm(void *pvEngine, const int64_t count, int64_t *pIds) { return IdentityIds(pvEngine, count, pIds, 2); }
+PQACORE_API uint8_t PqaEngine_EnsurePermQuizGreater(void *pvEngine, const int64_t bound) { (void)bound; return pvEngine ? 1 : 0; }
+PQACORE_API uint8_t PqaEngine_RemapQuizPermId(void *pvEngine, const int64_t srcPermId, const int64_t destPermId) {
+  (void)pvEngine; return srcPermId == destPermId ? 1 : 0;
+}
+
+PQACORE_API uint64_t PqaEngine_GetTotalQuestionsAsked(void *pvEngine, void **ppError) {
+  if (!pvEngine) { Assign(ppError, NullEngine()); return 0; }
+  Assign(ppError, nullptr);
+  return E(pvEngine)->GetTotalQuestionsAsked();
+}
+PQACORE_API uint8_t PqaEngine_CopyDims(void *pvEngine, CiEngineDimensions *pDims) {
+  if (!pvEngine || !pDims) return 0;
+  *pDims = E(pvEngine)->CopyDims();
+  return 1;
+}
+PQACORE_API int64_t PqaEngine_StartQuiz(void *pvEngine, void **ppError) {
+  if (!pvEngine) { Assign(ppError, NullEngine()); return -1; }
+  PqaError *err = nullptr;
+  const int64_t id = E(pvEngine)->StartQuiz(&err);
+  Assign(ppError, err);
+  return id;
+}
+PQACORE_API int64_t PqaEngine_ResumeQuiz(void *pvEngine, void **ppError, const int64_t nAnswered,
+                                         const CiAnsweredQuestion *const pAQs) {
+  if (!pvEngine) { Assign(ppError, NullEngine()); return -1; }
+  PqaError *err = nullptr;
+  const int64_t id = E(pvEngine)->ResumeQuiz(&err, nAnswered, pAQs);
+  Assign(ppError, err);
+  return id;
+}
+PQACORE_API int64_t PqaEngine_NextQuestion(void *pvEngine, void **ppError, const int64_t iQuiz) {
+  if (!pvEngine) { Assign(ppError, NullEngine()); return -1; }
+  PqaError *err = nullptr;
+  const int64_t q = E(pvEngine)->NextQuestion(&err, iQuiz);
+  Assign(ppError, err);
+  return q;
+}
+PQACORE_API void *PqaEngine_RecordAnswer(void *pvEngine, const int64_t iQuiz, const int64_t iAnswer) {
+  if (!pvEngine) return NullEngine();
+  return Ret(E(pvEngine)->RecordAnswer(iQuiz, iAnswer));
+}
+PQACORE_API void *PqaEngine_ClearOldQuizzes(void *pvEngine, const int64_t maxCount, const double maxAgeSec) {
+  (void)maxCount; (void)maxAgeSec;
+  if (!pvEngine) return NullEngine();
+  return ErrNotImplemented("B200 engine: ClearOldQuizzes (BaseEngine.cpp) -- quiz ageing is outside the hot-path scope");
+}
+PQACORE_API int64_t PqaEngine_GetActiveQuestionId(void *pvEngine, void **ppError, const int64_t iQuiz) {
+  if (!pvEngine) { Assign(ppError, NullEngine()); return -1; }
+  PqaError *err = nullptr;
+  const int64_t q = E(pvEngine)->GetActiveQuestionId(&err, iQuiz);
+  Assign(ppError, err);
+  return q;
+}
+PQACORE_API void *PqaEngine_SetActiveQuestion(void *pvEngine, const int64_t iQuiz, const int64_t iQuestion) {
+  if (!pvEngine) return NullEngine();
+  return Ret(E(pvEngine)->SetActiveQuestion(iQuiz, iQuestion));
+}
+PQACORE_API int64_t PqaEngine_ListTopTargets(void *pvEngine, void **ppError, const int64_t iQuiz,
+                                             const int64_t maxCount, CiRatedTarget *pDest) {
+  if (!pvEngine) { Assign(ppError, NullEngine()); return -1; }
+  PqaError *err = nullptr;
+  const int64_t n = E(pvEngine)->ListTopTargets(&err, iQuiz, maxCount, pDest);
+  Assign(ppError, err);
+  return n;
+}
+PQACORE_API void *PqaEngine_RecordQuizTarget(void *pvEngine, const int64_t iQuiz, const int64_t iTarget,
+                                             const double amount) {
+  if (!pvEngine) return NullEngine();
+  return Ret(E(pvEngine)->RecordQuizTarget(iQuiz, iTarget, amount));
+}
+PQACORE_API void *PqaEngine_ReleaseQuiz(void *pvEngine, const int64_t iQuiz) {
+  if (!pvEngine) return NullEngine();
+  return Ret(E(pvEngine)->ReleaseQuiz(iQuiz));
+}
+PQACORE_API void *PqaEngine_SaveKB(void *pvEngine, const char *const filePath, const uint8_t bDoubleBuffer) {
+  (void)bDoubleBuffer;
+  if (!pvEngine) return NullEngine();
+  return Ret(Guard([&] { return E(pvEngine)->SaveKB(filePath); }));
+}
+
+static PqaError *MaintenanceNotImplemented(const char *what) {
+  return ErrNotImplemented(std::string("B200 engine: ") + what +
+                           " -- maintenance mode (KB resize / removal / compaction) is outside the hot-path scope");
+}
+PQACORE_API void *PqaEngine_StartMaintenance(void *pvEngine, const bool forceQuizzes) {
+  (void)forceQuizzes;
+  return pvEngine ? MaintenanceNotImplemented("StartMaintenance") : NullEngine();
+}
+PQACORE_API void *PqaEngine_FinishMaintenance(void *pvEngine) {
+  return pvEngine ? MaintenanceNotImplemented("FinishMaintenance") : NullEngine();
+}
+PQACORE_API void *PqaEngine_AddQsTs(void *pvEngine, const int64_t, CiAddQorTParam *, const int64_t, CiAddQorTParam *) {
+  return pvEngine ? MaintenanceNotImplemented("AddQsTs") : NullEngine();
+}
+PQACORE_API void *PqaEngine_RemoveQuestions(void *pvEngine, const int64_t, const int64_t *) {
+  return pvEngine ? MaintenanceNotImplemented("RemoveQuestions") : NullEngine();
+}
+PQACORE_API void *PqaEngine_RemoveTargets(void *pvEngine, const int64_t, const int64_t *) {
+  return pvEngine ? MaintenanceNotImplemented("RemoveTargets") : NullEngine();
+}
+PQACORE_API void *PqaEngine_Compact(void *pvEngine, int64_t *pnQuestions, int64_t const **const ppOldQuestions,
+                                    int64_t *pnTargets, int64_t const **const ppOldTargets) {
+  if (pnQuestions) *pnQuestions = 0;
+  if (pnTargets) *pnTargets = 0;
+  if (ppOldQuestions) *ppOldQuestions = nullptr;
+  if (ppOldTargets) *ppOldTargets = nullptr;
+  return pvEngine ? MaintenanceNotImplemented("Compact") : NullEngine();
+}
+PQACORE_API void CiReleaseCompaction(const int64_t *p) { delete[] p; }
+PQACORE_API void *PqaEngine_Shutdown(void *pvEngine, const char *const saveFilePath) {
+  if (!pvEngine) return NullEngine();
+  if (saveFilePath && *saveFilePath) return Ret(Guard([&] { return E(pvEngine)->SaveKB(saveFilePath); }));
+  return Ret(E(pvEngine)->Synchronize());
+}
+PQACORE_API void *PqaEngine_SetLogger(void *pvEngine, void *pSRLogger) {
+  (void)pSRLogger;
+  return pvEngine ? nullptr : NullEngine();
+}
+
+// ------------------------------------------------------------------ PqaB200Ext.h
+PQACORE_API int32_t PqaB200_GetEmulatedWorkers(void *pvEngine) { return pvEngine ? E(pvEngine)->emulatedWorkers() : -1; }
+PQACORE_API int32_t PqaB200_GetDevice(void *pvEngine) { return pvEngine ? E(pvEngine)->device() : -1; }
+PQACORE_API const char *PqaB200_BuildInfo(void) {
+  return "probqa_b200 libPqaCore: sm_100a, fp64, -fmad=false, built " __DATE__ " " __TIME__;
+}
+PQACORE_API void *PqaEngine_CopyATargets(void *pvEngine, int64_t iQuestion, int64_t iAnswer, int64_t maxTargets, double *pFreqs) {
+  if (!pvEngine) return NullEngine();
+  return Ret(E(pvEngine)->CopyATargets(iQuestion, iAnswer, maxTargets, pFreqs));
+}
+PQACORE_API void *PqaEngine_CopyDTargets(void *pvEngine, int64_t iQuestion, int64_t maxTargets, double *pFreqs) {
+  if (!pvEngine) return NullEngine();
+  return Ret(E(pvEngine)->CopyDTargets(iQuestion, maxTargets, pFreqs));
+}
+PQACORE_API void *PqaEngine_CopyBTargets(void *pvEngine, int64_t maxTargets, double *pFreqs) {
+  if (!pvEngine) return NullEngine();
+  return Ret(E(pvEngine)->CopyBTargets(maxTargets, pFreqs));
+}
+PQACORE_API void *PqaB200_UploadKB(void *pvEngine, const double *sA, const double *mD, const double *vB) {
+  if (!pvEngine) return NullEngine();
+  return Ret(E(pvEngine)->UploadKB(sA, mD, vB));
+}
+PQACORE_API void *PqaB200_DownloadKB(void *pvEngine, double *sA, double *mD, double *vB) {
+  if (!pvEngine) return NullEngine();
+  return Ret(E(pvEngine)->DownloadKB(sA, mD, vB));
+}
+PQACORE_API void *PqaEngine_StartQuizBatch(void *pvEngine, int64_t n, int64_t *pQuizIds) {
+  if (!pvEngine) return NullEngine();
+  return Ret(E(pvEngine)->StartQuizBatch(n, pQuizIds));
+}
+PQACORE_API void *PqaEngine_NextQuestionBatch(void *pvEngine, int64_t n, const int64_t *pQuizIds,
+                                              const uint64_t *pRandoms, int64_t *pQuestions, void **ppErrors) {
+  if (!pvEngine) return NullEngine();
+  return Ret(E(pvEngine)->NextQuestionBatch(n, pQuizIds, pRandoms, pQuestions, ppErrors));
+}
+PQACORE_API void *PqaEngine_RecordAnswerBatch(void *pvEngine, int64_t n, const int64_t *pQuizIds, const int64_t *pAnswers) {
+  if (!pvEngine) return NullEngine();
+  return Ret(E(pvEngine)->RecordAnswerBatch(n, pQuizIds, pAnswers));
+}
+PQACORE_API void *PqaEngine_SetActiveQuestionBatch(void *pvEngine, int64_t n, const int64_t *pQuizIds, const int64_t *pQuestions) {
+  if (!pvEngine) return NullEngine();
+  return Ret(E(pvEngine)->SetActiveQuestionBatch(n, pQuizIds, pQuestions));
+}
+PQACORE_API void *PqaEngine_ListTopTargetsBatch(void *pvEngine, int64_t n, const int64_t *pQuizIds, int64_t maxCount,
+                                                CiRatedTarget *pDest, int64_t *pCounts) {
+  if (!pvEngine) return NullEngine();
+  return Ret(E(pvEngine)->ListTopTargetsBatch(n, pQuizIds, maxCount, pDest, pCounts));
+}
+PQACORE_API void *PqaEngine_RecordQuizTargetBatch(void *pvEngine, int64_t n, const int64_t *pQuizIds,
+                                                  const int64_t *pTargets, const double *pAmounts) {
+  if (!pvEngine) return NullEngine();
+  return Ret(Guard([&] { return E(pvEngine)->RecordQuizTargetBatch(n, pQuizIds, pTargets, pAmounts); }));
+}
+PQACORE_API void *PqaEngine_ReleaseQuizBatch(void *pvEngine, int64_t n, const int64_t *pQuizIds) {
+  if (!pvEngine) return NullEngine();
+  return Ret(E(pvEngine)->ReleaseQuizBatch(n, pQuizIds));
+}
+PQACORE_API void *PqaB200_CopyQuizPriors(void *pvEngine, int64_t iQuiz, double *pPriors) {
+  if (!pvEngine) return NullEngine();
+  return Ret(E(pvEngine)->CopyQuizPriors(iQuiz, pPriors));
+}
+PQACORE_API void *PqaB200_SetQuizPriors(void *pvEngine, int64_t iQuiz, const double *pPriors) {
+  if (!pvEngine) return NullEngine();
+  return Ret(E(pvEngine)->SetQuizPriors(iQuiz, pPriors));
+}
+PQACORE_API void *PqaB200_EvalQuestions(void *pvEngine, int64_t n, const int64_t *pQuizIds, double *pPriorities,
+                                        double *pRunLength, double *pGrandTotals, int64_t *pnChunks) {
+  if (!pvEngine) return NullEngine();
+  return Ret(E(pvEngine)->EvalQuestions(n, pQuizIds, pPriorities, pRunLength, pGrandTotals, pnChunks));
+}
+PQACORE_API void *PqaB200_EvalQuestionsDetailed(void *pvEngine, int64_t iQuiz, double *pW, double *pH, double *pV,
+                                                double *pLack, double *pPriorities) {
+  if (!pvEngine) return NullEngine();
+  return Ret(E(pvEngine)->EvalQuestionsDetailed(iQuiz, pW, pH, pV, pLack, pPriorities));
+}
+PQACORE_API void *PqaB200_SetEvalKernel(void *pvEngine, int32_t which) {
+  if (!pvEngine) return NullEngine();
+  return Ret(E(pvEngine)->SetEvalKernel(which, 0, 0));
+}
+PQACORE_API void *PqaB200_SetEvalTuning(void *pvEngine, int32_t which, int64_t chunkTargets, int64_t quizzesPerCta) {
+  if (!pvEngine) return NullEngine();
+  return Ret(E(pvEngine)->SetEvalKernel(which, chunkTargets, quizzesPerCta));
+}
+PQACORE_API void *PqaB200_ResidentBind(void *pvEngine, int64_t n, const int64_t *pQuizIds, const uint64_t *pRandoms) {
+  if (!pvEngine) return NullEngine();
+  return Ret(E(pvEngine)->ResidentBind(n, pQuizIds, pRandoms));
+}
+PQACORE_API void *PqaB200_ResidentStep(void *pvEngine) {
+  if (!pvEngine) return NullEngine();
+  return Ret(E(pvEngine)->ResidentStep());
+}
+PQACORE_API void *PqaB200_ResidentFetch(void *pvEngine, int64_t *pQuestions) {
+  if (!pvEngine) return NullEngine();
+  return Ret(E(pvEngine)->ResidentFetch(pQuestions));
+}
+PQACORE_API double PqaB200_ResidentLastEvalMs(void *pvEngine) { return pvEngine ? E(pvEngine)->ResidentLastEvalMs() : -1.0; }
+PQACORE_API void *PqaB200_Synchronize(void *pvEngine) {
+  if (!pvEngine) return NullEngine();
+  return Ret(E(pvEngine)->Synchronize());
+}
+PQACORE_API void *PqaB200_EventCreate(void) {
+  cudaEvent_t ev = nullptr;
+  if (cudaEventCreate(&ev) != cudaSuccess) return nullptr;
+  return ev;
+}
+PQACORE_API void PqaB200_EventDestroy(void *pvEvent) { if (pvEvent) cudaEventDestroy((cudaEvent_t)pvEvent); }
+PQACORE_API void *PqaB200_EventRecord(void *pvEngine, void *pvEvent) {
+  if (!pvEngine) return NullEngine();
+  const cudaError_t e = cudaEventRecord((cudaEvent_t)pvEvent, E(pvEngine)->stream());
+  return e == cudaSuccess ? nullptr : ErrCuda((int)e, "cudaEventRecord", __FILE__, __LINE__);
+}
+PQACORE_API void *PqaB200_EventSynchronize(void *pvEvent) {
+  const cudaError_t e = cudaEventSynchronize((cudaEvent_t)pvEvent);
+  return e == cudaSuccess ? nullptr : ErrCuda((int)e, "cudaEventSynchronize", __FILE__, __LINE__);
+}
+PQACORE_API double PqaB200_EventElapsedMs(void *pvStart, void *pvStop) {
+  float ms = -1.f;
+  if (cudaEventElapsedTime(&ms, (cudaEvent_t)pvStart, (cudaEvent_t)pvStop) != cudaSuccess) return -1.0;
+  return (double)ms;
+}
+PQACORE_API uint64_t PqaB200_KernelLaunchCount(void *pvEngine) { (void)pvEngine; return kernel_launch_count(); }
+PQACORE_API void *PqaB200_FlushL2(void *pvEngine) {
+  if (!pvEngine) return NullEngine();
+  return Ret(E(pvEngine)->FlushL2());
+}
+
+} // extern "C"

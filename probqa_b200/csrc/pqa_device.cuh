@@ -36,22 +36,32 @@ __device__ __forceinline__ double precise_sum4(const double s0, const double s1,
 }
 
 // Four Kahan lanes held by the four threads of a lane group (lane l = threadIdx & 3 owns element j with j%4==l).
-// Gathers the group's lanes with shuffles; every thread of the group returns the same bits.
+// Gathers the group's lanes with shuffles; every thread of the group returns the same bits. Only the four threads
+// of the group need to be converged (the mask names exactly them).
 __device__ __forceinline__ double group_precise_sum(const Kahan &k) {
-  const unsigned full = 0xffffffffu;
-  const double s0 = __shfl_sync(full, k.s, 0, 4), s1 = __shfl_sync(full, k.s, 1, 4);
-  const double s2 = __shfl_sync(full, k.s, 2, 4), s3 = __shfl_sync(full, k.s, 3, 4);
-  const double c0 = __shfl_sync(full, k.c, 0, 4), c1 = __shfl_sync(full, k.c, 1, 4);
-  const double c2 = __shfl_sync(full, k.c, 2, 4), c3 = __shfl_sync(full, k.c, 3, 4);
+  const unsigned mask = 0xFu << (threadIdx.x & 28u);
+  const double s0 = __shfl_sync(mask, k.s, 0, 4), s1 = __shfl_sync(mask, k.s, 1, 4);
+  const double s2 = __shfl_sync(mask, k.s, 2, 4), s3 = __shfl_sync(mask, k.s, 3, 4);
+  const double c0 = __shfl_sync(mask, k.c, 0, 4), c1 = __shfl_sync(mask, k.c, 1, 4);
+  const double c2 = __shfl_sync(mask, k.c, 2, 4), c3 = __shfl_sync(mask, k.c, 3, 4);
   return precise_sum4(s0, s1, s2, s3, c0, c1, c2, c3);
 }
 
-// Plain (tolerance-level) sum over the four lanes of a group: (l0 + l1) + (l2 + l3).
-__device__ __forceinline__ double group_tree_sum(double v) {
-  const unsigned full = 0xffffffffu;
-  v = __dadd_rn(v, __shfl_xor_sync(full, v, 1, 4));
-  v = __dadd_rn(v, __shfl_xor_sync(full, v, 2, 4));
+// Butterfly sum over the 32 lanes of a warp; every lane returns the total.
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = __dadd_rn(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
+}
+
+// 1/x to ~1 ulp for normal x: MUFU.RCP64H seed (2^-23 relative) + one cubically convergent step (3 DFMA).
+// Not IEEE-rounded; used only by the tolerance-level kernel.
+__device__ __forceinline__ double fast_rcp(const double x) {
+  double y0;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(x));
+  const double e = __fma_rn(-x, y0, 1.0);
+  const double e2 = __fma_rn(e, e, e);
+  return __fma_rn(y0, e2, y0);
 }
 
 // ---------------------------------------------------------------------------------------------------------

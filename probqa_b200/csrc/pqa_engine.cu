@@ -1,0 +1,782 @@
+// probqa_b200: host side of the B200 engine (see pqa_engine.h). Citations are relative to /root/reference/ProbQA/.
+#include "pqa_engine.h"
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <numeric>
+#include <random>
+#include <thread>
+
+namespace pqa {
+
+#define SRC_LINE_STR2(x) #x
+#define SRC_LINE_STR(x) SRC_LINE_STR2(x)
+#define PQA_FILE_LINE "pqa_engine.cu(" SRC_LINE_STR(__LINE__) "): "
+
+template <typename T> void DevBuf<T>::ensure(size_t n, cudaStream_t st, bool keep) {
+  if (n <= n_) return;
+  size_t cap = std::max(n, n_ * 2);
+  T *p = nullptr;
+  PQA_CU(cudaMalloc(&p, cap * sizeof(T)));
+  if (p_) {
+    if (keep) PQA_CU(cudaMemcpyAsync(p, p_, n_ * sizeof(T), cudaMemcpyDeviceToDevice, st));
+    PQA_CU(cudaStreamSynchronize(st));
+    cudaFree(p_);
+  }
+  p_ = p; n_ = cap;
+}
+template <typename T> void PinBuf<T>::ensure(size_t n) {
+  if (n <= n_) return;
+  size_t cap = std::max(n, n_ * 2);
+  T *p = nullptr;
+  PQA_CU(cudaMallocHost(&p, cap * sizeof(T)));
+  if (p_) { std::memcpy(p, p_, n_ * sizeof(T)); cudaFreeHost(p_); }
+  p_ = p; n_ = cap;
+}
+
+static int env_int(const char *name, int dflt) {
+  const char *v = std::getenv(name);
+  return (v && *v) ? std::atoi(v) : dflt;
+}
+
+// The 1024-entry Log2Hot table of SRPlatform/SRVectMath.cpp:30-44: log2 of each bucket's mid-point, entry 0 scaled
+// so that Log2Hot(1) <= 0. std::log2 here is the same libm call the reference makes at start-up.
+static void build_log2_table(double *tbl) {
+  for (uint32_t i = 0; i < 1024; i++) {
+    const uint64_t bitsMid = 0x3FF0000000000000ull | ((uint64_t)i << 42) | (1ull << 41);
+    double mid;
+    std::memcpy(&mid, &bitsMid, 8);
+    tbl[i] = std::log2(mid);
+  }
+  tbl[0] *= 9.9999999999999927e-01;
+}
+
+Engine::Engine(const CiEngineDefinition &def, const CiB200Options &opts) {
+  Q_ = def._nQuestions; K_ = def._nAnswers; T_ = def._nTargets;
+  Tp_ = (T_ + 3) & ~3ll;
+  askedWords_ = (Q_ + 63) >> 6;
+  initAmount_ = def._initAmount;
+  int nDev = 0;
+  PQA_CU(cudaGetDeviceCount(&nDev));
+  if (nDev <= 0) throw std::runtime_error("probqa_b200: no CUDA device is visible; this engine has no CPU path");
+  device_ = opts._device;
+  if (device_ < 0) device_ = env_int("PQA_B200_DEVICE", -1);
+  if (device_ < 0) PQA_CU(cudaGetDevice(&device_));
+  PQA_CU(cudaSetDevice(device_));
+  cudaDeviceProp prop;
+  PQA_CU(cudaGetDeviceProperties(&prop, device_));
+  if (prop.major < 10)
+    throw std::runtime_error("probqa_b200: device compute capability " + std::to_string(prop.major) + "." +
+                             std::to_string(prop.minor) + " < 10.0; the kernels are built for sm_100a only");
+  smCount_ = prop.multiProcessorCount;
+  evalCfg_.smCount = smCount_;
+  W_ = opts._emulatedWorkers;
+  if (W_ <= 0) W_ = env_int("PQA_B200_EMULATED_WORKERS", 0);
+  if (W_ <= 0) W_ = (int)std::thread::hardware_concurrency();  // BaseCpuEngine.cpp:21-22
+  if (W_ <= 0) W_ = 1;
+  uint64_t seed = opts._rngSeed;
+  if (seed == 0) { std::random_device rd; seed = ((uint64_t)rd() << 32) ^ rd(); }
+  rng_[0] = seed * 0x9E3779B97F4A7C15ull + 0xD1B54A32D192ED03ull;
+  rng_[1] = (seed ^ 0xBF58476D1CE4E5B9ull) * 0x94D049BB133111EBull + 1;
+  if (!rng_[0] && !rng_[1]) rng_[1] = 1;
+
+  PQA_CU(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+  PQA_CU(cudaMalloc(&dSA_, sizeof(double) * (size_t)(Q_ * K_ * Tp_)));
+  PQA_CU(cudaMalloc(&dMD_, sizeof(double) * (size_t)(Q_ * Tp_)));
+  PQA_CU(cudaMalloc(&dVB_, sizeof(double) * (size_t)Tp_));
+  PQA_CU(cudaMalloc(&dLog2Tbl_, sizeof(double) * 1024));
+  double tbl[1024];
+  build_log2_table(tbl);
+  PQA_CU(cudaMemcpyAsync(dLog2Tbl_, tbl, sizeof(tbl), cudaMemcpyHostToDevice, stream_));
+  // CpuEngine.cpp:44-45,53,66,71,83: sA = init^2, mD = K*init^2, vB = init
+  const double initSqr = initAmount_ * initAmount_;
+  launch_fill_kb(kb(), initSqr, initSqr * (double)K_, initAmount_, stream_);
+  EnsureQuizCapacity(opts._initialQuizCapacity > 0 ? opts._initialQuizCapacity : 256);
+  PQA_CU(cudaStreamSynchronize(stream_));
+}
+
+Engine::~Engine() {
+  if (stream_) cudaStreamSynchronize(stream_);
+  cudaFree(dSA_); cudaFree(dMD_); cudaFree(dVB_); cudaFree(dLog2Tbl_);
+  cudaFree(dPriors_); cudaFree(dLogPriors_); cudaFree(dAsked_); cudaFree(dActive_);
+  if (flushBuf_) cudaFree(flushBuf_);
+  if (evEvalStart_) { cudaEventDestroy(evEvalStart_); cudaEventDestroy(evEvalStop_); }
+  if (stream_) cudaStreamDestroy(stream_);
+}
+
+DeviceKB Engine::kb() const {
+  DeviceKB k;
+  k.sA = dSA_; k.mD = dMD_; k.vB = dVB_; k.log2tbl = dLog2Tbl_;
+  k.tgaps = nullptr; k.qgaps = nullptr;   // maintenance (RemoveQuestions/RemoveTargets) is out of scope: no gaps
+  k.Q = Q_; k.K = K_; k.T = T_; k.Tp = Tp_;
+  k.nValidTargets = T_;                    // CpuEngine.cpp:351 with no target gaps
+  return k;
+}
+QuizPool Engine::pool() const {
+  QuizPool p;
+  p.priors = dPriors_; p.logPriors = dLogPriors_; p.asked = dAsked_; p.active = dActive_;
+  p.askedWords = askedWords_; p.Tp = Tp_;
+  return p;
+}
+
+void Engine::EnsureQuizCapacity(int64_t nSlots) {
+  if (nSlots <= quizCap_) return;
+  const int64_t cap = std::max<int64_t>(nSlots, quizCap_ * 2);
+  double *np = nullptr, *nl = nullptr; uint64_t *na = nullptr; int64_t *nact = nullptr;
+  PQA_CU(cudaMalloc(&np, sizeof(double) * (size_t)(cap * Tp_)));
+  PQA_CU(cudaMalloc(&nl, sizeof(double) * (size_t)(cap * Tp_)));
+  PQA_CU(cudaMalloc(&na, sizeof(uint64_t) * (size_t)(cap * askedWords_)));
+  PQA_CU(cudaMalloc(&nact, sizeof(int64_t) * (size_t)cap));
+  if (quizCap_ > 0) {
+    PQA_CU(cudaMemcpyAsync(np, dPriors_, sizeof(double) * (size_t)(quizCap_ * Tp_), cudaMemcpyDeviceToDevice, stream_));
+    PQA_CU(cudaMemcpyAsync(nl, dLogPriors_, sizeof(double) * (size_t)(quizCap_ * Tp_), cudaMemcpyDeviceToDevice, stream_));
+    PQA_CU(cudaMemcpyAsync(na, dAsked_, sizeof(uint64_t) * (size_t)(quizCap_ * askedWords_), cudaMemcpyDeviceToDevice, stream_));
+    PQA_CU(cudaMemcpyAsync(nact, dActive_, sizeof(int64_t) * (size_t)quizCap_, cudaMemcpyDeviceToDevice, stream_));
+    PQA_CU(cudaStreamSynchronize(stream_));
+    cudaFree(dPriors_); cudaFree(dLogPriors_); cudaFree(dAsked_); cudaFree(dActive_);
+  }
+  dPriors_ = np; dLogPriors_ = nl; dAsked_ = na; dActive_ = nact;
+  quizCap_ = cap;
+}
+
+uint64_t Engine::NextRandom() {  // xorshift128+, the generator family of SRFastRandom (SRFastRandom.h:31-42)
+  uint64_t s1 = rng_[0];
+  const uint64_t s0 = rng_[1];
+  rng_[0] = s0;
+  s1 ^= s1 << 23;
+  rng_[1] = s1 ^ s0 ^ (s1 >> 18) ^ (s0 >> 5);
+  return rng_[1] + s0;
+}
+
+PqaError *Engine::CheckQuiz(int64_t iQuiz) const {
+  const int64_t nQuizzes = (int64_t)quizzes_.size();
+  if (iQuiz < 0 || iQuiz >= nQuizzes)
+    return ErrIndexOutOfRange(iQuiz, 0, nQuizzes - 1, PQA_FILE_LINE "Quiz index is not in quiz registry range.");
+  if (!quizzes_[iQuiz].present)
+    return ErrAbsentId(iQuiz, PQA_FILE_LINE "Quiz index is not in the registry (but rather at a gap).");
+  return nullptr;
+}
+
+int64_t Engine::AssignQuizId() {
+  int64_t id;
+  if (!quizGaps_.empty()) { id = quizGaps_.back(); quizGaps_.pop_back(); }
+  else { id = (int64_t)quizzes_.size(); quizzes_.emplace_back(); }
+  HostQuiz &q = quizzes_[id];
+  q.present = true; q.activeQuestion = -1; q.answers.clear();
+  return id;
+}
+
+void Engine::UploadIds(int64_t n, const int64_t *ids) {
+  hIds_.ensure(n); dIds_.ensure(n, stream_);
+  std::memcpy(hIds_.get(), ids, sizeof(int64_t) * (size_t)n);
+  PQA_CU(cudaMemcpyAsync(dIds_.get(), hIds_.get(), sizeof(int64_t) * (size_t)n, cudaMemcpyHostToDevice, stream_));
+}
+
+#define PQA_TRY try {
+#define PQA_CATCH_RETURN_ERR                                                              \
+  } catch (const CudaFail &cf) { return ErrCuda(cf.code, cf.what(), cf.file, cf.line);    \
+  } catch (const std::exception &ex) { return ErrStd(ex.what()); }
+#define PQA_CATCH_SET_ERR(ret)                                                            \
+  } catch (const CudaFail &cf) { *err = ErrCuda(cf.code, cf.what(), cf.file, cf.line); return ret; \
+  } catch (const std::exception &ex) { *err = ErrStd(ex.what()); return ret; }
+
+// ---------------------------------------------------------------------------------------------------------
+// StartQuiz: CpuEngine::StartQuiz -> CreateQuizInternal -> CECreateQuizStart::UpdateLikelihoods
+// (CpuEngine.cpp:185-275, CECreateQuizOperation.cpp:22-53)
+PqaError *Engine::StartQuizBatch(int64_t n, int64_t *pQuizIds) {
+  if (n < 0) return ErrNegativeCount(n, PQA_FILE_LINE "|n| must be non-negative.");
+  if (n == 0) return nullptr;
+  if (!pQuizIds) return MakeError(ErrCode::NullArgument, PQA_FILE_LINE "pQuizIds");
+  std::lock_guard<std::mutex> lk(mu_);
+  PQA_TRY
+  for (int64_t x = 0; x < n; x++) pQuizIds[x] = AssignQuizId();
+  EnsureQuizCapacity((int64_t)quizzes_.size());
+  UploadIds(n, pQuizIds);
+  launch_start_quiz(kb(), pool(), n, dIds_.get(), W_, stream_);
+  PQA_CU(cudaStreamSynchronize(stream_));
+  return nullptr;
+  PQA_CATCH_RETURN_ERR
+}
+
+int64_t Engine::StartQuiz(PqaError **err) {
+  int64_t id = -1;
+  *err = StartQuizBatch(1, &id);
+  return *err ? -1 : id;
+}
+
+int64_t Engine::ResumeQuiz(PqaError **err, int64_t, const CiAnsweredQuestion *) {
+  *err = ErrNotImplemented("B200 engine: ResumeQuiz (CpuEngine.cpp:277-282) is outside the first hot-path scope");
+  return -1;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// NextQuestion: BaseEngine::NextQuestion (BaseEngine.cpp:421-437) -> CpuEngine::NextQuestionSpec (CpuEngine.cpp:337-415)
+PqaError *Engine::NextQuestionBatch(int64_t n, const int64_t *pQuizIds, const uint64_t *pRandoms, int64_t *pQuestions,
+                                    void **ppErrors) {
+  if (n < 0) return ErrNegativeCount(n, PQA_FILE_LINE "|n| must be non-negative.");
+  if (n == 0) return nullptr;
+  if (!pQuizIds || !pQuestions) return MakeError(ErrCode::NullArgument, PQA_FILE_LINE "pQuizIds/pQuestions");
+  std::lock_guard<std::mutex> lk(mu_);
+  PQA_TRY
+  // validate; quizzes that fail validation get their own error and are left out of the launch
+  std::vector<int64_t> valid; valid.reserve(n);
+  std::vector<int64_t> where; where.reserve(n);
+  PqaError *firstErr = nullptr;
+  for (int64_t x = 0; x < n; x++) {
+    pQuestions[x] = -1;
+    if (ppErrors) ppErrors[x] = nullptr;
+    PqaError *e = CheckQuiz(pQuizIds[x]);
+    if (e) {
+      if (ppErrors) ppErrors[x] = e;
+      else if (!firstErr) firstErr = e;
+      else delete e;
+      continue;
+    }
+    valid.push_back(pQuizIds[x]); where.push_back(x);
+  }
+  const int64_t m = (int64_t)valid.size();
+  if (m > 0) {
+    UploadIds(m, valid.data());
+    hRandoms_.ensure(m); dRandoms_.ensure(m, stream_);
+    for (int64_t x = 0; x < m; x++) hRandoms_.get()[x] = pRandoms ? pRandoms[where[x]] : NextRandom();
+    PQA_CU(cudaMemcpyAsync(dRandoms_.get(), hRandoms_.get(), sizeof(uint64_t) * (size_t)m, cudaMemcpyHostToDevice, stream_));
+    dPriority_.ensure((size_t)(m * Q_), stream_); dRunLength_.ensure((size_t)(m * Q_), stream_);
+    dQuestions_.ensure(m, stream_); hQuestions_.ensure(m);
+    EvalDetail det{nullptr, nullptr, nullptr, nullptr};
+    launch_eval_questions(kb(), pool(), m, dIds_.get(), dPriority_.get(), det, evalCfg_, stream_);
+    launch_select_question(kb(), pool(), m, dIds_.get(), dPriority_.get(), dRandoms_.get(), W_, dRunLength_.get(),
+                           nullptr, dQuestions_.get(), 1, stream_);
+    PQA_CU(cudaMemcpyAsync(hQuestions_.get(), dQuestions_.get(), sizeof(int64_t) * (size_t)m, cudaMemcpyDeviceToHost, stream_));
+    PQA_CU(cudaStreamSynchronize(stream_));
+    uint64_t nAsked = 0;
+    for (int64_t x = 0; x < m; x++) {
+      const int64_t qst = hQuestions_.get()[x];
+      if (qst < 0) {  // CpuEngine.cpp:407-411
+        PqaError *e = MakeError(ErrCode::QuestionsExhausted, PQA_FILE_LINE "Found no unasked question that is not in a gap.");
+        if (ppErrors) ppErrors[where[x]] = e;
+        else if (!firstErr) firstErr = e;
+        else delete e;
+        continue;
+      }
+      pQuestions[where[x]] = qst;
+      quizzes_[valid[x]].activeQuestion = qst;  // :412
+      nAsked++;                                  // :413
+    }
+    nQuestionsAsked_.fetch_add(nAsked, std::memory_order_relaxed);
+  }
+  return firstErr;
+  PQA_CATCH_RETURN_ERR
+}
+
+int64_t Engine::NextQuestion(PqaError **err, int64_t iQuiz) {
+  int64_t q = -1;
+  *err = NextQuestionBatch(1, &iQuiz, nullptr, &q, nullptr);
+  return *err ? -1 : q;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// RecordAnswer: BaseEngine::RecordAnswer (BaseEngine.cpp:439-464) -> CEQuiz::RecordAnswer (CEQuiz.h:77-122)
+PqaError *Engine::RecordAnswerBatch(int64_t n, const int64_t *pQuizIds, const int64_t *pAnswers) {
+  if (n < 0) return ErrNegativeCount(n, PQA_FILE_LINE "|n| must be non-negative.");
+  if (n == 0) return nullptr;
+  if (!pQuizIds || !pAnswers) return MakeError(ErrCode::NullArgument, PQA_FILE_LINE "pQuizIds/pAnswers");
+  std::lock_guard<std::mutex> lk(mu_);
+  PQA_TRY
+  for (int64_t x = 0; x < n; x++) {  // validate everything before touching any quiz
+    if (pAnswers[x] < 0 || pAnswers[x] >= K_)
+      return ErrIndexOutOfRange(pAnswers[x], 0, K_ - 1, "Answer index is not in the answer range.");
+    if (PqaError *e = CheckQuiz(pQuizIds[x])) return e;
+    const HostQuiz &q = quizzes_[pQuizIds[x]];
+    if (q.activeQuestion == -1)
+      return ErrNoQuizActiveQuestion(pAnswers[x], PQA_FILE_LINE "An attempt to record an answer in a quiz that doesn't"
+                                                  " have an active question");
+    if (q.activeQuestion < 0 || q.activeQuestion >= Q_)
+      return ErrNoQuizActiveQuestion(pAnswers[x], PQA_FILE_LINE "An attempt to record an answer in a quiz that has"
+                                                  " invalid active question");
+  }
+  UploadIds(n, pQuizIds);
+  hAnswers_.ensure(n); dAnswers_.ensure(n, stream_);
+  std::memcpy(hAnswers_.get(), pAnswers, sizeof(int64_t) * (size_t)n);
+  PQA_CU(cudaMemcpyAsync(dAnswers_.get(), hAnswers_.get(), sizeof(int64_t) * (size_t)n, cudaMemcpyHostToDevice, stream_));
+  const int looseW = std::max(1, W_ - 1);  // CpuEngine GetNLooseWorkers, CEQuiz.h:98
+  launch_record_answer(kb(), pool(), n, dIds_.get(), dAnswers_.get(), looseW, stream_);
+  for (int64_t x = 0; x < n; x++) {
+    HostQuiz &q = quizzes_[pQuizIds[x]];
+    q.answers.push_back(CiAnsweredQuestion{q.activeQuestion, pAnswers[x]});  // CEQuiz.h:90
+    q.activeQuestion = -1;                                                     // :92
+  }
+  PQA_CU(cudaStreamSynchronize(stream_));
+  return nullptr;
+  PQA_CATCH_RETURN_ERR
+}
+
+PqaError *Engine::RecordAnswer(int64_t iQuiz, int64_t iAnswer) { return RecordAnswerBatch(1, &iQuiz, &iAnswer); }
+
+int64_t Engine::GetActiveQuestionId(PqaError **err, int64_t iQuiz) {
+  std::lock_guard<std::mutex> lk(mu_);
+  *err = CheckQuiz(iQuiz);
+  return *err ? -1 : quizzes_[iQuiz].activeQuestion;
+}
+
+PqaError *Engine::SetActiveQuestionBatch(int64_t n, const int64_t *pQuizIds, const int64_t *pQuestions) {
+  if (n < 0) return ErrNegativeCount(n, PQA_FILE_LINE "|n| must be non-negative.");
+  if (n == 0) return nullptr;
+  if (!pQuizIds || !pQuestions) return MakeError(ErrCode::NullArgument, PQA_FILE_LINE "pQuizIds/pQuestions");
+  std::lock_guard<std::mutex> lk(mu_);
+  PQA_TRY
+  for (int64_t x = 0; x < n; x++)
+    if (PqaError *e = CheckQuiz(pQuizIds[x])) return e;
+  UploadIds(n, pQuizIds);
+  hQuestions_.ensure(n); dQuestions_.ensure(n, stream_);
+  std::memcpy(hQuestions_.get(), pQuestions, sizeof(int64_t) * (size_t)n);
+  PQA_CU(cudaMemcpyAsync(dQuestions_.get(), hQuestions_.get(), sizeof(int64_t) * (size_t)n, cudaMemcpyHostToDevice, stream_));
+  launch_set_active(pool(), n, dIds_.get(), dQuestions_.get(), stream_);
+  for (int64_t x = 0; x < n; x++) quizzes_[pQuizIds[x]].activeQuestion = pQuestions[x];  // BaseQuiz::SetActiveQuestion
+  PQA_CU(cudaStreamSynchronize(stream_));
+  return nullptr;
+  PQA_CATCH_RETURN_ERR
+}
+PqaError *Engine::SetActiveQuestion(int64_t iQuiz, int64_t iQuestion) {
+  return SetActiveQuestionBatch(1, &iQuiz, &iQuestion);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// ListTopTargets: BaseEngine::ListTopTargets (BaseEngine.cpp:511-527) -> CpuEngine::ListTopTargetsSpec
+// (CpuEngine.cpp:417-440). The reference switches to a radix-sort variant when maxCount is a large fraction of
+// T/W (:424-432); that variant's merge order is inconsistent in the reference itself (SURVEY.md hard part 9), so
+// this engine always runs the heapify algorithm, which is what every top-10 style call reaches.
+PqaError *Engine::ListTopTargetsBatch(int64_t n, const int64_t *pQuizIds, int64_t maxCount, CiRatedTarget *pDest,
+                                      int64_t *pCounts) {
+  if (n < 0) return ErrNegativeCount(n, PQA_FILE_LINE "|n| must be non-negative.");
+  if (maxCount < 0) return ErrNegativeCount(maxCount, PQA_FILE_LINE "|maxCount| must be non-negative.");
+  if (n == 0) return nullptr;
+  if (!pQuizIds || !pCounts || (maxCount > 0 && !pDest))
+    return MakeError(ErrCode::NullArgument, PQA_FILE_LINE "pQuizIds/pDest/pCounts");
+  std::lock_guard<std::mutex> lk(mu_);
+  PQA_TRY
+  for (int64_t x = 0; x < n; x++)
+    if (PqaError *e = CheckQuiz(pQuizIds[x])) return e;
+  if (maxCount == 0) { for (int64_t x = 0; x < n; x++) pCounts[x] = 0; return nullptr; }
+  UploadIds(n, pQuizIds);
+  const size_t nItems = (size_t)(n * maxCount);
+  dTop_.ensure(nItems, stream_); hTop_.ensure(nItems); dCounts_.ensure(n, stream_); hCounts_.ensure(n);
+  const bool needScratch = (size_t)W_ * 32 + (size_t)T_ * 16 > 200 * 1024;
+  if (needScratch) dTopScratch_.ensure((size_t)(n * T_), stream_);
+  launch_list_top_targets(kb(), pool(), n, dIds_.get(), W_, maxCount, dTopScratch_.get(), dTop_.get(), dCounts_.get(), stream_);
+  PQA_CU(cudaMemcpyAsync(hTop_.get(), dTop_.get(), sizeof(CiRatedTarget) * nItems, cudaMemcpyDeviceToHost, stream_));
+  PQA_CU(cudaMemcpyAsync(hCounts_.get(), dCounts_.get(), sizeof(int64_t) * (size_t)n, cudaMemcpyDeviceToHost, stream_));
+  PQA_CU(cudaStreamSynchronize(stream_));
+  for (int64_t x = 0; x < n; x++) {
+    pCounts[x] = hCounts_.get()[x];
+    std::memcpy(pDest + x * maxCount, hTop_.get() + x * maxCount, sizeof(CiRatedTarget) * (size_t)pCounts[x]);
+  }
+  return nullptr;
+  PQA_CATCH_RETURN_ERR
+}
+
+int64_t Engine::ListTopTargets(PqaError **err, int64_t iQuiz, int64_t maxCount, CiRatedTarget *pDest) {
+  int64_t cnt = 0;
+  *err = ListTopTargetsBatch(1, &iQuiz, maxCount, pDest, &cnt);
+  return *err ? -1 : cnt;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// RecordQuizTarget / Train. The reference applies a quiz' answers two at a time (CpuEngine.cpp:451-462,
+// CETrainOperation.cpp:28-83); here every Perform2/Perform1 is split into per-cell operations (same-question pairs
+// stay fused because they share mD[q][t]) and grouped by (question, target) so that one device thread applies a
+// cell group's operations in the reference's sequence order.
+void Engine::AppendQuizOps(std::vector<TrainOp> &ops, const CiAnsweredQuestion *aqs, int64_t n, int64_t iTarget,
+                           double amount) {
+  int64_t x = 0;
+  for (; x + 1 < n; x += 2) {
+    const CiAnsweredQuestion &f = aqs[x], &s = aqs[x + 1];
+    if (f._iQuestion == s._iQuestion) {
+      ops.push_back(TrainOp{f._iQuestion, f._iAnswer, s._iAnswer, iTarget, amount});  // doubled step or 3-add form
+    } else {
+      ops.push_back(TrainOp{f._iQuestion, f._iAnswer, -1, iTarget, amount});
+      ops.push_back(TrainOp{s._iQuestion, s._iAnswer, -1, iTarget, amount});
+    }
+  }
+  if (x < n) ops.push_back(TrainOp{aqs[x]._iQuestion, aqs[x]._iAnswer, -1, iTarget, amount});
+}
+
+PqaError *Engine::ApplyTrain(const std::vector<TrainOp> &ops, const std::vector<int64_t> &targets,
+                             const std::vector<double> &amounts) {
+  // caller holds mu_
+  PQA_TRY
+  const int64_t nOps = (int64_t)ops.size();
+  if (nOps > 0) {
+    std::vector<int64_t> order(nOps);
+    std::iota(order.begin(), order.end(), 0);
+    auto key = [&](int64_t o) { return ops[o].q * T_ + ops[o].target; };
+    std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) { return key(a) < key(b); });
+    std::vector<TrainOp> sorted(nOps);
+    std::vector<int64_t> groupStart;
+    for (int64_t x = 0; x < nOps; x++) {
+      sorted[x] = ops[order[x]];
+      if (x == 0 || key(order[x]) != key(order[x - 1])) groupStart.push_back(x);
+    }
+    const int64_t nGroups = (int64_t)groupStart.size();
+    groupStart.push_back(nOps);
+    dOps_.ensure(nOps, stream_); dGroupStart_.ensure(groupStart.size(), stream_);
+    PQA_CU(cudaMemcpyAsync(dOps_.get(), sorted.data(), sizeof(TrainOp) * (size_t)nOps, cudaMemcpyHostToDevice, stream_));
+    PQA_CU(cudaMemcpyAsync(dGroupStart_.get(), groupStart.data(), sizeof(int64_t) * groupStart.size(), cudaMemcpyHostToDevice, stream_));
+    launch_train_ops(kb(), dOps_.get(), dGroupStart_.get(), nGroups, stream_);
+    PQA_CU(cudaStreamSynchronize(stream_));  // the staging vectors die at scope end
+  }
+  const int64_t nT = (int64_t)targets.size();
+  if (nT > 0) {
+    std::vector<int64_t> order(nT);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) { return targets[a] < targets[b]; });
+    std::vector<int64_t> st(nT), groupStart;
+    std::vector<double> sa(nT);
+    for (int64_t x = 0; x < nT; x++) {
+      st[x] = targets[order[x]]; sa[x] = amounts[order[x]];
+      if (x == 0 || st[x] != st[x - 1]) groupStart.push_back(x);
+    }
+    const int64_t nGroups = (int64_t)groupStart.size();
+    groupStart.push_back(nT);
+    dTargets_.ensure(nT, stream_); dAmounts_.ensure(nT, stream_); dGroupStart_.ensure(groupStart.size(), stream_);
+    PQA_CU(cudaMemcpyAsync(dTargets_.get(), st.data(), sizeof(int64_t) * (size_t)nT, cudaMemcpyHostToDevice, stream_));
+    PQA_CU(cudaMemcpyAsync(dAmounts_.get(), sa.data(), sizeof(double) * (size_t)nT, cudaMemcpyHostToDevice, stream_));
+    PQA_CU(cudaMemcpyAsync(dGroupStart_.get(), groupStart.data(), sizeof(int64_t) * groupStart.size(), cudaMemcpyHostToDevice, stream_));
+    launch_add_vb(kb(), dTargets_.get(), dAmounts_.get(), dGroupStart_.get(), nGroups, stream_);
+    PQA_CU(cudaStreamSynchronize(stream_));
+  }
+  return nullptr;
+  PQA_CATCH_RETURN_ERR
+}
+
+PqaError *Engine::RecordQuizTargetBatch(int64_t n, const int64_t *pQuizIds, const int64_t *pTargets,
+                                        const double *pAmounts) {
+  if (n < 0) return ErrNegativeCount(n, PQA_FILE_LINE "|n| must be non-negative.");
+  if (n == 0) return nullptr;
+  if (!pQuizIds || !pTargets) return MakeError(ErrCode::NullArgument, PQA_FILE_LINE "pQuizIds/pTargets");
+  std::lock_guard<std::mutex> lk(mu_);
+  std::vector<TrainOp> ops;
+  std::vector<int64_t> targets(n);
+  std::vector<double> amounts(n);
+  for (int64_t x = 0; x < n; x++) {  // BaseEngine::RecordQuizTarget, BaseEngine.cpp:529-566
+    const double amount = pAmounts ? pAmounts[x] : 1.0;
+    if (!(amount > 0)) return ErrNonPositiveAmount(amount, PQA_FILE_LINE "|amount| must be positive.");
+    if (pTargets[x] < 0 || pTargets[x] >= T_)
+      return ErrIndexOutOfRange(pTargets[x], 0, T_ - 1, PQA_FILE_LINE "Target index is not in KB range.");
+    if (PqaError *e = CheckQuiz(pQuizIds[x])) return e;
+    targets[x] = pTargets[x]; amounts[x] = amount;
+  }
+  for (int64_t x = 0; x < n; x++) {
+    const HostQuiz &q = quizzes_[pQuizIds[x]];
+    AppendQuizOps(ops, q.answers.data(), (int64_t)q.answers.size(), targets[x], amounts[x]);
+  }
+  return ApplyTrain(ops, targets, amounts);
+}
+
+PqaError *Engine::RecordQuizTarget(int64_t iQuiz, int64_t iTarget, double amount) {
+  return RecordQuizTargetBatch(1, &iQuiz, &iTarget, &amount);
+}
+
+// BaseEngine::Train (BaseEngine.cpp:235-250) -> CpuEngine::TrainSpec (CpuEngine.cpp:102-183): answered questions
+// are bucketed by iQuestion % W (CETrainSubtaskDistrib.h:19-52) into LIFO chains that are then consumed two at a
+// time (CETrainSubtaskAdd.cpp:17-38). Arrival tickets are taken in array order here (the reference's are racy).
+PqaError *Engine::Train(int64_t nQuestions, const CiAnsweredQuestion *pAQs, int64_t iTarget, double amount) {
+  if (nQuestions < 0) return ErrNegativeCount(nQuestions, "|nQuestions| must be non-negative.");
+  if (!(amount > 0)) return ErrNonPositiveAmount(amount, PQA_FILE_LINE "|amount| must be positive.");
+  if (nQuestions > 0 && !pAQs) return MakeError(ErrCode::NullArgument, PQA_FILE_LINE "pAQs");
+  std::lock_guard<std::mutex> lk(mu_);
+  if (iTarget < 0 || iTarget >= T_) return ErrIndexOutOfRange(iTarget, 0, T_ - 1, "Target index is not in KB range.");
+  for (int64_t x = 0; x < nQuestions; x++) {  // CETrainSubtaskDistrib.h:24-43
+    if (pAQs[x]._iQuestion < 0 || pAQs[x]._iQuestion >= Q_)
+      return ErrIndexOutOfRange(pAQs[x]._iQuestion, 0, Q_ - 1, PQA_FILE_LINE "Question index is not in KB range.");
+    if (pAQs[x]._iAnswer < 0 || pAQs[x]._iAnswer >= K_)
+      return ErrIndexOutOfRange(pAQs[x]._iAnswer, 0, K_ - 1, PQA_FILE_LINE "Answer index is not in KB range.");
+  }
+  std::vector<int64_t> last(W_, -1), prev(std::max<int64_t>(nQuestions, 1), -1);
+  for (int64_t x = 0; x < nQuestions; x++) {
+    const int64_t b = pAQs[x]._iQuestion % W_;
+    prev[x] = last[b]; last[b] = x;
+  }
+  std::vector<TrainOp> ops;
+  for (int w = 0; w < W_; w++) {
+    int64_t iLast = last[w];
+    while (iLast != -1) {
+      const CiAnsweredQuestion &f = pAQs[iLast];
+      iLast = prev[iLast];
+      if (iLast == -1) { ops.push_back(TrainOp{f._iQuestion, f._iAnswer, -1, iTarget, amount}); break; }
+      const CiAnsweredQuestion &s = pAQs[iLast];
+      iLast = prev[iLast];
+      if (f._iQuestion == s._iQuestion) {
+        ops.push_back(TrainOp{f._iQuestion, f._iAnswer, s._iAnswer, iTarget, amount});
+      } else {
+        ops.push_back(TrainOp{f._iQuestion, f._iAnswer, -1, iTarget, amount});
+        ops.push_back(TrainOp{s._iQuestion, s._iAnswer, -1, iTarget, amount});
+      }
+    }
+  }
+  PqaError *e = ApplyTrain(ops, std::vector<int64_t>{iTarget}, std::vector<double>{amount});
+  if (!e) nQuestionsAsked_.fetch_add((uint64_t)nQuestions, std::memory_order_relaxed);  // CpuEngine.cpp:179
+  return e;
+}
+
+// BaseEngine::ReleaseQuiz (BaseEngine.cpp:568-603)
+PqaError *Engine::ReleaseQuizBatch(int64_t n, const int64_t *pQuizIds) {
+  if (n < 0) return ErrNegativeCount(n, PQA_FILE_LINE "|n| must be non-negative.");
+  if (n > 0 && !pQuizIds) return MakeError(ErrCode::NullArgument, PQA_FILE_LINE "pQuizIds");
+  std::lock_guard<std::mutex> lk(mu_);
+  for (int64_t x = 0; x < n; x++) {
+    if (PqaError *e = CheckQuiz(pQuizIds[x])) return e;
+    HostQuiz &q = quizzes_[pQuizIds[x]];
+    q.present = false; q.answers.clear(); q.answers.shrink_to_fit(); q.activeQuestion = -1;
+    quizGaps_.push_back(pQuizIds[x]);
+  }
+  if (residentN_ > 0) residentN_ = 0;  // a released quiz may be part of the bound batch
+  return nullptr;
+}
+PqaError *Engine::ReleaseQuiz(int64_t iQuiz) { return ReleaseQuizBatch(1, &iQuiz); }
+
+// ---------------------------------------------------------------------------------------------------------
+// IPqaEngine::CopyATargets / CopyDTargets / CopyBTargets (Interface/IPqaEngine.h:36-39, CpuEngine.cpp:690-709)
+PqaError *Engine::CopyATargets(int64_t iQuestion, int64_t iAnswer, int64_t maxTargets, double *pFreqs) {
+  std::lock_guard<std::mutex> lk(mu_);
+  if (iQuestion < 0 || iQuestion >= Q_) return ErrIndexOutOfRange(iQuestion, 0, Q_ - 1, PQA_FILE_LINE "Question index is not in KB range.");
+  if (iAnswer < 0 || iAnswer >= K_) return ErrIndexOutOfRange(iAnswer, 0, K_ - 1, PQA_FILE_LINE "Answer index is not in KB range.");
+  PQA_TRY
+  const int64_t cnt = std::min(maxTargets, T_);
+  if (cnt > 0) PQA_CU(cudaMemcpy(pFreqs, dSA_ + (iQuestion * K_ + iAnswer) * Tp_, sizeof(double) * (size_t)cnt, cudaMemcpyDeviceToHost));
+  return nullptr;
+  PQA_CATCH_RETURN_ERR
+}
+PqaError *Engine::CopyDTargets(int64_t iQuestion, int64_t maxTargets, double *pFreqs) {
+  std::lock_guard<std::mutex> lk(mu_);
+  if (iQuestion < 0 || iQuestion >= Q_) return ErrIndexOutOfRange(iQuestion, 0, Q_ - 1, PQA_FILE_LINE "Question index is not in KB range.");
+  PQA_TRY
+  const int64_t cnt = std::min(maxTargets, T_);
+  if (cnt > 0) PQA_CU(cudaMemcpy(pFreqs, dMD_ + iQuestion * Tp_, sizeof(double) * (size_t)cnt, cudaMemcpyDeviceToHost));
+  return nullptr;
+  PQA_CATCH_RETURN_ERR
+}
+PqaError *Engine::CopyBTargets(int64_t maxTargets, double *pFreqs) {
+  std::lock_guard<std::mutex> lk(mu_);
+  PQA_TRY
+  const int64_t cnt = std::min(maxTargets, T_);
+  if (cnt > 0) PQA_CU(cudaMemcpy(pFreqs, dVB_, sizeof(double) * (size_t)cnt, cudaMemcpyDeviceToHost));
+  return nullptr;
+  PQA_CATCH_RETURN_ERR
+}
+
+// Whole-KB transfer in the reference's file layout (CpuEngine.cpp:664-688): rows of T doubles, no padding.
+PqaError *Engine::UploadKB(const double *sA, const double *mD, const double *vB) {
+  if (!sA || !mD || !vB) return MakeError(ErrCode::NullArgument, PQA_FILE_LINE "sA/mD/vB");
+  std::lock_guard<std::mutex> lk(mu_);
+  PQA_TRY
+  if (Tp_ == T_) {
+    PQA_CU(cudaMemcpyAsync(dSA_, sA, sizeof(double) * (size_t)(Q_ * K_ * T_), cudaMemcpyHostToDevice, stream_));
+    PQA_CU(cudaMemcpyAsync(dMD_, mD, sizeof(double) * (size_t)(Q_ * T_), cudaMemcpyHostToDevice, stream_));
+    PQA_CU(cudaMemcpyAsync(dVB_, vB, sizeof(double) * (size_t)T_, cudaMemcpyHostToDevice, stream_));
+  } else {
+    // stage through a device scratch in slabs of <= 256 MB, then pad rows on the device
+    const int64_t rowsPerSlab = std::max<int64_t>(1, (256ll << 20) / (T_ * 8));
+    dRowScratch_.ensure((size_t)(std::min(rowsPerSlab, Q_ * K_) * T_), stream_);
+    for (int64_t r0 = 0; r0 < Q_ * K_; r0 += rowsPerSlab) {
+      const int64_t nr = std::min(rowsPerSlab, Q_ * K_ - r0);
+      PQA_CU(cudaMemcpyAsync(dRowScratch_.get(), sA + r0 * T_, sizeof(double) * (size_t)(nr * T_), cudaMemcpyHostToDevice, stream_));
+      launch_pad_rows(dSA_ + r0 * Tp_, dRowScratch_.get(), nr, T_, Tp_, 0.0, stream_);
+    }
+    for (int64_t r0 = 0; r0 < Q_; r0 += rowsPerSlab) {
+      const int64_t nr = std::min(rowsPerSlab, Q_ - r0);
+      PQA_CU(cudaMemcpyAsync(dRowScratch_.get(), mD + r0 * T_, sizeof(double) * (size_t)(nr * T_), cudaMemcpyHostToDevice, stream_));
+      launch_pad_rows(dMD_ + r0 * Tp_, dRowScratch_.get(), nr, T_, Tp_, 1.0, stream_);
+    }
+    PQA_CU(cudaMemcpyAsync(dRowScratch_.get(), vB, sizeof(double) * (size_t)T_, cudaMemcpyHostToDevice, stream_));
+    launch_pad_rows(dVB_, dRowScratch_.get(), 1, T_, Tp_, 0.0, stream_);
+  }
+  PQA_CU(cudaStreamSynchronize(stream_));
+  return nullptr;
+  PQA_CATCH_RETURN_ERR
+}
+
+PqaError *Engine::DownloadKB(double *sA, double *mD, double *vB) {
+  std::lock_guard<std::mutex> lk(mu_);
+  PQA_TRY
+  if (Tp_ == T_) {
+    if (sA) PQA_CU(cudaMemcpyAsync(sA, dSA_, sizeof(double) * (size_t)(Q_ * K_ * T_), cudaMemcpyDeviceToHost, stream_));
+    if (mD) PQA_CU(cudaMemcpyAsync(mD, dMD_, sizeof(double) * (size_t)(Q_ * T_), cudaMemcpyDeviceToHost, stream_));
+  } else {
+    const int64_t rowsPerSlab = std::max<int64_t>(1, (256ll << 20) / (T_ * 8));
+    dRowScratch_.ensure((size_t)(std::min(rowsPerSlab, Q_ * K_) * T_), stream_);
+    for (int64_t r0 = 0; sA && r0 < Q_ * K_; r0 += rowsPerSlab) {
+      const int64_t nr = std::min(rowsPerSlab, Q_ * K_ - r0);
+      launch_unpad_rows(dRowScratch_.get(), dSA_ + r0 * Tp_, nr, T_, Tp_, stream_);
+      PQA_CU(cudaMemcpyAsync(sA + r0 * T_, dRowScratch_.get(), sizeof(double) * (size_t)(nr * T_), cudaMemcpyDeviceToHost, stream_));
+      PQA_CU(cudaStreamSynchronize(stream_));
+    }
+    for (int64_t r0 = 0; mD && r0 < Q_; r0 += rowsPerSlab) {
+      const int64_t nr = std::min(rowsPerSlab, Q_ - r0);
+      launch_unpad_rows(dRowScratch_.get(), dMD_ + r0 * Tp_, nr, T_, Tp_, stream_);
+      PQA_CU(cudaMemcpyAsync(mD + r0 * T_, dRowScratch_.get(), sizeof(double) * (size_t)(nr * T_), cudaMemcpyDeviceToHost, stream_));
+      PQA_CU(cudaStreamSynchronize(stream_));
+    }
+  }
+  if (vB) PQA_CU(cudaMemcpyAsync(vB, dVB_, sizeof(double) * (size_t)T_, cudaMemcpyDeviceToHost, stream_));
+  PQA_CU(cudaStreamSynchronize(stream_));
+  return nullptr;
+  PQA_CATCH_RETURN_ERR
+}
+
+PqaError *Engine::CopyQuizPriors(int64_t iQuiz, double *pPriors) {
+  std::lock_guard<std::mutex> lk(mu_);
+  if (PqaError *e = CheckQuiz(iQuiz)) return e;
+  PQA_TRY
+  PQA_CU(cudaMemcpyAsync(pPriors, dPriors_ + iQuiz * Tp_, sizeof(double) * (size_t)T_, cudaMemcpyDeviceToHost, stream_));
+  PQA_CU(cudaStreamSynchronize(stream_));
+  return nullptr;
+  PQA_CATCH_RETURN_ERR
+}
+PqaError *Engine::SetQuizPriors(int64_t iQuiz, const double *pPriors) {
+  std::lock_guard<std::mutex> lk(mu_);
+  if (PqaError *e = CheckQuiz(iQuiz)) return e;
+  PQA_TRY
+  PQA_CU(cudaMemcpyAsync(dPriors_ + iQuiz * Tp_, pPriors, sizeof(double) * (size_t)T_, cudaMemcpyHostToDevice, stream_));
+  UploadIds(1, &iQuiz);
+  launch_refresh_log_priors(pool(), 1, dIds_.get(), stream_);
+  PQA_CU(cudaStreamSynchronize(stream_));
+  return nullptr;
+  PQA_CATCH_RETURN_ERR
+}
+
+PqaError *Engine::SetEvalKernel(int32_t which, int64_t chunkTargets, int64_t quizzesPerCta) {
+  if (which < 0 || which > 2) return ErrIndexOutOfRange(which, 0, 2, PQA_FILE_LINE "which");
+  std::lock_guard<std::mutex> lk(mu_);
+  evalCfg_.which = which; evalCfg_.chunkTargets = chunkTargets; evalCfg_.quizzesPerCta = quizzesPerCta;
+  return nullptr;
+}
+
+PqaError *Engine::EvalQuestions(int64_t n, const int64_t *pQuizIds, double *pPriorities, double *pRunLength,
+                                double *pGrandTotals, int64_t *pnChunks) {
+  if (n <= 0) return ErrNegativeCount(n, PQA_FILE_LINE "|n| must be positive.");
+  std::lock_guard<std::mutex> lk(mu_);
+  for (int64_t x = 0; x < n; x++)
+    if (PqaError *e = CheckQuiz(pQuizIds[x])) return e;
+  PQA_TRY
+  UploadIds(n, pQuizIds);
+  const int64_t nChunks = select_chunk_count(Q_, W_);
+  if (pnChunks) *pnChunks = nChunks;
+  dPriority_.ensure((size_t)(n * Q_), stream_); dRunLength_.ensure((size_t)(n * Q_), stream_);
+  dGrand_.ensure((size_t)(n * nChunks), stream_);
+  EvalDetail det{nullptr, nullptr, nullptr, nullptr};
+  launch_eval_questions(kb(), pool(), n, dIds_.get(), dPriority_.get(), det, evalCfg_, stream_);
+  launch_select_question(kb(), pool(), n, dIds_.get(), dPriority_.get(), nullptr, W_, dRunLength_.get(), dGrand_.get(),
+                         nullptr, 0, stream_);
+  if (pPriorities) PQA_CU(cudaMemcpyAsync(pPriorities, dPriority_.get(), sizeof(double) * (size_t)(n * Q_), cudaMemcpyDeviceToHost, stream_));
+  if (pRunLength) PQA_CU(cudaMemcpyAsync(pRunLength, dRunLength_.get(), sizeof(double) * (size_t)(n * Q_), cudaMemcpyDeviceToHost, stream_));
+  if (pGrandTotals) PQA_CU(cudaMemcpyAsync(pGrandTotals, dGrand_.get(), sizeof(double) * (size_t)(n * nChunks), cudaMemcpyDeviceToHost, stream_));
+  PQA_CU(cudaStreamSynchronize(stream_));
+  return nullptr;
+  PQA_CATCH_RETURN_ERR
+}
+
+PqaError *Engine::EvalQuestionsDetailed(int64_t iQuiz, double *pW, double *pH, double *pV, double *pLack,
+                                        double *pPriorities) {
+  std::lock_guard<std::mutex> lk(mu_);
+  if (PqaError *e = CheckQuiz(iQuiz)) return e;
+  PQA_TRY
+  UploadIds(1, &iQuiz);
+  const size_t qk = (size_t)(Q_ * K_);
+  dDetail_.ensure(3 * qk + (size_t)Q_, stream_); dPriority_.ensure((size_t)Q_, stream_);
+  PQA_CU(cudaMemsetAsync(dDetail_.get(), 0xFF, sizeof(double) * (3 * qk + (size_t)Q_), stream_));  // NaN where not evaluated
+  EvalDetail det{dDetail_.get(), dDetail_.get() + qk, dDetail_.get() + 2 * qk, dDetail_.get() + 3 * qk};
+  launch_eval_questions(kb(), pool(), 1, dIds_.get(), dPriority_.get(), det, evalCfg_, stream_);
+  if (pW) PQA_CU(cudaMemcpyAsync(pW, det.W, sizeof(double) * qk, cudaMemcpyDeviceToHost, stream_));
+  if (pH) PQA_CU(cudaMemcpyAsync(pH, det.H, sizeof(double) * qk, cudaMemcpyDeviceToHost, stream_));
+  if (pV) PQA_CU(cudaMemcpyAsync(pV, det.V, sizeof(double) * qk, cudaMemcpyDeviceToHost, stream_));
+  if (pLack) PQA_CU(cudaMemcpyAsync(pLack, det.lack, sizeof(double) * (size_t)Q_, cudaMemcpyDeviceToHost, stream_));
+  if (pPriorities) PQA_CU(cudaMemcpyAsync(pPriorities, dPriority_.get(), sizeof(double) * (size_t)Q_, cudaMemcpyDeviceToHost, stream_));
+  PQA_CU(cudaStreamSynchronize(stream_));
+  return nullptr;
+  PQA_CATCH_RETURN_ERR
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Device-resident stepping: the batch's ids and random draws are bound once; a step is one NextQuestion pass
+// (evaluation + selection) whose results stay on the device. Used to time the hot path without host traffic.
+PqaError *Engine::ResidentBind(int64_t n, const int64_t *pQuizIds, const uint64_t *pRandoms) {
+  if (n <= 0) return ErrNegativeCount(n, PQA_FILE_LINE "|n| must be positive.");
+  std::lock_guard<std::mutex> lk(mu_);
+  for (int64_t x = 0; x < n; x++)
+    if (PqaError *e = CheckQuiz(pQuizIds[x])) return e;
+  PQA_TRY
+  dResIds_.ensure(n, stream_); dResRandoms_.ensure(n, stream_); dResQuestions_.ensure(n, stream_);
+  dResPriority_.ensure((size_t)(n * Q_), stream_); dResRunLength_.ensure((size_t)(n * Q_), stream_);
+  std::vector<uint64_t> rnd(n);
+  for (int64_t x = 0; x < n; x++) rnd[x] = pRandoms ? pRandoms[x] : NextRandom();
+  PQA_CU(cudaMemcpyAsync(dResIds_.get(), pQuizIds, sizeof(int64_t) * (size_t)n, cudaMemcpyHostToDevice, stream_));
+  PQA_CU(cudaMemcpyAsync(dResRandoms_.get(), rnd.data(), sizeof(uint64_t) * (size_t)n, cudaMemcpyHostToDevice, stream_));
+  PQA_CU(cudaStreamSynchronize(stream_));
+  residentN_ = n;
+  return nullptr;
+  PQA_CATCH_RETURN_ERR
+}
+PqaError *Engine::ResidentStep() {
+  std::lock_guard<std::mutex> lk(mu_);
+  if (residentN_ <= 0) return MakeError(ErrCode::NotInitialized, PQA_FILE_LINE "no resident batch is bound");
+  PQA_TRY
+  EvalDetail det{nullptr, nullptr, nullptr, nullptr};
+  if (!evEvalStart_) { PQA_CU(cudaEventCreate(&evEvalStart_)); PQA_CU(cudaEventCreate(&evEvalStop_)); }
+  PQA_CU(cudaEventRecord(evEvalStart_, stream_));
+  launch_eval_questions(kb(), pool(), residentN_, dResIds_.get(), dResPriority_.get(), det, evalCfg_, stream_);
+  PQA_CU(cudaEventRecord(evEvalStop_, stream_));
+  launch_select_question(kb(), pool(), residentN_, dResIds_.get(), dResPriority_.get(), dResRandoms_.get(), W_,
+                         dResRunLength_.get(), nullptr, dResQuestions_.get(), 0, stream_);
+  PQA_CU(cudaGetLastError());
+  return nullptr;
+  PQA_CATCH_RETURN_ERR
+}
+PqaError *Engine::ResidentFetch(int64_t *pQuestions) {
+  std::lock_guard<std::mutex> lk(mu_);
+  if (residentN_ <= 0) return MakeError(ErrCode::NotInitialized, PQA_FILE_LINE "no resident batch is bound");
+  PQA_TRY
+  PQA_CU(cudaMemcpyAsync(pQuestions, dResQuestions_.get(), sizeof(int64_t) * (size_t)residentN_, cudaMemcpyDeviceToHost, stream_));
+  PQA_CU(cudaStreamSynchronize(stream_));
+  return nullptr;
+  PQA_CATCH_RETURN_ERR
+}
+double Engine::ResidentLastEvalMs() {
+  std::lock_guard<std::mutex> lk(mu_);
+  if (!evEvalStart_) return -1.0;
+  float ms = -1.f;
+  if (cudaEventSynchronize(evEvalStop_) != cudaSuccess) return -1.0;
+  if (cudaEventElapsedTime(&ms, evEvalStart_, evEvalStop_) != cudaSuccess) return -1.0;
+  return (double)ms;
+}
+PqaError *Engine::Synchronize() {
+  PQA_TRY
+  PQA_CU(cudaStreamSynchronize(stream_));
+  PQA_CU(cudaGetLastError());
+  return nullptr;
+  PQA_CATCH_RETURN_ERR
+}
+PqaError *Engine::FlushL2() {
+  std::lock_guard<std::mutex> lk(mu_);
+  PQA_TRY
+  if (!flushBuf_) {
+    flushBytes_ = 256ull << 20;  // > 126 MB L2
+    PQA_CU(cudaMalloc(&flushBuf_, flushBytes_));
+  }
+  launch_flush_l2(flushBuf_, flushBytes_, stream_);
+  return nullptr;
+  PQA_CATCH_RETURN_ERR
+}
+
+PqaError *Engine::SaveKB(const char *) {
+  return ErrNotImplemented("B200 engine: SaveKB (BaseEngine.cpp:323-385) -- KB file format is SURVEY 8(f)-1");
+}
+Engine *Engine::LoadKB(const char *, const CiB200Options &, PqaError **err) {
+  *err = ErrNotImplemented("B200 engine: LoadCpuEngine (PqaEngineBaseFactory.cpp:56-83) -- KB file format is SURVEY 8(f)-1");
+  return nullptr;
+}
+
+} // namespace pqa

@@ -1,0 +1,167 @@
+// probqa_b200: host side of the B200 engine. The method set mirrors the reference's IPqaEngine
+// (PqaCore/Interface/IPqaEngine.h:13-114) for the quiz path, with the validation, error codes and quiz-registry
+// behaviour of BaseEngine (PqaCore/BaseEngine.cpp) and the arithmetic of CpuEngine<SRDoubleNumber> executed by the
+// kernels of pqa_kernels.cu / pqa_eval_staged.cu. There is no CPU compute path: every operation on priors, sA, mD
+// and vB runs on the device; the host only validates, keeps the quiz registry (ids, answered lists, active
+// question) and moves ids/answers/results through pinned staging buffers.
+#pragma once
+#include <atomic>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/PqaB200Ext.h"
+#include "pqa_errors.h"
+#include "pqa_kernels.cuh"
+
+namespace pqa {
+
+struct CudaFail : std::runtime_error {
+  int code; const char *file; int line;
+  CudaFail(int c, const char *what, const char *f, int l) : std::runtime_error(what), code(c), file(f), line(l) {}
+};
+#define PQA_CU(expr)                                                                 \
+  do {                                                                               \
+    cudaError_t e_ = (expr);                                                         \
+    if (e_ != cudaSuccess) throw ::pqa::CudaFail((int)e_, #expr, __FILE__, __LINE__); \
+  } while (0)
+
+template <typename T> class DevBuf {  // grow-only device array
+ public:
+  ~DevBuf() { if (p_) cudaFree(p_); }
+  T *get() const { return p_; }
+  size_t size() const { return n_; }
+  void ensure(size_t n, cudaStream_t st = nullptr, bool keep = false);
+ private:
+  T *p_ = nullptr;
+  size_t n_ = 0;
+};
+
+template <typename T> class PinBuf {  // grow-only pinned host array
+ public:
+  ~PinBuf() { if (p_) cudaFreeHost(p_); }
+  T *get() const { return p_; }
+  void ensure(size_t n);
+ private:
+  T *p_ = nullptr;
+  size_t n_ = 0;
+};
+
+struct HostQuiz {                      // BaseQuiz.h:13-36 (host part); priors and asked bits live on the device
+  bool present = false;
+  int64_t activeQuestion = -1;
+  std::vector<CiAnsweredQuestion> answers;
+};
+
+class Engine {
+ public:
+  Engine(const CiEngineDefinition &def, const CiB200Options &opts);
+  ~Engine();
+
+  // --- IPqaEngine mirror (one quiz per call) ---
+  PqaError *Train(int64_t nQuestions, const CiAnsweredQuestion *pAQs, int64_t iTarget, double amount);
+  int64_t StartQuiz(PqaError **err);
+  int64_t ResumeQuiz(PqaError **err, int64_t nAnswered, const CiAnsweredQuestion *pAQs);
+  int64_t NextQuestion(PqaError **err, int64_t iQuiz);
+  PqaError *RecordAnswer(int64_t iQuiz, int64_t iAnswer);
+  int64_t GetActiveQuestionId(PqaError **err, int64_t iQuiz);
+  PqaError *SetActiveQuestion(int64_t iQuiz, int64_t iQuestion);
+  int64_t ListTopTargets(PqaError **err, int64_t iQuiz, int64_t maxCount, CiRatedTarget *pDest);
+  PqaError *RecordQuizTarget(int64_t iQuiz, int64_t iTarget, double amount);
+  PqaError *ReleaseQuiz(int64_t iQuiz);
+  uint64_t GetTotalQuestionsAsked() const { return nQuestionsAsked_.load(std::memory_order_relaxed); }
+  CiEngineDimensions CopyDims() const { return CiEngineDimensions{K_, Q_, T_}; }
+  PqaError *CopyATargets(int64_t iQuestion, int64_t iAnswer, int64_t maxTargets, double *pFreqs);
+  PqaError *CopyDTargets(int64_t iQuestion, int64_t maxTargets, double *pFreqs);
+  PqaError *CopyBTargets(int64_t maxTargets, double *pFreqs);
+  PqaError *SaveKB(const char *filePath);
+  static Engine *LoadKB(const char *filePath, const CiB200Options &opts, PqaError **err);
+
+  // --- batches of concurrent quizzes ---
+  PqaError *StartQuizBatch(int64_t n, int64_t *pQuizIds);
+  PqaError *NextQuestionBatch(int64_t n, const int64_t *pQuizIds, const uint64_t *pRandoms, int64_t *pQuestions,
+                              void **ppErrors);
+  PqaError *RecordAnswerBatch(int64_t n, const int64_t *pQuizIds, const int64_t *pAnswers);
+  PqaError *SetActiveQuestionBatch(int64_t n, const int64_t *pQuizIds, const int64_t *pQuestions);
+  PqaError *ListTopTargetsBatch(int64_t n, const int64_t *pQuizIds, int64_t maxCount, CiRatedTarget *pDest,
+                                int64_t *pCounts);
+  PqaError *RecordQuizTargetBatch(int64_t n, const int64_t *pQuizIds, const int64_t *pTargets, const double *pAmounts);
+  PqaError *ReleaseQuizBatch(int64_t n, const int64_t *pQuizIds);
+
+  // --- KB transfer / inspection ---
+  PqaError *UploadKB(const double *sA, const double *mD, const double *vB);
+  PqaError *DownloadKB(double *sA, double *mD, double *vB);
+  PqaError *CopyQuizPriors(int64_t iQuiz, double *pPriors);
+  PqaError *SetQuizPriors(int64_t iQuiz, const double *pPriors);
+  PqaError *EvalQuestions(int64_t n, const int64_t *pQuizIds, double *pPriorities, double *pRunLength,
+                          double *pGrandTotals, int64_t *pnChunks);
+  PqaError *EvalQuestionsDetailed(int64_t iQuiz, double *pW, double *pH, double *pV, double *pLack, double *pPriorities);
+  PqaError *SetEvalKernel(int32_t which, int64_t chunkTargets, int64_t quizzesPerCta);
+
+  // --- device-resident stepping ---
+  PqaError *ResidentBind(int64_t n, const int64_t *pQuizIds, const uint64_t *pRandoms);
+  PqaError *ResidentStep();
+  PqaError *ResidentFetch(int64_t *pQuestions);
+  double ResidentLastEvalMs();   // device time of the evaluation kernel of the most recent ResidentStep (-1 on error)
+  PqaError *Synchronize();
+  PqaError *FlushL2();
+  cudaStream_t stream() const { return stream_; }
+  int device() const { return device_; }
+  int emulatedWorkers() const { return W_; }
+
+ private:
+  PqaError *CheckQuiz(int64_t iQuiz) const;              // BaseEngine::UseQuiz, BaseEngine.cpp:399-419
+  int64_t AssignQuizId();                                // BaseEngine::AssignQuiz + GapTracker::Acquire
+  void EnsureQuizCapacity(int64_t nSlots);
+  void EnsureBatchScratch(int64_t n, bool needTop, int64_t maxCount);
+  void UploadIds(int64_t n, const int64_t *ids);
+  uint64_t NextRandom();
+  DeviceKB kb() const;
+  QuizPool pool() const;
+  PqaError *ApplyTrain(const std::vector<TrainOp> &ops, const std::vector<int64_t> &targets,
+                       const std::vector<double> &amounts);
+  static void AppendQuizOps(std::vector<TrainOp> &ops, const CiAnsweredQuestion *aqs, int64_t n, int64_t iTarget,
+                            double amount);
+
+  mutable std::mutex mu_;
+  int device_ = 0, W_ = 1, smCount_ = 148;
+  int64_t Q_ = 0, K_ = 0, T_ = 0, Tp_ = 0, askedWords_ = 0;
+  double initAmount_ = 0;
+  cudaStream_t stream_ = nullptr;
+  EvalConfig evalCfg_;
+
+  double *dSA_ = nullptr, *dMD_ = nullptr, *dVB_ = nullptr, *dLog2Tbl_ = nullptr;
+  // quiz pool
+  int64_t quizCap_ = 0;
+  double *dPriors_ = nullptr, *dLogPriors_ = nullptr;
+  uint64_t *dAsked_ = nullptr;
+  int64_t *dActive_ = nullptr;
+  std::vector<HostQuiz> quizzes_;
+  std::vector<int64_t> quizGaps_;   // released ids, reused LIFO (GapTracker.h:38-49)
+
+  // per-call staging
+  DevBuf<int64_t> dIds_, dAnswers_, dQuestions_, dCounts_, dGroupStart_, dTargets_;
+  DevBuf<uint64_t> dRandoms_;
+  DevBuf<double> dPriority_, dRunLength_, dGrand_, dDetail_, dAmounts_, dRowScratch_;
+  DevBuf<CiRatedTarget> dTop_, dTopScratch_;
+  DevBuf<TrainOp> dOps_;
+  PinBuf<int64_t> hIds_, hAnswers_, hQuestions_, hCounts_;
+  PinBuf<uint64_t> hRandoms_;
+  PinBuf<CiRatedTarget> hTop_;
+  PinBuf<double> hRow_;
+
+  // resident batch
+  int64_t residentN_ = 0;
+  DevBuf<int64_t> dResIds_, dResQuestions_;
+  DevBuf<uint64_t> dResRandoms_;
+  DevBuf<double> dResPriority_, dResRunLength_;
+  cudaEvent_t evEvalStart_ = nullptr, evEvalStop_ = nullptr;
+  void *flushBuf_ = nullptr;
+  size_t flushBytes_ = 0;
+
+  uint64_t rng_[2];
+  std::atomic<uint64_t> nQuestionsAsked_{0};
+};
+
+} // namespace pqa

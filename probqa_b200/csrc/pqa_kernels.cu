@@ -1,0 +1,600 @@
+// probqa_b200: sm_100a kernels of the quiz path other than the throughput question-evaluation kernel
+// (pqa_eval_staged.cu): KB fill / row packing, StartQuiz, RecordAnswer (bit-exact posterior update), the exact
+// question evaluation (reference rounding order), question selection, ListTopTargets, RecordQuizTarget/Train.
+// Citations are relative to /root/reference/ProbQA/. Built with -fmad=false: every fused multiply-add is explicit.
+#include "pqa_kernels.cuh"
+#include "pqa_device.cuh"
+
+#include <atomic>
+#include <math.h>
+
+namespace pqa {
+
+static std::atomic<uint64_t> g_launches{0};
+uint64_t kernel_launch_count() { return g_launches.load(std::memory_order_relaxed); }
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+static inline int grid_for(int64_t n, int block, int cap = 148 * 16) {
+  int64_t g = (n + block - 1) / block;
+  if (g < 1) g = 1;
+  if (g > cap) g = cap;
+  return (int)g;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// KB initialisation (CpuEngine.cpp:34-93: sA = init^2, mD = K*init^2, vB = init) and row packing.
+__global__ void k_fill_kb(DeviceKB kb, double initSqr, double initMD, double init1) {
+  const int64_t nA = kb.Q * kb.K * kb.Tp, nD = kb.Q * kb.Tp, stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; x < nA; x += stride)
+    kb.sA[x] = (x % kb.Tp) < kb.T ? initSqr : 0.0;
+  for (int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; x < nD; x += stride)
+    kb.mD[x] = (x % kb.Tp) < kb.T ? initMD : 1.0;
+  for (int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; x < kb.Tp; x += stride)
+    kb.vB[x] = x < kb.T ? init1 : 0.0;
+}
+void launch_fill_kb(const DeviceKB &kb, double initSqr, double initMD, double init1, cudaStream_t st) {
+  k_fill_kb<<<148 * 8, 256, 0, st>>>(kb, initSqr, initMD, init1);
+  count_launch();
+}
+
+__global__ void k_pad_rows(double *__restrict__ dst, const double *__restrict__ src, int64_t nRows, int64_t T,
+                           int64_t Tp, double padValue) {
+  const int64_t n = nRows * Tp, stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; x < n; x += stride) {
+    const int64_t r = x / Tp, j = x - r * Tp;
+    dst[x] = j < T ? src[r * T + j] : padValue;
+  }
+}
+void launch_pad_rows(double *dst, const double *src, int64_t nRows, int64_t T, int64_t Tp, double padValue,
+                     cudaStream_t st) {
+  k_pad_rows<<<grid_for(nRows * Tp, 256), 256, 0, st>>>(dst, src, nRows, T, Tp, padValue);
+  count_launch();
+}
+__global__ void k_unpad_rows(double *__restrict__ dst, const double *__restrict__ src, int64_t nRows, int64_t T,
+                             int64_t Tp) {
+  const int64_t n = nRows * T, stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; x < n; x += stride) {
+    const int64_t r = x / T, j = x - r * T;
+    dst[x] = src[r * Tp + j];
+  }
+}
+void launch_unpad_rows(double *dst, const double *src, int64_t nRows, int64_t T, int64_t Tp, cudaStream_t st) {
+  k_unpad_rows<<<grid_for(nRows * T, 256), 256, 0, st>>>(dst, src, nRows, T, Tp);
+  count_launch();
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// StartQuiz / RecordAnswer: one CTA per quiz. Bit-exact with CpuEngine for the emulated worker count W:
+//   m[j]   = gap ? +0 : vB[j]                                   CESetPriorsSubtaskSum.cpp:30-35
+//          | gap ? +0 : prior[j] * (sA[q][a][j] / mD[q][j])     CERecordAnswerSubtaskMul.cpp:27-37 (divide first)
+//   pieces = CalcSplit(ceil(T/4) vectors, W); per piece four Kahan lanes in vector order, PreciseSum
+//            (SRAccumVectDbl256.h:83-91); scalar Kahan over the piece sums (Summator.h:11-21)
+//   prior[j] = m[j] / S                                         CEDivTargPriorsSubtask.h:16-21
+// Shared memory: 4W lane sums + 4W lane corrections + W piece sums + 1.
+template <int MODE>  // 0 = StartQuiz, 1 = RecordAnswer
+__global__ void __launch_bounds__(256) k_update_priors(DeviceKB kb, QuizPool qp, const int64_t *__restrict__ slots,
+                                                       const int64_t *__restrict__ answers, int W) {
+  extern __shared__ double sm[];
+  double *laneS = sm, *laneC = sm + 4 * W, *pieceSum = sm + 8 * W, *total = sm + 9 * W;
+  const int64_t slot = slots[blockIdx.x];
+  double *prior = qp.priors + slot * qp.Tp;
+  double *lprior = qp.logPriors + slot * qp.Tp;
+  const int64_t T = kb.T, Tp = kb.Tp;
+  const double *rowA = nullptr, *rowD = nullptr;
+  int64_t q = -1;
+  if (MODE == 1) {
+    q = qp.active[slot];
+    const int64_t a = answers[blockIdx.x];
+    rowA = kb.sA + (q * kb.K + a) * Tp;
+    rowD = kb.mD + q * Tp;
+  }
+  for (int64_t j = threadIdx.x; j < Tp; j += blockDim.x) {
+    double m = 0.0;
+    if (j < T && !bit32(kb.tgaps, j)) {
+      if (MODE == 0) m = kb.vB[j];
+      else m = __dmul_rn(prior[j], __ddiv_rn(rowA[j], rowD[j]));
+    }
+    prior[j] = m;
+  }
+  __syncthreads();
+  const int64_t nVects = Tp >> 2;
+  const int64_t nPieces = split_count(nVects, W);
+  for (int64_t t = threadIdx.x; t < nPieces * 4; t += blockDim.x) {
+    const int64_t p = t >> 2, lane = t & 3;
+    const int64_t first = split_start(nVects, W, p), limit = split_start(nVects, W, p + 1);
+    Kahan k; k.init();
+    for (int64_t v = first; v < limit; v++) k.add(prior[4 * v + lane]);
+    laneS[t] = k.s; laneC[t] = k.c;
+  }
+  __syncthreads();
+  for (int64_t p = threadIdx.x; p < nPieces; p += blockDim.x)
+    pieceSum[p] = precise_sum4(laneS[4 * p], laneS[4 * p + 1], laneS[4 * p + 2], laneS[4 * p + 3],
+                               laneC[4 * p], laneC[4 * p + 1], laneC[4 * p + 2], laneC[4 * p + 3]);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    Kahan k; k.init(0.0);
+    for (int64_t p = 0; p < nPieces; p++) k.add(pieceSum[p]);
+    total[0] = k.get();
+    if (MODE == 0) {
+      for (int64_t w = 0; w < qp.askedWords; w++) qp.asked[slot * qp.askedWords + w] = 0;
+      qp.active[slot] = -1;
+    } else {
+      qp.asked[slot * qp.askedWords + (q >> 6)] |= 1ull << (q & 63);  // CEQuiz.h:91
+      qp.active[slot] = -1;                                           // CEQuiz.h:92
+    }
+  }
+  __syncthreads();
+  const double S = total[0];
+  for (int64_t j = threadIdx.x; j < Tp; j += blockDim.x) {
+    const double v = j < T ? __ddiv_rn(prior[j], S) : 0.0;
+    prior[j] = v;
+    lprior[j] = log2(v);
+  }
+}
+
+static size_t priors_smem(int W) { return sizeof(double) * (size_t)(9 * W + 1); }
+
+void launch_start_quiz(const DeviceKB &kb, const QuizPool &qp, int64_t n, const int64_t *dSlots, int W,
+                       cudaStream_t st) {
+  if (n <= 0) return;
+  k_update_priors<0><<<(unsigned)n, 256, priors_smem(W), st>>>(kb, qp, dSlots, nullptr, W);
+  count_launch();
+}
+void launch_record_answer(const DeviceKB &kb, const QuizPool &qp, int64_t n, const int64_t *dSlots,
+                          const int64_t *dAnswers, int W, cudaStream_t st) {
+  if (n <= 0) return;
+  k_update_priors<1><<<(unsigned)n, 256, priors_smem(W), st>>>(kb, qp, dSlots, dAnswers, W);
+  count_launch();
+}
+
+__global__ void k_refresh_log_priors(QuizPool qp, const int64_t *__restrict__ slots) {
+  const int64_t slot = slots[blockIdx.x];
+  for (int64_t j = threadIdx.x; j < qp.Tp; j += blockDim.x)
+    qp.logPriors[slot * qp.Tp + j] = log2(qp.priors[slot * qp.Tp + j]);
+}
+void launch_refresh_log_priors(const QuizPool &qp, int64_t n, const int64_t *dSlots, cudaStream_t st) {
+  if (n <= 0) return;
+  k_refresh_log_priors<<<(unsigned)n, 256, 0, st>>>(qp, dSlots);
+  count_launch();
+}
+
+__global__ void k_set_active(QuizPool qp, int64_t n, const int64_t *__restrict__ slots,
+                             const int64_t *__restrict__ questions) {
+  const int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (x < n) qp.active[slots[x]] = questions[x];
+}
+void launch_set_active(const QuizPool &qp, int64_t n, const int64_t *dSlots, const int64_t *dQuestions,
+                       cudaStream_t st) {
+  if (n <= 0) return;
+  k_set_active<<<grid_for(n, 128), 128, 0, st>>>(qp, n, dSlots, dQuestions);
+  count_launch();
+}
+
+__global__ void k_flush_l2(double *buf, size_t n) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t x = (size_t)blockIdx.x * blockDim.x + threadIdx.x; x < n; x += stride) buf[x] = (double)x;
+}
+void launch_flush_l2(void *buf, size_t bytes, cudaStream_t st) {
+  k_flush_l2<<<148 * 8, 256, 0, st>>>((double *)buf, bytes / 8);
+  count_launch();
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Exact question evaluation: CEEvalQsSubtaskConsider<SRDoubleNumber>::Run (CEEvalQsSubtaskConsider.cpp:41-217)
+// with every rounding in the reference's order. Four threads play the four AVX lanes of one (quiz, question)
+// evaluation: thread l owns targets j with j % 4 == l and runs the lane's Kahan sums sequentially in vector
+// order; PreciseSum/PairSum gather the lanes. A warp holds 8 quizzes of the same question, so its sA/mD loads are
+// warp-broadcasts. lik and invD are recomputed in pass 2 instead of being spilled (deterministic => same bits).
+__global__ void __launch_bounds__(128) k_eval_exact(DeviceKB kb, QuizPool qp, int64_t n,
+                                                    const int64_t *__restrict__ slots,
+                                                    double *__restrict__ priority, EvalDetail det) {
+  const int64_t i = blockIdx.x;
+  const int lane = threadIdx.x & 3;
+  const int64_t b = (int64_t)blockIdx.y * 32 + (threadIdx.x >> 2);
+  if (b >= n) return;  // whole 4-thread group leaves together
+  const int64_t slot = slots[b];
+  if (bit32(kb.qgaps, i) || bit64(qp.asked + slot * qp.askedWords, i)) {  // :54-58
+    if (lane == 0) priority[b * kb.Q + i] = nan("");
+    return;
+  }
+  const int64_t T = kb.T, Tp = kb.Tp, K = kb.K, nTV = Tp >> 2;
+  const double *__restrict__ prior = qp.priors + slot * Tp;
+  const double *__restrict__ mDi = kb.mD + i * Tp;
+  const double *__restrict__ tbl = kb.log2tbl;
+
+  Kahan totW; totW.init(0.0);        // scalar accumulator, every lane carries an identical copy (:89,:134)
+  Kahan accL; accL.init();           // one lane of accLack, never reset across answers (:61,:117)
+  Kahan avgH, avgV; avgH.init(); avgV.init();  // this thread's lane of accAvgH / accAvgV (:139-172)
+  const int64_t nVectorized = (K >> 2) << 2;
+  for (int64_t k = 0; k < K; k++) {
+    const double *__restrict__ sAik = kb.sA + (i * K + k) * Tp;
+    Kahan accW; accW.init();
+    for (int64_t v = 0; v < nTV; v++) {                          // pass 1 (:66-87)
+      const int64_t j = 4 * v + lane;
+      const bool gap = j >= T || bit32(kb.tgaps, j);
+      const double invD = gap ? 0.0 : __ddiv_rn(1.0, mDi[j]);
+      const double P = gap ? 0.0 : __dmul_rn(sAik[j], invD);
+      const double lik = gap ? 0.0 : __dmul_rn(P, prior[j]);
+      accW.add(lik);
+    }
+    const double Wk = group_precise_sum(accW);                   // :88
+    totW.add(Wk);
+    const double invW = __ddiv_rn(1.0, Wk);                      // :91
+    Kahan accH, accV; accH.init(); accV.init();
+    for (int64_t v = 0; v < nTV; v++) {                          // pass 2 (:95-128)
+      const int64_t j = 4 * v + lane;
+      const bool gap = j >= T || bit32(kb.tgaps, j);
+      const double invD = gap ? 0.0 : __ddiv_rn(1.0, mDi[j]);
+      const double P = gap ? 0.0 : __dmul_rn(sAik[j], invD);
+      const double pr = gap ? 0.0 : prior[j];
+      const double lik = gap ? 0.0 : __dmul_rn(P, pr);
+      const double post = __dmul_rn(lik, invW);                  // :97
+      const double l2 = gap ? 0.0 : log2hot(post, tbl);          // :106
+      accH.add(__dmul_rn(post, l2));                             // :113-114
+      accL.add(gap ? 0.0 : __ddiv_rn(__dmul_rn(invD, invD), l2)); // :116-117
+      const double d = __dsub_rn(post, pr);                      // :119
+      accV.add(__dmul_rn(d, d));                                 // :126-127
+    }
+    const double Hk = -group_precise_sum(accH);                  // PairSum (:129-132)
+    const double Vk = group_precise_sum(accV);
+    // weighted averages: answers 0..nVectorized-1 go to lane k%4, the tail to lane k-nVectorized (:148-172)
+    const int tgtLane = (k < nVectorized) ? (int)(k & 3) : (int)(k - nVectorized);
+    if (lane == tgtLane) {
+      avgH.add(__dmul_rn(Wk, Hk));
+      avgV.add(__dmul_rn(Wk, sqrt(Vk)));
+    }
+    if (lane == 0) {
+      if (det.W) det.W[(b * kb.Q + i) * K + k] = Wk;
+      if (det.H) det.H[(b * kb.Q + i) * K + k] = Hk;
+      if (det.V) det.V[(b * kb.Q + i) * K + k] = Vk;
+    }
+  }
+  const double sumH = group_precise_sum(avgH), sumV = group_precise_sum(avgV);  // :175
+  const double lackSum = group_precise_sum(accL);
+  if (lane == 0) {
+    const double tw = totW.get();
+    const double aH = __ddiv_rn(sumH, tw), aV = __ddiv_rn(sumV, tw);            // :176-177
+    const double nExp = exp2(aH);                                               // :181
+    const double cLnMaxV = 0.34657359027997265470861606072909;                  // SRMath::_cLnSqrt2
+    const double lnV = (aV == 0) ? -746.0 : log(aV);                            // :27-29
+    const double n1 = (double)(kb.nValidTargets + 1);
+    const double vComp = __ddiv_rn(1.0, __dadd_rn(__dsub_rn(cLnMaxV, lnV), __ddiv_rn(cLnMaxV, __dmul_rn(n1, n1))));
+    const double lack = -lackSum;                                               // :201
+    priority[b * kb.Q + i] = __dmul_rn(__dmul_rn(lack, pow(vComp, 9.0)), pow(nExp, -2.0));  // :207
+    if (det.lack) det.lack[b * kb.Q + i] = lack;
+  }
+}
+
+void launch_eval_staged(const DeviceKB &kb, const QuizPool &qp, int64_t n, const int64_t *dSlots, double *dPriority,
+                        const EvalDetail &det, const EvalConfig &cfg, cudaStream_t st);
+
+void launch_eval_questions(const DeviceKB &kb, const QuizPool &qp, int64_t n, const int64_t *dSlots,
+                           double *dPriority, const EvalDetail &det, const EvalConfig &cfg, cudaStream_t st) {
+  if (n <= 0) return;
+  if (cfg.which == 1) {
+    dim3 grid((unsigned)kb.Q, (unsigned)((n + 31) / 32));
+    k_eval_exact<<<grid, 128, 0, st>>>(kb, qp, n, dSlots, dPriority, det);
+    count_launch();
+  } else {
+    launch_eval_staged(kb, qp, n, dSlots, dPriority, det, cfg, st);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Question selection: CpuEngine::NextQuestionSpec (CpuEngine.cpp:337-415) after the evaluation. One CTA per quiz.
+//   chunks = CalcSplit(Q, 8W); per chunk a scalar-Kahan running sum over its questions, asked/gap questions repeat
+//   the running value (CEEvalQsSubtaskConsider.cpp:54-58,212-214); grand totals = scalar Kahan over the chunks' last
+//   values (CpuEngine.cpp:362-374); r = totG * u64 / (2^64-1) (SRDoubleNumber.h:35-39); upper_bound over chunks,
+//   upper_bound inside the chunk (:380-400); asked/gap -> nearest available question (BaseEngine.cpp:60-124).
+int64_t select_chunk_count(int64_t Q, int W) { return split_count(Q, (int64_t)W * 8); }
+
+__device__ __forceinline__ uint64_t avail_word(const DeviceKB &kb, const uint64_t *asked, int64_t w) {
+  // bits of (qgaps | asked) for questions 64w..64w+63, complemented; questions >= Q read as gaps (GapTracker.h:12-15)
+  uint64_t g = 0;
+  if (kb.qgaps) g = (uint64_t)kb.qgaps[2 * w] | ((uint64_t)kb.qgaps[2 * w + 1] << 32);
+  const int64_t rem = kb.Q - 64 * w;
+  if (rem < 64) g |= ~0ull << rem;
+  return ~(g | asked[w]);
+}
+
+__device__ int64_t find_nearest_question(const DeviceKB &kb, const uint64_t *asked, int64_t iMiddle) {
+  const uint32_t dInf = 200;
+  const int64_t iPack = iMiddle >> 6;
+  const uint32_t iWithin = (uint32_t)(iMiddle & 63);
+  const uint64_t available = avail_word(kb, asked, iPack);
+  if (available != 0) {
+    const uint64_t baseMask = (1ull << iWithin) - 1;
+    const uint64_t higher = available & ~baseMask, lower = available & baseMask;
+    const uint32_t dHigher = higher ? (uint32_t)(__ffsll((long long)higher) - 1) - iWithin : dInf;
+    const uint32_t dLower = lower ? iWithin - (uint32_t)(63 - __clzll((long long)lower)) : dInf;
+    if (dHigher < dLower) return iMiddle + dHigher;
+    return iMiddle - dLower;
+  }
+  const int64_t limPack = (kb.Q + 63) >> 6;
+  int64_t i = 1;
+  while (iPack >= i && iPack + i < limPack) {
+    const uint64_t availLeft = avail_word(kb, asked, iPack - i), availRight = avail_word(kb, asked, iPack + i);
+    if ((availLeft | availRight) == 0) { i++; continue; }
+    const uint32_t dHigher = availRight ? (uint32_t)(__ffsll((long long)availRight) - 1) + 64 - iWithin : dInf;
+    const uint32_t dLower = availLeft ? iWithin + 64 - (uint32_t)(63 - __clzll((long long)availLeft)) : dInf;
+    if (dHigher < dLower) return iMiddle + dHigher + ((i - 1) << 6);
+    return iMiddle - dLower - ((i - 1) << 6);
+  }
+  while (iPack >= i) {
+    const uint64_t availLeft = avail_word(kb, asked, iPack - i);
+    if (!availLeft) { i++; continue; }
+    const uint32_t dLower = iWithin + 64 - (uint32_t)(63 - __clzll((long long)availLeft));
+    return iMiddle - dLower - ((i - 1) << 6);
+  }
+  while (iPack + i < limPack) {
+    const uint64_t availRight = avail_word(kb, asked, iPack + i);
+    if (!availRight) { i++; continue; }
+    const uint32_t dHigher = (uint32_t)(__ffsll((long long)availRight) - 1) + 64 - iWithin;
+    return iMiddle + dHigher + ((i - 1) << 6);
+  }
+  return -1;
+}
+
+__device__ __forceinline__ int64_t upper_bound_d(const double *a, int64_t n, double v) {
+  int64_t lo = 0, len = n;
+  while (len > 0) {
+    const int64_t half = len >> 1;
+    if (!(v < a[lo + half])) { lo += half + 1; len -= half + 1; } else len = half;
+  }
+  return lo;
+}
+
+// Shared memory: nChunks grand totals. runLength[n*Q] is required (the in-chunk binary search reads it back).
+__global__ void __launch_bounds__(256) k_select_question(DeviceKB kb, QuizPool qp, const int64_t *__restrict__ slots,
+                                                         const double *__restrict__ priority,
+                                                         const uint64_t *__restrict__ randoms, int W,
+                                                         double *__restrict__ runLength, double *__restrict__ grandOut,
+                                                         int64_t *__restrict__ questions, int setActive) {
+  extern __shared__ double sGrand[];
+  const int64_t b = blockIdx.x, slot = slots[b], Q = kb.Q;
+  const uint64_t *asked = qp.asked + slot * qp.askedWords;
+  const double *pri = priority + b * Q;
+  const int64_t nW = (int64_t)W * 8, nChunks = split_count(Q, nW);
+  for (int64_t c = threadIdx.x; c < nChunks; c += blockDim.x) {
+    const int64_t first = split_start(Q, nW, c), limit = split_start(Q, nW, c + 1);
+    Kahan run; run.init(0.0);
+    for (int64_t i = first; i < limit; i++) {
+      if (!(bit32(kb.qgaps, i) || bit64(asked, i))) run.add(pri[i]);
+      runLength[b * Q + i] = run.get();
+    }
+    sGrand[c] = run.get();
+  }
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  Kahan tot; tot.init(0.0);
+  for (int64_t c = 0; c < nChunks; c++) {  // CpuEngine.cpp:362-374
+    tot.add(sGrand[c]);
+    sGrand[c] = tot.get();
+    if (grandOut) grandOut[b * nChunks + c] = sGrand[c];
+  }
+  if (!questions) return;
+  const double totG = sGrand[nChunks - 1];
+  // SRDoubleNumber::MakeRandom: upper * rnd / max (left to right, both factors converted to double)
+  const double sel = __ddiv_rn(__dmul_rn(totG, __ull2double_rn(randoms[b])), __ull2double_rn(~0ull));
+  const int64_t iWorker = upper_bound_d(sGrand, nChunks, sel);
+  int64_t chosen;
+  if (iWorker >= nChunks) {
+    chosen = Q - 1;                                                       // :382-386
+  } else {
+    const double inWorker = __dsub_rn(sel, iWorker == 0 ? 0.0 : sGrand[iWorker - 1]);  // :388
+    const int64_t first = split_start(Q, nW, iWorker), limit = split_start(Q, nW, iWorker + 1);
+    chosen = first + upper_bound_d(runLength + b * Q + first, limit - first, inWorker);               // :391
+    if (chosen >= limit) chosen = limit - 1;                              // :392-400
+  }
+  if (bit32(kb.qgaps, chosen) || bit64(asked, chosen)) chosen = find_nearest_question(kb, asked, chosen);  // :404-406
+  questions[b] = chosen;
+  if (setActive && chosen >= 0) qp.active[slot] = chosen;                 // :412
+}
+
+void launch_select_question(const DeviceKB &kb, const QuizPool &qp, int64_t n, const int64_t *dSlots,
+                            const double *dPriority, const uint64_t *dRandoms, int W, double *dRunLength,
+                            double *dGrand, int64_t *dQuestions, int setActive, cudaStream_t st) {
+  if (n <= 0) return;
+  const int64_t nChunks = select_chunk_count(kb.Q, W);
+  int block = 32;
+  while (block < nChunks && block < 256) block <<= 1;
+  k_select_question<<<(unsigned)n, block, sizeof(double) * (size_t)nChunks, st>>>(
+      kb, qp, dSlots, dPriority, dRandoms, W, dRunLength, dGrand, dQuestions, setActive);
+  count_launch();
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// ListTopTargets: CEListTopTargetsAlgorithm::RunHeapifyBased (CEListTopTargetsAlgorithm.cpp:30-97) with the piece
+// heaps of CEHeapifyPriorsSubtaskMake (CEHeapifyPriorsSubtaskMake.cpp:42-87). Ties between equal probabilities are
+// resolved by the mechanics of libstdc++'s make_heap / pop_heap and SRHeapHelper::Down (SRHeap.h:12-37), so those
+// are restated here operation by operation; one thread builds one piece heap, thread 0 runs the merge.
+struct Rated { int64_t iTarget; double prob; };      // RatedTarget, Interface/PqaCommon.h:54-61
+struct HeadItem { double prob; int64_t iSource; };   // RatingsHeapItem, RatingsHeap.h:11-20
+
+template <typename TItem>
+__device__ void heap_push(TItem *first, int64_t hole, int64_t top, TItem value) {  // std::__push_heap
+  int64_t parent = (hole - 1) / 2;
+  while (hole > top && first[parent].prob < value.prob) {
+    first[hole] = first[parent];
+    hole = parent;
+    parent = (hole - 1) / 2;
+  }
+  first[hole] = value;
+}
+template <typename TItem>
+__device__ void heap_adjust(TItem *first, int64_t hole, int64_t len, TItem value) {  // std::__adjust_heap
+  const int64_t top = hole;
+  int64_t child = hole;
+  while (child < (len - 1) / 2) {
+    child = 2 * (child + 1);
+    if (first[child].prob < first[child - 1].prob) child--;
+    first[hole] = first[child];
+    hole = child;
+  }
+  if ((len & 1) == 0 && child == (len - 2) / 2) {
+    child = 2 * (child + 1);
+    first[hole] = first[child - 1];
+    hole = child - 1;
+  }
+  heap_push(first, hole, top, value);
+}
+template <typename TItem>
+__device__ void heap_make(TItem *first, int64_t len) {  // std::make_heap
+  if (len < 2) return;
+  for (int64_t parent = (len - 2) / 2;; parent--) {
+    const TItem value = first[parent];
+    heap_adjust(first, parent, len, value);
+    if (parent == 0) return;
+  }
+}
+template <typename TItem>
+__device__ void heap_pop(TItem *first, int64_t len) {  // std::pop_heap
+  if (len > 1) {
+    const TItem value = first[len - 1];
+    first[len - 1] = first[0];
+    heap_adjust(first, 0, len - 1, value);
+  }
+}
+__device__ void head_down(HeadItem *first, int64_t len) {  // SRHeapHelper::Down, SRHeap.h:16-37
+  int64_t cur = 0;
+  for (;;) {
+    const int64_t c1 = 2 * cur + 1;
+    if (c1 >= len) return;
+    const int64_t c2 = c1 + 1;
+    if (c2 >= len) {
+      if (first[cur].prob < first[c1].prob) { const HeadItem t = first[cur]; first[cur] = first[c1]; first[c1] = t; }
+      return;
+    }
+    const int64_t hi = (first[c2].prob < first[c1].prob) ? c1 : c2;
+    if (!(first[cur].prob < first[hi].prob)) return;
+    const HeadItem t = first[cur]; first[cur] = first[hi]; first[hi] = t;
+    cur = hi;
+  }
+}
+
+// Shared memory: W head items, W starts, W limits, then (if useSmem) T Rated items.
+__global__ void __launch_bounds__(256) k_list_top_targets(DeviceKB kb, QuizPool qp, const int64_t *__restrict__ slots,
+                                                          int W, int64_t maxCount, Rated *__restrict__ scratch,
+                                                          int useSmem, Rated *__restrict__ dest,
+                                                          int64_t *__restrict__ counts) {
+  extern __shared__ __align__(16) unsigned char smRaw[];
+  HeadItem *head = (HeadItem *)smRaw;
+  int64_t *starts = (int64_t *)(head + W);
+  int64_t *limits = starts + W;
+  Rated *ratings = useSmem ? (Rated *)(limits + W) : scratch + (int64_t)blockIdx.x * kb.T;
+  const int64_t b = blockIdx.x, slot = slots[b], T = kb.T;
+  const double *prior = qp.priors + slot * qp.Tp;
+  const int64_t nPieces = split_count(T, W);
+  for (int64_t p = threadIdx.x; p < nPieces; p += blockDim.x) {
+    const int64_t first = split_start(T, W, p), limit = split_start(T, W, p + 1);
+    int64_t sel = first;
+    for (int64_t j = first; j < limit; j++) {            // CEHeapifyPriorsSubtaskMake.cpp:42-53
+      if (bit32(kb.tgaps, j)) continue;
+      const double prob = prior[j];
+      if (prob <= 0) continue;
+      ratings[sel].prob = prob; ratings[sel].iTarget = j; sel++;
+    }
+    starts[p] = first; limits[p] = sel;
+    heap_make(ratings + first, sel - first);             // :85-86
+  }
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  int64_t nHh = 0;
+  for (int64_t p = 0; p < nPieces; p++) {                // CEListTopTargetsAlgorithm.cpp:57-66
+    if (limits[p] == starts[p]) continue;
+    head[nHh].iSource = p; head[nHh].prob = ratings[starts[p]].prob; nHh++;
+  }
+  heap_make(head, nHh);
+  int64_t listed = maxCount;
+  Rated *out = dest + b * maxCount;
+  for (int64_t i = 0; i < maxCount; i++) {               // :68-94
+    if (nHh == 0) { listed = i; break; }
+    const int64_t piece = head[0].iSource, start = starts[piece], lim = limits[piece];
+    out[i].prob = head[0].prob;
+    out[i].iTarget = ratings[start].iTarget;
+    if (start + 1 == lim) { heap_pop(head, nHh); nHh--; continue; }
+    heap_pop(ratings + start, lim - start);
+    limits[piece]--;
+    head[0].prob = ratings[start].prob;
+    head_down(head, nHh);
+  }
+  counts[b] = listed;
+}
+
+void launch_list_top_targets(const DeviceKB &kb, const QuizPool &qp, int64_t n, const int64_t *dSlots, int W,
+                             int64_t maxCount, void *dScratch, void *dDest, int64_t *dCounts, cudaStream_t st) {
+  if (n <= 0) return;
+  const size_t fixed = (size_t)W * (sizeof(HeadItem) + 2 * sizeof(int64_t));
+  const size_t items = (size_t)kb.T * sizeof(Rated);
+  const int useSmem = fixed + items <= 200 * 1024;
+  const size_t smem = fixed + (useSmem ? items : 0);
+  static bool attrSet = false;
+  if (!attrSet) {
+    cudaFuncSetAttribute(k_list_top_targets, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    attrSet = true;
+  }
+  int block = 32;
+  while (block < W && block < 256) block <<= 1;
+  k_list_top_targets<<<(unsigned)n, block, smem, st>>>(kb, qp, dSlots, W, maxCount, (Rated *)dScratch, useSmem,
+                                                       (Rated *)dDest, dCounts);
+  count_launch();
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// RecordQuizTarget / Train: CETrainOperation::{ProcessOne,Perform1,Perform2} (CETrainOperation.cpp:15-83) with the
+// increments of CETrainTaskNumSpec.h:24-32. One thread applies one (question, target) cell group's operations in
+// sequence order, so any interleaving of quizzes that hits the same cell reproduces the sequential result.
+__global__ void k_train_ops(DeviceKB kb, const TrainOp *__restrict__ ops, const int64_t *__restrict__ groupStart,
+                            int64_t nGroups) {
+  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= nGroups) return;
+  for (int64_t o = groupStart[g]; o < groupStart[g + 1]; o++) {
+    const TrainOp op = ops[o];
+    const double b = op.amount;
+    double *cellD = kb.mD + op.q * kb.Tp + op.target;
+    double *cellA0 = kb.sA + (op.q * kb.K + op.a0) * kb.Tp + op.target;
+    if (op.a1 < 0 || op.a1 == op.a0) {
+      // ProcessOne (:15-26) with (2b, b^2), or the doubled step (:34-36) with (4b, 4b^2)
+      const double twoB = (op.a1 < 0) ? __dmul_rn(2.0, b) : __dmul_rn(4.0, b);
+      const double bSq = (op.a1 < 0) ? __dmul_rn(b, b) : __dmul_rn(4.0, __dmul_rn(b, b));
+      const double aSq = *cellA0;
+      const double addend = __dadd_rn(__dmul_rn(sqrt(aSq), twoB), bSq);
+      *cellA0 = __dadd_rn(aSq, addend);
+      *cellD = __dadd_rn(*cellD, addend);
+    } else {
+      // same question, two different answers (:38-47): D receives addend0 twice, as in the reference
+      double *cellA1 = kb.sA + (op.q * kb.K + op.a1) * kb.Tp + op.target;
+      const double twoB = __dmul_rn(2.0, b), bSq = __dmul_rn(b, b);
+      const double a0Sq = *cellA0, a1Sq = *cellA1;
+      const double add0 = __dadd_rn(__dmul_rn(sqrt(a0Sq), twoB), bSq);
+      const double add1 = __dadd_rn(__dmul_rn(sqrt(a1Sq), twoB), bSq);
+      *cellA0 = __dadd_rn(a0Sq, add0);
+      *cellA1 = __dadd_rn(a1Sq, add1);
+      *cellD = __dadd_rn(*cellD, __dadd_rn(add0, add0));
+    }
+  }
+}
+void launch_train_ops(const DeviceKB &kb, const TrainOp *dOps, const int64_t *dGroupStart, int64_t nGroups,
+                      cudaStream_t st) {
+  if (nGroups <= 0) return;
+  k_train_ops<<<(unsigned)((nGroups + 127) / 128), 128, 0, st>>>(kb, dOps, dGroupStart, nGroups);
+  count_launch();
+}
+
+__global__ void k_add_vb(DeviceKB kb, const int64_t *__restrict__ targets, const double *__restrict__ amounts,
+                         const int64_t *__restrict__ groupStart, int64_t nGroups) {
+  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= nGroups) return;
+  const int64_t first = groupStart[g], limit = groupStart[g + 1];
+  double v = kb.vB[targets[first]];
+  for (int64_t o = first; o < limit; o++) v = __dadd_rn(v, amounts[o]);   // CpuEngine.cpp:462
+  kb.vB[targets[first]] = v;
+}
+void launch_add_vb(const DeviceKB &kb, const int64_t *dTargets, const double *dAmounts, const int64_t *dGroupStart,
+                   int64_t nGroups, cudaStream_t st) {
+  if (nGroups <= 0) return;
+  k_add_vb<<<(unsigned)((nGroups + 127) / 128), 128, 0, st>>>(kb, dTargets, dAmounts, dGroupStart, nGroups);
+  count_launch();
+}
+
+} // namespace pqa

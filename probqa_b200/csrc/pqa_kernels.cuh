@@ -25,6 +25,7 @@ struct DeviceKB {
 // Per-quiz state resident in HBM, addressed by quiz slot.
 struct QuizPool {
   double *priors;          // [slot][Tp]  normalised posterior (CEQuiz.decl.h _pPriorMants); padding = +0
+  double *logPriors;       // [slot][Tp]  log2 of priors (derived; rewritten whenever priors are)
   uint64_t *asked;         // [slot][askedWords]  bit i = question i already answered (CEBaseQuiz _isQAsked)
   int64_t *active;         // [slot] active question or -1 (BaseQuiz.h _activeQuestion)
   int64_t askedWords;      // ceil(Q/64)
@@ -47,10 +48,25 @@ void launch_start_quiz(const DeviceKB &kb, const QuizPool &qp, int64_t n, const 
 // dAnswers[n]; W = loose worker count max(1, hwc-1).
 void launch_record_answer(const DeviceKB &kb, const QuizPool &qp, int64_t n, const int64_t *dSlots,
                           const int64_t *dAnswers, int W, cudaStream_t st);
+// Renormalisation-free refresh of logPriors after priors were overwritten from the host.
+void launch_refresh_log_priors(const QuizPool &qp, int64_t n, const int64_t *dSlots, cudaStream_t st);
+
 // CEEvalQsSubtaskConsider::Run (CEEvalQsSubtaskConsider.cpp:41-217) for every (quiz, question):
-// dPriority[n*Q] (NaN where asked/gap). which: 1 generic, 2 staged (TMA + smem), 0 auto.
+// dPriority[n*Q] (NaN where asked/gap).
+//   which 1 = exact : every rounding of the reference reproduced (4-lane Kahan order, Log2Hot, IEEE divides);
+//                     W/H/V/lack bit-identical to CpuEngine, priority up to libm pow/exp2/log differences.
+//   which 2 = staged: the throughput kernel (bulk-async/TMA staging of the sA/mD slab into shared memory, log-split
+//                     entropy, warp-tree sums); results within the tolerance stated in DESIGN.md.
+//   which 0 = auto (= 2).
+// chunkTargets: 0 = auto; otherwise forces the number of targets staged per shared-memory chunk (tests).
+struct EvalConfig {
+  int which = 0;
+  int smCount = 148;
+  int64_t chunkTargets = 0;
+  int64_t quizzesPerCta = 0;   // 0 = auto
+};
 void launch_eval_questions(const DeviceKB &kb, const QuizPool &qp, int64_t n, const int64_t *dSlots,
-                           double *dPriority, const EvalDetail &det, int which, int smCount, cudaStream_t st);
+                           double *dPriority, const EvalDetail &det, const EvalConfig &cfg, cudaStream_t st);
 // CpuEngine::NextQuestionSpec (CpuEngine.cpp:337-415) after the evaluation: chunk run-lengths, grand totals,
 // weighted draw with dRandoms[n], nearest unasked question; writes dQuestions[n] and the quiz' active question.
 // dRunLength[n*Q] / dGrand[n*nChunks] optional outputs. setActive=0 leaves the quiz untouched.
@@ -58,20 +74,25 @@ void launch_select_question(const DeviceKB &kb, const QuizPool &qp, int64_t n, c
                             const double *dPriority, const uint64_t *dRandoms, int W, double *dRunLength,
                             double *dGrand, int64_t *dQuestions, int setActive, cudaStream_t st);
 int64_t select_chunk_count(int64_t Q, int W);
-// CEListTopTargetsAlgorithm::RunHeapifyBased (CEListTopTargetsAlgorithm.cpp:30-97). dScratch: n*T 16-byte items.
+// CEListTopTargetsAlgorithm::RunHeapifyBased (CEListTopTargetsAlgorithm.cpp:30-97). dScratch: n*T 16-byte items
+// (used only when T items do not fit in shared memory). dDest: n*maxCount {int64 iTarget; double prob}.
 void launch_list_top_targets(const DeviceKB &kb, const QuizPool &qp, int64_t n, const int64_t *dSlots, int W,
                              int64_t maxCount, void *dScratch, void *dDest, int64_t *dCounts, cudaStream_t st);
 
-// CETrainOperation (CETrainOperation.cpp:15-83) for a list of pre-paired operations, applied per (question,
-// target) cell group in sequence order. See TrainOp.
+// CETrainOperation (CETrainOperation.cpp:15-83). The host splits every Perform2/Perform1 of the reference's
+// sequential loop into per-cell operations and groups them by (question, target) cell group, keeping sequence
+// order inside a group; one thread applies one group.
 struct TrainOp {
-  int64_t q0, a0, q1, a1;  // q1 = -1 for a single; (q0,a0)==(q1,a1) = the doubled step; q0==q1,a0!=a1 = the 3-add form
+  int64_t q, a0, a1;       // a1 = -1: ProcessOne on (q,a0); a1 == a0: the doubled step (4b, 4b^2);
+                           // a1 != a0: same question, two answers (CETrainOperation.cpp:38-47, D += 2*addend0)
   int64_t target;
   double amount;
 };
-void launch_train_ops(const DeviceKB &kb, int64_t nOps, const TrainOp *dOps, const int64_t *dOrder,
-                      const int64_t *dGroupStart, int64_t nGroups, cudaStream_t st);
-void launch_add_vb(const DeviceKB &kb, int64_t n, const int64_t *dTargets, const double *dAmounts, cudaStream_t st);
+void launch_train_ops(const DeviceKB &kb, const TrainOp *dOps, const int64_t *dGroupStart, int64_t nGroups,
+                      cudaStream_t st);
+// vB[target] += amount, one thread per distinct target applying its amounts in sequence order.
+void launch_add_vb(const DeviceKB &kb, const int64_t *dTargets, const double *dAmounts, const int64_t *dGroupStart,
+                   int64_t nGroups, cudaStream_t st);
 
 void launch_set_active(const QuizPool &qp, int64_t n, const int64_t *dSlots, const int64_t *dQuestions, cudaStream_t st);
 void launch_flush_l2(void *buf, size_t bytes, cudaStream_t st);

@@ -1,0 +1,543 @@
+"""ctypes host binding of libPqaCore.so (the B200 engine), mirroring the class and method names of the reference's
+own Python client (Interop/Python/ProbQAInterop/ProbQA.py:300-760: PqaEngineFactory.create_cpu_engine, PqaEngine.
+start_quiz / next_question / record_answer / list_top_targets / record_quiz_target / train / release_quiz ...) so that
+code written against the reference binding runs unchanged, plus numpy-array batch methods over the additive entry
+points of include/PqaB200Ext.h.
+
+There is no fallback: if the shared library is missing or no CUDA device is visible, construction raises.
+Nothing in here imports or calls oracle/.
+"""
+import ctypes as C
+import os
+from enum import Enum
+from typing import List, Tuple
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libPqaCore.so")
+
+
+class CiEngineDefinition(C.Structure):  # PqaCInterop.h:10-19, pack 8
+    _pack_ = 8
+    _fields_ = [("nAnswers", C.c_int64), ("nQuestions", C.c_int64), ("nTargets", C.c_int64),
+                ("precType", C.c_uint8), ("precExponent", C.c_uint16), ("precMantissa", C.c_uint32),
+                ("initAmount", C.c_double), ("memPoolMaxBytes", C.c_uint64)]
+
+
+class CiAnsweredQuestion(C.Structure):  # :21-24
+    _pack_ = 8
+    _fields_ = [("iQuestion", C.c_int64), ("iAnswer", C.c_int64)]
+
+
+class CiEngineDimensions(C.Structure):  # :26-30
+    _pack_ = 8
+    _fields_ = [("nAnswers", C.c_int64), ("nQuestions", C.c_int64), ("nTargets", C.c_int64)]
+
+
+class CiRatedTarget(C.Structure):  # :32-35
+    _pack_ = 8
+    _fields_ = [("iTarget", C.c_int64), ("prob", C.c_double)]
+
+
+class CiB200Options(C.Structure):  # PqaB200Ext.h
+    _pack_ = 8
+    _fields_ = [("device", C.c_int32), ("emulatedWorkers", C.c_int32), ("rngSeed", C.c_uint64),
+                ("initialQuizCapacity", C.c_int64)]
+
+
+RATED_DTYPE = np.dtype([("iTarget", np.int64), ("prob", np.float64)])
+
+_vp, _i64, _u64, _dbl = C.c_void_p, C.c_int64, C.c_uint64, C.c_double
+_pi64, _pu64, _pd = C.POINTER(C.c_int64), C.POINTER(C.c_uint64), C.POINTER(C.c_double)
+_pvp = C.POINTER(C.c_void_p)
+
+# name -> (restype, argtypes); every symbol declared in include/PqaCInterop.h and include/PqaB200Ext.h
+SIGNATURES = {
+    "CiDebugBreak": (None, []),
+    "Logger_Init": (C.c_uint8, [_pvp, C.c_char_p]),
+    "CiReleaseString": (None, [_vp]),
+    "CiGetPqaEngineFactory": (_vp, []),
+    "PqaEngineFactory_CreateCpuEngine": (_vp, [_vp, _pvp, C.POINTER(CiEngineDefinition)]),
+    "PqaEngineFactory_LoadCpuEngine": (_vp, [_vp, _pvp, C.c_char_p, _u64]),
+    "CiReleasePqaError": (None, [_vp]),
+    "PqaError_ToString": (_vp, [_vp, C.c_uint8]),
+    "CiReleasePqaEngine": (None, [_vp]),
+    "PqaEngine_Train": (_vp, [_vp, _i64, C.POINTER(CiAnsweredQuestion), _i64, _dbl]),
+    "PqaEngine_QuestionPermFromComp": (C.c_uint8, [_vp, _i64, _pi64]),
+    "PqaEngine_QuestionCompFromPerm": (C.c_uint8, [_vp, _i64, _pi64]),
+    "PqaEngine_TargetPermFromComp": (C.c_uint8, [_vp, _i64, _pi64]),
+    "PqaEngine_TargetCompFromPerm": (C.c_uint8, [_vp, _i64, _pi64]),
+    "PqaEngine_QuizPermFromComp": (C.c_uint8, [_vp, _i64, _pi64]),
+    "PqaEngine_QuizCompFromPerm": (C.c_uint8, [_vp, _i64, _pi64]),
+    "PqaEngine_EnsurePermQuizGreater": (C.c_uint8, [_vp, _i64]),
+    "PqaEngine_RemapQuizPermId": (C.c_uint8, [_vp, _i64, _i64]),
+    "PqaEngine_GetTotalQuestionsAsked": (_u64, [_vp, _pvp]),
+    "PqaEngine_CopyDims": (C.c_uint8, [_vp, C.POINTER(CiEngineDimensions)]),
+    "PqaEngine_StartQuiz": (_i64, [_vp, _pvp]),
+    "PqaEngine_ResumeQuiz": (_i64, [_vp, _pvp, _i64, C.POINTER(CiAnsweredQuestion)]),
+    "PqaEngine_NextQuestion": (_i64, [_vp, _pvp, _i64]),
+    "PqaEngine_RecordAnswer": (_vp, [_vp, _i64, _i64]),
+    "PqaEngine_ClearOldQuizzes": (_vp, [_vp, _i64, _dbl]),
+    "PqaEngine_GetActiveQuestionId": (_i64, [_vp, _pvp, _i64]),
+    "PqaEngine_SetActiveQuestion": (_vp, [_vp, _i64, _i64]),
+    "PqaEngine_ListTopTargets": (_i64, [_vp, _pvp, _i64, _i64, C.POINTER(CiRatedTarget)]),
+    "PqaEngine_RecordQuizTarget": (_vp, [_vp, _i64, _i64, _dbl]),
+    "PqaEngine_ReleaseQuiz": (_vp, [_vp, _i64]),
+    "PqaEngine_SaveKB": (_vp, [_vp, C.c_char_p, C.c_uint8]),
+    "PqaEngine_StartMaintenance": (_vp, [_vp, C.c_bool]),
+    "PqaEngine_FinishMaintenance": (_vp, [_vp]),
+    "PqaEngine_AddQsTs": (_vp, [_vp, _i64, _vp, _i64, _vp]),
+    "PqaEngine_RemoveQuestions": (_vp, [_vp, _i64, _pi64]),
+    "PqaEngine_RemoveTargets": (_vp, [_vp, _i64, _pi64]),
+    "PqaEngine_Compact": (_vp, [_vp, _pi64, C.POINTER(_pi64), _pi64, C.POINTER(_pi64)]),
+    "CiReleaseCompaction": (None, [_pi64]),
+    "PqaEngine_Shutdown": (_vp, [_vp, C.c_char_p]),
+    "PqaEngine_SetLogger": (_vp, [_vp, _vp]),
+    # ---- PqaB200Ext.h
+    "PqaB200_CreateEngine": (_vp, [_pvp, C.POINTER(CiEngineDefinition), C.POINTER(CiB200Options)]),
+    "PqaB200_GetEmulatedWorkers": (C.c_int32, [_vp]),
+    "PqaB200_GetDevice": (C.c_int32, [_vp]),
+    "PqaB200_BuildInfo": (C.c_char_p, []),
+    "PqaEngine_CopyATargets": (_vp, [_vp, _i64, _i64, _i64, _pd]),
+    "PqaEngine_CopyDTargets": (_vp, [_vp, _i64, _i64, _pd]),
+    "PqaEngine_CopyBTargets": (_vp, [_vp, _i64, _pd]),
+    "PqaB200_UploadKB": (_vp, [_vp, _pd, _pd, _pd]),
+    "PqaB200_DownloadKB": (_vp, [_vp, _pd, _pd, _pd]),
+    "PqaEngine_StartQuizBatch": (_vp, [_vp, _i64, _pi64]),
+    "PqaEngine_NextQuestionBatch": (_vp, [_vp, _i64, _pi64, _pu64, _pi64, _pvp]),
+    "PqaEngine_RecordAnswerBatch": (_vp, [_vp, _i64, _pi64, _pi64]),
+    "PqaEngine_SetActiveQuestionBatch": (_vp, [_vp, _i64, _pi64, _pi64]),
+    "PqaEngine_ListTopTargetsBatch": (_vp, [_vp, _i64, _pi64, _i64, _vp, _pi64]),
+    "PqaEngine_RecordQuizTargetBatch": (_vp, [_vp, _i64, _pi64, _pi64, _pd]),
+    "PqaEngine_ReleaseQuizBatch": (_vp, [_vp, _i64, _pi64]),
+    "PqaB200_CopyQuizPriors": (_vp, [_vp, _i64, _pd]),
+    "PqaB200_SetQuizPriors": (_vp, [_vp, _i64, _pd]),
+    "PqaB200_EvalQuestions": (_vp, [_vp, _i64, _pi64, _pd, _pd, _pd, _pi64]),
+    "PqaB200_EvalQuestionsDetailed": (_vp, [_vp, _i64, _pd, _pd, _pd, _pd, _pd]),
+    "PqaB200_SetEvalKernel": (_vp, [_vp, C.c_int32]),
+    "PqaB200_SetEvalTuning": (_vp, [_vp, C.c_int32, _i64, _i64]),
+    "PqaB200_ResidentBind": (_vp, [_vp, _i64, _pi64, _pu64]),
+    "PqaB200_ResidentStep": (_vp, [_vp]),
+    "PqaB200_ResidentFetch": (_vp, [_vp, _pi64]),
+    "PqaB200_ResidentLastEvalMs": (_dbl, [_vp]),
+    "PqaB200_Synchronize": (_vp, [_vp]),
+    "PqaB200_EventCreate": (_vp, []),
+    "PqaB200_EventDestroy": (None, [_vp]),
+    "PqaB200_EventRecord": (_vp, [_vp, _vp]),
+    "PqaB200_EventSynchronize": (_vp, [_vp]),
+    "PqaB200_EventElapsedMs": (_dbl, [_vp, _vp]),
+    "PqaB200_KernelLaunchCount": (_u64, [_vp]),
+    "PqaB200_FlushL2": (_vp, [_vp]),
+}
+
+_lib = None
+
+
+def load_library(path: str = None):
+    """Loads libPqaCore.so and declares every entry point. Raises if the library is missing."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or os.environ.get("PQA_B200_LIB", LIB_PATH)
+    if not os.path.exists(p):
+        raise FileNotFoundError(
+            "%s not found: build it with `python -m probqa_b200.build` (there is no CPU fallback)" % p)
+    lib = C.CDLL(p)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    if path is None:
+        _lib = lib
+    return lib
+
+
+class PqaException(Exception):
+    def __init__(self, error: "PqaError"):
+        super().__init__(error.to_string(True))
+        self.error = error
+
+
+class PrecisionType(Enum):  # Interface/PqaCommon.h:17-24
+    NONE = 0
+    FLOAT = 1
+    FLOAT_PAIR = 2
+    DOUBLE = 3
+    DOUBLE_PAIR = 4
+    ARBITRARY = 5
+
+
+class AnsweredQuestion:
+    def __init__(self, i_question, i_answer):
+        self.i_question = i_question
+        self.i_answer = i_answer
+
+    def __repr__(self):
+        return "[AnsweredQuestion: i_question=%d, i_answer=%d]" % (self.i_question, self.i_answer)
+
+
+class RatedTarget:
+    def __init__(self, i_target: int, prob: float):
+        self.i_target = i_target
+        self.prob = prob
+
+    def __repr__(self):
+        return "[RatedTarget: i_target=%d, prob=%r]" % (self.i_target, self.prob)
+
+
+class EngineDefinition:
+    def __init__(self, n_answers: int, n_questions: int, n_targets: int, init_amount=1.0,
+                 prec_type=PrecisionType.DOUBLE, prec_exponent=11, prec_mantissa=53, mem_pool_max_bytes=512 << 20):
+        self.n_answers, self.n_questions, self.n_targets = n_answers, n_questions, n_targets
+        self.init_amount = init_amount
+        self.prec_type, self.prec_exponent, self.prec_mantissa = prec_type, prec_exponent, prec_mantissa
+        self.mem_pool_max_bytes = mem_pool_max_bytes
+
+    def to_c(self) -> CiEngineDefinition:
+        return CiEngineDefinition(self.n_answers, self.n_questions, self.n_targets, self.prec_type.value,
+                                  self.prec_exponent, self.prec_mantissa, self.init_amount, self.mem_pool_max_bytes)
+
+
+class EngineDimensions:
+    def __init__(self, n_answers: int, n_questions: int, n_targets: int):
+        self.n_answers, self.n_questions, self.n_targets = n_answers, n_questions, n_targets
+
+    def __repr__(self):
+        return "[n_answers=%d, n_questions=%d, n_targets=%d]" % (self.n_answers, self.n_questions, self.n_targets)
+
+
+class PqaError:
+    """Owns a native error object (NULL = success), like ProbQA.py:399-421."""
+
+    @staticmethod
+    def factor(c_err):
+        return PqaError(c_err) if c_err else None
+
+    def __init__(self, c_err):
+        self.c_err = C.c_void_p(c_err) if not isinstance(c_err, C.c_void_p) else c_err
+
+    def __del__(self):
+        if getattr(self, "c_err", None) and self.c_err.value and _lib is not None:
+            _lib.CiReleasePqaError(self.c_err)
+            self.c_err = None
+
+    def __repr__(self):
+        return self.to_string(True)
+
+    def to_string(self, with_params: bool) -> str:
+        lib = load_library()
+        s = lib.PqaError_ToString(self.c_err, 1 if with_params else 0)
+        try:
+            return C.cast(s, C.c_char_p).value.decode("utf-8", "replace")
+        finally:
+            lib.CiReleaseString(s)
+
+
+def _raise_or_return(c_err, throw=True):
+    err = PqaError.factor(c_err)
+    if err is not None and throw:
+        raise PqaException(err)
+    return err
+
+
+def _i64arr(a):
+    return np.ascontiguousarray(a, dtype=np.int64)
+
+
+def _p(a, typ):
+    return None if a is None else a.ctypes.data_as(typ)
+
+
+class PqaEngine:
+    def __init__(self, c_engine):
+        self.c_engine = C.c_void_p(c_engine)
+        self._lib = load_library()
+        d = self.copy_dims()
+        self.n_answers, self.n_questions, self.n_targets = d.n_answers, d.n_questions, d.n_targets
+
+    def __del__(self):
+        self.close()
+
+    def close(self):
+        if getattr(self, "c_engine", None) and self.c_engine.value:
+            self._lib.CiReleasePqaEngine(self.c_engine)
+            self.c_engine = C.c_void_p(None)
+
+    # ---------------------------------------------------------------- reference-binding methods
+    @staticmethod
+    def to_c_answered_questions(answered_questions: List[AnsweredQuestion]):
+        n = len(answered_questions)
+        arr = (CiAnsweredQuestion * max(n, 1))()
+        for i, aq in enumerate(answered_questions):
+            if isinstance(aq, AnsweredQuestion):
+                arr[i].iQuestion, arr[i].iAnswer = aq.i_question, aq.i_answer
+            else:
+                arr[i].iQuestion, arr[i].iAnswer = int(aq[0]), int(aq[1])
+        return arr, n
+
+    def train(self, answered_questions, i_target: int, amount: float = 1.0, throw: bool = True):
+        arr, n = self.to_c_answered_questions(answered_questions)
+        return _raise_or_return(self._lib.PqaEngine_Train(self.c_engine, n, arr, i_target, amount), throw)
+
+    def get_total_questions_asked(self) -> int:
+        e = C.c_void_p()
+        v = self._lib.PqaEngine_GetTotalQuestionsAsked(self.c_engine, C.byref(e))
+        _raise_or_return(e.value)
+        return v
+
+    def copy_dims(self) -> EngineDimensions:
+        d = CiEngineDimensions()
+        if not self._lib.PqaEngine_CopyDims(self.c_engine, C.byref(d)):
+            raise RuntimeError("PqaEngine_CopyDims failed")
+        return EngineDimensions(d.nAnswers, d.nQuestions, d.nTargets)
+
+    def start_quiz(self) -> int:
+        e = C.c_void_p()
+        q = self._lib.PqaEngine_StartQuiz(self.c_engine, C.byref(e))
+        _raise_or_return(e.value)
+        return q
+
+    def resume_quiz(self, answered_questions) -> int:
+        arr, n = self.to_c_answered_questions(answered_questions)
+        e = C.c_void_p()
+        q = self._lib.PqaEngine_ResumeQuiz(self.c_engine, C.byref(e), n, arr)
+        _raise_or_return(e.value)
+        return q
+
+    def next_question(self, i_quiz: int) -> int:
+        e = C.c_void_p()
+        q = self._lib.PqaEngine_NextQuestion(self.c_engine, C.byref(e), i_quiz)
+        _raise_or_return(e.value)
+        return q
+
+    def record_answer(self, i_quiz: int, i_answer: int, throw: bool = True):
+        return _raise_or_return(self._lib.PqaEngine_RecordAnswer(self.c_engine, i_quiz, i_answer), throw)
+
+    def get_active_question_id(self, i_quiz: int) -> int:
+        e = C.c_void_p()
+        q = self._lib.PqaEngine_GetActiveQuestionId(self.c_engine, C.byref(e), i_quiz)
+        _raise_or_return(e.value)
+        return q
+
+    def set_active_question(self, i_quiz: int, i_question: int, throw: bool = True):
+        return _raise_or_return(self._lib.PqaEngine_SetActiveQuestion(self.c_engine, i_quiz, i_question), throw)
+
+    def list_top_targets(self, i_quiz: int, max_count: int) -> List[RatedTarget]:
+        dest = (CiRatedTarget * max(max_count, 1))()
+        e = C.c_void_p()
+        n = self._lib.PqaEngine_ListTopTargets(self.c_engine, C.byref(e), i_quiz, max_count, dest)
+        _raise_or_return(e.value)
+        return [RatedTarget(dest[i].iTarget, dest[i].prob) for i in range(n)]
+
+    def record_quiz_target(self, i_quiz: int, i_target: int, amount: float = 1.0, throw: bool = True):
+        return _raise_or_return(self._lib.PqaEngine_RecordQuizTarget(self.c_engine, i_quiz, i_target, amount), throw)
+
+    def release_quiz(self, i_quiz: int, throw: bool = True):
+        return _raise_or_return(self._lib.PqaEngine_ReleaseQuiz(self.c_engine, i_quiz), throw)
+
+    def save_kb(self, file_path: str, b_double_buffer: bool = False, throw: bool = True):
+        return _raise_or_return(self._lib.PqaEngine_SaveKB(self.c_engine, file_path.encode(), int(b_double_buffer)), throw)
+
+    def shutdown(self, save_file_path: str = None, throw: bool = True):
+        p = save_file_path.encode() if save_file_path else None
+        return _raise_or_return(self._lib.PqaEngine_Shutdown(self.c_engine, p), throw)
+
+    # ---------------------------------------------------------------- B200 extensions (numpy in / numpy out)
+    @property
+    def emulated_workers(self) -> int:
+        return self._lib.PqaB200_GetEmulatedWorkers(self.c_engine)
+
+    def upload_kb(self, sA, mD, vB):
+        sA = np.ascontiguousarray(sA, dtype=np.float64)
+        mD = np.ascontiguousarray(mD, dtype=np.float64)
+        vB = np.ascontiguousarray(vB, dtype=np.float64)
+        assert sA.shape == (self.n_questions, self.n_answers, self.n_targets), sA.shape
+        assert mD.shape == (self.n_questions, self.n_targets) and vB.shape == (self.n_targets,)
+        _raise_or_return(self._lib.PqaB200_UploadKB(self.c_engine, _p(sA, _pd), _p(mD, _pd), _p(vB, _pd)))
+
+    def download_kb(self):
+        sA = np.empty((self.n_questions, self.n_answers, self.n_targets))
+        mD = np.empty((self.n_questions, self.n_targets))
+        vB = np.empty(self.n_targets)
+        _raise_or_return(self._lib.PqaB200_DownloadKB(self.c_engine, _p(sA, _pd), _p(mD, _pd), _p(vB, _pd)))
+        return sA, mD, vB
+
+    def copy_a_targets(self, i_question, i_answer):
+        out = np.empty(self.n_targets)
+        _raise_or_return(self._lib.PqaEngine_CopyATargets(self.c_engine, i_question, i_answer, self.n_targets, _p(out, _pd)))
+        return out
+
+    def copy_d_targets(self, i_question):
+        out = np.empty(self.n_targets)
+        _raise_or_return(self._lib.PqaEngine_CopyDTargets(self.c_engine, i_question, self.n_targets, _p(out, _pd)))
+        return out
+
+    def copy_b_targets(self):
+        out = np.empty(self.n_targets)
+        _raise_or_return(self._lib.PqaEngine_CopyBTargets(self.c_engine, self.n_targets, _p(out, _pd)))
+        return out
+
+    def start_quiz_batch(self, n: int) -> np.ndarray:
+        ids = np.empty(n, dtype=np.int64)
+        _raise_or_return(self._lib.PqaEngine_StartQuizBatch(self.c_engine, n, _p(ids, _pi64)))
+        return ids
+
+    def next_question_batch(self, quiz_ids, randoms=None) -> np.ndarray:
+        ids = _i64arr(quiz_ids)
+        rnd = None if randoms is None else np.ascontiguousarray(randoms, dtype=np.uint64)
+        out = np.empty(ids.size, dtype=np.int64)
+        _raise_or_return(self._lib.PqaEngine_NextQuestionBatch(self.c_engine, ids.size, _p(ids, _pi64), _p(rnd, _pu64),
+                                                               _p(out, _pi64), None))
+        return out
+
+    def record_answer_batch(self, quiz_ids, answers):
+        ids, ans = _i64arr(quiz_ids), _i64arr(answers)
+        assert ids.size == ans.size
+        _raise_or_return(self._lib.PqaEngine_RecordAnswerBatch(self.c_engine, ids.size, _p(ids, _pi64), _p(ans, _pi64)))
+
+    def set_active_question_batch(self, quiz_ids, questions):
+        ids, qs = _i64arr(quiz_ids), _i64arr(questions)
+        assert ids.size == qs.size
+        _raise_or_return(self._lib.PqaEngine_SetActiveQuestionBatch(self.c_engine, ids.size, _p(ids, _pi64), _p(qs, _pi64)))
+
+    def list_top_targets_batch(self, quiz_ids, max_count: int):
+        """Returns (items[n, max_count] structured array {iTarget, prob}, counts[n])."""
+        ids = _i64arr(quiz_ids)
+        dest = np.zeros((ids.size, max_count), dtype=RATED_DTYPE)
+        counts = np.zeros(ids.size, dtype=np.int64)
+        _raise_or_return(self._lib.PqaEngine_ListTopTargetsBatch(self.c_engine, ids.size, _p(ids, _pi64), max_count,
+                                                                 dest.ctypes.data_as(C.c_void_p), _p(counts, _pi64)))
+        return dest, counts
+
+    def record_quiz_target_batch(self, quiz_ids, targets, amounts=None):
+        ids, tg = _i64arr(quiz_ids), _i64arr(targets)
+        am = None if amounts is None else np.ascontiguousarray(amounts, dtype=np.float64)
+        _raise_or_return(self._lib.PqaEngine_RecordQuizTargetBatch(self.c_engine, ids.size, _p(ids, _pi64), _p(tg, _pi64),
+                                                                   _p(am, _pd)))
+
+    def release_quiz_batch(self, quiz_ids):
+        ids = _i64arr(quiz_ids)
+        _raise_or_return(self._lib.PqaEngine_ReleaseQuizBatch(self.c_engine, ids.size, _p(ids, _pi64)))
+
+    def copy_quiz_priors(self, i_quiz: int) -> np.ndarray:
+        out = np.empty(self.n_targets)
+        _raise_or_return(self._lib.PqaB200_CopyQuizPriors(self.c_engine, i_quiz, _p(out, _pd)))
+        return out
+
+    def set_quiz_priors(self, i_quiz: int, priors):
+        pr = np.ascontiguousarray(priors, dtype=np.float64)
+        assert pr.shape == (self.n_targets,)
+        _raise_or_return(self._lib.PqaB200_SetQuizPriors(self.c_engine, i_quiz, _p(pr, _pd)))
+
+    def eval_questions(self, quiz_ids):
+        """dict(priority[n,Q] (NaN where asked), runLength[n,Q], grand[n,nChunks])."""
+        ids = _i64arr(quiz_ids)
+        n, Q = ids.size, self.n_questions
+        pri, run = np.empty((n, Q)), np.empty((n, Q))
+        maxChunks = min(Q, 8 * self.emulated_workers)
+        grand = np.empty((n, maxChunks))
+        nch = C.c_int64()
+        _raise_or_return(self._lib.PqaB200_EvalQuestions(self.c_engine, n, _p(ids, _pi64), _p(pri, _pd), _p(run, _pd),
+                                                         _p(grand, _pd), C.byref(nch)))
+        assert nch.value == maxChunks
+        return dict(priority=pri, runLength=run, grand=grand)
+
+    def eval_questions_detailed(self, i_quiz: int):
+        Q, K = self.n_questions, self.n_answers
+        W, H, V = np.empty((Q, K)), np.empty((Q, K)), np.empty((Q, K))
+        lack, pri = np.empty(Q), np.empty(Q)
+        _raise_or_return(self._lib.PqaB200_EvalQuestionsDetailed(self.c_engine, i_quiz, _p(W, _pd), _p(H, _pd), _p(V, _pd),
+                                                                 _p(lack, _pd), _p(pri, _pd)))
+        return dict(W=W, H=H, V=V, lack=lack, priority=pri)
+
+    def set_eval_kernel(self, which: int, chunk_targets: int = 0, quizzes_per_cta: int = 0):
+        """0 auto, 1 exact (CpuEngine rounding order), 2 staged (throughput kernel)."""
+        _raise_or_return(self._lib.PqaB200_SetEvalTuning(self.c_engine, which, chunk_targets, quizzes_per_cta))
+
+    def resident_bind(self, quiz_ids, randoms=None):
+        ids = _i64arr(quiz_ids)
+        rnd = None if randoms is None else np.ascontiguousarray(randoms, dtype=np.uint64)
+        _raise_or_return(self._lib.PqaB200_ResidentBind(self.c_engine, ids.size, _p(ids, _pi64), _p(rnd, _pu64)))
+        self._resident_n = ids.size
+
+    def resident_step(self):
+        _raise_or_return(self._lib.PqaB200_ResidentStep(self.c_engine))
+
+    def resident_fetch(self) -> np.ndarray:
+        out = np.empty(self._resident_n, dtype=np.int64)
+        _raise_or_return(self._lib.PqaB200_ResidentFetch(self.c_engine, _p(out, _pi64)))
+        return out
+
+    def resident_last_eval_ms(self) -> float:
+        return self._lib.PqaB200_ResidentLastEvalMs(self.c_engine)
+
+    def synchronize(self):
+        _raise_or_return(self._lib.PqaB200_Synchronize(self.c_engine))
+
+    def flush_l2(self):
+        _raise_or_return(self._lib.PqaB200_FlushL2(self.c_engine))
+
+    def kernel_launch_count(self) -> int:
+        return self._lib.PqaB200_KernelLaunchCount(self.c_engine)
+
+
+class DeviceEvent:
+    """CUDA event recorded on the engine's own stream (torch.cuda.Event would only see torch's current stream)."""
+
+    def __init__(self):
+        self._lib = load_library()
+        self.h = C.c_void_p(self._lib.PqaB200_EventCreate())
+        if not self.h.value:
+            raise RuntimeError("cudaEventCreate failed")
+
+    def record(self, engine: PqaEngine):
+        _raise_or_return(self._lib.PqaB200_EventRecord(engine.c_engine, self.h))
+
+    def resident_last_eval_ms(self) -> float:
+        return self._lib.PqaB200_ResidentLastEvalMs(self.c_engine)
+
+    def synchronize(self):
+        _raise_or_return(self._lib.PqaB200_EventSynchronize(self.h))
+
+    def elapsed_ms(self, stop: "DeviceEvent") -> float:
+        return self._lib.PqaB200_EventElapsedMs(self.h, stop.h)
+
+    def __del__(self):
+        if getattr(self, "h", None) and self.h.value:
+            self._lib.PqaB200_EventDestroy(self.h)
+            self.h = C.c_void_p(None)
+
+
+class PqaEngineFactory:
+    def __init__(self):
+        self._lib = load_library()
+        self.c_factory = C.c_void_p(self._lib.CiGetPqaEngineFactory())
+
+    def create_cpu_engine(self, eng_def: EngineDefinition) -> Tuple[PqaEngine, PqaError]:
+        """Same name and shape as ProbQA.py:747; returns the B200 engine (there is no CPU engine in this library)."""
+        c_def = eng_def.to_c()
+        e = C.c_void_p()
+        c_engine = self._lib.PqaEngineFactory_CreateCpuEngine(self.c_factory, C.byref(e), C.byref(c_def))
+        err = PqaError.factor(e.value)
+        if not c_engine:
+            raise PqaException(err)
+        return PqaEngine(c_engine), err
+
+    def create_b200_engine(self, eng_def: EngineDefinition, device: int = -1, emulated_workers: int = 0,
+                           rng_seed: int = 0, initial_quiz_capacity: int = 0) -> PqaEngine:
+        c_def = eng_def.to_c()
+        opts = CiB200Options(device, emulated_workers, rng_seed, initial_quiz_capacity)
+        e = C.c_void_p()
+        c_engine = self._lib.PqaB200_CreateEngine(C.byref(e), C.byref(c_def), C.byref(opts))
+        if not c_engine:
+            raise PqaException(PqaError.factor(e.value))
+        return PqaEngine(c_engine)
+
+    def load_cpu_engine(self, file_path: str, mem_pool_max_bytes: int = 512 << 20) -> Tuple[PqaEngine, PqaError]:
+        e = C.c_void_p()
+        c_engine = self._lib.PqaEngineFactory_LoadCpuEngine(self.c_factory, C.byref(e), file_path.encode(), mem_pool_max_bytes)
+        err = PqaError.factor(e.value)
+        if not c_engine:
+            raise PqaException(err)
+        return PqaEngine(c_engine), err

@@ -1,0 +1,398 @@
+"""GPU parity tests: the CUDA path, called through the C ABI of libPqaCore.so, against the CPU oracle (oracle/).
+
+Bars (DESIGN.md "Parity"):
+  * priors after StartQuiz / RecordAnswer ........ bit-exact (Kahan order of CpuEngine emulated for worker count W)
+  * ListTopTargets ............................... identical indices, order and probability bits (ties included)
+  * exact evaluation kernel (which=1) ............ W_k, H_k, V_k, lack bit-exact; priority <= 8 ulp (device libm pow/exp2/log)
+  * staged evaluation kernel (which=2, default) .. relative tolerance  1e-11 + 2^-47 / min_j |log2 posterior_j|  per question
+        (the reference's lack term  sum invD^2 / Log2Hot(post)  has condition number 1/|log2 post| with respect to the
+        last bits of the normaliser W_k, whose summation order differs)
+  * question selection ........................... identical index for identical run-lengths and the same 64-bit draw
+  * RecordQuizTarget / Train ..................... sA, mD, vB bit-exact
+"""
+import numpy as np
+import pytest
+
+from probqa_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+INIT = 0.1
+
+
+def bits(a):
+    return np.ascontiguousarray(a, dtype=np.float64).view(np.uint64)
+
+
+def ulp_diff(a, b):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    b = np.ascontiguousarray(b, dtype=np.float64)
+    ia = a.view(np.int64).astype(np.float64)
+    ib = b.view(np.int64).astype(np.float64)
+    return np.abs(ia - ib)
+
+
+@pytest.fixture(scope="module")
+def pqa():
+    from probqa_b200 import engine
+    engine.load_library()
+    return engine
+
+
+def make_engine(pqa, Q, K, T, W, kb=None, seed=12345):
+    eng = pqa.PqaEngineFactory().create_b200_engine(pqa.EngineDefinition(K, Q, T, init_amount=INIT),
+                                                    emulated_workers=W, rng_seed=seed)
+    if kb is not None:
+        eng.upload_kb(*kb)
+    return eng
+
+
+KBS = {
+    "binary": lambda Q, K, T: synth.binary_search_kb(Q, K, T, INIT, 3),
+    "gamma": lambda Q, K, T: synth.gamma_kb(Q, K, T, INIT),
+    "uniform": lambda Q, K, T: synth.uniform_kb(Q, K, T, INIT),
+}
+
+
+def drive_quiz(eng, ora, kb, W, quiz, prefix, check_top=True):
+    """Answers `prefix` in quiz, checking priors and top-10 against the oracle after every step. Returns the prior."""
+    sA, mD, vB = kb
+    prior = ora.start_quiz(vB, W)
+    got = eng.copy_quiz_priors(quiz)
+    assert np.array_equal(bits(got), bits(prior)), "StartQuiz priors differ"
+    for (q, a) in prefix:
+        eng.set_active_question(quiz, q)
+        eng.record_answer(quiz, a)
+        prior = ora.record_answer(prior, sA[q, a], mD[q], max(1, W - 1))
+        got = eng.copy_quiz_priors(quiz)
+        assert np.array_equal(bits(got), bits(prior)), "RecordAnswer priors differ at question %d" % q
+        if check_top:
+            want = ora.list_top_targets(prior, W, 10)
+            have = eng.list_top_targets(quiz, 10)
+            assert [(r.i_target, r.prob) for r in have] == want
+    return prior
+
+
+@pytest.mark.parametrize("kbname", ["binary", "gamma", "uniform"])
+@pytest.mark.parametrize("dims,W", [((64, 5, 1000), 8), ((33, 5, 203), 7), ((16, 3, 50), 1), ((20, 5, 1000), 64)])
+def test_priors_and_top_targets_bit_exact(pqa, ora, kbname, dims, W):
+    Q, K, T = dims
+    kb = KBS[kbname](Q, K, T)
+    eng = make_engine(pqa, Q, K, T, W, kb)
+    for b in range(3):
+        quiz = eng.start_quiz()
+        want = ora.list_top_targets(ora.start_quiz(kb[2], W), W, 10)
+        have = eng.list_top_targets(quiz, 10)
+        assert [(r.i_target, r.prob) for r in have] == want   # all-ties case: pure heap mechanics
+        drive_quiz(eng, ora, kb, W, quiz, synth.quiz_prefix(b, min(6, Q - 1), Q, T, K))
+        eng.release_quiz(quiz)
+
+
+def test_top_targets_more_than_positive(pqa, ora):
+    Q, K, T, W = 8, 5, 40, 4
+    kb = synth.gamma_kb(Q, K, T, INIT)
+    eng = make_engine(pqa, Q, K, T, W, kb)
+    quiz = eng.start_quiz()
+    prior = np.zeros(T)
+    prior[[3, 17, 18, 39]] = [0.25, 0.5, 0.125, 0.125]
+    eng.set_quiz_priors(quiz, prior)
+    have = eng.list_top_targets(quiz, 10)
+    want = ora.list_top_targets(prior, W, 10)
+    assert len(have) == 4 and [(r.i_target, r.prob) for r in have] == want
+    # whole list, with ties
+    prior = np.full(T, 1.0 / T)
+    eng.set_quiz_priors(quiz, prior)
+    assert [(r.i_target, r.prob) for r in eng.list_top_targets(quiz, T)] == ora.list_top_targets(prior, W, T)
+
+
+def oracle_eval_all(ora, kb, prior, W, asked=None):
+    sA, mD, _ = kb
+    return ora.eval_questions(sA, mD, prior, W, asked=asked, nThreads=8)
+
+
+@pytest.mark.parametrize("kbname", ["binary", "gamma", "uniform"])
+@pytest.mark.parametrize("dims,W", [((48, 5, 1000), 8), ((21, 5, 203), 3), ((12, 2, 64), 1), ((10, 9, 77), 2)])
+def test_exact_kernel_bit_exact(pqa, ora, kbname, dims, W):
+    Q, K, T = dims
+    kb = KBS[kbname](Q, K, T)
+    eng = make_engine(pqa, Q, K, T, W, kb)
+    eng.set_eval_kernel(1)
+    for depth in (0, 3):
+        quiz = eng.start_quiz()
+        prefix = synth.quiz_prefix(depth + 1, min(depth, Q - 1), Q, T, K)
+        prior = drive_quiz(eng, ora, kb, W, quiz, prefix, check_top=False)
+        asked = np.zeros(Q, dtype=bool)
+        asked[[q for q, _ in prefix]] = True
+        det = eng.eval_questions_detailed(quiz)
+        for i in range(Q):
+            if asked[i]:
+                assert np.isnan(det["priority"][i])
+                continue
+            o = ora.eval_question(kb[0][i], kb[1][i], prior)
+            assert np.array_equal(bits(det["W"][i]), bits(o["W"])), (i, det["W"][i], o["W"])
+            assert np.array_equal(bits(det["H"][i]), bits(o["H"])), i
+            assert np.array_equal(bits(det["V"][i]), bits(o["V"])), i
+            assert bits(det["lack"][i]) == bits(o["lack"]), i
+            assert ulp_diff(det["priority"][i], o["priority"]) <= 8, (i, det["priority"][i], o["priority"])
+        # run-lengths, grand totals and selection through the same API
+        ev = eng.eval_questions([quiz])
+        oev = oracle_eval_all(ora, kb, prior, W, asked)
+        assert np.allclose(ev["runLength"][0], oev["runLength"], rtol=1e-14, atol=0)
+        assert np.allclose(ev["grand"][0], oev["grand"], rtol=1e-14, atol=0)
+        eng.release_quiz(quiz)
+
+
+def staged_tolerance(kb, prior):
+    """Per-question relative tolerance of the staged kernel: 1e-11 + 2^-47 / min_j |log2 posterior_j| (see module doc)."""
+    sA, mD, _ = kb
+    lik = sA / mD[:, None, :] * prior[None, None, :]
+    W = lik.sum(axis=2, keepdims=True)
+    post = lik / W
+    mx = np.minimum(post.max(axis=2).max(axis=1), 1.0)
+    l2 = np.maximum(-np.log2(mx), 2.0 ** -60)
+    return 1e-11 + 2.0 ** -47 / l2
+
+
+@pytest.mark.parametrize("kbname", ["binary", "gamma", "uniform"])
+@pytest.mark.parametrize("dims,W,chunk", [((48, 5, 1000), 8, 0), ((48, 5, 1000), 8, 96), ((21, 5, 203), 3, 0),
+                                          ((21, 5, 203), 3, 32), ((12, 2, 64), 1, 0), ((9, 8, 130), 2, 64),
+                                          ((10, 9, 77), 2, 0)])
+def test_staged_kernel_within_tolerance(pqa, ora, kbname, dims, W, chunk):
+    Q, K, T = dims
+    kb = KBS[kbname](Q, K, T)
+    eng = make_engine(pqa, Q, K, T, W, kb)
+    eng.set_eval_kernel(2, chunk_targets=chunk)
+    quizzes, priors, askeds = [], [], []
+    for b, depth in enumerate((0, 1, 3, 5, 2)):   # odd batch: exercises the half-filled quiz pair
+        quiz = eng.start_quiz()
+        prefix = synth.quiz_prefix(b, min(depth, Q - 1), Q, T, K)
+        priors.append(drive_quiz(eng, ora, kb, W, quiz, prefix, check_top=False))
+        asked = np.zeros(Q, dtype=bool)
+        asked[[q for q, _ in prefix]] = True
+        askeds.append(asked)
+        quizzes.append(quiz)
+    ev = eng.eval_questions(quizzes)
+    single = eng.eval_questions(quizzes[:1])     # n = 1 path (one quiz per warp)
+    for x, quiz in enumerate(quizzes):
+        oev = oracle_eval_all(ora, kb, priors[x], W, askeds[x])
+        tol = staged_tolerance(kb, priors[x])
+        got, want = ev["priority"][x], oev["priority"]
+        assert np.array_equal(np.isnan(got), askeds[x])
+        ok = ~askeds[x]
+        rel = np.abs(got[ok] - want[ok]) / np.abs(want[ok])
+        assert np.all(rel <= tol[ok]), (x, float(np.max(rel / tol[ok])), float(rel.max()))
+        if x == 0:
+            assert np.array_equal(np.isnan(single["priority"][0]), askeds[0])
+            rel1 = np.abs(single["priority"][0][ok] - want[ok]) / np.abs(want[ok])
+            assert np.all(rel1 <= tol[ok])
+        # run-lengths / grand totals inherit the tolerance
+        assert np.allclose(ev["runLength"][x], oev["runLength"], rtol=float(tol[ok].max()) * 4, atol=0)
+        assert np.allclose(ev["grand"][x], oev["grand"], rtol=float(tol[ok].max()) * 4, atol=0)
+
+
+def test_staged_matches_detail_outputs(pqa, ora):
+    Q, K, T, W = 40, 5, 1000, 8
+    kb = synth.binary_search_kb(Q, K, T, INIT, 3)
+    eng = make_engine(pqa, Q, K, T, W, kb)
+    quiz = eng.start_quiz()
+    prior = drive_quiz(eng, ora, kb, W, quiz, synth.quiz_prefix(7, 3, Q, T, K), check_top=False)
+    det = eng.eval_questions_detailed(quiz)   # default kernel = staged
+    for i in range(Q):
+        if np.isnan(det["priority"][i]):
+            continue
+        o = ora.eval_question(kb[0][i], kb[1][i], prior)
+        assert np.allclose(det["W"][i], o["W"], rtol=1e-13, atol=0)
+        assert np.allclose(det["H"][i], o["H"], rtol=1e-11, atol=1e-300)
+        assert np.allclose(det["V"][i], o["V"], rtol=1e-11, atol=1e-300)
+
+
+def test_zero_prior_targets_follow_log2hot_edge(pqa, ora):
+    """Posterior exactly 0 contributes invD^2 / Log2Hot(0) = invD^2 / -1023 to lack (SURVEY hard part 5)."""
+    Q, K, T, W = 6, 5, 64, 2
+    kb = synth.gamma_kb(Q, K, T, INIT)
+    eng = make_engine(pqa, Q, K, T, W, kb)
+    quiz = eng.start_quiz()
+    prior = np.random.default_rng(5).uniform(0.1, 1, T)
+    prior[::3] = 0.0
+    prior[5] = 1e-320   # subnormal posterior
+    prior /= prior.sum()
+    eng.set_quiz_priors(quiz, prior)
+    for which, tol in ((1, 0.0), (2, 1e-11)):
+        eng.set_eval_kernel(which)
+        det = eng.eval_questions_detailed(quiz)
+        for i in range(Q):
+            o = ora.eval_question(kb[0][i], kb[1][i], prior)
+            if which == 1:
+                assert bits(det["lack"][i]) == bits(o["lack"])
+            assert abs(det["lack"][i] - o["lack"]) <= tol * abs(o["lack"])
+            assert abs(det["priority"][i] - o["priority"]) <= max(tol, 1e-15) * abs(o["priority"])
+
+
+@pytest.mark.parametrize("which", [1, 2])
+def test_next_question_selection(pqa, ora, which):
+    Q, K, T, W = 96, 5, 300, 4
+    kb = synth.binary_search_kb(Q, K, T, INIT, 3)
+    eng = make_engine(pqa, Q, K, T, W, kb)
+    eng.set_eval_kernel(which)
+    rng = np.random.default_rng(11)
+    n = 24
+    quizzes = eng.start_quiz_batch(n)
+    askeds = np.zeros((n, Q), dtype=bool)
+    for x, quiz in enumerate(quizzes):
+        for (q, a) in synth.quiz_prefix(x, x % 5, Q, T, K):
+            eng.set_active_question(int(quiz), q)
+            eng.record_answer(int(quiz), a)
+            askeds[x, q] = True
+    randoms = rng.integers(0, 2 ** 64, size=n, dtype=np.uint64)
+    randoms[0], randoms[1] = 0, 2 ** 64 - 1
+    ev = eng.eval_questions(quizzes)
+    asked_before = eng.get_total_questions_asked()
+    chosen = eng.next_question_batch(quizzes, randoms)
+    assert eng.get_total_questions_asked() == asked_before + n
+    bounds = ora.calc_split(Q, 8 * W)
+    for x in range(n):
+        e1 = dict(runLength=ev["runLength"][x], grand=ev["grand"][x], bounds=bounds)
+        want = ora.select_question(e1, Q, int(randoms[x]), asked=askeds[x])
+        assert chosen[x] == want, (x, chosen[x], want)
+        assert not askeds[x, chosen[x]]
+        assert eng.get_active_question_id(int(quizzes[x])) == chosen[x]
+
+
+def test_selection_skips_to_nearest_unasked(pqa, ora):
+    Q, K, T, W = 130, 5, 64, 1
+    kb = synth.uniform_kb(Q, K, T, INIT)
+    eng = make_engine(pqa, Q, K, T, W, kb)
+    quiz = eng.start_quiz()
+    asked = np.zeros(Q, dtype=bool)
+    for q in list(range(0, 70)) + list(range(71, 129)):   # leaves 70 and 129
+        eng.set_active_question(quiz, q)
+        eng.record_answer(quiz, 0)
+        asked[q] = True
+    for rnd in (0, 2 ** 63, 2 ** 64 - 1):
+        got = eng.next_question_batch([quiz], np.array([rnd], dtype=np.uint64))[0]
+        assert got in (70, 129)
+    # exhaust
+    for q in (70, 129):
+        eng.set_active_question(quiz, q)
+        eng.record_answer(quiz, 1)
+    with pytest.raises(pqa.PqaException) as ei:
+        eng.next_question(quiz)
+    assert "Engine has run out of questions" in str(ei.value)
+
+
+def test_record_quiz_target_and_train_bit_exact(pqa, ora):
+    Q, K, T, W = 50, 5, 120, 4
+    kb = synth.gamma_kb(Q, K, T, INIT)
+    sA, mD, vB = [a.copy() for a in kb]
+    eng = make_engine(pqa, Q, K, T, W, kb)
+    rng = np.random.default_rng(3)
+    # many quizzes sharing targets and questions => colliding cells, applied in array order
+    n = 40
+    quizzes = eng.start_quiz_batch(n)
+    targets = rng.integers(0, 6, size=n)
+    amounts = rng.choice([1.0, 0.5, 2.25], size=n)
+    all_aqs = []
+    for x, quiz in enumerate(quizzes):
+        aqs = []
+        for q in rng.choice(12, size=int(rng.integers(0, 9)), replace=False):
+            a = int(rng.integers(0, K))
+            eng.set_active_question(int(quiz), int(q))
+            eng.record_answer(int(quiz), a)
+            aqs.append((int(q), a))
+        all_aqs.append(aqs)
+        ora.record_quiz_target(sA, mD, vB, aqs, int(targets[x]), float(amounts[x]))
+    eng.record_quiz_target_batch(quizzes, targets, amounts)
+    gA, gD, gB = eng.download_kb()
+    assert np.array_equal(bits(gA), bits(sA)) and np.array_equal(bits(gD), bits(mD)) and np.array_equal(bits(gB), bits(vB))
+    # single-call form
+    eng.record_quiz_target(int(quizzes[3]), 7, 1.5)
+    ora.record_quiz_target(sA, mD, vB, all_aqs[3], 7, 1.5)
+    # Train(): duplicate questions (same and different answers) inside one call
+    aqs = [(3, 1), (7, 2), (3, 1), (11, 0), (7, 4), (15, 2), (3, 2), (19, 1), (23, 3)]
+    before = eng.get_total_questions_asked()
+    eng.train([pqa.AnsweredQuestion(q, a) for q, a in aqs], 9, 0.75)
+    assert eng.get_total_questions_asked() == before + len(aqs)
+    ora.train(sA, mD, vB, aqs, 9, 0.75, W)
+    gA, gD, gB = eng.download_kb()
+    assert np.array_equal(bits(gA), bits(sA)) and np.array_equal(bits(gD), bits(mD)) and np.array_equal(bits(gB), bits(vB))
+
+
+def test_initial_kb_and_dims(pqa):
+    """Dimensions.CpuIncrease-style check (PqaCoreTests/Dimensions.cpp:62-77): A = init^2, D = K*init^2, B = init."""
+    Q, K, T = 7, 5, 203
+    eng = make_engine(pqa, Q, K, T, 2)
+    d = eng.copy_dims()
+    assert (d.n_answers, d.n_questions, d.n_targets) == (K, Q, T)
+    assert np.all(eng.copy_a_targets(3, 2) == INIT * INIT)
+    assert np.all(eng.copy_d_targets(6) == K * (INIT * INIT))
+    assert np.all(eng.copy_b_targets() == INIT)
+    sA, mD, vB = eng.download_kb()
+    assert np.all(sA == INIT * INIT) and np.all(mD == K * (INIT * INIT)) and np.all(vB == INIT)
+
+
+def test_error_contract(pqa):
+    Q, K, T = 8, 3, 16
+    eng = make_engine(pqa, Q, K, T, 2)
+    quiz = eng.start_quiz()
+    with pytest.raises(pqa.PqaException) as ei:
+        eng.record_answer(quiz, 0)
+    assert "[No active question in the quiz]" in str(ei.value) and "answerId=0" in str(ei.value)
+    eng.next_question(quiz)
+    with pytest.raises(pqa.PqaException) as ei:
+        eng.record_answer(quiz, K)
+    assert "[Index is out of range]" in str(ei.value) and "subjIndex=3 not in 0...2" in str(ei.value)
+    with pytest.raises(pqa.PqaException) as ei:
+        eng.next_question(quiz + 5)
+    assert "[Index is out of range]" in str(ei.value)
+    with pytest.raises(pqa.PqaException) as ei:
+        eng.record_quiz_target(quiz, 3, 0.0)
+    assert "[The amount is not positive]" in str(ei.value)
+    with pytest.raises(pqa.PqaException) as ei:
+        eng.record_quiz_target(quiz, T, 1.0)
+    assert "[Index is out of range]" in str(ei.value)
+    eng.release_quiz(quiz)
+    with pytest.raises(pqa.PqaException) as ei:
+        eng.next_question(quiz)
+    assert "[The ID is absent from KB]" in str(ei.value)
+    assert eng.start_quiz() == quiz          # ids are recycled LIFO (GapTracker.h:38-49)
+    with pytest.raises(pqa.PqaException) as ei:
+        eng.train([pqa.AnsweredQuestion(0, 0)], 0, -1.0)
+    assert "[The amount is not positive]" in str(ei.value)
+    with pytest.raises(pqa.PqaException):
+        pqa.PqaEngineFactory().create_cpu_engine(pqa.EngineDefinition(1, 1, 1))
+
+
+@pytest.mark.parametrize("depth", [0, 3, 8])
+def test_full_size_staged_vs_exact_and_oracle(pqa, ora, depth):
+    """BASELINE config 2 size (1000x5x1000): the staged kernel against the exact kernel for a batch of quizzes, and
+    against the oracle for one quiz (the oracle needs ~1 s per quiz at this size)."""
+    Q, K, T, W = 1000, 5, 1000, 8
+    kb = synth.binary_search_kb(Q, K, T, INIT, 3)
+    eng = make_engine(pqa, Q, K, T, W, kb)
+    n = 16
+    quizzes = eng.start_quiz_batch(n)
+    for x, quiz in enumerate(quizzes):
+        for (q, a) in synth.quiz_prefix(x, depth, Q, T, K):
+            eng.set_active_question(int(quiz), q)
+            eng.record_answer(int(quiz), a)
+    eng.set_eval_kernel(2)
+    fast = eng.eval_questions(quizzes)["priority"]
+    eng.set_eval_kernel(1)
+    exact = eng.eval_questions(quizzes)["priority"]
+    assert np.array_equal(np.isnan(fast), np.isnan(exact))
+    for x, quiz in enumerate(quizzes):
+        prior = eng.copy_quiz_priors(int(quiz))
+        tol = staged_tolerance(kb, prior)
+        ok = ~np.isnan(exact[x])
+        rel = np.abs(fast[x][ok] - exact[x][ok]) / np.abs(exact[x][ok])
+        assert np.all(rel <= tol[ok]), (x, float(np.max(rel / tol[ok])))
+    prior0 = eng.copy_quiz_priors(int(quizzes[0]))
+    asked0 = np.isnan(exact[0])
+    oev = oracle_eval_all(ora, kb, prior0, W, asked0)
+    ok = ~asked0
+    assert np.max(ulp_diff(exact[0][ok], oev["priority"][ok])) <= 8
+    # top-10 lists of every quiz are bit-identical to the oracle's
+    items, counts = eng.list_top_targets_batch(quizzes, 10)
+    for x, quiz in enumerate(quizzes):
+        want = ora.list_top_targets(eng.copy_quiz_priors(int(quiz)), W, 10)
+        assert [(int(t), float(p)) for t, p in items[x][:counts[x]]] == want
