@@ -225,6 +225,7 @@ def main():
     ap.add_argument("--kernel", type=int, default=0, help="0 auto (staged), 1 exact, 2 staged")
     ap.add_argument("--quizzes-per-cta", type=int, default=0)
     ap.add_argument("--chunk-targets", type=int, default=0)
+    ap.add_argument("--lanes", type=int, default=0, help="Kahan lanes per thread of the staged kernel: 0 auto, 1, 4")
     ap.add_argument("--ref-quizzes", type=int, default=8, help="quizzes per step of the reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-flush", action="store_true")
@@ -275,7 +276,7 @@ def main():
     eng = pqa.PqaEngineFactory().create_b200_engine(pqa.EngineDefinition(K, Q, T, init_amount=INIT), device=local_rank,
                                                     emulated_workers=cores, rng_seed=1234 + rank, initial_quiz_capacity=B)
     eng.upload_kb(*synth.binary_search_kb(Q, K, T, INIT, 3))
-    eng.set_eval_kernel(args.kernel, args.chunk_targets, args.quizzes_per_cta)
+    eng.set_eval_kernel(args.kernel, args.chunk_targets, args.quizzes_per_cta, args.lanes)
     # this rank's shard of the batch: quizzes rank*B .. rank*B+B-1 (weak scaling: B per GPU)
     states = quiz_states(cfg, rank * B, B)
     quizzes = eng.start_quiz_batch(B)

@@ -72,8 +72,10 @@ PQACORE_API void *PqaB200_EvalQuestionsDetailed(void *pvEngine, int64_t iQuiz, d
  * bit-identical W/H/V/lack), 2 staged (TMA + shared memory throughput kernel, tolerance-level parity). */
 PQACORE_API void *PqaB200_SetEvalKernel(void *pvEngine, int32_t which);
 /* Same, plus tuning knobs of the staged kernel (tests force the chunked-targets path on small T with these):
- * chunkTargets = targets staged per shared-memory chunk (0 auto), quizzesPerCta = quiz tile of one CTA (0 auto). */
-PQACORE_API void *PqaB200_SetEvalTuning(void *pvEngine, int32_t which, int64_t chunkTargets, int64_t quizzesPerCta);
+ * chunkTargets = targets staged per shared-memory chunk (0 auto), quizzesPerCta = quiz tile of one CTA (0 auto),
+ * kahanLanesPerThread = 4 (one thread per quiz), 1 (four threads per quiz) or 0 (auto: 4 for batches >= 64). */
+PQACORE_API void *PqaB200_SetEvalTuning(void *pvEngine, int32_t which, int64_t chunkTargets, int64_t quizzesPerCta,
+                                        int32_t kahanLanesPerThread);
 
 /* ---- device-resident stepping and timing (bench.py "value" leg: no host<->device traffic inside) ---- */
 /* Binds n quizzes as the resident batch: ids and one random draw per quiz are copied to the device once. */

@@ -316,11 +316,12 @@ PQACORE_API void *PqaB200_EvalQuestionsDetailed(void *pvEngine, int64_t iQuiz, d
 }
 PQACORE_API void *PqaB200_SetEvalKernel(void *pvEngine, int32_t which) {
   if (!pvEngine) return NullEngine();
-  return Ret(E(pvEngine)->SetEvalKernel(which, 0, 0));
+  return Ret(E(pvEngine)->SetEvalKernel(which, 0, 0, 0));
 }
-PQACORE_API void *PqaB200_SetEvalTuning(void *pvEngine, int32_t which, int64_t chunkTargets, int64_t quizzesPerCta) {
+PQACORE_API void *PqaB200_SetEvalTuning(void *pvEngine, int32_t which, int64_t chunkTargets, int64_t quizzesPerCta,
+                                        int32_t kahanLanesPerThread) {
   if (!pvEngine) return NullEngine();
-  return Ret(E(pvEngine)->SetEvalKernel(which, chunkTargets, quizzesPerCta));
+  return Ret(E(pvEngine)->SetEvalKernel(which, chunkTargets, quizzesPerCta, kahanLanesPerThread));
 }
 PQACORE_API void *PqaB200_ResidentBind(void *pvEngine, int64_t n, const int64_t *pQuizIds, const uint64_t *pRandoms) {
   if (!pvEngine) return NullEngine();

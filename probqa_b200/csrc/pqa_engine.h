@@ -97,7 +97,7 @@ class Engine {
   PqaError *EvalQuestions(int64_t n, const int64_t *pQuizIds, double *pPriorities, double *pRunLength,
                           double *pGrandTotals, int64_t *pnChunks);
   PqaError *EvalQuestionsDetailed(int64_t iQuiz, double *pW, double *pH, double *pV, double *pLack, double *pPriorities);
-  PqaError *SetEvalKernel(int32_t which, int64_t chunkTargets, int64_t quizzesPerCta);
+  PqaError *SetEvalKernel(int32_t which, int64_t chunkTargets, int64_t quizzesPerCta, int32_t kahanLanesPerThread);
 
   // --- device-resident stepping ---
   PqaError *ResidentBind(int64_t n, const int64_t *pQuizIds, const uint64_t *pRandoms);

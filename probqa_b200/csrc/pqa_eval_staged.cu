@@ -8,20 +8,21 @@
 //    transformed in place once per CTA: invD = 1/mD, r[k][j] = sA*invD (the reference's per-target likelihood factor,
 //    :72-81), lr[k][j] = log2 r, id2[j] = invD^2 (the numerator of the "lack" term, :116-117). Every quiz of the tile
 //    then reuses the staged slab, so HBM/L2 sees the slab once per CTA instead of once per quiz.
-//  * A warp evaluates 8 quizzes at a time: lane = (quiz q8 = lane/4, Kahan lane l = lane%4). Thread (q8, l) owns the
-//    targets j with j%4 == l of its quiz and walks them in vector order -- exactly the element-to-lane assignment
-//    and order of the reference's AVX2 code, so pass 1 reproduces the reference's normaliser W_k BIT FOR BIT
-//    (4-lane Kahan sum + PreciseSum, :81-88), hence its posteriors post = lik * (1/W_k) (:91,:97) and the differences
-//    post - prior of the velocity term (:119) bit for bit. This matters: for a question that is uninformative under
-//    the current posterior, sum (post - prior)^2 is pure rounding noise and the reference's priority depends on it.
-//    The four lanes of a quiz read the same r/lr/id2 vector (32 contiguous bytes), and the 8 quizzes of a warp read
-//    the same vector: shared-memory loads are warp broadcasts; the end-of-pass reductions are width-4 shuffles.
+//  * The reference sums with a 4-lane AVX2 Kahan accumulator: target j goes to lane j%4, lanes advance in vector
+//    order (SRAccumVectDbl256.h:40-46). A GPU thread here owns KL of those 4 Kahan lanes of ONE quiz (KL = 4: one
+//    thread per quiz, 32 quizzes per warp, used for big batches; KL = 1: four threads per quiz, 8 quizzes per warp,
+//    used for small batches) and walks the 4-target vectors in order, so pass 1 reproduces the reference's normaliser
+//    W_k BIT FOR BIT (4-lane Kahan sum + PreciseSum, :81-88), hence its posteriors post = lik * (1/W_k) (:91,:97)
+//    and the differences post - prior of the velocity term (:119) bit for bit. This matters: for a question that
+//    is uninformative under the current posterior, sum (post - prior)^2 is pure rounding noise and the reference's
+//    priority depends on it. All threads of a warp read the same r/lr/id2 vector: shared-memory loads are 128-bit
+//    warp broadcasts. A thread carries KL*K independent dependency chains, which is what keeps the fp64 pipe busy.
 //  * Pass 2 needs log2(posterior) per element (:106): instead of the reference's Log2Hot (one IEEE divide + series)
 //    it uses log2(post) = lr[k][j] + log2(prior[j]) - log2(W_k) (two adds; log2 prior is kept per quiz), and falls
 //    back to the bit-faithful Log2Hot for the elements where that split would lose accuracy or where Log2Hot's edge
 //    semantics matter: post >= 0.5 (cancellation; also Log2Hot(1) = -6.56e-20 != 0) and post < 2^-1022 (Log2Hot(0) =
 //    -1023, subnormals). The lack term's divide is a MUFU seed + 3 DFMA reciprocal. The entropy / lack / velocity
-//    sums are plain per-lane sums (the reference uses Kahan sums): their terms are same-signed, so this costs ~1e-14
+//    sums are plain sums (the reference uses Kahan sums): their terms are same-signed, so this costs ~1e-14
 //    relative. Net: W_k bit-exact, H_k / V_k / lack / priority within the tolerance stated in DESIGN.md and enforced
 //    by tests/test_gpu_parity.py; the fully bit-level path is k_eval_exact in pqa_kernels.cu.
 //  * When a slab does not fit in shared memory (large T) the targets are processed in chunks; pass 1 runs over all
@@ -36,10 +37,6 @@
 namespace pqa {
 void count_launch();
 
-constexpr int kEvalWarps = 8;
-constexpr int kEvalThreads = kEvalWarps * 32;
-constexpr int kQuizzesPerWarp = 8;   // lane = (quiz, Kahan lane): 8 quizzes x 4 lanes
-
 struct StagedParams {
   DeviceKB kb;
   QuizPool qp;
@@ -49,10 +46,40 @@ struct StagedParams {
   EvalDetail det;
   int64_t Jc;             // targets per shared-memory chunk (multiple of 4)
   int64_t nChunks;
-  int64_t quizzesPerCta;  // == kEvalWarps*kQuizzesPerWarp when nChunks > 1
+  int64_t quizzesPerCta;  // == quizzes per pass of one CTA when nChunks > 1
 };
 
-template <int K>
+template <int KL> struct VecD { double v[KL]; };
+
+// KL consecutive doubles starting at a KL*8-byte aligned address
+template <int KL> __device__ __forceinline__ VecD<KL> lds_vec(const double *p) {
+  VecD<KL> o;
+  if (KL == 4) {
+    const double2 a = *reinterpret_cast<const double2 *>(p), b = *reinterpret_cast<const double2 *>(p + 2);
+    o.v[0] = a.x; o.v[1 % KL] = a.y; o.v[2 % KL] = b.x; o.v[3 % KL] = b.y;
+  } else if (KL == 2) {
+    const double2 a = *reinterpret_cast<const double2 *>(p);
+    o.v[0] = a.x; o.v[1 % KL] = a.y;
+  } else {
+    o.v[0] = *p;
+  }
+  return o;
+}
+template <int KL> __device__ __forceinline__ VecD<KL> ldg_vec(const double *p) {
+  VecD<KL> o;
+  if (KL == 4) {
+    const double2 a = __ldg(reinterpret_cast<const double2 *>(p)), b = __ldg(reinterpret_cast<const double2 *>(p + 2));
+    o.v[0] = a.x; o.v[1 % KL] = a.y; o.v[2 % KL] = b.x; o.v[3 % KL] = b.y;
+  } else if (KL == 2) {
+    const double2 a = __ldg(reinterpret_cast<const double2 *>(p));
+    o.v[0] = a.x; o.v[1 % KL] = a.y;
+  } else {
+    o.v[0] = __ldg(p);
+  }
+  return o;
+}
+
+template <int K, int THREADS>
 __device__ __forceinline__ void stage_chunk(const StagedParams &P, int64_t i, int64_t c, bool withLog, double *sR,
                                             double *sLR, double *sID2, uint64_t *bar, uint32_t &parity) {
   const int64_t Jc = P.Jc, Tp = P.kb.Tp, T = P.kb.T;
@@ -69,7 +96,7 @@ __device__ __forceinline__ void stage_chunk(const StagedParams &P, int64_t i, in
   }
   mbar_wait(bar, parity);
   parity ^= 1u;
-  for (int64_t j = threadIdx.x; j < cnt; j += kEvalThreads) {
+  for (int64_t j = threadIdx.x; j < cnt; j += THREADS) {
     const int64_t gj = j0 + j;
     const bool gap = gj >= T || bit32(P.kb.tgaps, gj);
     const double invD = __ddiv_rn(1.0, sID2[j]);                         // :72-76
@@ -84,78 +111,116 @@ __device__ __forceinline__ void stage_chunk(const StagedParams &P, int64_t i, in
   __syncthreads();
 }
 
-// lane = (q8, l): q8 = quiz within the warp's group of 8, l = Kahan lane. One pass-1 step per 4-target vector.
-template <int K>
+// Pass 1 over one chunk: thread owns Kahan lanes l0 .. l0+KL-1 of its quiz. Padding / gap lanes hold prior = +0 and
+// r = 0, which add +0 exactly as the reference's masked lanes do.
+template <int K, int KL>
 __device__ __forceinline__ void pass1_chunk(const double *__restrict__ sR, int64_t Jc, int nVects, int64_t j0,
-                                            const double *__restrict__ pr, int l, Kahan (&kw)[K]) {
-#pragma unroll 2
+                                            const double *__restrict__ pr, int l0, Kahan (&kw)[KL][K]) {
+  const double *prc = pr + j0 + l0;
+  VecD<KL> pn = ldg_vec<KL>(prc);
   for (int v = 0; v < nVects; v++) {
-    const int j = 4 * v + l;
-    const double p = __ldg(pr + j0 + j);               // padding lanes hold +0 (and r = 0 there)
-#pragma unroll
-    for (int k = 0; k < K; k++) kw[k].add(__dmul_rn(sR[k * Jc + j], p));   // :81-86
-  }
-}
-
-template <int K>
-__device__ __forceinline__ void pass2_chunk(const double *__restrict__ sR, const double *__restrict__ sLR,
-                                            const double *__restrict__ sID2, int64_t Jc, int nVects, int valid,
-                                            int64_t j0, const double *__restrict__ pr, const double *__restrict__ lpr,
-                                            const double *__restrict__ tbl, int l, const double (&iW)[K],
-                                            const double (&lW)[K], double (&H)[K], double (&V)[K], double &L) {
-#pragma unroll 2
-  for (int v = 0; v < nVects; v++) {
-    const int j = 4 * v + l;
-    if (j >= valid) break;                               // padding lanes of the last vector (gap mask, :103-117)
-    const double p = __ldg(pr + j0 + j), lp = __ldg(lpr + j0 + j);
-    const double id2 = sID2[j];
+    const VecD<KL> p = pn;
+    if (v + 1 < nVects) pn = ldg_vec<KL>(prc + 4 * (v + 1));           // prefetch the next vector's priors
+    const int j = 4 * v + l0;
 #pragma unroll
     for (int k = 0; k < K; k++) {
-      const double lik = __dmul_rn(sR[k * Jc + j], p);                  // :81-82
-      const double post = __dmul_rn(lik, iW[k]);                        // :97
-      double l2 = __dsub_rn(__dadd_rn(sLR[k * Jc + j], lp), lW[k]);
-      double rl2;
-      // high word in [0x00100000, 0x3FE00000) <=> 2^-1022 <= post < 0.5 (positive, normal): the split log is accurate
-      const unsigned hi = (unsigned)__double2hiint(post);
-      if (hi - 0x00100000u >= 0x3FE00000u - 0x00100000u) {
-        l2 = log2hot(post, tbl);                                        // :106, reference semantics
-        rl2 = __ddiv_rn(1.0, l2);
-      } else {
-        rl2 = fast_rcp(l2);
-      }
-      H[k] = __fma_rn(post, l2, H[k]);                                  // :113-114
-      L = __fma_rn(id2, rl2, L);                                        // :116-117
-      const double d = __dsub_rn(post, p);                              // :119
-      V[k] = __fma_rn(d, d, V[k]);                                      // :126-127
+      const VecD<KL> r = lds_vec<KL>(sR + k * Jc + j);
+#pragma unroll
+      for (int e = 0; e < KL; e++) kw[e][k].add(__dmul_rn(r.v[e], p.v[e]));   // :81-86
     }
   }
 }
 
-// sum over the four lanes of a quiz; every lane of the group returns the total
-__device__ __forceinline__ double group_sum4(double v) {
-  const unsigned mask = 0xFu << (threadIdx.x & 28u);
-  v = __dadd_rn(v, __shfl_xor_sync(mask, v, 1, 4));
-  v = __dadd_rn(v, __shfl_xor_sync(mask, v, 2, 4));
-  return v;
+template <int K, int KL>
+__device__ __forceinline__ void pass2_chunk(const double *__restrict__ sR, const double *__restrict__ sLR,
+                                            const double *__restrict__ sID2, int64_t Jc, int nVects, int64_t j0,
+                                            const double *__restrict__ pr, const double *__restrict__ lpr,
+                                            const double *__restrict__ tbl, int l0, const double (&iW)[K],
+                                            const double (&lW)[K], double (&H)[K], double (&V)[K], double (&L)[KL]) {
+  const double *prc = pr + j0 + l0, *lprc = lpr + j0 + l0;
+  VecD<KL> pn = ldg_vec<KL>(prc), lpn = ldg_vec<KL>(lprc);
+  for (int v = 0; v < nVects; v++) {
+    const VecD<KL> p = pn, lp = lpn;
+    if (v + 1 < nVects) { pn = ldg_vec<KL>(prc + 4 * (v + 1)); lpn = ldg_vec<KL>(lprc + 4 * (v + 1)); }
+    const int j = 4 * v + l0;
+    const VecD<KL> id2 = lds_vec<KL>(sID2 + j);
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+      const VecD<KL> r = lds_vec<KL>(sR + k * Jc + j), lr = lds_vec<KL>(sLR + k * Jc + j);
+      double post[KL], l2[KL], rl2[KL];
+      unsigned slow = 0;
+#pragma unroll
+      for (int e = 0; e < KL; e++) {
+        const double lik = __dmul_rn(r.v[e], p.v[e]);                   // :81-82
+        post[e] = __dmul_rn(lik, iW[k]);                                // :97
+        l2[e] = __dsub_rn(__dadd_rn(lr.v[e], lp.v[e]), lW[k]);
+        // high word in [0x00100000, 0x3FE00000) <=> 2^-1022 <= post < 0.5 (positive, normal): the split log is accurate
+        const unsigned hi = (unsigned)__double2hiint(post[e]);
+        slow |= (hi - 0x00100000u >= 0x3FE00000u - 0x00100000u) ? (1u << e) : 0u;
+      }
+      if (slow) {
+#pragma unroll
+        for (int e = 0; e < KL; e++) {
+          if (slow & (1u << e)) {
+            l2[e] = log2hot(post[e], tbl);                              // :106, reference semantics
+            rl2[e] = __ddiv_rn(1.0, l2[e]);
+          } else {
+            rl2[e] = fast_rcp(l2[e]);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < KL; e++) rl2[e] = fast_rcp(l2[e]);
+      }
+#pragma unroll
+      for (int e = 0; e < KL; e++) {
+        H[k] = __fma_rn(post[e], l2[e], H[k]);                          // :113-114
+        L[e] = __fma_rn(id2.v[e], rl2[e], L[e]);                        // :116-117 (id2 = 0 on gap / padding lanes)
+        const double d = __dsub_rn(post[e], p.v[e]);                    // :119
+        V[k] = __fma_rn(d, d, V[k]);                                    // :126-127
+      }
+    }
+  }
 }
 
-template <int K>
-__device__ __forceinline__ void finish_pass1(const Kahan (&kw)[K], double (&W)[K], double (&iW)[K], double (&lW)[K]) {
+// PreciseSum of the four Kahan lanes of a quiz (SRAccumVectDbl256.h:83-91); the lanes live in 4/KL threads.
+template <int K, int KL>
+__device__ __forceinline__ void finish_pass1(const Kahan (&kw)[KL][K], double (&W)[K], double (&iW)[K], double (&lW)[K]) {
+  constexpr int LPQ = 4 / KL;   // threads per quiz
+  const unsigned mask = (LPQ == 4) ? (0xFu << (threadIdx.x & 28u)) : (LPQ == 2) ? (0x3u << (threadIdx.x & 30u)) : 0u;
 #pragma unroll
   for (int k = 0; k < K; k++) {
-    W[k] = group_precise_sum(kw[k]);                                    // :88 (PreciseSum of the 4 Kahan lanes)
-    iW[k] = __ddiv_rn(1.0, W[k]);                                       // :91
+    double s[4], c[4];
+#pragma unroll
+    for (int ln = 0; ln < 4; ln++) {
+      if (LPQ == 1) { s[ln] = kw[ln % KL][k].s; c[ln] = kw[ln % KL][k].c; }
+      else { s[ln] = __shfl_sync(mask, kw[ln % KL][k].s, ln / KL, LPQ); c[ln] = __shfl_sync(mask, kw[ln % KL][k].c, ln / KL, LPQ); }
+    }
+    W[k] = precise_sum4(s[0], s[1], s[2], s[3], c[0], c[1], c[2], c[3]);   // :88
+    iW[k] = __ddiv_rn(1.0, W[k]);                                          // :91
     lW[k] = log2(W[k]);
   }
 }
 
-template <int K>
-__device__ __forceinline__ void finish_pass2(const StagedParams &P, int64_t i, int64_t b, int l, const double (&W)[K],
-                                             double (&H)[K], double (&V)[K], double L) {
+template <int KL> __device__ __forceinline__ double quiz_sum(double v) {
+  constexpr int LPQ = 4 / KL;
+  if (LPQ == 1) return v;
+  const unsigned mask = (LPQ == 4) ? (0xFu << (threadIdx.x & 28u)) : (0x3u << (threadIdx.x & 30u));
 #pragma unroll
-  for (int k = 0; k < K; k++) { H[k] = group_sum4(H[k]); V[k] = group_sum4(V[k]); }
-  L = group_sum4(L);
-  if (l != 0) return;
+  for (int o = 1; o < LPQ; o <<= 1) v = __dadd_rn(v, __shfl_xor_sync(mask, v, o, LPQ));
+  return v;
+}
+
+template <int K, int KL>
+__device__ __forceinline__ void finish_pass2(const StagedParams &P, int64_t i, int64_t b, int l0, const double (&W)[K],
+                                             double (&H)[K], double (&V)[K], const double (&Lp)[KL]) {
+  double L = Lp[0];
+#pragma unroll
+  for (int e = 1; e < KL; e++) L = __dadd_rn(L, Lp[e]);
+#pragma unroll
+  for (int k = 0; k < K; k++) { H[k] = quiz_sum<KL>(H[k]); V[k] = quiz_sum<KL>(V[k]); }
+  L = quiz_sum<KL>(L);
+  if (l0 != 0) return;
   const int64_t o = b * P.kb.Q + i;
   double totW = 0.0, sumH = 0.0, sumV = 0.0;
 #pragma unroll
@@ -178,23 +243,26 @@ __device__ __forceinline__ void finish_pass2(const StagedParams &P, int64_t i, i
   if (P.det.lack) P.det.lack[o] = lack;
 }
 
-template <int K>
-__global__ void __launch_bounds__(kEvalThreads, 2) k_eval_staged(const StagedParams P) {
+template <int K, int KL, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 2) k_eval_staged(const StagedParams P) {
+  constexpr int THREADS = WARPS * 32;
+  constexpr int LPQ = 4 / KL;              // threads per quiz
+  constexpr int QPW = 32 / LPQ;            // quizzes per warp
   extern __shared__ __align__(128) unsigned char smRaw[];
   __shared__ uint64_t bar;
   double *sR = (double *)smRaw;        // [K][Jc]  sA, then r = sA/mD
   double *sLR = sR + K * P.Jc;         // [K][Jc]  log2 r
   double *sID2 = sLR + K * P.Jc;       // [Jc]     mD, then 1/mD^2
 
-  const int64_t i = blockIdx.x, Q = P.kb.Q, Tp = P.kb.Tp, T = P.kb.T;
+  const int64_t i = blockIdx.x, Q = P.kb.Q, Tp = P.kb.Tp;
   const int64_t tileFirst = (int64_t)blockIdx.y * P.quizzesPerCta;
   const int64_t tileLimit = (tileFirst + P.quizzesPerCta < P.n) ? tileFirst + P.quizzesPerCta : P.n;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q8 = lane >> 2, l = lane & 3;
+  const int qw = lane / LPQ, l0 = (lane % LPQ) * KL;
   const double qnan = __longlong_as_double(0x7FF8000000000000ll);
 
   if (bit32(P.kb.qgaps, i)) {          // CEEvalQsSubtaskConsider.cpp:54-58
-    for (int64_t b = tileFirst + threadIdx.x; b < tileLimit; b += kEvalThreads) P.priority[b * Q + i] = qnan;
+    for (int64_t b = tileFirst + threadIdx.x; b < tileLimit; b += THREADS) P.priority[b * Q + i] = qnan;
     return;
   }
   if (threadIdx.x == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
@@ -203,77 +271,107 @@ __global__ void __launch_bounds__(kEvalThreads, 2) k_eval_staged(const StagedPar
   const double *__restrict__ tbl = P.kb.log2tbl;
 
   if (P.nChunks == 1) {
-    stage_chunk<K>(P, i, 0, true, sR, sLR, sID2, &bar, parity);
-    const int nVects = (int)(Tp >> 2), valid = (int)T;
-    for (int64_t g0 = tileFirst + (int64_t)warp * kQuizzesPerWarp; g0 < tileLimit; g0 += (int64_t)kEvalWarps * kQuizzesPerWarp) {
-      const int64_t b = g0 + q8;
+    stage_chunk<K, THREADS>(P, i, 0, true, sR, sLR, sID2, &bar, parity);
+    const int nVects = (int)(Tp >> 2);
+    for (int64_t g0 = tileFirst + (int64_t)warp * QPW; g0 < tileLimit; g0 += (int64_t)WARPS * QPW) {
+      const int64_t b = g0 + qw;
       bool live = b < tileLimit;
       const int64_t slot = P.slots[live ? b : tileLimit - 1];
       if (live && bit64(P.qp.asked + slot * P.qp.askedWords, i)) {
-        if (l == 0) P.priority[b * Q + i] = qnan;
+        if (l0 == 0) P.priority[b * Q + i] = qnan;
         live = false;
       }
-      if (!live) continue;             // the whole 4-lane group of this quiz leaves together
+      if (!live) continue;             // all threads of this quiz leave together
       const double *pr = P.qp.priors + slot * Tp, *lpr = P.qp.logPriors + slot * Tp;
-      double W[K], iW[K], lW[K], H[K], V[K], L = 0.0;
+      double W[K], iW[K], lW[K], H[K], V[K], L[KL];
       {
-        Kahan kw[K];
+        Kahan kw[KL][K];
 #pragma unroll
-        for (int k = 0; k < K; k++) kw[k].init();
-        pass1_chunk<K>(sR, P.Jc, nVects, 0, pr, l, kw);
-        finish_pass1<K>(kw, W, iW, lW);
+        for (int e = 0; e < KL; e++)
+#pragma unroll
+          for (int k = 0; k < K; k++) kw[e][k].init();
+        pass1_chunk<K, KL>(sR, P.Jc, nVects, 0, pr, l0, kw);
+        finish_pass1<K, KL>(kw, W, iW, lW);
       }
 #pragma unroll
       for (int k = 0; k < K; k++) { H[k] = 0.0; V[k] = 0.0; }
-      pass2_chunk<K>(sR, sLR, sID2, P.Jc, nVects, valid, 0, pr, lpr, tbl, l, iW, lW, H, V, L);
-      finish_pass2<K>(P, i, b, l, W, H, V, L);
+#pragma unroll
+      for (int e = 0; e < KL; e++) L[e] = 0.0;
+      pass2_chunk<K, KL>(sR, sLR, sID2, P.Jc, nVects, 0, pr, lpr, tbl, l0, iW, lW, H, V, L);
+      finish_pass2<K, KL>(P, i, b, l0, W, H, V, L);
     }
   } else {
-    // chunked targets: this lane keeps its quiz for the whole question
-    const int64_t b = tileFirst + (int64_t)warp * kQuizzesPerWarp + q8;
+    // chunked targets: this thread keeps its quiz for the whole question
+    const int64_t b = tileFirst + (int64_t)warp * QPW + qw;
     bool live = b < tileLimit;
     const int64_t slot = P.slots[live ? b : tileLimit - 1];
     if (live && bit64(P.qp.asked + slot * P.qp.askedWords, i)) {
-      if (l == 0) P.priority[b * Q + i] = qnan;
+      if (l0 == 0) P.priority[b * Q + i] = qnan;
       live = false;
     }
     const double *pr = P.qp.priors + slot * Tp, *lpr = P.qp.logPriors + slot * Tp;
-    double W[K], iW[K], lW[K], H[K], V[K], L = 0.0;
-    Kahan kw[K];
+    double W[K], iW[K], lW[K], H[K], V[K], L[KL];
+    Kahan kw[KL][K];
 #pragma unroll
-    for (int k = 0; k < K; k++) { kw[k].init(); H[k] = 0.0; V[k] = 0.0; W[k] = 0.0; iW[k] = 0.0; lW[k] = 0.0; }
+    for (int k = 0; k < K; k++) { H[k] = 0.0; V[k] = 0.0; W[k] = 0.0; iW[k] = 0.0; lW[k] = 0.0; }
+#pragma unroll
+    for (int e = 0; e < KL; e++) {
+      L[e] = 0.0;
+#pragma unroll
+      for (int k = 0; k < K; k++) kw[e][k].init();
+    }
     for (int64_t c = 0; c < P.nChunks; c++) {
-      stage_chunk<K>(P, i, c, false, sR, sLR, sID2, &bar, parity);
+      stage_chunk<K, THREADS>(P, i, c, false, sR, sLR, sID2, &bar, parity);
       const int64_t j0 = c * P.Jc;
       const int nVects = (int)(((Tp - j0 < P.Jc) ? (Tp - j0) : P.Jc) >> 2);
-      if (live) pass1_chunk<K>(sR, P.Jc, nVects, j0, pr, l, kw);
+      if (live) pass1_chunk<K, KL>(sR, P.Jc, nVects, j0, pr, l0, kw);
       __syncthreads();  // everyone is done with the buffers before the next stage overwrites them
     }
-    if (live) finish_pass1<K>(kw, W, iW, lW);
+    if (live) finish_pass1<K, KL>(kw, W, iW, lW);
     for (int64_t c = 0; c < P.nChunks; c++) {
-      stage_chunk<K>(P, i, c, true, sR, sLR, sID2, &bar, parity);
+      stage_chunk<K, THREADS>(P, i, c, true, sR, sLR, sID2, &bar, parity);
       const int64_t j0 = c * P.Jc;
-      const int64_t cnt = (Tp - j0 < P.Jc) ? (Tp - j0) : P.Jc;
-      const int nVects = (int)(cnt >> 2);
-      const int valid = (int)((T - j0 < cnt) ? (T - j0 > 0 ? T - j0 : 0) : cnt);
-      if (live) pass2_chunk<K>(sR, sLR, sID2, P.Jc, nVects, valid, j0, pr, lpr, tbl, l, iW, lW, H, V, L);
+      const int nVects = (int)(((Tp - j0 < P.Jc) ? (Tp - j0) : P.Jc) >> 2);
+      if (live) pass2_chunk<K, KL>(sR, sLR, sID2, P.Jc, nVects, j0, pr, lpr, tbl, l0, iW, lW, H, V, L);
       __syncthreads();
     }
-    if (live) finish_pass2<K>(P, i, b, l, W, H, V, L);
+    if (live) finish_pass2<K, KL>(P, i, b, l0, W, H, V, L);
   }
 }
 
-template <int K>
-static void launch_k(const StagedParams &P, size_t smem, cudaStream_t st) {
+template <int K, int KL, int WARPS>
+static void launch_cfg(StagedParams P, const EvalConfig &cfg, size_t smem, cudaStream_t st) {
   static bool attrSet = false;
   if (!attrSet) {
-    cudaFuncSetAttribute(k_eval_staged<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(k_eval_staged<K, KL, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     attrSet = true;
+  }
+  const int64_t perPass = (int64_t)WARPS * (32 / (4 / KL));   // quizzes one CTA evaluates concurrently
+  if (P.nChunks > 1) {
+    P.quizzesPerCta = perPass;
+  } else if (cfg.quizzesPerCta > 0) {
+    P.quizzesPerCta = ((cfg.quizzesPerCta + perPass - 1) / perPass) * perPass;
+  } else {
+    // enough CTAs for ~12 waves of 2 CTAs/SM when the batch allows it, else one pass per CTA
+    const int64_t passesTotal = (P.n + perPass - 1) / perPass;
+    const int64_t targetCtas = (int64_t)cfg.smCount * 2 * 12;
+    int64_t passesPerCta = (P.kb.Q * passesTotal) / targetCtas;
+    if (passesPerCta < 1) passesPerCta = 1;
+    if (passesPerCta > passesTotal) passesPerCta = passesTotal;
+    P.quizzesPerCta = passesPerCta * perPass;
   }
   const int64_t tiles = (P.n + P.quizzesPerCta - 1) / P.quizzesPerCta;
   dim3 grid((unsigned)P.kb.Q, (unsigned)tiles);
-  k_eval_staged<K><<<grid, kEvalThreads, smem, st>>>(P);
+  k_eval_staged<K, KL, WARPS><<<grid, WARPS * 32, smem, st>>>(P);
   count_launch();
+}
+
+template <int K>
+static void launch_k(const StagedParams &P, const EvalConfig &cfg, size_t smem, cudaStream_t st) {
+  // big batches: one thread per quiz (32 quizzes per warp, 4 warps); small batches: four threads per quiz
+  const int lanesPerThread = cfg.kahanLanesPerThread > 0 ? cfg.kahanLanesPerThread : (P.n >= 64 ? 4 : 1);
+  if (lanesPerThread == 4) launch_cfg<K, 4, 4>(P, cfg, smem, st);
+  else launch_cfg<K, 1, 8>(P, cfg, smem, st);
 }
 
 void launch_eval_staged(const DeviceKB &kb, const QuizPool &qp, int64_t n, const int64_t *dSlots, double *dPriority,
@@ -293,29 +391,16 @@ void launch_eval_staged(const DeviceKB &kb, const QuizPool &qp, int64_t n, const
   if (Jc * bytesPerTarget > budget) Jc = (budget / bytesPerTarget) & ~31ll;
   P.Jc = Jc;
   P.nChunks = (kb.Tp + Jc - 1) / Jc;
-  const int64_t perPass = (int64_t)kEvalWarps * kQuizzesPerWarp;
-  if (P.nChunks > 1) {
-    P.quizzesPerCta = perPass;
-  } else if (cfg.quizzesPerCta > 0) {
-    P.quizzesPerCta = ((cfg.quizzesPerCta + perPass - 1) / perPass) * perPass;
-  } else {
-    // enough CTAs for ~12 waves of 2 CTAs/SM when the batch allows it, else one pass per CTA
-    const int64_t passesTotal = (n + perPass - 1) / perPass;
-    const int64_t targetCtas = (int64_t)cfg.smCount * 2 * 12;
-    int64_t passesPerCta = (kb.Q * passesTotal) / targetCtas;
-    if (passesPerCta < 1) passesPerCta = 1;
-    if (passesPerCta > passesTotal) passesPerCta = passesTotal;
-    P.quizzesPerCta = passesPerCta * perPass;
-  }
+  P.quizzesPerCta = 0;
   const size_t smem = (size_t)(Jc * bytesPerTarget);
   switch (kb.K) {
-    case 2: launch_k<2>(P, smem, st); break;
-    case 3: launch_k<3>(P, smem, st); break;
-    case 4: launch_k<4>(P, smem, st); break;
-    case 5: launch_k<5>(P, smem, st); break;
-    case 6: launch_k<6>(P, smem, st); break;
-    case 7: launch_k<7>(P, smem, st); break;
-    default: launch_k<8>(P, smem, st); break;
+    case 2: launch_k<2>(P, cfg, smem, st); break;
+    case 3: launch_k<3>(P, cfg, smem, st); break;
+    case 4: launch_k<4>(P, cfg, smem, st); break;
+    case 5: launch_k<5>(P, cfg, smem, st); break;
+    case 6: launch_k<6>(P, cfg, smem, st); break;
+    case 7: launch_k<7>(P, cfg, smem, st); break;
+    default: launch_k<8>(P, cfg, smem, st); break;
   }
 }
 

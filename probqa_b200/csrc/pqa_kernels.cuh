@@ -64,6 +64,7 @@ struct EvalConfig {
   int smCount = 148;
   int64_t chunkTargets = 0;
   int64_t quizzesPerCta = 0;   // 0 = auto
+  int kahanLanesPerThread = 0; // staged kernel: 4 = one thread per quiz, 1 = four threads per quiz, 0 = auto by batch
 };
 void launch_eval_questions(const DeviceKB &kb, const QuizPool &qp, int64_t n, const int64_t *dSlots,
                            double *dPriority, const EvalDetail &det, const EvalConfig &cfg, cudaStream_t st);

@@ -116,7 +116,7 @@ SIGNATURES = {
     "PqaB200_EvalQuestions": (_vp, [_vp, _i64, _pi64, _pd, _pd, _pd, _pi64]),
     "PqaB200_EvalQuestionsDetailed": (_vp, [_vp, _i64, _pd, _pd, _pd, _pd, _pd]),
     "PqaB200_SetEvalKernel": (_vp, [_vp, C.c_int32]),
-    "PqaB200_SetEvalTuning": (_vp, [_vp, C.c_int32, _i64, _i64]),
+    "PqaB200_SetEvalTuning": (_vp, [_vp, C.c_int32, _i64, _i64, C.c_int32]),
     "PqaB200_ResidentBind": (_vp, [_vp, _i64, _pi64, _pu64]),
     "PqaB200_ResidentStep": (_vp, [_vp]),
     "PqaB200_ResidentFetch": (_vp, [_vp, _pi64]),
@@ -451,9 +451,10 @@ class PqaEngine:
                                                                  _p(lack, _pd), _p(pri, _pd)))
         return dict(W=W, H=H, V=V, lack=lack, priority=pri)
 
-    def set_eval_kernel(self, which: int, chunk_targets: int = 0, quizzes_per_cta: int = 0):
+    def set_eval_kernel(self, which: int, chunk_targets: int = 0, quizzes_per_cta: int = 0, kahan_lanes_per_thread: int = 0):
         """0 auto, 1 exact (CpuEngine rounding order), 2 staged (throughput kernel)."""
-        _raise_or_return(self._lib.PqaB200_SetEvalTuning(self.c_engine, which, chunk_targets, quizzes_per_cta))
+        _raise_or_return(self._lib.PqaB200_SetEvalTuning(self.c_engine, which, chunk_targets, quizzes_per_cta,
+                                                         kahan_lanes_per_thread))
 
     def resident_bind(self, quiz_ids, randoms=None):
         ids = _i64arr(quiz_ids)

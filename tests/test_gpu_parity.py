@@ -152,11 +152,12 @@ def staged_tolerance(kb, prior):
 @pytest.mark.parametrize("dims,W,chunk", [((48, 5, 1000), 8, 0), ((48, 5, 1000), 8, 96), ((21, 5, 203), 3, 0),
                                           ((21, 5, 203), 3, 32), ((12, 2, 64), 1, 0), ((9, 8, 130), 2, 64),
                                           ((10, 9, 77), 2, 0)])
-def test_staged_kernel_within_tolerance(pqa, ora, kbname, dims, W, chunk):
+@pytest.mark.parametrize("lanes", [1, 4])   # four threads per quiz / one thread per quiz
+def test_staged_kernel_within_tolerance(pqa, ora, kbname, dims, W, chunk, lanes):
     Q, K, T = dims
     kb = KBS[kbname](Q, K, T)
     eng = make_engine(pqa, Q, K, T, W, kb)
-    eng.set_eval_kernel(2, chunk_targets=chunk)
+    eng.set_eval_kernel(2, chunk_targets=chunk, kahan_lanes_per_thread=lanes)
     quizzes, priors, askeds = [], [], []
     for b, depth in enumerate((0, 1, 3, 5, 2)):   # odd batch: exercises the half-filled quiz pair
         quiz = eng.start_quiz()
@@ -371,8 +372,12 @@ def test_full_size_staged_vs_exact_and_oracle(pqa, ora, depth):
         for (q, a) in synth.quiz_prefix(x, depth, Q, T, K):
             eng.set_active_question(int(quiz), q)
             eng.record_answer(int(quiz), a)
-    eng.set_eval_kernel(2)
+    eng.set_eval_kernel(2, kahan_lanes_per_thread=1)
     fast = eng.eval_questions(quizzes)["priority"]
+    eng.set_eval_kernel(2, kahan_lanes_per_thread=4)
+    fast4 = eng.eval_questions(quizzes)["priority"]
+    assert np.array_equal(np.isnan(fast), np.isnan(fast4))
+    assert np.allclose(fast[~np.isnan(fast)], fast4[~np.isnan(fast)], rtol=TOL_STAGED, atol=0)
     eng.set_eval_kernel(1)
     exact = eng.eval_questions(quizzes)["priority"]
     assert np.array_equal(np.isnan(fast), np.isnan(exact))
