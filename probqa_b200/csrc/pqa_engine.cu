@@ -651,7 +651,7 @@ PqaError *Engine::SetQuizPriors(int64_t iQuiz, const double *pPriors) {
 PqaError *Engine::SetEvalKernel(int32_t which, int64_t chunkTargets, int64_t quizzesPerCta, int32_t kahanLanesPerThread) {
   if (which < 0 || which > 2) return ErrIndexOutOfRange(which, 0, 2, PQA_FILE_LINE "which");
   std::lock_guard<std::mutex> lk(mu_);
-  if (kahanLanesPerThread != 0 && kahanLanesPerThread != 1 && kahanLanesPerThread != 4)
+  if (kahanLanesPerThread != 0 && kahanLanesPerThread != 1 && kahanLanesPerThread != 2 && kahanLanesPerThread != 4)
     return ErrIndexOutOfRange(kahanLanesPerThread, 0, 4, PQA_FILE_LINE "kahanLanesPerThread must be 0, 1 or 4");
   evalCfg_.which = which; evalCfg_.chunkTargets = chunkTargets; evalCfg_.quizzesPerCta = quizzesPerCta;
   evalCfg_.kahanLanesPerThread = kahanLanesPerThread;
