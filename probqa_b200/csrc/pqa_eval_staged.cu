@@ -131,33 +131,24 @@ __device__ __forceinline__ void pass1_chunk(const double *__restrict__ sR, int64
   }
 }
 
-// Contributions of the elements that take the reference's Log2Hot (post >= 0.5, or zero / subnormal post). The arrays
-// are indexed dynamically, so this lives in local memory; it is touched only on the rare path.
-template <int K> struct SlowAcc { double iW[K]; double H[K]; double L; };
-
-// mask bit (k*KL + e) = element (answer k, Kahan lane e of this thread's vector); sRj / sID2j / prj point at lane 0.
-template <int K, int KL>
-__device__ __noinline__ void slow_elements(unsigned mask, const double *sRj, const double *sID2j, int64_t Jc,
-                                           const double *prj, const double *__restrict__ tbl, SlowAcc<K> &sa) {
-  while (mask) {
-    const int bit = __ffs((int)mask) - 1;
-    mask &= mask - 1;
-    const int k = bit / KL, e = bit - k * KL;
-    const double lik = __dmul_rn(sRj[k * Jc + e], __ldg(prj + e));      // :81-82
-    const double post = __dmul_rn(lik, sa.iW[k]);                       // :97
-    const double l2 = log2hot(post, tbl);                               // :106, reference semantics
-    sa.H[k] = __fma_rn(post, l2, sa.H[k]);                              // :113-114
-    sa.L = __fma_rn(sID2j[e], __ddiv_rn(1.0, l2), sa.L);                // :116-117
-  }
+// The reference's Log2Hot and an IEEE reciprocal for an element outside the fast range (post >= 0.5, or zero /
+// subnormal post). Out of line: it is the rare path and must not bloat the vector step.
+__device__ __noinline__ double slow_log2(double post, const double *__restrict__ tbl, double *rl2) {
+  const double l2 = log2hot(post, tbl);                                 // :106, reference semantics
+  *rl2 = __ddiv_rn(1.0, l2);
+  return l2;
 }
+
+// high word of post in [0x00100000, 0x3FE00000) <=> 2^-1022 <= post < 0.5 (positive, normal): the split log is accurate
+__device__ __forceinline__ unsigned fast_range_key(double post) { return (unsigned)__double2hiint(post) - 0x00100000u; }
+constexpr unsigned kFastRangeLimit = 0x3FE00000u - 0x00100000u;
 
 template <int K, int KL>
 __device__ __forceinline__ void pass2_chunk(const double *__restrict__ sR, const double *__restrict__ sLR,
                                             const double *__restrict__ sID2, int64_t Jc, int nVects, int64_t j0,
                                             const double *__restrict__ pr, const double *__restrict__ lpr,
                                             const double *__restrict__ tbl, int l0, const double (&iW)[K],
-                                            const double (&lW)[K], double (&H)[K], double (&V)[K], double (&L)[KL],
-                                            SlowAcc<K> &sa) {
+                                            const double (&lW)[K], double (&H)[K], double (&V)[K], double (&L)[KL]) {
   const double *prc = pr + j0 + l0, *lprc = lpr + j0 + l0;
   VecD<KL> pn = ldg_vec<KL>(prc), lpn = ldg_vec<KL>(lprc);
   for (int v = 0; v < nVects; v++) {
@@ -165,29 +156,52 @@ __device__ __forceinline__ void pass2_chunk(const double *__restrict__ sR, const
     if (v + 1 < nVects) { pn = ldg_vec<KL>(prc + 4 * (v + 1)); lpn = ldg_vec<KL>(lprc + 4 * (v + 1)); }
     const int j = 4 * v + l0;
     const VecD<KL> id2 = lds_vec<KL>(sID2 + j);
-    // The whole vector step is branch-free: elements that need the reference's Log2Hot contribute 0 to the entropy
-    // and lack sums here and are flagged; slow_elements() adds their true contributions afterwards (rare).
-    unsigned slow = 0;
+    // posteriors of the K*KL elements of this vector step, and whether all of them are in the fast range
+    double post[K][KL];
+    unsigned worst = 0;
 #pragma unroll
     for (int k = 0; k < K; k++) {
-      const VecD<KL> r = lds_vec<KL>(sR + k * Jc + j), lr = lds_vec<KL>(sLR + k * Jc + j);
+      const VecD<KL> r = lds_vec<KL>(sR + k * Jc + j);
 #pragma unroll
       for (int e = 0; e < KL; e++) {
-        const double lik = __dmul_rn(r.v[e], p.v[e]);                   // :81-82
-        const double post = __dmul_rn(lik, iW[k]);                      // :97
-        const double l2 = __dsub_rn(__dadd_rn(lr.v[e], lp.v[e]), lW[k]);
-        // high word in [0x00100000, 0x3FE00000) <=> 2^-1022 <= post < 0.5 (positive, normal): the split log is accurate
-        const unsigned hi = (unsigned)__double2hiint(post);
-        const bool s = hi - 0x00100000u >= 0x3FE00000u - 0x00100000u;
-        slow |= s ? (1u << (k * KL + e)) : 0u;
-        const double rl2 = fast_rcp(l2);
-        H[k] = __fma_rn(post, s ? 0.0 : l2, H[k]);                      // :113-114
-        L[e] = __fma_rn(id2.v[e], s ? 0.0 : rl2, L[e]);                 // :116-117 (id2 = 0 on gap / padding lanes)
-        const double d = __dsub_rn(post, p.v[e]);                       // :119
-        V[k] = __fma_rn(d, d, V[k]);                                    // :126-127
+        post[k][e] = __dmul_rn(__dmul_rn(r.v[e], p.v[e]), iW[k]);       // :81-82, :97
+        worst = max(worst, fast_range_key(post[k][e]));
       }
     }
-    if (slow) slow_elements<K, KL>(slow, sR + j, sID2 + j, Jc, prc + 4 * v, tbl, sa);
+    if (worst < kFastRangeLimit) {
+      // common case: no masks, no selects
+#pragma unroll
+      for (int k = 0; k < K; k++) {
+        const VecD<KL> lr = lds_vec<KL>(sLR + k * Jc + j);
+#pragma unroll
+        for (int e = 0; e < KL; e++) {
+          const double l2 = __dsub_rn(__dadd_rn(lr.v[e], lp.v[e]), lW[k]);
+          H[k] = __fma_rn(post[k][e], l2, H[k]);                        // :113-114
+          L[e] = __fma_rn(id2.v[e], fast_rcp(l2), L[e]);                // :116-117 (id2 = 0 on gap / padding lanes)
+          const double d = __dsub_rn(post[k][e], p.v[e]);               // :119
+          V[k] = __fma_rn(d, d, V[k]);                                  // :126-127
+        }
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < K; k++) {
+        const VecD<KL> lr = lds_vec<KL>(sLR + k * Jc + j);
+#pragma unroll
+        for (int e = 0; e < KL; e++) {
+          double l2, rl2;
+          if (fast_range_key(post[k][e]) < kFastRangeLimit) {
+            l2 = __dsub_rn(__dadd_rn(lr.v[e], lp.v[e]), lW[k]);
+            rl2 = fast_rcp(l2);
+          } else {
+            l2 = slow_log2(post[k][e], tbl, &rl2);
+          }
+          H[k] = __fma_rn(post[k][e], l2, H[k]);
+          L[e] = __fma_rn(id2.v[e], rl2, L[e]);
+          const double d = __dsub_rn(post[k][e], p.v[e]);
+          V[k] = __fma_rn(d, d, V[k]);
+        }
+      }
+    }
   }
 }
 
@@ -221,13 +235,12 @@ template <int KL> __device__ __forceinline__ double quiz_sum(double v) {
 
 template <int K, int KL>
 __device__ __forceinline__ void finish_pass2(const StagedParams &P, int64_t i, int64_t b, int l0, const double (&W)[K],
-                                             double (&H)[K], double (&V)[K], const double (&Lp)[KL],
-                                             const SlowAcc<K> &sa) {
-  double L = sa.L;
+                                             double (&H)[K], double (&V)[K], const double (&Lp)[KL]) {
+  double L = Lp[0];
 #pragma unroll
-  for (int e = 0; e < KL; e++) L = __dadd_rn(L, Lp[e]);
+  for (int e = 1; e < KL; e++) L = __dadd_rn(L, Lp[e]);
 #pragma unroll
-  for (int k = 0; k < K; k++) { H[k] = quiz_sum<KL>(__dadd_rn(H[k], sa.H[k])); V[k] = quiz_sum<KL>(V[k]); }
+  for (int k = 0; k < K; k++) { H[k] = quiz_sum<KL>(H[k]); V[k] = quiz_sum<KL>(V[k]); }
   L = quiz_sum<KL>(L);
   if (l0 != 0) return;
   const int64_t o = b * P.kb.Q + i;
@@ -306,12 +319,8 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_eval_staged(const StagedParam
       for (int k = 0; k < K; k++) { H[k] = 0.0; V[k] = 0.0; }
 #pragma unroll
       for (int e = 0; e < KL; e++) L[e] = 0.0;
-      SlowAcc<K> sa;
-      sa.L = 0.0;
-#pragma unroll
-      for (int k = 0; k < K; k++) { sa.iW[k] = iW[k]; sa.H[k] = 0.0; }
-      pass2_chunk<K, KL>(sR, sLR, sID2, P.Jc, nVects, 0, pr, lpr, tbl, l0, iW, lW, H, V, L, sa);
-      finish_pass2<K, KL>(P, i, b, l0, W, H, V, L, sa);
+      pass2_chunk<K, KL>(sR, sLR, sID2, P.Jc, nVects, 0, pr, lpr, tbl, l0, iW, lW, H, V, L);
+      finish_pass2<K, KL>(P, i, b, l0, W, H, V, L);
     }
   } else {
     // chunked targets: this thread keeps its quiz for the whole question
@@ -341,18 +350,14 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_eval_staged(const StagedParam
       __syncthreads();  // everyone is done with the buffers before the next stage overwrites them
     }
     if (live) finish_pass1<K, KL>(kw, W, iW, lW);
-    SlowAcc<K> sa;
-    sa.L = 0.0;
-#pragma unroll
-    for (int k = 0; k < K; k++) { sa.iW[k] = iW[k]; sa.H[k] = 0.0; }
     for (int64_t c = 0; c < P.nChunks; c++) {
       stage_chunk<K, THREADS>(P, i, c, true, sR, sLR, sID2, &bar, parity);
       const int64_t j0 = c * P.Jc;
       const int nVects = (int)(((Tp - j0 < P.Jc) ? (Tp - j0) : P.Jc) >> 2);
-      if (live) pass2_chunk<K, KL>(sR, sLR, sID2, P.Jc, nVects, j0, pr, lpr, tbl, l0, iW, lW, H, V, L, sa);
+      if (live) pass2_chunk<K, KL>(sR, sLR, sID2, P.Jc, nVects, j0, pr, lpr, tbl, l0, iW, lW, H, V, L);
       __syncthreads();
     }
-    if (live) finish_pass2<K, KL>(P, i, b, l0, W, H, V, L, sa);
+    if (live) finish_pass2<K, KL>(P, i, b, l0, W, H, V, L);
   }
 }
 
