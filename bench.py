@@ -215,6 +215,69 @@ def cpu_baseline(cfg, budget_s=12.0):
                 n_calls, "/".join(map(str, DEPTHS)), dt, cores)}
 
 
+def bench_question_sharded(args, cfg, pqa, dist, rank, world, local_rank, cores, barrier, max_over_ranks):
+    """Strong scaling of ONE batch over N GPUs: every rank holds Q/N questions of the KB and evaluates them for all B
+    quizzes; NCCL all-reduce (sum, zero-padded) of the [B][Q] priorities, then every rank selects. The whole step goes
+    through the public sharded API with host buffers, so value == e2e here."""
+    import torch
+    from probqa_b200 import sharded
+    Q, K, T, B = cfg["Q"], cfg["K"], cfg["T"], cfg["B"]
+    first, count = sharded.shard_ranges(Q, world)[rank]
+    eng = pqa.PqaEngineFactory().create_b200_engine(pqa.EngineDefinition(K, Q, T, init_amount=INIT), device=local_rank,
+                                                    emulated_workers=cores, rng_seed=1234, initial_quiz_capacity=B,
+                                                    question_shard_first=first, question_shard_count=count)
+    eng.upload_kb(*synth.binary_search_kb(Q, K, T, INIT, 3))
+    eng.set_eval_kernel(args.kernel, args.chunk_targets, args.quizzes_per_cta, args.lanes)
+    se = sharded.QuestionShardedEngine([sharded.B200Shard(eng)], group=dist.group.WORLD)
+    states = quiz_states(cfg, 0, B)
+    quizzes = se.start_quiz_batch(B)
+    for s in range(max(DEPTHS)):
+        sel = [x for x in range(B) if len(states[x]) > s]
+        if not sel:
+            break
+        se.set_active_question_batch(quizzes[sel], [states[x][s][0] for x in sel])
+        se.record_answer_batch(quizzes[sel], [states[x][s][1] for x in sel])
+    qevals_step = int(sum(Q - len(pf) for pf in states))
+    randoms = np.random.default_rng(99).integers(0, 2 ** 64, size=B, dtype=np.uint64)
+    for _ in range(args.warmup):
+        chosen = se.next_question_batch(quizzes, randoms)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = eng.kernel_launch_count()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        chosen = se.next_question_batch(quizzes, randoms)
+    torch.cuda.synchronize()
+    dt = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    launches = eng.kernel_launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    if rank != 0:
+        return
+    value = qevals_step * args.steps / dt
+    peak, peak_src = measured_peak()
+    line = {
+        "metric": METRIC, "value": value, "unit": "questions/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": args.workload, "Q": Q, "A": K, "T": T, "batch_total": B, "quiz_depths": list(DEPTHS),
+                   "kb": "binary_search_kb(init=0.1, rounds=3)",
+                   "parallelism": "questions sharded over %d GPUs (Q/N rows of sA/mD each), NCCL all-reduce of [B][Q] priorities" % world,
+                   "l2": "inputs re-read every step; KB shard %.1f MB" % (count * (K + 1) * T * 8 / 1e6),
+                   "timing": "wall clock around the public sharded API (host sync inside every step), max over ranks"},
+        "e2e": {"value": value, "unit": "questions/s", "h2d_bytes_per_step": int(B * 16), "d2h_bytes_per_step": int(B * 8),
+                "api": "sharded.QuestionShardedEngine.next_question_batch", "allreduce_bytes_per_step": int(B * Q * 8)},
+        "gpu_launches": int(launches), "clocks": clocks,
+        "roofline": {"bound": "hbm", "achieved": qevals_step * (K + 1) * T * 8 / (dt / args.steps) / 1e9 / world, "peak": peak,
+                     "unit": "GB/s", "frac": qevals_step * (K + 1) * T * 8 / (dt / args.steps) / 1e9 / world / peak, "traffic": None,
+                     "peak_source": peak_src, "note": "per GPU, whole step (evaluation + all-reduce + selection), algorithmic bytes"},
+    }
+    print(json.dumps(line), flush=True)
+    dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -227,6 +290,9 @@ def main():
     ap.add_argument("--chunk-targets", type=int, default=0)
     ap.add_argument("--lanes", type=int, default=0, help="Kahan lanes per thread of the staged kernel: 0 auto, 1, 4")
     ap.add_argument("--ref-quizzes", type=int, default=8, help="quizzes per step of the reference arm")
+    ap.add_argument("--shard", default="quizzes", choices=["quizzes", "questions"],
+                    help="N>1: quizzes = KB replicated, batch sharded, no collective; questions = each rank holds Q/N "
+                         "questions, NCCL all-reduce of the per-question priorities (probqa_b200/sharded.py)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-flush", action="store_true")
     args = ap.parse_args()
@@ -273,6 +339,8 @@ def main():
     from probqa_b200 import engine as pqa
     Q, K, T, B = cfg["Q"], cfg["K"], cfg["T"], cfg["B"]
     cores = host_cores()
+    if args.shard == "questions" and world > 1:
+        return bench_question_sharded(args, cfg, pqa, dist, rank, world, local_rank, cores, barrier, max_over_ranks)
     eng = pqa.PqaEngineFactory().create_b200_engine(pqa.EngineDefinition(K, Q, T, init_amount=INIT), device=local_rank,
                                                     emulated_workers=cores, rng_seed=1234 + rank, initial_quiz_capacity=B)
     eng.upload_kb(*synth.binary_search_kb(Q, K, T, INIT, 3))

@@ -18,6 +18,11 @@ typedef struct {
   int32_t _emulatedWorkers;
   uint64_t _rngSeed;         /* seed of the host xorshift128+ used by NextQuestion; 0 = std::random_device */
   int64_t _initialQuizCapacity; /* quiz slots pre-allocated on the device; 0 = 256 */
+  /* Question shard of a multi-GPU engine: this device holds the sA/mD rows of questions
+   * [_questionShardFirst, _questionShardFirst + _questionShardCount) only; _questionShardCount = 0 means all questions.
+   * Quiz state (priors, asked bits) is replicated on every shard; see the "question-sharded" entry points below. */
+  int64_t _questionShardFirst;
+  int64_t _questionShardCount;
 } CiB200Options;
 #pragma pack(pop)
 
@@ -76,6 +81,23 @@ PQACORE_API void *PqaB200_SetEvalKernel(void *pvEngine, int32_t which);
  * kahanLanesPerThread = 4 (one thread per quiz), 1 (four threads per quiz) or 0 (auto: 4 for batches >= 64). */
 PQACORE_API void *PqaB200_SetEvalTuning(void *pvEngine, int32_t which, int64_t chunkTargets, int64_t quizzesPerCta,
                                         int32_t kahanLanesPerThread);
+
+/* ---- question-sharded engines (one engine per GPU, each with a CiB200Options question shard) ----
+ * The exchange between shards is done by the caller (NCCL all-reduce through torch.distributed, or any other sum) on
+ * the device buffers returned by PqaB200_ShardBuffer; adding the other shards' zeros is exact, so results are those of a
+ * single engine. Protocol per NextQuestion:   ShardEval -> all-reduce(buffer 0, n*Q doubles) -> ShardSelect.
+ * Protocol per RecordAnswer:                  ShardRecordAnswerBegin -> all-reduce(buffer 1, n*Tp doubles) -> ...End.
+ * StartQuiz / ListTopTargets / SetActiveQuestion are local (replicated state). RecordQuizTarget / Train apply the
+ * operations of owned questions only; vB is updated on every shard. */
+PQACORE_API void *PqaB200_ShardEval(void *pvEngine, int64_t n, const int64_t *pQuizIds);
+PQACORE_API void *PqaB200_ShardSelect(void *pvEngine, int64_t n, const int64_t *pQuizIds, const uint64_t *pRandoms,
+                                      int64_t *pQuestions, void **ppErrors);
+PQACORE_API void *PqaB200_ShardRecordAnswerBegin(void *pvEngine, int64_t n, const int64_t *pQuizIds, const int64_t *pAnswers);
+PQACORE_API void *PqaB200_ShardRecordAnswerEnd(void *pvEngine, int64_t n, const int64_t *pQuizIds);
+/* which: 0 = priorities [n][Q], 1 = priors [n][Tp]. Returns the device pointer and the number of doubles of the last
+ * Shard* call that filled it. */
+PQACORE_API void *PqaB200_ShardBuffer(void *pvEngine, int32_t which, void **ppDevice, int64_t *pCount);
+PQACORE_API void *PqaB200_GetQuestionShard(void *pvEngine, int64_t *pFirst, int64_t *pCount);
 
 /* ---- device-resident stepping and timing (bench.py "value" leg: no host<->device traffic inside) ---- */
 /* Binds n quizzes as the resident batch: ids and one random draw per quiz are copied to the device once. */

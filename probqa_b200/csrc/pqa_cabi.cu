@@ -46,7 +46,7 @@ PqaError *CreateEngineImpl(const CiEngineDefinition *pEngDef, const CiB200Option
     return ErrInsufficientDims(pEngDef->_nAnswers, pEngDef->_nQuestions, pEngDef->_nTargets);
   CiB200Options opts;
   if (pOpts) opts = *pOpts;
-  else { opts._device = -1; opts._emulatedWorkers = 0; opts._rngSeed = 0; opts._initialQuizCapacity = 0; }
+  else { std::memset(&opts, 0, sizeof(opts)); opts._device = -1; }
   return Guard([&]() -> PqaError * { *out = new Engine(*pEngDef, opts); return nullptr; });
 }
 
@@ -80,7 +80,7 @@ PQACORE_API void *PqaB200_CreateEngine(void **ppError, const CiEngineDefinition 
 PQACORE_API void *PqaEngineFactory_LoadCpuEngine(void *pvFactory, void **ppError, const char *filePath,
                                                  uint64_t memPoolMaxBytes) {
   (void)pvFactory; (void)memPoolMaxBytes;
-  CiB200Options opts; opts._device = -1; opts._emulatedWorkers = 0; opts._rngSeed = 0; opts._initialQuizCapacity = 0;
+  CiB200Options opts; std::memset(&opts, 0, sizeof(opts)); opts._device = -1;
   PqaError *err = nullptr;
   Engine *eng = nullptr;
   PqaError *g = Guard([&]() -> PqaError * { eng = Engine::LoadKB(filePath, opts, &err); return nullptr; });
@@ -322,6 +322,33 @@ PQACORE_API void *PqaB200_SetEvalTuning(void *pvEngine, int32_t which, int64_t c
                                         int32_t kahanLanesPerThread) {
   if (!pvEngine) return NullEngine();
   return Ret(E(pvEngine)->SetEvalKernel(which, chunkTargets, quizzesPerCta, kahanLanesPerThread));
+}
+PQACORE_API void *PqaB200_ShardEval(void *pvEngine, int64_t n, const int64_t *pQuizIds) {
+  if (!pvEngine) return NullEngine();
+  return Ret(E(pvEngine)->ShardEval(n, pQuizIds));
+}
+PQACORE_API void *PqaB200_ShardSelect(void *pvEngine, int64_t n, const int64_t *pQuizIds, const uint64_t *pRandoms,
+                                      int64_t *pQuestions, void **ppErrors) {
+  if (!pvEngine) return NullEngine();
+  return Ret(E(pvEngine)->ShardSelect(n, pQuizIds, pRandoms, pQuestions, ppErrors));
+}
+PQACORE_API void *PqaB200_ShardRecordAnswerBegin(void *pvEngine, int64_t n, const int64_t *pQuizIds, const int64_t *pAnswers) {
+  if (!pvEngine) return NullEngine();
+  return Ret(E(pvEngine)->ShardRecordAnswerBegin(n, pQuizIds, pAnswers));
+}
+PQACORE_API void *PqaB200_ShardRecordAnswerEnd(void *pvEngine, int64_t n, const int64_t *pQuizIds) {
+  if (!pvEngine) return NullEngine();
+  return Ret(E(pvEngine)->ShardRecordAnswerEnd(n, pQuizIds));
+}
+PQACORE_API void *PqaB200_ShardBuffer(void *pvEngine, int32_t which, void **ppDevice, int64_t *pCount) {
+  if (!pvEngine) return NullEngine();
+  return Ret(E(pvEngine)->ShardBuffer(which, ppDevice, pCount));
+}
+PQACORE_API void *PqaB200_GetQuestionShard(void *pvEngine, int64_t *pFirst, int64_t *pCount) {
+  if (!pvEngine) return NullEngine();
+  if (pFirst) *pFirst = E(pvEngine)->questionShardFirst();
+  if (pCount) *pCount = E(pvEngine)->questionShardCount();
+  return nullptr;
 }
 PQACORE_API void *PqaB200_ResidentBind(void *pvEngine, int64_t n, const int64_t *pQuizIds, const uint64_t *pRandoms) {
   if (!pvEngine) return NullEngine();

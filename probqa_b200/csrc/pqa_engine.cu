@@ -60,6 +60,13 @@ Engine::Engine(const CiEngineDefinition &def, const CiB200Options &opts) {
   Tp_ = (T_ + 3) & ~3ll;
   askedWords_ = (Q_ + 63) >> 6;
   initAmount_ = def._initAmount;
+  qFirst_ = 0; qLocal_ = Q_;
+  if (opts._questionShardCount > 0) {
+    if (opts._questionShardFirst < 0 || opts._questionShardFirst + opts._questionShardCount > Q_)
+      throw std::runtime_error("probqa_b200: question shard [" + std::to_string(opts._questionShardFirst) + ", +" +
+                               std::to_string(opts._questionShardCount) + ") is outside 0.." + std::to_string(Q_));
+    qFirst_ = opts._questionShardFirst; qLocal_ = opts._questionShardCount;
+  }
   int nDev = 0;
   PQA_CU(cudaGetDeviceCount(&nDev));
   if (nDev <= 0) throw std::runtime_error("probqa_b200: no CUDA device is visible; this engine has no CPU path");
@@ -85,8 +92,8 @@ Engine::Engine(const CiEngineDefinition &def, const CiB200Options &opts) {
   if (!rng_[0] && !rng_[1]) rng_[1] = 1;
 
   PQA_CU(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
-  PQA_CU(cudaMalloc(&dSA_, sizeof(double) * (size_t)(Q_ * K_ * Tp_)));
-  PQA_CU(cudaMalloc(&dMD_, sizeof(double) * (size_t)(Q_ * Tp_)));
+  PQA_CU(cudaMalloc(&dSA_, sizeof(double) * (size_t)(qLocal_ * K_ * Tp_)));
+  PQA_CU(cudaMalloc(&dMD_, sizeof(double) * (size_t)(qLocal_ * Tp_)));
   PQA_CU(cudaMalloc(&dVB_, sizeof(double) * (size_t)Tp_));
   PQA_CU(cudaMalloc(&dLog2Tbl_, sizeof(double) * 1024));
   double tbl[1024];
@@ -114,6 +121,7 @@ DeviceKB Engine::kb() const {
   k.tgaps = nullptr; k.qgaps = nullptr;   // maintenance (RemoveQuestions/RemoveTargets) is out of scope: no gaps
   k.Q = Q_; k.K = K_; k.T = T_; k.Tp = Tp_;
   k.nValidTargets = T_;                    // CpuEngine.cpp:351 with no target gaps
+  k.qFirst = qFirst_; k.qCount = qLocal_;
   return k;
 }
 QuizPool Engine::pool() const {
@@ -220,6 +228,7 @@ PqaError *Engine::NextQuestionBatch(int64_t n, const int64_t *pQuizIds, const ui
   if (n < 0) return ErrNegativeCount(n, PQA_FILE_LINE "|n| must be non-negative.");
   if (n == 0) return nullptr;
   if (!pQuizIds || !pQuestions) return MakeError(ErrCode::NullArgument, PQA_FILE_LINE "pQuizIds/pQuestions");
+  if (qLocal_ != Q_) return ErrNotImplemented("NextQuestion on a question-sharded engine: use PqaB200_ShardEval / ShardSelect");
   std::lock_guard<std::mutex> lk(mu_);
   PQA_TRY
   // validate; quizzes that fail validation get their own error and are left out of the launch
@@ -284,20 +293,10 @@ PqaError *Engine::RecordAnswerBatch(int64_t n, const int64_t *pQuizIds, const in
   if (n < 0) return ErrNegativeCount(n, PQA_FILE_LINE "|n| must be non-negative.");
   if (n == 0) return nullptr;
   if (!pQuizIds || !pAnswers) return MakeError(ErrCode::NullArgument, PQA_FILE_LINE "pQuizIds/pAnswers");
+  if (qLocal_ != Q_) return ErrNotImplemented("RecordAnswer on a question-sharded engine: use PqaB200_ShardRecordAnswerBegin / End");
   std::lock_guard<std::mutex> lk(mu_);
   PQA_TRY
-  for (int64_t x = 0; x < n; x++) {  // validate everything before touching any quiz
-    if (pAnswers[x] < 0 || pAnswers[x] >= K_)
-      return ErrIndexOutOfRange(pAnswers[x], 0, K_ - 1, "Answer index is not in the answer range.");
-    if (PqaError *e = CheckQuiz(pQuizIds[x])) return e;
-    const HostQuiz &q = quizzes_[pQuizIds[x]];
-    if (q.activeQuestion == -1)
-      return ErrNoQuizActiveQuestion(pAnswers[x], PQA_FILE_LINE "An attempt to record an answer in a quiz that doesn't"
-                                                  " have an active question");
-    if (q.activeQuestion < 0 || q.activeQuestion >= Q_)
-      return ErrNoQuizActiveQuestion(pAnswers[x], PQA_FILE_LINE "An attempt to record an answer in a quiz that has"
-                                                  " invalid active question");
-  }
+  if (PqaError *e = ValidateRecordAnswer(n, pQuizIds, pAnswers)) return e;
   UploadIds(n, pQuizIds);
   hAnswers_.ensure(n); dAnswers_.ensure(n, stream_);
   std::memcpy(hAnswers_.get(), pAnswers, sizeof(int64_t) * (size_t)n);
@@ -315,6 +314,130 @@ PqaError *Engine::RecordAnswerBatch(int64_t n, const int64_t *pQuizIds, const in
 }
 
 PqaError *Engine::RecordAnswer(int64_t iQuiz, int64_t iAnswer) { return RecordAnswerBatch(1, &iQuiz, &iAnswer); }
+
+PqaError *Engine::ValidateRecordAnswer(int64_t n, const int64_t *pQuizIds, const int64_t *pAnswers) const {
+  for (int64_t x = 0; x < n; x++) {  // validate everything before touching any quiz
+    if (pAnswers[x] < 0 || pAnswers[x] >= K_)
+      return ErrIndexOutOfRange(pAnswers[x], 0, K_ - 1, "Answer index is not in the answer range.");
+    if (PqaError *e = CheckQuiz(pQuizIds[x])) return e;
+    const HostQuiz &q = quizzes_[pQuizIds[x]];
+    if (q.activeQuestion == -1)
+      return ErrNoQuizActiveQuestion(pAnswers[x], PQA_FILE_LINE "An attempt to record an answer in a quiz that doesn't"
+                                                  " have an active question");
+    if (q.activeQuestion < 0 || q.activeQuestion >= Q_)
+      return ErrNoQuizActiveQuestion(pAnswers[x], PQA_FILE_LINE "An attempt to record an answer in a quiz that has"
+                                                  " invalid active question");
+  }
+  return nullptr;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Question-sharded operation: see the protocol in include/PqaB200Ext.h. The buffers are filled here, summed across
+// shards by the caller, and consumed by the second half of each operation.
+PqaError *Engine::ShardEval(int64_t n, const int64_t *pQuizIds) {
+  if (n <= 0) return ErrNegativeCount(n, PQA_FILE_LINE "|n| must be positive.");
+  std::lock_guard<std::mutex> lk(mu_);
+  for (int64_t x = 0; x < n; x++)
+    if (PqaError *e = CheckQuiz(pQuizIds[x])) return e;
+  PQA_TRY
+  UploadIds(n, pQuizIds);
+  shardPriorityCount_ = n * Q_;
+  dShardPriority_.ensure((size_t)shardPriorityCount_, stream_);
+  PQA_CU(cudaMemsetAsync(dShardPriority_.get(), 0, sizeof(double) * (size_t)shardPriorityCount_, stream_));  // +0.0
+  EvalDetail det{nullptr, nullptr, nullptr, nullptr};
+  launch_eval_questions(kb(), pool(), n, dIds_.get(), dShardPriority_.get(), det, evalCfg_, stream_);
+  PQA_CU(cudaStreamSynchronize(stream_));   // the caller's collective runs on another stream
+  return nullptr;
+  PQA_CATCH_RETURN_ERR
+}
+
+PqaError *Engine::ShardSelect(int64_t n, const int64_t *pQuizIds, const uint64_t *pRandoms, int64_t *pQuestions,
+                              void **ppErrors) {
+  if (n <= 0) return ErrNegativeCount(n, PQA_FILE_LINE "|n| must be positive.");
+  if (!pQuizIds || !pQuestions || !pRandoms)
+    return MakeError(ErrCode::NullArgument, PQA_FILE_LINE "pQuizIds/pQuestions/pRandoms (every shard must use the same draws)");
+  std::lock_guard<std::mutex> lk(mu_);
+  if (shardPriorityCount_ != n * Q_) return MakeError(ErrCode::NotInitialized, PQA_FILE_LINE "ShardSelect without a matching ShardEval");
+  for (int64_t x = 0; x < n; x++)
+    if (PqaError *e = CheckQuiz(pQuizIds[x])) return e;
+  PQA_TRY
+  UploadIds(n, pQuizIds);
+  hRandoms_.ensure(n); dRandoms_.ensure(n, stream_);
+  std::memcpy(hRandoms_.get(), pRandoms, sizeof(uint64_t) * (size_t)n);
+  PQA_CU(cudaMemcpyAsync(dRandoms_.get(), hRandoms_.get(), sizeof(uint64_t) * (size_t)n, cudaMemcpyHostToDevice, stream_));
+  dRunLength_.ensure((size_t)(n * Q_), stream_); dQuestions_.ensure(n, stream_); hQuestions_.ensure(n);
+  launch_select_question(kb(), pool(), n, dIds_.get(), dShardPriority_.get(), dRandoms_.get(), W_, dRunLength_.get(),
+                         nullptr, dQuestions_.get(), 1, stream_);
+  PQA_CU(cudaMemcpyAsync(hQuestions_.get(), dQuestions_.get(), sizeof(int64_t) * (size_t)n, cudaMemcpyDeviceToHost, stream_));
+  PQA_CU(cudaStreamSynchronize(stream_));
+  PqaError *firstErr = nullptr;
+  uint64_t nAsked = 0;
+  for (int64_t x = 0; x < n; x++) {
+    const int64_t qst = hQuestions_.get()[x];
+    pQuestions[x] = qst;
+    if (ppErrors) ppErrors[x] = nullptr;
+    if (qst < 0) {
+      PqaError *e = MakeError(ErrCode::QuestionsExhausted, PQA_FILE_LINE "Found no unasked question that is not in a gap.");
+      if (ppErrors) ppErrors[x] = e;
+      else if (!firstErr) firstErr = e;
+      else delete e;
+      continue;
+    }
+    quizzes_[pQuizIds[x]].activeQuestion = qst;
+    nAsked++;
+  }
+  nQuestionsAsked_.fetch_add(nAsked, std::memory_order_relaxed);
+  return firstErr;
+  PQA_CATCH_RETURN_ERR
+}
+
+PqaError *Engine::ShardRecordAnswerBegin(int64_t n, const int64_t *pQuizIds, const int64_t *pAnswers) {
+  if (n <= 0) return ErrNegativeCount(n, PQA_FILE_LINE "|n| must be positive.");
+  if (!pQuizIds || !pAnswers) return MakeError(ErrCode::NullArgument, PQA_FILE_LINE "pQuizIds/pAnswers");
+  std::lock_guard<std::mutex> lk(mu_);
+  PQA_TRY
+  if (PqaError *e = ValidateRecordAnswer(n, pQuizIds, pAnswers)) return e;
+  UploadIds(n, pQuizIds);
+  hAnswers_.ensure(n); dAnswers_.ensure(n, stream_);
+  std::memcpy(hAnswers_.get(), pAnswers, sizeof(int64_t) * (size_t)n);
+  PQA_CU(cudaMemcpyAsync(dAnswers_.get(), hAnswers_.get(), sizeof(int64_t) * (size_t)n, cudaMemcpyHostToDevice, stream_));
+  const int looseW = std::max(1, W_ - 1);
+  launch_record_answer(kb(), pool(), n, dIds_.get(), dAnswers_.get(), looseW, stream_);   // owner: update; others: zeros
+  shardPriorsCount_ = n * Tp_;
+  dShardPriors_.ensure((size_t)shardPriorsCount_, stream_);
+  launch_gather_prior_rows(pool(), n, dIds_.get(), dShardPriors_.get(), stream_);
+  for (int64_t x = 0; x < n; x++) {
+    HostQuiz &q = quizzes_[pQuizIds[x]];
+    q.answers.push_back(CiAnsweredQuestion{q.activeQuestion, pAnswers[x]});
+    q.activeQuestion = -1;
+  }
+  PQA_CU(cudaStreamSynchronize(stream_));
+  return nullptr;
+  PQA_CATCH_RETURN_ERR
+}
+
+PqaError *Engine::ShardRecordAnswerEnd(int64_t n, const int64_t *pQuizIds) {
+  if (n <= 0) return ErrNegativeCount(n, PQA_FILE_LINE "|n| must be positive.");
+  std::lock_guard<std::mutex> lk(mu_);
+  if (shardPriorsCount_ != n * Tp_) return MakeError(ErrCode::NotInitialized, PQA_FILE_LINE "ShardRecordAnswerEnd without a matching Begin");
+  for (int64_t x = 0; x < n; x++)
+    if (PqaError *e = CheckQuiz(pQuizIds[x])) return e;
+  PQA_TRY
+  UploadIds(n, pQuizIds);
+  launch_scatter_prior_rows(pool(), n, dIds_.get(), dShardPriors_.get(), stream_);
+  PQA_CU(cudaStreamSynchronize(stream_));
+  return nullptr;
+  PQA_CATCH_RETURN_ERR
+}
+
+PqaError *Engine::ShardBuffer(int32_t which, void **ppDevice, int64_t *pCount) {
+  std::lock_guard<std::mutex> lk(mu_);
+  if (!ppDevice || !pCount) return MakeError(ErrCode::NullArgument, PQA_FILE_LINE "ppDevice/pCount");
+  if (which == 0) { *ppDevice = dShardPriority_.get(); *pCount = shardPriorityCount_; }
+  else if (which == 1) { *ppDevice = dShardPriors_.get(); *pCount = shardPriorsCount_; }
+  else return ErrIndexOutOfRange(which, 0, 1, PQA_FILE_LINE "which");
+  return nullptr;
+}
 
 int64_t Engine::GetActiveQuestionId(PqaError **err, int64_t iQuiz) {
   std::lock_guard<std::mutex> lk(mu_);
@@ -404,10 +527,15 @@ void Engine::AppendQuizOps(std::vector<TrainOp> &ops, const CiAnsweredQuestion *
   if (x < n) ops.push_back(TrainOp{aqs[x]._iQuestion, aqs[x]._iAnswer, -1, iTarget, amount});
 }
 
-PqaError *Engine::ApplyTrain(const std::vector<TrainOp> &ops, const std::vector<int64_t> &targets,
+PqaError *Engine::ApplyTrain(const std::vector<TrainOp> &opsAll, const std::vector<int64_t> &targets,
                              const std::vector<double> &amounts) {
   // caller holds mu_
   PQA_TRY
+  std::vector<TrainOp> owned;
+  if (qLocal_ != Q_) {   // question-sharded engine: cells of other shards' questions are theirs to update
+    for (const TrainOp &o : opsAll) if (OwnsQuestion(o.q)) owned.push_back(o);
+  }
+  const std::vector<TrainOp> &ops = (qLocal_ != Q_) ? owned : opsAll;
   const int64_t nOps = (int64_t)ops.size();
   if (nOps > 0) {
     std::vector<int64_t> order(nOps);
@@ -544,18 +672,20 @@ PqaError *Engine::CopyATargets(int64_t iQuestion, int64_t iAnswer, int64_t maxTa
   std::lock_guard<std::mutex> lk(mu_);
   if (iQuestion < 0 || iQuestion >= Q_) return ErrIndexOutOfRange(iQuestion, 0, Q_ - 1, PQA_FILE_LINE "Question index is not in KB range.");
   if (iAnswer < 0 || iAnswer >= K_) return ErrIndexOutOfRange(iAnswer, 0, K_ - 1, PQA_FILE_LINE "Answer index is not in KB range.");
+  if (!OwnsQuestion(iQuestion)) return ErrIndexOutOfRange(iQuestion, qFirst_, qFirst_ + qLocal_ - 1, PQA_FILE_LINE "Question is not in this engine's shard.");
   PQA_TRY
   const int64_t cnt = std::min(maxTargets, T_);
-  if (cnt > 0) PQA_CU(cudaMemcpy(pFreqs, dSA_ + (iQuestion * K_ + iAnswer) * Tp_, sizeof(double) * (size_t)cnt, cudaMemcpyDeviceToHost));
+  if (cnt > 0) PQA_CU(cudaMemcpy(pFreqs, dSA_ + ((iQuestion - qFirst_) * K_ + iAnswer) * Tp_, sizeof(double) * (size_t)cnt, cudaMemcpyDeviceToHost));
   return nullptr;
   PQA_CATCH_RETURN_ERR
 }
 PqaError *Engine::CopyDTargets(int64_t iQuestion, int64_t maxTargets, double *pFreqs) {
   std::lock_guard<std::mutex> lk(mu_);
   if (iQuestion < 0 || iQuestion >= Q_) return ErrIndexOutOfRange(iQuestion, 0, Q_ - 1, PQA_FILE_LINE "Question index is not in KB range.");
+  if (!OwnsQuestion(iQuestion)) return ErrIndexOutOfRange(iQuestion, qFirst_, qFirst_ + qLocal_ - 1, PQA_FILE_LINE "Question is not in this engine's shard.");
   PQA_TRY
   const int64_t cnt = std::min(maxTargets, T_);
-  if (cnt > 0) PQA_CU(cudaMemcpy(pFreqs, dMD_ + iQuestion * Tp_, sizeof(double) * (size_t)cnt, cudaMemcpyDeviceToHost));
+  if (cnt > 0) PQA_CU(cudaMemcpy(pFreqs, dMD_ + (iQuestion - qFirst_) * Tp_, sizeof(double) * (size_t)cnt, cudaMemcpyDeviceToHost));
   return nullptr;
   PQA_CATCH_RETURN_ERR
 }
@@ -573,6 +703,9 @@ PqaError *Engine::UploadKB(const double *sA, const double *mD, const double *vB)
   if (!sA || !mD || !vB) return MakeError(ErrCode::NullArgument, PQA_FILE_LINE "sA/mD/vB");
   std::lock_guard<std::mutex> lk(mu_);
   PQA_TRY
+  // the host arrays always describe the whole KB; a question-sharded engine takes its rows out of them
+  sA += qFirst_ * K_ * T_; mD += qFirst_ * T_;
+  const int64_t Q_ = qLocal_;   // rows handled below
   if (Tp_ == T_) {
     PQA_CU(cudaMemcpyAsync(dSA_, sA, sizeof(double) * (size_t)(Q_ * K_ * T_), cudaMemcpyHostToDevice, stream_));
     PQA_CU(cudaMemcpyAsync(dMD_, mD, sizeof(double) * (size_t)(Q_ * T_), cudaMemcpyHostToDevice, stream_));
@@ -602,6 +735,10 @@ PqaError *Engine::UploadKB(const double *sA, const double *mD, const double *vB)
 PqaError *Engine::DownloadKB(double *sA, double *mD, double *vB) {
   std::lock_guard<std::mutex> lk(mu_);
   PQA_TRY
+  // whole-KB host arrays; a question-sharded engine fills its rows only
+  if (sA) sA += qFirst_ * K_ * T_;
+  if (mD) mD += qFirst_ * T_;
+  const int64_t Q_ = qLocal_;
   if (Tp_ == T_) {
     if (sA) PQA_CU(cudaMemcpyAsync(sA, dSA_, sizeof(double) * (size_t)(Q_ * K_ * T_), cudaMemcpyDeviceToHost, stream_));
     if (mD) PQA_CU(cudaMemcpyAsync(mD, dMD_, sizeof(double) * (size_t)(Q_ * T_), cudaMemcpyDeviceToHost, stream_));

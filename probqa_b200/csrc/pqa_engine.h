@@ -99,6 +99,15 @@ class Engine {
   PqaError *EvalQuestionsDetailed(int64_t iQuiz, double *pW, double *pH, double *pV, double *pLack, double *pPriorities);
   PqaError *SetEvalKernel(int32_t which, int64_t chunkTargets, int64_t quizzesPerCta, int32_t kahanLanesPerThread);
 
+  // --- question-sharded operation (PqaB200Ext.h) ---
+  PqaError *ShardEval(int64_t n, const int64_t *pQuizIds);
+  PqaError *ShardSelect(int64_t n, const int64_t *pQuizIds, const uint64_t *pRandoms, int64_t *pQuestions, void **ppErrors);
+  PqaError *ShardRecordAnswerBegin(int64_t n, const int64_t *pQuizIds, const int64_t *pAnswers);
+  PqaError *ShardRecordAnswerEnd(int64_t n, const int64_t *pQuizIds);
+  PqaError *ShardBuffer(int32_t which, void **ppDevice, int64_t *pCount);
+  int64_t questionShardFirst() const { return qFirst_; }
+  int64_t questionShardCount() const { return qLocal_; }
+
   // --- device-resident stepping ---
   PqaError *ResidentBind(int64_t n, const int64_t *pQuizIds, const uint64_t *pRandoms);
   PqaError *ResidentStep();
@@ -112,6 +121,10 @@ class Engine {
 
  private:
   PqaError *CheckQuiz(int64_t iQuiz) const;              // BaseEngine::UseQuiz, BaseEngine.cpp:399-419
+  PqaError *ValidateRecordAnswer(int64_t n, const int64_t *pQuizIds, const int64_t *pAnswers) const;
+  PqaError *FinishNextQuestion(int64_t m, const std::vector<int64_t> &valid, const std::vector<int64_t> &where,
+                               int64_t *pQuestions, void **ppErrors, PqaError *firstErr);
+  bool OwnsQuestion(int64_t q) const { return q >= qFirst_ && q < qFirst_ + qLocal_; }
   int64_t AssignQuizId();                                // BaseEngine::AssignQuiz + GapTracker::Acquire
   void EnsureQuizCapacity(int64_t nSlots);
   void EnsureBatchScratch(int64_t n, bool needTop, int64_t maxCount);
@@ -127,6 +140,9 @@ class Engine {
   mutable std::mutex mu_;
   int device_ = 0, W_ = 1, smCount_ = 148;
   int64_t Q_ = 0, K_ = 0, T_ = 0, Tp_ = 0, askedWords_ = 0;
+  int64_t qFirst_ = 0, qLocal_ = 0;   // question shard held by this engine (0, Q_ for a single-device engine)
+  int64_t shardPriorityCount_ = 0, shardPriorsCount_ = 0;
+  DevBuf<double> dShardPriority_, dShardPriors_;
   double initAmount_ = 0;
   cudaStream_t stream_ = nullptr;
   EvalConfig evalCfg_;

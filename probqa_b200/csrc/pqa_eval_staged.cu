@@ -80,7 +80,7 @@ template <int KL> __device__ __forceinline__ VecD<KL> ldg_vec(const double *p) {
 }
 
 template <int K, int THREADS>
-__device__ __forceinline__ void stage_chunk(const StagedParams &P, int64_t i, int64_t c, bool withLog, double *sR,
+__device__ __forceinline__ void stage_chunk(const StagedParams &P, int64_t iLocal, int64_t c, bool withLog, double *sR,
                                             double *sLR, double *sID2, uint64_t *bar, uint32_t &parity) {
   const int64_t Jc = P.Jc, Tp = P.kb.Tp, T = P.kb.T;
   const int64_t j0 = c * Jc;
@@ -91,8 +91,8 @@ __device__ __forceinline__ void stage_chunk(const StagedParams &P, int64_t i, in
     const uint32_t bytes = (uint32_t)(cnt * sizeof(double));
     mbar_arrive_expect_tx(bar, bytes * (K + 1));
 #pragma unroll
-    for (int k = 0; k < K; k++) bulk_g2s(sR + k * Jc, P.kb.sA + (i * K + k) * Tp + j0, bytes, bar);
-    bulk_g2s(sID2, P.kb.mD + i * Tp + j0, bytes, bar);
+    for (int k = 0; k < K; k++) bulk_g2s(sR + k * Jc, P.kb.sA + (iLocal * K + k) * Tp + j0, bytes, bar);
+    bulk_g2s(sID2, P.kb.mD + iLocal * Tp + j0, bytes, bar);
   }
   mbar_wait(bar, parity);
   parity ^= 1u;
@@ -276,7 +276,7 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_eval_staged(const StagedParam
   double *sLR = sR + K * P.Jc;         // [K][Jc]  log2 r
   double *sID2 = sLR + K * P.Jc;       // [Jc]     mD, then 1/mD^2
 
-  const int64_t i = blockIdx.x, Q = P.kb.Q, Tp = P.kb.Tp;
+  const int64_t iLocal = blockIdx.x, i = P.kb.qFirst + iLocal, Q = P.kb.Q, Tp = P.kb.Tp;
   const int64_t tileFirst = (int64_t)blockIdx.y * P.quizzesPerCta;
   const int64_t tileLimit = (tileFirst + P.quizzesPerCta < P.n) ? tileFirst + P.quizzesPerCta : P.n;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -293,7 +293,7 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_eval_staged(const StagedParam
   const double *__restrict__ tbl = P.kb.log2tbl;
 
   if (P.nChunks == 1) {
-    stage_chunk<K, THREADS>(P, i, 0, true, sR, sLR, sID2, &bar, parity);
+    stage_chunk<K, THREADS>(P, iLocal, 0, true, sR, sLR, sID2, &bar, parity);
     const int nVects = (int)(Tp >> 2);
     for (int64_t g0 = tileFirst + (int64_t)warp * QPW; g0 < tileLimit; g0 += (int64_t)WARPS * QPW) {
       const int64_t b = g0 + qw;
@@ -343,7 +343,7 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_eval_staged(const StagedParam
       for (int k = 0; k < K; k++) kw[e][k].init();
     }
     for (int64_t c = 0; c < P.nChunks; c++) {
-      stage_chunk<K, THREADS>(P, i, c, false, sR, sLR, sID2, &bar, parity);
+      stage_chunk<K, THREADS>(P, iLocal, c, false, sR, sLR, sID2, &bar, parity);
       const int64_t j0 = c * P.Jc;
       const int nVects = (int)(((Tp - j0 < P.Jc) ? (Tp - j0) : P.Jc) >> 2);
       if (live) pass1_chunk<K, KL>(sR, P.Jc, nVects, j0, pr, l0, kw);
@@ -351,7 +351,7 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_eval_staged(const StagedParam
     }
     if (live) finish_pass1<K, KL>(kw, W, iW, lW);
     for (int64_t c = 0; c < P.nChunks; c++) {
-      stage_chunk<K, THREADS>(P, i, c, true, sR, sLR, sID2, &bar, parity);
+      stage_chunk<K, THREADS>(P, iLocal, c, true, sR, sLR, sID2, &bar, parity);
       const int64_t j0 = c * P.Jc;
       const int nVects = (int)(((Tp - j0 < P.Jc) ? (Tp - j0) : P.Jc) >> 2);
       if (live) pass2_chunk<K, KL>(sR, sLR, sID2, P.Jc, nVects, j0, pr, lpr, tbl, l0, iW, lW, H, V, L);
@@ -377,13 +377,13 @@ static void launch_cfg(StagedParams P, const EvalConfig &cfg, size_t smem, cudaS
     // enough CTAs for ~12 waves of 2 CTAs/SM when the batch allows it, else one pass per CTA
     const int64_t passesTotal = (P.n + perPass - 1) / perPass;
     const int64_t targetCtas = (int64_t)cfg.smCount * 2 * 12;
-    int64_t passesPerCta = (P.kb.Q * passesTotal) / targetCtas;
+    int64_t passesPerCta = (P.kb.qCount * passesTotal) / targetCtas;
     if (passesPerCta < 1) passesPerCta = 1;
     if (passesPerCta > passesTotal) passesPerCta = passesTotal;
     P.quizzesPerCta = passesPerCta * perPass;
   }
   const int64_t tiles = (P.n + P.quizzesPerCta - 1) / P.quizzesPerCta;
-  dim3 grid((unsigned)P.kb.Q, (unsigned)tiles);
+  dim3 grid((unsigned)P.kb.qCount, (unsigned)tiles);
   k_eval_staged<K, KL, WARPS><<<grid, WARPS * 32, smem, st>>>(P);
   count_launch();
 }

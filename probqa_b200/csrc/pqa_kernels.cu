@@ -24,7 +24,7 @@ static inline int grid_for(int64_t n, int block, int cap = 148 * 16) {
 // ---------------------------------------------------------------------------------------------------------
 // KB initialisation (CpuEngine.cpp:34-93: sA = init^2, mD = K*init^2, vB = init) and row packing.
 __global__ void k_fill_kb(DeviceKB kb, double initSqr, double initMD, double init1) {
-  const int64_t nA = kb.Q * kb.K * kb.Tp, nD = kb.Q * kb.Tp, stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t nA = kb.qCount * kb.K * kb.Tp, nD = kb.qCount * kb.Tp, stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; x < nA; x += stride)
     kb.sA[x] = (x % kb.Tp) < kb.T ? initSqr : 0.0;
   for (int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; x < nD; x += stride)
@@ -84,9 +84,19 @@ __global__ void __launch_bounds__(256) k_update_priors(DeviceKB kb, QuizPool qp,
   int64_t q = -1;
   if (MODE == 1) {
     q = qp.active[slot];
+    if (q < kb.qFirst || q >= kb.qFirst + kb.qCount) {
+      // question-sharded engine, question owned by another device: contribute zeros to the all-reduce of the
+      // updated priors (x + 0 is exact), keep the bookkeeping of CEQuiz.h:90-92 identical on every device
+      for (int64_t j = threadIdx.x; j < Tp; j += blockDim.x) prior[j] = 0.0;
+      if (threadIdx.x == 0) {
+        qp.asked[slot * qp.askedWords + (q >> 6)] |= 1ull << (q & 63);
+        qp.active[slot] = -1;
+      }
+      return;
+    }
     const int64_t a = answers[blockIdx.x];
-    rowA = kb.sA + (q * kb.K + a) * Tp;
-    rowD = kb.mD + q * Tp;
+    rowA = kb.sA + ((q - kb.qFirst) * kb.K + a) * Tp;
+    rowD = kb.mD + (q - kb.qFirst) * Tp;
   }
   for (int64_t j = threadIdx.x; j < Tp; j += blockDim.x) {
     double m = 0.0;
@@ -158,6 +168,30 @@ void launch_refresh_log_priors(const QuizPool &qp, int64_t n, const int64_t *dSl
   count_launch();
 }
 
+// prior rows of a batch <-> a contiguous [n][Tp] staging buffer (all-reduce of updated priors in question-sharded mode)
+__global__ void k_gather_prior_rows(QuizPool qp, const int64_t *__restrict__ slots, double *__restrict__ buf) {
+  const int64_t slot = slots[blockIdx.x];
+  for (int64_t j = threadIdx.x; j < qp.Tp; j += blockDim.x) buf[blockIdx.x * qp.Tp + j] = qp.priors[slot * qp.Tp + j];
+}
+__global__ void k_scatter_prior_rows(QuizPool qp, const int64_t *__restrict__ slots, const double *__restrict__ buf) {
+  const int64_t slot = slots[blockIdx.x];
+  for (int64_t j = threadIdx.x; j < qp.Tp; j += blockDim.x) {
+    const double v = buf[blockIdx.x * qp.Tp + j];
+    qp.priors[slot * qp.Tp + j] = v;
+    qp.logPriors[slot * qp.Tp + j] = log2(v);
+  }
+}
+void launch_gather_prior_rows(const QuizPool &qp, int64_t n, const int64_t *dSlots, double *dBuf, cudaStream_t st) {
+  if (n <= 0) return;
+  k_gather_prior_rows<<<(unsigned)n, 256, 0, st>>>(qp, dSlots, dBuf);
+  count_launch();
+}
+void launch_scatter_prior_rows(const QuizPool &qp, int64_t n, const int64_t *dSlots, const double *dBuf, cudaStream_t st) {
+  if (n <= 0) return;
+  k_scatter_prior_rows<<<(unsigned)n, 256, 0, st>>>(qp, dSlots, dBuf);
+  count_launch();
+}
+
 __global__ void k_set_active(QuizPool qp, int64_t n, const int64_t *__restrict__ slots,
                              const int64_t *__restrict__ questions) {
   const int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -188,7 +222,7 @@ void launch_flush_l2(void *buf, size_t bytes, cudaStream_t st) {
 __global__ void __launch_bounds__(128) k_eval_exact(DeviceKB kb, QuizPool qp, int64_t n,
                                                     const int64_t *__restrict__ slots,
                                                     double *__restrict__ priority, EvalDetail det) {
-  const int64_t i = blockIdx.x;
+  const int64_t iLocal = blockIdx.x, i = kb.qFirst + iLocal;
   const int lane = threadIdx.x & 3;
   const int64_t b = (int64_t)blockIdx.y * 32 + (threadIdx.x >> 2);
   if (b >= n) return;  // whole 4-thread group leaves together
@@ -199,7 +233,7 @@ __global__ void __launch_bounds__(128) k_eval_exact(DeviceKB kb, QuizPool qp, in
   }
   const int64_t T = kb.T, Tp = kb.Tp, K = kb.K, nTV = Tp >> 2;
   const double *__restrict__ prior = qp.priors + slot * Tp;
-  const double *__restrict__ mDi = kb.mD + i * Tp;
+  const double *__restrict__ mDi = kb.mD + iLocal * Tp;
   const double *__restrict__ tbl = kb.log2tbl;
 
   Kahan totW; totW.init(0.0);        // scalar accumulator, every lane carries an identical copy (:89,:134)
@@ -207,7 +241,7 @@ __global__ void __launch_bounds__(128) k_eval_exact(DeviceKB kb, QuizPool qp, in
   Kahan avgH, avgV; avgH.init(); avgV.init();  // this thread's lane of accAvgH / accAvgV (:139-172)
   const int64_t nVectorized = (K >> 2) << 2;
   for (int64_t k = 0; k < K; k++) {
-    const double *__restrict__ sAik = kb.sA + (i * K + k) * Tp;
+    const double *__restrict__ sAik = kb.sA + (iLocal * K + k) * Tp;
     Kahan accW; accW.init();
     for (int64_t v = 0; v < nTV; v++) {                          // pass 1 (:66-87)
       const int64_t j = 4 * v + lane;
@@ -272,7 +306,7 @@ void launch_eval_questions(const DeviceKB &kb, const QuizPool &qp, int64_t n, co
                            double *dPriority, const EvalDetail &det, const EvalConfig &cfg, cudaStream_t st) {
   if (n <= 0) return;
   if (cfg.which == 1) {
-    dim3 grid((unsigned)kb.Q, (unsigned)((n + 31) / 32));
+    dim3 grid((unsigned)kb.qCount, (unsigned)((n + 31) / 32));
     k_eval_exact<<<grid, 128, 0, st>>>(kb, qp, n, dSlots, dPriority, det);
     count_launch();
   } else {
@@ -551,8 +585,9 @@ __global__ void k_train_ops(DeviceKB kb, const TrainOp *__restrict__ ops, const 
   for (int64_t o = groupStart[g]; o < groupStart[g + 1]; o++) {
     const TrainOp op = ops[o];
     const double b = op.amount;
-    double *cellD = kb.mD + op.q * kb.Tp + op.target;
-    double *cellA0 = kb.sA + (op.q * kb.K + op.a0) * kb.Tp + op.target;
+    const int64_t ql = op.q - kb.qFirst;   // the host only sends operations on questions this device owns
+    double *cellD = kb.mD + ql * kb.Tp + op.target;
+    double *cellA0 = kb.sA + (ql * kb.K + op.a0) * kb.Tp + op.target;
     if (op.a1 < 0 || op.a1 == op.a0) {
       // ProcessOne (:15-26) with (2b, b^2), or the doubled step (:34-36) with (4b, 4b^2)
       const double twoB = (op.a1 < 0) ? __dmul_rn(2.0, b) : __dmul_rn(4.0, b);
@@ -563,7 +598,7 @@ __global__ void k_train_ops(DeviceKB kb, const TrainOp *__restrict__ ops, const 
       *cellD = __dadd_rn(*cellD, addend);
     } else {
       // same question, two different answers (:38-47): D receives addend0 twice, as in the reference
-      double *cellA1 = kb.sA + (op.q * kb.K + op.a1) * kb.Tp + op.target;
+      double *cellA1 = kb.sA + (ql * kb.K + op.a1) * kb.Tp + op.target;
       const double twoB = __dmul_rn(2.0, b), bSq = __dmul_rn(b, b);
       const double a0Sq = *cellA0, a1Sq = *cellA1;
       const double add0 = __dadd_rn(__dmul_rn(sqrt(a0Sq), twoB), bSq);

@@ -20,6 +20,9 @@ struct DeviceKB {
   const uint32_t *qgaps;   // question gap bitmap or nullptr
   int64_t Q, K, T, Tp;
   int64_t nValidTargets;   // T - #target gaps (CpuEngine.cpp:351)
+  // Question shard held by this device: rows of questions qFirst .. qFirst+qCount-1 (sA/mD are indexed by i - qFirst).
+  // A single-device engine has qFirst = 0, qCount = Q.
+  int64_t qFirst, qCount;
 };
 
 // Per-quiz state resident in HBM, addressed by quiz slot.
@@ -95,6 +98,8 @@ void launch_train_ops(const DeviceKB &kb, const TrainOp *dOps, const int64_t *dG
 void launch_add_vb(const DeviceKB &kb, const int64_t *dTargets, const double *dAmounts, const int64_t *dGroupStart,
                    int64_t nGroups, cudaStream_t st);
 
+void launch_gather_prior_rows(const QuizPool &qp, int64_t n, const int64_t *dSlots, double *dBuf, cudaStream_t st);
+void launch_scatter_prior_rows(const QuizPool &qp, int64_t n, const int64_t *dSlots, const double *dBuf, cudaStream_t st);
 void launch_set_active(const QuizPool &qp, int64_t n, const int64_t *dSlots, const int64_t *dQuestions, cudaStream_t st);
 void launch_flush_l2(void *buf, size_t bytes, cudaStream_t st);
 

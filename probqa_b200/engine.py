@@ -43,7 +43,7 @@ class CiRatedTarget(C.Structure):  # :32-35
 class CiB200Options(C.Structure):  # PqaB200Ext.h
     _pack_ = 8
     _fields_ = [("device", C.c_int32), ("emulatedWorkers", C.c_int32), ("rngSeed", C.c_uint64),
-                ("initialQuizCapacity", C.c_int64)]
+                ("initialQuizCapacity", C.c_int64), ("questionShardFirst", C.c_int64), ("questionShardCount", C.c_int64)]
 
 
 RATED_DTYPE = np.dtype([("iTarget", np.int64), ("prob", np.float64)])
@@ -117,6 +117,12 @@ SIGNATURES = {
     "PqaB200_EvalQuestionsDetailed": (_vp, [_vp, _i64, _pd, _pd, _pd, _pd, _pd]),
     "PqaB200_SetEvalKernel": (_vp, [_vp, C.c_int32]),
     "PqaB200_SetEvalTuning": (_vp, [_vp, C.c_int32, _i64, _i64, C.c_int32]),
+    "PqaB200_ShardEval": (_vp, [_vp, _i64, _pi64]),
+    "PqaB200_ShardSelect": (_vp, [_vp, _i64, _pi64, _pu64, _pi64, _pvp]),
+    "PqaB200_ShardRecordAnswerBegin": (_vp, [_vp, _i64, _pi64, _pi64]),
+    "PqaB200_ShardRecordAnswerEnd": (_vp, [_vp, _i64, _pi64]),
+    "PqaB200_ShardBuffer": (_vp, [_vp, C.c_int32, _pvp, _pi64]),
+    "PqaB200_GetQuestionShard": (_vp, [_vp, _pi64, _pi64]),
     "PqaB200_ResidentBind": (_vp, [_vp, _i64, _pi64, _pu64]),
     "PqaB200_ResidentStep": (_vp, [_vp]),
     "PqaB200_ResidentFetch": (_vp, [_vp, _pi64]),
@@ -456,6 +462,38 @@ class PqaEngine:
         _raise_or_return(self._lib.PqaB200_SetEvalTuning(self.c_engine, which, chunk_targets, quizzes_per_cta,
                                                          kahan_lanes_per_thread))
 
+    # ---------------------------------------------------------------- question-sharded protocol (PqaB200Ext.h)
+    def question_shard(self) -> Tuple[int, int]:
+        first, count = C.c_int64(), C.c_int64()
+        _raise_or_return(self._lib.PqaB200_GetQuestionShard(self.c_engine, C.byref(first), C.byref(count)))
+        return first.value, count.value
+
+    def shard_buffer(self, which: int) -> Tuple[int, int]:
+        """(device pointer, number of doubles) of buffer 0 (priorities [n][Q]) or 1 (priors [n][Tp])."""
+        ptr, cnt = C.c_void_p(), C.c_int64()
+        _raise_or_return(self._lib.PqaB200_ShardBuffer(self.c_engine, which, C.byref(ptr), C.byref(cnt)))
+        return ptr.value, cnt.value
+
+    def shard_eval(self, quiz_ids):
+        ids = _i64arr(quiz_ids)
+        _raise_or_return(self._lib.PqaB200_ShardEval(self.c_engine, ids.size, _p(ids, _pi64)))
+
+    def shard_select(self, quiz_ids, randoms) -> np.ndarray:
+        ids = _i64arr(quiz_ids)
+        rnd = np.ascontiguousarray(randoms, dtype=np.uint64)
+        out = np.empty(ids.size, dtype=np.int64)
+        _raise_or_return(self._lib.PqaB200_ShardSelect(self.c_engine, ids.size, _p(ids, _pi64), _p(rnd, _pu64),
+                                                       _p(out, _pi64), None))
+        return out
+
+    def shard_record_answer_begin(self, quiz_ids, answers):
+        ids, ans = _i64arr(quiz_ids), _i64arr(answers)
+        _raise_or_return(self._lib.PqaB200_ShardRecordAnswerBegin(self.c_engine, ids.size, _p(ids, _pi64), _p(ans, _pi64)))
+
+    def shard_record_answer_end(self, quiz_ids):
+        ids = _i64arr(quiz_ids)
+        _raise_or_return(self._lib.PqaB200_ShardRecordAnswerEnd(self.c_engine, ids.size, _p(ids, _pi64)))
+
     def resident_bind(self, quiz_ids, randoms=None):
         ids = _i64arr(quiz_ids)
         rnd = None if randoms is None else np.ascontiguousarray(randoms, dtype=np.uint64)
@@ -526,9 +564,11 @@ class PqaEngineFactory:
         return PqaEngine(c_engine), err
 
     def create_b200_engine(self, eng_def: EngineDefinition, device: int = -1, emulated_workers: int = 0,
-                           rng_seed: int = 0, initial_quiz_capacity: int = 0) -> PqaEngine:
+                           rng_seed: int = 0, initial_quiz_capacity: int = 0, question_shard_first: int = 0,
+                           question_shard_count: int = 0) -> PqaEngine:
         c_def = eng_def.to_c()
-        opts = CiB200Options(device, emulated_workers, rng_seed, initial_quiz_capacity)
+        opts = CiB200Options(device, emulated_workers, rng_seed, initial_quiz_capacity, question_shard_first,
+                             question_shard_count)
         e = C.c_void_p()
         c_engine = self._lib.PqaB200_CreateEngine(C.byref(e), C.byref(c_def), C.byref(opts))
         if not c_engine:

@@ -1,0 +1,167 @@
+"""Question-sharded multi-GPU engine: one B200 engine per GPU, each holding the sA/mD rows of a contiguous slice of the
+questions (SURVEY.md 8e "Questions" row; the reference itself parallelises NextQuestion over questions,
+CpuEngine.cpp:355-360). Quiz state (priors, asked bits) is replicated on every shard.
+
+  NextQuestion : every shard evaluates its questions for all quizzes of the batch into a zero-initialised [n][Q] buffer
+                 -> all-reduce(sum) of the buffers (NCCL over NVLink through torch.distributed) -> every shard runs the
+                 same selection with the same 64-bit draws. Adding the other shards' +0.0 is exact, so priorities,
+                 run-lengths and the chosen questions are those of a single engine.
+  RecordAnswer : the shard that owns the answered question computes the new posterior, the others contribute zero rows
+                 -> all-reduce(sum) of the [n][Tp] rows -> every shard stores the row (bit-identical to a single engine).
+  StartQuiz / ListTopTargets / SetActiveQuestion are local; RecordQuizTarget / Train touch only the owner's cells (vB is
+  replicated and updated everywhere).
+
+`shards` is the list of shard ports driven by THIS process: one per process under torchrun (pass the process group), or
+several in one process (tests on a single GPU; group=None). A shard port is anything with the methods of B200Shard.
+"""
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+
+def shard_ranges(n_questions: int, n_shards: int):
+    """[(first, count)]: contiguous, the first n_questions % n_shards shards get one more (like CalcSplit,
+    SRPoolRunner.h:96-110)."""
+    quot, rem = divmod(n_questions, n_shards)
+    out, first = [], 0
+    for s in range(n_shards):
+        cnt = quot + (1 if s < rem else 0)
+        out.append((first, cnt))
+        first += cnt
+    return out
+
+
+class _CudaView:
+    """Exposes engine-owned device memory to torch without a copy (torch.as_tensor reads __cuda_array_interface__)."""
+
+    def __init__(self, ptr: int, count: int):
+        self.__cuda_array_interface__ = {"shape": (count,), "typestr": "<f8", "data": (ptr, False), "version": 2}
+
+
+class B200Shard:
+    """Shard port over a PqaEngine created with a question shard (probqa_b200.engine)."""
+
+    def __init__(self, engine):
+        self.engine = engine
+        self.first, self.count = engine.question_shard()
+
+    def _view(self, which):
+        import torch
+        ptr, cnt = self.engine.shard_buffer(which)
+        return torch.as_tensor(_CudaView(ptr, cnt), device="cuda")
+
+    def start_quiz_batch(self, n):
+        return self.engine.start_quiz_batch(n)
+
+    def eval(self, quiz_ids):
+        self.engine.shard_eval(quiz_ids)
+        return self._view(0)
+
+    def select(self, quiz_ids, randoms):
+        return self.engine.shard_select(quiz_ids, randoms)
+
+    def record_answer_begin(self, quiz_ids, answers):
+        self.engine.shard_record_answer_begin(quiz_ids, answers)
+        return self._view(1)
+
+    def record_answer_end(self, quiz_ids):
+        self.engine.shard_record_answer_end(quiz_ids)
+
+    def set_active_question_batch(self, quiz_ids, questions):
+        self.engine.set_active_question_batch(quiz_ids, questions)
+
+    def list_top_targets_batch(self, quiz_ids, max_count):
+        return self.engine.list_top_targets_batch(quiz_ids, max_count)
+
+    def record_quiz_target_batch(self, quiz_ids, targets, amounts=None):
+        self.engine.record_quiz_target_batch(quiz_ids, targets, amounts)
+
+    def train(self, answered_questions, i_target, amount=1.0):
+        self.engine.train(answered_questions, i_target, amount)
+
+    def release_quiz_batch(self, quiz_ids):
+        self.engine.release_quiz_batch(quiz_ids)
+
+    def copy_quiz_priors(self, quiz):
+        return self.engine.copy_quiz_priors(quiz)
+
+
+class QuestionShardedEngine:
+    def __init__(self, shards: Sequence, group=None, seed: int = 0x5EED):
+        assert len(shards) >= 1
+        self.shards = list(shards)
+        self.group = group
+        self._rng = np.random.default_rng(seed)   # same seed on every rank => same draws on every shard
+
+    # ---- the exchange step
+    def _all_reduce(self, tensors: List):
+        """Sum over the local shards' tensors and over the process group; every local tensor receives the total."""
+        total = tensors[0]
+        for t in tensors[1:]:
+            total.add_(t)
+        if self.group is not None:
+            import torch.distributed as dist
+            if total.is_cuda:
+                import torch
+                torch.cuda.synchronize()
+            dist.all_reduce(total, op=dist.ReduceOp.SUM, group=self.group)
+        if total.is_cuda:
+            import torch
+            for t in tensors[1:]:
+                t.copy_(total)
+            torch.cuda.synchronize()   # the engines consume the buffers on their own streams
+        else:
+            for t in tensors[1:]:
+                t.copy_(total)
+
+    def _same(self, results):
+        first = results[0]
+        for r in results[1:]:
+            assert np.array_equal(np.asarray(first), np.asarray(r)), "shards disagree"
+        return first
+
+    # ---- quiz path
+    def start_quiz_batch(self, n: int) -> np.ndarray:
+        return self._same([s.start_quiz_batch(n) for s in self.shards])
+
+    def next_question_batch(self, quiz_ids, randoms: Optional[np.ndarray] = None) -> np.ndarray:
+        quiz_ids = np.ascontiguousarray(quiz_ids, dtype=np.int64)
+        if randoms is None:
+            randoms = self._rng.integers(0, 2 ** 64, size=quiz_ids.size, dtype=np.uint64)
+        self._all_reduce([s.eval(quiz_ids) for s in self.shards])
+        return self._same([s.select(quiz_ids, randoms) for s in self.shards])
+
+    def eval_priorities(self, quiz_ids):
+        """All-reduced priorities [n, Q] (NaN where asked) as a host array, without selecting."""
+        quiz_ids = np.ascontiguousarray(quiz_ids, dtype=np.int64)
+        bufs = [s.eval(quiz_ids) for s in self.shards]
+        self._all_reduce(bufs)
+        return bufs[0].detach().cpu().numpy().reshape(quiz_ids.size, -1).copy()
+
+    def record_answer_batch(self, quiz_ids, answers):
+        quiz_ids = np.ascontiguousarray(quiz_ids, dtype=np.int64)
+        self._all_reduce([s.record_answer_begin(quiz_ids, answers) for s in self.shards])
+        for s in self.shards:
+            s.record_answer_end(quiz_ids)
+
+    def set_active_question_batch(self, quiz_ids, questions):
+        for s in self.shards:
+            s.set_active_question_batch(quiz_ids, questions)
+
+    def list_top_targets_batch(self, quiz_ids, max_count: int):
+        return self.shards[0].list_top_targets_batch(quiz_ids, max_count)   # replicated state: any shard answers
+
+    def record_quiz_target_batch(self, quiz_ids, targets, amounts=None):
+        for s in self.shards:
+            s.record_quiz_target_batch(quiz_ids, targets, amounts)
+
+    def train(self, answered_questions, i_target, amount=1.0):
+        for s in self.shards:
+            s.train(answered_questions, i_target, amount)
+
+    def release_quiz_batch(self, quiz_ids):
+        for s in self.shards:
+            s.release_quiz_batch(quiz_ids)
+
+    def copy_quiz_priors(self, quiz):
+        return self.shards[0].copy_quiz_priors(quiz)
