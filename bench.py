@@ -81,7 +81,7 @@ class ClockSampler:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.QUERY,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -281,8 +281,8 @@ def bench_question_sharded(args, cfg, pqa, dist, rank, world, local_rank, cores,
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="1000x5x1000_b256", choices=sorted(WORKLOADS))
     ap.add_argument("--kernel", type=int, default=0, help="0 auto (staged), 1 exact, 2 staged")
@@ -360,14 +360,14 @@ def main():
 
     # ---------------- device-resident leg (value, roofline)
     eng.resident_bind(quizzes, randoms)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()     # nvidia-smi needs ~100 ms per sample: it runs from the warm-up to the end of the timed steps
     for _ in range(args.warmup):
         if not args.no_flush:
             eng.flush_l2()
         eng.resident_step()
     eng.synchronize()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     launches0 = eng.kernel_launch_count()
     ev = [(pqa.DeviceEvent(), pqa.DeviceEvent()) for _ in range(args.steps)]
     eval_ms = []

@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <numeric>
 #include <random>
 #include <thread>
@@ -60,6 +61,7 @@ Engine::Engine(const CiEngineDefinition &def, const CiB200Options &opts) {
   Tp_ = (T_ + 3) & ~3ll;
   askedWords_ = (Q_ + 63) >> 6;
   initAmount_ = def._initAmount;
+  precMantissa_ = def._precMantissa; precExponent_ = def._precExponent;
   qFirst_ = 0; qLocal_ = Q_;
   if (opts._questionShardCount > 0) {
     if (opts._questionShardFirst < 0 || opts._questionShardFirst + opts._questionShardCount > Q_)
@@ -911,12 +913,108 @@ PqaError *Engine::FlushL2() {
   PQA_CATCH_RETURN_ERR
 }
 
-PqaError *Engine::SaveKB(const char *) {
-  return ErrNotImplemented("B200 engine: SaveKB (BaseEngine.cpp:323-385) -- KB file format is SURVEY 8(f)-1");
+// ---------------------------------------------------------------------------------------------------------
+// KB file, byte-compatible with the reference (BaseEngine::LockedSaveKB BaseEngine.cpp:323-385, CpuEngine::SaveStatistics
+// CpuEngine.cpp:664-688, BaseEngine::WriteGaps :142-152, PermanentIdManager::Save PermanentIdManager.cpp:27-39; load side
+// PqaEngineBaseFactory::LoadEngineDefinition PqaEngineBaseFactory.cpp:56-83, BaseEngine ctor BaseEngine.cpp:26-57):
+//   u64 PrecisionDefinition {type:4, mantissa:28, exponent:16, reserved:16}; i64 nAnswers, nQuestions, nTargets;
+//   u64 nQuestionsAsked; sA as Q*K rows of T doubles; mD as Q rows; vB;
+//   question gaps {i64 n, n x i64}; target gaps; id maps of questions, targets {i64 nextPermId, i64 nComp, nComp x i64};
+//   quiz id map saved empty {nextPermId, 0}.
+namespace {
+struct FileCloser { FILE *f; ~FileCloser() { if (f) std::fclose(f); } };
+bool wr(FILE *f, const void *p, size_t bytes) { return std::fwrite(p, 1, bytes, f) == bytes; }
+bool rd(FILE *f, void *p, size_t bytes) { return std::fread(p, 1, bytes, f) == bytes; }
+PqaError *FileOpErr(const char *path, const std::string &what) {
+  return MakeError(ErrCode::FileOp, what, std::string("filePath=[") + path + "]");
 }
-Engine *Engine::LoadKB(const char *, const CiB200Options &, PqaError **err) {
-  *err = ErrNotImplemented("B200 engine: LoadCpuEngine (PqaEngineBaseFactory.cpp:56-83) -- KB file format is SURVEY 8(f)-1");
+}  // namespace
+
+PqaError *Engine::SaveKB(const char *filePath) {
+  if (!filePath) return MakeError(ErrCode::NullArgument, PQA_FILE_LINE "Nullptr is passed in place of KB file name.");
+  if (qLocal_ != Q_) return ErrNotImplemented("SaveKB on a question-sharded engine");
+  std::lock_guard<std::mutex> lk(mu_);   // the KB must not be trained while it is written (reference: shared lock)
+  FileCloser fc{std::fopen(filePath, "wb")};
+  if (!fc.f) return MakeError(ErrCode::CantOpenFile, PQA_FILE_LINE "Can't open the KB file to write.",
+                              std::string("filePath=[") + filePath + "]");
+  const uint64_t prec = (uint64_t)3 | ((uint64_t)(precMantissa_ & 0xFFFFFFF) << 4) | ((uint64_t)(precExponent_ & 0xFFFF) << 32);
+  const int64_t dims[3] = {K_, Q_, T_};
+  const uint64_t asked = nQuestionsAsked_.load(std::memory_order_acquire);
+  if (!wr(fc.f, &prec, 8) || !wr(fc.f, dims, 24) || !wr(fc.f, &asked, 8)) return FileOpErr(filePath, PQA_FILE_LINE "Can't write the KB header.");
+  // stream the KB out in slabs of <= 64 MB of rows
+  const int64_t rowsPerSlab = std::max<int64_t>(1, (64ll << 20) / (T_ * 8));
+  std::vector<double> slab((size_t)(rowsPerSlab * T_));
+  auto dumpRows = [&](const double *dBase, int64_t nRows) -> PqaError * {
+    for (int64_t r0 = 0; r0 < nRows; r0 += rowsPerSlab) {
+      const int64_t nr = std::min(rowsPerSlab, nRows - r0);
+      try {
+        PQA_CU(cudaMemcpy2DAsync(slab.data(), (size_t)T_ * 8, dBase + r0 * Tp_, (size_t)Tp_ * 8, (size_t)T_ * 8, (size_t)nr,
+                                 cudaMemcpyDeviceToHost, stream_));
+        PQA_CU(cudaStreamSynchronize(stream_));
+      } catch (const CudaFail &cf) { return ErrCuda(cf.code, cf.what(), cf.file, cf.line); }
+      if (!wr(fc.f, slab.data(), (size_t)(nr * T_) * 8)) return FileOpErr(filePath, PQA_FILE_LINE "Can't write KB rows.");
+    }
+    return nullptr;
+  };
+  if (PqaError *e = dumpRows(dSA_, Q_ * K_)) return e;
+  if (PqaError *e = dumpRows(dMD_, Q_)) return e;
+  if (PqaError *e = dumpRows(dVB_, 1)) return e;
+  const int64_t zero = 0;
+  if (!wr(fc.f, &zero, 8) || !wr(fc.f, &zero, 8)) return FileOpErr(filePath, PQA_FILE_LINE "Can't write the gaps.");  // no gaps
+  auto dumpIdentity = [&](int64_t n) {
+    std::vector<int64_t> ids((size_t)n);
+    std::iota(ids.begin(), ids.end(), 0);
+    return wr(fc.f, &n, 8) && wr(fc.f, &n, 8) && wr(fc.f, ids.data(), (size_t)n * 8);   // nextPermId = n, nComp = n, comp2perm
+  };
+  if (!dumpIdentity(Q_) || !dumpIdentity(T_)) return FileOpErr(filePath, PQA_FILE_LINE "Can't write the ID mappings.");
+  const int64_t nextQuizPerm = (int64_t)quizzes_.size();
+  if (!wr(fc.f, &nextQuizPerm, 8) || !wr(fc.f, &zero, 8)) return FileOpErr(filePath, PQA_FILE_LINE "Can't write the quiz ID mapping.");
+  if (std::fflush(fc.f) != 0) return FileOpErr(filePath, PQA_FILE_LINE "Can't flush the KB file.");
   return nullptr;
+}
+
+Engine *Engine::LoadKB(const char *filePath, const CiB200Options &opts, PqaError **err) {
+  *err = nullptr;
+  if (!filePath) { *err = MakeError(ErrCode::NullArgument, PQA_FILE_LINE "Nullptr is passed in place of KB file name."); return nullptr; }
+  FileCloser fc{std::fopen(filePath, "rb")};
+  if (!fc.f) {
+    *err = MakeError(ErrCode::CantOpenFile, PQA_FILE_LINE "Can't open the KB file to read.", std::string("filePath=[") + filePath + "]");
+    return nullptr;
+  }
+  uint64_t prec = 0, asked = 0;
+  int64_t dims[3] = {0, 0, 0};
+  if (!rd(fc.f, &prec, 8) || !rd(fc.f, dims, 24) || !rd(fc.f, &asked, 8)) { *err = FileOpErr(filePath, PQA_FILE_LINE "Can't read the KB header."); return nullptr; }
+  if ((prec & 0xF) != 3) { *err = ErrNotImplemented("B200 engine on precision type other than double (KB file header)."); return nullptr; }
+  if (dims[0] < 2 || dims[1] < 1 || dims[2] < 2) { *err = ErrInsufficientDims(dims[0], dims[1], dims[2]); return nullptr; }
+  CiEngineDefinition def;
+  std::memset(&def, 0, sizeof(def));
+  def._nAnswers = dims[0]; def._nQuestions = dims[1]; def._nTargets = dims[2];
+  def._precType = 3; def._precMantissa = (uint32_t)((prec >> 4) & 0xFFFFFFF); def._precExponent = (uint16_t)((prec >> 32) & 0xFFFF);
+  def._initAmount = 1.0;   // not stored in the file; only used to fill a fresh KB, which is overwritten below
+  const int64_t K = dims[0], Q = dims[1], T = dims[2];
+  std::unique_ptr<Engine> eng(new Engine(def, opts));
+  // rows arrive in file order; upload them slab by slab through the whole-KB upload path of this engine's shard
+  std::vector<double> sA((size_t)(Q * K * T)), mD((size_t)(Q * T)), vB((size_t)T);
+  if (!rd(fc.f, sA.data(), sA.size() * 8) || !rd(fc.f, mD.data(), mD.size() * 8) || !rd(fc.f, vB.data(), vB.size() * 8)) {
+    *err = FileOpErr(filePath, PQA_FILE_LINE "Can't read the KB statistics.");
+    return nullptr;
+  }
+  for (int g = 0; g < 2; g++) {   // question gaps, target gaps
+    int64_t nGaps = 0;
+    if (!rd(fc.f, &nGaps, 8)) { *err = FileOpErr(filePath, PQA_FILE_LINE "Can't read the gaps."); return nullptr; }
+    if (nGaps != 0) { *err = ErrNotImplemented("B200 engine: KB files with removed questions/targets (gaps) need maintenance mode"); return nullptr; }
+  }
+  for (int m = 0; m < 3; m++) {   // id maps: accepted when they are the identity (no removals ever happened)
+    int64_t nextPerm = 0, nComp = 0;
+    if (!rd(fc.f, &nextPerm, 8) || !rd(fc.f, &nComp, 8)) { *err = FileOpErr(filePath, PQA_FILE_LINE "Can't read the ID mappings."); return nullptr; }
+    std::vector<int64_t> ids((size_t)std::max<int64_t>(nComp, 0));
+    if (nComp > 0 && !rd(fc.f, ids.data(), ids.size() * 8)) { *err = FileOpErr(filePath, PQA_FILE_LINE "Can't read the ID mappings."); return nullptr; }
+    for (int64_t x = 0; x < nComp; x++)
+      if (ids[x] != x) { *err = ErrNotImplemented("B200 engine: KB files with remapped permanent IDs need maintenance mode"); return nullptr; }
+  }
+  if (PqaError *e = eng->UploadKB(sA.data(), mD.data(), vB.data())) { *err = e; return nullptr; }
+  eng->nQuestionsAsked_.store(asked, std::memory_order_relaxed);
+  return eng.release();
 }
 
 } // namespace pqa

@@ -144,6 +144,7 @@ class Engine {
   int64_t shardPriorityCount_ = 0, shardPriorsCount_ = 0;
   DevBuf<double> dShardPriority_, dShardPriors_;
   double initAmount_ = 0;
+  uint32_t precMantissa_ = 0; uint16_t precExponent_ = 0;   // kept only to write them back into a KB file header
   cudaStream_t stream_ = nullptr;
   EvalConfig evalCfg_;
 

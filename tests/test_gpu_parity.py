@@ -397,3 +397,39 @@ def test_full_size_staged_vs_exact_and_oracle(pqa, ora, depth):
     for x, quiz in enumerate(quizzes):
         want = ora.list_top_targets(eng.copy_quiz_priors(int(quiz)), W, 10)
         assert [(int(t), float(p)) for t, p in items[x][:counts[x]]] == want
+
+
+def test_kb_file_roundtrip_in_reference_layout(pqa, tmp_path):
+    """SaveKB / LoadCpuEngine in the reference's byte layout (BaseEngine.cpp:323-385, CpuEngine.cpp:664-688,
+    PermanentIdManager.cpp:27-39): header, sA rows, mD rows, vB, empty gap lists, identity id maps."""
+    Q, K, T = 9, 5, 203     # T not a multiple of 4: device rows are padded, file rows are not
+    kb = synth.gamma_kb(Q, K, T, INIT)
+    eng = make_engine(pqa, Q, K, T, 3, kb)
+    quiz = eng.start_quiz()
+    eng.next_question(quiz)
+    eng.record_answer(quiz, 1)
+    eng.record_quiz_target(quiz, 17)
+    sA, mD, vB = eng.download_kb()
+    path = str(tmp_path / "kb.bin")
+    eng.save_kb(path)
+    raw = open(path, "rb").read()
+    hdr = np.frombuffer(raw[:40], dtype=np.uint64)
+    assert hdr[0] & 0xF == 3 and (hdr[0] >> 4) & 0xFFFFFFF == 53 and (hdr[0] >> 32) & 0xFFFF == 11
+    assert tuple(np.frombuffer(raw[8:32], dtype=np.int64)) == (K, Q, T) and hdr[4] == eng.get_total_questions_asked() == 1
+    off = 40
+    fA = np.frombuffer(raw, dtype=np.float64, count=Q * K * T, offset=off).reshape(Q, K, T); off += fA.nbytes
+    fD = np.frombuffer(raw, dtype=np.float64, count=Q * T, offset=off).reshape(Q, T); off += fD.nbytes
+    fB = np.frombuffer(raw, dtype=np.float64, count=T, offset=off); off += fB.nbytes
+    assert np.array_equal(bits(fA), bits(sA)) and np.array_equal(bits(fD), bits(mD)) and np.array_equal(bits(fB), bits(vB))
+    tail = np.frombuffer(raw, dtype=np.int64, offset=off)
+    want_tail = [0, 0, Q, Q] + list(range(Q)) + [T, T] + list(range(T)) + [1, 0]
+    assert tail.tolist() == want_tail
+    eng2, err = pqa.PqaEngineFactory().load_cpu_engine(path)
+    assert err is None and eng2.get_total_questions_asked() == 1
+    d = eng2.copy_dims()
+    assert (d.n_answers, d.n_questions, d.n_targets) == (K, Q, T)
+    lA, lD, lB = eng2.download_kb()
+    assert np.array_equal(bits(lA), bits(sA)) and np.array_equal(bits(lD), bits(mD)) and np.array_equal(bits(lB), bits(vB))
+    with pytest.raises(pqa.PqaException) as ei:
+        pqa.PqaEngineFactory().load_cpu_engine(str(tmp_path / "absent.bin"))
+    assert "[Cannot open file]" in str(ei.value)
