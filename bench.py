@@ -403,9 +403,30 @@ def main():
     assert np.array_equal(out, chosen), "resident and host-buffer paths chose different questions"
     e2e_value = total_qevals * args.steps / t_e2e
 
+    # ---------------------------------------------------------------- BASELINE configs[0]: one quiz through the reference's one-quiz-per-call entry point
+    single = None
+    if rank == 0 and world == 1:
+        n_calls = 200
+        q1 = int(quizzes[0])
+        for _ in range(20):
+            eng.next_question(q1)
+        t0 = time.perf_counter()
+        for _ in range(n_calls):
+            eng.next_question(q1)
+        dt1 = time.perf_counter() - t0
+        single = {"api": "PqaEngine_NextQuestion (one quiz per call)", "calls_per_s": n_calls / dt1, "us_per_call": 1e6 * dt1 / n_calls,
+                  "questions_per_s": (Q - len(states[0])) * n_calls / dt1}
+
     if rank != 0:
         return
     peak, peak_src = measured_peak()
+    traffic = None   # physical DRAM bytes per launch from the committed ncu --set full capture of this workload
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_eval_traffic.json")))
+        if tj["workload"] == args.workload and args.kernel != 1:
+            traffic = tj["dram_bytes_read_per_launch"] + tj["dram_bytes_write_per_launch"]
+    except Exception:
+        pass
     alg_bytes = qevals_step * (K + 1) * T * 8           # per launch of the evaluation kernel on one GPU
     achieved = alg_bytes / (eval_ms_avg * 1e-3) / 1e9
     line = {
@@ -423,12 +444,14 @@ def main():
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "kernel": "k_eval_staged" if args.kernel != 1 else "k_eval_exact",
+                     "traffic": traffic, "kernel": "k_eval_staged" if args.kernel != 1 else "k_eval_exact",
                      "kernel_ms": eval_ms_avg, "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                      "note": "algorithmic bytes are counted per quiz ((K+1)*T*8 per evaluated question, SURVEY 8d); the slab is "
                              "staged once per CTA and shared by its quizzes, so physical DRAM traffic is far lower and the "
                              "kernel is bound by fp64 issue, see DESIGN.md"},
     }
+    if single is not None:
+        line["single_quiz"] = single
     if not args.no_cpu_baseline and world == 1:
         try:
             line["cpu_baseline"] = cpu_baseline(cfg)
