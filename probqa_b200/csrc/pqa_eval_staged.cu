@@ -224,25 +224,11 @@ __device__ __forceinline__ void finish_pass1(const Kahan (&kw)[KL][K], double (&
   }
 }
 
-template <int KL> __device__ __forceinline__ double quiz_sum(double v) {
-  constexpr int LPQ = 4 / KL;
-  if (LPQ == 1) return v;
-  const unsigned mask = (LPQ == 4) ? (0xFu << (threadIdx.x & 28u)) : (0x3u << (threadIdx.x & 30u));
-#pragma unroll
-  for (int o = 1; o < LPQ; o <<= 1) v = __dadd_rn(v, __shfl_xor_sync(mask, v, o, LPQ));
-  return v;
-}
-
-template <int K, int KL>
-__device__ __forceinline__ void finish_pass2(const StagedParams &P, int64_t i, int64_t b, int l0, const double (&W)[K],
-                                             double (&H)[K], double (&V)[K], const double (&Lp)[KL]) {
-  double L = Lp[0];
-#pragma unroll
-  for (int e = 1; e < KL; e++) L = __dadd_rn(L, Lp[e]);
-#pragma unroll
-  for (int k = 0; k < K; k++) { H[k] = quiz_sum<KL>(H[k]); V[k] = quiz_sum<KL>(V[k]); }
-  L = quiz_sum<KL>(L);
-  if (l0 != 0) return;
+// Per (quiz, question) epilogue: CEEvalQsSubtaskConsider.cpp:134-207. H holds sum post*log2 post (negative), L the
+// lack sum (negative), V the squared distances.
+template <int K>
+__device__ __forceinline__ void write_priority(const StagedParams &P, int64_t i, int64_t b, const double (&W)[K],
+                                               const double (&H)[K], const double (&V)[K], double L) {
   const int64_t o = b * P.kb.Q + i;
   double totW = 0.0, sumH = 0.0, sumV = 0.0;
 #pragma unroll
@@ -263,6 +249,28 @@ __device__ __forceinline__ void finish_pass2(const StagedParams &P, int64_t i, i
   const double lack = -L;                                               // :201
   P.priority[o] = lack * pow(vComp, 9.0) * pow(nExp, -2.0);             // :207
   if (P.det.lack) P.det.lack[o] = lack;
+}
+
+template <int KL> __device__ __forceinline__ double quiz_sum(double v) {
+  constexpr int LPQ = 4 / KL;
+  if (LPQ == 1) return v;
+  const unsigned mask = (LPQ == 4) ? (0xFu << (threadIdx.x & 28u)) : (0x3u << (threadIdx.x & 30u));
+#pragma unroll
+  for (int o = 1; o < LPQ; o <<= 1) v = __dadd_rn(v, __shfl_xor_sync(mask, v, o, LPQ));
+  return v;
+}
+
+template <int K, int KL>
+__device__ __forceinline__ void finish_pass2(const StagedParams &P, int64_t i, int64_t b, int l0, const double (&W)[K],
+                                             double (&H)[K], double (&V)[K], const double (&Lp)[KL]) {
+  double L = Lp[0];
+#pragma unroll
+  for (int e = 1; e < KL; e++) L = __dadd_rn(L, Lp[e]);
+#pragma unroll
+  for (int k = 0; k < K; k++) { H[k] = quiz_sum<KL>(H[k]); V[k] = quiz_sum<KL>(V[k]); }
+  L = quiz_sum<KL>(L);
+  if (l0 != 0) return;
+  write_priority<K>(P, i, b, W, H, V, L);
 }
 
 template <int K, int KL, int WARPS>
@@ -361,6 +369,126 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_eval_staged(const StagedParam
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Small batches (fewer quizzes than one warp of the kernel above would hold): latency matters more than throughput.
+// One CTA per question handles 8 quizzes per round. Pass 1 cannot be spread over targets (the reference's Kahan order is
+// a serial dependency per (answer, Kahan lane)): warp w runs the 4K chains of quiz w on lanes 4k + l -- W_k stays
+// bit-exact. Pass 2 has no such dependency: for every quiz of the round ALL threads of the CTA stride over the targets,
+// warp butterflies leave per-warp partial sums in shared memory, and warp w finishes quiz w. Single chunk only.
+// With few quizzes per slab, staging log2 r would cost as much as it saves, so pass 2 evaluates the reference's
+// Log2Hot and an IEEE divide for every element (entropy and lack TERMS are then the reference's bits; only the
+// summation order differs) and the slab is just (K+1) rows: 48 KB at 1000x5x1000, four CTAs per SM.
+constexpr int kSmallWarps = 4;
+
+template <int K>
+__global__ void __launch_bounds__(kSmallWarps * 32, 4) k_eval_small(const StagedParams P) {
+  constexpr int THREADS = kSmallWarps * 32;
+  constexpr int NV = 2 * K + 1;                       // H_k, V_k, L
+  extern __shared__ __align__(128) unsigned char smRaw[];
+  __shared__ uint64_t bar;
+  __shared__ double sWk[kSmallWarps][3][K];           // per quiz of the round: W_k, 1/W_k, log2 W_k
+  __shared__ double sPart[kSmallWarps][kSmallWarps][NV];   // [quiz][warp][value] partial sums of pass 2
+  __shared__ int64_t sSlot[kSmallWarps];              // slot of the quiz, or -1 when absent / already asked
+  double *sR = (double *)smRaw, *sID2 = sR + K * P.Jc;
+  const int64_t iLocal = blockIdx.x, i = P.kb.qFirst + iLocal, Q = P.kb.Q, Tp = P.kb.Tp, T = P.kb.T, Jc = P.Jc;
+  const int64_t tileFirst = (int64_t)blockIdx.y * P.quizzesPerCta;
+  const int64_t tileLimit = (tileFirst + P.quizzesPerCta < P.n) ? tileFirst + P.quizzesPerCta : P.n;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const double qnan = __longlong_as_double(0x7FF8000000000000ll);
+  if (bit32(P.kb.qgaps, i)) {
+    for (int64_t b = tileFirst + threadIdx.x; b < tileLimit; b += THREADS) P.priority[b * Q + i] = qnan;
+    return;
+  }
+  if (threadIdx.x == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+  __syncthreads();
+  uint32_t parity = 0;
+  stage_chunk<K, THREADS>(P, iLocal, 0, false, sR, nullptr, sID2, &bar, parity);
+  const double *__restrict__ tbl = P.kb.log2tbl;
+  const int nVects = (int)(Tp >> 2);
+  for (int64_t b0 = tileFirst; b0 < tileLimit; b0 += kSmallWarps) {      // CTA-uniform
+    // ---- pass 1: warp w <-> quiz b0 + w
+    {
+      const int64_t b = b0 + warp;
+      int64_t slot = -1;
+      if (b < tileLimit) {
+        slot = P.slots[b];
+        if (bit64(P.qp.asked + slot * P.qp.askedWords, i)) {
+          if (lane == 0) P.priority[b * Q + i] = qnan;
+          slot = -1;
+        }
+      }
+      if (lane == 0) sSlot[warp] = slot;
+      if (slot >= 0 && lane < 4 * K) {
+        const int k = lane >> 2, l = lane & 3;
+        const double *rk = sR + k * Jc + l;
+        const double *__restrict__ prl = P.qp.priors + slot * Tp + l;
+        Kahan kw; kw.init();
+#pragma unroll 4
+        for (int v = 0; v < nVects; v++) kw.add(__dmul_rn(rk[4 * v], __ldg(prl + 4 * v)));   // :81-86
+        const double w = group_precise_sum(kw);                          // :88
+        if (l == 0) { sWk[warp][0][k] = w; sWk[warp][1][k] = __ddiv_rn(1.0, w); sWk[warp][2][k] = log2(w); }
+      }
+    }
+    __syncthreads();
+    // ---- pass 2: every quiz of the round, all threads over the targets
+    for (int q = 0; q < kSmallWarps; q++) {
+      const int64_t slot = sSlot[q];
+      if (slot < 0) continue;                                            // CTA-uniform
+      const double *__restrict__ pr = P.qp.priors + slot * Tp;
+      double iW[K], H[K], V[K], L = 0.0;
+#pragma unroll
+      for (int k = 0; k < K; k++) { iW[k] = sWk[q][1][k]; H[k] = 0.0; V[k] = 0.0; }
+      for (int j = threadIdx.x; j < (int)T; j += THREADS) {
+        const double p = __ldg(pr + j), id2 = sID2[j];
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+          const double post = __dmul_rn(__dmul_rn(sR[k * Jc + j], p), iW[k]);   // :81-82, :97
+          const double l2 = log2hot(post, tbl);                         // :106
+          H[k] = __fma_rn(post, l2, H[k]);                              // :113-114
+          L = __dadd_rn(L, __ddiv_rn(id2, l2));                         // :116-117
+          const double d = __dsub_rn(post, p);                          // :119
+          V[k] = __fma_rn(d, d, V[k]);                                  // :126-127
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < K; k++) {
+        const double h = warp_sum(H[k]), vv = warp_sum(V[k]);
+        if (lane == 0) { sPart[q][warp][k] = h; sPart[q][warp][K + k] = vv; }
+      }
+      L = warp_sum(L);
+      if (lane == 0) sPart[q][warp][2 * K] = L;
+    }
+    __syncthreads();
+    // ---- finish: warp w <-> quiz b0 + w
+    if (sSlot[warp] >= 0 && lane == 0) {
+      double W[K], H[K], V[K], L = 0.0;
+#pragma unroll
+      for (int k = 0; k < K; k++) { W[k] = sWk[warp][0][k]; H[k] = 0.0; V[k] = 0.0; }
+      for (int w = 0; w < kSmallWarps; w++) {
+#pragma unroll
+        for (int k = 0; k < K; k++) { H[k] = __dadd_rn(H[k], sPart[warp][w][k]); V[k] = __dadd_rn(V[k], sPart[warp][w][K + k]); }
+        L = __dadd_rn(L, sPart[warp][w][2 * K]);
+      }
+      write_priority<K>(P, i, b0 + warp, W, H, V, L);
+    }
+    __syncthreads();   // sWk / sPart / sSlot are rewritten by the next round
+  }
+}
+
+template <int K>
+static void launch_small(StagedParams P, size_t smem, cudaStream_t st) {
+  static bool attrSet = false;
+  if (!attrSet) {
+    cudaFuncSetAttribute(k_eval_small<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attrSet = true;
+  }
+  P.quizzesPerCta = kSmallWarps;
+  dim3 grid((unsigned)P.kb.qCount, (unsigned)((P.n + kSmallWarps - 1) / kSmallWarps));
+  smem = (size_t)((K + 1) * P.Jc) * sizeof(double);
+  k_eval_small<K><<<grid, kSmallWarps * 32, smem, st>>>(P);
+  count_launch();
+}
+
 template <int K, int KL, int WARPS>
 static void launch_cfg(StagedParams P, const EvalConfig &cfg, size_t smem, cudaStream_t st) {
   static bool attrSet = false;
@@ -390,6 +518,7 @@ static void launch_cfg(StagedParams P, const EvalConfig &cfg, size_t smem, cudaS
 
 template <int K>
 static void launch_k(const StagedParams &P, const EvalConfig &cfg, size_t smem, cudaStream_t st) {
+  if (cfg.kahanLanesPerThread == 0 && P.n < 32 && P.nChunks == 1 && cfg.chunkTargets == 0) { launch_small<K>(P, smem, st); return; }
   // batches >= 32: two threads per quiz (16 quizzes per warp, 16 warps per SM; measured fastest); small batches: four
   // threads per quiz; one thread per quiz (4 lanes, 4 warps per CTA) is kept selectable for experiments
   const int lanesPerThread = cfg.kahanLanesPerThread > 0 ? cfg.kahanLanesPerThread : (P.n >= 32 ? 2 : 1);

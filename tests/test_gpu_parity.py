@@ -152,7 +152,7 @@ def staged_tolerance(kb, prior):
 @pytest.mark.parametrize("dims,W,chunk", [((48, 5, 1000), 8, 0), ((48, 5, 1000), 8, 96), ((21, 5, 203), 3, 0),
                                           ((21, 5, 203), 3, 32), ((12, 2, 64), 1, 0), ((9, 8, 130), 2, 64),
                                           ((10, 9, 77), 2, 0)])
-@pytest.mark.parametrize("lanes", [1, 4])   # four threads per quiz / one thread per quiz
+@pytest.mark.parametrize("lanes", [0, 1, 4])   # auto (small-batch kernel here) / four threads per quiz / one thread per quiz
 def test_staged_kernel_within_tolerance(pqa, ora, kbname, dims, W, chunk, lanes):
     Q, K, T = dims
     kb = KBS[kbname](Q, K, T)
