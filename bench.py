@@ -416,6 +416,22 @@ def main():
         dt1 = time.perf_counter() - t0
         single = {"api": "PqaEngine_NextQuestion (one quiz per call)", "calls_per_s": n_calls / dt1, "us_per_call": 1e6 * dt1 / n_calls,
                   "questions_per_s": (Q - len(states[0])) * n_calls / dt1}
+        # the same entry point from many client threads at once (the engine combines pending calls into one launch)
+        import threading
+        n_thr, per_thr = min(64, B), 100
+        def client(x):
+            qx = int(quizzes[x])
+            for _ in range(per_thr):
+                eng.next_question(qx)
+        thr = [threading.Thread(target=client, args=(x,)) for x in range(n_thr)]
+        t0 = time.perf_counter()
+        for t in thr:
+            t.start()
+        for t in thr:
+            t.join()
+        dtm = time.perf_counter() - t0
+        single.update(threads=n_thr, threaded_calls_per_s=n_thr * per_thr / dtm,
+                      threaded_questions_per_s=sum(Q - len(states[x]) for x in range(n_thr)) * per_thr / dtm)
 
     if rank != 0:
         return

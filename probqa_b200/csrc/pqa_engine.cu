@@ -283,10 +283,93 @@ PqaError *Engine::NextQuestionBatch(int64_t n, const int64_t *pQuizIds, const ui
   PQA_CATCH_RETURN_ERR
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Combining of concurrent one-quiz calls. The reference ABI is synchronous and one quiz per call, and its clients
+// (PqaClient.cpp:238-245, a web front-end) call it from many threads at once. The thread that finds no batch in flight
+// becomes the leader and executes everything that queued up -- its own call plus the calls other threads made while the
+// previous batch was on the GPU -- as ONE batch launch per kind; then it hands leadership over. A single caller gets a
+// batch of one with no added latency; under load the batch size grows by itself and the KB is streamed once per batch.
+void Engine::Submit(CallSlot &slot) {
+  std::unique_lock<std::mutex> lk(combineMu_);
+  combinePending_.push_back(&slot);
+  combineCv_.wait(lk, [&] { return slot.done || !combineLeader_; });
+  if (slot.done) return;
+  combineLeader_ = true;
+  while (!slot.done) {                       // at most two rounds: the batch in flight when we arrived, then ours
+    std::vector<CallSlot *> batch;
+    batch.swap(combinePending_);
+    lk.unlock();
+    RunCombined(batch);
+    lk.lock();
+    for (CallSlot *c : batch) c->done = true;
+    combineCv_.notify_all();
+  }
+  combineLeader_ = false;
+  combineCv_.notify_all();                    // a waiter whose call is still pending takes over
+}
+
+void Engine::RunCombined(const std::vector<CallSlot *> &batch) {
+  std::vector<int64_t> ids, args;
+  std::vector<CallSlot *> who;
+  // ---- NextQuestion: per-call errors come back through ppErrors
+  for (CallSlot *c : batch) if (c->kind == 0) { ids.push_back(c->quiz); who.push_back(c); }
+  if (!ids.empty()) {
+    std::vector<int64_t> out(ids.size(), -1);
+    std::vector<void *> errs(ids.size(), nullptr);
+    PqaError *e = NextQuestionBatch((int64_t)ids.size(), ids.data(), nullptr, out.data(), errs.data());
+    for (size_t x = 0; x < who.size(); x++) {
+      who[x]->result = out[x];
+      who[x]->err = static_cast<PqaError *>(errs[x]);
+      if (e && !who[x]->err) who[x]->err = new PqaError(*e);   // a batch-wide failure (CUDA error) reaches every caller
+      if (who[x]->err) who[x]->result = -1;
+    }
+    delete e;
+  }
+  // ---- RecordAnswer: validate each call on its own so that one bad call does not fail the others
+  ids.clear(); who.clear();
+  for (CallSlot *c : batch) if (c->kind == 1) {
+    PqaError *e;
+    { std::lock_guard<std::mutex> lk(mu_); e = ValidateRecordAnswer(1, &c->quiz, &c->arg); }
+    if (e) { c->err = e; continue; }
+    ids.push_back(c->quiz); args.push_back(c->arg); who.push_back(c);
+  }
+  if (!ids.empty()) {
+    PqaError *e = RecordAnswerBatch((int64_t)ids.size(), ids.data(), args.data());
+    if (e) { for (CallSlot *c : who) c->err = new PqaError(*e); delete e; }
+  }
+  // ---- ListTopTargets: one launch per distinct maxCount
+  std::vector<CallSlot *> tops;
+  for (CallSlot *c : batch) if (c->kind == 2) {
+    PqaError *e = nullptr;
+    if (c->arg < 0) e = ErrNegativeCount(c->arg, PQA_FILE_LINE "|maxCount| must be non-negative.");
+    else { std::lock_guard<std::mutex> lk(mu_); e = CheckQuiz(c->quiz); }
+    if (e) { c->err = e; c->result = -1; continue; }
+    tops.push_back(c);
+  }
+  while (!tops.empty()) {
+    const int64_t maxCount = tops.front()->arg;
+    ids.clear(); who.clear();
+    std::vector<CallSlot *> rest;
+    for (CallSlot *c : tops) { if (c->arg == maxCount) { ids.push_back(c->quiz); who.push_back(c); } else rest.push_back(c); }
+    std::vector<CiRatedTarget> dest((size_t)(ids.size() * std::max<int64_t>(maxCount, 1)));
+    std::vector<int64_t> counts(ids.size(), 0);
+    PqaError *e = ListTopTargetsBatch((int64_t)ids.size(), ids.data(), maxCount, dest.data(), counts.data());
+    for (size_t x = 0; x < who.size(); x++) {
+      if (e) { who[x]->err = new PqaError(*e); who[x]->result = -1; continue; }
+      who[x]->result = counts[x];
+      if (counts[x] > 0) std::memcpy(who[x]->dest, dest.data() + x * maxCount, sizeof(CiRatedTarget) * (size_t)counts[x]);
+    }
+    delete e;
+    tops.swap(rest);
+  }
+}
+
 int64_t Engine::NextQuestion(PqaError **err, int64_t iQuiz) {
-  int64_t q = -1;
-  *err = NextQuestionBatch(1, &iQuiz, nullptr, &q, nullptr);
-  return *err ? -1 : q;
+  if (qLocal_ != Q_) { int64_t q = -1; *err = NextQuestionBatch(1, &iQuiz, nullptr, &q, nullptr); return -1; }
+  CallSlot s; s.kind = 0; s.quiz = iQuiz;
+  Submit(s);
+  *err = s.err;
+  return s.err ? -1 : s.result;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -315,7 +398,12 @@ PqaError *Engine::RecordAnswerBatch(int64_t n, const int64_t *pQuizIds, const in
   PQA_CATCH_RETURN_ERR
 }
 
-PqaError *Engine::RecordAnswer(int64_t iQuiz, int64_t iAnswer) { return RecordAnswerBatch(1, &iQuiz, &iAnswer); }
+PqaError *Engine::RecordAnswer(int64_t iQuiz, int64_t iAnswer) {
+  if (qLocal_ != Q_) return RecordAnswerBatch(1, &iQuiz, &iAnswer);
+  CallSlot s; s.kind = 1; s.quiz = iQuiz; s.arg = iAnswer;
+  Submit(s);
+  return s.err;
+}
 
 PqaError *Engine::ValidateRecordAnswer(int64_t n, const int64_t *pQuizIds, const int64_t *pAnswers) const {
   for (int64_t x = 0; x < n; x++) {  // validate everything before touching any quiz
@@ -504,9 +592,11 @@ PqaError *Engine::ListTopTargetsBatch(int64_t n, const int64_t *pQuizIds, int64_
 }
 
 int64_t Engine::ListTopTargets(PqaError **err, int64_t iQuiz, int64_t maxCount, CiRatedTarget *pDest) {
-  int64_t cnt = 0;
-  *err = ListTopTargetsBatch(1, &iQuiz, maxCount, pDest, &cnt);
-  return *err ? -1 : cnt;
+  if (maxCount > 0 && !pDest) { *err = MakeError(ErrCode::NullArgument, PQA_FILE_LINE "pDest"); return -1; }
+  CallSlot s; s.kind = 2; s.quiz = iQuiz; s.arg = maxCount; s.dest = pDest;
+  Submit(s);
+  *err = s.err;
+  return s.err ? -1 : s.result;
 }
 
 // ---------------------------------------------------------------------------------------------------------

@@ -6,6 +6,7 @@
 // question) and moves ids/answers/results through pinned staging buffers.
 #pragma once
 #include <atomic>
+#include <condition_variable>
 #include <mutex>
 #include <stdexcept>
 #include <string>
@@ -52,6 +53,17 @@ struct HostQuiz {                      // BaseQuiz.h:13-36 (host part); priors a
   bool present = false;
   int64_t activeQuestion = -1;
   std::vector<CiAnsweredQuestion> answers;
+};
+
+// One pending one-quiz call (NextQuestion / RecordAnswer / ListTopTargets) waiting to be combined with the calls other
+// client threads make at the same time.
+struct CallSlot {
+  int kind = 0;                 // 0 NextQuestion, 1 RecordAnswer, 2 ListTopTargets
+  int64_t quiz = -1, arg = 0;   // arg: answer (kind 1) or maxCount (kind 2)
+  CiRatedTarget *dest = nullptr;
+  int64_t result = -1;
+  PqaError *err = nullptr;
+  bool done = false;
 };
 
 class Engine {
@@ -120,6 +132,8 @@ class Engine {
   int emulatedWorkers() const { return W_; }
 
  private:
+  void Submit(CallSlot &slot);                           // flat combining of concurrent one-quiz calls
+  void RunCombined(const std::vector<CallSlot *> &batch);
   PqaError *CheckQuiz(int64_t iQuiz) const;              // BaseEngine::UseQuiz, BaseEngine.cpp:399-419
   PqaError *ValidateRecordAnswer(int64_t n, const int64_t *pQuizIds, const int64_t *pAnswers) const;
   PqaError *FinishNextQuestion(int64_t m, const std::vector<int64_t> &valid, const std::vector<int64_t> &where,
@@ -138,6 +152,10 @@ class Engine {
                             double amount);
 
   mutable std::mutex mu_;
+  std::mutex combineMu_;
+  std::condition_variable combineCv_;
+  std::vector<CallSlot *> combinePending_;
+  bool combineLeader_ = false;
   int device_ = 0, W_ = 1, smCount_ = 148;
   int64_t Q_ = 0, K_ = 0, T_ = 0, Tp_ = 0, askedWords_ = 0;
   int64_t qFirst_ = 0, qLocal_ = 0;   // question shard held by this engine (0, Q_ for a single-device engine)

@@ -433,3 +433,48 @@ def test_kb_file_roundtrip_in_reference_layout(pqa, tmp_path):
     with pytest.raises(pqa.PqaException) as ei:
         pqa.PqaEngineFactory().load_cpu_engine(str(tmp_path / "absent.bin"))
     assert "[Cannot open file]" in str(ei.value)
+
+
+def test_concurrent_one_quiz_calls_are_combined_correctly(pqa, ora):
+    """Many client threads on the reference's one-quiz-per-call ABI at once (like PqaClient.cpp:238-245): the engine
+    combines whatever calls are pending into one batch launch. Every quiz must still see exactly its own posterior
+    (bit-exact against the oracle for its own answer sequence) and its own errors."""
+    import threading
+    Q, K, T, W = 60, 5, 300, 4
+    kb = synth.gamma_kb(Q, K, T, INIT)
+    eng = make_engine(pqa, Q, K, T, W, kb)
+    n_threads, n_quizzes, n_steps = 12, 4, 5
+    failures, lock = [], threading.Lock()
+
+    def client(tid):
+        try:
+            for z in range(n_quizzes):
+                quiz = eng.start_quiz()
+                prior = ora.start_quiz(kb[2], W)
+                for step in range(n_steps):
+                    q = eng.next_question(quiz)
+                    assert 0 <= q < Q and eng.get_active_question_id(quiz) == q
+                    a = (q + tid + step) % K
+                    eng.record_answer(quiz, a)
+                    prior = ora.record_answer(prior, kb[0][q, a], kb[1][q], max(1, W - 1))
+                    assert np.array_equal(bits(eng.copy_quiz_priors(quiz)), bits(prior))
+                    top = [(r.i_target, r.prob) for r in eng.list_top_targets(quiz, 3 + tid % 4)]
+                    assert top == ora.list_top_targets(prior, W, 3 + tid % 4)
+                if tid % 3 == 0:   # an invalid call from this thread must not disturb the others
+                    with pytest.raises(pqa.PqaException) as ei:
+                        eng.record_answer(quiz, 0)
+                    assert "[No active question in the quiz]" in str(ei.value)
+                    with pytest.raises(pqa.PqaException):
+                        eng.next_question(10 ** 6 + tid)
+                eng.release_quiz(quiz)
+        except BaseException as ex:   # noqa: BLE001 - reported to the main thread
+            with lock:
+                failures.append((tid, repr(ex)))
+
+    threads = [threading.Thread(target=client, args=(t,)) for t in range(n_threads)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=300)
+    assert not failures, failures[:3]
+    assert eng.get_total_questions_asked() == n_threads * n_quizzes * n_steps
