@@ -48,6 +48,10 @@ PQACORE_API void *PqaB200_DownloadKB(void *pvEngine, double *sA, double *mD, dou
 
 /* ---- batches of concurrent quizzes (each quiz id must appear at most once per call) ---- */
 PQACORE_API void *PqaEngine_StartQuizBatch(void *pvEngine, int64_t n, int64_t *pQuizIds);
+/* n quizzes resumed at once (PqaEngine_ResumeQuiz semantics each): quiz x has answered pCounts[x] questions, taken in
+ * order from pAQs; pQuizIds[x] receives its id (-1 for a quiz that hit the reference's I64Underflow error). */
+PQACORE_API void *PqaEngine_ResumeQuizBatch(void *pvEngine, int64_t n, const int64_t *pCounts, const CiAnsweredQuestion *pAQs,
+                                            int64_t *pQuizIds);
 /* pRandoms: optional n 64-bit draws replacing the engine RNG (SRDoubleNumber.h:35-39 consumes one per call).
  * pQuestions[i] = chosen question or -1; ppErrors: optional n slots receiving NULL / owned per-quiz errors. */
 PQACORE_API void *PqaEngine_NextQuestionBatch(void *pvEngine, int64_t n, const int64_t *pQuizIds,

@@ -20,7 +20,7 @@ for f in "$REF"/SRPlatform/Interface/*.h; do "$HERE/refshim/patch.pl" "$f" > "$T
 for f in "$REF"/PqaCore/*.h; do "$HERE/refshim/patch.pl" "$f" > "$TMP/ProbQA/PqaCore/$(basename "$f")"; done
 for f in "$REF"/PqaCore/Interface/*.h; do "$HERE/refshim/patch.pl" "$f" > "$TMP/ProbQA/PqaCore/Interface/$(basename "$f")"; done
 SR_CPP="SRSimd.cpp SRVectMath.cpp"
-PQA_CPP="CEEvalQsSubtaskConsider.cpp CERecordAnswerSubtaskMul.cpp CESetPriorsSubtaskSum.cpp CEHeapifyPriorsSubtaskMake.cpp CEListTopTargetsAlgorithm.cpp CERadixSortRatingsSubtaskSort.cpp CETrainOperation.cpp"
+PQA_CPP="CEEvalQsSubtaskConsider.cpp CERecordAnswerSubtaskMul.cpp CESetPriorsSubtaskSum.cpp CEHeapifyPriorsSubtaskMake.cpp CEUpdatePriorsSubtaskMul.cpp CENormPriorsSubtaskMax.cpp CENormPriorsSubtaskCorrSum.cpp CEListTopTargetsAlgorithm.cpp CERadixSortRatingsSubtaskSort.cpp CETrainOperation.cpp"
 for f in $SR_CPP; do "$HERE/refshim/patch.pl" "$REF/SRPlatform/$f" > "$TMP/ProbQA/SRPlatform/$f"; done
 for f in $PQA_CPP; do "$HERE/refshim/patch.pl" "$REF/PqaCore/$f" > "$TMP/ProbQA/PqaCore/$f"; done
 # overlay the stubs (they replace the same-named scratch copies)

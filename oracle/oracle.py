@@ -59,6 +59,9 @@ def lib():
         L.ora_calc_split.argtypes = [C.c_int64, C.c_int64, _i64p]
         L.ora_start_quiz.argtypes = [_dp, _u8p, C.c_int64, C.c_int64, _dp]
         L.ora_record_answer.argtypes = [_dp, _dp, _u8p, C.c_int64, C.c_int64, _dp]
+        L.ora_resume_quiz.restype = C.c_int
+        L.ora_resume_quiz.argtypes = [_dp, _dp, _dp, C.c_int64, C.c_int64, C.c_int64, C.c_int64, _u8p,
+                                      C.POINTER(AnsweredQuestion), C.c_int64, _dp]
         L.ora_eval_question.restype = C.c_double
         L.ora_eval_question.argtypes = [_dp, _dp, C.c_int64, _dp, _u8p, C.c_int64, C.c_int64, C.c_int64,
                                         _dp, _dp, _dp, _dp, _dp]
@@ -130,6 +133,19 @@ def record_answer(prior, sArow, mDrow, W, tgaps=None):
     mDrow = np.ascontiguousarray(mDrow, dtype=np.float64)
     g = pack_bits(tgaps)
     lib().ora_record_answer(_d(sArow), _d(mDrow), _bits(g), prior.size, W, _d(prior))
+    return prior
+
+
+def resume_quiz(sA, mD, vB, aqs, W, tgaps=None):
+    """ResumeQuiz priors for the answered questions aqs = [(q, a), ...] (len >= 1). Raises on the I64Underflow case."""
+    sA = np.ascontiguousarray(sA, dtype=np.float64); mD = np.ascontiguousarray(mD, dtype=np.float64)
+    vB = np.ascontiguousarray(vB, dtype=np.float64)
+    Q, K, T = sA.shape
+    prior = np.empty(T)
+    g = pack_bits(tgaps)
+    rc = lib().ora_resume_quiz(_d(sA), _d(mD), _d(vB), T, K, T, W, _bits(g), _aq_array(aqs), len(aqs), _d(prior))
+    if rc != 0:
+        raise OverflowError("I64Underflow (CpuEngine.cpp:316-319)")
     return prior
 
 

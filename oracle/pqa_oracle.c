@@ -163,6 +163,55 @@ void ora_record_answer(const double *sArow, const double *mDrow, const uint8_t *
   for (int64_t j = 0; j < T; j++) prior[j] = prior[j] / S;
 }
 
+/* ------------------------------------------------------------------ ResumeQuiz */
+static uint8_t ceil_log2_u64(uint64_t v);
+
+int ora_resume_quiz(const double *sA, const double *mD, const double *vB, int64_t ldT, int64_t K, int64_t T, int64_t W,
+                    const uint8_t *tgaps, const OraAnsweredQuestion *aqs, int64_t nAQs, double *prior) {
+  const uint64_t EXPMASK = 0x7FF0000000000000ULL, EXP0 = 0x3FF0000000000000ULL;
+  const int64_t Tp = (T + 3) & ~(int64_t)3;
+  double *mant = (double *)malloc(sizeof(double) * (size_t)Tp);
+  int64_t *exps = (int64_t *)malloc(sizeof(int64_t) * (size_t)Tp);
+  for (int64_t j = 0; j < Tp; j++) {                       /* CEUpdatePriorsSubtaskMul.cpp:40-82 */
+    double m = 0; int64_t e = 0;
+    for (int64_t i = 0; i < nAQs; i++) {
+      const int64_t q = aqs[i].iQuestion, a = aqs[i].iAnswer;
+      /* padding lanes of the last vector: the reference's rows are padded (A pad / D pad); their values never reach the
+       * result because padding lanes are gaps in the normalisation below */
+      const double A = (j < T) ? sA[(q * K + a) * ldT + j] : 0.0, D = (j < T) ? mD[q * ldT + j] : 1.0;
+      const double P = A / D;                              /* :46, :65 */
+      const double old = (i == 0) ? vB[j & 3] : m;         /* :48 loads pvB (vector 0) for every j; :68 */
+      const double product = old * P;                      /* :49, :69 */
+      const uint64_t pb = u64_of(product);
+      m = f64_of((pb & ~EXPMASK) | EXP0);                  /* MakeExponent0, SRSimd.h:194-198 */
+      const int64_t pe = (int64_t)((pb & EXPMASK) >> 52);  /* ExtractExponents64<false>, SRSimd.h:130-135 */
+      e = (i == 0) ? pe : e + pe;                          /* :54-55, :74-77 */
+    }
+    mant[j] = m; exps[j] = e;
+  }
+  int64_t fullMax = INT64_MIN;                             /* CENormPriorsSubtaskMax.cpp:21-29,43-49 */
+  for (int64_t j = 0; j < Tp; j++) {
+    if (lane_gap(tgaps, j, T)) continue;
+    const int64_t tot = exps[j] + (int64_t)((u64_of(mant[j]) & EXPMASK) >> 52);
+    if (tot > fullMax) fullMax = tot;
+  }
+  const int64_t highBound = 1023 + 1023 - (int64_t)ceil_log2_u64((uint64_t)T) - 2;   /* CpuEngine.cpp:314 */
+  const int64_t minAllowed = INT64_MIN + highBound + 1;
+  if (fullMax <= minAllowed) { free(mant); free(exps); return 1; }                    /* :316-319 */
+  const int64_t corr = highBound - fullMax;                /* :320 */
+  for (int64_t j = 0; j < Tp; j++) {                       /* CENormPriorsSubtaskCorrSum.cpp:24-41 */
+    const uint64_t mb = u64_of(mant[j]);
+    const int64_t normExp = exps[j] + (int64_t)((mb & EXPMASK) >> 52) + corr;
+    const int zero = (normExp < 1) || lane_gap(tgaps, j, T);
+    const double nm = zero ? 0.0 : f64_of((mb & ~EXPMASK) | ((uint64_t)normExp << 52));   /* ReplaceExponents, SRSimd.h:200-204 */
+    if (j < T) prior[j] = nm;
+  }
+  const double S = piecewise_sum(prior, T, W);             /* :57-62 + Summator.h:11-21 */
+  for (int64_t j = 0; j < T; j++) prior[j] = prior[j] / S; /* CEDivTargPriorsSubtask.h:16-21 */
+  free(mant); free(exps);
+  return 0;
+}
+
 /* ------------------------------------------------------------------ question evaluation */
 static double calc_velocity_component(double V, int64_t nTargets) { /* CEEvalQsSubtaskConsider.cpp:24-34 */
   const double cLnMaxV = 0.34657359027997265470861606072909;       /* SRMath::_cLnSqrt2 */
@@ -504,7 +553,7 @@ static void hh_down(HeadItem *first, int64_t len) {       /* SRPlatform/Interfac
   }
 }
 
-static uint8_t ceil_log2_u64(uint64_t v) {                /* SRMath::CeilLog2 */
+static uint8_t ceil_log2_u64(uint64_t v) {                 /* SRMath::CeilLog2 */
   if (v <= 1) return 0;
   return (uint8_t)(64 - __builtin_clzll(v - 1));
 }

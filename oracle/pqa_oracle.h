@@ -50,6 +50,14 @@ void ora_start_quiz(const double *vB, const uint8_t *tgaps, int64_t T, int64_t W
 void ora_record_answer(const double *sArow, const double *mDrow, const uint8_t *tgaps, int64_t T, int64_t W,
                        double *prior);
 
+/* ResumeQuiz: CECreateQuizOperation.cpp:55-83 + CEUpdatePriorsSubtaskMul.cpp:12-111 (mantissa/exponent-split product of
+ * the answered questions' likelihoods; NOTE the reference multiplies by vB[j % 4] -- it loads the first vector of vB for
+ * every target vector, :53 -- which is reproduced) + CpuEngine::NormalizePriors CpuEngine.cpp:284-335 with
+ * CENormPriorsSubtaskMax.cpp / CENormPriorsSubtaskCorrSum.cpp + CEDivTargPriorsSubtask.h. W = worker count.
+ * Returns 0, or 1 for the reference's I64Underflow error. nAQs must be >= 1 (0 is StartQuiz, BaseEngine.cpp:392-394). */
+int ora_resume_quiz(const double *sA, const double *mD, const double *vB, int64_t ldT, int64_t K, int64_t T, int64_t W,
+                    const uint8_t *tgaps, const OraAnsweredQuestion *aqs, int64_t nAQs, double *prior);
+
 /* CEEvalQsSubtaskConsider.cpp:41-217 for ONE question (must be neither asked nor gap).
  * Outputs (any may be NULL): Wk/Hk/Vk [K], *lack, *totW. Returns the priority. */
 double ora_eval_question(const double *sAi /* K rows, stride ldT */, const double *mDi, int64_t ldT,

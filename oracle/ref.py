@@ -69,6 +69,8 @@ def lib():
         L.ref_eval_questions.restype = C.c_int64
         L.ref_eval_questions.argtypes = [C.c_void_p, _dp, _u8p, _dp, _dp, _i64p]
         L.ref_list_top_targets.restype = C.c_int64
+        L.ref_resume_quiz.restype = C.c_int64
+        L.ref_resume_quiz.argtypes = [C.c_void_p, C.POINTER(AnsweredQuestion), C.c_int64, _dp]
         L.ref_list_top_targets.argtypes = [C.c_void_p, _dp, C.c_int64, C.POINTER(RatedTarget)]
         L.ref_record_quiz_target.argtypes = [C.c_void_p, C.POINTER(AnsweredQuestion), C.c_int64, C.c_int64, C.c_double]
         _lib = L
@@ -165,6 +167,16 @@ class RefEngine:
     def record_answer(self, prior, q, a):
         p = np.array(prior, dtype=np.float64, copy=True)
         lib().ref_record_answer(self.h, _d(p), q, a)
+        return p
+
+    def resume_quiz(self, aqs):
+        arr = (AnsweredQuestion * max(len(aqs), 1))()
+        for i, (q, a) in enumerate(aqs):
+            arr[i].iQuestion = int(q); arr[i].iAnswer = int(a)
+        p = np.empty(self.T)
+        rc = lib().ref_resume_quiz(self.h, arr, len(aqs), _d(p))
+        if rc != 0:
+            raise OverflowError("I64Underflow")
         return p
 
     def eval_questions(self, prior, asked=None):

@@ -18,6 +18,11 @@
 #include "../PqaCore/CEListTopTargetsAlgorithm.h"
 #include "../PqaCore/CETrainOperation.h"
 #include "../PqaCore/CETrainTaskNumSpec.h"
+#include "../PqaCore/CEUpdatePriorsTask.h"
+#include "../PqaCore/CEUpdatePriorsSubtaskMul.h"
+#include "../PqaCore/CENormPriorsTask.h"
+#include "../PqaCore/CENormPriorsSubtaskMax.h"
+#include "../PqaCore/CENormPriorsSubtaskCorrSum.h"
 
 using namespace SRPlat;
 using namespace ProbQA;
@@ -152,6 +157,44 @@ int64_t ref_eval_questions(void *h, const double *prior, const uint8_t *asked, d
     bounds[i] = int64_t(questionSplit._pBounds[i]);
   }
   return int64_t(questionSplit._nSubtasks);
+}
+
+// ResumeQuiz: CECreateQuizResume::UpdateLikelihoods (CECreateQuizOperation.cpp:55-83) driving the reference's
+// CEUpdatePriorsSubtaskMul::Run, then CpuEngine::NormalizePriors (CpuEngine.cpp:284-335) driving
+// CENormPriorsSubtaskMax::Run, CENormPriorsSubtaskCorrSum::Run and CEDivTargPriorsSubtask::Run.
+// Returns 0, or 1 for the reference's I64Underflow error (:315-318).
+int64_t ref_resume_quiz(void *h, const AnsweredQuestion *pAQs, int64_t nAnswered, double *priorOut) {
+  RefEngine *re = static_cast<RefEngine*>(h); TEngine &engine = re->eng; TQuiz &quiz = re->quiz;
+  const EngineDimensions& dims = engine.GetDims();
+  const SRThreadCount nWorkers = engine.GetWorkers().GetWorkerCount();                // CECreateQuizOperation.cpp:63
+  std::vector<uint8_t> stMem(nWorkers * 256 + 64);
+  std::vector<size_t> splitMem(nWorkers + 1);
+  SRPoolRunner pr(engine.GetWorkers(), stMem.data());
+  const TPqaId nTargetVects = SRSimd::VectsFromComps<SRDoubleNumber>(dims._nTargets); // :73
+  const SRPoolRunner::Split targSplit = SRPoolRunner::CalcSplit(splitMem.data(), nTargetVects, nWorkers); // :74
+  {
+    CEUpdatePriorsTask<SRDoubleNumber> task(engine, quiz, nAnswered, pAQs, 0 /* no cache blocking: same arithmetic */);
+    pr.RunPreSplit<CEUpdatePriorsSubtaskMul<SRDoubleNumber>>(task, targSplit);        // :79
+  }
+  CENormPriorsTask<SRDoubleNumber> normPriorsTask(engine, quiz);                      // CpuEngine.cpp:287
+  {
+    SRPoolRunner::Keeper<CENormPriorsSubtaskMax<SRDoubleNumber>> kp =
+      pr.RunPreSplit<CENormPriorsSubtaskMax<SRDoubleNumber>>(normPriorsTask, targSplit); // :290-291
+    int64_t fullMax = std::numeric_limits<int64_t>::min();                            // :293-313 is an integer max
+    for (SRSubtaskCount i = 0; i < kp.GetNSubtasks(); i++) fullMax = std::max(fullMax, kp.GetSubtask(i)->_maxExp);
+    const int64_t highBound = SRDoubleNumber::_cMaxExp + SRDoubleNumber::_cExpOffs - SRMath::CeilLog2(dims._nTargets) - 2; // :314
+    const int64_t minAllowed = std::numeric_limits<int64_t>::min() + highBound + 1;
+    if (fullMax <= minAllowed) return 1;                                              // :316-319
+    normPriorsTask._corrExp = _mm256_set1_epi64x(highBound - fullMax);                // :320
+  }
+  {
+    typedef CENormPriorsSubtaskCorrSum<SRDoubleNumber> TCorrSumSubtask;
+    SRPoolRunner::Keeper<TCorrSumSubtask> kp = pr.RunPreSplit<TCorrSumSubtask>(normPriorsTask, targSplit); // :325
+    Summator<SRDoubleNumber>::ForPriors(kp, normPriorsTask);                          // :326
+  }
+  pr.RunPreSplit<CEDivTargPriorsSubtask<CENormPriorsTask<SRDoubleNumber>>>(normPriorsTask, targSplit); // :330
+  store_prior(re, priorOut);
+  return 0;
 }
 
 // CpuEngine::ListTopTargetsSpec heapify branch, CpuEngine.cpp:417-440 -> CEListTopTargetsAlgorithm.cpp:30-97

@@ -269,6 +269,11 @@ PQACORE_API void *PqaEngine_StartQuizBatch(void *pvEngine, int64_t n, int64_t *p
   if (!pvEngine) return NullEngine();
   return Ret(E(pvEngine)->StartQuizBatch(n, pQuizIds));
 }
+PQACORE_API void *PqaEngine_ResumeQuizBatch(void *pvEngine, int64_t n, const int64_t *pCounts, const CiAnsweredQuestion *pAQs,
+                                            int64_t *pQuizIds) {
+  if (!pvEngine) return NullEngine();
+  return Ret(Guard([&] { return E(pvEngine)->ResumeQuizBatch(n, pCounts, pAQs, pQuizIds); }));
+}
 PQACORE_API void *PqaEngine_NextQuestionBatch(void *pvEngine, int64_t n, const int64_t *pQuizIds,
                                               const uint64_t *pRandoms, int64_t *pQuestions, void **ppErrors) {
   if (!pvEngine) return NullEngine();

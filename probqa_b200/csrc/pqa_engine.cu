@@ -218,9 +218,89 @@ int64_t Engine::StartQuiz(PqaError **err) {
   return *err ? -1 : id;
 }
 
-int64_t Engine::ResumeQuiz(PqaError **err, int64_t, const CiAnsweredQuestion *) {
-  *err = ErrNotImplemented("B200 engine: ResumeQuiz (CpuEngine.cpp:277-282) is outside the first hot-path scope");
-  return -1;
+// ResumeQuiz: BaseEngine::ResumeQuiz (BaseEngine.cpp:386-397) -> CpuEngine::ResumeQuizSpec (CpuEngine.cpp:277-282) ->
+// CreateQuizInternal (:185-270: index validation, asked bits, answers) -> CECreateQuizResume::UpdateLikelihoods.
+// pCounts[x] answered questions of quiz x are taken from pAQs in order. A quiz with zero answers is a StartQuiz (:392-394).
+PqaError *Engine::ResumeQuizBatch(int64_t n, const int64_t *pCounts, const CiAnsweredQuestion *pAQs, int64_t *pQuizIds) {
+  if (n < 0) return ErrNegativeCount(n, PQA_FILE_LINE "|n| must be non-negative.");
+  if (n == 0) return nullptr;
+  if (!pCounts || !pQuizIds) return MakeError(ErrCode::NullArgument, PQA_FILE_LINE "pCounts/pQuizIds");
+  if (qLocal_ != Q_) return ErrNotImplemented("ResumeQuiz on a question-sharded engine");
+  int64_t total = 0;
+  for (int64_t x = 0; x < n; x++) {
+    if (pCounts[x] < 0) return ErrNegativeCount(pCounts[x], "|nAnswered| must be non-negative.");
+    total += pCounts[x];
+  }
+  if (total > 0 && !pAQs) return MakeError(ErrCode::NullArgument, PQA_FILE_LINE "pAQs");
+  for (int64_t x = 0; x < total; x++) {   // CpuEngine.cpp:219-231 (reported there through an aggregate error)
+    PqaError *inner = nullptr;
+    if (pAQs[x]._iQuestion < 0 || pAQs[x]._iQuestion >= Q_)
+      inner = ErrIndexOutOfRange(pAQs[x]._iQuestion, 0, Q_ - 1, PQA_FILE_LINE "Question index is not in KB range.");
+    else if (pAQs[x]._iAnswer < 0 || pAQs[x]._iAnswer >= K_)
+      inner = ErrIndexOutOfRange(pAQs[x]._iAnswer, 0, K_ - 1, PQA_FILE_LINE "Answer index is not in KB range.");
+    if (inner) {
+      PqaError *agg = MakeError(ErrCode::Aggregate, "", "Aggregate error [" + inner->ToString(true) + "]");
+      delete inner;
+      return agg;
+    }
+  }
+  std::lock_guard<std::mutex> lk(mu_);
+  PQA_TRY
+  for (int64_t x = 0; x < n; x++) pQuizIds[x] = AssignQuizId();
+  EnsureQuizCapacity((int64_t)quizzes_.size());
+  // quizzes without answers start; the others resume
+  std::vector<int64_t> startIds, resumeIds, aqStart{0}, aqQ, aqA;
+  int64_t off = 0;
+  for (int64_t x = 0; x < n; x++) {
+    if (pCounts[x] == 0) { startIds.push_back(pQuizIds[x]); continue; }
+    resumeIds.push_back(pQuizIds[x]);
+    HostQuiz &q = quizzes_[pQuizIds[x]];
+    for (int64_t y = 0; y < pCounts[x]; y++) {
+      aqQ.push_back(pAQs[off + y]._iQuestion); aqA.push_back(pAQs[off + y]._iAnswer);
+      q.answers.push_back(pAQs[off + y]);                                     // CpuEngine.cpp:236-241
+    }
+    off += pCounts[x];
+    aqStart.push_back((int64_t)aqQ.size());
+  }
+  if (!startIds.empty()) {
+    UploadIds((int64_t)startIds.size(), startIds.data());
+    launch_start_quiz(kb(), pool(), (int64_t)startIds.size(), dIds_.get(), W_, stream_);
+    PQA_CU(cudaStreamSynchronize(stream_));
+  }
+  PqaError *result = nullptr;
+  if (!resumeIds.empty()) {
+    const int64_t m = (int64_t)resumeIds.size();
+    UploadIds(m, resumeIds.data());
+    dGroupStart_.ensure(aqStart.size(), stream_); dTargets_.ensure(aqQ.size(), stream_); dAnswers_.ensure(aqA.size(), stream_);
+    dCounts_.ensure((size_t)m, stream_);   // reused as the int status array (m ints fit in m int64 slots)
+    PQA_CU(cudaMemcpyAsync(dGroupStart_.get(), aqStart.data(), sizeof(int64_t) * aqStart.size(), cudaMemcpyHostToDevice, stream_));
+    PQA_CU(cudaMemcpyAsync(dTargets_.get(), aqQ.data(), sizeof(int64_t) * aqQ.size(), cudaMemcpyHostToDevice, stream_));
+    PQA_CU(cudaMemcpyAsync(dAnswers_.get(), aqA.data(), sizeof(int64_t) * aqA.size(), cudaMemcpyHostToDevice, stream_));
+    launch_resume_quiz(kb(), pool(), m, dIds_.get(), dGroupStart_.get(), dTargets_.get(), dAnswers_.get(), W_,
+                       reinterpret_cast<int *>(dCounts_.get()), stream_);
+    std::vector<int> status((size_t)m);
+    PQA_CU(cudaMemcpyAsync(status.data(), dCounts_.get(), sizeof(int) * (size_t)m, cudaMemcpyDeviceToHost, stream_));
+    PQA_CU(cudaStreamSynchronize(stream_));
+    for (int64_t x = 0; x < m; x++) {
+      if (status[x] == 0) continue;
+      // CpuEngine.cpp:316-319 -> CreateQuizInternal unassigns the quiz (:257-261)
+      HostQuiz &q = quizzes_[resumeIds[x]];
+      q.present = false; q.answers.clear(); q.activeQuestion = -1;
+      quizGaps_.push_back(resumeIds[x]);
+      for (int64_t y = 0; y < n; y++) if (pQuizIds[y] == resumeIds[x]) pQuizIds[y] = -1;
+      if (!result) result = MakeError(ErrCode::I64Underflow, "Max exponent over the priors is too low. Are all the targets in gaps?",
+                                      "actual=<underflow>, minAllowed=<see CpuEngine.cpp:315>");
+    }
+  }
+  return result;
+  PQA_CATCH_RETURN_ERR
+}
+
+int64_t Engine::ResumeQuiz(PqaError **err, int64_t nAnswered, const CiAnsweredQuestion *pAQs) {
+  if (nAnswered < 0) { *err = ErrNegativeCount(nAnswered, "|nAnswered| must be non-negative."); return -1; }
+  int64_t id = -1;
+  *err = ResumeQuizBatch(1, &nAnswered, pAQs, &id);
+  return *err ? -1 : id;
 }
 
 // ---------------------------------------------------------------------------------------------------------

@@ -92,6 +92,7 @@ class Engine {
 
   // --- batches of concurrent quizzes ---
   PqaError *StartQuizBatch(int64_t n, int64_t *pQuizIds);
+  PqaError *ResumeQuizBatch(int64_t n, const int64_t *pCounts, const CiAnsweredQuestion *pAQs, int64_t *pQuizIds);
   PqaError *NextQuestionBatch(int64_t n, const int64_t *pQuizIds, const uint64_t *pRandoms, int64_t *pQuestions,
                               void **ppErrors);
   PqaError *RecordAnswerBatch(int64_t n, const int64_t *pQuizIds, const int64_t *pAnswers);

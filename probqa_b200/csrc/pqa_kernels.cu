@@ -6,6 +6,7 @@
 #include "pqa_device.cuh"
 
 #include <atomic>
+#include <limits.h>
 #include <math.h>
 
 namespace pqa {
@@ -71,11 +72,44 @@ void launch_unpad_rows(double *dst, const double *src, int64_t nRows, int64_t T,
 //            (SRAccumVectDbl256.h:83-91); scalar Kahan over the piece sums (Summator.h:11-21)
 //   prior[j] = m[j] / S                                         CEDivTargPriorsSubtask.h:16-21
 // Shared memory: 4W lane sums + 4W lane corrections + W piece sums + 1.
+// prior[0..Tp) holds the un-normalised m[j] (padding lanes +0). Sums it in the reference's order -- pieces =
+// CalcSplit(ceil(T/4) vectors, W), four sequential Kahan lanes per piece, PreciseSum, scalar Kahan over the pieces
+// (SRPoolRunner.h:96-110, SRAccumVectDbl256.h:40-46,83-91, Summator.h:11-21) -- divides (CEDivTargPriorsSubtask.h:16-21)
+// and refreshes log2 prior. Called by every thread of the CTA; sm: 9W+1 doubles of shared memory.
+__device__ void kahan_normalise(double *prior, double *lprior, int64_t T, int64_t Tp, int W, double *sm) {
+  double *laneS = sm, *laneC = sm + 4 * W, *pieceSum = sm + 8 * W, *total = sm + 9 * W;
+  const int64_t nVects = Tp >> 2;
+  const int64_t nPieces = split_count(nVects, W);
+  for (int64_t t = threadIdx.x; t < nPieces * 4; t += blockDim.x) {
+    const int64_t p = t >> 2, lane = t & 3;
+    const int64_t first = split_start(nVects, W, p), limit = split_start(nVects, W, p + 1);
+    Kahan k; k.init();
+    for (int64_t v = first; v < limit; v++) k.add(prior[4 * v + lane]);
+    laneS[t] = k.s; laneC[t] = k.c;
+  }
+  __syncthreads();
+  for (int64_t p = threadIdx.x; p < nPieces; p += blockDim.x)
+    pieceSum[p] = precise_sum4(laneS[4 * p], laneS[4 * p + 1], laneS[4 * p + 2], laneS[4 * p + 3],
+                               laneC[4 * p], laneC[4 * p + 1], laneC[4 * p + 2], laneC[4 * p + 3]);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    Kahan k; k.init(0.0);
+    for (int64_t p = 0; p < nPieces; p++) k.add(pieceSum[p]);
+    total[0] = k.get();
+  }
+  __syncthreads();
+  const double S = total[0];
+  for (int64_t j = threadIdx.x; j < Tp; j += blockDim.x) {
+    const double v = j < T ? __ddiv_rn(prior[j], S) : 0.0;
+    prior[j] = v;
+    lprior[j] = log2(v);
+  }
+}
+
 template <int MODE>  // 0 = StartQuiz, 1 = RecordAnswer
 __global__ void __launch_bounds__(256) k_update_priors(DeviceKB kb, QuizPool qp, const int64_t *__restrict__ slots,
                                                        const int64_t *__restrict__ answers, int W) {
   extern __shared__ double sm[];
-  double *laneS = sm, *laneC = sm + 4 * W, *pieceSum = sm + 8 * W, *total = sm + 9 * W;
   const int64_t slot = slots[blockIdx.x];
   double *prior = qp.priors + slot * qp.Tp;
   double *lprior = qp.logPriors + slot * qp.Tp;
@@ -107,24 +141,7 @@ __global__ void __launch_bounds__(256) k_update_priors(DeviceKB kb, QuizPool qp,
     prior[j] = m;
   }
   __syncthreads();
-  const int64_t nVects = Tp >> 2;
-  const int64_t nPieces = split_count(nVects, W);
-  for (int64_t t = threadIdx.x; t < nPieces * 4; t += blockDim.x) {
-    const int64_t p = t >> 2, lane = t & 3;
-    const int64_t first = split_start(nVects, W, p), limit = split_start(nVects, W, p + 1);
-    Kahan k; k.init();
-    for (int64_t v = first; v < limit; v++) k.add(prior[4 * v + lane]);
-    laneS[t] = k.s; laneC[t] = k.c;
-  }
-  __syncthreads();
-  for (int64_t p = threadIdx.x; p < nPieces; p += blockDim.x)
-    pieceSum[p] = precise_sum4(laneS[4 * p], laneS[4 * p + 1], laneS[4 * p + 2], laneS[4 * p + 3],
-                               laneC[4 * p], laneC[4 * p + 1], laneC[4 * p + 2], laneC[4 * p + 3]);
-  __syncthreads();
   if (threadIdx.x == 0) {
-    Kahan k; k.init(0.0);
-    for (int64_t p = 0; p < nPieces; p++) k.add(pieceSum[p]);
-    total[0] = k.get();
     if (MODE == 0) {
       for (int64_t w = 0; w < qp.askedWords; w++) qp.asked[slot * qp.askedWords + w] = 0;
       qp.active[slot] = -1;
@@ -133,13 +150,7 @@ __global__ void __launch_bounds__(256) k_update_priors(DeviceKB kb, QuizPool qp,
       qp.active[slot] = -1;                                           // CEQuiz.h:92
     }
   }
-  __syncthreads();
-  const double S = total[0];
-  for (int64_t j = threadIdx.x; j < Tp; j += blockDim.x) {
-    const double v = j < T ? __ddiv_rn(prior[j], S) : 0.0;
-    prior[j] = v;
-    lprior[j] = log2(v);
-  }
+  kahan_normalise(prior, lprior, T, Tp, W, sm);
 }
 
 static size_t priors_smem(int W) { return sizeof(double) * (size_t)(9 * W + 1); }
@@ -154,6 +165,78 @@ void launch_record_answer(const DeviceKB &kb, const QuizPool &qp, int64_t n, con
                           const int64_t *dAnswers, int W, cudaStream_t st) {
   if (n <= 0) return;
   k_update_priors<1><<<(unsigned)n, 256, priors_smem(W), st>>>(kb, qp, dSlots, dAnswers, W);
+  count_launch();
+}
+
+// ResumeQuiz: CECreateQuizResume::UpdateLikelihoods (CECreateQuizOperation.cpp:55-83) = CEUpdatePriorsSubtaskMul
+// (CEUpdatePriorsSubtaskMul.cpp:40-82) + CpuEngine::NormalizePriors (CpuEngine.cpp:284-335; CENormPriorsSubtaskMax.cpp,
+// CENormPriorsSubtaskCorrSum.cpp). One CTA per quiz; bit-exact. The likelihood product over the answered questions is
+// kept as a mantissa in [1,2) plus an integer sum of biased exponents so that it cannot underflow; the reference
+// multiplies by vB[j % 4] (it loads the FIRST vector of vB for every target vector, :48) and that is reproduced.
+// status[b] = 1 reports the reference's I64Underflow (:316-319). The log-prior row doubles as the exponent scratch.
+__global__ void __launch_bounds__(256) k_resume_quiz(DeviceKB kb, QuizPool qp, const int64_t *__restrict__ slots,
+                                                     const int64_t *__restrict__ aqStart, const int64_t *__restrict__ aqQ,
+                                                     const int64_t *__restrict__ aqA, int W, int *__restrict__ status) {
+  extern __shared__ double sm[];
+  __shared__ long long sMax[256];
+  const int64_t slot = slots[blockIdx.x];
+  double *prior = qp.priors + slot * qp.Tp;
+  double *lprior = qp.logPriors + slot * qp.Tp;
+  long long *totExp = reinterpret_cast<long long *>(lprior);
+  const int64_t T = kb.T, Tp = kb.Tp, first = aqStart[blockIdx.x], limit = aqStart[blockIdx.x + 1];
+  const unsigned long long EXPMASK = 0x7FF0000000000000ull, EXP0 = 0x3FF0000000000000ull;
+  long long myMax = LLONG_MIN;
+  for (int64_t j = threadIdx.x; j < Tp; j += blockDim.x) {
+    double m = 0.0;
+    long long e = 0;
+    for (int64_t x = first; x < limit; x++) {
+      const int64_t q = aqQ[x] - kb.qFirst, a = aqA[x];
+      const double P = __ddiv_rn(kb.sA[(q * kb.K + a) * Tp + j], kb.mD[q * Tp + j]);   // padding lanes: 0 / 1
+      const double old = (x == first) ? kb.vB[j & 3] : m;
+      const unsigned long long pb = (unsigned long long)__double_as_longlong(__dmul_rn(old, P));
+      m = __longlong_as_double((long long)((pb & ~EXPMASK) | EXP0));                   // MakeExponent0
+      const long long pe = (long long)((pb & EXPMASK) >> 52);                          // ExtractExponents64<false>
+      e = (x == first) ? pe : e + pe;
+    }
+    const long long tot = e + 1023;   // + exponent field of the mantissa, which MakeExponent0 just set to 1023
+    prior[j] = m;
+    totExp[j] = tot;
+    if (j < T && !bit32(kb.tgaps, j)) myMax = max(myMax, tot);
+  }
+  sMax[threadIdx.x] = myMax;
+  __syncthreads();
+  for (int o = blockDim.x >> 1; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) sMax[threadIdx.x] = max(sMax[threadIdx.x], sMax[threadIdx.x + o]);
+    __syncthreads();
+  }
+  const long long fullMax = sMax[0];
+  int ceilLog2T = 0;
+  while ((1ll << ceilLog2T) < T) ceilLog2T++;                                          // SRMath::CeilLog2
+  const long long highBound = 1023 + 1023 - ceilLog2T - 2;                             // CpuEngine.cpp:314
+  if (fullMax <= LLONG_MIN + highBound + 1) {                                          // :316-319
+    if (threadIdx.x == 0) status[blockIdx.x] = 1;
+    return;
+  }
+  const long long corr = highBound - fullMax;                                          // :320
+  for (int64_t j = threadIdx.x; j < Tp; j += blockDim.x) {                             // CENormPriorsSubtaskCorrSum.cpp:24-41
+    const unsigned long long mb = (unsigned long long)__double_as_longlong(prior[j]);
+    const long long normExp = totExp[j] + corr;
+    const bool zero = normExp < 1 || j >= T || bit32(kb.tgaps, j);
+    prior[j] = zero ? 0.0 : __longlong_as_double((long long)((mb & ~EXPMASK) | ((unsigned long long)normExp << 52)));
+  }
+  if (threadIdx.x == 0) {
+    status[blockIdx.x] = 0;
+    for (int64_t w = 0; w < qp.askedWords; w++) qp.asked[slot * qp.askedWords + w] = 0;
+    for (int64_t x = first; x < limit; x++) qp.asked[slot * qp.askedWords + (aqQ[x] >> 6)] |= 1ull << (aqQ[x] & 63);
+    qp.active[slot] = -1;
+  }
+  __syncthreads();
+  kahan_normalise(prior, lprior, T, Tp, W, sm);
+}
+void launch_resume_quiz(const DeviceKB &kb, const QuizPool &qp, int64_t n, const int64_t *dSlots, const int64_t *dAqStart,
+                        const int64_t *dAqQ, const int64_t *dAqA, int W, int *dStatus, cudaStream_t st) {
+  if (n <= 0) return;
+  k_resume_quiz<<<(unsigned)n, 256, priors_smem(W), st>>>(kb, qp, dSlots, dAqStart, dAqQ, dAqA, W, dStatus);
   count_launch();
 }
 

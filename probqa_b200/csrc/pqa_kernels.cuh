@@ -51,6 +51,10 @@ void launch_start_quiz(const DeviceKB &kb, const QuizPool &qp, int64_t n, const 
 // dAnswers[n]; W = loose worker count max(1, hwc-1).
 void launch_record_answer(const DeviceKB &kb, const QuizPool &qp, int64_t n, const int64_t *dSlots,
                           const int64_t *dAnswers, int W, cudaStream_t st);
+// ResumeQuiz (CECreateQuizOperation.cpp:55-83, CEUpdatePriorsSubtaskMul.cpp, CpuEngine::NormalizePriors): quiz b answers
+// questions dAqQ[dAqStart[b] .. dAqStart[b+1]) with dAqA; dStatus[b] = 1 on the reference's I64Underflow.
+void launch_resume_quiz(const DeviceKB &kb, const QuizPool &qp, int64_t n, const int64_t *dSlots, const int64_t *dAqStart,
+                        const int64_t *dAqQ, const int64_t *dAqA, int W, int *dStatus, cudaStream_t st);
 // Renormalisation-free refresh of logPriors after priors were overwritten from the host.
 void launch_refresh_log_priors(const QuizPool &qp, int64_t n, const int64_t *dSlots, cudaStream_t st);
 

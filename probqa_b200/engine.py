@@ -105,6 +105,7 @@ SIGNATURES = {
     "PqaB200_UploadKB": (_vp, [_vp, _pd, _pd, _pd]),
     "PqaB200_DownloadKB": (_vp, [_vp, _pd, _pd, _pd]),
     "PqaEngine_StartQuizBatch": (_vp, [_vp, _i64, _pi64]),
+    "PqaEngine_ResumeQuizBatch": (_vp, [_vp, _i64, _pi64, C.POINTER(CiAnsweredQuestion), _pi64]),
     "PqaEngine_NextQuestionBatch": (_vp, [_vp, _i64, _pi64, _pu64, _pi64, _pvp]),
     "PqaEngine_RecordAnswerBatch": (_vp, [_vp, _i64, _pi64, _pi64]),
     "PqaEngine_SetActiveQuestionBatch": (_vp, [_vp, _i64, _pi64, _pi64]),
@@ -387,6 +388,15 @@ class PqaEngine:
     def start_quiz_batch(self, n: int) -> np.ndarray:
         ids = np.empty(n, dtype=np.int64)
         _raise_or_return(self._lib.PqaEngine_StartQuizBatch(self.c_engine, n, _p(ids, _pi64)))
+        return ids
+
+    def resume_quiz_batch(self, answered_lists) -> np.ndarray:
+        """answered_lists: one list of (question, answer) pairs (or AnsweredQuestion) per quiz."""
+        counts = np.array([len(l) for l in answered_lists], dtype=np.int64)
+        flat = [aq for l in answered_lists for aq in l]
+        arr, _ = self.to_c_answered_questions(flat)
+        ids = np.empty(counts.size, dtype=np.int64)
+        _raise_or_return(self._lib.PqaEngine_ResumeQuizBatch(self.c_engine, counts.size, _p(counts, _pi64), arr, _p(ids, _pi64)))
         return ids
 
     def next_question_batch(self, quiz_ids, randoms=None) -> np.ndarray:

@@ -478,3 +478,35 @@ def test_concurrent_one_quiz_calls_are_combined_correctly(pqa, ora):
         t.join(timeout=300)
     assert not failures, failures[:3]
     assert eng.get_total_questions_asked() == n_threads * n_quizzes * n_steps
+
+
+@pytest.mark.parametrize("dims,W", [((30, 5, 64), 4), ((25, 5, 203), 3), ((300, 4, 50), 1), ((40, 5, 1000), 8)])
+def test_resume_quiz_bit_exact(pqa, ora, dims, W):
+    """ResumeQuiz: priors bit-exact against the oracle (itself pinned on the reference's own
+    CEUpdatePriorsSubtaskMul / NormalizePriors code), asked bits and answers installed, then the quiz continues normally."""
+    Q, K, T = dims
+    rng = np.random.default_rng(5)
+    sA, mD, vB = synth.gamma_kb(Q, K, T, INIT)
+    vB = vB + rng.uniform(0, 3, size=T)
+    eng = make_engine(pqa, Q, K, T, W, (sA, mD, vB))
+    lists = []
+    for n in (1, 2, 7, 0, min(Q - 1, 250)):
+        qs = rng.choice(Q, size=n, replace=False)
+        lists.append([(int(q), int(rng.integers(0, K))) for q in qs])
+    ids = eng.resume_quiz_batch(lists)
+    for quiz, aqs in zip(ids, lists):
+        want = ora.resume_quiz(sA, mD, vB, aqs, W) if aqs else ora.start_quiz(vB, W)
+        assert np.array_equal(bits(eng.copy_quiz_priors(int(quiz))), bits(want)), len(aqs)
+        pri = eng.eval_questions([int(quiz)])["priority"][0]
+        assert sorted(np.nonzero(np.isnan(pri))[0].tolist()) == sorted(q for q, _ in aqs)   # asked bits
+        assert [(r.i_target, r.prob) for r in eng.list_top_targets(int(quiz), 10)] == ora.list_top_targets(want, W, 10)
+    # the single-call form, then the quiz goes on: NextQuestion never returns an answered question
+    quiz = eng.resume_quiz([pqa.AnsweredQuestion(q, a) for q, a in lists[2]])
+    assert np.array_equal(bits(eng.copy_quiz_priors(quiz)), bits(ora.resume_quiz(sA, mD, vB, lists[2], W)))
+    nxt = eng.next_question(quiz)
+    assert nxt not in [q for q, _ in lists[2]]
+    eng.record_answer(quiz, 0)
+    eng.record_quiz_target(quiz, 1)     # trains with the resumed answers + the new one
+    with pytest.raises(pqa.PqaException) as ei:
+        eng.resume_quiz([pqa.AnsweredQuestion(Q, 0)])
+    assert "[Aggregate error]" in str(ei.value) and "[Index is out of range]" in str(ei.value)

@@ -192,3 +192,23 @@ def test_selection_and_nearest_question(ora):
             assert got == best[0]
         else:
             assert got in free
+
+
+def test_resume_quiz_bit_exact_vs_reference(ora, ref):
+    """ResumeQuiz (CEUpdatePriorsSubtaskMul + NormalizePriors): the oracle restatement against the reference's own
+    subtask bodies, including the reference's vB[j % 4] load (CEUpdatePriorsSubtaskMul.cpp:48) and long answer lists whose
+    likelihood products would underflow a plain double."""
+    rng = np.random.default_rng(11)
+    for (Q, K, T), W in (((30, 5, 64), 4), ((25, 5, 203), 3), ((300, 4, 50), 1), ((40, 5, 1000), 8)):
+        for kbf in (synth.binary_search_kb, synth.gamma_kb):
+            sA, mD, vB = kbf(Q, K, T, 0.1)
+            vB = vB + rng.uniform(0, 3, size=T)           # make the vB[j % 4] quirk visible
+            eng = ref.RefEngine(sA, mD, vB, nWorkers=W)
+            for n in (1, 2, 7, min(Q, 250)):
+                qs = rng.choice(Q, size=n, replace=False)
+                aqs = [(int(q), int(rng.integers(0, K))) for q in qs]
+                want = eng.resume_quiz(aqs)
+                got = ora.resume_quiz(sA, mD, vB, aqs, W)
+                assert np.array_equal(bits(got), bits(want)), (Q, K, T, W, n)
+                assert abs(got.sum() - 1.0) < 1e-12
+            eng.close()
