@@ -23,6 +23,12 @@ typedef struct {
    * Quiz state (priors, asked bits) is replicated on every shard; see the "question-sharded" entry points below. */
   int64_t _questionShardFirst;
   int64_t _questionShardCount;
+  /* Target shard of a multi-GPU engine (BASELINE config 4): this device holds columns
+   * [_targetShardFirst, _targetShardFirst + _targetShardCount) of every sA/mD row; _targetShardCount = 0 means all
+   * targets. First and count must be multiples of 4 targets (the last shard ends at nTargets). Quiz state is replicated
+   * with full-length priors; see the "target-sharded" entry points below. Not combinable with a question shard. */
+  int64_t _targetShardFirst;
+  int64_t _targetShardCount;
 } CiB200Options;
 #pragma pack(pop)
 
@@ -98,10 +104,31 @@ PQACORE_API void *PqaB200_ShardSelect(void *pvEngine, int64_t n, const int64_t *
                                       int64_t *pQuestions, void **ppErrors);
 PQACORE_API void *PqaB200_ShardRecordAnswerBegin(void *pvEngine, int64_t n, const int64_t *pQuizIds, const int64_t *pAnswers);
 PQACORE_API void *PqaB200_ShardRecordAnswerEnd(void *pvEngine, int64_t n, const int64_t *pQuizIds);
-/* which: 0 = priorities [n][Q], 1 = priors [n][Tp]. Returns the device pointer and the number of doubles of the last
+/* which: 0 = priorities [n][Q], 1 = priors [n][Tp], 2 = W_k partials [n][Q][K], 3 = H/V/lack partials [n][Q][2K+1]
+ * (2 and 3: target-sharded engines). Returns the device pointer and the number of doubles of the last
  * Shard* call that filled it. */
 PQACORE_API void *PqaB200_ShardBuffer(void *pvEngine, int32_t which, void **ppDevice, int64_t *pCount);
 PQACORE_API void *PqaB200_GetQuestionShard(void *pvEngine, int64_t *pFirst, int64_t *pCount);
+
+/* ---- target-sharded engines (one engine per GPU, each with a CiB200Options target shard) ----
+ * The question evaluation needs the complete normaliser W_k before the entropy / lack / distance sums can be formed
+ * (log2(lik/W_k) is in the lack term's denominator), so it runs in two phases with a sum over shards after each:
+ *   TShardEvalW   -> sum(buffer 2: n*Q*K partial W_k)            -> TShardEvalHVL
+ *                 -> sum(buffer 3: n*Q*(2K+1) partial H_k,V_k,L) -> TShardPriority (fills buffer 0) -> ShardSelect.
+ * Sums over shards are in a different order than CpuEngine's single Kahan pass: priorities are tolerance-level
+ * (DESIGN.md), while posteriors stay bit-exact: ShardRecordAnswerBegin fills this shard's columns of the
+ * un-normalised row (zeros elsewhere) -> sum(buffer 1: n*Tp) -> ShardRecordAnswerEnd normalises the complete row in the
+ * reference's order on every shard. StartQuiz / ListTopTargets / SetActiveQuestion are local. RecordQuizTarget / Train
+ * update the cells of owned targets; vB is replicated and updated on every shard.
+ * PqaB200_UploadKB / DownloadKB / CopyATargets / CopyDTargets take whole-KB host arrays and touch only this shard's
+ * columns of them. */
+PQACORE_API void *PqaB200_TShardEvalW(void *pvEngine, int64_t n, const int64_t *pQuizIds);
+PQACORE_API void *PqaB200_TShardEvalHVL(void *pvEngine, int64_t n, const int64_t *pQuizIds);
+PQACORE_API void *PqaB200_TShardPriority(void *pvEngine, int64_t n, const int64_t *pQuizIds);
+PQACORE_API void *PqaB200_GetTargetShard(void *pvEngine, int64_t *pFirst, int64_t *pCount);
+/* Fills this engine's shard of the KB with the closed-form "binary-search trained" KB of SURVEY.md 8d
+ * (probqa_b200/synth.py binary_search_kb, bit-identical) on the device: KBs too large to stage through the host. */
+PQACORE_API void *PqaB200_FillBinarySearchKB(void *pvEngine, double rounds);
 
 /* ---- device-resident stepping and timing (bench.py "value" leg: no host<->device traffic inside) ---- */
 /* Binds n quizzes as the resident batch: ids and one random draw per quiz are copied to the device once. */

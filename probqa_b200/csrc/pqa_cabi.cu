@@ -355,6 +355,28 @@ PQACORE_API void *PqaB200_GetQuestionShard(void *pvEngine, int64_t *pFirst, int6
   if (pCount) *pCount = E(pvEngine)->questionShardCount();
   return nullptr;
 }
+PQACORE_API void *PqaB200_TShardEvalW(void *pvEngine, int64_t n, const int64_t *pQuizIds) {
+  if (!pvEngine) return NullEngine();
+  return Ret(E(pvEngine)->TShardEvalW(n, pQuizIds));
+}
+PQACORE_API void *PqaB200_TShardEvalHVL(void *pvEngine, int64_t n, const int64_t *pQuizIds) {
+  if (!pvEngine) return NullEngine();
+  return Ret(E(pvEngine)->TShardEvalHVL(n, pQuizIds));
+}
+PQACORE_API void *PqaB200_TShardPriority(void *pvEngine, int64_t n, const int64_t *pQuizIds) {
+  if (!pvEngine) return NullEngine();
+  return Ret(E(pvEngine)->TShardPriority(n, pQuizIds));
+}
+PQACORE_API void *PqaB200_GetTargetShard(void *pvEngine, int64_t *pFirst, int64_t *pCount) {
+  if (!pvEngine) return NullEngine();
+  if (pFirst) *pFirst = E(pvEngine)->targetShardFirst();
+  if (pCount) *pCount = E(pvEngine)->targetShardCount();
+  return nullptr;
+}
+PQACORE_API void *PqaB200_FillBinarySearchKB(void *pvEngine, double rounds) {
+  if (!pvEngine) return NullEngine();
+  return Ret(E(pvEngine)->FillBinarySearchKB(rounds));
+}
 PQACORE_API void *PqaB200_ResidentBind(void *pvEngine, int64_t n, const int64_t *pQuizIds, const uint64_t *pRandoms) {
   if (!pvEngine) return NullEngine();
   return Ret(E(pvEngine)->ResidentBind(n, pQuizIds, pRandoms));

@@ -69,6 +69,17 @@ Engine::Engine(const CiEngineDefinition &def, const CiB200Options &opts) {
                                std::to_string(opts._questionShardCount) + ") is outside 0.." + std::to_string(Q_));
     qFirst_ = opts._questionShardFirst; qLocal_ = opts._questionShardCount;
   }
+  tFirst_ = 0; tLocal_ = T_;
+  if (opts._targetShardCount > 0) {
+    if (qLocal_ != Q_) throw std::runtime_error("probqa_b200: an engine is sharded over questions or over targets, not both");
+    if (opts._targetShardFirst < 0 || opts._targetShardFirst + opts._targetShardCount > T_ || (opts._targetShardFirst & 3) ||
+        ((opts._targetShardCount & 3) && opts._targetShardFirst + opts._targetShardCount != T_))
+      throw std::runtime_error("probqa_b200: target shard [" + std::to_string(opts._targetShardFirst) + ", +" +
+                               std::to_string(opts._targetShardCount) + ") must lie in 0.." + std::to_string(T_) +
+                               " and start/end on multiples of 4 targets (the last shard ends at T)");
+    tFirst_ = opts._targetShardFirst; tLocal_ = opts._targetShardCount;
+  }
+  TpL_ = (tLocal_ + 3) & ~3ll;
   int nDev = 0;
   PQA_CU(cudaGetDeviceCount(&nDev));
   if (nDev <= 0) throw std::runtime_error("probqa_b200: no CUDA device is visible; this engine has no CPU path");
@@ -94,8 +105,8 @@ Engine::Engine(const CiEngineDefinition &def, const CiB200Options &opts) {
   if (!rng_[0] && !rng_[1]) rng_[1] = 1;
 
   PQA_CU(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
-  PQA_CU(cudaMalloc(&dSA_, sizeof(double) * (size_t)(qLocal_ * K_ * Tp_)));
-  PQA_CU(cudaMalloc(&dMD_, sizeof(double) * (size_t)(qLocal_ * Tp_)));
+  PQA_CU(cudaMalloc(&dSA_, sizeof(double) * (size_t)(qLocal_ * K_ * TpL_)));
+  PQA_CU(cudaMalloc(&dMD_, sizeof(double) * (size_t)(qLocal_ * TpL_)));
   PQA_CU(cudaMalloc(&dVB_, sizeof(double) * (size_t)Tp_));
   PQA_CU(cudaMalloc(&dLog2Tbl_, sizeof(double) * 1024));
   double tbl[1024];
@@ -104,6 +115,7 @@ Engine::Engine(const CiEngineDefinition &def, const CiB200Options &opts) {
   // CpuEngine.cpp:44-45,53,66,71,83: sA = init^2, mD = K*init^2, vB = init
   const double initSqr = initAmount_ * initAmount_;
   launch_fill_kb(kb(), initSqr, initSqr * (double)K_, initAmount_, stream_);
+  if (IsTargetSharded()) launch_fill_kb(kbQuiz(), initSqr, initSqr * (double)K_, initAmount_, stream_);   // full-length vB
   EnsureQuizCapacity(opts._initialQuizCapacity > 0 ? opts._initialQuizCapacity : 256);
   PQA_CU(cudaStreamSynchronize(stream_));
 }
@@ -121,9 +133,16 @@ DeviceKB Engine::kb() const {
   DeviceKB k;
   k.sA = dSA_; k.mD = dMD_; k.vB = dVB_; k.log2tbl = dLog2Tbl_;
   k.tgaps = nullptr; k.qgaps = nullptr;   // maintenance (RemoveQuestions/RemoveTargets) is out of scope: no gaps
-  k.Q = Q_; k.K = K_; k.T = T_; k.Tp = Tp_;
+  k.Q = Q_; k.K = K_; k.T = tLocal_; k.Tp = TpL_;   // a target-sharded engine sees its own columns here
   k.nValidTargets = T_;                    // CpuEngine.cpp:351 with no target gaps
   k.qFirst = qFirst_; k.qCount = qLocal_;
+  return k;
+}
+// The view the quiz-level kernels use (StartQuiz, selection, ListTopTargets, vB updates): whole-length vB / priors.
+// Identical to kb() unless the engine is target-sharded, in which case it carries no sA/mD rows at all.
+DeviceKB Engine::kbQuiz() const {
+  DeviceKB k = kb();
+  if (IsTargetSharded()) { k.sA = nullptr; k.mD = nullptr; k.qCount = 0; k.T = T_; k.Tp = Tp_; }
   return k;
 }
 QuizPool Engine::pool() const {
@@ -206,7 +225,7 @@ PqaError *Engine::StartQuizBatch(int64_t n, int64_t *pQuizIds) {
   for (int64_t x = 0; x < n; x++) pQuizIds[x] = AssignQuizId();
   EnsureQuizCapacity((int64_t)quizzes_.size());
   UploadIds(n, pQuizIds);
-  launch_start_quiz(kb(), pool(), n, dIds_.get(), W_, stream_);
+  launch_start_quiz(kbQuiz(), pool(), n, dIds_.get(), W_, stream_);
   PQA_CU(cudaStreamSynchronize(stream_));
   return nullptr;
   PQA_CATCH_RETURN_ERR
@@ -225,7 +244,7 @@ PqaError *Engine::ResumeQuizBatch(int64_t n, const int64_t *pCounts, const CiAns
   if (n < 0) return ErrNegativeCount(n, PQA_FILE_LINE "|n| must be non-negative.");
   if (n == 0) return nullptr;
   if (!pCounts || !pQuizIds) return MakeError(ErrCode::NullArgument, PQA_FILE_LINE "pCounts/pQuizIds");
-  if (qLocal_ != Q_) return ErrNotImplemented("ResumeQuiz on a question-sharded engine");
+  if (IsSharded()) return ErrNotImplemented("ResumeQuiz on a sharded engine");
   int64_t total = 0;
   for (int64_t x = 0; x < n; x++) {
     if (pCounts[x] < 0) return ErrNegativeCount(pCounts[x], "|nAnswered| must be non-negative.");
@@ -264,7 +283,7 @@ PqaError *Engine::ResumeQuizBatch(int64_t n, const int64_t *pCounts, const CiAns
   }
   if (!startIds.empty()) {
     UploadIds((int64_t)startIds.size(), startIds.data());
-    launch_start_quiz(kb(), pool(), (int64_t)startIds.size(), dIds_.get(), W_, stream_);
+    launch_start_quiz(kbQuiz(), pool(), (int64_t)startIds.size(), dIds_.get(), W_, stream_);
     PQA_CU(cudaStreamSynchronize(stream_));
   }
   PqaError *result = nullptr;
@@ -310,7 +329,7 @@ PqaError *Engine::NextQuestionBatch(int64_t n, const int64_t *pQuizIds, const ui
   if (n < 0) return ErrNegativeCount(n, PQA_FILE_LINE "|n| must be non-negative.");
   if (n == 0) return nullptr;
   if (!pQuizIds || !pQuestions) return MakeError(ErrCode::NullArgument, PQA_FILE_LINE "pQuizIds/pQuestions");
-  if (qLocal_ != Q_) return ErrNotImplemented("NextQuestion on a question-sharded engine: use PqaB200_ShardEval / ShardSelect");
+  if (IsSharded()) return ErrNotImplemented("NextQuestion on a sharded engine: use the PqaB200_Shard* protocol");
   std::lock_guard<std::mutex> lk(mu_);
   PQA_TRY
   // validate; quizzes that fail validation get their own error and are left out of the launch
@@ -339,7 +358,7 @@ PqaError *Engine::NextQuestionBatch(int64_t n, const int64_t *pQuizIds, const ui
     dQuestions_.ensure(m, stream_); hQuestions_.ensure(m);
     EvalDetail det{nullptr, nullptr, nullptr, nullptr};
     launch_eval_questions(kb(), pool(), m, dIds_.get(), dPriority_.get(), det, evalCfg_, stream_);
-    launch_select_question(kb(), pool(), m, dIds_.get(), dPriority_.get(), dRandoms_.get(), W_, dRunLength_.get(),
+    launch_select_question(kbQuiz(), pool(), m, dIds_.get(), dPriority_.get(), dRandoms_.get(), W_, dRunLength_.get(),
                            nullptr, dQuestions_.get(), 1, stream_);
     PQA_CU(cudaMemcpyAsync(hQuestions_.get(), dQuestions_.get(), sizeof(int64_t) * (size_t)m, cudaMemcpyDeviceToHost, stream_));
     PQA_CU(cudaStreamSynchronize(stream_));
@@ -445,7 +464,7 @@ void Engine::RunCombined(const std::vector<CallSlot *> &batch) {
 }
 
 int64_t Engine::NextQuestion(PqaError **err, int64_t iQuiz) {
-  if (qLocal_ != Q_) { int64_t q = -1; *err = NextQuestionBatch(1, &iQuiz, nullptr, &q, nullptr); return -1; }
+  if (IsSharded()) { int64_t q = -1; *err = NextQuestionBatch(1, &iQuiz, nullptr, &q, nullptr); return -1; }
   CallSlot s; s.kind = 0; s.quiz = iQuiz;
   Submit(s);
   *err = s.err;
@@ -458,7 +477,7 @@ PqaError *Engine::RecordAnswerBatch(int64_t n, const int64_t *pQuizIds, const in
   if (n < 0) return ErrNegativeCount(n, PQA_FILE_LINE "|n| must be non-negative.");
   if (n == 0) return nullptr;
   if (!pQuizIds || !pAnswers) return MakeError(ErrCode::NullArgument, PQA_FILE_LINE "pQuizIds/pAnswers");
-  if (qLocal_ != Q_) return ErrNotImplemented("RecordAnswer on a question-sharded engine: use PqaB200_ShardRecordAnswerBegin / End");
+  if (IsSharded()) return ErrNotImplemented("RecordAnswer on a sharded engine: use PqaB200_ShardRecordAnswerBegin / End");
   std::lock_guard<std::mutex> lk(mu_);
   PQA_TRY
   if (PqaError *e = ValidateRecordAnswer(n, pQuizIds, pAnswers)) return e;
@@ -479,7 +498,7 @@ PqaError *Engine::RecordAnswerBatch(int64_t n, const int64_t *pQuizIds, const in
 }
 
 PqaError *Engine::RecordAnswer(int64_t iQuiz, int64_t iAnswer) {
-  if (qLocal_ != Q_) return RecordAnswerBatch(1, &iQuiz, &iAnswer);
+  if (IsSharded()) return RecordAnswerBatch(1, &iQuiz, &iAnswer);
   CallSlot s; s.kind = 1; s.quiz = iQuiz; s.arg = iAnswer;
   Submit(s);
   return s.err;
@@ -506,6 +525,7 @@ PqaError *Engine::ValidateRecordAnswer(int64_t n, const int64_t *pQuizIds, const
 // shards by the caller, and consumed by the second half of each operation.
 PqaError *Engine::ShardEval(int64_t n, const int64_t *pQuizIds) {
   if (n <= 0) return ErrNegativeCount(n, PQA_FILE_LINE "|n| must be positive.");
+  if (IsTargetSharded()) return ErrNotImplemented("ShardEval on a target-sharded engine: use PqaB200_TShardEvalW / EvalHVL / Priority");
   std::lock_guard<std::mutex> lk(mu_);
   for (int64_t x = 0; x < n; x++)
     if (PqaError *e = CheckQuiz(pQuizIds[x])) return e;
@@ -536,7 +556,7 @@ PqaError *Engine::ShardSelect(int64_t n, const int64_t *pQuizIds, const uint64_t
   std::memcpy(hRandoms_.get(), pRandoms, sizeof(uint64_t) * (size_t)n);
   PQA_CU(cudaMemcpyAsync(dRandoms_.get(), hRandoms_.get(), sizeof(uint64_t) * (size_t)n, cudaMemcpyHostToDevice, stream_));
   dRunLength_.ensure((size_t)(n * Q_), stream_); dQuestions_.ensure(n, stream_); hQuestions_.ensure(n);
-  launch_select_question(kb(), pool(), n, dIds_.get(), dShardPriority_.get(), dRandoms_.get(), W_, dRunLength_.get(),
+  launch_select_question(kbQuiz(), pool(), n, dIds_.get(), dShardPriority_.get(), dRandoms_.get(), W_, dRunLength_.get(),
                          nullptr, dQuestions_.get(), 1, stream_);
   PQA_CU(cudaMemcpyAsync(hQuestions_.get(), dQuestions_.get(), sizeof(int64_t) * (size_t)n, cudaMemcpyDeviceToHost, stream_));
   PQA_CU(cudaStreamSynchronize(stream_));
@@ -572,10 +592,17 @@ PqaError *Engine::ShardRecordAnswerBegin(int64_t n, const int64_t *pQuizIds, con
   std::memcpy(hAnswers_.get(), pAnswers, sizeof(int64_t) * (size_t)n);
   PQA_CU(cudaMemcpyAsync(dAnswers_.get(), hAnswers_.get(), sizeof(int64_t) * (size_t)n, cudaMemcpyHostToDevice, stream_));
   const int looseW = std::max(1, W_ - 1);
-  launch_record_answer(kb(), pool(), n, dIds_.get(), dAnswers_.get(), looseW, stream_);   // owner: update; others: zeros
   shardPriorsCount_ = n * Tp_;
   dShardPriors_.ensure((size_t)shardPriorsCount_, stream_);
-  launch_gather_prior_rows(pool(), n, dIds_.get(), dShardPriors_.get(), stream_);
+  if (IsTargetSharded()) {
+    // this shard's columns of m[j] = prior * (sA/mD); the other columns stay +0 for the caller's sum over shards
+    PQA_CU(cudaMemsetAsync(dShardPriors_.get(), 0, sizeof(double) * (size_t)shardPriorsCount_, stream_));
+    PeerBufs out; out.n = 1; out.p[0] = dShardPriors_.get();
+    launch_tshard_record_answer_partial(kb(), pool(), tFirst_, n, dIds_.get(), dAnswers_.get(), out, stream_);
+  } else {
+    launch_record_answer(kb(), pool(), n, dIds_.get(), dAnswers_.get(), looseW, stream_);   // owner: update; others: zeros
+    launch_gather_prior_rows(pool(), n, dIds_.get(), dShardPriors_.get(), stream_);
+  }
   for (int64_t x = 0; x < n; x++) {
     HostQuiz &q = quizzes_[pQuizIds[x]];
     q.answers.push_back(CiAnsweredQuestion{q.activeQuestion, pAnswers[x]});
@@ -594,7 +621,10 @@ PqaError *Engine::ShardRecordAnswerEnd(int64_t n, const int64_t *pQuizIds) {
     if (PqaError *e = CheckQuiz(pQuizIds[x])) return e;
   PQA_TRY
   UploadIds(n, pQuizIds);
-  launch_scatter_prior_rows(pool(), n, dIds_.get(), dShardPriors_.get(), stream_);
+  if (IsTargetSharded())   // complete rows of m[j]: bookkeeping + the reference's normalisation, bit-exact
+    launch_tshard_record_answer_finish(kbQuiz(), pool(), n, dIds_.get(), dShardPriors_.get(), std::max(1, W_ - 1), stream_);
+  else
+    launch_scatter_prior_rows(pool(), n, dIds_.get(), dShardPriors_.get(), stream_);
   PQA_CU(cudaStreamSynchronize(stream_));
   return nullptr;
   PQA_CATCH_RETURN_ERR
@@ -605,7 +635,9 @@ PqaError *Engine::ShardBuffer(int32_t which, void **ppDevice, int64_t *pCount) {
   if (!ppDevice || !pCount) return MakeError(ErrCode::NullArgument, PQA_FILE_LINE "ppDevice/pCount");
   if (which == 0) { *ppDevice = dShardPriority_.get(); *pCount = shardPriorityCount_; }
   else if (which == 1) { *ppDevice = dShardPriors_.get(); *pCount = shardPriorsCount_; }
-  else return ErrIndexOutOfRange(which, 0, 1, PQA_FILE_LINE "which");
+  else if (which == 2) { *ppDevice = dShardW_.get(); *pCount = shardWCount_; }
+  else if (which == 3) { *ppDevice = dShardHVL_.get(); *pCount = shardHVLCount_; }
+  else return ErrIndexOutOfRange(which, 0, 3, PQA_FILE_LINE "which");
   return nullptr;
 }
 
@@ -659,7 +691,7 @@ PqaError *Engine::ListTopTargetsBatch(int64_t n, const int64_t *pQuizIds, int64_
   dTop_.ensure(nItems, stream_); hTop_.ensure(nItems); dCounts_.ensure(n, stream_); hCounts_.ensure(n);
   const bool needScratch = (size_t)W_ * 32 + (size_t)T_ * 16 > 200 * 1024;
   if (needScratch) dTopScratch_.ensure((size_t)(n * T_), stream_);
-  launch_list_top_targets(kb(), pool(), n, dIds_.get(), W_, maxCount, dTopScratch_.get(), dTop_.get(), dCounts_.get(), stream_);
+  launch_list_top_targets(kbQuiz(), pool(), n, dIds_.get(), W_, maxCount, dTopScratch_.get(), dTop_.get(), dCounts_.get(), stream_);
   PQA_CU(cudaMemcpyAsync(hTop_.get(), dTop_.get(), sizeof(CiRatedTarget) * nItems, cudaMemcpyDeviceToHost, stream_));
   PQA_CU(cudaMemcpyAsync(hCounts_.get(), dCounts_.get(), sizeof(int64_t) * (size_t)n, cudaMemcpyDeviceToHost, stream_));
   PQA_CU(cudaStreamSynchronize(stream_));
@@ -706,8 +738,11 @@ PqaError *Engine::ApplyTrain(const std::vector<TrainOp> &opsAll, const std::vect
   std::vector<TrainOp> owned;
   if (qLocal_ != Q_) {   // question-sharded engine: cells of other shards' questions are theirs to update
     for (const TrainOp &o : opsAll) if (OwnsQuestion(o.q)) owned.push_back(o);
+  } else if (IsTargetSharded()) {   // target-sharded engine: only the cells of its own columns, addressed locally
+    for (const TrainOp &o : opsAll)
+      if (o.target >= tFirst_ && o.target < tFirst_ + tLocal_) { owned.push_back(o); owned.back().target -= tFirst_; }
   }
-  const std::vector<TrainOp> &ops = (qLocal_ != Q_) ? owned : opsAll;
+  const std::vector<TrainOp> &ops = IsSharded() ? owned : opsAll;
   const int64_t nOps = (int64_t)ops.size();
   if (nOps > 0) {
     std::vector<int64_t> order(nOps);
@@ -745,7 +780,7 @@ PqaError *Engine::ApplyTrain(const std::vector<TrainOp> &opsAll, const std::vect
     PQA_CU(cudaMemcpyAsync(dTargets_.get(), st.data(), sizeof(int64_t) * (size_t)nT, cudaMemcpyHostToDevice, stream_));
     PQA_CU(cudaMemcpyAsync(dAmounts_.get(), sa.data(), sizeof(double) * (size_t)nT, cudaMemcpyHostToDevice, stream_));
     PQA_CU(cudaMemcpyAsync(dGroupStart_.get(), groupStart.data(), sizeof(int64_t) * groupStart.size(), cudaMemcpyHostToDevice, stream_));
-    launch_add_vb(kb(), dTargets_.get(), dAmounts_.get(), dGroupStart_.get(), nGroups, stream_);
+    launch_add_vb(kbQuiz(), dTargets_.get(), dAmounts_.get(), dGroupStart_.get(), nGroups, stream_);
     PQA_CU(cudaStreamSynchronize(stream_));
   }
   return nullptr;
@@ -846,8 +881,9 @@ PqaError *Engine::CopyATargets(int64_t iQuestion, int64_t iAnswer, int64_t maxTa
   if (iAnswer < 0 || iAnswer >= K_) return ErrIndexOutOfRange(iAnswer, 0, K_ - 1, PQA_FILE_LINE "Answer index is not in KB range.");
   if (!OwnsQuestion(iQuestion)) return ErrIndexOutOfRange(iQuestion, qFirst_, qFirst_ + qLocal_ - 1, PQA_FILE_LINE "Question is not in this engine's shard.");
   PQA_TRY
-  const int64_t cnt = std::min(maxTargets, T_);
-  if (cnt > 0) PQA_CU(cudaMemcpy(pFreqs, dSA_ + ((iQuestion - qFirst_) * K_ + iAnswer) * Tp_, sizeof(double) * (size_t)cnt, cudaMemcpyDeviceToHost));
+  // a target-sharded engine fills its own columns of pFreqs (positions tFirst .. tFirst+tLocal-1) and leaves the rest
+  const int64_t cnt = std::min(maxTargets, tFirst_ + tLocal_) - tFirst_;
+  if (cnt > 0) PQA_CU(cudaMemcpy(pFreqs + tFirst_, dSA_ + ((iQuestion - qFirst_) * K_ + iAnswer) * TpL_, sizeof(double) * (size_t)cnt, cudaMemcpyDeviceToHost));
   return nullptr;
   PQA_CATCH_RETURN_ERR
 }
@@ -856,8 +892,8 @@ PqaError *Engine::CopyDTargets(int64_t iQuestion, int64_t maxTargets, double *pF
   if (iQuestion < 0 || iQuestion >= Q_) return ErrIndexOutOfRange(iQuestion, 0, Q_ - 1, PQA_FILE_LINE "Question index is not in KB range.");
   if (!OwnsQuestion(iQuestion)) return ErrIndexOutOfRange(iQuestion, qFirst_, qFirst_ + qLocal_ - 1, PQA_FILE_LINE "Question is not in this engine's shard.");
   PQA_TRY
-  const int64_t cnt = std::min(maxTargets, T_);
-  if (cnt > 0) PQA_CU(cudaMemcpy(pFreqs, dMD_ + (iQuestion - qFirst_) * Tp_, sizeof(double) * (size_t)cnt, cudaMemcpyDeviceToHost));
+  const int64_t cnt = std::min(maxTargets, tFirst_ + tLocal_) - tFirst_;
+  if (cnt > 0) PQA_CU(cudaMemcpy(pFreqs + tFirst_, dMD_ + (iQuestion - qFirst_) * TpL_, sizeof(double) * (size_t)cnt, cudaMemcpyDeviceToHost));
   return nullptr;
   PQA_CATCH_RETURN_ERR
 }
@@ -875,30 +911,33 @@ PqaError *Engine::UploadKB(const double *sA, const double *mD, const double *vB)
   if (!sA || !mD || !vB) return MakeError(ErrCode::NullArgument, PQA_FILE_LINE "sA/mD/vB");
   std::lock_guard<std::mutex> lk(mu_);
   PQA_TRY
-  // the host arrays always describe the whole KB; a question-sharded engine takes its rows out of them
-  sA += qFirst_ * K_ * T_; mD += qFirst_ * T_;
+  // the host arrays always describe the whole KB; a question-sharded engine takes its rows out of them, a
+  // target-sharded engine its columns
+  sA += qFirst_ * K_ * T_ + tFirst_; mD += qFirst_ * T_ + tFirst_;
   const int64_t Q_ = qLocal_;   // rows handled below
-  if (Tp_ == T_) {
+  if (Tp_ == T_ && !IsTargetSharded()) {
     PQA_CU(cudaMemcpyAsync(dSA_, sA, sizeof(double) * (size_t)(Q_ * K_ * T_), cudaMemcpyHostToDevice, stream_));
     PQA_CU(cudaMemcpyAsync(dMD_, mD, sizeof(double) * (size_t)(Q_ * T_), cudaMemcpyHostToDevice, stream_));
-    PQA_CU(cudaMemcpyAsync(dVB_, vB, sizeof(double) * (size_t)T_, cudaMemcpyHostToDevice, stream_));
   } else {
-    // stage through a device scratch in slabs of <= 256 MB, then pad rows on the device
-    const int64_t rowsPerSlab = std::max<int64_t>(1, (256ll << 20) / (T_ * 8));
-    dRowScratch_.ensure((size_t)(std::min(rowsPerSlab, Q_ * K_) * T_), stream_);
+    // stage the rows' local columns through a device scratch in slabs of <= 256 MB, then pad rows on the device
+    const int64_t TL = tLocal_;
+    const int64_t rowsPerSlab = std::max<int64_t>(1, (256ll << 20) / (TL * 8));
+    dRowScratch_.ensure((size_t)(std::min(rowsPerSlab, Q_ * K_) * TL), stream_);
     for (int64_t r0 = 0; r0 < Q_ * K_; r0 += rowsPerSlab) {
       const int64_t nr = std::min(rowsPerSlab, Q_ * K_ - r0);
-      PQA_CU(cudaMemcpyAsync(dRowScratch_.get(), sA + r0 * T_, sizeof(double) * (size_t)(nr * T_), cudaMemcpyHostToDevice, stream_));
-      launch_pad_rows(dSA_ + r0 * Tp_, dRowScratch_.get(), nr, T_, Tp_, 0.0, stream_);
+      PQA_CU(cudaMemcpy2DAsync(dRowScratch_.get(), (size_t)TL * 8, sA + r0 * T_, (size_t)T_ * 8, (size_t)TL * 8, (size_t)nr,
+                               cudaMemcpyHostToDevice, stream_));
+      launch_pad_rows(dSA_ + r0 * TpL_, dRowScratch_.get(), nr, TL, TpL_, 0.0, stream_);
     }
     for (int64_t r0 = 0; r0 < Q_; r0 += rowsPerSlab) {
       const int64_t nr = std::min(rowsPerSlab, Q_ - r0);
-      PQA_CU(cudaMemcpyAsync(dRowScratch_.get(), mD + r0 * T_, sizeof(double) * (size_t)(nr * T_), cudaMemcpyHostToDevice, stream_));
-      launch_pad_rows(dMD_ + r0 * Tp_, dRowScratch_.get(), nr, T_, Tp_, 1.0, stream_);
+      PQA_CU(cudaMemcpy2DAsync(dRowScratch_.get(), (size_t)TL * 8, mD + r0 * T_, (size_t)T_ * 8, (size_t)TL * 8, (size_t)nr,
+                               cudaMemcpyHostToDevice, stream_));
+      launch_pad_rows(dMD_ + r0 * TpL_, dRowScratch_.get(), nr, TL, TpL_, 1.0, stream_);
     }
-    PQA_CU(cudaMemcpyAsync(dRowScratch_.get(), vB, sizeof(double) * (size_t)T_, cudaMemcpyHostToDevice, stream_));
-    launch_pad_rows(dVB_, dRowScratch_.get(), 1, T_, Tp_, 0.0, stream_);
   }
+  PQA_CU(cudaMemsetAsync(dVB_, 0, sizeof(double) * (size_t)Tp_, stream_));
+  PQA_CU(cudaMemcpyAsync(dVB_, vB, sizeof(double) * (size_t)T_, cudaMemcpyHostToDevice, stream_));
   PQA_CU(cudaStreamSynchronize(stream_));
   return nullptr;
   PQA_CATCH_RETURN_ERR
@@ -907,28 +946,21 @@ PqaError *Engine::UploadKB(const double *sA, const double *mD, const double *vB)
 PqaError *Engine::DownloadKB(double *sA, double *mD, double *vB) {
   std::lock_guard<std::mutex> lk(mu_);
   PQA_TRY
-  // whole-KB host arrays; a question-sharded engine fills its rows only
-  if (sA) sA += qFirst_ * K_ * T_;
-  if (mD) mD += qFirst_ * T_;
+  // whole-KB host arrays; a question-sharded engine fills its rows only, a target-sharded engine its columns only
+  if (sA) sA += qFirst_ * K_ * T_ + tFirst_;
+  if (mD) mD += qFirst_ * T_ + tFirst_;
   const int64_t Q_ = qLocal_;
-  if (Tp_ == T_) {
-    if (sA) PQA_CU(cudaMemcpyAsync(sA, dSA_, sizeof(double) * (size_t)(Q_ * K_ * T_), cudaMemcpyDeviceToHost, stream_));
-    if (mD) PQA_CU(cudaMemcpyAsync(mD, dMD_, sizeof(double) * (size_t)(Q_ * T_), cudaMemcpyDeviceToHost, stream_));
-  } else {
-    const int64_t rowsPerSlab = std::max<int64_t>(1, (256ll << 20) / (T_ * 8));
-    dRowScratch_.ensure((size_t)(std::min(rowsPerSlab, Q_ * K_) * T_), stream_);
-    for (int64_t r0 = 0; sA && r0 < Q_ * K_; r0 += rowsPerSlab) {
-      const int64_t nr = std::min(rowsPerSlab, Q_ * K_ - r0);
-      launch_unpad_rows(dRowScratch_.get(), dSA_ + r0 * Tp_, nr, T_, Tp_, stream_);
-      PQA_CU(cudaMemcpyAsync(sA + r0 * T_, dRowScratch_.get(), sizeof(double) * (size_t)(nr * T_), cudaMemcpyDeviceToHost, stream_));
-      PQA_CU(cudaStreamSynchronize(stream_));
-    }
-    for (int64_t r0 = 0; mD && r0 < Q_; r0 += rowsPerSlab) {
-      const int64_t nr = std::min(rowsPerSlab, Q_ - r0);
-      launch_unpad_rows(dRowScratch_.get(), dMD_ + r0 * Tp_, nr, T_, Tp_, stream_);
-      PQA_CU(cudaMemcpyAsync(mD + r0 * T_, dRowScratch_.get(), sizeof(double) * (size_t)(nr * T_), cudaMemcpyDeviceToHost, stream_));
-      PQA_CU(cudaStreamSynchronize(stream_));
-    }
+  const int64_t TL = tLocal_;
+  const int64_t rowsPerSlab = std::max<int64_t>(1, (256ll << 20) / (TL * 8));
+  for (int64_t r0 = 0; sA && r0 < Q_ * K_; r0 += rowsPerSlab) {
+    const int64_t nr = std::min(rowsPerSlab, Q_ * K_ - r0);
+    PQA_CU(cudaMemcpy2DAsync(sA + r0 * T_, (size_t)T_ * 8, dSA_ + r0 * TpL_, (size_t)TpL_ * 8, (size_t)TL * 8, (size_t)nr,
+                             cudaMemcpyDeviceToHost, stream_));
+  }
+  for (int64_t r0 = 0; mD && r0 < Q_; r0 += rowsPerSlab) {
+    const int64_t nr = std::min(rowsPerSlab, Q_ - r0);
+    PQA_CU(cudaMemcpy2DAsync(mD + r0 * T_, (size_t)T_ * 8, dMD_ + r0 * TpL_, (size_t)TpL_ * 8, (size_t)TL * 8, (size_t)nr,
+                             cudaMemcpyDeviceToHost, stream_));
   }
   if (vB) PQA_CU(cudaMemcpyAsync(vB, dVB_, sizeof(double) * (size_t)T_, cudaMemcpyDeviceToHost, stream_));
   PQA_CU(cudaStreamSynchronize(stream_));
@@ -970,6 +1002,7 @@ PqaError *Engine::SetEvalKernel(int32_t which, int64_t chunkTargets, int64_t qui
 PqaError *Engine::EvalQuestions(int64_t n, const int64_t *pQuizIds, double *pPriorities, double *pRunLength,
                                 double *pGrandTotals, int64_t *pnChunks) {
   if (n <= 0) return ErrNegativeCount(n, PQA_FILE_LINE "|n| must be positive.");
+  if (IsTargetSharded()) return ErrNotImplemented("EvalQuestions on a target-sharded engine: use the PqaB200_TShard* protocol");
   std::lock_guard<std::mutex> lk(mu_);
   for (int64_t x = 0; x < n; x++)
     if (PqaError *e = CheckQuiz(pQuizIds[x])) return e;
@@ -981,7 +1014,7 @@ PqaError *Engine::EvalQuestions(int64_t n, const int64_t *pQuizIds, double *pPri
   dGrand_.ensure((size_t)(n * nChunks), stream_);
   EvalDetail det{nullptr, nullptr, nullptr, nullptr};
   launch_eval_questions(kb(), pool(), n, dIds_.get(), dPriority_.get(), det, evalCfg_, stream_);
-  launch_select_question(kb(), pool(), n, dIds_.get(), dPriority_.get(), nullptr, W_, dRunLength_.get(), dGrand_.get(),
+  launch_select_question(kbQuiz(), pool(), n, dIds_.get(), dPriority_.get(), nullptr, W_, dRunLength_.get(), dGrand_.get(),
                          nullptr, 0, stream_);
   if (pPriorities) PQA_CU(cudaMemcpyAsync(pPriorities, dPriority_.get(), sizeof(double) * (size_t)(n * Q_), cudaMemcpyDeviceToHost, stream_));
   if (pRunLength) PQA_CU(cudaMemcpyAsync(pRunLength, dRunLength_.get(), sizeof(double) * (size_t)(n * Q_), cudaMemcpyDeviceToHost, stream_));
@@ -993,6 +1026,7 @@ PqaError *Engine::EvalQuestions(int64_t n, const int64_t *pQuizIds, double *pPri
 
 PqaError *Engine::EvalQuestionsDetailed(int64_t iQuiz, double *pW, double *pH, double *pV, double *pLack,
                                         double *pPriorities) {
+  if (IsTargetSharded()) return ErrNotImplemented("EvalQuestionsDetailed on a target-sharded engine");
   std::lock_guard<std::mutex> lk(mu_);
   if (PqaError *e = CheckQuiz(iQuiz)) return e;
   PQA_TRY
@@ -1017,6 +1051,7 @@ PqaError *Engine::EvalQuestionsDetailed(int64_t iQuiz, double *pW, double *pH, d
 // (evaluation + selection) whose results stay on the device. Used to time the hot path without host traffic.
 PqaError *Engine::ResidentBind(int64_t n, const int64_t *pQuizIds, const uint64_t *pRandoms) {
   if (n <= 0) return ErrNegativeCount(n, PQA_FILE_LINE "|n| must be positive.");
+  if (IsTargetSharded()) return ErrNotImplemented("resident stepping on a target-sharded engine");
   std::lock_guard<std::mutex> lk(mu_);
   for (int64_t x = 0; x < n; x++)
     if (PqaError *e = CheckQuiz(pQuizIds[x])) return e;
@@ -1041,7 +1076,7 @@ PqaError *Engine::ResidentStep() {
   PQA_CU(cudaEventRecord(evEvalStart_, stream_));
   launch_eval_questions(kb(), pool(), residentN_, dResIds_.get(), dResPriority_.get(), det, evalCfg_, stream_);
   PQA_CU(cudaEventRecord(evEvalStop_, stream_));
-  launch_select_question(kb(), pool(), residentN_, dResIds_.get(), dResPriority_.get(), dResRandoms_.get(), W_,
+  launch_select_question(kbQuiz(), pool(), residentN_, dResIds_.get(), dResPriority_.get(), dResRandoms_.get(), W_,
                          dResRunLength_.get(), nullptr, dResQuestions_.get(), 0, stream_);
   PQA_CU(cudaGetLastError());
   return nullptr;
@@ -1084,6 +1119,73 @@ PqaError *Engine::FlushL2() {
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Target-sharded evaluation, host-exchanged form (include/PqaB200Ext.h): each call enqueues one phase and waits for it;
+// the caller sums buffer 2 (W) / buffer 3 (H, V, lack) over the shards between the calls.
+PqaError *Engine::TShardEvalW(int64_t n, const int64_t *pQuizIds) {
+  if (n <= 0) return ErrNegativeCount(n, PQA_FILE_LINE "|n| must be positive.");
+  if (!IsTargetSharded()) return ErrNotImplemented("TShardEvalW on an engine without a target shard");
+  std::lock_guard<std::mutex> lk(mu_);
+  for (int64_t x = 0; x < n; x++)
+    if (PqaError *e = CheckQuiz(pQuizIds[x])) return e;
+  PQA_TRY
+  UploadIds(n, pQuizIds);
+  shardWCount_ = n * Q_ * K_; shardHVLCount_ = 0; shardPriorityCount_ = 0;
+  dShardW_.ensure((size_t)shardWCount_, stream_);
+  PQA_CU(cudaMemsetAsync(dShardW_.get(), 0, sizeof(double) * (size_t)shardWCount_, stream_));   // asked questions: +0
+  PeerBufs out; out.n = 1; out.p[0] = dShardW_.get();
+  launch_eval_tshard_w(kb(), pool(), tFirst_, n, dIds_.get(), out, evalCfg_, stream_);
+  PQA_CU(cudaStreamSynchronize(stream_));
+  return nullptr;
+  PQA_CATCH_RETURN_ERR
+}
+
+PqaError *Engine::TShardEvalHVL(int64_t n, const int64_t *pQuizIds) {
+  if (n <= 0) return ErrNegativeCount(n, PQA_FILE_LINE "|n| must be positive.");
+  std::lock_guard<std::mutex> lk(mu_);
+  if (shardWCount_ != n * Q_ * K_) return MakeError(ErrCode::NotInitialized, PQA_FILE_LINE "TShardEvalHVL without a matching TShardEvalW");
+  for (int64_t x = 0; x < n; x++)
+    if (PqaError *e = CheckQuiz(pQuizIds[x])) return e;
+  PQA_TRY
+  UploadIds(n, pQuizIds);
+  shardHVLCount_ = n * Q_ * (2 * K_ + 1);
+  dShardHVL_.ensure((size_t)shardHVLCount_, stream_);
+  PQA_CU(cudaMemsetAsync(dShardHVL_.get(), 0, sizeof(double) * (size_t)shardHVLCount_, stream_));
+  PeerBufs in, out; in.n = 1; in.p[0] = dShardW_.get(); out.n = 1; out.p[0] = dShardHVL_.get();
+  launch_eval_tshard_hvl(kb(), pool(), tFirst_, n, dIds_.get(), in, out, evalCfg_, stream_);
+  PQA_CU(cudaStreamSynchronize(stream_));
+  return nullptr;
+  PQA_CATCH_RETURN_ERR
+}
+
+PqaError *Engine::TShardPriority(int64_t n, const int64_t *pQuizIds) {
+  if (n <= 0) return ErrNegativeCount(n, PQA_FILE_LINE "|n| must be positive.");
+  std::lock_guard<std::mutex> lk(mu_);
+  if (shardWCount_ != n * Q_ * K_ || shardHVLCount_ != n * Q_ * (2 * K_ + 1))
+    return MakeError(ErrCode::NotInitialized, PQA_FILE_LINE "TShardPriority without matching TShardEvalW / TShardEvalHVL");
+  for (int64_t x = 0; x < n; x++)
+    if (PqaError *e = CheckQuiz(pQuizIds[x])) return e;
+  PQA_TRY
+  UploadIds(n, pQuizIds);
+  shardPriorityCount_ = n * Q_;
+  dShardPriority_.ensure((size_t)shardPriorityCount_, stream_);
+  PeerBufs inW, inHVL; inW.n = 1; inW.p[0] = dShardW_.get(); inHVL.n = 1; inHVL.p[0] = dShardHVL_.get();
+  EvalDetail det{nullptr, nullptr, nullptr, nullptr};
+  launch_tshard_priority(kb(), pool(), n, dIds_.get(), inW, inHVL, dShardPriority_.get(), det, stream_);
+  PQA_CU(cudaStreamSynchronize(stream_));
+  return nullptr;
+  PQA_CATCH_RETURN_ERR
+}
+
+PqaError *Engine::FillBinarySearchKB(double rounds) {
+  std::lock_guard<std::mutex> lk(mu_);
+  PQA_TRY
+  launch_fill_binary_search_kb(kb(), tFirst_, T_, initAmount_, rounds, stream_);
+  PQA_CU(cudaStreamSynchronize(stream_));
+  return nullptr;
+  PQA_CATCH_RETURN_ERR
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // KB file, byte-compatible with the reference (BaseEngine::LockedSaveKB BaseEngine.cpp:323-385, CpuEngine::SaveStatistics
 // CpuEngine.cpp:664-688, BaseEngine::WriteGaps :142-152, PermanentIdManager::Save PermanentIdManager.cpp:27-39; load side
 // PqaEngineBaseFactory::LoadEngineDefinition PqaEngineBaseFactory.cpp:56-83, BaseEngine ctor BaseEngine.cpp:26-57):
@@ -1102,7 +1204,7 @@ PqaError *FileOpErr(const char *path, const std::string &what) {
 
 PqaError *Engine::SaveKB(const char *filePath) {
   if (!filePath) return MakeError(ErrCode::NullArgument, PQA_FILE_LINE "Nullptr is passed in place of KB file name.");
-  if (qLocal_ != Q_) return ErrNotImplemented("SaveKB on a question-sharded engine");
+  if (IsSharded()) return ErrNotImplemented("SaveKB on a sharded engine");
   std::lock_guard<std::mutex> lk(mu_);   // the KB must not be trained while it is written (reference: shared lock)
   FileCloser fc{std::fopen(filePath, "wb")};
   if (!fc.f) return MakeError(ErrCode::CantOpenFile, PQA_FILE_LINE "Can't open the KB file to write.",

@@ -121,6 +121,17 @@ class Engine {
   int64_t questionShardFirst() const { return qFirst_; }
   int64_t questionShardCount() const { return qLocal_; }
 
+  // --- target-sharded operation (PqaB200Ext.h) ---
+  PqaError *TShardEvalW(int64_t n, const int64_t *pQuizIds);
+  PqaError *TShardEvalHVL(int64_t n, const int64_t *pQuizIds);
+  PqaError *TShardPriority(int64_t n, const int64_t *pQuizIds);
+  int64_t targetShardFirst() const { return tFirst_; }
+  int64_t targetShardCount() const { return tLocal_; }
+  bool IsTargetSharded() const { return tLocal_ != T_; }
+  bool IsSharded() const { return qLocal_ != Q_ || tLocal_ != T_; }
+  // closed-form synthetic KB of SURVEY.md 8d written on the device (this engine's shard of it)
+  PqaError *FillBinarySearchKB(double rounds);
+
   // --- device-resident stepping ---
   PqaError *ResidentBind(int64_t n, const int64_t *pQuizIds, const uint64_t *pRandoms);
   PqaError *ResidentStep();
@@ -146,6 +157,7 @@ class Engine {
   void UploadIds(int64_t n, const int64_t *ids);
   uint64_t NextRandom();
   DeviceKB kb() const;
+  DeviceKB kbQuiz() const;
   QuizPool pool() const;
   PqaError *ApplyTrain(const std::vector<TrainOp> &ops, const std::vector<int64_t> &targets,
                        const std::vector<double> &amounts);
@@ -160,8 +172,9 @@ class Engine {
   int device_ = 0, W_ = 1, smCount_ = 148;
   int64_t Q_ = 0, K_ = 0, T_ = 0, Tp_ = 0, askedWords_ = 0;
   int64_t qFirst_ = 0, qLocal_ = 0;   // question shard held by this engine (0, Q_ for a single-device engine)
-  int64_t shardPriorityCount_ = 0, shardPriorsCount_ = 0;
-  DevBuf<double> dShardPriority_, dShardPriors_;
+  int64_t tFirst_ = 0, tLocal_ = 0, TpL_ = 0;   // target shard (0, T_ unless target-sharded); TpL_ = row stride of sA/mD
+  int64_t shardPriorityCount_ = 0, shardPriorsCount_ = 0, shardWCount_ = 0, shardHVLCount_ = 0;
+  DevBuf<double> dShardPriority_, dShardPriors_, dShardW_, dShardHVL_;
   double initAmount_ = 0;
   uint32_t precMantissa_ = 0; uint16_t precExponent_ = 0;   // kept only to write them back into a KB file header
   cudaStream_t stream_ = nullptr;

@@ -33,6 +33,7 @@
 
 #include <math.h>
 #include <stdio.h>
+#include <stdexcept>
 
 namespace pqa {
 void count_launch();
@@ -473,6 +474,221 @@ __global__ void __launch_bounds__(kSmallWarps * 32, 4) k_eval_small(const Staged
     }
     __syncthreads();   // sWk / sPart / sSlot are rewritten by the next round
   }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Target-sharded evaluation (SURVEY.md 8e "Targets"; pqa_kernels.cuh): this device holds the columns
+// [tFirst, tFirst + P.kb.T) of every row. Same CTA shape and chunk loop as the chunked branch of k_eval_staged, split at
+// the point where the reference needs the complete W_k (:88-91):
+//   PHASE 1  pass 1 over the local targets -> partial W_k (the local 4 Kahan lanes + PreciseSum) into every peer slot
+//   PHASE 2  W_k = sum of the shards' partials in shard order (identical bits on every shard) -> pass 2 over the local
+//            targets -> partial H_k (sum post*log2 post), V_k, lack sum into every peer slot
+// A quiz' priors are full-length; the thread reads them at offset tFirst. Shard boundaries are multiples of 4 targets
+// (the Kahan lane of a target stays j % 4) and only the last shard may have padding lanes, where the priors are +0.
+struct TShardParams {
+  StagedParams S;
+  int64_t tFirst;
+  PeerBufs outW, inW, outHVL;
+};
+
+template <int K, int KL, int WARPS, int PHASE>
+__global__ void __launch_bounds__(WARPS * 32, 2) k_eval_tshard(const TShardParams TP) {
+  constexpr int THREADS = WARPS * 32;
+  constexpr int LPQ = 4 / KL;
+  constexpr int QPW = 32 / LPQ;
+  constexpr int NV = 2 * K + 1;
+  const StagedParams &P = TP.S;
+  extern __shared__ __align__(128) unsigned char smRaw[];
+  __shared__ uint64_t bar;
+  double *sR = (double *)smRaw;
+  double *sLR = sR + K * P.Jc;
+  double *sID2 = sLR + K * P.Jc;
+  const int64_t iLocal = blockIdx.x, i = P.kb.qFirst + iLocal, Q = P.kb.Q, TpL = P.kb.Tp;
+  if (bit32(P.kb.qgaps, i)) return;      // the epilogue writes the NaN
+  const int64_t tileFirst = (int64_t)blockIdx.y * P.quizzesPerCta;
+  const int64_t tileLimit = (tileFirst + P.quizzesPerCta < P.n) ? tileFirst + P.quizzesPerCta : P.n;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qw = lane / LPQ, l0 = (lane % LPQ) * KL;
+  if (threadIdx.x == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+  __syncthreads();
+  uint32_t parity = 0;
+  const int64_t b = tileFirst + (int64_t)warp * QPW + qw;
+  bool live = b < tileLimit;
+  const int64_t slot = P.slots[live ? b : tileLimit - 1];
+  if (live && bit64(P.qp.asked + slot * P.qp.askedWords, i)) live = false;
+  const double *pr = P.qp.priors + slot * P.qp.Tp + TP.tFirst, *lpr = P.qp.logPriors + slot * P.qp.Tp + TP.tFirst;
+  const int64_t o = b * Q + i;
+  if (PHASE == 1) {
+    Kahan kw[KL][K];
+#pragma unroll
+    for (int e = 0; e < KL; e++)
+#pragma unroll
+      for (int k = 0; k < K; k++) kw[e][k].init();
+    for (int64_t c = 0; c < P.nChunks; c++) {
+      stage_chunk<K, THREADS>(P, iLocal, c, false, sR, sLR, sID2, &bar, parity);
+      const int64_t j0 = c * P.Jc;
+      const int nVects = (int)(((TpL - j0 < P.Jc) ? (TpL - j0) : P.Jc) >> 2);
+      if (live) pass1_chunk<K, KL>(sR, P.Jc, nVects, j0, pr, l0, kw);
+      __syncthreads();
+    }
+    if (live) {
+      double W[K], iW[K], lW[K];
+      finish_pass1<K, KL>(kw, W, iW, lW);
+      if (l0 == 0) {
+        for (int r = 0; r < TP.outW.n; r++)
+#pragma unroll
+          for (int k = 0; k < K; k++) TP.outW.p[r][o * K + k] = W[k];
+      }
+    }
+  } else {
+    double W[K], iW[K], lW[K], H[K], V[K], L[KL];
+#pragma unroll
+    for (int k = 0; k < K; k++) { H[k] = 0.0; V[k] = 0.0; W[k] = 0.0; iW[k] = 0.0; lW[k] = 0.0; }
+#pragma unroll
+    for (int e = 0; e < KL; e++) L[e] = 0.0;
+    if (live) {
+#pragma unroll
+      for (int k = 0; k < K; k++) {
+        double w = TP.inW.p[0][o * K + k];
+        for (int r = 1; r < TP.inW.n; r++) w = __dadd_rn(w, TP.inW.p[r][o * K + k]);
+        W[k] = w;
+        iW[k] = __ddiv_rn(1.0, w);                                         // :91
+        lW[k] = log2(w);
+      }
+    }
+    for (int64_t c = 0; c < P.nChunks; c++) {
+      stage_chunk<K, THREADS>(P, iLocal, c, true, sR, sLR, sID2, &bar, parity);
+      const int64_t j0 = c * P.Jc;
+      const int nVects = (int)(((TpL - j0 < P.Jc) ? (TpL - j0) : P.Jc) >> 2);
+      if (live) pass2_chunk<K, KL>(sR, sLR, sID2, P.Jc, nVects, j0, pr, lpr, P.kb.log2tbl, l0, iW, lW, H, V, L);
+      __syncthreads();
+    }
+    if (live) {
+      double Ls = L[0];
+#pragma unroll
+      for (int e = 1; e < KL; e++) Ls = __dadd_rn(Ls, L[e]);
+#pragma unroll
+      for (int k = 0; k < K; k++) { H[k] = quiz_sum<KL>(H[k]); V[k] = quiz_sum<KL>(V[k]); }
+      Ls = quiz_sum<KL>(Ls);
+      if (l0 == 0) {
+        for (int r = 0; r < TP.outHVL.n; r++) {
+          double *dst = TP.outHVL.p[r] + o * NV;
+#pragma unroll
+          for (int k = 0; k < K; k++) { dst[k] = H[k]; dst[K + k] = V[k]; }
+          dst[2 * K] = Ls;
+        }
+      }
+    }
+  }
+}
+
+// Epilogue of the target-sharded evaluation: one thread per (quiz, question) sums the shards' slots in shard order and
+// computes the priority exactly like the single-device kernel does from its own sums.
+struct TShardEpilogueParams {
+  StagedParams S;
+  PeerBufs inW, inHVL;
+};
+template <int K>
+__global__ void __launch_bounds__(128) k_tshard_priority(const TShardEpilogueParams EP) {
+  constexpr int NV = 2 * K + 1;
+  const StagedParams &P = EP.S;
+  const int64_t Q = P.kb.Q, total = P.n * Q;
+  const double qnan = __longlong_as_double(0x7FF8000000000000ll);
+  for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < total; o += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = o / Q, i = o - b * Q;
+    const int64_t slot = P.slots[b];
+    if (bit32(P.kb.qgaps, i) || bit64(P.qp.asked + slot * P.qp.askedWords, i)) { P.priority[o] = qnan; continue; }
+    double W[K], H[K], V[K], L;
+#pragma unroll
+    for (int k = 0; k < K; k++) { W[k] = EP.inW.p[0][o * K + k]; H[k] = EP.inHVL.p[0][o * NV + k]; V[k] = EP.inHVL.p[0][o * NV + K + k]; }
+    L = EP.inHVL.p[0][o * NV + 2 * K];
+    for (int r = 1; r < EP.inW.n; r++) {
+#pragma unroll
+      for (int k = 0; k < K; k++) {
+        W[k] = __dadd_rn(W[k], EP.inW.p[r][o * K + k]);
+        H[k] = __dadd_rn(H[k], EP.inHVL.p[r][o * NV + k]);
+        V[k] = __dadd_rn(V[k], EP.inHVL.p[r][o * NV + K + k]);
+      }
+      L = __dadd_rn(L, EP.inHVL.p[r][o * NV + 2 * K]);
+    }
+    write_priority<K>(P, i, b, W, H, V, L);
+  }
+}
+
+template <int K, int PHASE>
+static void launch_tshard_k(TShardParams TP, size_t smem, cudaStream_t st) {
+  // two threads per quiz (128 quizzes per CTA pass) for big batches, four threads per quiz (64 per pass) below that
+  const bool wide = TP.S.n >= 128;
+  static bool attrSet = false;
+  if (!attrSet) {
+    cudaFuncSetAttribute(k_eval_tshard<K, 2, 8, PHASE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(k_eval_tshard<K, 1, 8, PHASE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attrSet = true;
+  }
+  const int64_t perPass = wide ? 128 : 64;
+  TP.S.quizzesPerCta = perPass;
+  dim3 grid((unsigned)TP.S.kb.qCount, (unsigned)((TP.S.n + perPass - 1) / perPass));
+  if (wide) k_eval_tshard<K, 2, 8, PHASE><<<grid, 256, smem, st>>>(TP);
+  else k_eval_tshard<K, 1, 8, PHASE><<<grid, 256, smem, st>>>(TP);
+  count_launch();
+}
+
+static size_t tshard_geometry(StagedParams &P, const EvalConfig &cfg) {
+  const int64_t bytesPerTarget = (2 * P.kb.K + 1) * (int64_t)sizeof(double);
+  const int64_t budget = 100 * 1024;  // two CTAs per SM
+  int64_t Jc = cfg.chunkTargets > 0 ? ((cfg.chunkTargets + 3) & ~3ll) : P.kb.Tp;
+  if (Jc > P.kb.Tp) Jc = P.kb.Tp;
+  if (Jc * bytesPerTarget > budget) Jc = (budget / bytesPerTarget) & ~31ll;
+  P.Jc = Jc;
+  P.nChunks = (P.kb.Tp + Jc - 1) / Jc;
+  P.quizzesPerCta = 0;
+  return (size_t)(Jc * bytesPerTarget);
+}
+
+#define PQA_K_SWITCH(K_, CALL)                                  \
+  switch (K_) {                                                 \
+    case 2: { constexpr int KK = 2; CALL; } break;              \
+    case 3: { constexpr int KK = 3; CALL; } break;              \
+    case 4: { constexpr int KK = 4; CALL; } break;              \
+    case 5: { constexpr int KK = 5; CALL; } break;              \
+    case 6: { constexpr int KK = 6; CALL; } break;              \
+    case 7: { constexpr int KK = 7; CALL; } break;              \
+    case 8: { constexpr int KK = 8; CALL; } break;              \
+    default: throw std::runtime_error("probqa_b200: target-sharded evaluation supports 2..8 answer options"); \
+  }
+
+void launch_eval_tshard_w(const DeviceKB &kbLocal, const QuizPool &qp, int64_t tFirst, int64_t n, const int64_t *dSlots,
+                          const PeerBufs &outW, const EvalConfig &cfg, cudaStream_t st) {
+  TShardParams TP;
+  TP.S.kb = kbLocal; TP.S.qp = qp; TP.S.n = n; TP.S.slots = dSlots; TP.S.priority = nullptr;
+  TP.S.det = EvalDetail{nullptr, nullptr, nullptr, nullptr};
+  TP.tFirst = tFirst; TP.outW = outW; TP.inW.n = 0; TP.outHVL.n = 0;
+  const size_t smem = tshard_geometry(TP.S, cfg);
+  PQA_K_SWITCH(kbLocal.K, (launch_tshard_k<KK, 1>(TP, smem, st)))
+}
+
+void launch_eval_tshard_hvl(const DeviceKB &kbLocal, const QuizPool &qp, int64_t tFirst, int64_t n, const int64_t *dSlots,
+                            const PeerBufs &inW, const PeerBufs &outHVL, const EvalConfig &cfg, cudaStream_t st) {
+  TShardParams TP;
+  TP.S.kb = kbLocal; TP.S.qp = qp; TP.S.n = n; TP.S.slots = dSlots; TP.S.priority = nullptr;
+  TP.S.det = EvalDetail{nullptr, nullptr, nullptr, nullptr};
+  TP.tFirst = tFirst; TP.outW.n = 0; TP.inW = inW; TP.outHVL = outHVL;
+  const size_t smem = tshard_geometry(TP.S, cfg);
+  PQA_K_SWITCH(kbLocal.K, (launch_tshard_k<KK, 2>(TP, smem, st)))
+}
+
+void launch_tshard_priority(const DeviceKB &kbLocal, const QuizPool &qp, int64_t n, const int64_t *dSlots,
+                            const PeerBufs &inW, const PeerBufs &inHVL, double *dPriority, const EvalDetail &det,
+                            cudaStream_t st) {
+  TShardEpilogueParams EP;
+  EP.S.kb = kbLocal; EP.S.qp = qp; EP.S.n = n; EP.S.slots = dSlots; EP.S.priority = dPriority; EP.S.det = det;
+  EP.S.Jc = 0; EP.S.nChunks = 0; EP.S.quizzesPerCta = 0;
+  EP.inW = inW; EP.inHVL = inHVL;
+  const int64_t total = n * kbLocal.Q;
+  int64_t g = (total + 127) / 128;
+  if (g > 148 * 16) g = 148 * 16;
+  PQA_K_SWITCH(kbLocal.K, (k_tshard_priority<KK><<<(unsigned)g, 128, 0, st>>>(EP)))
+  count_launch();
 }
 
 template <int K>

@@ -168,6 +168,88 @@ void launch_record_answer(const DeviceKB &kb, const QuizPool &qp, int64_t n, con
   count_launch();
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// RecordAnswer on a target shard (pqa_kernels.cuh): the elementwise half on the local columns, then -- once the row is
+// complete on every shard -- the bookkeeping and the reference's Kahan normalisation on the full row. The division and
+// the multiplication are the reference's (CERecordAnswerSubtaskMul.cpp:31-34), so the finished priors are bit-exact.
+__global__ void __launch_bounds__(256) k_tshard_ra_partial(DeviceKB kbL, QuizPool qp, int64_t tFirst,
+                                                           const int64_t *__restrict__ slots,
+                                                           const int64_t *__restrict__ answers, PeerBufs out) {
+  const int64_t b = blockIdx.y, slot = slots[b];
+  const int64_t q = qp.active[slot], a = answers[b];
+  const double *rowA = kbL.sA + ((q - kbL.qFirst) * kbL.K + a) * kbL.Tp, *rowD = kbL.mD + (q - kbL.qFirst) * kbL.Tp;
+  const double *prior = qp.priors + slot * qp.Tp + tFirst;
+  for (int64_t jl = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; jl < kbL.T; jl += (int64_t)gridDim.x * blockDim.x) {
+    const double m = bit32(kbL.tgaps, jl) ? 0.0 : __dmul_rn(prior[jl], __ddiv_rn(rowA[jl], rowD[jl]));
+    for (int r = 0; r < out.n; r++) out.p[r][b * qp.Tp + tFirst + jl] = m;
+  }
+}
+void launch_tshard_record_answer_partial(const DeviceKB &kbLocal, const QuizPool &qp, int64_t tFirst, int64_t n,
+                                         const int64_t *dSlots, const int64_t *dAnswers, const PeerBufs &out,
+                                         cudaStream_t st) {
+  if (n <= 0) return;
+  int64_t gx = (kbLocal.T + 255) / 256;
+  if (gx > 64) gx = 64;
+  k_tshard_ra_partial<<<dim3((unsigned)gx, (unsigned)n), 256, 0, st>>>(kbLocal, qp, tFirst, dSlots, dAnswers, out);
+  count_launch();
+}
+
+__global__ void __launch_bounds__(256) k_tshard_ra_finish(DeviceKB kb, QuizPool qp, const int64_t *__restrict__ slots,
+                                                          const double *__restrict__ rows, int W) {
+  extern __shared__ double sm[];
+  const int64_t slot = slots[blockIdx.x];
+  double *prior = qp.priors + slot * qp.Tp, *lprior = qp.logPriors + slot * qp.Tp;
+  const double *row = rows + (int64_t)blockIdx.x * qp.Tp;
+  for (int64_t j = threadIdx.x; j < kb.Tp; j += blockDim.x) prior[j] = (j < kb.T && !bit32(kb.tgaps, j)) ? row[j] : 0.0;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int64_t q = qp.active[slot];
+    qp.asked[slot * qp.askedWords + (q >> 6)] |= 1ull << (q & 63);  // CEQuiz.h:91
+    qp.active[slot] = -1;                                           // CEQuiz.h:92
+  }
+  kahan_normalise(prior, lprior, kb.T, kb.Tp, W, sm);
+}
+void launch_tshard_record_answer_finish(const DeviceKB &kbFull, const QuizPool &qp, int64_t n, const int64_t *dSlots,
+                                        const double *dRows, int W, cudaStream_t st) {
+  if (n <= 0) return;
+  k_tshard_ra_finish<<<(unsigned)n, 256, priors_smem(W), st>>>(kbFull, qp, dSlots, dRows, W);
+  count_launch();
+}
+
+// Closed-form binary-search KB (probqa_b200/synth.py answer_rule / binary_search_kb): the same double operations in the
+// same order, so the device-filled shard is bit-identical to the numpy arrays.
+__global__ void k_fill_binary_search_kb(DeviceKB kb, int64_t tFirst, int64_t Tg, double init, double rounds) {
+  const int64_t w = (32 * Tg) / 1000 > 1 ? (32 * Tg) / 1000 : 1;
+  const int64_t nD = kb.qCount * kb.Tp, stride = (int64_t)gridDim.x * blockDim.x;
+  const double hit = __dadd_rn(init, rounds), hit2 = __dmul_rn(hit, hit), miss2 = __dmul_rn(init, init);
+  for (int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; x < nD; x += stride) {
+    const int64_t il = x / kb.Tp, jl = x - il * kb.Tp;
+    const int64_t i = kb.qFirst + il, j = tFirst + jl;
+    const int64_t piv = (i * Tg) / kb.Q;
+    int64_t ans = j < piv - w ? 0 : j < piv ? 1 : j == piv ? 2 : j <= piv + w ? 3 : 4;
+    if (ans > kb.K - 1) ans = kb.K - 1;
+    double d = 0.0;
+    for (int64_t k = 0; k < kb.K; k++) {
+      const double a = jl < kb.T ? (k == ans ? hit2 : miss2) : 0.0;
+      kb.sA[(il * kb.K + k) * kb.Tp + jl] = a;
+      d = __dadd_rn(d, a);
+    }
+    kb.mD[x] = jl < kb.T ? d : 1.0;
+  }
+}
+__global__ void k_fill_vector(double *v, int64_t n, int64_t nValid, double value) {
+  for (int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; x < n; x += (int64_t)gridDim.x * blockDim.x)
+    v[x] = x < nValid ? value : 0.0;
+}
+void launch_fill_binary_search_kb(const DeviceKB &kbLocal, int64_t tFirst, int64_t Tglobal, double init, double rounds,
+                                  cudaStream_t st) {
+  k_fill_binary_search_kb<<<148 * 8, 256, 0, st>>>(kbLocal, tFirst, Tglobal, init, rounds);
+  count_launch();
+  const int64_t TpG = (Tglobal + 3) & ~3ll;
+  k_fill_vector<<<grid_for(TpG, 256), 256, 0, st>>>(kbLocal.vB, TpG, Tglobal, init + rounds);
+  count_launch();
+}
+
 // ResumeQuiz: CECreateQuizResume::UpdateLikelihoods (CECreateQuizOperation.cpp:55-83) = CEUpdatePriorsSubtaskMul
 // (CEUpdatePriorsSubtaskMul.cpp:40-82) + CpuEngine::NormalizePriors (CpuEngine.cpp:284-335; CENormPriorsSubtaskMax.cpp,
 // CENormPriorsSubtaskCorrSum.cpp). One CTA per quiz; bit-exact. The likelihood product over the answered questions is

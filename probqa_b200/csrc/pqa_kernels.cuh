@@ -102,6 +102,48 @@ void launch_train_ops(const DeviceKB &kb, const TrainOp *dOps, const int64_t *dG
 void launch_add_vb(const DeviceKB &kb, const int64_t *dTargets, const double *dAmounts, const int64_t *dGroupStart,
                    int64_t nGroups, cudaStream_t st);
 
+// ---------------------------------------------------------------------------------------------------------
+// Target-sharded engines (SURVEY.md 8e "Targets" row; BASELINE config 4): a device holds the columns
+// [tFirst, tFirst + kbLocal.T) of every sA/mD row (kbLocal: T = local target count, Tp = local row stride; Q, K and
+// nValidTargets describe the WHOLE KB), quiz state is replicated with full-length priors. The evaluation is two-phase
+// with one exchange between the phases:
+//   phase 1  partial W_k[b][i][k]  = sum over local targets of lik (4-lane Kahan in the reference's lane order)
+//   -------  sum over shards (NCCL all-reduce, or partials pushed into every peer's inbox over NVLink) -------
+//   phase 2  partial sum post*log2 post [K], sum (post-prior)^2 [K], lack sum [1] per (quiz, question)
+//   -------  sum over shards -------
+//   priority epilogue (CEEvalQsSubtaskConsider.cpp:134-207) on every shard, identical bits everywhere.
+// W_k is needed before phase 2 because log2(lik/W_k) sits in the denominator of the lack term.
+constexpr int kMaxPeers = 8;
+struct PeerBufs {           // where a partial result goes / comes from
+  int n;                    // 1 = this device's own buffer only (the caller sums across shards);
+                            // N = one buffer per shard: out[r] is this shard's slot in shard r's inbox (peer memory),
+                            //     in[r] is shard r's slot in this shard's inbox, summed in shard order
+  double *p[kMaxPeers];
+};
+// phase 1: outW.p[*][(b*Q + i)*K + k]
+void launch_eval_tshard_w(const DeviceKB &kbLocal, const QuizPool &qp, int64_t tFirst, int64_t n, const int64_t *dSlots,
+                          const PeerBufs &outW, const EvalConfig &cfg, cudaStream_t st);
+// phase 2: W = sum_r inW.p[r]; outHVL.p[*][(b*Q + i)*(2K+1) + {H_0..H_{K-1}, V_0..V_{K-1}, L}]
+void launch_eval_tshard_hvl(const DeviceKB &kbLocal, const QuizPool &qp, int64_t tFirst, int64_t n, const int64_t *dSlots,
+                            const PeerBufs &inW, const PeerBufs &outHVL, const EvalConfig &cfg, cudaStream_t st);
+// epilogue: priority[b*Q + i] (NaN where asked / gap) from the summed W and H/V/L; det optional
+void launch_tshard_priority(const DeviceKB &kbLocal, const QuizPool &qp, int64_t n, const int64_t *dSlots,
+                            const PeerBufs &inW, const PeerBufs &inHVL, double *dPriority, const EvalDetail &det,
+                            cudaStream_t st);
+// RecordAnswer on a target shard: out.p[*][b*qp.Tp + tFirst + jl] = prior * (sA[q][a][jl] / mD[q][jl]) for the local
+// targets (CERecordAnswerSubtaskMul.cpp:27-37, divide first); the other columns of the row are not touched.
+void launch_tshard_record_answer_partial(const DeviceKB &kbLocal, const QuizPool &qp, int64_t tFirst, int64_t n,
+                                         const int64_t *dSlots, const int64_t *dAnswers, const PeerBufs &out,
+                                         cudaStream_t st);
+// ... and its second half on the complete row dRows[b*Tp + j]: asked bit, active = -1, the reference's Kahan
+// normalisation (bit-exact, same as launch_record_answer). kbFull: T/Tp of the whole KB.
+void launch_tshard_record_answer_finish(const DeviceKB &kbFull, const QuizPool &qp, int64_t n, const int64_t *dSlots,
+                                        const double *dRows, int W, cudaStream_t st);
+// Closed-form synthetic KB of SURVEY.md 8d (probqa_b200/synth.py binary_search_kb, bit-identical) written straight into
+// this device's shard: sA = (init + rounds*[k == ans(i,j)])^2, mD = sum_k sA, vB = init + rounds.
+void launch_fill_binary_search_kb(const DeviceKB &kbLocal, int64_t tFirst, int64_t Tglobal, double init, double rounds,
+                                  cudaStream_t st);
+
 void launch_gather_prior_rows(const QuizPool &qp, int64_t n, const int64_t *dSlots, double *dBuf, cudaStream_t st);
 void launch_scatter_prior_rows(const QuizPool &qp, int64_t n, const int64_t *dSlots, const double *dBuf, cudaStream_t st);
 void launch_set_active(const QuizPool &qp, int64_t n, const int64_t *dSlots, const int64_t *dQuestions, cudaStream_t st);

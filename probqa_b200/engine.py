@@ -43,7 +43,8 @@ class CiRatedTarget(C.Structure):  # :32-35
 class CiB200Options(C.Structure):  # PqaB200Ext.h
     _pack_ = 8
     _fields_ = [("device", C.c_int32), ("emulatedWorkers", C.c_int32), ("rngSeed", C.c_uint64),
-                ("initialQuizCapacity", C.c_int64), ("questionShardFirst", C.c_int64), ("questionShardCount", C.c_int64)]
+                ("initialQuizCapacity", C.c_int64), ("questionShardFirst", C.c_int64), ("questionShardCount", C.c_int64),
+                ("targetShardFirst", C.c_int64), ("targetShardCount", C.c_int64)]
 
 
 RATED_DTYPE = np.dtype([("iTarget", np.int64), ("prob", np.float64)])
@@ -124,6 +125,11 @@ SIGNATURES = {
     "PqaB200_ShardRecordAnswerEnd": (_vp, [_vp, _i64, _pi64]),
     "PqaB200_ShardBuffer": (_vp, [_vp, C.c_int32, _pvp, _pi64]),
     "PqaB200_GetQuestionShard": (_vp, [_vp, _pi64, _pi64]),
+    "PqaB200_TShardEvalW": (_vp, [_vp, _i64, _pi64]),
+    "PqaB200_TShardEvalHVL": (_vp, [_vp, _i64, _pi64]),
+    "PqaB200_TShardPriority": (_vp, [_vp, _i64, _pi64]),
+    "PqaB200_GetTargetShard": (_vp, [_vp, _pi64, _pi64]),
+    "PqaB200_FillBinarySearchKB": (_vp, [_vp, C.c_double]),
     "PqaB200_ResidentBind": (_vp, [_vp, _i64, _pi64, _pu64]),
     "PqaB200_ResidentStep": (_vp, [_vp]),
     "PqaB200_ResidentFetch": (_vp, [_vp, _pi64]),
@@ -504,6 +510,28 @@ class PqaEngine:
         ids = _i64arr(quiz_ids)
         _raise_or_return(self._lib.PqaB200_ShardRecordAnswerEnd(self.c_engine, ids.size, _p(ids, _pi64)))
 
+    # ---------------------------------------------------------------- target-sharded protocol (PqaB200Ext.h)
+    def target_shard(self) -> Tuple[int, int]:
+        first, count = C.c_int64(), C.c_int64()
+        _raise_or_return(self._lib.PqaB200_GetTargetShard(self.c_engine, C.byref(first), C.byref(count)))
+        return first.value, count.value
+
+    def tshard_eval_w(self, quiz_ids):
+        ids = _i64arr(quiz_ids)
+        _raise_or_return(self._lib.PqaB200_TShardEvalW(self.c_engine, ids.size, _p(ids, _pi64)))
+
+    def tshard_eval_hvl(self, quiz_ids):
+        ids = _i64arr(quiz_ids)
+        _raise_or_return(self._lib.PqaB200_TShardEvalHVL(self.c_engine, ids.size, _p(ids, _pi64)))
+
+    def tshard_priority(self, quiz_ids):
+        ids = _i64arr(quiz_ids)
+        _raise_or_return(self._lib.PqaB200_TShardPriority(self.c_engine, ids.size, _p(ids, _pi64)))
+
+    def fill_binary_search_kb(self, rounds: float = 3.0):
+        """Device-side fill of this engine's shard with synth.binary_search_kb(Q, K, T, init_amount, rounds)."""
+        _raise_or_return(self._lib.PqaB200_FillBinarySearchKB(self.c_engine, float(rounds)))
+
     def resident_bind(self, quiz_ids, randoms=None):
         ids = _i64arr(quiz_ids)
         rnd = None if randoms is None else np.ascontiguousarray(randoms, dtype=np.uint64)
@@ -575,10 +603,11 @@ class PqaEngineFactory:
 
     def create_b200_engine(self, eng_def: EngineDefinition, device: int = -1, emulated_workers: int = 0,
                            rng_seed: int = 0, initial_quiz_capacity: int = 0, question_shard_first: int = 0,
-                           question_shard_count: int = 0) -> PqaEngine:
+                           question_shard_count: int = 0, target_shard_first: int = 0,
+                           target_shard_count: int = 0) -> PqaEngine:
         c_def = eng_def.to_c()
         opts = CiB200Options(device, emulated_workers, rng_seed, initial_quiz_capacity, question_shard_first,
-                             question_shard_count)
+                             question_shard_count, target_shard_first, target_shard_count)
         e = C.c_void_p()
         c_engine = self._lib.PqaB200_CreateEngine(C.byref(e), C.byref(c_def), C.byref(opts))
         if not c_engine:

@@ -31,6 +31,16 @@ def shard_ranges(n_questions: int, n_shards: int):
     return out
 
 
+def target_shard_ranges(n_targets: int, n_shards: int):
+    """[(first, count)] over targets in units of 4-target vectors (a target keeps its Kahan lane j % 4 inside a shard;
+    only the last shard can end off a multiple of 4, where the global padding lanes are)."""
+    out = []
+    for first_v, cnt_v in shard_ranges((n_targets + 3) // 4, n_shards):
+        first = 4 * first_v
+        out.append((first, min(4 * cnt_v, n_targets - first)))
+    return out
+
+
 class _CudaView:
     """Exposes engine-owned device memory to torch without a copy (torch.as_tensor reads __cuda_array_interface__)."""
 
@@ -165,3 +175,93 @@ class QuestionShardedEngine:
 
     def copy_quiz_priors(self, quiz):
         return self.shards[0].copy_quiz_priors(quiz)
+
+
+class B200TargetShard:
+    """Shard port over a PqaEngine created with a target shard (probqa_b200.engine): the columns
+    [first, first + count) of every sA/mD row live on this device, quiz state is replicated."""
+
+    def __init__(self, engine):
+        self.engine = engine
+        self.first, self.count = engine.target_shard()
+
+    def _view(self, which):
+        import torch
+        ptr, cnt = self.engine.shard_buffer(which)
+        return torch.as_tensor(_CudaView(ptr, cnt), device="cuda")
+
+    def start_quiz_batch(self, n):
+        return self.engine.start_quiz_batch(n)
+
+    def eval_w(self, quiz_ids):
+        self.engine.tshard_eval_w(quiz_ids)
+        return self._view(2)
+
+    def eval_hvl(self, quiz_ids):
+        self.engine.tshard_eval_hvl(quiz_ids)
+        return self._view(3)
+
+    def priority(self, quiz_ids):
+        self.engine.tshard_priority(quiz_ids)
+        return self._view(0)
+
+    def select(self, quiz_ids, randoms):
+        return self.engine.shard_select(quiz_ids, randoms)
+
+    def record_answer_begin(self, quiz_ids, answers):
+        self.engine.shard_record_answer_begin(quiz_ids, answers)
+        return self._view(1)
+
+    def record_answer_end(self, quiz_ids):
+        self.engine.shard_record_answer_end(quiz_ids)
+
+    def set_active_question_batch(self, quiz_ids, questions):
+        self.engine.set_active_question_batch(quiz_ids, questions)
+
+    def list_top_targets_batch(self, quiz_ids, max_count):
+        return self.engine.list_top_targets_batch(quiz_ids, max_count)
+
+    def record_quiz_target_batch(self, quiz_ids, targets, amounts=None):
+        self.engine.record_quiz_target_batch(quiz_ids, targets, amounts)
+
+    def train(self, answered_questions, i_target, amount=1.0):
+        self.engine.train(answered_questions, i_target, amount)
+
+    def release_quiz_batch(self, quiz_ids):
+        self.engine.release_quiz_batch(quiz_ids)
+
+    def copy_quiz_priors(self, quiz):
+        return self.engine.copy_quiz_priors(quiz)
+
+
+class TargetShardedEngine(QuestionShardedEngine):
+    """Target-sharded multi-GPU engine (SURVEY.md 8e "Targets" row, BASELINE config 4): every shard holds a slice of the
+    targets of every row. NextQuestion is two-phase with an all-reduce after each phase:
+
+      phase 1: partial W_k[n][Q][K] over the local targets            -> all-reduce(sum)
+      phase 2: partial sum post*log2 post, sum (post-prior)^2, lack   -> all-reduce(sum) -> priority epilogue -> selection
+
+    The sums over shards are not in CpuEngine's order, so priorities are tolerance-level here (identical on all shards:
+    every shard receives the same reduced bits), unlike the question-sharded engine. Posteriors stay bit-exact:
+    RecordAnswer all-reduces the shards' disjoint column slices of the un-normalised row (x + 0 is exact) and every shard
+    normalises the complete row in the reference's order. The remaining calls are inherited."""
+
+    def _priorities(self, quiz_ids):
+        self._all_reduce([s.eval_w(quiz_ids) for s in self.shards])
+        self._all_reduce([s.eval_hvl(quiz_ids) for s in self.shards])
+        return [s.priority(quiz_ids) for s in self.shards]
+
+    def next_question_batch(self, quiz_ids, randoms: Optional[np.ndarray] = None) -> np.ndarray:
+        quiz_ids = np.ascontiguousarray(quiz_ids, dtype=np.int64)
+        if randoms is None:
+            randoms = self._rng.integers(0, 2 ** 64, size=quiz_ids.size, dtype=np.uint64)
+        self._priorities(quiz_ids)
+        return self._same([s.select(quiz_ids, randoms) for s in self.shards])
+
+    def eval_priorities(self, quiz_ids):
+        quiz_ids = np.ascontiguousarray(quiz_ids, dtype=np.int64)
+        bufs = self._priorities(quiz_ids)
+        out = [b.detach().cpu().numpy().reshape(quiz_ids.size, -1).copy() for b in bufs]
+        for o in out[1:]:
+            assert np.array_equal(out[0].view(np.uint64), o.view(np.uint64)), "shards computed different priorities"
+        return out[0]

@@ -75,3 +75,103 @@ def test_sharded_engines_match_single_engine(dims, n_shards, lanes):
     # a sharded engine refuses the single-engine calls instead of answering from a partial KB
     with pytest.raises(pqa.PqaException):
         shards[0].engine.next_question(int(ids[0]))
+
+
+@pytest.mark.parametrize("dims,n_shards,chunk,n", [((40, 5, 203), 2, 0, 9), ((64, 5, 1000), 3, 64, 70), ((37, 4, 96), 4, 0, 5),
+                                                   ((24, 5, 2050), 2, 0, 130)])
+def test_target_sharded_engines_match_single_engine(dims, n_shards, chunk, n):
+    """Target shards (BASELINE config 4's axis) on one GPU against one un-sharded engine. Posteriors, top-10 lists and the
+    trained KB are bit-identical; priorities are tolerance-level (the sums over shards are not CpuEngine's single Kahan
+    pass): W_k 1e-14, priority 1e-10 relative on this KB, and every shard holds the same priority bits."""
+    from probqa_b200 import engine as pqa
+    Q, K, T = dims
+    W = 6
+    kb = synth.gamma_kb(Q, K, T, INIT)
+    fac = pqa.PqaEngineFactory()
+    edef = pqa.EngineDefinition(K, Q, T, init_amount=INIT)
+    full = fac.create_b200_engine(edef, emulated_workers=W, rng_seed=5)
+    full.upload_kb(*kb)
+    shards = []
+    ranges = sharded.target_shard_ranges(T, n_shards)
+    assert sum(c for _, c in ranges) == T and all(f % 4 == 0 for f, _ in ranges)
+    for first, count in ranges:
+        e = fac.create_b200_engine(edef, emulated_workers=W, rng_seed=5, target_shard_first=first, target_shard_count=count)
+        e.upload_kb(*kb)
+        e.set_eval_kernel(2, chunk_targets=chunk)
+        assert e.target_shard() == (first, count)
+        shards.append(sharded.B200TargetShard(e))
+    eng = sharded.TargetShardedEngine(shards)
+
+    ids = eng.start_quiz_batch(n)
+    ids_full = full.start_quiz_batch(n)
+    assert np.array_equal(ids, ids_full)
+    rng = np.random.default_rng(78)
+    for step in range(3):
+        want_pri = full.eval_questions(ids_full)["priority"]
+        got_pri = eng.eval_priorities(ids)      # also asserts that all shards hold identical bits
+        assert np.array_equal(np.isnan(got_pri), np.isnan(want_pri))
+        ok = ~np.isnan(want_pri)
+        rel = np.abs(got_pri[ok] - want_pri[ok]) / np.abs(want_pri[ok])
+        assert rel.max() < 1e-10, rel.max()
+        # the all-reduced normalisers against the single engine's bit-exact W_k
+        det = full.eval_questions_detailed(int(ids_full[0]))
+        w_sh = shards[0]._view(2).cpu().numpy().reshape(n, Q, K)[0]
+        okw = ~np.isnan(det["W"])
+        assert np.max(np.abs(w_sh[okw] - det["W"][okw]) / det["W"][okw]) < 1e-14
+        randoms = rng.integers(0, 2 ** 64, size=n, dtype=np.uint64)
+        chosen = eng.next_question_batch(ids, randoms)
+        assert np.all((chosen >= 0) & (chosen < Q))
+        full.set_active_question_batch(ids_full, chosen)     # same state on both sides whatever the draw resolved to
+        answers = [(int(c) * 7 + step) % K for c in chosen]
+        eng.record_answer_batch(ids, answers)
+        full.record_answer_batch(ids_full, answers)
+        for s in shards:
+            for q in ids[:6]:
+                assert np.array_equal(bits(s.copy_quiz_priors(int(q))), bits(full.copy_quiz_priors(int(q))))
+        items, counts = eng.list_top_targets_batch(ids, 10)
+        items_f, counts_f = full.list_top_targets_batch(ids_full, 10)
+        assert np.array_equal(counts, counts_f) and items.tobytes() == items_f.tobytes()
+    targets = rng.integers(0, T, size=n)
+    eng.record_quiz_target_batch(ids, targets)
+    full.record_quiz_target_batch(ids_full, targets)
+    aqs = [pqa.AnsweredQuestion(int(q), int(a)) for q, a in zip(rng.integers(0, Q, 12), rng.integers(0, K, 12))]
+    eng.train(aqs, 3, 0.5)
+    full.train(aqs, 3, 0.5)
+    wA, wD, wB = full.download_kb()
+    gA, gD = np.full_like(wA, np.nan), np.full_like(wD, np.nan)
+    for s in shards:
+        a, d, b = s.engine.download_kb()    # fills this shard's columns only
+        f, c = s.first, s.count
+        gA[:, :, f:f + c], gD[:, f:f + c] = a[:, :, f:f + c], d[:, f:f + c]
+        assert np.array_equal(bits(b), bits(wB))
+        assert np.array_equal(bits(s.engine.copy_a_targets(1, 2)[f:f + c]), bits(wA[1, 2, f:f + c]))
+        assert np.array_equal(bits(s.engine.copy_d_targets(1)[f:f + c]), bits(wD[1, f:f + c]))
+    assert np.array_equal(bits(gA), bits(wA)) and np.array_equal(bits(gD), bits(wD))
+    with pytest.raises(pqa.PqaException):
+        shards[0].engine.next_question(int(ids[0]))
+
+
+@pytest.mark.parametrize("dims", [(50, 5, 1000), (33, 3, 250), (20, 5, 4100)])
+def test_device_filled_binary_search_kb_is_bit_identical(dims):
+    from probqa_b200 import engine as pqa
+    Q, K, T = dims
+    want = synth.binary_search_kb(Q, K, T, INIT, 3)
+    fac = pqa.PqaEngineFactory()
+    edef = pqa.EngineDefinition(K, Q, T, init_amount=INIT)
+    full = fac.create_b200_engine(edef, emulated_workers=4)
+    full.fill_binary_search_kb(3)
+    for g, w in zip(full.download_kb(), want):
+        assert np.array_equal(bits(g), bits(w))
+    gA, gD = np.full_like(want[0], np.nan), np.full_like(want[1], np.nan)
+    for f, c in sharded.target_shard_ranges(T, 3):
+        e = fac.create_b200_engine(edef, emulated_workers=4, target_shard_first=f, target_shard_count=c)
+        e.fill_binary_search_kb(3)
+        a, d, b = e.download_kb()
+        gA[:, :, f:f + c], gD[:, f:f + c] = a[:, :, f:f + c], d[:, f:f + c]
+        assert np.array_equal(bits(b), bits(want[2]))
+    assert np.array_equal(bits(gA), bits(want[0])) and np.array_equal(bits(gD), bits(want[1]))
+    f, c = sharded.shard_ranges(Q, 2)[1]
+    e = fac.create_b200_engine(edef, emulated_workers=4, question_shard_first=f, question_shard_count=c)
+    e.fill_binary_search_kb(3)
+    a, d, b = e.download_kb()
+    assert np.array_equal(bits(a[f:f + c]), bits(want[0][f:f + c])) and np.array_equal(bits(d[f:f + c]), bits(want[1][f:f + c]))
