@@ -130,6 +130,28 @@ PQACORE_API void *PqaB200_GetTargetShard(void *pvEngine, int64_t *pFirst, int64_
  * (probqa_b200/synth.py binary_search_kb, bit-identical) on the device: KBs too large to stage through the host. */
 PQACORE_API void *PqaB200_FillBinarySearchKB(void *pvEngine, double rounds);
 
+/* ---- shard exchange over peer memory (NVLink P2P), for question-sharded and target-sharded engines ----
+ * Instead of handing buffers to the caller for an all-reduce, the engines exchange directly: each engine owns an
+ * "inbox" allocation; the evaluation / RecordAnswer kernels store what the other shards need straight into the other
+ * shards' inboxes from their epilogues, and a one-CTA barrier kernel (release/acquire flags in the inboxes) orders the
+ * phases on the device. No host round trip or separate collective launch sits between the phases of a call.
+ *   setup : P2PInit on every engine (same nRanks / maxQuizzes) -> exchange the inbox bases: within one process pass
+ *           *ppBase around; between processes P2PExportHandle (64-byte cudaIpcMemHandle_t) -> all-gather -> P2POpenHandle
+ *           -> P2PConnect(bases of all ranks, own entry ignored).
+ *   calls : every shard issues the same sequence of P2PNextQuestionBegin/End and P2PRecordAnswerBegin/End calls with
+ *           the same quiz ids, draws and answers. Begin only enqueues (so one thread can drive several engines of one
+ *           process: Begin on all, then End on all); End waits and returns the results. Results equal those of the
+ *           caller-exchanged Shard* / TShard* protocol bit for bit (shard partials are summed in rank order).
+ * A shard that does not show up within 20 s makes the barrier give up: End returns an Internal error. */
+PQACORE_API void *PqaB200_P2PInit(void *pvEngine, int32_t rank, int32_t nRanks, int64_t maxQuizzes, void **ppBase, int64_t *pBytes);
+PQACORE_API void *PqaB200_P2PExportHandle(void *pvEngine, uint8_t *pHandle64);
+PQACORE_API void *PqaB200_P2POpenHandle(void *pvEngine, const uint8_t *pHandle64, void **ppPeerBase);
+PQACORE_API void *PqaB200_P2PConnect(void *pvEngine, void *const *pBases);
+PQACORE_API void *PqaB200_P2PNextQuestionBegin(void *pvEngine, int64_t n, const int64_t *pQuizIds, const uint64_t *pRandoms);
+PQACORE_API void *PqaB200_P2PNextQuestionEnd(void *pvEngine, int64_t n, const int64_t *pQuizIds, int64_t *pQuestions, void **ppErrors);
+PQACORE_API void *PqaB200_P2PRecordAnswerBegin(void *pvEngine, int64_t n, const int64_t *pQuizIds, const int64_t *pAnswers);
+PQACORE_API void *PqaB200_P2PRecordAnswerEnd(void *pvEngine);
+
 /* ---- device-resident stepping and timing (bench.py "value" leg: no host<->device traffic inside) ---- */
 /* Binds n quizzes as the resident batch: ids and one random draw per quiz are copied to the device once. */
 PQACORE_API void *PqaB200_ResidentBind(void *pvEngine, int64_t n, const int64_t *pQuizIds, const uint64_t *pRandoms);

@@ -377,6 +377,38 @@ PQACORE_API void *PqaB200_FillBinarySearchKB(void *pvEngine, double rounds) {
   if (!pvEngine) return NullEngine();
   return Ret(E(pvEngine)->FillBinarySearchKB(rounds));
 }
+PQACORE_API void *PqaB200_P2PInit(void *pvEngine, int32_t rank, int32_t nRanks, int64_t maxQuizzes, void **ppBase, int64_t *pBytes) {
+  if (!pvEngine) return NullEngine();
+  return Ret(E(pvEngine)->P2PInit(rank, nRanks, maxQuizzes, ppBase, pBytes));
+}
+PQACORE_API void *PqaB200_P2PExportHandle(void *pvEngine, uint8_t *pHandle64) {
+  if (!pvEngine) return NullEngine();
+  return Ret(E(pvEngine)->P2PExportHandle(pHandle64));
+}
+PQACORE_API void *PqaB200_P2POpenHandle(void *pvEngine, const uint8_t *pHandle64, void **ppPeerBase) {
+  if (!pvEngine) return NullEngine();
+  return Ret(E(pvEngine)->P2POpenHandle(pHandle64, ppPeerBase));
+}
+PQACORE_API void *PqaB200_P2PConnect(void *pvEngine, void *const *pBases) {
+  if (!pvEngine) return NullEngine();
+  return Ret(E(pvEngine)->P2PConnect(pBases));
+}
+PQACORE_API void *PqaB200_P2PNextQuestionBegin(void *pvEngine, int64_t n, const int64_t *pQuizIds, const uint64_t *pRandoms) {
+  if (!pvEngine) return NullEngine();
+  return Ret(E(pvEngine)->P2PNextQuestionBegin(n, pQuizIds, pRandoms));
+}
+PQACORE_API void *PqaB200_P2PNextQuestionEnd(void *pvEngine, int64_t n, const int64_t *pQuizIds, int64_t *pQuestions, void **ppErrors) {
+  if (!pvEngine) return NullEngine();
+  return Ret(E(pvEngine)->P2PNextQuestionEnd(n, pQuizIds, pQuestions, ppErrors));
+}
+PQACORE_API void *PqaB200_P2PRecordAnswerBegin(void *pvEngine, int64_t n, const int64_t *pQuizIds, const int64_t *pAnswers) {
+  if (!pvEngine) return NullEngine();
+  return Ret(E(pvEngine)->P2PRecordAnswerBegin(n, pQuizIds, pAnswers));
+}
+PQACORE_API void *PqaB200_P2PRecordAnswerEnd(void *pvEngine) {
+  if (!pvEngine) return NullEngine();
+  return Ret(E(pvEngine)->P2PRecordAnswerEnd());
+}
 PQACORE_API void *PqaB200_ResidentBind(void *pvEngine, int64_t n, const int64_t *pQuizIds, const uint64_t *pRandoms) {
   if (!pvEngine) return NullEngine();
   return Ret(E(pvEngine)->ResidentBind(n, pQuizIds, pRandoms));

@@ -124,6 +124,8 @@ Engine::~Engine() {
   if (stream_) cudaStreamSynchronize(stream_);
   cudaFree(dSA_); cudaFree(dMD_); cudaFree(dVB_); cudaFree(dLog2Tbl_);
   cudaFree(dPriors_); cudaFree(dLogPriors_); cudaFree(dAsked_); cudaFree(dActive_);
+  for (int r = 0; r < kMaxPeers; r++) if (p2pOpened_[r]) cudaIpcCloseMemHandle(p2pPeer_[r]);
+  if (p2pInbox_) cudaFree(p2pInbox_);
   if (flushBuf_) cudaFree(flushBuf_);
   if (evEvalStart_) { cudaEventDestroy(evEvalStart_); cudaEventDestroy(evEvalStop_); }
   if (stream_) cudaStreamDestroy(stream_);
@@ -633,7 +635,7 @@ PqaError *Engine::ShardRecordAnswerEnd(int64_t n, const int64_t *pQuizIds) {
 PqaError *Engine::ShardBuffer(int32_t which, void **ppDevice, int64_t *pCount) {
   std::lock_guard<std::mutex> lk(mu_);
   if (!ppDevice || !pCount) return MakeError(ErrCode::NullArgument, PQA_FILE_LINE "ppDevice/pCount");
-  if (which == 0) { *ppDevice = dShardPriority_.get(); *pCount = shardPriorityCount_; }
+  if (which == 0) { *ppDevice = p2pLastPriority_ ? p2pLastPriority_ : dShardPriority_.get(); *pCount = shardPriorityCount_; }
   else if (which == 1) { *ppDevice = dShardPriors_.get(); *pCount = shardPriorsCount_; }
   else if (which == 2) { *ppDevice = dShardW_.get(); *pCount = shardWCount_; }
   else if (which == 3) { *ppDevice = dShardHVL_.get(); *pCount = shardHVLCount_; }
@@ -1174,6 +1176,262 @@ PqaError *Engine::TShardPriority(int64_t n, const int64_t *pQuizIds) {
   PQA_CU(cudaStreamSynchronize(stream_));
   return nullptr;
   PQA_CATCH_RETURN_ERR
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Shard exchange over peer memory. Inbox layout (identical on every shard; [2] = parity of the operation counter, so a
+// shard that runs ahead into the next operation never overwrites what a slower shard is still reading):
+//   0    flags[kMaxPeers] u64 (last epoch published by each rank)    64   error flag
+//   W    [2][nRanks][cap*Q*K]        partial normalisers, slot r written by shard r        (target shards)
+//   HVL  [2][nRanks][cap*Q*(2K+1)]   partial H/V/lack sums, slot r written by shard r      (target shards)
+//   rows [2][cap*Tp]                 RecordAnswer rows: disjoint column slices (target shards) / owner's row (question shards)
+//   pri  [2][cap*Q]                  priorities: disjoint question columns                 (question shards)
+PqaError *Engine::P2PInit(int32_t rank, int32_t nRanks, int64_t maxQuizzes, void **ppBase, int64_t *pBytes) {
+  if (nRanks < 1 || nRanks > kMaxPeers) return ErrIndexOutOfRange(nRanks, 1, kMaxPeers, PQA_FILE_LINE "nRanks");
+  if (rank < 0 || rank >= nRanks) return ErrIndexOutOfRange(rank, 0, nRanks - 1, PQA_FILE_LINE "rank");
+  if (maxQuizzes <= 0) return ErrNegativeCount(maxQuizzes, PQA_FILE_LINE "|maxQuizzes| must be positive.");
+  if (!IsSharded()) return ErrNotImplemented("P2PInit on an engine without a question or target shard");
+  std::lock_guard<std::mutex> lk(mu_);
+  if (p2pInbox_) return MakeError(ErrCode::WrongMode, PQA_FILE_LINE "the peer-memory inbox exists already");
+  PQA_TRY
+  PQA_CU(cudaSetDevice(device_));
+  auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
+  const bool ts = IsTargetSharded();
+  p2pSzW_ = ts ? up(sizeof(double) * (size_t)(maxQuizzes * Q_ * K_)) : 0;
+  p2pSzHVL_ = ts ? up(sizeof(double) * (size_t)(maxQuizzes * Q_ * (2 * K_ + 1))) : 0;
+  p2pSzRows_ = up(sizeof(double) * (size_t)(maxQuizzes * Tp_));
+  p2pSzPri_ = ts ? 0 : up(sizeof(double) * (size_t)(maxQuizzes * Q_));
+  p2pOffW_ = 256;
+  p2pOffHVL_ = p2pOffW_ + 2 * (size_t)nRanks * p2pSzW_;
+  p2pOffRows_ = p2pOffHVL_ + 2 * (size_t)nRanks * p2pSzHVL_;
+  p2pOffPri_ = p2pOffRows_ + 2 * p2pSzRows_;
+  p2pBytes_ = p2pOffPri_ + 2 * p2pSzPri_;
+  PQA_CU(cudaMalloc(&p2pInbox_, p2pBytes_));
+  PQA_CU(cudaMemsetAsync(p2pInbox_, 0, p2pBytes_, stream_));
+  preload_exchange_kernels((int)K_);
+  // size every scratch buffer of the P2P calls now: growing one later would cudaFree, which waits for the whole device
+  // -- including another engine's barrier kernel that is waiting for THIS engine (several engines in one process)
+  dIds_.ensure((size_t)maxQuizzes, stream_); dRandoms_.ensure((size_t)maxQuizzes, stream_);
+  dAnswers_.ensure((size_t)maxQuizzes, stream_); dQuestions_.ensure((size_t)maxQuizzes, stream_);
+  dRunLength_.ensure((size_t)(maxQuizzes * Q_), stream_);
+  if (ts) dShardPriority_.ensure((size_t)(maxQuizzes * Q_), stream_);
+  hIds_.ensure((size_t)maxQuizzes); hRandoms_.ensure((size_t)maxQuizzes); hAnswers_.ensure((size_t)maxQuizzes);
+  hQuestions_.ensure((size_t)maxQuizzes);
+  PQA_CU(cudaStreamSynchronize(stream_));
+  p2pRank_ = rank; p2pRanks_ = nRanks; p2pCap_ = maxQuizzes;
+  p2pPeer_[rank] = p2pInbox_;
+  if (ppBase) *ppBase = p2pInbox_;
+  if (pBytes) *pBytes = (int64_t)p2pBytes_;
+  return nullptr;
+  PQA_CATCH_RETURN_ERR
+}
+
+PqaError *Engine::P2PExportHandle(uint8_t *pHandle64) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  if (!pHandle64) return MakeError(ErrCode::NullArgument, PQA_FILE_LINE "pHandle64");
+  std::lock_guard<std::mutex> lk(mu_);
+  if (!p2pInbox_) return MakeError(ErrCode::NotInitialized, PQA_FILE_LINE "P2PInit first");
+  PQA_TRY
+  cudaIpcMemHandle_t h;
+  PQA_CU(cudaIpcGetMemHandle(&h, p2pInbox_));
+  std::memcpy(pHandle64, &h, 64);
+  return nullptr;
+  PQA_CATCH_RETURN_ERR
+}
+
+PqaError *Engine::P2POpenHandle(const uint8_t *pHandle64, void **ppPeerBase) {
+  if (!pHandle64 || !ppPeerBase) return MakeError(ErrCode::NullArgument, PQA_FILE_LINE "pHandle64/ppPeerBase");
+  std::lock_guard<std::mutex> lk(mu_);
+  PQA_TRY
+  PQA_CU(cudaSetDevice(device_));
+  cudaIpcMemHandle_t h;
+  std::memcpy(&h, pHandle64, 64);
+  PQA_CU(cudaIpcOpenMemHandle(ppPeerBase, h, cudaIpcMemLazyEnablePeerAccess));
+  return nullptr;
+  PQA_CATCH_RETURN_ERR
+}
+
+PqaError *Engine::P2PConnect(void *const *pBases) {
+  if (!pBases) return MakeError(ErrCode::NullArgument, PQA_FILE_LINE "pBases");
+  std::lock_guard<std::mutex> lk(mu_);
+  if (!p2pInbox_) return MakeError(ErrCode::NotInitialized, PQA_FILE_LINE "P2PInit first");
+  PQA_TRY
+  for (int r = 0; r < p2pRanks_; r++) {
+    if (r == p2pRank_) continue;
+    if (!pBases[r]) return MakeError(ErrCode::NullArgument, PQA_FILE_LINE "a peer inbox base is NULL");
+    p2pPeer_[r] = (char *)pBases[r];
+    // inboxes of other devices in this process need peer access; IPC-opened ones got it when they were opened
+    cudaPointerAttributes at;
+    PQA_CU(cudaPointerGetAttributes(&at, pBases[r]));
+    if (at.device != device_) {
+      PQA_CU(cudaSetDevice(device_));
+      const cudaError_t e = cudaDeviceEnablePeerAccess(at.device, 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) PQA_CU(e);
+      (void)cudaGetLastError();
+    }
+  }
+  p2pConnected_ = true;
+  return nullptr;
+  PQA_CATCH_RETURN_ERR
+}
+
+P2PFlags Engine::p2pFlags() const {
+  P2PFlags f;
+  f.rank = p2pRank_; f.nRanks = p2pRanks_;
+  for (int r = 0; r < kMaxPeers; r++) f.flags[r] = (uint64_t *)p2pPeer_[r];
+  f.errFlag = (uint64_t *)(p2pInbox_ + 64);
+  return f;
+}
+
+PqaError *Engine::P2PCheckError() {
+  uint64_t flag = 0;
+  PQA_TRY
+  PQA_CU(cudaMemcpyAsync(&flag, p2pInbox_ + 64, 8, cudaMemcpyDeviceToHost, stream_));
+  PQA_CU(cudaStreamSynchronize(stream_));
+  if (flag != 0)
+    return MakeError(ErrCode::Internal, PQA_FILE_LINE "peer-memory barrier timed out: a shard did not reach epoch " +
+                     std::to_string(flag) + " (all shards must issue the same P2P calls in the same order)");
+  return nullptr;
+  PQA_CATCH_RETURN_ERR
+}
+
+static const uint64_t kP2PTimeoutNs = 20ull * 1000 * 1000 * 1000;
+
+PqaError *Engine::P2PNextQuestionBegin(int64_t n, const int64_t *pQuizIds, const uint64_t *pRandoms) {
+  if (n <= 0) return ErrNegativeCount(n, PQA_FILE_LINE "|n| must be positive.");
+  if (!pQuizIds || !pRandoms)
+    return MakeError(ErrCode::NullArgument, PQA_FILE_LINE "pQuizIds/pRandoms (every shard must use the same draws)");
+  std::lock_guard<std::mutex> lk(mu_);
+  if (!p2pConnected_) return MakeError(ErrCode::NotInitialized, PQA_FILE_LINE "P2PInit / P2PConnect first");
+  if (p2pPending_) return MakeError(ErrCode::WrongMode, PQA_FILE_LINE "a P2P operation is pending: call its End first");
+  if (n > p2pCap_) return ErrIndexOutOfRange(n, 1, p2pCap_, PQA_FILE_LINE "more quizzes than the inbox was sized for");
+  if (!IsTargetSharded() && evalCfg_.which == 1) return ErrNotImplemented("peer-memory exchange with the exact kernel");
+  for (int64_t x = 0; x < n; x++)
+    if (PqaError *e = CheckQuiz(pQuizIds[x])) return e;
+  PQA_TRY
+  UploadIds(n, pQuizIds);
+  hRandoms_.ensure(n); dRandoms_.ensure(n, stream_);
+  std::memcpy(hRandoms_.get(), pRandoms, sizeof(uint64_t) * (size_t)n);
+  PQA_CU(cudaMemcpyAsync(dRandoms_.get(), hRandoms_.get(), sizeof(uint64_t) * (size_t)n, cudaMemcpyHostToDevice, stream_));
+  dRunLength_.ensure((size_t)(n * Q_), stream_); dQuestions_.ensure(n, stream_); hQuestions_.ensure(n);
+  const size_t par = (size_t)(p2pOps_++ & 1);
+  const P2PFlags flags = p2pFlags();
+  double *priority = nullptr;
+  if (IsTargetSharded()) {
+    PeerBufs outW, inW, outHVL, inHVL;
+    outW.n = inW.n = outHVL.n = inHVL.n = p2pRanks_;
+    for (int r = 0; r < p2pRanks_; r++) {
+      outW.p[r] = (double *)(p2pPeer_[r] + p2pOffW_ + (par * p2pRanks_ + p2pRank_) * p2pSzW_);
+      inW.p[r] = (double *)(p2pInbox_ + p2pOffW_ + (par * p2pRanks_ + r) * p2pSzW_);
+      outHVL.p[r] = (double *)(p2pPeer_[r] + p2pOffHVL_ + (par * p2pRanks_ + p2pRank_) * p2pSzHVL_);
+      inHVL.p[r] = (double *)(p2pInbox_ + p2pOffHVL_ + (par * p2pRanks_ + r) * p2pSzHVL_);
+    }
+    launch_eval_tshard_w(kb(), pool(), tFirst_, n, dIds_.get(), outW, evalCfg_, stream_);   // partial W_k -> every inbox
+    launch_p2p_barrier(flags, ++p2pEpoch_, kP2PTimeoutNs, stream_);
+    launch_eval_tshard_hvl(kb(), pool(), tFirst_, n, dIds_.get(), inW, outHVL, evalCfg_, stream_);
+    launch_p2p_barrier(flags, ++p2pEpoch_, kP2PTimeoutNs, stream_);
+    dShardPriority_.ensure((size_t)(n * Q_), stream_);
+    priority = dShardPriority_.get();
+    EvalDetail det{nullptr, nullptr, nullptr, nullptr};
+    launch_tshard_priority(kb(), pool(), n, dIds_.get(), inW, inHVL, priority, det, stream_);
+    shardWCount_ = 0; shardHVLCount_ = 0;
+    p2pLastPriority_ = nullptr;
+  } else {
+    priority = (double *)(p2pInbox_ + p2pOffPri_ + par * p2pSzPri_);
+    EvalConfig cfg = evalCfg_;
+    for (int r = 0; r < p2pRanks_; r++)
+      if (r != p2pRank_) cfg.mirror.p[cfg.mirror.n++] = (double *)(p2pPeer_[r] + p2pOffPri_ + par * p2pSzPri_);
+    EvalDetail det{nullptr, nullptr, nullptr, nullptr};
+    launch_eval_questions(kb(), pool(), n, dIds_.get(), priority, det, cfg, stream_);   // own columns -> every inbox
+    launch_p2p_barrier(flags, ++p2pEpoch_, kP2PTimeoutNs, stream_);
+    p2pLastPriority_ = priority;
+  }
+  shardPriorityCount_ = n * Q_;
+  launch_select_question(kbQuiz(), pool(), n, dIds_.get(), priority, dRandoms_.get(), W_, dRunLength_.get(), nullptr,
+                         dQuestions_.get(), 1, stream_);
+  PQA_CU(cudaMemcpyAsync(hQuestions_.get(), dQuestions_.get(), sizeof(int64_t) * (size_t)n, cudaMemcpyDeviceToHost, stream_));
+  p2pPending_ = true;
+  return nullptr;
+  PQA_CATCH_RETURN_ERR
+}
+
+PqaError *Engine::P2PNextQuestionEnd(int64_t n, const int64_t *pQuizIds, int64_t *pQuestions, void **ppErrors) {
+  if (n <= 0) return ErrNegativeCount(n, PQA_FILE_LINE "|n| must be positive.");
+  if (!pQuizIds || !pQuestions) return MakeError(ErrCode::NullArgument, PQA_FILE_LINE "pQuizIds/pQuestions");
+  std::lock_guard<std::mutex> lk(mu_);
+  if (!p2pPending_) return MakeError(ErrCode::NotInitialized, PQA_FILE_LINE "P2PNextQuestionEnd without a Begin");
+  p2pPending_ = false;
+  if (PqaError *e = P2PCheckError()) return e;
+  PqaError *firstErr = nullptr;
+  uint64_t nAsked = 0;
+  for (int64_t x = 0; x < n; x++) {
+    const int64_t qst = hQuestions_.get()[x];
+    pQuestions[x] = qst;
+    if (ppErrors) ppErrors[x] = nullptr;
+    if (qst < 0) {
+      PqaError *e = MakeError(ErrCode::QuestionsExhausted, PQA_FILE_LINE "Found no unasked question that is not in a gap.");
+      if (ppErrors) ppErrors[x] = e;
+      else if (!firstErr) firstErr = e;
+      else delete e;
+      continue;
+    }
+    quizzes_[pQuizIds[x]].activeQuestion = qst;
+    nAsked++;
+  }
+  nQuestionsAsked_.fetch_add(nAsked, std::memory_order_relaxed);
+  return firstErr;
+}
+
+PqaError *Engine::P2PRecordAnswerBegin(int64_t n, const int64_t *pQuizIds, const int64_t *pAnswers) {
+  if (n <= 0) return ErrNegativeCount(n, PQA_FILE_LINE "|n| must be positive.");
+  if (!pQuizIds || !pAnswers) return MakeError(ErrCode::NullArgument, PQA_FILE_LINE "pQuizIds/pAnswers");
+  std::lock_guard<std::mutex> lk(mu_);
+  if (!p2pConnected_) return MakeError(ErrCode::NotInitialized, PQA_FILE_LINE "P2PInit / P2PConnect first");
+  if (p2pPending_) return MakeError(ErrCode::WrongMode, PQA_FILE_LINE "a P2P operation is pending: call its End first");
+  if (n > p2pCap_) return ErrIndexOutOfRange(n, 1, p2pCap_, PQA_FILE_LINE "more quizzes than the inbox was sized for");
+  PQA_TRY
+  if (PqaError *e = ValidateRecordAnswer(n, pQuizIds, pAnswers)) return e;
+  UploadIds(n, pQuizIds);
+  hAnswers_.ensure(n); dAnswers_.ensure(n, stream_);
+  std::memcpy(hAnswers_.get(), pAnswers, sizeof(int64_t) * (size_t)n);
+  PQA_CU(cudaMemcpyAsync(dAnswers_.get(), hAnswers_.get(), sizeof(int64_t) * (size_t)n, cudaMemcpyHostToDevice, stream_));
+  const int looseW = std::max(1, W_ - 1);
+  const size_t par = (size_t)(p2pOps_++ & 1);
+  const P2PFlags flags = p2pFlags();
+  double *rows = (double *)(p2pInbox_ + p2pOffRows_ + par * p2pSzRows_);
+  PeerBufs out;
+  if (IsTargetSharded()) {
+    out.n = p2pRanks_;
+    for (int r = 0; r < p2pRanks_; r++) out.p[r] = (double *)(p2pPeer_[r] + p2pOffRows_ + par * p2pSzRows_);
+    launch_tshard_record_answer_partial(kb(), pool(), tFirst_, n, dIds_.get(), dAnswers_.get(), out, stream_);
+    launch_p2p_barrier(flags, ++p2pEpoch_, kP2PTimeoutNs, stream_);
+    launch_tshard_record_answer_finish(kbQuiz(), pool(), n, dIds_.get(), rows, looseW, stream_);
+  } else {
+    hQuestions_.ensure(n); dQuestions_.ensure(n, stream_);
+    for (int64_t x = 0; x < n; x++) hQuestions_.get()[x] = quizzes_[pQuizIds[x]].activeQuestion;
+    PQA_CU(cudaMemcpyAsync(dQuestions_.get(), hQuestions_.get(), sizeof(int64_t) * (size_t)n, cudaMemcpyHostToDevice, stream_));
+    launch_record_answer(kb(), pool(), n, dIds_.get(), dAnswers_.get(), looseW, stream_);   // owner: update; others: bookkeeping
+    for (int r = 0; r < p2pRanks_; r++)
+      if (r != p2pRank_) out.p[out.n++] = (double *)(p2pPeer_[r] + p2pOffRows_ + par * p2pSzRows_);
+    launch_p2p_push_prior_rows(kb(), pool(), n, dIds_.get(), dQuestions_.get(), out, stream_);
+    launch_p2p_barrier(flags, ++p2pEpoch_, kP2PTimeoutNs, stream_);
+    launch_p2p_pull_prior_rows(kb(), pool(), n, dIds_.get(), dQuestions_.get(), rows, stream_);
+  }
+  for (int64_t x = 0; x < n; x++) {
+    HostQuiz &q = quizzes_[pQuizIds[x]];
+    q.answers.push_back(CiAnsweredQuestion{q.activeQuestion, pAnswers[x]});
+    q.activeQuestion = -1;
+  }
+  p2pPending_ = true;
+  return nullptr;
+  PQA_CATCH_RETURN_ERR
+}
+
+PqaError *Engine::P2PRecordAnswerEnd() {
+  std::lock_guard<std::mutex> lk(mu_);
+  if (!p2pPending_) return MakeError(ErrCode::NotInitialized, PQA_FILE_LINE "P2PRecordAnswerEnd without a Begin");
+  p2pPending_ = false;
+  return P2PCheckError();
 }
 
 PqaError *Engine::FillBinarySearchKB(double rounds) {

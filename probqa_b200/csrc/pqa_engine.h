@@ -129,6 +129,15 @@ class Engine {
   int64_t targetShardCount() const { return tLocal_; }
   bool IsTargetSharded() const { return tLocal_ != T_; }
   bool IsSharded() const { return qLocal_ != Q_ || tLocal_ != T_; }
+  // --- shard exchange over peer memory (PqaB200Ext.h "P2P" entry points); works for question and target shards ---
+  PqaError *P2PInit(int32_t rank, int32_t nRanks, int64_t maxQuizzes, void **ppBase, int64_t *pBytes);
+  PqaError *P2PExportHandle(uint8_t *pHandle64);
+  PqaError *P2POpenHandle(const uint8_t *pHandle64, void **ppPeerBase);
+  PqaError *P2PConnect(void *const *pBases);
+  PqaError *P2PNextQuestionBegin(int64_t n, const int64_t *pQuizIds, const uint64_t *pRandoms);
+  PqaError *P2PNextQuestionEnd(int64_t n, const int64_t *pQuizIds, int64_t *pQuestions, void **ppErrors);
+  PqaError *P2PRecordAnswerBegin(int64_t n, const int64_t *pQuizIds, const int64_t *pAnswers);
+  PqaError *P2PRecordAnswerEnd();
   // closed-form synthetic KB of SURVEY.md 8d written on the device (this engine's shard of it)
   PqaError *FillBinarySearchKB(double rounds);
 
@@ -175,6 +184,19 @@ class Engine {
   int64_t tFirst_ = 0, tLocal_ = 0, TpL_ = 0;   // target shard (0, T_ unless target-sharded); TpL_ = row stride of sA/mD
   int64_t shardPriorityCount_ = 0, shardPriorsCount_ = 0, shardWCount_ = 0, shardHVLCount_ = 0;
   DevBuf<double> dShardPriority_, dShardPriors_, dShardW_, dShardHVL_;
+  // peer-memory exchange state: own inbox, every shard's inbox base, lockstep counters (identical on all shards)
+  int p2pRank_ = -1, p2pRanks_ = 0;
+  int64_t p2pCap_ = 0;
+  char *p2pInbox_ = nullptr;
+  size_t p2pBytes_ = 0, p2pOffW_ = 0, p2pOffHVL_ = 0, p2pOffRows_ = 0, p2pOffPri_ = 0;
+  size_t p2pSzW_ = 0, p2pSzHVL_ = 0, p2pSzRows_ = 0, p2pSzPri_ = 0;   // bytes of one slot / one parity copy
+  char *p2pPeer_[kMaxPeers] = {};
+  bool p2pOpened_[kMaxPeers] = {};
+  bool p2pConnected_ = false, p2pPending_ = false;
+  uint64_t p2pEpoch_ = 0, p2pOps_ = 0;
+  double *p2pLastPriority_ = nullptr;
+  P2PFlags p2pFlags() const;
+  PqaError *P2PCheckError();
   double initAmount_ = 0;
   uint32_t precMantissa_ = 0; uint16_t precExponent_ = 0;   // kept only to write them back into a KB file header
   cudaStream_t stream_ = nullptr;

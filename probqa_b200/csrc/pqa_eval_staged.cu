@@ -48,7 +48,13 @@ struct StagedParams {
   int64_t Jc;             // targets per shared-memory chunk (multiple of 4)
   int64_t nChunks;
   int64_t quizzesPerCta;  // == quizzes per pass of one CTA when nChunks > 1
+  PeerBufs mirror;        // EvalConfig::mirror
 };
+
+__device__ __forceinline__ void store_priority(const StagedParams &P, int64_t o, double v) {
+  P.priority[o] = v;
+  for (int r = 0; r < P.mirror.n; r++) P.mirror.p[r][o] = v;   // other shards' inboxes (peer memory)
+}
 
 template <int KL> struct VecD { double v[KL]; };
 
@@ -248,7 +254,7 @@ __device__ __forceinline__ void write_priority(const StagedParams &P, int64_t i,
   const double n1 = (double)(P.kb.nValidTargets + 1);
   const double vComp = 1.0 / (cLnMaxV - lnV + cLnMaxV / (n1 * n1));     // :30-33
   const double lack = -L;                                               // :201
-  P.priority[o] = lack * pow(vComp, 9.0) * pow(nExp, -2.0);             // :207
+  store_priority(P, o, lack * pow(vComp, 9.0) * pow(nExp, -2.0));       // :207
   if (P.det.lack) P.det.lack[o] = lack;
 }
 
@@ -293,7 +299,7 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_eval_staged(const StagedParam
   const double qnan = __longlong_as_double(0x7FF8000000000000ll);
 
   if (bit32(P.kb.qgaps, i)) {          // CEEvalQsSubtaskConsider.cpp:54-58
-    for (int64_t b = tileFirst + threadIdx.x; b < tileLimit; b += THREADS) P.priority[b * Q + i] = qnan;
+    for (int64_t b = tileFirst + threadIdx.x; b < tileLimit; b += THREADS) store_priority(P, b * Q + i, qnan);
     return;
   }
   if (threadIdx.x == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
@@ -309,7 +315,7 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_eval_staged(const StagedParam
       bool live = b < tileLimit;
       const int64_t slot = P.slots[live ? b : tileLimit - 1];
       if (live && bit64(P.qp.asked + slot * P.qp.askedWords, i)) {
-        if (l0 == 0) P.priority[b * Q + i] = qnan;
+        if (l0 == 0) store_priority(P, b * Q + i, qnan);
         live = false;
       }
       if (!live) continue;             // all threads of this quiz leave together
@@ -337,7 +343,7 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_eval_staged(const StagedParam
     bool live = b < tileLimit;
     const int64_t slot = P.slots[live ? b : tileLimit - 1];
     if (live && bit64(P.qp.asked + slot * P.qp.askedWords, i)) {
-      if (l0 == 0) P.priority[b * Q + i] = qnan;
+      if (l0 == 0) store_priority(P, b * Q + i, qnan);
       live = false;
     }
     const double *pr = P.qp.priors + slot * Tp, *lpr = P.qp.logPriors + slot * Tp;
@@ -397,7 +403,7 @@ __global__ void __launch_bounds__(kSmallWarps * 32, 4) k_eval_small(const Staged
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const double qnan = __longlong_as_double(0x7FF8000000000000ll);
   if (bit32(P.kb.qgaps, i)) {
-    for (int64_t b = tileFirst + threadIdx.x; b < tileLimit; b += THREADS) P.priority[b * Q + i] = qnan;
+    for (int64_t b = tileFirst + threadIdx.x; b < tileLimit; b += THREADS) store_priority(P, b * Q + i, qnan);
     return;
   }
   if (threadIdx.x == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
@@ -414,7 +420,7 @@ __global__ void __launch_bounds__(kSmallWarps * 32, 4) k_eval_small(const Staged
       if (b < tileLimit) {
         slot = P.slots[b];
         if (bit64(P.qp.asked + slot * P.qp.askedWords, i)) {
-          if (lane == 0) P.priority[b * Q + i] = qnan;
+          if (lane == 0) store_priority(P, b * Q + i, qnan);
           slot = -1;
         }
       }
@@ -597,7 +603,7 @@ __global__ void __launch_bounds__(128) k_tshard_priority(const TShardEpiloguePar
   for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < total; o += (int64_t)gridDim.x * blockDim.x) {
     const int64_t b = o / Q, i = o - b * Q;
     const int64_t slot = P.slots[b];
-    if (bit32(P.kb.qgaps, i) || bit64(P.qp.asked + slot * P.qp.askedWords, i)) { P.priority[o] = qnan; continue; }
+    if (bit32(P.kb.qgaps, i) || bit64(P.qp.asked + slot * P.qp.askedWords, i)) { store_priority(P, o, qnan); continue; }
     double W[K], H[K], V[K], L;
 #pragma unroll
     for (int k = 0; k < K; k++) { W[k] = EP.inW.p[0][o * K + k]; H[k] = EP.inHVL.p[0][o * NV + k]; V[k] = EP.inHVL.p[0][o * NV + K + k]; }
@@ -752,7 +758,7 @@ void launch_eval_staged(const DeviceKB &kb, const QuizPool &qp, int64_t n, const
     return;
   }
   StagedParams P;
-  P.kb = kb; P.qp = qp; P.n = n; P.slots = dSlots; P.priority = dPriority; P.det = det;
+  P.kb = kb; P.qp = qp; P.n = n; P.slots = dSlots; P.priority = dPriority; P.det = det; P.mirror = cfg.mirror;
   const int64_t bytesPerTarget = (2 * kb.K + 1) * (int64_t)sizeof(double);
   const int64_t budget = 100 * 1024;  // two CTAs per SM
   int64_t Jc = cfg.chunkTargets > 0 ? ((cfg.chunkTargets + 3) & ~3ll) : kb.Tp;
@@ -771,6 +777,23 @@ void launch_eval_staged(const DeviceKB &kb, const QuizPool &qp, int64_t n, const
     case 7: launch_k<7>(P, cfg, smem, st); break;
     default: launch_k<8>(P, cfg, smem, st); break;
   }
+}
+
+template <int K> static void preload_staged_k() {
+  cudaFuncAttributes a;
+  cudaFuncGetAttributes(&a, k_eval_staged<K, 1, 8>);
+  cudaFuncGetAttributes(&a, k_eval_staged<K, 2, 8>);
+  cudaFuncGetAttributes(&a, k_eval_staged<K, 4, 4>);
+  cudaFuncGetAttributes(&a, k_eval_small<K>);
+  cudaFuncGetAttributes(&a, k_eval_tshard<K, 1, 8, 1>);
+  cudaFuncGetAttributes(&a, k_eval_tshard<K, 2, 8, 1>);
+  cudaFuncGetAttributes(&a, k_eval_tshard<K, 1, 8, 2>);
+  cudaFuncGetAttributes(&a, k_eval_tshard<K, 2, 8, 2>);
+  cudaFuncGetAttributes(&a, k_tshard_priority<K>);
+}
+void preload_staged_kernels(int K) {
+  if (K < 2 || K > 8) return;
+  PQA_K_SWITCH(K, (preload_staged_k<KK>()))
 }
 
 } // namespace pqa

@@ -357,6 +357,74 @@ void launch_scatter_prior_rows(const QuizPool &qp, int64_t n, const int64_t *dSl
   count_launch();
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Exchange over peer memory (pqa_kernels.cuh). The stores of the kernels that ran before this one on the stream are
+// complete at the kernel boundary; the system fence + release store order them before the flag for the peer GPUs.
+__device__ __forceinline__ uint64_t globaltimer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__global__ void k_p2p_barrier(P2PFlags f, uint64_t epoch, uint64_t timeoutNs) {
+  const int r = threadIdx.x;
+  if (r >= f.nRanks) return;
+  __threadfence_system();
+  uint64_t *dst = f.flags[r] + f.rank;
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(dst), "l"(epoch) : "memory");
+  const uint64_t *mine = f.flags[f.rank] + r;
+  const uint64_t t0 = globaltimer_ns();
+  for (;;) {
+    uint64_t seen;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(mine) : "memory");
+    if (seen >= epoch) break;
+    if (globaltimer_ns() - t0 > timeoutNs) { *f.errFlag = epoch; break; }
+    __nanosleep(200);
+  }
+  __threadfence_system();
+}
+void launch_p2p_barrier(const P2PFlags &f, uint64_t epoch, uint64_t timeoutNs, cudaStream_t st) {
+  k_p2p_barrier<<<1, 32, 0, st>>>(f, epoch, timeoutNs);
+  count_launch();
+}
+
+__global__ void k_p2p_push_prior_rows(DeviceKB kb, QuizPool qp, const int64_t *__restrict__ slots,
+                                      const int64_t *__restrict__ questions, PeerBufs out) {
+  const int64_t b = blockIdx.y, q = questions[b];
+  if (q < kb.qFirst || q >= kb.qFirst + kb.qCount) return;        // another shard answers for this quiz
+  const double *prior = qp.priors + slots[b] * qp.Tp;
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < qp.Tp; j += (int64_t)gridDim.x * blockDim.x) {
+    const double v = prior[j];
+    for (int r = 0; r < out.n; r++) out.p[r][b * qp.Tp + j] = v;
+  }
+}
+void launch_p2p_push_prior_rows(const DeviceKB &kb, const QuizPool &qp, int64_t n, const int64_t *dSlots,
+                                const int64_t *dQuestions, const PeerBufs &out, cudaStream_t st) {
+  if (n <= 0 || out.n <= 0) return;
+  int64_t gx = (qp.Tp + 255) / 256;
+  if (gx > 64) gx = 64;
+  k_p2p_push_prior_rows<<<dim3((unsigned)gx, (unsigned)n), 256, 0, st>>>(kb, qp, dSlots, dQuestions, out);
+  count_launch();
+}
+__global__ void k_p2p_pull_prior_rows(DeviceKB kb, QuizPool qp, const int64_t *__restrict__ slots,
+                                      const int64_t *__restrict__ questions, const double *__restrict__ rows) {
+  const int64_t b = blockIdx.y, q = questions[b];
+  if (q >= kb.qFirst && q < kb.qFirst + kb.qCount) return;        // own row: already in place
+  double *prior = qp.priors + slots[b] * qp.Tp, *lprior = qp.logPriors + slots[b] * qp.Tp;
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < qp.Tp; j += (int64_t)gridDim.x * blockDim.x) {
+    const double v = rows[b * qp.Tp + j];
+    prior[j] = v;
+    lprior[j] = log2(v);
+  }
+}
+void launch_p2p_pull_prior_rows(const DeviceKB &kb, const QuizPool &qp, int64_t n, const int64_t *dSlots,
+                                const int64_t *dQuestions, const double *dRows, cudaStream_t st) {
+  if (n <= 0) return;
+  int64_t gx = (qp.Tp + 255) / 256;
+  if (gx > 64) gx = 64;
+  k_p2p_pull_prior_rows<<<dim3((unsigned)gx, (unsigned)n), 256, 0, st>>>(kb, qp, dSlots, dQuestions, dRows);
+  count_launch();
+}
+
 __global__ void k_set_active(QuizPool qp, int64_t n, const int64_t *__restrict__ slots,
                              const int64_t *__restrict__ questions) {
   const int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -795,6 +863,28 @@ void launch_add_vb(const DeviceKB &kb, const int64_t *dTargets, const double *dA
   if (nGroups <= 0) return;
   k_add_vb<<<(unsigned)((nGroups + 127) / 128), 128, 0, st>>>(kb, dTargets, dAmounts, dGroupStart, nGroups);
   count_launch();
+}
+
+// CUDA loads a kernel's code lazily at its first launch, and that load can wait for running kernels. A barrier kernel
+// that is spinning for another engine of the same process must never be what such a load waits for, so the engines of a
+// peer-memory exchange load every kernel of the exchanged call sequences up front (cudaFuncGetAttributes loads).
+void preload_staged_kernels(int K);
+void preload_exchange_kernels(int K) {
+  cudaFuncAttributes a;
+  cudaFuncGetAttributes(&a, k_update_priors<0>);
+  cudaFuncGetAttributes(&a, k_update_priors<1>);
+  cudaFuncGetAttributes(&a, k_tshard_ra_partial);
+  cudaFuncGetAttributes(&a, k_tshard_ra_finish);
+  cudaFuncGetAttributes(&a, k_p2p_barrier);
+  cudaFuncGetAttributes(&a, k_p2p_push_prior_rows);
+  cudaFuncGetAttributes(&a, k_p2p_pull_prior_rows);
+  cudaFuncGetAttributes(&a, k_select_question);
+  cudaFuncGetAttributes(&a, k_set_active);
+  cudaFuncGetAttributes(&a, k_list_top_targets);
+  cudaFuncGetAttributes(&a, k_gather_prior_rows);
+  cudaFuncGetAttributes(&a, k_scatter_prior_rows);
+  preload_staged_kernels(K);
+  (void)cudaGetLastError();
 }
 
 } // namespace pqa

@@ -35,6 +35,15 @@ struct QuizPool {
   int64_t Tp;
 };
 
+constexpr int kMaxPeers = 8;
+struct PeerBufs {           // where a result goes / comes from when several devices cooperate
+  int n = 0;                // 1 = this device's own buffer only (the caller sums across shards);
+                            // N = one buffer per shard: as output, p[r] is this shard's slot in shard r's inbox (peer
+                            //     memory over NVLink); as input, p[r] is shard r's slot in this shard's inbox, summed in
+                            //     shard order
+  double *p[kMaxPeers] = {};
+};
+
 struct EvalDetail {        // optional per-answer outputs of the question evaluation (may all be nullptr)
   double *W, *H, *V;       // [n][Q][K]
   double *lack;            // [n][Q]
@@ -72,6 +81,10 @@ struct EvalConfig {
   int64_t chunkTargets = 0;
   int64_t quizzesPerCta = 0;   // 0 = auto
   int kahanLanesPerThread = 0; // staged kernel: 4 = one thread per quiz, 1 = four threads per quiz, 0 = auto by batch
+  // question-sharded engines exchanging over peer memory: every priority (and the NaN of an asked question) of this
+  // device's questions is also stored at the same [b*Q + i] position of these buffers (the other shards' inboxes), from
+  // the evaluation kernel's own epilogue. Staged kernels only.
+  PeerBufs mirror;
 };
 void launch_eval_questions(const DeviceKB &kb, const QuizPool &qp, int64_t n, const int64_t *dSlots,
                            double *dPriority, const EvalDetail &det, const EvalConfig &cfg, cudaStream_t st);
@@ -113,13 +126,6 @@ void launch_add_vb(const DeviceKB &kb, const int64_t *dTargets, const double *dA
 //   -------  sum over shards -------
 //   priority epilogue (CEEvalQsSubtaskConsider.cpp:134-207) on every shard, identical bits everywhere.
 // W_k is needed before phase 2 because log2(lik/W_k) sits in the denominator of the lack term.
-constexpr int kMaxPeers = 8;
-struct PeerBufs {           // where a partial result goes / comes from
-  int n;                    // 1 = this device's own buffer only (the caller sums across shards);
-                            // N = one buffer per shard: out[r] is this shard's slot in shard r's inbox (peer memory),
-                            //     in[r] is shard r's slot in this shard's inbox, summed in shard order
-  double *p[kMaxPeers];
-};
 // phase 1: outW.p[*][(b*Q + i)*K + k]
 void launch_eval_tshard_w(const DeviceKB &kbLocal, const QuizPool &qp, int64_t tFirst, int64_t n, const int64_t *dSlots,
                           const PeerBufs &outW, const EvalConfig &cfg, cudaStream_t st);
@@ -143,6 +149,27 @@ void launch_tshard_record_answer_finish(const DeviceKB &kbFull, const QuizPool &
 // this device's shard: sA = (init + rounds*[k == ans(i,j)])^2, mD = sum_k sA, vB = init + rounds.
 void launch_fill_binary_search_kb(const DeviceKB &kbLocal, int64_t tFirst, int64_t Tglobal, double init, double rounds,
                                   cudaStream_t st);
+
+// ---------------------------------------------------------------------------------------------------------
+// Exchange between shard engines over peer memory (NVLink P2P stores / same-device pointers), no host round trip.
+// Every engine owns an "inbox" allocation whose base pointers are known to all engines (cudaIpc handles between
+// processes). A kernel's epilogue stores what the other shards need straight into their inboxes; the barrier kernel
+// below then makes those stores visible: thread r publishes `epoch` into shard r's flag word for this rank
+// (st.release.sys after a system fence) and spins until shard r's word in the own inbox reaches `epoch`
+// (ld.acquire.sys). Gives up after timeoutNs and raises *errFlag (the host turns it into an error) instead of hanging.
+struct P2PFlags {
+  int rank, nRanks;
+  uint64_t *flags[kMaxPeers];   // flags[r] = shard r's flag array (kMaxPeers words, indexed by the signalling rank)
+  uint64_t *errFlag;            // own inbox
+};
+void preload_exchange_kernels(int K);   // loads every kernel of the exchanged call sequences now (see pqa_kernels.cu)
+void launch_p2p_barrier(const P2PFlags &f, uint64_t epoch, uint64_t timeoutNs, cudaStream_t st);
+// question-sharded RecordAnswer: rows of quizzes whose answered question (dQuestions[b]) this device owns go to every
+// peer's inbox rows [b*Tp ..]; after the barrier the other quizzes' rows come out of the own inbox into the pool.
+void launch_p2p_push_prior_rows(const DeviceKB &kb, const QuizPool &qp, int64_t n, const int64_t *dSlots,
+                                const int64_t *dQuestions, const PeerBufs &out, cudaStream_t st);
+void launch_p2p_pull_prior_rows(const DeviceKB &kb, const QuizPool &qp, int64_t n, const int64_t *dSlots,
+                                const int64_t *dQuestions, const double *dRows, cudaStream_t st);
 
 void launch_gather_prior_rows(const QuizPool &qp, int64_t n, const int64_t *dSlots, double *dBuf, cudaStream_t st);
 void launch_scatter_prior_rows(const QuizPool &qp, int64_t n, const int64_t *dSlots, const double *dBuf, cudaStream_t st);

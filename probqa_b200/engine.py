@@ -130,6 +130,14 @@ SIGNATURES = {
     "PqaB200_TShardPriority": (_vp, [_vp, _i64, _pi64]),
     "PqaB200_GetTargetShard": (_vp, [_vp, _pi64, _pi64]),
     "PqaB200_FillBinarySearchKB": (_vp, [_vp, C.c_double]),
+    "PqaB200_P2PInit": (_vp, [_vp, C.c_int32, C.c_int32, _i64, _pvp, _pi64]),
+    "PqaB200_P2PExportHandle": (_vp, [_vp, C.c_char_p]),
+    "PqaB200_P2POpenHandle": (_vp, [_vp, C.c_char_p, _pvp]),
+    "PqaB200_P2PConnect": (_vp, [_vp, _pvp]),
+    "PqaB200_P2PNextQuestionBegin": (_vp, [_vp, _i64, _pi64, _pu64]),
+    "PqaB200_P2PNextQuestionEnd": (_vp, [_vp, _i64, _pi64, _pi64, _pvp]),
+    "PqaB200_P2PRecordAnswerBegin": (_vp, [_vp, _i64, _pi64, _pi64]),
+    "PqaB200_P2PRecordAnswerEnd": (_vp, [_vp]),
     "PqaB200_ResidentBind": (_vp, [_vp, _i64, _pi64, _pu64]),
     "PqaB200_ResidentStep": (_vp, [_vp]),
     "PqaB200_ResidentFetch": (_vp, [_vp, _pi64]),
@@ -531,6 +539,45 @@ class PqaEngine:
     def fill_binary_search_kb(self, rounds: float = 3.0):
         """Device-side fill of this engine's shard with synth.binary_search_kb(Q, K, T, init_amount, rounds)."""
         _raise_or_return(self._lib.PqaB200_FillBinarySearchKB(self.c_engine, float(rounds)))
+
+    # ---------------------------------------------------------------- shard exchange over peer memory (PqaB200Ext.h)
+    def p2p_init(self, rank: int, n_ranks: int, max_quizzes: int) -> Tuple[int, int]:
+        """Allocates this shard's inbox; returns (device pointer, bytes)."""
+        base, nbytes = C.c_void_p(), C.c_int64()
+        _raise_or_return(self._lib.PqaB200_P2PInit(self.c_engine, rank, n_ranks, max_quizzes, C.byref(base), C.byref(nbytes)))
+        return base.value, nbytes.value
+
+    def p2p_export_handle(self) -> bytes:
+        buf = C.create_string_buffer(64)
+        _raise_or_return(self._lib.PqaB200_P2PExportHandle(self.c_engine, buf))
+        return buf.raw
+
+    def p2p_open_handle(self, handle: bytes) -> int:
+        base = C.c_void_p()
+        _raise_or_return(self._lib.PqaB200_P2POpenHandle(self.c_engine, C.create_string_buffer(handle, 64), C.byref(base)))
+        return base.value
+
+    def p2p_connect(self, bases):
+        arr = (C.c_void_p * len(bases))(*[C.c_void_p(b) for b in bases])
+        _raise_or_return(self._lib.PqaB200_P2PConnect(self.c_engine, arr))
+
+    def p2p_next_question_begin(self, quiz_ids, randoms):
+        ids = _i64arr(quiz_ids)
+        rnd = np.ascontiguousarray(randoms, dtype=np.uint64)
+        _raise_or_return(self._lib.PqaB200_P2PNextQuestionBegin(self.c_engine, ids.size, _p(ids, _pi64), _p(rnd, _pu64)))
+
+    def p2p_next_question_end(self, quiz_ids) -> np.ndarray:
+        ids = _i64arr(quiz_ids)
+        out = np.empty(ids.size, dtype=np.int64)
+        _raise_or_return(self._lib.PqaB200_P2PNextQuestionEnd(self.c_engine, ids.size, _p(ids, _pi64), _p(out, _pi64), None))
+        return out
+
+    def p2p_record_answer_begin(self, quiz_ids, answers):
+        ids, ans = _i64arr(quiz_ids), _i64arr(answers)
+        _raise_or_return(self._lib.PqaB200_P2PRecordAnswerBegin(self.c_engine, ids.size, _p(ids, _pi64), _p(ans, _pi64)))
+
+    def p2p_record_answer_end(self):
+        _raise_or_return(self._lib.PqaB200_P2PRecordAnswerEnd(self.c_engine))
 
     def resident_bind(self, quiz_ids, randoms=None):
         ids = _i64arr(quiz_ids)

@@ -35,9 +35,11 @@ def target_shard_ranges(n_targets: int, n_shards: int):
     """[(first, count)] over targets in units of 4-target vectors (a target keeps its Kahan lane j % 4 inside a shard;
     only the last shard can end off a multiple of 4, where the global padding lanes are)."""
     out = []
+    if n_shards > (n_targets + 3) // 4:
+        raise ValueError("more target shards (%d) than 4-target vectors (%d)" % (n_shards, (n_targets + 3) // 4))
     for first_v, cnt_v in shard_ranges((n_targets + 3) // 4, n_shards):
         first = 4 * first_v
-        out.append((first, min(4 * cnt_v, n_targets - first)))
+        out.append((first, max(0, min(4 * cnt_v, n_targets - first))))
     return out
 
 
@@ -102,6 +104,40 @@ class QuestionShardedEngine:
         self.shards = list(shards)
         self.group = group
         self._rng = np.random.default_rng(seed)   # same seed on every rank => same draws on every shard
+        self._p2p = False
+
+    # ---- exchange over peer memory instead of the caller-side all-reduce (PqaB200Ext.h "P2P" entry points)
+    def enable_p2p(self, max_quizzes: int):
+        """Gives every shard engine an inbox and connects them: directly when all shards live in this process
+        (group=None), through cudaIpc handles all-gathered over the process group when there is one shard per process.
+        From then on next_question_batch / record_answer_batch run without any host-side exchange."""
+        engines = [s.engine for s in self.shards]
+        if self.group is None:
+            bases = [e.p2p_init(r, len(engines), max_quizzes)[0] for r, e in enumerate(engines)]
+            for e in engines:
+                e.p2p_connect(bases)
+        else:
+            import torch.distributed as dist
+            assert len(engines) == 1, "one shard per process under a process group"
+            rank, world = dist.get_rank(self.group), dist.get_world_size(self.group)
+            base, _ = engines[0].p2p_init(rank, world, max_quizzes)
+            handles = [None] * world
+            dist.all_gather_object(handles, engines[0].p2p_export_handle(), group=self.group)
+            bases = [base if r == rank else engines[0].p2p_open_handle(handles[r]) for r in range(world)]
+            engines[0].p2p_connect(bases)
+            dist.barrier(group=self.group)
+        self._p2p = True
+
+    def _p2p_next_question(self, quiz_ids, randoms):
+        for s in self.shards:
+            s.engine.p2p_next_question_begin(quiz_ids, randoms)
+        return self._same([s.engine.p2p_next_question_end(quiz_ids) for s in self.shards])
+
+    def _p2p_record_answer(self, quiz_ids, answers):
+        for s in self.shards:
+            s.engine.p2p_record_answer_begin(quiz_ids, answers)
+        for s in self.shards:
+            s.engine.p2p_record_answer_end()
 
     # ---- the exchange step
     def _all_reduce(self, tensors: List):
@@ -138,6 +174,8 @@ class QuestionShardedEngine:
         quiz_ids = np.ascontiguousarray(quiz_ids, dtype=np.int64)
         if randoms is None:
             randoms = self._rng.integers(0, 2 ** 64, size=quiz_ids.size, dtype=np.uint64)
+        if self._p2p:
+            return self._p2p_next_question(quiz_ids, randoms)
         self._all_reduce([s.eval(quiz_ids) for s in self.shards])
         return self._same([s.select(quiz_ids, randoms) for s in self.shards])
 
@@ -150,6 +188,8 @@ class QuestionShardedEngine:
 
     def record_answer_batch(self, quiz_ids, answers):
         quiz_ids = np.ascontiguousarray(quiz_ids, dtype=np.int64)
+        if self._p2p:
+            return self._p2p_record_answer(quiz_ids, answers)
         self._all_reduce([s.record_answer_begin(quiz_ids, answers) for s in self.shards])
         for s in self.shards:
             s.record_answer_end(quiz_ids)
@@ -255,6 +295,8 @@ class TargetShardedEngine(QuestionShardedEngine):
         quiz_ids = np.ascontiguousarray(quiz_ids, dtype=np.int64)
         if randoms is None:
             randoms = self._rng.integers(0, 2 ** 64, size=quiz_ids.size, dtype=np.uint64)
+        if self._p2p:
+            return self._p2p_next_question(quiz_ids, randoms)
         self._priorities(quiz_ids)
         return self._same([s.select(quiz_ids, randoms) for s in self.shards])
 

@@ -175,3 +175,67 @@ def test_device_filled_binary_search_kb_is_bit_identical(dims):
     e.fill_binary_search_kb(3)
     a, d, b = e.download_kb()
     assert np.array_equal(bits(a[f:f + c]), bits(want[0][f:f + c])) and np.array_equal(bits(d[f:f + c]), bits(want[1][f:f + c]))
+
+
+@pytest.mark.parametrize("axis,dims,n_shards,n", [("questions", (40, 5, 203), 2, 9), ("questions", (64, 5, 1000), 3, 40),
+                                                  ("targets", (40, 5, 203), 2, 9), ("targets", (30, 5, 1000), 4, 130)])
+def test_peer_memory_exchange_matches_caller_side_exchange(axis, dims, n_shards, n):
+    """The same sharded session twice: shards exchanging through the caller (sum of the Shard*/TShard* buffers) and
+    shards exchanging over peer memory from their kernels' epilogues with the device-side barrier (P2P entry points;
+    several engines of one process on one GPU, so "peer memory" is ordinary device memory here). Chosen questions,
+    priorities, posteriors and top-10 lists must agree bit for bit."""
+    from probqa_b200 import engine as pqa
+    Q, K, T = dims
+    W = 6
+    kb = synth.gamma_kb(Q, K, T, INIT)
+    fac = pqa.PqaEngineFactory()
+    edef = pqa.EngineDefinition(K, Q, T, init_amount=INIT)
+
+    def make():
+        shards = []
+        if axis == "questions":
+            for first, count in sharded.shard_ranges(Q, n_shards):
+                e = fac.create_b200_engine(edef, emulated_workers=W, rng_seed=5, question_shard_first=first, question_shard_count=count)
+                e.upload_kb(*kb)
+                shards.append(sharded.B200Shard(e))
+            return sharded.QuestionShardedEngine(shards)
+        for first, count in sharded.target_shard_ranges(T, n_shards):
+            e = fac.create_b200_engine(edef, emulated_workers=W, rng_seed=5, target_shard_first=first, target_shard_count=count)
+            e.upload_kb(*kb)
+            shards.append(sharded.B200TargetShard(e))
+        return sharded.TargetShardedEngine(shards)
+
+    host, p2p = make(), make()
+    p2p.enable_p2p(n)
+    ids = host.start_quiz_batch(n)
+    assert np.array_equal(ids, p2p.start_quiz_batch(n))
+    rng = np.random.default_rng(79)
+    for step in range(4):     # consecutive NextQuestion calls exercise both parities of the inbox
+        for rep in range(2):
+            randoms = rng.integers(0, 2 ** 64, size=n, dtype=np.uint64)
+            chosen = host.next_question_batch(ids, randoms)
+            assert np.array_equal(chosen, p2p.next_question_batch(ids, randoms))
+            want = host.shards[0]._view(0).cpu().numpy()
+            for s in p2p.shards:
+                got = s._view(0).cpu().numpy()[:want.size]
+                assert np.array_equal(np.isnan(got), np.isnan(want))
+                assert np.array_equal(bits(got[~np.isnan(got)]), bits(want[~np.isnan(want)]))
+        answers = [(int(c) * 7 + step) % K for c in chosen]
+        host.record_answer_batch(ids, answers)
+        p2p.record_answer_batch(ids, answers)
+        for s in p2p.shards:
+            for q in ids[:5]:
+                assert np.array_equal(bits(s.copy_quiz_priors(int(q))), bits(host.copy_quiz_priors(int(q))))
+        items, counts = p2p.list_top_targets_batch(ids, 10)
+        items_h, counts_h = host.list_top_targets_batch(ids, 10)
+        assert np.array_equal(counts, counts_h) and items.tobytes() == items_h.tobytes()
+    # a smaller batch than the inbox was sized for, and a call sequence error
+    sub = ids[:3]
+    randoms = rng.integers(0, 2 ** 64, size=3, dtype=np.uint64)
+    assert np.array_equal(host.next_question_batch(sub, randoms), p2p.next_question_batch(sub, randoms))
+    for s in p2p.shards:
+        s.engine.p2p_next_question_begin(sub, randoms)
+    with pytest.raises(pqa.PqaException):
+        p2p.shards[0].engine.p2p_next_question_begin(sub, randoms)      # its End is pending
+    for s in p2p.shards:
+        s.engine.p2p_next_question_end(sub)
