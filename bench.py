@@ -34,6 +34,10 @@ WORKLOADS = {
     "1000x5x1000_b256": dict(Q=1000, K=5, T=1000, B=256),
     # configs[2]: 10000Q x 5A x 10000T, batch = 1024 (4.8 GB KB)
     "10000x5x10000_b1024": dict(Q=10000, K=5, T=10000, B=1024),
+    # configs[3]: 10000Q x 5A x 100000T (48 GB KB), sharded across the GPUs of one box (--shard targets / questions)
+    "10000x5x100000_b64": dict(Q=10000, K=5, T=100000, B=64),
+    "10000x5x100000_b256": dict(Q=10000, K=5, T=100000, B=256),
+    "2000x5x20000_b64": dict(Q=2000, K=5, T=20000, B=64),
     # small smoke size
     "200x5x500_b32": dict(Q=200, K=5, T=500, B=32),
 }
@@ -215,20 +219,37 @@ def cpu_baseline(cfg, budget_s=12.0):
                 n_calls, "/".join(map(str, DEPTHS)), dt, cores)}
 
 
-def bench_question_sharded(args, cfg, pqa, dist, rank, world, local_rank, cores, barrier, max_over_ranks):
-    """Strong scaling of ONE batch over N GPUs: every rank holds Q/N questions of the KB and evaluates them for all B
-    quizzes; NCCL all-reduce (sum, zero-padded) of the [B][Q] priorities, then every rank selects. The whole step goes
-    through the public sharded API with host buffers, so value == e2e here."""
+def bench_sharded(args, cfg, pqa, dist, rank, world, local_rank, cores, barrier, max_over_ranks):
+    """Strong scaling of ONE batch over N GPUs. --shard questions: every rank holds Q/N question rows of the KB, the
+    ranks' priority columns are exchanged, every rank selects (bit-identical to one engine). --shard targets (BASELINE
+    config 4's axis): every rank holds T/N target columns, two-phase evaluation with an exchange of the W_k partials and
+    of the H/V/lack partials. --exchange nccl: torch.distributed all-reduce on the engine's buffers (host sync on both
+    sides); --exchange p2p: the kernels store into the peers' inboxes over NVLink and a device-side barrier orders the
+    phases. The whole step goes through the public sharded API with host buffers, so value == e2e here."""
     import torch
     from probqa_b200 import sharded
     Q, K, T, B = cfg["Q"], cfg["K"], cfg["T"], cfg["B"]
-    first, count = sharded.shard_ranges(Q, world)[rank]
-    eng = pqa.PqaEngineFactory().create_b200_engine(pqa.EngineDefinition(K, Q, T, init_amount=INIT), device=local_rank,
-                                                    emulated_workers=cores, rng_seed=1234, initial_quiz_capacity=B,
-                                                    question_shard_first=first, question_shard_count=count)
-    eng.upload_kb(*synth.binary_search_kb(Q, K, T, INIT, 3))
+    fac = pqa.PqaEngineFactory()
+    edef = pqa.EngineDefinition(K, Q, T, init_amount=INIT)
+    if args.shard == "questions":
+        first, count = sharded.shard_ranges(Q, world)[rank]
+        eng = fac.create_b200_engine(edef, device=local_rank, emulated_workers=cores, rng_seed=1234, initial_quiz_capacity=B,
+                                     question_shard_first=first, question_shard_count=count)
+        shard_bytes = count * (K + 1) * T * 8
+    else:
+        first, count = sharded.target_shard_ranges(T, world)[rank]
+        eng = fac.create_b200_engine(edef, device=local_rank, emulated_workers=cores, rng_seed=1234, initial_quiz_capacity=B,
+                                     target_shard_first=first, target_shard_count=count)
+        shard_bytes = Q * (K + 1) * count * 8
+    eng.fill_binary_search_kb(3)       # this rank's shard of synth.binary_search_kb, written on the device
     eng.set_eval_kernel(args.kernel, args.chunk_targets, args.quizzes_per_cta, args.lanes)
-    se = sharded.QuestionShardedEngine([sharded.B200Shard(eng)], group=dist.group.WORLD)
+    group = dist.group.WORLD if dist is not None else None
+    if args.shard == "questions":
+        se = sharded.QuestionShardedEngine([sharded.B200Shard(eng)], group=group)
+    else:
+        se = sharded.TargetShardedEngine([sharded.B200TargetShard(eng)], group=group)
+    if args.exchange == "p2p":
+        se.enable_p2p(B)
     states = quiz_states(cfg, 0, B)
     quizzes = se.start_quiz_batch(B)
     for s in range(max(DEPTHS)):
@@ -254,28 +275,39 @@ def bench_question_sharded(args, cfg, pqa, dist, rank, world, local_rank, cores,
     barrier()
     launches = eng.kernel_launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
+    assert np.all((chosen >= 0) & (chosen < Q))
     if rank != 0:
         return
     value = qevals_step * args.steps / dt
     peak, peak_src = measured_peak()
+    if args.shard == "questions":
+        par = "questions sharded over %d GPUs (Q/N rows of sA/mD each), exchange of the [B][Q] priority columns" % world
+        xbytes = int(B * Q * 8)
+    else:
+        par = ("targets sharded over %d GPUs (T/N columns of every sA/mD row each), two-phase evaluation: exchange of the "
+               "[B][Q][K] W_k partials, then of the [B][Q][2K+1] H/V/lack partials" % world)
+        xbytes = int(B * Q * (3 * K + 1) * 8)
+    per_gpu = qevals_step * (K + 1) * T * 8 / (dt / args.steps) / 1e9 / world
     line = {
         "metric": METRIC, "value": value, "unit": "questions/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": args.workload, "Q": Q, "A": K, "T": T, "batch_total": B, "quiz_depths": list(DEPTHS),
-                   "kb": "binary_search_kb(init=0.1, rounds=3)",
-                   "parallelism": "questions sharded over %d GPUs (Q/N rows of sA/mD each), NCCL all-reduce of [B][Q] priorities" % world,
-                   "l2": "inputs re-read every step; KB shard %.1f MB" % (count * (K + 1) * T * 8 / 1e6),
-                   "timing": "wall clock around the public sharded API (host sync inside every step), max over ranks"},
+                   "kb": "binary_search_kb(init=0.1, rounds=3), filled on the device", "parallelism": par,
+                   "exchange": ("NCCL all-reduce via torch.distributed (host sync on both sides)" if args.exchange == "nccl" else
+                                "peer-memory stores from the kernel epilogues + device-side barrier (no host round trip)"),
+                   "l2": "inputs re-read every step; KB shard %.1f MB per GPU" % (shard_bytes / 1e6),
+                   "timing": "wall clock around the public sharded API (result D2H + host sync inside every step), max over ranks",
+                   "chosen_checksum": int(np.sum(chosen * (np.arange(B) + 1)) % 1000000007)},
         "e2e": {"value": value, "unit": "questions/s", "h2d_bytes_per_step": int(B * 16), "d2h_bytes_per_step": int(B * 8),
-                "api": "sharded.QuestionShardedEngine.next_question_batch", "allreduce_bytes_per_step": int(B * Q * 8)},
+                "api": "sharded.%s.next_question_batch" % type(se).__name__, "exchanged_bytes_per_step_per_gpu": xbytes},
         "gpu_launches": int(launches), "clocks": clocks,
-        "roofline": {"bound": "hbm", "achieved": qevals_step * (K + 1) * T * 8 / (dt / args.steps) / 1e9 / world, "peak": peak,
-                     "unit": "GB/s", "frac": qevals_step * (K + 1) * T * 8 / (dt / args.steps) / 1e9 / world / peak, "traffic": None,
-                     "peak_source": peak_src, "note": "per GPU, whole step (evaluation + all-reduce + selection), algorithmic bytes"},
+        "roofline": {"bound": "hbm", "achieved": per_gpu, "peak": peak, "unit": "GB/s", "frac": per_gpu / peak, "traffic": None,
+                     "peak_source": peak_src, "note": "per GPU, whole step (evaluation + exchange + selection), algorithmic bytes"},
     }
     print(json.dumps(line), flush=True)
-    dist.destroy_process_group()
+    if dist is not None:
+        dist.destroy_process_group()
 
 
 def main():
@@ -290,7 +322,9 @@ def main():
     ap.add_argument("--chunk-targets", type=int, default=0)
     ap.add_argument("--lanes", type=int, default=0, help="Kahan lanes per thread of the staged kernel: 0 auto, 1, 4")
     ap.add_argument("--ref-quizzes", type=int, default=8, help="quizzes per step of the reference arm")
-    ap.add_argument("--shard", default="quizzes", choices=["quizzes", "questions"],
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+                    help="sharded modes: how the shards exchange partial results (peer memory from the kernels, or NCCL)")
+    ap.add_argument("--shard", default="quizzes", choices=["quizzes", "questions", "targets"],
                     help="N>1: quizzes = KB replicated, batch sharded, no collective; questions = each rank holds Q/N "
                          "questions, NCCL all-reduce of the per-question priorities (probqa_b200/sharded.py)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -339,11 +373,14 @@ def main():
     from probqa_b200 import engine as pqa
     Q, K, T, B = cfg["Q"], cfg["K"], cfg["T"], cfg["B"]
     cores = host_cores()
-    if args.shard == "questions" and world > 1:
-        return bench_question_sharded(args, cfg, pqa, dist, rank, world, local_rank, cores, barrier, max_over_ranks)
+    if args.shard in ("questions", "targets") and world > 1:
+        return bench_sharded(args, cfg, pqa, dist, rank, world, local_rank, cores, barrier, max_over_ranks)
     eng = pqa.PqaEngineFactory().create_b200_engine(pqa.EngineDefinition(K, Q, T, init_amount=INIT), device=local_rank,
                                                     emulated_workers=cores, rng_seed=1234 + rank, initial_quiz_capacity=B)
-    eng.upload_kb(*synth.binary_search_kb(Q, K, T, INIT, 3))
+    if Q * K * T * 8 > (1 << 30):
+        eng.fill_binary_search_kb(3)     # the same KB bit for bit (tests/test_gpu_sharded.py), written on the device
+    else:
+        eng.upload_kb(*synth.binary_search_kb(Q, K, T, INIT, 3))
     eng.set_eval_kernel(args.kernel, args.chunk_targets, args.quizzes_per_cta, args.lanes)
     # this rank's shard of the batch: quizzes rank*B .. rank*B+B-1 (weak scaling: B per GPU)
     states = quiz_states(cfg, rank * B, B)
@@ -405,7 +442,7 @@ def main():
 
     # ---------------------------------------------------------------- BASELINE configs[0]: one quiz through the reference's one-quiz-per-call entry point
     single = None
-    if rank == 0 and world == 1:
+    if rank == 0 and world == 1 and Q * K * T * 8 <= (1 << 30):
         n_calls = 200
         q1 = int(quizzes[0])
         for _ in range(20):

@@ -280,8 +280,10 @@ __device__ __forceinline__ void finish_pass2(const StagedParams &P, int64_t i, i
   write_priority<K>(P, i, b, W, H, V, L);
 }
 
+// WARPS = 8: 256 threads, two CTAs per SM (slab budget 100 KB); WARPS = 4: 128 threads, four CTAs per SM (50 KB), used
+// when the batch has at most 64 quizzes so that no warp of a CTA pass is idle.
 template <int K, int KL, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, 2) k_eval_staged(const StagedParams P) {
+__global__ void __launch_bounds__(WARPS * 32, WARPS == 4 ? 4 : 2) k_eval_staged(const StagedParams P) {
   constexpr int THREADS = WARPS * 32;
   constexpr int LPQ = 4 / KL;              // threads per quiz
   constexpr int QPW = 32 / LPQ;            // quizzes per warp
@@ -498,7 +500,7 @@ struct TShardParams {
 };
 
 template <int K, int KL, int WARPS, int PHASE>
-__global__ void __launch_bounds__(WARPS * 32, 2) k_eval_tshard(const TShardParams TP) {
+__global__ void __launch_bounds__(WARPS * 32, WARPS == 4 ? 4 : 2) k_eval_tshard(const TShardParams TP) {
   constexpr int THREADS = WARPS * 32;
   constexpr int LPQ = 4 / KL;
   constexpr int QPW = 32 / LPQ;
@@ -621,27 +623,30 @@ __global__ void __launch_bounds__(128) k_tshard_priority(const TShardEpiloguePar
   }
 }
 
+constexpr int64_t kSlabBudgetWide = 100 * 1024;    // two CTAs of 8 warps per SM
+constexpr int64_t kSlabBudgetNarrow = 50 * 1024;   // four CTAs of 4 warps per SM (batches of <= 64 quizzes)
+
 template <int K, int PHASE>
 static void launch_tshard_k(TShardParams TP, size_t smem, cudaStream_t st) {
-  // two threads per quiz (128 quizzes per CTA pass) for big batches, four threads per quiz (64 per pass) below that
-  const bool wide = TP.S.n >= 128;
+  // two threads per quiz; 128 quizzes per CTA pass (8 warps), or 64 (4 warps, twice the CTAs per SM) for small batches
+  const bool wide = TP.S.n > 64;
   static bool attrSet = false;
   if (!attrSet) {
     cudaFuncSetAttribute(k_eval_tshard<K, 2, 8, PHASE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(k_eval_tshard<K, 1, 8, PHASE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(k_eval_tshard<K, 2, 4, PHASE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     attrSet = true;
   }
   const int64_t perPass = wide ? 128 : 64;
   TP.S.quizzesPerCta = perPass;
   dim3 grid((unsigned)TP.S.kb.qCount, (unsigned)((TP.S.n + perPass - 1) / perPass));
   if (wide) k_eval_tshard<K, 2, 8, PHASE><<<grid, 256, smem, st>>>(TP);
-  else k_eval_tshard<K, 1, 8, PHASE><<<grid, 256, smem, st>>>(TP);
+  else k_eval_tshard<K, 2, 4, PHASE><<<grid, 128, smem, st>>>(TP);
   count_launch();
 }
 
-static size_t tshard_geometry(StagedParams &P, const EvalConfig &cfg) {
+// Chunk geometry: the whole local row when it fits the budget, else chunks of a multiple of 32 targets.
+static size_t slab_geometry(StagedParams &P, const EvalConfig &cfg, int64_t budget) {
   const int64_t bytesPerTarget = (2 * P.kb.K + 1) * (int64_t)sizeof(double);
-  const int64_t budget = 100 * 1024;  // two CTAs per SM
   int64_t Jc = cfg.chunkTargets > 0 ? ((cfg.chunkTargets + 3) & ~3ll) : P.kb.Tp;
   if (Jc > P.kb.Tp) Jc = P.kb.Tp;
   if (Jc * bytesPerTarget > budget) Jc = (budget / bytesPerTarget) & ~31ll;
@@ -649,6 +654,9 @@ static size_t tshard_geometry(StagedParams &P, const EvalConfig &cfg) {
   P.nChunks = (P.kb.Tp + Jc - 1) / Jc;
   P.quizzesPerCta = 0;
   return (size_t)(Jc * bytesPerTarget);
+}
+static size_t tshard_geometry(StagedParams &P, const EvalConfig &cfg) {
+  return slab_geometry(P, cfg, P.n > 64 ? kSlabBudgetWide : kSlabBudgetNarrow);
 }
 
 #define PQA_K_SWITCH(K_, CALL)                                  \
@@ -745,6 +753,7 @@ static void launch_k(const StagedParams &P, const EvalConfig &cfg, size_t smem, 
   // threads per quiz; one thread per quiz (4 lanes, 4 warps per CTA) is kept selectable for experiments
   const int lanesPerThread = cfg.kahanLanesPerThread > 0 ? cfg.kahanLanesPerThread : (P.n >= 32 ? 2 : 1);
   if (lanesPerThread == 4) launch_cfg<K, 4, 4>(P, cfg, smem, st);
+  else if (lanesPerThread == 2 && P.n <= 64) launch_cfg<K, 2, 4>(P, cfg, smem, st);   // 64 quizzes per CTA pass, no idle warps
   else if (lanesPerThread == 2) launch_cfg<K, 2, 8>(P, cfg, smem, st);
   else launch_cfg<K, 1, 8>(P, cfg, smem, st);
 }
@@ -759,15 +768,11 @@ void launch_eval_staged(const DeviceKB &kb, const QuizPool &qp, int64_t n, const
   }
   StagedParams P;
   P.kb = kb; P.qp = qp; P.n = n; P.slots = dSlots; P.priority = dPriority; P.det = det; P.mirror = cfg.mirror;
-  const int64_t bytesPerTarget = (2 * kb.K + 1) * (int64_t)sizeof(double);
-  const int64_t budget = 100 * 1024;  // two CTAs per SM
-  int64_t Jc = cfg.chunkTargets > 0 ? ((cfg.chunkTargets + 3) & ~3ll) : kb.Tp;
-  if (Jc > kb.Tp) Jc = kb.Tp;
-  if (Jc * bytesPerTarget > budget) Jc = (budget / bytesPerTarget) & ~31ll;
-  P.Jc = Jc;
-  P.nChunks = (kb.Tp + Jc - 1) / Jc;
-  P.quizzesPerCta = 0;
-  const size_t smem = (size_t)(Jc * bytesPerTarget);
+  // a slab that fits 100 KB is staged whole; a chunked one uses 50 KB chunks for batches of <= 64 quizzes, which run
+  // four 4-warp CTAs per SM (launch_k)
+  size_t smem = slab_geometry(P, cfg, kSlabBudgetWide);
+  if (P.nChunks > 1 && n <= 64 && cfg.chunkTargets == 0 && (cfg.kahanLanesPerThread == 0 || cfg.kahanLanesPerThread == 2))
+    smem = slab_geometry(P, cfg, kSlabBudgetNarrow);
   switch (kb.K) {
     case 2: launch_k<2>(P, cfg, smem, st); break;
     case 3: launch_k<3>(P, cfg, smem, st); break;
@@ -785,9 +790,10 @@ template <int K> static void preload_staged_k() {
   cudaFuncGetAttributes(&a, k_eval_staged<K, 2, 8>);
   cudaFuncGetAttributes(&a, k_eval_staged<K, 4, 4>);
   cudaFuncGetAttributes(&a, k_eval_small<K>);
-  cudaFuncGetAttributes(&a, k_eval_tshard<K, 1, 8, 1>);
+  cudaFuncGetAttributes(&a, k_eval_staged<K, 2, 4>);
+  cudaFuncGetAttributes(&a, k_eval_tshard<K, 2, 4, 1>);
   cudaFuncGetAttributes(&a, k_eval_tshard<K, 2, 8, 1>);
-  cudaFuncGetAttributes(&a, k_eval_tshard<K, 1, 8, 2>);
+  cudaFuncGetAttributes(&a, k_eval_tshard<K, 2, 4, 2>);
   cudaFuncGetAttributes(&a, k_eval_tshard<K, 2, 8, 2>);
   cudaFuncGetAttributes(&a, k_tshard_priority<K>);
 }
