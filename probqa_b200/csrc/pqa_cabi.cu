@@ -104,25 +104,22 @@ PQACORE_API void *PqaEngine_Train(void *pvEngine, int64_t nQuestions, const CiAn
   return Ret(Guard([&] { return E(pvEngine)->Train(nQuestions, pAQs, iTarget, amount); }));
 }
 
-// Permanent <-> compact id maps: without maintenance (no removals, no compaction) the two id spaces coincide
-// (PermanentIdManager.cpp: GrowTo assigns perm = comp), so the maps are the identity on valid ids.
-static uint8_t IdentityIds(void *pvEngine, int64_t count, int64_t *pIds, int which) {
+// Permanent <-> compact id maps (BaseEngine.cpp:154-218, PermanentIdManager.cpp); ids that do not map give -1.
+static uint8_t MapIds(void *pvEngine, int kind, bool permFromComp, int64_t count, int64_t *pIds) {
   if (!pvEngine || (count > 0 && !pIds)) return 0;
-  const CiEngineDimensions d = E(pvEngine)->CopyDims();
-  const int64_t lim = which == 0 ? d._nQuestions : which == 1 ? d._nTargets : INT64_MAX;
-  for (int64_t i = 0; i < count; i++)
-    if (pIds[i] < 0 || pIds[i] >= lim) pIds[i] = -1;
-  return 1;
+  return E(pvEngine)->MapIds(kind, permFromComp, count, pIds) ? 1 : 0;
 }
-PQACORE_API uint8_t PqaEngine_QuestionPermFromComp(void *pvEngine, const int64_t count, int64_t *pIds) { return IdentityIds(pvEngine, count, pIds, 0); }
-PQACORE_API uint8_t PqaEngine_QuestionCompFromPerm(void *pvEngine, const int64_t count, int64_t *pIds) { return IdentityIds(pvEngine, count, pIds, 0); }
-PQACORE_API uint8_t PqaEngine_TargetPermFromComp(void *pvEngine, const int64_t count, int64_t *pIds) { return IdentityIds(pvEngine, count, pIds, 1); }
-PQACORE_API uint8_t PqaEngine_TargetCompFromPerm(void *pvEngine, const int64_t count, int64_t *pIds) { return IdentityIds(pvEngine, count, pIds, 1); }
-PQACORE_API uint8_t PqaEngine_QuizPermFromComp(void *pvEngine, const int64_t count, int64_t *pIds) { return IdentityIds(pvEngine, count, pIds, 2); }
-PQACORE_API uint8_t PqaEngine_QuizCompFromPerm(void *pvEngine, const int64_t count, int64_t *pIds) { return IdentityIds(pvEngine, count, pIds, 2); }
-PQACORE_API uint8_t PqaEngine_EnsurePermQuizGreater(void *pvEngine, const int64_t bound) { (void)bound; return pvEngine ? 1 : 0; }
+PQACORE_API uint8_t PqaEngine_QuestionPermFromComp(void *pvEngine, const int64_t count, int64_t *pIds) { return MapIds(pvEngine, 0, true, count, pIds); }
+PQACORE_API uint8_t PqaEngine_QuestionCompFromPerm(void *pvEngine, const int64_t count, int64_t *pIds) { return MapIds(pvEngine, 0, false, count, pIds); }
+PQACORE_API uint8_t PqaEngine_TargetPermFromComp(void *pvEngine, const int64_t count, int64_t *pIds) { return MapIds(pvEngine, 1, true, count, pIds); }
+PQACORE_API uint8_t PqaEngine_TargetCompFromPerm(void *pvEngine, const int64_t count, int64_t *pIds) { return MapIds(pvEngine, 1, false, count, pIds); }
+PQACORE_API uint8_t PqaEngine_QuizPermFromComp(void *pvEngine, const int64_t count, int64_t *pIds) { return MapIds(pvEngine, 2, true, count, pIds); }
+PQACORE_API uint8_t PqaEngine_QuizCompFromPerm(void *pvEngine, const int64_t count, int64_t *pIds) { return MapIds(pvEngine, 2, false, count, pIds); }
+PQACORE_API uint8_t PqaEngine_EnsurePermQuizGreater(void *pvEngine, const int64_t bound) {
+  return pvEngine && E(pvEngine)->EnsurePermQuizGreater(bound) ? 1 : 0;
+}
 PQACORE_API uint8_t PqaEngine_RemapQuizPermId(void *pvEngine, const int64_t srcPermId, const int64_t destPermId) {
-  (void)pvEngine; return srcPermId == destPermId ? 1 : 0;
+  return pvEngine && E(pvEngine)->RemapQuizPermId(srcPermId, destPermId) ? 1 : 0;
 }
 
 PQACORE_API uint64_t PqaEngine_GetTotalQuestionsAsked(void *pvEngine, void **ppError) {
@@ -200,33 +197,31 @@ PQACORE_API void *PqaEngine_SaveKB(void *pvEngine, const char *const filePath, c
   return Ret(Guard([&] { return E(pvEngine)->SaveKB(filePath); }));
 }
 
-static PqaError *MaintenanceNotImplemented(const char *what) {
-  return ErrNotImplemented(std::string("B200 engine: ") + what +
-                           " -- maintenance mode (KB resize / removal / compaction) is outside the hot-path scope");
-}
 PQACORE_API void *PqaEngine_StartMaintenance(void *pvEngine, const bool forceQuizzes) {
-  (void)forceQuizzes;
-  return pvEngine ? MaintenanceNotImplemented("StartMaintenance") : NullEngine();
+  if (!pvEngine) return NullEngine();
+  return Ret(Guard([&] { return E(pvEngine)->StartMaintenance(forceQuizzes); }));
 }
 PQACORE_API void *PqaEngine_FinishMaintenance(void *pvEngine) {
-  return pvEngine ? MaintenanceNotImplemented("FinishMaintenance") : NullEngine();
+  if (!pvEngine) return NullEngine();
+  return Ret(Guard([&] { return E(pvEngine)->FinishMaintenance(); }));
 }
-PQACORE_API void *PqaEngine_AddQsTs(void *pvEngine, const int64_t, CiAddQorTParam *, const int64_t, CiAddQorTParam *) {
-  return pvEngine ? MaintenanceNotImplemented("AddQsTs") : NullEngine();
+PQACORE_API void *PqaEngine_AddQsTs(void *pvEngine, const int64_t nQuestions, CiAddQorTParam *pAddQuestionParams,
+                                    const int64_t nTargets, CiAddQorTParam *pAddTargetParams) {
+  if (!pvEngine) return NullEngine();
+  return Ret(Guard([&] { return E(pvEngine)->AddQsTs(nQuestions, pAddQuestionParams, nTargets, pAddTargetParams); }));
 }
-PQACORE_API void *PqaEngine_RemoveQuestions(void *pvEngine, const int64_t, const int64_t *) {
-  return pvEngine ? MaintenanceNotImplemented("RemoveQuestions") : NullEngine();
+PQACORE_API void *PqaEngine_RemoveQuestions(void *pvEngine, const int64_t nQuestions, const int64_t *pQIds) {
+  if (!pvEngine) return NullEngine();
+  return Ret(Guard([&] { return E(pvEngine)->RemoveQuestions(nQuestions, pQIds); }));
 }
-PQACORE_API void *PqaEngine_RemoveTargets(void *pvEngine, const int64_t, const int64_t *) {
-  return pvEngine ? MaintenanceNotImplemented("RemoveTargets") : NullEngine();
+PQACORE_API void *PqaEngine_RemoveTargets(void *pvEngine, const int64_t nTargets, const int64_t *pTIds) {
+  if (!pvEngine) return NullEngine();
+  return Ret(Guard([&] { return E(pvEngine)->RemoveTargets(nTargets, pTIds); }));
 }
 PQACORE_API void *PqaEngine_Compact(void *pvEngine, int64_t *pnQuestions, int64_t const **const ppOldQuestions,
                                     int64_t *pnTargets, int64_t const **const ppOldTargets) {
-  if (pnQuestions) *pnQuestions = 0;
-  if (pnTargets) *pnTargets = 0;
-  if (ppOldQuestions) *ppOldQuestions = nullptr;
-  if (ppOldTargets) *ppOldTargets = nullptr;
-  return pvEngine ? MaintenanceNotImplemented("Compact") : NullEngine();
+  if (!pvEngine) return NullEngine();
+  return Ret(Guard([&] { return E(pvEngine)->Compact(pnQuestions, ppOldQuestions, pnTargets, ppOldTargets); }));
 }
 PQACORE_API void CiReleaseCompaction(const int64_t *p) { delete[] p; }
 PQACORE_API void *PqaEngine_Shutdown(void *pvEngine, const char *const saveFilePath) {

@@ -18,27 +18,6 @@ namespace pqa {
 #define SRC_LINE_STR(x) SRC_LINE_STR2(x)
 #define PQA_FILE_LINE "pqa_engine.cu(" SRC_LINE_STR(__LINE__) "): "
 
-template <typename T> void DevBuf<T>::ensure(size_t n, cudaStream_t st, bool keep) {
-  if (n <= n_) return;
-  size_t cap = std::max(n, n_ * 2);
-  T *p = nullptr;
-  PQA_CU(cudaMalloc(&p, cap * sizeof(T)));
-  if (p_) {
-    if (keep) PQA_CU(cudaMemcpyAsync(p, p_, n_ * sizeof(T), cudaMemcpyDeviceToDevice, st));
-    PQA_CU(cudaStreamSynchronize(st));
-    cudaFree(p_);
-  }
-  p_ = p; n_ = cap;
-}
-template <typename T> void PinBuf<T>::ensure(size_t n) {
-  if (n <= n_) return;
-  size_t cap = std::max(n, n_ * 2);
-  T *p = nullptr;
-  PQA_CU(cudaMallocHost(&p, cap * sizeof(T)));
-  if (p_) { std::memcpy(p, p_, n_ * sizeof(T)); cudaFreeHost(p_); }
-  p_ = p; n_ = cap;
-}
-
 static int env_int(const char *name, int dflt) {
   const char *v = std::getenv(name);
   return (v && *v) ? std::atoi(v) : dflt;
@@ -80,6 +59,8 @@ Engine::Engine(const CiEngineDefinition &def, const CiB200Options &opts) {
     tFirst_ = opts._targetShardFirst; tLocal_ = opts._targetShardCount;
   }
   TpL_ = (tLocal_ + 3) & ~3ll;
+  qGaps_.GrowTo(Q_); tGaps_.GrowTo(T_);     // BaseEngine::AfterStatisticsInit (BaseEngine.cpp:32-34)
+  pimQ_.GrowTo(Q_); pimT_.GrowTo(T_);
   int nDev = 0;
   PQA_CU(cudaGetDeviceCount(&nDev));
   if (nDev <= 0) throw std::runtime_error("probqa_b200: no CUDA device is visible; this engine has no CPU path");
@@ -134,9 +115,11 @@ Engine::~Engine() {
 DeviceKB Engine::kb() const {
   DeviceKB k;
   k.sA = dSA_; k.mD = dMD_; k.vB = dVB_; k.log2tbl = dLog2Tbl_;
-  k.tgaps = nullptr; k.qgaps = nullptr;   // maintenance (RemoveQuestions/RemoveTargets) is out of scope: no gaps
+  // gap bitmaps exist only while something is removed (RemoveTargets / RemoveQuestions without a Compact yet)
+  k.tgaps = tGaps_.GetNGaps() > 0 ? dTGapBits_.get() : nullptr;
+  k.qgaps = qGaps_.GetNGaps() > 0 ? dQGapBits_.get() : nullptr;
   k.Q = Q_; k.K = K_; k.T = tLocal_; k.Tp = TpL_;   // a target-sharded engine sees its own columns here
-  k.nValidTargets = T_;                    // CpuEngine.cpp:351 with no target gaps
+  k.nValidTargets = T_ - tGaps_.GetNGaps();  // CpuEngine.cpp:351
   k.qFirst = qFirst_; k.qCount = qLocal_;
   return k;
 }
@@ -156,7 +139,7 @@ QuizPool Engine::pool() const {
 
 void Engine::EnsureQuizCapacity(int64_t nSlots) {
   if (nSlots <= quizCap_) return;
-  const int64_t cap = std::max<int64_t>(nSlots, quizCap_ * 2);
+  const int64_t cap = std::max<int64_t>(std::max<int64_t>(nSlots, quizCap_ * 2), 64);
   double *np = nullptr, *nl = nullptr; uint64_t *na = nullptr; int64_t *nact = nullptr;
   PQA_CU(cudaMalloc(&np, sizeof(double) * (size_t)(cap * Tp_)));
   PQA_CU(cudaMalloc(&nl, sizeof(double) * (size_t)(cap * Tp_)));
@@ -194,8 +177,8 @@ PqaError *Engine::CheckQuiz(int64_t iQuiz) const {
 
 int64_t Engine::AssignQuizId() {
   int64_t id;
-  if (!quizGaps_.empty()) { id = quizGaps_.back(); quizGaps_.pop_back(); }
-  else { id = (int64_t)quizzes_.size(); quizzes_.emplace_back(); }
+  if (!quizGaps_.empty()) { id = quizGaps_.back(); quizGaps_.pop_back(); pimQuiz_.RenewComp(id); }   // BaseEngine.cpp:781-794
+  else { id = (int64_t)quizzes_.size(); quizzes_.emplace_back(); pimQuiz_.GrowTo((int64_t)quizzes_.size()); }
   HostQuiz &q = quizzes_[id];
   q.present = true; q.activeQuestion = -1; q.answers.clear();
   return id;
@@ -222,6 +205,7 @@ PqaError *Engine::StartQuizBatch(int64_t n, int64_t *pQuizIds) {
   if (n < 0) return ErrNegativeCount(n, PQA_FILE_LINE "|n| must be non-negative.");
   if (n == 0) return nullptr;
   if (!pQuizIds) return MakeError(ErrCode::NullArgument, PQA_FILE_LINE "pQuizIds");
+  if (maintenance_) return WrongMode("Start/Resume quiz");
   std::lock_guard<std::mutex> lk(mu_);
   PQA_TRY
   for (int64_t x = 0; x < n; x++) pQuizIds[x] = AssignQuizId();
@@ -247,6 +231,7 @@ PqaError *Engine::ResumeQuizBatch(int64_t n, const int64_t *pCounts, const CiAns
   if (n == 0) return nullptr;
   if (!pCounts || !pQuizIds) return MakeError(ErrCode::NullArgument, PQA_FILE_LINE "pCounts/pQuizIds");
   if (IsSharded()) return ErrNotImplemented("ResumeQuiz on a sharded engine");
+  if (maintenance_) return WrongMode("Start/Resume quiz");
   int64_t total = 0;
   for (int64_t x = 0; x < n; x++) {
     if (pCounts[x] < 0) return ErrNegativeCount(pCounts[x], "|nAnswered| must be non-negative.");
@@ -308,6 +293,7 @@ PqaError *Engine::ResumeQuizBatch(int64_t n, const int64_t *pCounts, const CiAns
       HostQuiz &q = quizzes_[resumeIds[x]];
       q.present = false; q.answers.clear(); q.activeQuestion = -1;
       quizGaps_.push_back(resumeIds[x]);
+      pimQuiz_.RemoveComp(resumeIds[x]);
       for (int64_t y = 0; y < n; y++) if (pQuizIds[y] == resumeIds[x]) pQuizIds[y] = -1;
       if (!result) result = MakeError(ErrCode::I64Underflow, "Max exponent over the priors is too low. Are all the targets in gaps?",
                                       "actual=<underflow>, minAllowed=<see CpuEngine.cpp:315>");
@@ -332,6 +318,7 @@ PqaError *Engine::NextQuestionBatch(int64_t n, const int64_t *pQuizIds, const ui
   if (n == 0) return nullptr;
   if (!pQuizIds || !pQuestions) return MakeError(ErrCode::NullArgument, PQA_FILE_LINE "pQuizIds/pQuestions");
   if (IsSharded()) return ErrNotImplemented("NextQuestion on a sharded engine: use the PqaB200_Shard* protocol");
+  if (maintenance_) return WrongMode("compute next question");
   std::lock_guard<std::mutex> lk(mu_);
   PQA_TRY
   // validate; quizzes that fail validation get their own error and are left out of the launch
@@ -467,6 +454,7 @@ void Engine::RunCombined(const std::vector<CallSlot *> &batch) {
 
 int64_t Engine::NextQuestion(PqaError **err, int64_t iQuiz) {
   if (IsSharded()) { int64_t q = -1; *err = NextQuestionBatch(1, &iQuiz, nullptr, &q, nullptr); return -1; }
+  if (maintenance_) { *err = WrongMode("compute next question"); return -1; }   // BaseEngine.cpp:422-427
   CallSlot s; s.kind = 0; s.quiz = iQuiz;
   Submit(s);
   *err = s.err;
@@ -480,6 +468,7 @@ PqaError *Engine::RecordAnswerBatch(int64_t n, const int64_t *pQuizIds, const in
   if (n == 0) return nullptr;
   if (!pQuizIds || !pAnswers) return MakeError(ErrCode::NullArgument, PQA_FILE_LINE "pQuizIds/pAnswers");
   if (IsSharded()) return ErrNotImplemented("RecordAnswer on a sharded engine: use PqaB200_ShardRecordAnswerBegin / End");
+  if (maintenance_) return WrongMode("record an answer");
   std::lock_guard<std::mutex> lk(mu_);
   PQA_TRY
   if (PqaError *e = ValidateRecordAnswer(n, pQuizIds, pAnswers)) return e;
@@ -501,6 +490,7 @@ PqaError *Engine::RecordAnswerBatch(int64_t n, const int64_t *pQuizIds, const in
 
 PqaError *Engine::RecordAnswer(int64_t iQuiz, int64_t iAnswer) {
   if (IsSharded()) return RecordAnswerBatch(1, &iQuiz, &iAnswer);
+  if (maintenance_) return WrongMode("record an answer");                       // BaseEngine.cpp:440-444
   CallSlot s; s.kind = 1; s.quiz = iQuiz; s.arg = iAnswer;
   Submit(s);
   return s.err;
@@ -644,6 +634,7 @@ PqaError *Engine::ShardBuffer(int32_t which, void **ppDevice, int64_t *pCount) {
 }
 
 int64_t Engine::GetActiveQuestionId(PqaError **err, int64_t iQuiz) {
+  if (maintenance_) { *err = WrongMode("get active question ID for a quiz"); return -1; }
   std::lock_guard<std::mutex> lk(mu_);
   *err = CheckQuiz(iQuiz);
   return *err ? -1 : quizzes_[iQuiz].activeQuestion;
@@ -653,6 +644,7 @@ PqaError *Engine::SetActiveQuestionBatch(int64_t n, const int64_t *pQuizIds, con
   if (n < 0) return ErrNegativeCount(n, PQA_FILE_LINE "|n| must be non-negative.");
   if (n == 0) return nullptr;
   if (!pQuizIds || !pQuestions) return MakeError(ErrCode::NullArgument, PQA_FILE_LINE "pQuizIds/pQuestions");
+  if (maintenance_) return WrongMode("get active question ID for a quiz");   // sic, BaseEngine.cpp:491-493
   std::lock_guard<std::mutex> lk(mu_);
   PQA_TRY
   for (int64_t x = 0; x < n; x++)
@@ -683,6 +675,7 @@ PqaError *Engine::ListTopTargetsBatch(int64_t n, const int64_t *pQuizIds, int64_
   if (n == 0) return nullptr;
   if (!pQuizIds || !pCounts || (maxCount > 0 && !pDest))
     return MakeError(ErrCode::NullArgument, PQA_FILE_LINE "pQuizIds/pDest/pCounts");
+  if (maintenance_) return WrongMode("compute next question");   // sic, BaseEngine.cpp:514-516
   std::lock_guard<std::mutex> lk(mu_);
   PQA_TRY
   for (int64_t x = 0; x < n; x++)
@@ -707,6 +700,7 @@ PqaError *Engine::ListTopTargetsBatch(int64_t n, const int64_t *pQuizIds, int64_
 
 int64_t Engine::ListTopTargets(PqaError **err, int64_t iQuiz, int64_t maxCount, CiRatedTarget *pDest) {
   if (maxCount > 0 && !pDest) { *err = MakeError(ErrCode::NullArgument, PQA_FILE_LINE "pDest"); return -1; }
+  if (maintenance_) { *err = WrongMode("compute next question"); return -1; }   // sic, BaseEngine.cpp:512-517
   CallSlot s; s.kind = 2; s.quiz = iQuiz; s.arg = maxCount; s.dest = pDest;
   Submit(s);
   *err = s.err;
@@ -794,6 +788,10 @@ PqaError *Engine::RecordQuizTargetBatch(int64_t n, const int64_t *pQuizIds, cons
   if (n < 0) return ErrNegativeCount(n, PQA_FILE_LINE "|n| must be non-negative.");
   if (n == 0) return nullptr;
   if (!pQuizIds || !pTargets) return MakeError(ErrCode::NullArgument, PQA_FILE_LINE "pQuizIds/pTargets");
+  if (pAmounts)
+    for (int64_t x = 0; x < n; x++)
+      if (!(pAmounts[x] > 0)) return ErrNonPositiveAmount(pAmounts[x], PQA_FILE_LINE "|amount| must be positive.");
+  if (maintenance_) return WrongMode("record quiz target");
   std::lock_guard<std::mutex> lk(mu_);
   std::vector<TrainOp> ops;
   std::vector<int64_t> targets(n);
@@ -803,6 +801,8 @@ PqaError *Engine::RecordQuizTargetBatch(int64_t n, const int64_t *pQuizIds, cons
     if (!(amount > 0)) return ErrNonPositiveAmount(amount, PQA_FILE_LINE "|amount| must be positive.");
     if (pTargets[x] < 0 || pTargets[x] >= T_)
       return ErrIndexOutOfRange(pTargets[x], 0, T_ - 1, PQA_FILE_LINE "Target index is not in KB range.");
+    if (tGaps_.IsGap(pTargets[x]))
+      return ErrAbsentId(pTargets[x], PQA_FILE_LINE "Target index is not in KB (but rather at a gap).");
     if (PqaError *e = CheckQuiz(pQuizIds[x])) return e;
     targets[x] = pTargets[x]; amounts[x] = amount;
   }
@@ -826,9 +826,12 @@ PqaError *Engine::Train(int64_t nQuestions, const CiAnsweredQuestion *pAQs, int6
   if (nQuestions > 0 && !pAQs) return MakeError(ErrCode::NullArgument, PQA_FILE_LINE "pAQs");
   std::lock_guard<std::mutex> lk(mu_);
   if (iTarget < 0 || iTarget >= T_) return ErrIndexOutOfRange(iTarget, 0, T_ - 1, "Target index is not in KB range.");
+  if (tGaps_.IsGap(iTarget)) return ErrAbsentId(iTarget, PQA_FILE_LINE "Target index is not in KB (but rather at a gap).");   // CpuEngine.cpp:148-152
   for (int64_t x = 0; x < nQuestions; x++) {  // CETrainSubtaskDistrib.h:24-43
     if (pAQs[x]._iQuestion < 0 || pAQs[x]._iQuestion >= Q_)
       return ErrIndexOutOfRange(pAQs[x]._iQuestion, 0, Q_ - 1, PQA_FILE_LINE "Question index is not in KB range.");
+    if (qGaps_.IsGap(pAQs[x]._iQuestion))
+      return ErrAbsentId(pAQs[x]._iQuestion, "Question index is not in KB (but rather at a gap).");
     if (pAQs[x]._iAnswer < 0 || pAQs[x]._iAnswer >= K_)
       return ErrIndexOutOfRange(pAQs[x]._iAnswer, 0, K_ - 1, PQA_FILE_LINE "Answer index is not in KB range.");
   }
@@ -863,12 +866,14 @@ PqaError *Engine::Train(int64_t nQuestions, const CiAnsweredQuestion *pAQs, int6
 PqaError *Engine::ReleaseQuizBatch(int64_t n, const int64_t *pQuizIds) {
   if (n < 0) return ErrNegativeCount(n, PQA_FILE_LINE "|n| must be non-negative.");
   if (n > 0 && !pQuizIds) return MakeError(ErrCode::NullArgument, PQA_FILE_LINE "pQuizIds");
+  if (maintenance_) return WrongMode("release quiz");
   std::lock_guard<std::mutex> lk(mu_);
   for (int64_t x = 0; x < n; x++) {
     if (PqaError *e = CheckQuiz(pQuizIds[x])) return e;
     HostQuiz &q = quizzes_[pQuizIds[x]];
     q.present = false; q.answers.clear(); q.answers.shrink_to_fit(); q.activeQuestion = -1;
     quizGaps_.push_back(pQuizIds[x]);
+    pimQuiz_.RemoveComp(pQuizIds[x]);      // BaseEngine::UnassignQuiz, BaseEngine.cpp:796-801
   }
   if (residentN_ > 0) residentN_ = 0;  // a released quiz may be part of the bound batch
   return nullptr;
@@ -1489,16 +1494,15 @@ PqaError *Engine::SaveKB(const char *filePath) {
   if (PqaError *e = dumpRows(dSA_, Q_ * K_)) return e;
   if (PqaError *e = dumpRows(dMD_, Q_)) return e;
   if (PqaError *e = dumpRows(dVB_, 1)) return e;
-  const int64_t zero = 0;
-  if (!wr(fc.f, &zero, 8) || !wr(fc.f, &zero, 8)) return FileOpErr(filePath, PQA_FILE_LINE "Can't write the gaps.");  // no gaps
-  auto dumpIdentity = [&](int64_t n) {
-    std::vector<int64_t> ids((size_t)n);
-    std::iota(ids.begin(), ids.end(), 0);
-    return wr(fc.f, &n, 8) && wr(fc.f, &n, 8) && wr(fc.f, ids.data(), (size_t)n * 8);   // nextPermId = n, nComp = n, comp2perm
+  auto dumpGaps = [&](const GapSet &g) {     // BaseEngine::WriteGaps, BaseEngine.cpp:142-152: count, then the ids in LIFO order
+    const int64_t nGaps = g.GetNGaps();
+    return wr(fc.f, &nGaps, 8) && (nGaps == 0 || wr(fc.f, g.Gaps().data(), (size_t)nGaps * 8));
   };
-  if (!dumpIdentity(Q_) || !dumpIdentity(T_)) return FileOpErr(filePath, PQA_FILE_LINE "Can't write the ID mappings.");
-  const int64_t nextQuizPerm = (int64_t)quizzes_.size();
-  if (!wr(fc.f, &nextQuizPerm, 8) || !wr(fc.f, &zero, 8)) return FileOpErr(filePath, PQA_FILE_LINE "Can't write the quiz ID mapping.");
+  if (!dumpGaps(qGaps_)) return FileOpErr(filePath, PQA_FILE_LINE "Can't write the question gaps.");
+  if (!dumpGaps(tGaps_)) return FileOpErr(filePath, PQA_FILE_LINE "Can't write the target gaps.");
+  if (!pimQ_.Save(fc.f)) return FileOpErr(filePath, PQA_FILE_LINE "Can't write the question permanent-compact ID mappings.");
+  if (!pimT_.Save(fc.f)) return FileOpErr(filePath, PQA_FILE_LINE "Can't write the target permanent-compact ID mappings.");
+  if (!pimQuiz_.Save(fc.f, true)) return FileOpErr(filePath, PQA_FILE_LINE "Can't write the quiz permanent-compact ID mappings.");
   if (std::fflush(fc.f) != 0) return FileOpErr(filePath, PQA_FILE_LINE "Can't flush the KB file.");
   return nullptr;
 }
@@ -1529,19 +1533,24 @@ Engine *Engine::LoadKB(const char *filePath, const CiB200Options &opts, PqaError
     *err = FileOpErr(filePath, PQA_FILE_LINE "Can't read the KB statistics.");
     return nullptr;
   }
-  for (int g = 0; g < 2; g++) {   // question gaps, target gaps
+  for (int g = 0; g < 2; g++) {   // question gaps, target gaps (BaseEngine::ReadGaps, BaseEngine.cpp:126-140)
     int64_t nGaps = 0;
     if (!rd(fc.f, &nGaps, 8)) { *err = FileOpErr(filePath, PQA_FILE_LINE "Can't read the gaps."); return nullptr; }
-    if (nGaps != 0) { *err = ErrNotImplemented("B200 engine: KB files with removed questions/targets (gaps) need maintenance mode"); return nullptr; }
+    const int64_t range = g == 0 ? Q : T;
+    if (nGaps < 0 || nGaps > range) { *err = FileOpErr(filePath, PQA_FILE_LINE "Corrupt gap count."); return nullptr; }
+    std::vector<int64_t> ids((size_t)nGaps);
+    if (nGaps > 0 && !rd(fc.f, ids.data(), ids.size() * 8)) { *err = FileOpErr(filePath, PQA_FILE_LINE "Can't read the gaps."); return nullptr; }
+    GapSet &gs = g == 0 ? eng->qGaps_ : eng->tGaps_;
+    for (int64_t id : ids) {
+      if (id < 0 || id >= range || gs.IsGap(id)) { *err = FileOpErr(filePath, PQA_FILE_LINE "Corrupt gap list."); return nullptr; }
+      gs.Release(id);
+    }
   }
-  for (int m = 0; m < 3; m++) {   // id maps: accepted when they are the identity (no removals ever happened)
-    int64_t nextPerm = 0, nComp = 0;
-    if (!rd(fc.f, &nextPerm, 8) || !rd(fc.f, &nComp, 8)) { *err = FileOpErr(filePath, PQA_FILE_LINE "Can't read the ID mappings."); return nullptr; }
-    std::vector<int64_t> ids((size_t)std::max<int64_t>(nComp, 0));
-    if (nComp > 0 && !rd(fc.f, ids.data(), ids.size() * 8)) { *err = FileOpErr(filePath, PQA_FILE_LINE "Can't read the ID mappings."); return nullptr; }
-    for (int64_t x = 0; x < nComp; x++)
-      if (ids[x] != x) { *err = ErrNotImplemented("B200 engine: KB files with remapped permanent IDs need maintenance mode"); return nullptr; }
+  if (!eng->pimQ_.Load(fc.f) || !eng->pimT_.Load(fc.f) || !eng->pimQuiz_.Load(fc.f)) {   // BaseEngine.cpp:45-56
+    *err = FileOpErr(filePath, PQA_FILE_LINE "Can't read the permanent-compact ID mappings.");
+    return nullptr;
   }
+  eng->SyncGapBits();
   if (PqaError *e = eng->UploadKB(sA.data(), mD.data(), vB.data())) { *err = e; return nullptr; }
   eng->nQuestionsAsked_.store(asked, std::memory_order_relaxed);
   return eng.release();

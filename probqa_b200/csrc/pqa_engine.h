@@ -5,12 +5,16 @@
 // and vB runs on the device; the host only validates, keeps the quiz registry (ids, answered lists, active
 // question) and moves ids/answers/results through pinned staging buffers.
 #pragma once
+#include <algorithm>
 #include <atomic>
+#include <cstring>
 #include <condition_variable>
 #include <mutex>
 #include <stdexcept>
 #include <string>
+#include <unordered_map>
 #include <vector>
+#include <cstdio>
 
 #include "../../include/PqaB200Ext.h"
 #include "pqa_errors.h"
@@ -48,6 +52,69 @@ template <typename T> class PinBuf {  // grow-only pinned host array
   T *p_ = nullptr;
   size_t n_ = 0;
 };
+
+// GapTracker<TPqaId> (PqaCore/GapTracker.h:11-70): removed ids, reused LIFO.
+class GapSet {
+ public:
+  bool IsGap(int64_t at) const { return isGap_[(size_t)at] != 0; }
+  void Release(int64_t at) { isGap_[(size_t)at] = 1; gaps_.push_back(at); }
+  int64_t Acquire() {                       // :38-49
+    if (gaps_.empty()) { isGap_.push_back(0); return (int64_t)isGap_.size() - 1; }
+    const int64_t a = gaps_.back();
+    gaps_.pop_back();
+    isGap_[(size_t)a] = 0;
+    return a;
+  }
+  void GrowTo(int64_t n) { isGap_.resize((size_t)n, 0); }
+  void Compact(int64_t n) { isGap_.assign((size_t)n, 0); gaps_.clear(); }
+  int64_t GetNGaps() const { return (int64_t)gaps_.size(); }
+  const std::vector<int64_t> &Gaps() const { return gaps_; }
+  int64_t Size() const { return (int64_t)isGap_.size(); }
+ private:
+  std::vector<int64_t> gaps_;
+  std::vector<uint8_t> isGap_;
+};
+
+// PermanentIdManager (PqaCore/PermanentIdManager.cpp): compact (array index) <-> permanent (never reused) ids.
+class PermIds {
+ public:
+  int64_t PermFromComp(int64_t comp) const;
+  int64_t CompFromPerm(int64_t perm) const;
+  bool RemoveComp(int64_t comp);
+  bool RenewComp(int64_t comp);
+  bool GrowTo(int64_t nComp);
+  bool OnCompact(int64_t nNew, const int64_t *pOldIds);
+  bool EnsurePermIdGreater(int64_t bound);
+  bool RemapPermId(int64_t srcPerm, int64_t destPerm);
+  bool Save(FILE *f, bool empty = false) const;   // {i64 nextPermId, i64 nComp, nComp x i64}
+  bool Load(FILE *f);
+ private:
+  int64_t nextPerm_ = 0;
+  std::vector<int64_t> comp2perm_;
+  std::unordered_map<int64_t, int64_t> perm2comp_;
+};
+
+template <typename T> inline void DevBuf<T>::ensure(size_t n, cudaStream_t st, bool keep) {
+  if (n <= n_) return;
+  size_t cap = std::max(n, n_ * 2);
+  T *p = nullptr;
+  PQA_CU(cudaMalloc(&p, cap * sizeof(T)));
+  if (p_) {
+    if (keep) PQA_CU(cudaMemcpyAsync(p, p_, n_ * sizeof(T), cudaMemcpyDeviceToDevice, st));
+    PQA_CU(cudaStreamSynchronize(st));
+    cudaFree(p_);
+  }
+  p_ = p; n_ = cap;
+}
+template <typename T> inline void PinBuf<T>::ensure(size_t n) {
+  if (n <= n_) return;
+  size_t cap = std::max(n, n_ * 2);
+  T *p = nullptr;
+  PQA_CU(cudaMallocHost(&p, cap * sizeof(T)));
+  if (p_) { std::memcpy(p, p_, n_ * sizeof(T)); cudaFreeHost(p_); }
+  p_ = p; n_ = cap;
+}
+
 
 struct HostQuiz {                      // BaseQuiz.h:13-36 (host part); priors and asked bits live on the device
   bool present = false;
@@ -89,6 +156,17 @@ class Engine {
   PqaError *CopyBTargets(int64_t maxTargets, double *pFreqs);
   PqaError *SaveKB(const char *filePath);
   static Engine *LoadKB(const char *filePath, const CiB200Options &opts, PqaError **err);
+
+  // --- maintenance mode (BaseEngine.cpp:640-779, CpuEngine.cpp:468-658) and id maps (BaseEngine.cpp:154-218) ---
+  PqaError *StartMaintenance(bool forceQuizzes);
+  PqaError *FinishMaintenance();
+  PqaError *AddQsTs(int64_t nQuestions, CiAddQorTParam *pAqps, int64_t nTargets, CiAddQorTParam *pAtps);
+  PqaError *RemoveQuestions(int64_t nQuestions, const int64_t *pQIds);
+  PqaError *RemoveTargets(int64_t nTargets, const int64_t *pTIds);
+  PqaError *Compact(int64_t *pnQuestions, const int64_t **ppOldQuestions, int64_t *pnTargets, const int64_t **ppOldTargets);
+  bool MapIds(int kind, bool permFromComp, int64_t count, int64_t *pIds);   // kind: 0 questions, 1 targets, 2 quizzes
+  bool EnsurePermQuizGreater(int64_t bound);
+  bool RemapQuizPermId(int64_t srcPermId, int64_t destPermId);
 
   // --- batches of concurrent quizzes ---
   PqaError *StartQuizBatch(int64_t n, int64_t *pQuizIds);
@@ -159,6 +237,10 @@ class Engine {
   PqaError *ValidateRecordAnswer(int64_t n, const int64_t *pQuizIds, const int64_t *pAnswers) const;
   PqaError *FinishNextQuestion(int64_t m, const std::vector<int64_t> &valid, const std::vector<int64_t> &where,
                                int64_t *pQuestions, void **ppErrors, PqaError *firstErr);
+  PqaError *WrongMode(const char *what) const;          // regular-only operation called in maintenance mode
+  void SyncGapBits();                                    // host gap trackers -> device bitmaps read by the kernels
+  void ResizeKB(int64_t newQ, int64_t newT);             // grows sA/mD/vB on the device, keeps the old cells
+  void DropQuizPool();
   bool OwnsQuestion(int64_t q) const { return q >= qFirst_ && q < qFirst_ + qLocal_; }
   int64_t AssignQuizId();                                // BaseEngine::AssignQuiz + GapTracker::Acquire
   void EnsureQuizCapacity(int64_t nSlots);
@@ -197,6 +279,10 @@ class Engine {
   double *p2pLastPriority_ = nullptr;
   P2PFlags p2pFlags() const;
   PqaError *P2PCheckError();
+  std::atomic<bool> maintenance_{false};                           // MaintenanceSwitch mode (MaintenanceSwitch.h): Regular / Maintenance
+  GapSet qGaps_, tGaps_;                                 // removed questions / targets (BaseEngine _questionGaps, _targetGaps)
+  PermIds pimQ_, pimT_, pimQuiz_;
+  DevBuf<uint32_t> dQGapBits_, dTGapBits_;
   double initAmount_ = 0;
   uint32_t precMantissa_ = 0; uint16_t precExponent_ = 0;   // kept only to write them back into a KB file header
   cudaStream_t stream_ = nullptr;

@@ -184,7 +184,7 @@ __device__ __forceinline__ void pass2_chunk(const double *__restrict__ sR, const
         for (int e = 0; e < KL; e++) {
           const double l2 = __dsub_rn(__dadd_rn(lr.v[e], lp.v[e]), lW[k]);
           H[k] = __fma_rn(post[k][e], l2, H[k]);                        // :113-114
-          L[e] = __fma_rn(id2.v[e], fast_rcp(l2), L[e]);                // :116-117 (id2 = 0 on gap / padding lanes)
+          L[e] = __fma_rn(id2.v[e], fast_rcp46(l2), L[e]);              // :116-117 (id2 = 0 on gap / padding lanes)
           const double d = __dsub_rn(post[k][e], p.v[e]);               // :119
           V[k] = __fma_rn(d, d, V[k]);                                  // :126-127
         }

@@ -425,6 +425,56 @@ void launch_p2p_pull_prior_rows(const DeviceKB &kb, const QuizPool &qp, int64_t 
   count_launch();
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Maintenance helpers (pqa_kernels.cuh)
+__global__ void k_copy_rows(double *__restrict__ dst, int64_t dstStride, const double *__restrict__ src, int64_t srcStride,
+                            int64_t nRows, int64_t nCols) {
+  const int64_t n = nRows * nCols, stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; x < n; x += stride) {
+    const int64_t r = x / nCols, c = x - r * nCols;
+    dst[r * dstStride + c] = src[r * srcStride + c];
+  }
+}
+void launch_copy_rows(double *dst, int64_t dstStride, const double *src, int64_t srcStride, int64_t nRows, int64_t nCols,
+                      cudaStream_t st) {
+  if (nRows <= 0 || nCols <= 0) return;
+  k_copy_rows<<<grid_for(nRows * nCols, 256), 256, 0, st>>>(dst, dstStride, src, srcStride, nRows, nCols);
+  count_launch();
+}
+__global__ void k_fill_rects(const FillRect *__restrict__ rects) {
+  const FillRect R = rects[blockIdx.y];
+  const int64_t n = R.nRows * R.nCols, stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; x < n; x += stride) {
+    const int64_t r = x / R.nCols, c = x - r * R.nCols;
+    R.base[(R.row0 + r) * R.stride + R.col0 + c] = R.value;
+  }
+}
+void launch_fill_rects(const FillRect *dRects, int64_t nRects, cudaStream_t st) {
+  for (int64_t r0 = 0; r0 < nRects; r0 += 32768) {     // grid.y limit
+    const int64_t nr = nRects - r0 < 32768 ? nRects - r0 : 32768;
+    k_fill_rects<<<dim3(64, (unsigned)nr), 256, 0, st>>>(dRects + r0);
+    count_launch();
+  }
+}
+__global__ void k_gather_kb(double *__restrict__ dst, int64_t dstStride, const double *__restrict__ src, int64_t srcStride,
+                            const int64_t *__restrict__ oldRow, int64_t nNewRows, int64_t rowsPer,
+                            const int64_t *__restrict__ oldCol, int64_t nNewCols, double padValue) {
+  const int64_t n = nNewRows * rowsPer * dstStride, stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; x < n; x += stride) {
+    const int64_t row = x / dstStride, j = x - row * dstStride;
+    const int64_t i = row / rowsPer, k = row - i * rowsPer;
+    dst[x] = j < nNewCols ? src[(oldRow[i] * rowsPer + k) * srcStride + oldCol[j]] : padValue;
+  }
+}
+void launch_gather_kb(double *dst, int64_t dstStride, const double *src, int64_t srcStride, const int64_t *dOldRow,
+                      int64_t nNewRows, int64_t rowsPer, const int64_t *dOldCol, int64_t nNewCols, double padValue,
+                      cudaStream_t st) {
+  if (nNewRows <= 0) return;
+  k_gather_kb<<<grid_for(nNewRows * rowsPer * dstStride, 256), 256, 0, st>>>(dst, dstStride, src, srcStride, dOldRow, nNewRows,
+                                                                            rowsPer, dOldCol, nNewCols, padValue);
+  count_launch();
+}
+
 __global__ void k_set_active(QuizPool qp, int64_t n, const int64_t *__restrict__ slots,
                              const int64_t *__restrict__ questions) {
   const int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -171,6 +171,23 @@ void launch_p2p_push_prior_rows(const DeviceKB &kb, const QuizPool &qp, int64_t 
 void launch_p2p_pull_prior_rows(const DeviceKB &kb, const QuizPool &qp, int64_t n, const int64_t *dSlots,
                                 const int64_t *dQuestions, const double *dRows, cudaStream_t st);
 
+// ---------------------------------------------------------------------------------------------------------
+// Maintenance (CpuEngine::AddQsTsSpec / CompactSpec, CpuEngine.cpp:468-658): KB resize, initial amounts, compaction.
+// dst[r*dstStride + c] = src[r*srcStride + c] for r < nRows, c < nCols
+void launch_copy_rows(double *dst, int64_t dstStride, const double *src, int64_t srcStride, int64_t nRows, int64_t nCols,
+                      cudaStream_t st);
+struct FillRect {           // base[(row0 + r)*stride + col0 + c] = value for r < nRows, c < nCols
+  double *base;
+  int64_t stride, row0, nRows, col0, nCols;
+  double value;
+};
+void launch_fill_rects(const FillRect *dRects, int64_t nRects, cudaStream_t st);
+// dst[(i*rowsPer + k)*dstStride + j] = src[(oldRow[i]*rowsPer + k)*srcStride + oldCol[j]] for i < nNewRows, j < nNewCols;
+// columns nNewCols .. dstStride-1 receive padValue
+void launch_gather_kb(double *dst, int64_t dstStride, const double *src, int64_t srcStride, const int64_t *dOldRow,
+                      int64_t nNewRows, int64_t rowsPer, const int64_t *dOldCol, int64_t nNewCols, double padValue,
+                      cudaStream_t st);
+
 void launch_gather_prior_rows(const QuizPool &qp, int64_t n, const int64_t *dSlots, double *dBuf, cudaStream_t st);
 void launch_scatter_prior_rows(const QuizPool &qp, int64_t n, const int64_t *dSlots, const double *dBuf, cudaStream_t st);
 void launch_set_active(const QuizPool &qp, int64_t n, const int64_t *dSlots, const int64_t *dQuestions, cudaStream_t st);

@@ -40,6 +40,11 @@ class CiRatedTarget(C.Structure):  # :32-35
     _fields_ = [("iTarget", C.c_int64), ("prob", C.c_double)]
 
 
+class CiAddQorTParam(C.Structure):  # :37-40
+    _pack_ = 8
+    _fields_ = [("index", C.c_int64), ("initAmount", C.c_double)]
+
+
 class CiB200Options(C.Structure):  # PqaB200Ext.h
     _pack_ = 8
     _fields_ = [("device", C.c_int32), ("emulatedWorkers", C.c_int32), ("rngSeed", C.c_uint64),
@@ -277,6 +282,10 @@ class PqaEngine:
         d = self.copy_dims()
         self.n_answers, self.n_questions, self.n_targets = d.n_answers, d.n_questions, d.n_targets
 
+    def _refresh_dims(self):
+        d = self.copy_dims()
+        self.n_answers, self.n_questions, self.n_targets = d.n_answers, d.n_questions, d.n_targets
+
     def __del__(self):
         self.close()
 
@@ -359,6 +368,74 @@ class PqaEngine:
 
     def save_kb(self, file_path: str, b_double_buffer: bool = False, throw: bool = True):
         return _raise_or_return(self._lib.PqaEngine_SaveKB(self.c_engine, file_path.encode(), int(b_double_buffer)), throw)
+
+    # maintenance mode and id maps: same names and shapes as ProbQA.py:634-720 / :560-632
+    def start_maintenance(self, force_quizzes: bool, throw: bool = True):
+        return _raise_or_return(self._lib.PqaEngine_StartMaintenance(self.c_engine, bool(force_quizzes)), throw)
+
+    def finish_maintenance(self, throw: bool = True):
+        err = _raise_or_return(self._lib.PqaEngine_FinishMaintenance(self.c_engine), throw)
+        self._refresh_dims()
+        return err
+
+    def add_qs_ts(self, question_init_amounts, target_init_amounts, throw: bool = True):
+        """Adds len(question_init_amounts) questions and len(target_init_amounts) targets; returns the compact ids they
+        received (removed ids are reused first), or the error when throw is False."""
+        nq, nt = len(question_init_amounts), len(target_init_amounts)
+        cq, ct = (CiAddQorTParam * max(nq, 1))(), (CiAddQorTParam * max(nt, 1))()
+        for i, a in enumerate(question_init_amounts):
+            cq[i].index, cq[i].initAmount = -1, float(a)
+        for i, a in enumerate(target_init_amounts):
+            ct[i].index, ct[i].initAmount = -1, float(a)
+        err = _raise_or_return(self._lib.PqaEngine_AddQsTs(self.c_engine, nq, C.cast(cq, C.c_void_p), nt, C.cast(ct, C.c_void_p)), throw)
+        if err is not None:
+            return err
+        self._refresh_dims()
+        return [cq[i].index for i in range(nq)], [ct[i].index for i in range(nt)]
+
+    def remove_questions(self, question_ids, throw: bool = True):
+        ids = _i64arr(question_ids)
+        return _raise_or_return(self._lib.PqaEngine_RemoveQuestions(self.c_engine, ids.size, _p(ids, _pi64)), throw)
+
+    def remove_targets(self, target_ids, throw: bool = True):
+        ids = _i64arr(target_ids)
+        return _raise_or_return(self._lib.PqaEngine_RemoveTargets(self.c_engine, ids.size, _p(ids, _pi64)), throw)
+
+    def compact(self):
+        """(old_questions, old_targets): new compact id -> the compact id it had before (ProbQA.py:700-720)."""
+        nq, nt = C.c_int64(), C.c_int64()
+        pq, pt = _pi64(), _pi64()
+        _raise_or_return(self._lib.PqaEngine_Compact(self.c_engine, C.byref(nq), C.byref(pq), C.byref(nt), C.byref(pt)))
+        try:
+            return [pq[i] for i in range(nq.value)], [pt[i] for i in range(nt.value)]
+        finally:
+            self._lib.CiReleaseCompaction(pq)
+            self._lib.CiReleaseCompaction(pt)
+            self._refresh_dims()
+
+    def _map_ids(self, fn, ids):
+        arr = _i64arr(ids).copy()
+        if not fn(self.c_engine, arr.size, _p(arr, _pi64)):
+            raise RuntimeError("id mapping failed")
+        return arr
+
+    def question_perm_from_comp(self, ids):
+        return self._map_ids(self._lib.PqaEngine_QuestionPermFromComp, ids)
+
+    def question_comp_from_perm(self, ids):
+        return self._map_ids(self._lib.PqaEngine_QuestionCompFromPerm, ids)
+
+    def target_perm_from_comp(self, ids):
+        return self._map_ids(self._lib.PqaEngine_TargetPermFromComp, ids)
+
+    def target_comp_from_perm(self, ids):
+        return self._map_ids(self._lib.PqaEngine_TargetCompFromPerm, ids)
+
+    def quiz_perm_from_comp(self, ids):
+        return self._map_ids(self._lib.PqaEngine_QuizPermFromComp, ids)
+
+    def quiz_comp_from_perm(self, ids):
+        return self._map_ids(self._lib.PqaEngine_QuizCompFromPerm, ids)
 
     def shutdown(self, save_file_path: str = None, throw: bool = True):
         p = save_file_path.encode() if save_file_path else None
