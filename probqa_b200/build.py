@@ -58,5 +58,20 @@ def build(force=False, verbose=False):
     return LIB_PATH
 
 
+CLIENT_SRC = os.path.join(os.path.dirname(_HERE), "clients", "pqa_client.cpp")
+CLIENT_PATH = os.path.join(LIB_DIR, "pqa_client")
+
+
+def build_client(force=False):
+    """clients/pqa_client.cpp (the reference's PqaClient learner loop over the C ABI) -> probqa_b200/lib/pqa_client."""
+    build()
+    hdr = os.path.join(os.path.dirname(_HERE), "include", "PqaCInterop.h")
+    if force or _stale(CLIENT_PATH, [CLIENT_SRC, hdr, LIB_PATH]):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-Wall", CLIENT_SRC, "-o", CLIENT_PATH, "-L" + LIB_DIR, "-lPqaCore",
+                               "-Wl,-rpath,$ORIGIN", "-lpthread"])
+    return CLIENT_PATH
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_client(force="--force" in sys.argv))
