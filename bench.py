@@ -38,6 +38,8 @@ WORKLOADS = {
     "10000x5x100000_b64": dict(Q=10000, K=5, T=100000, B=64),
     "10000x5x100000_b256": dict(Q=10000, K=5, T=100000, B=256),
     "2000x5x20000_b64": dict(Q=2000, K=5, T=20000, B=64),
+    "1000x5x1000_b64": dict(Q=1000, K=5, T=1000, B=64),
+    "1000x5x1000_b128": dict(Q=1000, K=5, T=1000, B=128),
     # small smoke size
     "200x5x500_b32": dict(Q=200, K=5, T=500, B=32),
 }

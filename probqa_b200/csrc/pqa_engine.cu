@@ -103,6 +103,16 @@ Engine::Engine(const CiEngineDefinition &def, const CiB200Options &opts) {
 
 Engine::~Engine() {
   if (stream_) cudaStreamSynchronize(stream_);
+  if (env_int("PQA_B200_STATS", 0) && statBatches_ > 0) {
+    static const char *names[6] = {"NextQuestion", "RecordAnswer", "ListTopTargets", "StartQuiz", "RecordQuizTarget", "ReleaseQuiz"};
+    fprintf(stderr, "[probqa_b200] combined batches: %llu, in-batch time %.3f s, gather-window time %.3f s\n",
+            (unsigned long long)statBatches_, statRunSec_, statGatherSec_);
+    for (int k = 0; k < 6; k++)
+      if (statCalls_[k])
+        fprintf(stderr, "[probqa_b200]   %-16s %10llu calls in %8llu launches (%.1f per launch)\n", names[k],
+                (unsigned long long)statCalls_[k], (unsigned long long)statKindLaunches_[k],
+                (double)statCalls_[k] / (double)statKindLaunches_[k]);
+  }
   cudaFree(dSA_); cudaFree(dMD_); cudaFree(dVB_); cudaFree(dLog2Tbl_);
   cudaFree(dPriors_); cudaFree(dLogPriors_); cudaFree(dAsked_); cudaFree(dActive_);
   for (int r = 0; r < kMaxPeers; r++) if (p2pOpened_[r]) cudaIpcCloseMemHandle(p2pPeer_[r]);
@@ -218,9 +228,12 @@ PqaError *Engine::StartQuizBatch(int64_t n, int64_t *pQuizIds) {
 }
 
 int64_t Engine::StartQuiz(PqaError **err) {
-  int64_t id = -1;
-  *err = StartQuizBatch(1, &id);
-  return *err ? -1 : id;
+  if (IsSharded()) { int64_t id = -1; *err = StartQuizBatch(1, &id); return *err ? -1 : id; }
+  if (maintenance_) { *err = WrongMode("Start/Resume quiz"); return -1; }
+  CallSlot s; s.kind = 3;
+  Submit(s);                    // combined with the concurrent one-quiz calls of other client threads
+  *err = s.err;
+  return s.err ? -1 : s.result;
 }
 
 // ResumeQuiz: BaseEngine::ResumeQuiz (BaseEngine.cpp:386-397) -> CpuEngine::ResumeQuizSpec (CpuEngine.cpp:277-282) ->
@@ -380,25 +393,83 @@ PqaError *Engine::NextQuestionBatch(int64_t n, const int64_t *pQuizIds, const ui
 void Engine::Submit(CallSlot &slot) {
   std::unique_lock<std::mutex> lk(combineMu_);
   combinePending_.push_back(&slot);
-  combineCv_.wait(lk, [&] { return slot.done || !combineLeader_; });
-  if (slot.done) return;
-  combineLeader_ = true;
-  while (!slot.done) {                       // at most two rounds: the batch in flight when we arrived, then ours
+  if (combineLeader_) {
+    if (gathering_) gatherCv_.notify_one();
+    // wait for this call's result, or for the leadership (every call has its own condition variable: finishing a batch
+    // wakes exactly the callers it served)
+    slot.cv.wait(lk, [&] { return slot.done || slot.lead; });
+    if (slot.done) return;
+  }
+  combineLeader_ = true;                     // this call is in combinePending_, so it is part of a batch below
+  while (!slot.done) {
+    // Callers that were served by the previous batch come back with their next call within microseconds of each other.
+    // When recent batches had company, give the cohort a short window to arrive instead of launching for the first one
+    // alone (a lone caller never waits: expectedBatch_ stays 1).
+    if (expectedBatch_ > 1 && combinePending_.size() < expectedBatch_) {
+      gathering_ = true;
+      const auto g0 = std::chrono::steady_clock::now();
+      gatherCv_.wait_for(lk, std::chrono::microseconds(120), [&] { return combinePending_.size() >= expectedBatch_; });
+      statGatherSec_ += std::chrono::duration<double>(std::chrono::steady_clock::now() - g0).count();
+      gathering_ = false;
+    }
     std::vector<CallSlot *> batch;
     batch.swap(combinePending_);
+    expectedBatch_ = std::max<size_t>(1, std::max(batch.size() - batch.size() / 8, expectedBatch_ - (expectedBatch_ + 3) / 4));
+    // NextQuestion is the expensive call and its cost hardly depends on the batch size, while clients drift apart (a
+    // client that finishes a quiz makes three cheap calls before its next NextQuestion). So when cheap calls are pending
+    // too, the NextQuestion calls are held back for up to three rounds: the cheap calls run at once, their callers come
+    // back with the next call, and the cohort meets again at one big NextQuestion launch.
+    size_t nNext = 0, nOther = 0;
+    int maxDefers = 0;
+    for (CallSlot *c : batch) {
+      if (c->kind == 0) { nNext++; maxDefers = std::max(maxDefers, c->defers); } else nOther++;
+    }
+    if (nNext > 0 && nOther > 0 && maxDefers < 3) {
+      std::vector<CallSlot *> now;
+      for (CallSlot *c : batch) {
+        if (c->kind == 0) { c->defers++; combinePending_.push_back(c); } else now.push_back(c);
+      }
+      batch.swap(now);
+    }
     lk.unlock();
+    const auto r0 = std::chrono::steady_clock::now();
     RunCombined(batch);
     lk.lock();
-    for (CallSlot *c : batch) c->done = true;
-    combineCv_.notify_all();
+    statRunSec_ += std::chrono::duration<double>(std::chrono::steady_clock::now() - r0).count();
+    statBatches_++;
+    {
+      bool seen[6] = {};
+      for (CallSlot *c : batch) { statCalls_[c->kind]++; seen[c->kind] = true; }
+      for (int k = 0; k < 6; k++) statKindLaunches_[k] += seen[k];
+    }
+    for (CallSlot *c : batch) {
+      c->done = true;
+      if (c != &slot) c->cv.notify_one();
+    }
   }
-  combineLeader_ = false;
-  combineCv_.notify_all();                    // a waiter whose call is still pending takes over
+  if (!combinePending_.empty()) {            // hand the leadership to a caller that arrived meanwhile
+    combinePending_.front()->lead = true;
+    combinePending_.front()->cv.notify_one();
+  } else {
+    combineLeader_ = false;
+  }
 }
 
 void Engine::RunCombined(const std::vector<CallSlot *> &batch) {
   std::vector<int64_t> ids, args;
   std::vector<CallSlot *> who;
+  // ---- StartQuiz: one launch for all new quizzes
+  for (CallSlot *c : batch) if (c->kind == 3) who.push_back(c);
+  if (!who.empty()) {
+    ids.assign(who.size(), -1);
+    PqaError *e = StartQuizBatch((int64_t)ids.size(), ids.data());
+    for (size_t x = 0; x < who.size(); x++) {
+      who[x]->result = e ? -1 : ids[x];
+      if (e) who[x]->err = new PqaError(*e);
+    }
+    delete e;
+    ids.clear(); who.clear();
+  }
   // ---- NextQuestion: per-call errors come back through ppErrors
   for (CallSlot *c : batch) if (c->kind == 0) { ids.push_back(c->quiz); who.push_back(c); }
   if (!ids.empty()) {
@@ -450,6 +521,26 @@ void Engine::RunCombined(const std::vector<CallSlot *> &batch) {
     delete e;
     tops.swap(rest);
   }
+  // ---- RecordQuizTarget: each call validated on its own, then applied in arrival order by one launch
+  ids.clear(); args.clear(); who.clear();
+  std::vector<double> amounts;
+  for (CallSlot *c : batch) if (c->kind == 4) {
+    PqaError *e = nullptr;
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      if (c->arg < 0 || c->arg >= T_) e = ErrIndexOutOfRange(c->arg, 0, T_ - 1, PQA_FILE_LINE "Target index is not in KB range.");
+      else if (tGaps_.IsGap(c->arg)) e = ErrAbsentId(c->arg, PQA_FILE_LINE "Target index is not in KB (but rather at a gap).");
+      else e = CheckQuiz(c->quiz);
+    }
+    if (e) { c->err = e; continue; }
+    ids.push_back(c->quiz); args.push_back(c->arg); amounts.push_back(c->amount); who.push_back(c);
+  }
+  if (!ids.empty()) {
+    PqaError *e = RecordQuizTargetBatch((int64_t)ids.size(), ids.data(), args.data(), amounts.data());
+    if (e) { for (CallSlot *c : who) c->err = new PqaError(*e); delete e; }
+  }
+  // ---- ReleaseQuiz
+  for (CallSlot *c : batch) if (c->kind == 5) c->err = ReleaseQuizBatch(1, &c->quiz);
 }
 
 int64_t Engine::NextQuestion(PqaError **err, int64_t iQuiz) {
@@ -814,7 +905,12 @@ PqaError *Engine::RecordQuizTargetBatch(int64_t n, const int64_t *pQuizIds, cons
 }
 
 PqaError *Engine::RecordQuizTarget(int64_t iQuiz, int64_t iTarget, double amount) {
-  return RecordQuizTargetBatch(1, &iQuiz, &iTarget, &amount);
+  if (IsSharded()) return RecordQuizTargetBatch(1, &iQuiz, &iTarget, &amount);
+  if (!(amount > 0)) return ErrNonPositiveAmount(amount, PQA_FILE_LINE "|amount| must be positive.");   // BaseEngine.cpp:530-533
+  if (maintenance_) return WrongMode("record quiz target");
+  CallSlot s; s.kind = 4; s.quiz = iQuiz; s.arg = iTarget; s.amount = amount;
+  Submit(s);
+  return s.err;
 }
 
 // BaseEngine::Train (BaseEngine.cpp:235-250) -> CpuEngine::TrainSpec (CpuEngine.cpp:102-183): answered questions
@@ -878,7 +974,13 @@ PqaError *Engine::ReleaseQuizBatch(int64_t n, const int64_t *pQuizIds) {
   if (residentN_ > 0) residentN_ = 0;  // a released quiz may be part of the bound batch
   return nullptr;
 }
-PqaError *Engine::ReleaseQuiz(int64_t iQuiz) { return ReleaseQuizBatch(1, &iQuiz); }
+PqaError *Engine::ReleaseQuiz(int64_t iQuiz) {
+  if (IsSharded()) return ReleaseQuizBatch(1, &iQuiz);
+  if (maintenance_) return WrongMode("release quiz");
+  CallSlot s; s.kind = 5; s.quiz = iQuiz;
+  Submit(s);
+  return s.err;
+}
 
 // ---------------------------------------------------------------------------------------------------------
 // IPqaEngine::CopyATargets / CopyDTargets / CopyBTargets (Interface/IPqaEngine.h:36-39, CpuEngine.cpp:690-709)

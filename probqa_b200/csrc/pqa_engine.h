@@ -125,12 +125,15 @@ struct HostQuiz {                      // BaseQuiz.h:13-36 (host part); priors a
 // One pending one-quiz call (NextQuestion / RecordAnswer / ListTopTargets) waiting to be combined with the calls other
 // client threads make at the same time.
 struct CallSlot {
-  int kind = 0;                 // 0 NextQuestion, 1 RecordAnswer, 2 ListTopTargets
-  int64_t quiz = -1, arg = 0;   // arg: answer (kind 1) or maxCount (kind 2)
+  int kind = 0;                 // 0 NextQuestion, 1 RecordAnswer, 2 ListTopTargets, 3 StartQuiz, 4 RecordQuizTarget, 5 ReleaseQuiz
+  int64_t quiz = -1, arg = 0;   // arg: answer (kind 1), maxCount (kind 2) or target (kind 4)
+  double amount = 1.0;          // kind 4
   CiRatedTarget *dest = nullptr;
   int64_t result = -1;
   PqaError *err = nullptr;
-  bool done = false;
+  int defers = 0;                    // rounds this NextQuestion call was held back to let the cheap calls catch up
+  bool done = false, lead = false;   // lead: the previous leader handed the leadership to this (still pending) call
+  std::condition_variable cv;        // signalled for this call only (with Engine::combineMu_)
 };
 
 class Engine {
@@ -257,9 +260,13 @@ class Engine {
 
   mutable std::mutex mu_;
   std::mutex combineMu_;
-  std::condition_variable combineCv_;
   std::vector<CallSlot *> combinePending_;
-  bool combineLeader_ = false;
+  std::condition_variable gatherCv_;   // the leader waits here (briefly) for the rest of a cohort of concurrent callers
+  bool combineLeader_ = false, gathering_ = false;
+  // PQA_B200_STATS=1: combining statistics printed to stderr when the engine is released
+  uint64_t statBatches_ = 0, statCalls_[6] = {}, statKindLaunches_[6] = {};
+  double statRunSec_ = 0, statGatherSec_ = 0;
+  size_t expectedBatch_ = 1;           // recent batch size: how many concurrent callers a leader may expect to show up
   int device_ = 0, W_ = 1, smCount_ = 148;
   int64_t Q_ = 0, K_ = 0, T_ = 0, Tp_ = 0, askedWords_ = 0;
   int64_t qFirst_ = 0, qLocal_ = 0;   // question shard held by this engine (0, Q_ for a single-device engine)
