@@ -831,6 +831,23 @@ PqaError *Engine::ApplyTrain(const std::vector<TrainOp> &opsAll, const std::vect
   }
   const std::vector<TrainOp> &ops = IsSharded() ? owned : opsAll;
   const int64_t nOps = (int64_t)ops.size();
+  const int64_t nT = (int64_t)targets.size();
+  const int64_t kDeviceGrouping = 8192;   // from here on the grouping by cell is a device radix sort (pqa_train_sort.cu)
+  if (nOps >= kDeviceGrouping) {
+    const size_t need = std::max(train_sort_scratch_bytes(nOps), train_sort_scratch_bytes(nT));
+    dSortScratch_.ensure(need, stream_);
+    dOps_.ensure(nOps, stream_);
+    PQA_CU(cudaMemcpyAsync(dOps_.get(), ops.data(), sizeof(TrainOp) * (size_t)nOps, cudaMemcpyHostToDevice, stream_));
+    launch_train_ops_device_grouped(kb(), dOps_.get(), nOps, dSortScratch_.get(), dSortScratch_.size(), stream_);
+    if (nT > 0) {
+      dTargets_.ensure(nT, stream_); dAmounts_.ensure(nT, stream_);
+      PQA_CU(cudaMemcpyAsync(dTargets_.get(), targets.data(), sizeof(int64_t) * (size_t)nT, cudaMemcpyHostToDevice, stream_));
+      PQA_CU(cudaMemcpyAsync(dAmounts_.get(), amounts.data(), sizeof(double) * (size_t)nT, cudaMemcpyHostToDevice, stream_));
+      launch_add_vb_device_grouped(kbQuiz(), dTargets_.get(), dAmounts_.get(), nT, dSortScratch_.get(), dSortScratch_.size(), stream_);
+    }
+    PQA_CU(cudaStreamSynchronize(stream_));   // the host vectors die at scope end
+    return nullptr;
+  }
   if (nOps > 0) {
     std::vector<int64_t> order(nOps);
     std::iota(order.begin(), order.end(), 0);
@@ -850,7 +867,6 @@ PqaError *Engine::ApplyTrain(const std::vector<TrainOp> &opsAll, const std::vect
     launch_train_ops(kb(), dOps_.get(), dGroupStart_.get(), nGroups, stream_);
     PQA_CU(cudaStreamSynchronize(stream_));  // the staging vectors die at scope end
   }
-  const int64_t nT = (int64_t)targets.size();
   if (nT > 0) {
     std::vector<int64_t> order(nT);
     std::iota(order.begin(), order.end(), 0);

@@ -310,6 +310,7 @@ class Engine {
   DevBuf<double> dPriority_, dRunLength_, dGrand_, dDetail_, dAmounts_, dRowScratch_;
   DevBuf<CiRatedTarget> dTop_, dTopScratch_;
   DevBuf<TrainOp> dOps_;
+  DevBuf<uint8_t> dSortScratch_;
   PinBuf<int64_t> hIds_, hAnswers_, hQuestions_, hCounts_;
   PinBuf<uint64_t> hRandoms_;
   PinBuf<CiRatedTarget> hTop_;

@@ -188,6 +188,14 @@ void launch_gather_kb(double *dst, int64_t dstStride, const double *src, int64_t
                       int64_t nNewRows, int64_t rowsPer, const int64_t *dOldCol, int64_t nNewCols, double padValue,
                       cudaStream_t st);
 
+// Device-grouped forms for large batches (pqa_train_sort.cu): operations / (target, amount) pairs arrive in sequence
+// order, a stable radix sort by cell groups them on the device. Same results as the host-grouped launchers above.
+size_t train_sort_scratch_bytes(int64_t n);
+void launch_train_ops_device_grouped(const DeviceKB &kb, const TrainOp *dOps, int64_t nOps, void *dScratch,
+                                     size_t scratchBytes, cudaStream_t st);
+void launch_add_vb_device_grouped(const DeviceKB &kb, const int64_t *dTargets, const double *dAmounts, int64_t n,
+                                  void *dScratch, size_t scratchBytes, cudaStream_t st);
+
 void launch_gather_prior_rows(const QuizPool &qp, int64_t n, const int64_t *dSlots, double *dBuf, cudaStream_t st);
 void launch_scatter_prior_rows(const QuizPool &qp, int64_t n, const int64_t *dSlots, const double *dBuf, cudaStream_t st);
 void launch_set_active(const QuizPool &qp, int64_t n, const int64_t *dSlots, const int64_t *dQuestions, cudaStream_t st);

@@ -314,6 +314,30 @@ def test_record_quiz_target_and_train_bit_exact(pqa, ora):
     assert np.array_equal(bits(gA), bits(sA)) and np.array_equal(bits(gD), bits(mD)) and np.array_equal(bits(gB), bits(vB))
 
 
+def test_large_record_quiz_target_batch_device_grouped(pqa, ora):
+    """A batch big enough (>= 8192 cell operations) to take the device-grouped path (radix sort by cell, pqa_train_sort.cu)
+    with heavy cell collisions: the KB must equal the oracle applying the quizzes one by one, bit for bit."""
+    Q, K, T, W = 40, 5, 64, 4
+    kb = synth.gamma_kb(Q, K, T, INIT)
+    sA, mD, vB = [a.copy() for a in kb]
+    eng = make_engine(pqa, Q, K, T, W, kb)
+    rng = np.random.default_rng(8)
+    n, d = 1800, 6
+    quizzes = eng.start_quiz_batch(n)
+    qs = np.argsort(rng.random((n, Q)), axis=1)[:, :d]
+    ans = rng.integers(0, K, size=(n, d))
+    for s_ in range(d):
+        eng.set_active_question_batch(quizzes, qs[:, s_])
+        eng.record_answer_batch(quizzes, ans[:, s_])
+    targets = rng.integers(0, T, size=n)
+    amounts = rng.choice([1.0, 0.5, 2.25], size=n)
+    eng.record_quiz_target_batch(quizzes, targets, amounts)
+    for x in range(n):
+        ora.record_quiz_target(sA, mD, vB, list(zip(qs[x].tolist(), ans[x].tolist())), int(targets[x]), float(amounts[x]))
+    gA, gD, gB = eng.download_kb()
+    assert np.array_equal(bits(gA), bits(sA)) and np.array_equal(bits(gD), bits(mD)) and np.array_equal(bits(gB), bits(vB))
+
+
 def test_initial_kb_and_dims(pqa):
     """Dimensions.CpuIncrease-style check (PqaCoreTests/Dimensions.cpp:62-77): A = init^2, D = K*init^2, B = init."""
     Q, K, T = 7, 5, 203
