@@ -159,9 +159,8 @@ PQACORE_API void *PqaEngine_RecordAnswer(void *pvEngine, const int64_t iQuiz, co
   return Ret(E(pvEngine)->RecordAnswer(iQuiz, iAnswer));
 }
 PQACORE_API void *PqaEngine_ClearOldQuizzes(void *pvEngine, const int64_t maxCount, const double maxAgeSec) {
-  (void)maxCount; (void)maxAgeSec;
   if (!pvEngine) return NullEngine();
-  return ErrNotImplemented("B200 engine: ClearOldQuizzes (BaseEngine.cpp) -- quiz ageing is outside the hot-path scope");
+  return Ret(Guard([&] { return E(pvEngine)->ClearOldQuizzes(maxCount, maxAgeSec); }));
 }
 PQACORE_API int64_t PqaEngine_GetActiveQuestionId(void *pvEngine, void **ppError, const int64_t iQuiz) {
   if (!pvEngine) { Assign(ppError, NullEngine()); return -1; }

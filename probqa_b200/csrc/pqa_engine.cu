@@ -182,6 +182,7 @@ PqaError *Engine::CheckQuiz(int64_t iQuiz) const {
     return ErrIndexOutOfRange(iQuiz, 0, nQuizzes - 1, PQA_FILE_LINE "Quiz index is not in quiz registry range.");
   if (!quizzes_[iQuiz].present)
     return ErrAbsentId(iQuiz, PQA_FILE_LINE "Quiz index is not in the registry (but rather at a gap).");
+  quizzes_[iQuiz].lastUsage = std::time(nullptr);   // BaseQuiz::OnUsage, BaseEngine.cpp:416
   return nullptr;
 }
 
@@ -191,6 +192,7 @@ int64_t Engine::AssignQuizId() {
   else { id = (int64_t)quizzes_.size(); quizzes_.emplace_back(); pimQuiz_.GrowTo((int64_t)quizzes_.size()); }
   HostQuiz &q = quizzes_[id];
   q.present = true; q.activeQuestion = -1; q.answers.clear();
+  q.lastUsage = std::time(nullptr);
   return id;
 }
 

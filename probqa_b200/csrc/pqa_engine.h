@@ -15,6 +15,7 @@
 #include <unordered_map>
 #include <vector>
 #include <cstdio>
+#include <ctime>
 
 #include "../../include/PqaB200Ext.h"
 #include "pqa_errors.h"
@@ -120,6 +121,7 @@ struct HostQuiz {                      // BaseQuiz.h:13-36 (host part); priors a
   bool present = false;
   int64_t activeQuestion = -1;
   std::vector<CiAnsweredQuestion> answers;
+  mutable time_t lastUsage = 0;        // BaseQuiz::_lastUsage (BaseQuiz.h:21,34): refreshed by every call that uses the quiz
 };
 
 // One pending one-quiz call (NextQuestion / RecordAnswer / ListTopTargets) waiting to be combined with the calls other
@@ -161,6 +163,7 @@ class Engine {
   static Engine *LoadKB(const char *filePath, const CiB200Options &opts, PqaError **err);
 
   // --- maintenance mode (BaseEngine.cpp:640-779, CpuEngine.cpp:468-658) and id maps (BaseEngine.cpp:154-218) ---
+  PqaError *ClearOldQuizzes(int64_t maxCount, double maxAgeSec);   // BaseEngine.cpp:814-872
   PqaError *StartMaintenance(bool forceQuizzes);
   PqaError *FinishMaintenance();
   PqaError *AddQsTs(int64_t nQuestions, CiAddQorTParam *pAqps, int64_t nTargets, CiAddQorTParam *pAtps);

@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <cstring>
+#include <ctime>
 #include <memory>
 
 namespace pqa {
@@ -158,6 +159,42 @@ void Engine::DropQuizPool() {
     quizCap_ = 0;
   }
   residentN_ = 0;
+}
+
+// BaseEngine::ClearOldQuizzes (BaseEngine.cpp:814-872): quizzes idle for more than maxAgeSec are released; if more than
+// maxCount remain, the oldest are released until maxCount are left. A no-op outside regular mode.
+PqaError *Engine::ClearOldQuizzes(int64_t maxCount, double maxAgeSec) {
+  if (maxCount < 0) return ErrNegativeCount(maxCount, PQA_FILE_LINE "The number of quizzes to keep cannot be less than 0.");
+  if (maintenance_) return nullptr;
+  std::lock_guard<std::mutex> lk(mu_);
+  struct QuizAge {
+    int64_t iQuiz; double ageSec;
+    bool operator<(const QuizAge &o) const { return ageSec < o.ageSec; }
+  };
+  std::vector<QuizAge> ages;
+  const time_t callTime = std::time(nullptr);
+  auto release = [&](int64_t i) {                          // LockedReleaseQuiz, :803-812
+    HostQuiz &q = quizzes_[(size_t)i];
+    q.present = false; q.answers.clear(); q.answers.shrink_to_fit(); q.activeQuestion = -1;
+    quizGaps_.push_back(i);
+    pimQuiz_.RemoveComp(i);
+  };
+  for (int64_t i = 0; i < (int64_t)quizzes_.size(); i++) {
+    if (!quizzes_[(size_t)i].present) continue;
+    const double ageSec = std::difftime(callTime, quizzes_[(size_t)i].lastUsage);
+    if (ageSec > maxAgeSec) { release(i); continue; }
+    ages.push_back(QuizAge{i, ageSec});
+  }
+  if ((int64_t)ages.size() > maxCount) {
+    std::make_heap(ages.begin(), ages.end());
+    while ((int64_t)ages.size() > maxCount) {
+      release(ages.front().iQuiz);
+      std::pop_heap(ages.begin(), ages.end());
+      ages.pop_back();
+    }
+  }
+  residentN_ = 0;
+  return nullptr;
 }
 
 // BaseEngine::StartMaintenance (BaseEngine.cpp:640-683): with quizzes alive it either destroys them all

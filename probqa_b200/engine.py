@@ -366,6 +366,10 @@ class PqaEngine:
     def release_quiz(self, i_quiz: int, throw: bool = True):
         return _raise_or_return(self._lib.PqaEngine_ReleaseQuiz(self.c_engine, i_quiz), throw)
 
+    def clear_old_quizzes(self, max_count: int, max_age_sec: float, throw: bool = True):
+        """ProbQA.py clear_old_quizzes: releases quizzes idle for more than max_age_sec, then the oldest beyond max_count."""
+        return _raise_or_return(self._lib.PqaEngine_ClearOldQuizzes(self.c_engine, max_count, float(max_age_sec)), throw)
+
     def save_kb(self, file_path: str, b_double_buffer: bool = False, throw: bool = True):
         return _raise_or_return(self._lib.PqaEngine_SaveKB(self.c_engine, file_path.encode(), int(b_double_buffer)), throw)
 

@@ -290,3 +290,32 @@ def test_kb_file_with_gaps_roundtrip(pqa, ora, tmp_path):
     eng2.start_maintenance(True)
     got_q, got_t = eng2.add_qs_ts([1.0], [1.0, 1.0])
     assert got_q == [7] and got_t == [3, 17]                               # the loaded gap lists keep their LIFO order
+
+
+def test_clear_old_quizzes(pqa):
+    """BaseEngine::ClearOldQuizzes (BaseEngine.cpp:814-872): age limit first, then the oldest quizzes beyond maxCount."""
+    import time
+    eng = make_engine(pqa, 6, 3, 9, 2)
+    old = [eng.start_quiz() for _ in range(3)]
+    time.sleep(2.1)
+    young = [eng.start_quiz() for _ in range(4)]
+    eng.next_question(old[1])                       # using a quiz refreshes its age
+    with pytest.raises(pqa.PqaException):
+        eng.clear_old_quizzes(-1, 10.0)
+    eng.clear_old_quizzes(100, 1.5)                 # older than 1.5 s: old[0] and old[2]
+    for q in (old[0], old[2]):
+        with pytest.raises(pqa.PqaException):
+            eng.next_question(q)
+    for q in [old[1]] + young:
+        eng.list_top_targets(q, 2)
+    eng.clear_old_quizzes(2, 1e9)                   # keep at most two
+    alive = 0
+    for q in [old[1]] + young:
+        try:
+            eng.list_top_targets(q, 2)
+            alive += 1
+        except pqa.PqaException:
+            pass
+    assert alive == 2
+    eng.start_maintenance(True)
+    assert eng.clear_old_quizzes(0, 0.0, throw=False) is None      # a no-op outside regular mode
