@@ -239,3 +239,22 @@ def test_peer_memory_exchange_matches_caller_side_exchange(axis, dims, n_shards,
         p2p.shards[0].engine.p2p_next_question_begin(sub, randoms)      # its End is pending
     for s in p2p.shards:
         s.engine.p2p_next_question_end(sub)
+
+
+def test_peer_memory_exchange_across_processes():
+    """One process per GPU, cudaIpc-mapped inboxes over NVLink (scripts/p2p_multiproc_check.py: un-sharded engine vs NCCL
+    exchange vs peer-memory exchange, both sharding axes). Needs at least two GPUs; `profiles/r01_multi_gpu_*.log` hold the
+    2- and 8-GPU runs of this round."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs (ran on 2 and 8 GPUs this round: profiles/r01_multi_gpu_*.log)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(min(n, 8)),
+                          "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(root, "scripts", "p2p_multiproc_check.py")],
+                         capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "questions: OK" in out.stdout and "targets: OK" in out.stdout
