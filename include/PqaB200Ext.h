@@ -151,6 +151,13 @@ PQACORE_API void *PqaB200_P2PNextQuestionBegin(void *pvEngine, int64_t n, const 
 PQACORE_API void *PqaB200_P2PNextQuestionEnd(void *pvEngine, int64_t n, const int64_t *pQuizIds, int64_t *pQuestions, void **ppErrors);
 PQACORE_API void *PqaB200_P2PRecordAnswerBegin(void *pvEngine, int64_t n, const int64_t *pQuizIds, const int64_t *pAnswers);
 PQACORE_API void *PqaB200_P2PRecordAnswerEnd(void *pvEngine);
+/* Target shards only. on != 0: the evaluation's first phase becomes a pipeline in target order -- the 4-lane Kahan state of
+ * every (quiz, question, answer) is handed from shard to shard through the inboxes, tile of questions by tile, and the
+ * last shard finishes the reference's own sum and publishes W_k to all shards. W_k is then bit-identical to a single
+ * engine's (and CpuEngine's), so posteriors inside the evaluation are too and priorities meet the single-engine bar
+ * (2e-12) instead of the summed-partials bar. Costs the pipeline fill: (shards-1)/tiles of phase 1. Same setting on every
+ * shard. */
+PQACORE_API void *PqaB200_P2PSetExactOrder(void *pvEngine, int32_t on);
 
 /* ---- device-resident stepping and timing (bench.py "value" leg: no host<->device traffic inside) ---- */
 /* Binds n quizzes as the resident batch: ids and one random draw per quiz are copied to the device once. */

@@ -403,6 +403,10 @@ PQACORE_API void *PqaB200_P2PRecordAnswerEnd(void *pvEngine) {
   if (!pvEngine) return NullEngine();
   return Ret(E(pvEngine)->P2PRecordAnswerEnd());
 }
+PQACORE_API void *PqaB200_P2PSetExactOrder(void *pvEngine, int32_t on) {
+  if (!pvEngine) return NullEngine();
+  return Ret(E(pvEngine)->P2PSetExactOrder(on));
+}
 PQACORE_API void *PqaB200_ResidentBind(void *pvEngine, int64_t n, const int64_t *pQuizIds, const uint64_t *pRandoms) {
   if (!pvEngine) return NullEngine();
   return Ret(E(pvEngine)->ResidentBind(n, pQuizIds, pRandoms));

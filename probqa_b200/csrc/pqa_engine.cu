@@ -1307,10 +1307,24 @@ PqaError *Engine::TShardPriority(int64_t n, const int64_t *pQuizIds) {
 // Shard exchange over peer memory. Inbox layout (identical on every shard; [2] = parity of the operation counter, so a
 // shard that runs ahead into the next operation never overwrites what a slower shard is still reading):
 //   0    flags[kMaxPeers] u64 (last epoch published by each rank)    64   error flag
+//   1024 hand-over flags [kP2PMaxTiles] u64 (exact-order pipeline: the previous shard finished tile t of operation e)
+//   16384 W-ready flags  [kP2PMaxTiles] u64 (the last shard published the complete W_k of tile t)
+//   state [2][cap*Q*K*8]             Kahan lanes handed over by the previous shard               (target shards)
 //   W    [2][nRanks][cap*Q*K]        partial normalisers, slot r written by shard r        (target shards)
 //   HVL  [2][nRanks][cap*Q*(2K+1)]   partial H/V/lack sums, slot r written by shard r      (target shards)
 //   rows [2][cap*Tp]                 RecordAnswer rows: disjoint column slices (target shards) / owner's row (question shards)
 //   pri  [2][cap*Q]                  priorities: disjoint question columns                 (question shards)
+static const int64_t kP2PMaxTiles = 1920;                         // 15 KB of flag words per array
+static const size_t kP2PHeaderBytes = 32768, kP2POffHandOver = 1024, kP2POffWReady = 16384;
+
+PqaError *Engine::P2PSetExactOrder(int32_t on) {
+  std::lock_guard<std::mutex> lk(mu_);
+  if (!IsTargetSharded()) return ErrNotImplemented("exact-order pipeline on an engine without a target shard (question shards are exact already)");
+  if (p2pPending_) return MakeError(ErrCode::WrongMode, PQA_FILE_LINE "a P2P operation is pending");
+  p2pExactOrder_ = on != 0;
+  return nullptr;
+}
+
 PqaError *Engine::P2PInit(int32_t rank, int32_t nRanks, int64_t maxQuizzes, void **ppBase, int64_t *pBytes) {
   if (nRanks < 1 || nRanks > kMaxPeers) return ErrIndexOutOfRange(nRanks, 1, kMaxPeers, PQA_FILE_LINE "nRanks");
   if (rank < 0 || rank >= nRanks) return ErrIndexOutOfRange(rank, 0, nRanks - 1, PQA_FILE_LINE "rank");
@@ -1326,11 +1340,17 @@ PqaError *Engine::P2PInit(int32_t rank, int32_t nRanks, int64_t maxQuizzes, void
   p2pSzHVL_ = ts ? up(sizeof(double) * (size_t)(maxQuizzes * Q_ * (2 * K_ + 1))) : 0;
   p2pSzRows_ = up(sizeof(double) * (size_t)(maxQuizzes * Tp_));
   p2pSzPri_ = ts ? 0 : up(sizeof(double) * (size_t)(maxQuizzes * Q_));
-  p2pOffW_ = 256;
+  p2pSzState_ = ts ? up(sizeof(double) * (size_t)(maxQuizzes * Q_ * K_ * 8)) : 0;
+  p2pOffW_ = kP2PHeaderBytes;
   p2pOffHVL_ = p2pOffW_ + 2 * (size_t)nRanks * p2pSzW_;
   p2pOffRows_ = p2pOffHVL_ + 2 * (size_t)nRanks * p2pSzHVL_;
   p2pOffPri_ = p2pOffRows_ + 2 * p2pSzRows_;
-  p2pBytes_ = p2pOffPri_ + 2 * p2pSzPri_;
+  p2pOffState_ = p2pOffPri_ + 2 * p2pSzPri_;
+  p2pBytes_ = p2pOffState_ + 2 * p2pSzState_;
+  if (ts) {
+    dTileCounters_.ensure((size_t)kP2PMaxTiles, stream_);
+    PQA_CU(cudaMemsetAsync(dTileCounters_.get(), 0, sizeof(unsigned) * (size_t)kP2PMaxTiles, stream_));
+  }
   PQA_CU(cudaMalloc(&p2pInbox_, p2pBytes_));
   PQA_CU(cudaMemsetAsync(p2pInbox_, 0, p2pBytes_, stream_));
   preload_exchange_kernels((int)K_);
@@ -1388,6 +1408,7 @@ PqaError *Engine::P2PConnect(void *const *pBases) {
     // inboxes of other devices in this process need peer access; IPC-opened ones got it when they were opened
     cudaPointerAttributes at;
     PQA_CU(cudaPointerGetAttributes(&at, pBases[r]));
+    if (at.device == device_) p2pSameDevicePeer_ = true;
     if (at.device != device_) {
       PQA_CU(cudaSetDevice(device_));
       const cudaError_t e = cudaDeviceEnablePeerAccess(at.device, 0);
@@ -1451,9 +1472,46 @@ PqaError *Engine::P2PNextQuestionBegin(int64_t n, const int64_t *pQuizIds, const
       outHVL.p[r] = (double *)(p2pPeer_[r] + p2pOffHVL_ + (par * p2pRanks_ + p2pRank_) * p2pSzHVL_);
       inHVL.p[r] = (double *)(p2pInbox_ + p2pOffHVL_ + (par * p2pRanks_ + r) * p2pSzHVL_);
     }
-    launch_eval_tshard_w(kb(), pool(), tFirst_, n, dIds_.get(), outW, evalCfg_, stream_);   // partial W_k -> every inbox
-    launch_p2p_barrier(flags, ++p2pEpoch_, kP2PTimeoutNs, stream_);
-    launch_eval_tshard_hvl(kb(), pool(), tFirst_, n, dIds_.get(), inW, outHVL, evalCfg_, stream_);
+    if (!p2pExactOrder_ || p2pRanks_ == 1) {
+      launch_eval_tshard_w(kb(), pool(), tFirst_, n, dIds_.get(), outW, evalCfg_, stream_);   // partial W_k -> every inbox
+      launch_p2p_barrier(flags, ++p2pEpoch_, kP2PTimeoutNs, stream_);
+      launch_eval_tshard_hvl(kb(), pool(), tFirst_, n, dIds_.get(), inW, outHVL, evalCfg_, stream_);
+    } else {
+      // Exact-order pipeline: the Kahan lanes travel shard 0 -> 1 -> ... -> N-1 tile by tile (tiles of consecutive
+      // questions, about two waves of CTAs each); shard N-1 finishes the reference's own sum and publishes W_k to every
+      // shard, whose phase-2 CTAs wait per tile. All waiting and signalling happens inside the two kernels.
+      const uint64_t opEpoch = p2pOps_;                      // identical on all shards, grows with every operation
+      const int64_t gridY = tshard_quiz_tiles(n);
+      int64_t tileQ = std::max<int64_t>(1, (2 * (int64_t)smCount_ + gridY - 1) / gridY);
+      if ((Q_ + tileQ - 1) / tileQ > kP2PMaxTiles) tileQ = (Q_ + kP2PMaxTiles - 1) / kP2PMaxTiles;
+      const bool first = p2pRank_ == 0, last = p2pRank_ == p2pRanks_ - 1;
+      PipeCtl p1;
+      p1.tileQ = tileQ; p1.epoch = opEpoch; p1.timeoutNs = kP2PTimeoutNs; p1.errFlag = (uint64_t *)(p2pInbox_ + 64);
+      p1.tileCounters = dTileCounters_.get();
+      p1.waitFlags = first ? nullptr : (const uint64_t *)(p2pInbox_ + kP2POffHandOver);
+      if (last) {
+        for (int r = 0; r < p2pRanks_; r++) p1.signalFlags[p1.nSignal++] = (uint64_t *)(p2pPeer_[r] + kP2POffWReady);
+      } else {
+        p1.signalFlags[p1.nSignal++] = (uint64_t *)(p2pPeer_[p2pRank_ + 1] + kP2POffHandOver);
+      }
+      const double *inState = first ? nullptr : (const double *)(p2pInbox_ + p2pOffState_ + par * p2pSzState_);
+      double *outState = last ? nullptr : (double *)(p2pPeer_[p2pRank_ + 1] + p2pOffState_ + par * p2pSzState_);
+      PeerBufs wAll;                                        // the complete W_k lives in slot 0 of every inbox
+      if (last) { wAll.n = p2pRanks_; for (int r = 0; r < p2pRanks_; r++) wAll.p[r] = (double *)(p2pPeer_[r] + p2pOffW_ + (par * p2pRanks_) * p2pSzW_); }
+      launch_eval_tshard_w(kb(), pool(), tFirst_, n, dIds_.get(), wAll, evalCfg_, stream_, inState, outState, &p1);
+      PipeCtl p2;
+      p2.tileQ = tileQ; p2.epoch = opEpoch; p2.timeoutNs = kP2PTimeoutNs; p2.errFlag = p1.errFlag;
+      p2.waitFlags = (const uint64_t *)(p2pInbox_ + kP2POffWReady);
+      inW.n = 1;                                            // slot 0 = the complete W_k (inHVL still sums all shards)
+      if (p2pSameDevicePeer_) {
+        // several shard engines share this GPU (tests): phase-2 CTAs that spin for W_k would occupy the SMs the other
+        // engines' phase 1 needs, so a one-CTA kernel waits for all tiles instead
+        const int64_t nTiles = (Q_ + tileQ - 1) / tileQ;
+        launch_p2p_wait(p2.waitFlags, (int)nTiles, opEpoch, p1.errFlag, kP2PTimeoutNs, stream_);
+        p2.waitFlags = nullptr;
+      }
+      launch_eval_tshard_hvl(kb(), pool(), tFirst_, n, dIds_.get(), inW, outHVL, evalCfg_, stream_, &p2);
+    }
     launch_p2p_barrier(flags, ++p2pEpoch_, kP2PTimeoutNs, stream_);
     dShardPriority_.ensure((size_t)(n * Q_), stream_);
     priority = dShardPriority_.get();

@@ -222,6 +222,7 @@ class Engine {
   PqaError *P2PNextQuestionEnd(int64_t n, const int64_t *pQuizIds, int64_t *pQuestions, void **ppErrors);
   PqaError *P2PRecordAnswerBegin(int64_t n, const int64_t *pQuizIds, const int64_t *pAnswers);
   PqaError *P2PRecordAnswerEnd();
+  PqaError *P2PSetExactOrder(int32_t on);   // target shards: hand the Kahan lanes from shard to shard (W_k bit-exact)
   // closed-form synthetic KB of SURVEY.md 8d written on the device (this engine's shard of it)
   PqaError *FillBinarySearchKB(double rounds);
 
@@ -280,8 +281,10 @@ class Engine {
   int p2pRank_ = -1, p2pRanks_ = 0;
   int64_t p2pCap_ = 0;
   char *p2pInbox_ = nullptr;
-  size_t p2pBytes_ = 0, p2pOffW_ = 0, p2pOffHVL_ = 0, p2pOffRows_ = 0, p2pOffPri_ = 0;
-  size_t p2pSzW_ = 0, p2pSzHVL_ = 0, p2pSzRows_ = 0, p2pSzPri_ = 0;   // bytes of one slot / one parity copy
+  size_t p2pBytes_ = 0, p2pOffW_ = 0, p2pOffHVL_ = 0, p2pOffRows_ = 0, p2pOffPri_ = 0, p2pOffState_ = 0;
+  size_t p2pSzW_ = 0, p2pSzHVL_ = 0, p2pSzRows_ = 0, p2pSzPri_ = 0, p2pSzState_ = 0;   // bytes of one slot / one parity copy
+  bool p2pExactOrder_ = false, p2pSameDevicePeer_ = false;
+  DevBuf<unsigned> dTileCounters_;
   char *p2pPeer_[kMaxPeers] = {};
   bool p2pOpened_[kMaxPeers] = {};
   bool p2pConnected_ = false, p2pPending_ = false;

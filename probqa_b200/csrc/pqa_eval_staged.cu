@@ -497,7 +497,36 @@ struct TShardParams {
   StagedParams S;
   int64_t tFirst;
   PeerBufs outW, inW, outHVL;
+  // Exact-order pipeline (phase 1 only): the 4-lane Kahan state (s, c) of every (quiz, question, answer) is handed from
+  // shard to shard in target order, so the LAST shard finishes the reference's own sum: W_k bit-exact across shards.
+  // Layout [((b*Q + i)*K + k)*4 + lane]*2 + {s, c}. inState = the previous shard's hand-over (nullptr on the first
+  // shard), outState = the next shard's inbox (nullptr on the last shard, which writes W_k to outW instead).
+  const double *inState;
+  double *outState;
+  PipeCtl pipe;
 };
+
+__device__ __forceinline__ uint64_t tshard_timer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// thread 0 of the CTA spins until flags[tile] >= epoch (acquire at system scope), everybody else waits at the barrier
+__device__ __forceinline__ void pipe_wait(const PipeCtl &pc, int64_t tile) {
+  if (pc.waitFlags != nullptr) {
+    if (threadIdx.x == 0) {
+      const uint64_t t0 = tshard_timer_ns();
+      for (;;) {
+        uint64_t seen;
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(pc.waitFlags + tile) : "memory");
+        if (seen >= pc.epoch) break;
+        if (tshard_timer_ns() - t0 > pc.timeoutNs) { *pc.errFlag = pc.epoch; break; }
+        __nanosleep(100);
+      }
+    }
+    __syncthreads();
+  }
+}
 
 template <int K, int KL, int WARPS, int PHASE>
 __global__ void __launch_bounds__(WARPS * 32, WARPS == 4 ? 4 : 2) k_eval_tshard(const TShardParams TP) {
@@ -526,12 +555,23 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 4 ? 4 : 2) k_eval_tshard(
   if (live && bit64(P.qp.asked + slot * P.qp.askedWords, i)) live = false;
   const double *pr = P.qp.priors + slot * P.qp.Tp + TP.tFirst, *lpr = P.qp.logPriors + slot * P.qp.Tp + TP.tFirst;
   const int64_t o = b * Q + i;
+  const int64_t pipeTile = iLocal / TP.pipe.tileQ;
+  pipe_wait(TP.pipe, pipeTile);          // phase 1: the previous shard's hand-over; phase 2: the complete W_k of this tile
   if (PHASE == 1) {
     Kahan kw[KL][K];
 #pragma unroll
     for (int e = 0; e < KL; e++)
 #pragma unroll
       for (int k = 0; k < K; k++) kw[e][k].init();
+    if (live && TP.inState != nullptr) {                 // continue the previous shard's Kahan lanes
+#pragma unroll
+      for (int e = 0; e < KL; e++)
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+          const double2 sc = *reinterpret_cast<const double2 *>(TP.inState + (((o * K + k) * 4 + l0 + e) * 2));
+          kw[e][k].s = sc.x; kw[e][k].c = sc.y;
+        }
+    }
     for (int64_t c = 0; c < P.nChunks; c++) {
       stage_chunk<K, THREADS>(P, iLocal, c, false, sR, sLR, sID2, &bar, parity);
       const int64_t j0 = c * P.Jc;
@@ -539,13 +579,33 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 4 ? 4 : 2) k_eval_tshard(
       if (live) pass1_chunk<K, KL>(sR, P.Jc, nVects, j0, pr, l0, kw);
       __syncthreads();
     }
-    if (live) {
+    if (live && TP.outState != nullptr) {                // hand the lanes over to the next shard
+#pragma unroll
+      for (int e = 0; e < KL; e++)
+#pragma unroll
+        for (int k = 0; k < K; k++)
+          *reinterpret_cast<double2 *>(TP.outState + (((o * K + k) * 4 + l0 + e) * 2)) = make_double2(kw[e][k].s, kw[e][k].c);
+    } else if (live) {
       double W[K], iW[K], lW[K];
       finish_pass1<K, KL>(kw, W, iW, lW);
       if (l0 == 0) {
         for (int r = 0; r < TP.outW.n; r++)
 #pragma unroll
           for (int k = 0; k < K; k++) TP.outW.p[r][o * K + k] = W[k];
+      }
+    }
+    if (TP.pipe.nSignal > 0) {             // last CTA of the tile publishes it
+      __threadfence_system();
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        const int64_t tileLen = (P.kb.qCount - pipeTile * TP.pipe.tileQ < TP.pipe.tileQ) ? P.kb.qCount - pipeTile * TP.pipe.tileQ : TP.pipe.tileQ;
+        const unsigned want = (unsigned)(tileLen * gridDim.y);
+        if (atomicAdd(TP.pipe.tileCounters + pipeTile, 1u) + 1u == want) {
+          TP.pipe.tileCounters[pipeTile] = 0u;
+          __threadfence_system();
+          for (int r = 0; r < TP.pipe.nSignal; r++)
+            asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(TP.pipe.signalFlags[r] + pipeTile), "l"(TP.pipe.epoch) : "memory");
+        }
       }
     }
   } else {
@@ -610,10 +670,13 @@ __global__ void __launch_bounds__(128) k_tshard_priority(const TShardEpiloguePar
 #pragma unroll
     for (int k = 0; k < K; k++) { W[k] = EP.inW.p[0][o * K + k]; H[k] = EP.inHVL.p[0][o * NV + k]; V[k] = EP.inHVL.p[0][o * NV + K + k]; }
     L = EP.inHVL.p[0][o * NV + 2 * K];
-    for (int r = 1; r < EP.inW.n; r++) {
+    for (int r = 1; r < EP.inW.n; r++) {       // n = 1 when the exact-order pipeline delivered the complete W_k
+#pragma unroll
+      for (int k = 0; k < K; k++) W[k] = __dadd_rn(W[k], EP.inW.p[r][o * K + k]);
+    }
+    for (int r = 1; r < EP.inHVL.n; r++) {
 #pragma unroll
       for (int k = 0; k < K; k++) {
-        W[k] = __dadd_rn(W[k], EP.inW.p[r][o * K + k]);
         H[k] = __dadd_rn(H[k], EP.inHVL.p[r][o * NV + k]);
         V[k] = __dadd_rn(V[k], EP.inHVL.p[r][o * NV + K + k]);
       }
@@ -655,6 +718,10 @@ static size_t slab_geometry(StagedParams &P, const EvalConfig &cfg, int64_t budg
   P.quizzesPerCta = 0;
   return (size_t)(Jc * bytesPerTarget);
 }
+int64_t tshard_quiz_tiles(int64_t n) {
+  const int64_t perPass = n > 64 ? 128 : 64;
+  return (n + perPass - 1) / perPass;
+}
 static size_t tshard_geometry(StagedParams &P, const EvalConfig &cfg) {
   return slab_geometry(P, cfg, P.n > 64 ? kSlabBudgetWide : kSlabBudgetNarrow);
 }
@@ -672,8 +739,11 @@ static size_t tshard_geometry(StagedParams &P, const EvalConfig &cfg) {
   }
 
 void launch_eval_tshard_w(const DeviceKB &kbLocal, const QuizPool &qp, int64_t tFirst, int64_t n, const int64_t *dSlots,
-                          const PeerBufs &outW, const EvalConfig &cfg, cudaStream_t st) {
+                          const PeerBufs &outW, const EvalConfig &cfg, cudaStream_t st, const double *inState,
+                          double *outState, const PipeCtl *pipe) {
   TShardParams TP;
+  TP.inState = inState; TP.outState = outState;
+  if (pipe) TP.pipe = *pipe;
   TP.S.kb = kbLocal; TP.S.qp = qp; TP.S.n = n; TP.S.slots = dSlots; TP.S.priority = nullptr;
   TP.S.det = EvalDetail{nullptr, nullptr, nullptr, nullptr};
   TP.tFirst = tFirst; TP.outW = outW; TP.inW.n = 0; TP.outHVL.n = 0;
@@ -682,11 +752,14 @@ void launch_eval_tshard_w(const DeviceKB &kbLocal, const QuizPool &qp, int64_t t
 }
 
 void launch_eval_tshard_hvl(const DeviceKB &kbLocal, const QuizPool &qp, int64_t tFirst, int64_t n, const int64_t *dSlots,
-                            const PeerBufs &inW, const PeerBufs &outHVL, const EvalConfig &cfg, cudaStream_t st) {
+                            const PeerBufs &inW, const PeerBufs &outHVL, const EvalConfig &cfg, cudaStream_t st,
+                            const PipeCtl *pipe) {
   TShardParams TP;
+  if (pipe) { TP.pipe.waitFlags = pipe->waitFlags; TP.pipe.epoch = pipe->epoch; TP.pipe.tileQ = pipe->tileQ;
+              TP.pipe.timeoutNs = pipe->timeoutNs; TP.pipe.errFlag = pipe->errFlag; }
   TP.S.kb = kbLocal; TP.S.qp = qp; TP.S.n = n; TP.S.slots = dSlots; TP.S.priority = nullptr;
   TP.S.det = EvalDetail{nullptr, nullptr, nullptr, nullptr};
-  TP.tFirst = tFirst; TP.outW.n = 0; TP.inW = inW; TP.outHVL = outHVL;
+  TP.tFirst = tFirst; TP.outW.n = 0; TP.inW = inW; TP.outHVL = outHVL; TP.inState = nullptr; TP.outState = nullptr;
   const size_t smem = tshard_geometry(TP.S, cfg);
   PQA_K_SWITCH(kbLocal.K, (launch_tshard_k<KK, 2>(TP, smem, st)))
 }

@@ -387,6 +387,34 @@ void launch_p2p_barrier(const P2PFlags &f, uint64_t epoch, uint64_t timeoutNs, c
   count_launch();
 }
 
+__global__ void k_p2p_wait(const uint64_t *flags, int nFlags, uint64_t value, uint64_t *errFlag, uint64_t timeoutNs) {
+  const uint64_t t0 = globaltimer_ns();
+  for (int f = threadIdx.x; f < nFlags; f += blockDim.x) {
+    for (;;) {
+      uint64_t seen;
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(flags + f) : "memory");
+      if (seen >= value) break;
+      if (globaltimer_ns() - t0 > timeoutNs) { *errFlag = value; break; }
+      __nanosleep(200);
+    }
+  }
+  __threadfence_system();
+}
+void launch_p2p_wait(const uint64_t *flags, int nFlags, uint64_t value, uint64_t *errFlag, uint64_t timeoutNs, cudaStream_t st) {
+  k_p2p_wait<<<1, 32, 0, st>>>(flags, nFlags, value, errFlag, timeoutNs);
+  count_launch();
+}
+__global__ void k_p2p_signal(PeerBufs targets, uint64_t value) {
+  const int r = threadIdx.x;
+  if (r >= targets.n) return;
+  __threadfence_system();
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(targets.p[r]), "l"(value) : "memory");
+}
+void launch_p2p_signal(const PeerBufs &targets, uint64_t value, cudaStream_t st) {
+  k_p2p_signal<<<1, 32, 0, st>>>(targets, value);
+  count_launch();
+}
+
 __global__ void k_p2p_push_prior_rows(DeviceKB kb, QuizPool qp, const int64_t *__restrict__ slots,
                                       const int64_t *__restrict__ questions, PeerBufs out) {
   const int64_t b = blockIdx.y, q = questions[b];
@@ -926,6 +954,8 @@ void preload_exchange_kernels(int K) {
   cudaFuncGetAttributes(&a, k_tshard_ra_partial);
   cudaFuncGetAttributes(&a, k_tshard_ra_finish);
   cudaFuncGetAttributes(&a, k_p2p_barrier);
+  cudaFuncGetAttributes(&a, k_p2p_wait);
+  cudaFuncGetAttributes(&a, k_p2p_signal);
   cudaFuncGetAttributes(&a, k_p2p_push_prior_rows);
   cudaFuncGetAttributes(&a, k_p2p_pull_prior_rows);
   cudaFuncGetAttributes(&a, k_select_question);

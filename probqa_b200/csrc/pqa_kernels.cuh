@@ -127,11 +127,31 @@ void launch_add_vb(const DeviceKB &kb, const int64_t *dTargets, const double *dA
 //   priority epilogue (CEEvalQsSubtaskConsider.cpp:134-207) on every shard, identical bits everywhere.
 // W_k is needed before phase 2 because log2(lik/W_k) sits in the denominator of the lack term.
 // phase 1: outW.p[*][(b*Q + i)*K + k]
+// inState / outState (optional): exact-order pipeline -- the Kahan lanes (s, c) per (quiz, question, answer, lane),
+// [((b*Q + i)*K + k)*4 + lane]*2 doubles, continue from the previous shard's hand-over and go to the next shard instead
+// of being summed; the shard without outState finishes the reference's sum and writes the complete W_k to outW.
+// kbLocal.qFirst / qCount (with sA/mD pointing at row qFirst) select the questions of one pipeline tile.
+// In-kernel control of the exact-order pipeline. Questions are grouped into tiles of tileQ consecutive questions. A CTA
+// first waits until waitFlags[tile] >= epoch (the previous shard has handed over that tile; nullptr = do not wait); when
+// the last CTA of a tile is done (tileCounters, self-resetting) it publishes epoch into signalFlags[r][tile] for
+// r < nSignal (the next shard's wait flags; on the last shard the W_k-ready flags of every shard, which phase 2 waits on).
+struct PipeCtl {
+  const uint64_t *waitFlags = nullptr;
+  uint64_t *signalFlags[kMaxPeers] = {};
+  int nSignal = 0;
+  unsigned *tileCounters = nullptr;
+  uint64_t epoch = 0, timeoutNs = 0;
+  uint64_t *errFlag = nullptr;
+  int64_t tileQ = 1;
+};
 void launch_eval_tshard_w(const DeviceKB &kbLocal, const QuizPool &qp, int64_t tFirst, int64_t n, const int64_t *dSlots,
-                          const PeerBufs &outW, const EvalConfig &cfg, cudaStream_t st);
+                          const PeerBufs &outW, const EvalConfig &cfg, cudaStream_t st, const double *inState = nullptr,
+                          double *outState = nullptr, const PipeCtl *pipe = nullptr);
+int64_t tshard_quiz_tiles(int64_t n);   // gridDim.y of the target-sharded kernels for a batch of n quizzes
 // phase 2: W = sum_r inW.p[r]; outHVL.p[*][(b*Q + i)*(2K+1) + {H_0..H_{K-1}, V_0..V_{K-1}, L}]
 void launch_eval_tshard_hvl(const DeviceKB &kbLocal, const QuizPool &qp, int64_t tFirst, int64_t n, const int64_t *dSlots,
-                            const PeerBufs &inW, const PeerBufs &outHVL, const EvalConfig &cfg, cudaStream_t st);
+                            const PeerBufs &inW, const PeerBufs &outHVL, const EvalConfig &cfg, cudaStream_t st,
+                            const PipeCtl *pipe = nullptr);   // pipe: only waitFlags / epoch / tileQ are used
 // epilogue: priority[b*Q + i] (NaN where asked / gap) from the summed W and H/V/L; det optional
 void launch_tshard_priority(const DeviceKB &kbLocal, const QuizPool &qp, int64_t n, const int64_t *dSlots,
                             const PeerBufs &inW, const PeerBufs &inHVL, double *dPriority, const EvalDetail &det,
@@ -164,6 +184,10 @@ struct P2PFlags {
 };
 void preload_exchange_kernels(int K);   // loads every kernel of the exchanged call sequences now (see pqa_kernels.cu)
 void launch_p2p_barrier(const P2PFlags &f, uint64_t epoch, uint64_t timeoutNs, cudaStream_t st);
+// point-to-point halves of the barrier, for pipelines: wait until flags[0 .. nFlags) >= value; publish value into
+// *targets.p[r] for r < targets.n (the pointers are uint64_t flag words in peer inboxes)
+void launch_p2p_wait(const uint64_t *flags, int nFlags, uint64_t value, uint64_t *errFlag, uint64_t timeoutNs, cudaStream_t st);
+void launch_p2p_signal(const PeerBufs &targets, uint64_t value, cudaStream_t st);
 // question-sharded RecordAnswer: rows of quizzes whose answered question (dQuestions[b]) this device owns go to every
 // peer's inbox rows [b*Tp ..]; after the barrier the other quizzes' rows come out of the own inbox into the pool.
 void launch_p2p_push_prior_rows(const DeviceKB &kb, const QuizPool &qp, int64_t n, const int64_t *dSlots,

@@ -143,6 +143,7 @@ SIGNATURES = {
     "PqaB200_P2PNextQuestionEnd": (_vp, [_vp, _i64, _pi64, _pi64, _pvp]),
     "PqaB200_P2PRecordAnswerBegin": (_vp, [_vp, _i64, _pi64, _pi64]),
     "PqaB200_P2PRecordAnswerEnd": (_vp, [_vp]),
+    "PqaB200_P2PSetExactOrder": (_vp, [_vp, C.c_int32]),
     "PqaB200_ResidentBind": (_vp, [_vp, _i64, _pi64, _pu64]),
     "PqaB200_ResidentStep": (_vp, [_vp]),
     "PqaB200_ResidentFetch": (_vp, [_vp, _pi64]),
@@ -656,6 +657,10 @@ class PqaEngine:
     def p2p_record_answer_begin(self, quiz_ids, answers):
         ids, ans = _i64arr(quiz_ids), _i64arr(answers)
         _raise_or_return(self._lib.PqaB200_P2PRecordAnswerBegin(self.c_engine, ids.size, _p(ids, _pi64), _p(ans, _pi64)))
+
+    def p2p_set_exact_order(self, on: bool):
+        """Target shards: hand the Kahan lanes from shard to shard so that W_k is bit-identical to a single engine's."""
+        _raise_or_return(self._lib.PqaB200_P2PSetExactOrder(self.c_engine, 1 if on else 0))
 
     def p2p_record_answer_end(self):
         _raise_or_return(self._lib.PqaB200_P2PRecordAnswerEnd(self.c_engine))

@@ -107,7 +107,7 @@ class QuestionShardedEngine:
         self._p2p = False
 
     # ---- exchange over peer memory instead of the caller-side all-reduce (PqaB200Ext.h "P2P" entry points)
-    def enable_p2p(self, max_quizzes: int):
+    def enable_p2p(self, max_quizzes: int, exact_order: bool = False):
         """Gives every shard engine an inbox and connects them: directly when all shards live in this process
         (group=None), through cudaIpc handles all-gathered over the process group when there is one shard per process.
         From then on next_question_batch / record_answer_batch run without any host-side exchange."""
@@ -126,6 +126,9 @@ class QuestionShardedEngine:
             bases = [base if r == rank else engines[0].p2p_open_handle(handles[r]) for r in range(world)]
             engines[0].p2p_connect(bases)
             dist.barrier(group=self.group)
+        if exact_order:      # target shards: W_k summed in the reference's own order across the shards (PqaB200Ext.h)
+            for e in engines:
+                e.p2p_set_exact_order(True)
         self._p2p = True
 
     def _p2p_next_question(self, quiz_ids, randoms):

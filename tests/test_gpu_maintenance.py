@@ -108,16 +108,17 @@ def test_mode_contract(pqa):
     assert eng.target_comp_from_perm([3])[0] == -1
 
 
-@pytest.mark.parametrize("dims,W,kernel", [((40, 5, 203), 6, 2), ((64, 5, 1000), 8, 2), ((24, 4, 96), 3, 1), ((30, 5, 700), 5, 2)])
-def test_gaps_parity_then_compact(pqa, ora, dims, W, kernel):
+@pytest.mark.parametrize("dims,W,kernel,n_quizzes,chunk", [((40, 5, 203), 6, 2, 5, 0), ((64, 5, 1000), 8, 2, 40, 0), ((24, 4, 96), 3, 1, 5, 0),
+                                                           ((30, 5, 700), 5, 2, 70, 64), ((20, 5, 400), 4, 2, 33, 96)])
+def test_gaps_parity_then_compact(pqa, ora, dims, W, kernel, n_quizzes, chunk):
     """Remove targets and questions; the quiz path must then equal the oracle run with the same gap masks (priors and
     top-10 bit-exact, priorities within the kernel's bar, gap questions never chosen). Compact; the compacted engine must
     equal the oracle on the numpy-compacted KB, and the old-id arrays must be the reference's (CpuEngine.cpp:585-658)."""
     Q, K, T = dims
     kb = synth.gamma_kb(Q, K, T, INIT)
     eng = make_engine(pqa, Q, K, T, W, kb)
-    eng.set_eval_kernel(kernel)
-    rng = np.random.default_rng(11)
+    eng.set_eval_kernel(kernel, chunk_targets=chunk)     # n_quizzes / chunk pick the kernel shape: small, 4 threads per quiz,
+    rng = np.random.default_rng(11)                      # 2 threads per quiz (8- and 4-warp CTAs), whole slab or chunked targets
     rm_t = rng.choice(T - 8, size=max(3, T // 9), replace=False)          # keeps the last targets: no trailing gaps
     rm_q = rng.choice(Q - 6, size=max(2, Q // 7), replace=False)
     eng.start_maintenance(False)
@@ -131,7 +132,7 @@ def test_gaps_parity_then_compact(pqa, ora, dims, W, kernel):
     def check_session(eng, sA, mD, vB, tg, qg, n_steps=3):
         Qc, Tc = sA.shape[0], sA.shape[2]
         tgm, qgm = (tg if tg.any() else None), (qg if qg.any() else None)
-        quizzes = eng.start_quiz_batch(5)
+        quizzes = eng.start_quiz_batch(n_quizzes)
         priors = [ora.start_quiz(vB, W, tgaps=tgm) for _ in quizzes]
         asked = [np.zeros(Qc, dtype=bool) for _ in quizzes]
         r2 = np.random.default_rng(12)

@@ -258,3 +258,58 @@ def test_peer_memory_exchange_across_processes():
                          capture_output=True, text=True, timeout=600, cwd=root)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert "questions: OK" in out.stdout and "targets: OK" in out.stdout
+
+
+@pytest.mark.parametrize("kbname,dims,n_shards,n,chunk", [("binary", (64, 5, 1000), 2, 9, 0), ("binary", (200, 5, 1000), 4, 70, 0),
+                                                          ("gamma", (48, 5, 2050), 3, 130, 128), ("binary", (300, 5, 500), 3, 40, 0)])
+def test_target_shards_exact_order_pipeline(kbname, dims, n_shards, n, chunk):
+    """Exact-order pipeline (PqaB200_P2PSetExactOrder): the Kahan lanes of pass 1 travel from shard to shard in target
+    order, so W_k is the reference's own sum. Priorities must then meet the SINGLE-engine bar (2e-12 flat against the
+    un-sharded staged kernel) even on the binary-search KB, whose uninformative questions amplify any other W_k to
+    percent-level priority differences; the plain target-sharded exchange is run beside it to show exactly that."""
+    from probqa_b200 import engine as pqa
+    Q, K, T = dims
+    W = 6
+    kb = synth.binary_search_kb(Q, K, T, INIT, 3) if kbname == "binary" else synth.gamma_kb(Q, K, T, INIT)
+    fac = pqa.PqaEngineFactory()
+    edef = pqa.EngineDefinition(K, Q, T, init_amount=INIT)
+    full = fac.create_b200_engine(edef, emulated_workers=W, rng_seed=5)
+    full.upload_kb(*kb)
+
+    def make(exact):
+        shards = []
+        for first, count in sharded.target_shard_ranges(T, n_shards):
+            e = fac.create_b200_engine(edef, emulated_workers=W, rng_seed=5, target_shard_first=first, target_shard_count=count)
+            e.upload_kb(*kb)
+            e.set_eval_kernel(2, chunk_targets=chunk)
+            shards.append(sharded.B200TargetShard(e))
+        se = sharded.TargetShardedEngine(shards)
+        se.enable_p2p(n, exact_order=exact)
+        return se
+
+    exact, plain = make(True), make(False)
+    ids = full.start_quiz_batch(n)
+    assert np.array_equal(ids, exact.start_quiz_batch(n)) and np.array_equal(ids, plain.start_quiz_batch(n))
+    rng = np.random.default_rng(81)
+    worst_exact = worst_plain = 0.0
+    for step in range(4):
+        for rep in range(2):                                   # both parities of the inbox
+            randoms = rng.integers(0, 2 ** 64, size=n, dtype=np.uint64)
+            want = full.eval_questions(ids)["priority"].ravel()
+            chosen = exact.next_question_batch(ids, randoms)
+            plain.next_question_batch(ids, randoms)
+            ok = ~np.isnan(want)
+            got = [s._view(0).cpu().numpy()[:want.size] for s in exact.shards]
+            for g in got[1:]:
+                assert np.array_equal(bits(g[ok]), bits(got[0][ok])), "shards disagree"
+            assert np.array_equal(np.isnan(got[0]), ~ok)
+            worst_exact = max(worst_exact, float(np.max(np.abs(got[0][ok] - want[ok]) / np.abs(want[ok]))))
+            gp = plain.shards[0]._view(0).cpu().numpy()[:want.size]
+            worst_plain = max(worst_plain, float(np.max(np.abs(gp[ok] - want[ok]) / np.abs(want[ok]))))
+        for e in (full, plain):
+            e.set_active_question_batch(ids, chosen)
+        answers = [(int(c) * 7 + step) % K for c in chosen]
+        for e in (full, exact, plain):
+            e.record_answer_batch(ids, answers)
+    assert worst_exact < 2e-12, worst_exact
+    print("max relative priority difference vs the single engine: exact-order %.3g, summed partials %.3g" % (worst_exact, worst_plain))
