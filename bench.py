@@ -251,7 +251,7 @@ def bench_sharded(args, cfg, pqa, dist, rank, world, local_rank, cores, barrier,
     else:
         se = sharded.TargetShardedEngine([sharded.B200TargetShard(eng)], group=group)
     if args.exchange == "p2p":
-        se.enable_p2p(B)
+        se.enable_p2p(B, exact_order=args.exact_order and args.shard == "targets")
     states = quiz_states(cfg, 0, B)
     quizzes = se.start_quiz_batch(B)
     for s in range(max(DEPTHS)):
@@ -297,7 +297,9 @@ def bench_sharded(args, cfg, pqa, dist, rank, world, local_rank, cores, barrier,
         "config": {"workload": args.workload, "Q": Q, "A": K, "T": T, "batch_total": B, "quiz_depths": list(DEPTHS),
                    "kb": "binary_search_kb(init=0.1, rounds=3), filled on the device", "parallelism": par,
                    "exchange": ("NCCL all-reduce via torch.distributed (host sync on both sides)" if args.exchange == "nccl" else
-                                "peer-memory stores from the kernel epilogues + device-side barrier (no host round trip)"),
+                                "peer-memory stores from the kernel epilogues + device-side barrier (no host round trip)" +
+                                ("; exact-order pipeline of the Kahan lanes (W_k bit-exact across shards)"
+                                 if args.exact_order and args.shard == "targets" else "")),
                    "l2": "inputs re-read every step; KB shard %.1f MB per GPU" % (shard_bytes / 1e6),
                    "timing": "wall clock around the public sharded API (result D2H + host sync inside every step), max over ranks",
                    "chosen_checksum": int(np.sum(chosen * (np.arange(B) + 1)) % 1000000007)},
@@ -324,6 +326,8 @@ def main():
     ap.add_argument("--chunk-targets", type=int, default=0)
     ap.add_argument("--lanes", type=int, default=0, help="Kahan lanes per thread of the staged kernel: 0 auto, 1, 4")
     ap.add_argument("--ref-quizzes", type=int, default=8, help="quizzes per step of the reference arm")
+    ap.add_argument("--exact-order", action="store_true",
+                    help="--shard targets --exchange p2p: hand the Kahan lanes from shard to shard (W_k bit-exact across shards)")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="sharded modes: how the shards exchange partial results (peer memory from the kernels, or NCCL)")
     ap.add_argument("--shard", default="quizzes", choices=["quizzes", "questions", "targets"],

@@ -29,7 +29,7 @@ def session(axis, rank, world, local_rank):
     full = fac.create_b200_engine(edef, device=local_rank, emulated_workers=W, rng_seed=5)
     full.upload_kb(*kb)
 
-    def make(p2p):
+    def make(p2p, exact=False):
         if axis == "questions":
             f, c = sharded.shard_ranges(Q, world)[rank]
             e = fac.create_b200_engine(edef, device=local_rank, emulated_workers=W, rng_seed=5, question_shard_first=f, question_shard_count=c)
@@ -41,12 +41,16 @@ def session(axis, rank, world, local_rank):
             e.upload_kb(*kb)
             se = sharded.TargetShardedEngine([sharded.B200TargetShard(e)], group=dist.group.WORLD)
         if p2p:
-            se.enable_p2p(n)
+            se.enable_p2p(n, exact_order=exact)
         return se
 
     nccl, p2p = make(False), make(True)
+    exact = make(True, exact=True) if axis == "targets" else None     # Kahan lanes handed from shard to shard
     ids = full.start_quiz_batch(n)
     assert np.array_equal(ids, nccl.start_quiz_batch(n)) and np.array_equal(ids, p2p.start_quiz_batch(n))
+    if exact is not None:
+        assert np.array_equal(ids, exact.start_quiz_batch(n))
+    worst_exact = 0.0
     rng = np.random.default_rng(80)
     for step in range(5):
         for rep in range(2):
@@ -67,10 +71,14 @@ def session(axis, rank, world, local_rank):
                 assert rel < 1e-10, rel
                 if world == 2:      # a + b == b + a: NCCL's order cannot differ from the rank order
                     assert np.array_equal(bits(got_p[ok]), bits(got_n[ok])) and np.array_equal(c_n, c_p)
+                exact.next_question_batch(ids, randoms)
+                got_e = exact.shards[0]._view(0).cpu().numpy()[:want.size]
+                worst_exact = max(worst_exact, float(np.max(np.abs(got_e[ok] - want[ok]) / want[ok])))
                 nccl.set_active_question_batch(ids, c_p)
                 full.set_active_question_batch(ids, c_p)
+                exact.set_active_question_batch(ids, c_p)
         answers = [(int(c) * 7 + step) % K for c in c_p]
-        for e in (full, nccl, p2p):
+        for e in (full, nccl, p2p) + ((exact,) if exact is not None else ()):
             e.record_answer_batch(ids, answers)
         for q in ids[:8]:
             w = bits(full.copy_quiz_priors(int(q)))
@@ -79,8 +87,11 @@ def session(axis, rank, world, local_rank):
         it_p, cn_p = p2p.list_top_targets_batch(ids, 10)
         assert np.array_equal(cn_f, cn_p) and it_f.tobytes() == it_p.tobytes()
     dist.barrier()
+    if exact is not None:
+        assert worst_exact < 2e-12, worst_exact          # the single-engine bar, with W_k summed in the reference's order
     if rank == 0:
-        print("p2p_multiproc_check %s: OK (world %d)" % (axis, world), flush=True)
+        print("p2p_multiproc_check %s: OK (world %d)%s" % (axis, world, "" if exact is None else
+              "; exact-order pipeline max rel priority diff vs single engine %.3g" % worst_exact), flush=True)
 
 
 def main():
