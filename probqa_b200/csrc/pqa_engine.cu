@@ -435,7 +435,11 @@ void Engine::Submit(CallSlot &slot) {
     }
     lk.unlock();
     const auto r0 = std::chrono::steady_clock::now();
-    RunCombined(batch);
+    try {
+      RunCombined(batch);
+    } catch (const std::exception &ex) {     // e.g. bad_alloc in the host bookkeeping: every caller of the batch hears about it
+      for (CallSlot *c : batch) if (!c->err) { c->err = ErrStd(ex.what()); c->result = -1; }
+    }
     lk.lock();
     statRunSec_ += std::chrono::duration<double>(std::chrono::steady_clock::now() - r0).count();
     statBatches_++;
