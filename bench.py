@@ -38,6 +38,9 @@ WORKLOADS = {
     "10000x5x100000_b64": dict(Q=10000, K=5, T=100000, B=64),
     "10000x5x100000_b256": dict(Q=10000, K=5, T=100000, B=256),
     "2000x5x20000_b64": dict(Q=2000, K=5, T=20000, B=64),
+    "1000x5x1000_b8": dict(Q=1000, K=5, T=1000, B=8),
+    "1000x5x1000_b16": dict(Q=1000, K=5, T=1000, B=16),
+    "1000x5x1000_b32": dict(Q=1000, K=5, T=1000, B=32),
     "1000x5x1000_b64": dict(Q=1000, K=5, T=1000, B=64),
     "1000x5x1000_b128": dict(Q=1000, K=5, T=1000, B=128),
     # small smoke size

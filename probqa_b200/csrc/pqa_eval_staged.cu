@@ -387,10 +387,13 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 4 ? 4 : 2) k_eval_staged(
 // With few quizzes per slab, staging log2 r would cost as much as it saves, so pass 2 evaluates the reference's
 // Log2Hot and an IEEE divide for every element (entropy and lack TERMS are then the reference's bits; only the
 // summation order differs) and the slab is just (K+1) rows: 48 KB at 1000x5x1000, four CTAs per SM.
-constexpr int kSmallWarps = 4;
-
-template <int K>
-__global__ void __launch_bounds__(kSmallWarps * 32, 4) k_eval_small(const StagedParams P) {
+// Two shapes. <K, 4, false>: one or two quizzes -- (K+1)-row slab, four CTAs per SM, pass 2 with the reference's Log2Hot and
+// IEEE divide per element as described above. <K, 8, true>: 3 .. 31 quizzes -- the slab also carries log2 r (staged once per
+// CTA, worth it from the third quiz on) and pass 2 uses the throughput kernel's split logarithm and reciprocal (15 instead
+// of ~70 fp64 instructions per element); eight warps = eight quizzes per round, one CTA per question takes all quizzes.
+template <int K, int SW, bool LOGSPLIT>
+__global__ void __launch_bounds__(SW * 32, LOGSPLIT ? 2 : 4) k_eval_small(const StagedParams P) {
+  constexpr int kSmallWarps = SW;
   constexpr int THREADS = kSmallWarps * 32;
   constexpr int NV = 2 * K + 1;                       // H_k, V_k, L
   extern __shared__ __align__(128) unsigned char smRaw[];
@@ -398,7 +401,7 @@ __global__ void __launch_bounds__(kSmallWarps * 32, 4) k_eval_small(const Staged
   __shared__ double sWk[kSmallWarps][3][K];           // per quiz of the round: W_k, 1/W_k, log2 W_k
   __shared__ double sPart[kSmallWarps][kSmallWarps][NV];   // [quiz][warp][value] partial sums of pass 2
   __shared__ int64_t sSlot[kSmallWarps];              // slot of the quiz, or -1 when absent / already asked
-  double *sR = (double *)smRaw, *sID2 = sR + K * P.Jc;
+  double *sR = (double *)smRaw, *sLR = sR + K * P.Jc, *sID2 = sR + (LOGSPLIT ? 2 * K : K) * P.Jc;
   const int64_t iLocal = blockIdx.x, i = P.kb.qFirst + iLocal, Q = P.kb.Q, Tp = P.kb.Tp, T = P.kb.T, Jc = P.Jc;
   const int64_t tileFirst = (int64_t)blockIdx.y * P.quizzesPerCta;
   const int64_t tileLimit = (tileFirst + P.quizzesPerCta < P.n) ? tileFirst + P.quizzesPerCta : P.n;
@@ -411,7 +414,7 @@ __global__ void __launch_bounds__(kSmallWarps * 32, 4) k_eval_small(const Staged
   if (threadIdx.x == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
   __syncthreads();
   uint32_t parity = 0;
-  stage_chunk<K, THREADS>(P, iLocal, 0, false, sR, nullptr, sID2, &bar, parity);
+  stage_chunk<K, THREADS>(P, iLocal, 0, LOGSPLIT, sR, sLR, sID2, &bar, parity);
   const double *__restrict__ tbl = P.kb.log2tbl;
   const int nVects = (int)(Tp >> 2);
   for (int64_t b0 = tileFirst; b0 < tileLimit; b0 += kSmallWarps) {      // CTA-uniform
@@ -444,17 +447,31 @@ __global__ void __launch_bounds__(kSmallWarps * 32, 4) k_eval_small(const Staged
       const int64_t slot = sSlot[q];
       if (slot < 0) continue;                                            // CTA-uniform
       const double *__restrict__ pr = P.qp.priors + slot * Tp;
-      double iW[K], H[K], V[K], L = 0.0;
+      const double *__restrict__ lpr = P.qp.logPriors + slot * Tp;
+      double iW[K], lW[K], H[K], V[K], L = 0.0;
 #pragma unroll
-      for (int k = 0; k < K; k++) { iW[k] = sWk[q][1][k]; H[k] = 0.0; V[k] = 0.0; }
+      for (int k = 0; k < K; k++) { iW[k] = sWk[q][1][k]; lW[k] = sWk[q][2][k]; H[k] = 0.0; V[k] = 0.0; }
       for (int j = threadIdx.x; j < (int)T; j += THREADS) {
         const double p = __ldg(pr + j), id2 = sID2[j];
+        const double lp = LOGSPLIT ? __ldg(lpr + j) : 0.0;
 #pragma unroll
         for (int k = 0; k < K; k++) {
           const double post = __dmul_rn(__dmul_rn(sR[k * Jc + j], p), iW[k]);   // :81-82, :97
-          const double l2 = log2hot(post, tbl);                         // :106
-          H[k] = __fma_rn(post, l2, H[k]);                              // :113-114
-          L = __dadd_rn(L, __ddiv_rn(id2, l2));                         // :116-117
+          if (LOGSPLIT) {
+            double l2, rl2;
+            if (fast_range_key(post) < kFastRangeLimit) {               // the throughput kernel's split logarithm
+              l2 = __dsub_rn(__dadd_rn(sLR[k * Jc + j], lp), lW[k]);
+              rl2 = fast_rcp46(l2);
+            } else {
+              l2 = slow_log2(post, tbl, &rl2);
+            }
+            H[k] = __fma_rn(post, l2, H[k]);
+            L = __fma_rn(id2, rl2, L);
+          } else {
+            const double l2 = log2hot(post, tbl);                       // :106
+            H[k] = __fma_rn(post, l2, H[k]);                            // :113-114
+            L = __dadd_rn(L, __ddiv_rn(id2, l2));                       // :116-117
+          }
           const double d = __dsub_rn(post, p);                          // :119
           V[k] = __fma_rn(d, d, V[k]);                                  // :126-127
         }
@@ -782,13 +799,21 @@ template <int K>
 static void launch_small(StagedParams P, size_t smem, cudaStream_t st) {
   static bool attrSet = false;
   if (!attrSet) {
-    cudaFuncSetAttribute(k_eval_small<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(k_eval_small<K, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(k_eval_small<K, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     attrSet = true;
   }
-  P.quizzesPerCta = kSmallWarps;
-  dim3 grid((unsigned)P.kb.qCount, (unsigned)((P.n + kSmallWarps - 1) / kSmallWarps));
-  smem = (size_t)((K + 1) * P.Jc) * sizeof(double);
-  k_eval_small<K><<<grid, kSmallWarps * 32, smem, st>>>(P);
+  if (P.n <= 2) {
+    P.quizzesPerCta = 4;
+    dim3 grid((unsigned)P.kb.qCount, (unsigned)((P.n + 3) / 4));
+    smem = (size_t)((K + 1) * P.Jc) * sizeof(double);
+    k_eval_small<K, 4, false><<<grid, 4 * 32, smem, st>>>(P);
+  } else {
+    P.quizzesPerCta = 32;                                    // one CTA per question, rounds of eight quizzes
+    dim3 grid((unsigned)P.kb.qCount, (unsigned)((P.n + 31) / 32));
+    smem = (size_t)((2 * K + 1) * P.Jc) * sizeof(double);
+    k_eval_small<K, 8, true><<<grid, 8 * 32, smem, st>>>(P);
+  }
   count_launch();
 }
 
@@ -864,7 +889,8 @@ template <int K> static void preload_staged_k() {
   cudaFuncGetAttributes(&a, k_eval_staged<K, 1, 8>);
   cudaFuncGetAttributes(&a, k_eval_staged<K, 2, 8>);
   cudaFuncGetAttributes(&a, k_eval_staged<K, 4, 4>);
-  cudaFuncGetAttributes(&a, k_eval_small<K>);
+  cudaFuncGetAttributes(&a, k_eval_small<K, 4, false>);
+  cudaFuncGetAttributes(&a, k_eval_small<K, 8, true>);
   cudaFuncGetAttributes(&a, k_eval_staged<K, 2, 4>);
   cudaFuncGetAttributes(&a, k_eval_tshard<K, 2, 4, 1>);
   cudaFuncGetAttributes(&a, k_eval_tshard<K, 2, 8, 1>);
