@@ -88,7 +88,9 @@ PQACORE_API void *PqaB200_EvalQuestionsDetailed(void *pvEngine, int64_t iQuiz, d
 PQACORE_API void *PqaB200_SetEvalKernel(void *pvEngine, int32_t which);
 /* Same, plus tuning knobs of the staged kernel (tests force the chunked-targets path on small T with these):
  * chunkTargets = targets staged per shared-memory chunk (0 auto), quizzesPerCta = quiz tile of one CTA (0 auto),
- * kahanLanesPerThread = 4 (one thread per quiz), 1 (four threads per quiz) or 0 (auto: 4 for batches >= 64). */
+ * kahanLanesPerThread = 4 (one thread per quiz), 2 (two threads per quiz), 1 (four threads per quiz) or 0 = auto:
+ * batches > 64 two threads per quiz in 8-warp CTAs; 33..64 quizzes four threads per quiz (whole slab) or two threads per
+ * quiz in 4-warp CTAs (chunked targets); fewer than 32 the small-batch kernel. */
 PQACORE_API void *PqaB200_SetEvalTuning(void *pvEngine, int32_t which, int64_t chunkTargets, int64_t quizzesPerCta,
                                         int32_t kahanLanesPerThread);
 

@@ -1,7 +1,8 @@
 // probqa_b200: the extern "C" layer of libPqaCore.so. Every PqaCInterop.h symbol of the reference
 // (PqaCore/Interface/PqaCInterop.h:48-108, definitions in PqaCore/PqaCInterop.cpp) is exported with the same
-// signature and error convention; entry points outside the hot-path scope return a NotImplemented error object
-// (the reference's own convention for unimplemented engine features, e.g. CudaEngine.cpp:62-98).
+// signature and error convention; every reference entry point is implemented (Logger_Init / SetLogger are accepted and
+// ignored). Combinations this engine does not offer (e.g. maintenance mode on a sharded engine) return the reference's
+// NotImplemented error object, its own convention for unimplemented engine features (CudaEngine.cpp:62-98).
 #include <cstdio>
 #include <cstring>
 #include <new>
