@@ -38,6 +38,12 @@ extern "C" {
 
 /* Same contract as PqaEngineFactory_CreateCpuEngine, with explicit options. */
 PQACORE_API void *PqaB200_CreateEngine(void **ppError, const CiEngineDefinition *pEngDef, const CiB200Options *pOpts);
+/* Same contract as PqaEngineFactory_LoadCpuEngine, with explicit options: a sharded engine streams only its question rows /
+ * target columns out of the file (the whole KB is never staged on the host). */
+PQACORE_API void *PqaB200_LoadEngine(void **ppError, const char *filePath, const CiB200Options *pOpts);
+/* Sharded engines save into ONE file in the reference's layout: the shard called with writeFrame != 0 goes first (creates
+ * the file; header, vB, gap lists, id maps), then every other shard writes its cells in place (writeFrame = 0). */
+PQACORE_API void *PqaB200_SaveKBShard(void *pvEngine, const char *filePath, int32_t writeFrame);
 PQACORE_API int32_t PqaB200_GetEmulatedWorkers(void *pvEngine);
 PQACORE_API int32_t PqaB200_GetDevice(void *pvEngine);
 PQACORE_API const char *PqaB200_BuildInfo(void); /* static string: arch, build flags */

@@ -89,6 +89,21 @@ PQACORE_API void *PqaEngineFactory_LoadCpuEngine(void *pvFactory, void **ppError
   return eng;
 }
 
+PQACORE_API void *PqaB200_LoadEngine(void **ppError, const char *filePath, const CiB200Options *pOpts) {
+  CiB200Options opts;
+  if (pOpts) opts = *pOpts;
+  else { std::memset(&opts, 0, sizeof(opts)); opts._device = -1; }
+  PqaError *err = nullptr;
+  Engine *eng = nullptr;
+  PqaError *g = Guard([&]() -> PqaError * { eng = Engine::LoadKB(filePath, opts, &err); return nullptr; });
+  Assign(ppError, g ? g : err);
+  return eng;
+}
+PQACORE_API void *PqaB200_SaveKBShard(void *pvEngine, const char *filePath, int32_t writeFrame) {
+  if (!pvEngine) return NullEngine();
+  return Ret(Guard([&] { return E(pvEngine)->SaveKBShard(filePath, writeFrame != 0); }));
+}
+
 PQACORE_API void CiReleasePqaError(void *pvErr) { delete static_cast<PqaError *>(pvErr); }
 PQACORE_API void *PqaError_ToString(void *pvError, const uint8_t withParams) {
   const std::string s = pvError ? static_cast<PqaError *>(pvError)->ToString(withParams != 0) : std::string("Success");

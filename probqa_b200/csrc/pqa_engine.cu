@@ -1647,46 +1647,81 @@ PqaError *FileOpErr(const char *path, const std::string &what) {
 }
 }  // namespace
 
+// The cells of this engine (all of them, or its question rows / target columns) go to their places in the file: sA at 40,
+// mD after it, vB after that (CpuEngine::SaveStatistics, CpuEngine.cpp:664-688). `frame` = also write the header, vB and the
+// tail (gap lists, id maps); a sharded KB is saved by one shard writing the frame first and then every shard writing its
+// cells into the same file (PqaB200_SaveKBShard).
+PqaError *Engine::WriteKBFile(FILE *f, const char *filePath, bool frame) {
+  const int64_t hdr = 40;
+  const int64_t offA = hdr, offD = offA + Q_ * K_ * T_ * 8, offB = offD + Q_ * T_ * 8, offTail = offB + T_ * 8;
+  if (frame) {
+    const uint64_t prec = (uint64_t)3 | ((uint64_t)(precMantissa_ & 0xFFFFFFF) << 4) | ((uint64_t)(precExponent_ & 0xFFFF) << 32);
+    const int64_t dims[3] = {K_, Q_, T_};
+    const uint64_t asked = nQuestionsAsked_.load(std::memory_order_acquire);
+    if (std::fseek(f, 0, SEEK_SET) != 0 || !wr(f, &prec, 8) || !wr(f, dims, 24) || !wr(f, &asked, 8))
+      return FileOpErr(filePath, PQA_FILE_LINE "Can't write the KB header.");
+  }
+  // stream the cells out in slabs of <= 64 MB of (local) rows
+  const int64_t TL = tLocal_;
+  const int64_t rowsPerSlab = std::max<int64_t>(1, (64ll << 20) / (TL * 8));
+  std::vector<double> slab((size_t)(rowsPerSlab * TL));
+  auto dumpRows = [&](const double *dBase, int64_t stride, int64_t nRows, int64_t nCols, int64_t fileOff, int64_t fileRowDoubles) -> PqaError * {
+    for (int64_t r0 = 0; r0 < nRows; r0 += rowsPerSlab) {
+      const int64_t nr = std::min(rowsPerSlab, nRows - r0);
+      try {
+        PQA_CU(cudaMemcpy2DAsync(slab.data(), (size_t)nCols * 8, dBase + r0 * stride, (size_t)stride * 8, (size_t)nCols * 8, (size_t)nr,
+                                 cudaMemcpyDeviceToHost, stream_));
+        PQA_CU(cudaStreamSynchronize(stream_));
+      } catch (const CudaFail &cf) { return ErrCuda(cf.code, cf.what(), cf.file, cf.line); }
+      if (nCols == fileRowDoubles) {            // whole rows: one contiguous write
+        if (fseeko(f, (off_t)(fileOff + r0 * fileRowDoubles * 8), SEEK_SET) != 0 || !wr(f, slab.data(), (size_t)(nr * nCols) * 8))
+          return FileOpErr(filePath, PQA_FILE_LINE "Can't write KB rows.");
+      } else {                                  // a column slice of every row
+        for (int64_t r = 0; r < nr; r++)
+          if (fseeko(f, (off_t)(fileOff + (r0 + r) * fileRowDoubles * 8), SEEK_SET) != 0 || !wr(f, slab.data() + r * nCols, (size_t)nCols * 8))
+            return FileOpErr(filePath, PQA_FILE_LINE "Can't write KB rows.");
+      }
+    }
+    return nullptr;
+  };
+  if (PqaError *e = dumpRows(dSA_, TpL_, qLocal_ * K_, TL, offA + (qFirst_ * K_ * T_ + tFirst_) * 8, T_)) return e;
+  if (PqaError *e = dumpRows(dMD_, TpL_, qLocal_, TL, offD + (qFirst_ * T_ + tFirst_) * 8, T_)) return e;
+  if (frame) {
+    if (PqaError *e = dumpRows(dVB_, Tp_, 1, T_, offB, T_)) return e;
+    if (fseeko(f, (off_t)offTail, SEEK_SET) != 0) return FileOpErr(filePath, PQA_FILE_LINE "Can't seek to the KB tail.");
+    auto dumpGaps = [&](const GapSet &g) {   // BaseEngine::WriteGaps, BaseEngine.cpp:142-152: count, then the ids in LIFO order
+      const int64_t nGaps = g.GetNGaps();
+      return wr(f, &nGaps, 8) && (nGaps == 0 || wr(f, g.Gaps().data(), (size_t)nGaps * 8));
+    };
+    if (!dumpGaps(qGaps_)) return FileOpErr(filePath, PQA_FILE_LINE "Can't write the question gaps.");
+    if (!dumpGaps(tGaps_)) return FileOpErr(filePath, PQA_FILE_LINE "Can't write the target gaps.");
+    if (!pimQ_.Save(f)) return FileOpErr(filePath, PQA_FILE_LINE "Can't write the question permanent-compact ID mappings.");
+    if (!pimT_.Save(f)) return FileOpErr(filePath, PQA_FILE_LINE "Can't write the target permanent-compact ID mappings.");
+    if (!pimQuiz_.Save(f, true)) return FileOpErr(filePath, PQA_FILE_LINE "Can't write the quiz permanent-compact ID mappings.");
+  }
+  if (std::fflush(f) != 0) return FileOpErr(filePath, PQA_FILE_LINE "Can't flush the KB file.");
+  return nullptr;
+}
+
 PqaError *Engine::SaveKB(const char *filePath) {
   if (!filePath) return MakeError(ErrCode::NullArgument, PQA_FILE_LINE "Nullptr is passed in place of KB file name.");
-  if (IsSharded()) return ErrNotImplemented("SaveKB on a sharded engine");
+  if (IsSharded()) return ErrNotImplemented("SaveKB on a sharded engine: use PqaB200_SaveKBShard on every shard");
   std::lock_guard<std::mutex> lk(mu_);   // the KB must not be trained while it is written (reference: shared lock)
   FileCloser fc{std::fopen(filePath, "wb")};
   if (!fc.f) return MakeError(ErrCode::CantOpenFile, PQA_FILE_LINE "Can't open the KB file to write.",
                               std::string("filePath=[") + filePath + "]");
-  const uint64_t prec = (uint64_t)3 | ((uint64_t)(precMantissa_ & 0xFFFFFFF) << 4) | ((uint64_t)(precExponent_ & 0xFFFF) << 32);
-  const int64_t dims[3] = {K_, Q_, T_};
-  const uint64_t asked = nQuestionsAsked_.load(std::memory_order_acquire);
-  if (!wr(fc.f, &prec, 8) || !wr(fc.f, dims, 24) || !wr(fc.f, &asked, 8)) return FileOpErr(filePath, PQA_FILE_LINE "Can't write the KB header.");
-  // stream the KB out in slabs of <= 64 MB of rows
-  const int64_t rowsPerSlab = std::max<int64_t>(1, (64ll << 20) / (T_ * 8));
-  std::vector<double> slab((size_t)(rowsPerSlab * T_));
-  auto dumpRows = [&](const double *dBase, int64_t nRows) -> PqaError * {
-    for (int64_t r0 = 0; r0 < nRows; r0 += rowsPerSlab) {
-      const int64_t nr = std::min(rowsPerSlab, nRows - r0);
-      try {
-        PQA_CU(cudaMemcpy2DAsync(slab.data(), (size_t)T_ * 8, dBase + r0 * Tp_, (size_t)Tp_ * 8, (size_t)T_ * 8, (size_t)nr,
-                                 cudaMemcpyDeviceToHost, stream_));
-        PQA_CU(cudaStreamSynchronize(stream_));
-      } catch (const CudaFail &cf) { return ErrCuda(cf.code, cf.what(), cf.file, cf.line); }
-      if (!wr(fc.f, slab.data(), (size_t)(nr * T_) * 8)) return FileOpErr(filePath, PQA_FILE_LINE "Can't write KB rows.");
-    }
-    return nullptr;
-  };
-  if (PqaError *e = dumpRows(dSA_, Q_ * K_)) return e;
-  if (PqaError *e = dumpRows(dMD_, Q_)) return e;
-  if (PqaError *e = dumpRows(dVB_, 1)) return e;
-  auto dumpGaps = [&](const GapSet &g) {     // BaseEngine::WriteGaps, BaseEngine.cpp:142-152: count, then the ids in LIFO order
-    const int64_t nGaps = g.GetNGaps();
-    return wr(fc.f, &nGaps, 8) && (nGaps == 0 || wr(fc.f, g.Gaps().data(), (size_t)nGaps * 8));
-  };
-  if (!dumpGaps(qGaps_)) return FileOpErr(filePath, PQA_FILE_LINE "Can't write the question gaps.");
-  if (!dumpGaps(tGaps_)) return FileOpErr(filePath, PQA_FILE_LINE "Can't write the target gaps.");
-  if (!pimQ_.Save(fc.f)) return FileOpErr(filePath, PQA_FILE_LINE "Can't write the question permanent-compact ID mappings.");
-  if (!pimT_.Save(fc.f)) return FileOpErr(filePath, PQA_FILE_LINE "Can't write the target permanent-compact ID mappings.");
-  if (!pimQuiz_.Save(fc.f, true)) return FileOpErr(filePath, PQA_FILE_LINE "Can't write the quiz permanent-compact ID mappings.");
-  if (std::fflush(fc.f) != 0) return FileOpErr(filePath, PQA_FILE_LINE "Can't flush the KB file.");
-  return nullptr;
+  return WriteKBFile(fc.f, filePath, true);
+}
+
+// One shard's part of a KB file shared by all shards. The shard called with writeFrame != 0 goes first (it creates the
+// file and writes header, vB and tail); the others then open the existing file and write their cells in place.
+PqaError *Engine::SaveKBShard(const char *filePath, bool writeFrame) {
+  if (!filePath) return MakeError(ErrCode::NullArgument, PQA_FILE_LINE "Nullptr is passed in place of KB file name.");
+  std::lock_guard<std::mutex> lk(mu_);
+  FileCloser fc{std::fopen(filePath, writeFrame ? "wb" : "r+b")};
+  if (!fc.f) return MakeError(ErrCode::CantOpenFile, PQA_FILE_LINE "Can't open the KB file to write.",
+                              std::string("filePath=[") + filePath + "]");
+  return WriteKBFile(fc.f, filePath, writeFrame);
 }
 
 Engine *Engine::LoadKB(const char *filePath, const CiB200Options &opts, PqaError **err) {
@@ -1709,17 +1744,49 @@ Engine *Engine::LoadKB(const char *filePath, const CiB200Options &opts, PqaError
   def._initAmount = 1.0;   // not stored in the file; only used to fill a fresh KB, which is overwritten below
   const int64_t K = dims[0], Q = dims[1], T = dims[2];
   std::unique_ptr<Engine> eng(new Engine(def, opts));
-  // rows arrive in file order; upload them slab by slab through the whole-KB upload path of this engine's shard
-  std::vector<double> sA((size_t)(Q * K * T)), mD((size_t)(Q * T)), vB((size_t)T);
-  if (!rd(fc.f, sA.data(), sA.size() * 8) || !rd(fc.f, mD.data(), mD.size() * 8) || !rd(fc.f, vB.data(), vB.size() * 8)) {
-    *err = FileOpErr(filePath, PQA_FILE_LINE "Can't read the KB statistics.");
-    return nullptr;
+  // Stream this engine's cells (all rows, or the question rows / target columns of its shard) from the file to the device
+  // in slabs of <= 64 MB; the whole KB is never held on the host.
+  const int64_t offA = 40, offD = offA + Q * K * T * 8, offB = offD + Q * T * 8, offTail = offB + T * 8;
+  {
+    Engine &E = *eng;
+    const int64_t TL = E.tLocal_;
+    const int64_t rowsPerSlab = std::max<int64_t>(1, (64ll << 20) / (TL * 8));
+    PinBuf<double> slab;
+    slab.ensure((size_t)(rowsPerSlab * TL));
+    auto loadRows = [&](double *dBase, int64_t stride, int64_t nRows, int64_t nCols, int64_t fileOff, int64_t fileRowDoubles) -> bool {
+      for (int64_t r0 = 0; r0 < nRows; r0 += rowsPerSlab) {
+        const int64_t nr = std::min(rowsPerSlab, nRows - r0);
+        if (nCols == fileRowDoubles) {
+          if (fseeko(fc.f, (off_t)(fileOff + r0 * fileRowDoubles * 8), SEEK_SET) != 0 || !rd(fc.f, slab.get(), (size_t)(nr * nCols) * 8)) return false;
+        } else {
+          for (int64_t r = 0; r < nr; r++)
+            if (fseeko(fc.f, (off_t)(fileOff + (r0 + r) * fileRowDoubles * 8), SEEK_SET) != 0 || !rd(fc.f, slab.get() + r * nCols, (size_t)nCols * 8)) return false;
+        }
+        if (cudaMemcpy2DAsync(dBase + r0 * stride, (size_t)stride * 8, slab.get(), (size_t)nCols * 8, (size_t)nCols * 8, (size_t)nr,
+                              cudaMemcpyHostToDevice, E.stream_) != cudaSuccess || cudaStreamSynchronize(E.stream_) != cudaSuccess) return false;
+      }
+      return true;
+    };
+    // rows are padded on the device: the fill of the constructor left the padding lanes at their neutral values
+    if (!loadRows(E.dSA_, E.TpL_, E.qLocal_ * K, TL, offA + (E.qFirst_ * K * T + E.tFirst_) * 8, T) ||
+        !loadRows(E.dMD_, E.TpL_, E.qLocal_, TL, offD + (E.qFirst_ * T + E.tFirst_) * 8, T)) {
+      *err = FileOpErr(filePath, PQA_FILE_LINE "Can't read the KB statistics.");
+      return nullptr;
+    }
+    std::vector<double> vB((size_t)T);
+    if (fseeko(fc.f, (off_t)offB, SEEK_SET) != 0 || !rd(fc.f, vB.data(), vB.size() * 8) ||
+        cudaMemcpy(E.dVB_, vB.data(), vB.size() * 8, cudaMemcpyHostToDevice) != cudaSuccess) {
+      *err = FileOpErr(filePath, PQA_FILE_LINE "Can't read the _vB weights.");
+      return nullptr;
+    }
+    if (fseeko(fc.f, (off_t)offTail, SEEK_SET) != 0) { *err = FileOpErr(filePath, PQA_FILE_LINE "Can't seek to the KB tail."); return nullptr; }
   }
   for (int g = 0; g < 2; g++) {   // question gaps, target gaps (BaseEngine::ReadGaps, BaseEngine.cpp:126-140)
     int64_t nGaps = 0;
     if (!rd(fc.f, &nGaps, 8)) { *err = FileOpErr(filePath, PQA_FILE_LINE "Can't read the gaps."); return nullptr; }
     const int64_t range = g == 0 ? Q : T;
     if (nGaps < 0 || nGaps > range) { *err = FileOpErr(filePath, PQA_FILE_LINE "Corrupt gap count."); return nullptr; }
+    if (nGaps > 0 && eng->IsSharded()) { *err = ErrNotImplemented("B200 engine: a KB file with removed questions/targets (gaps) on a sharded engine; compact it first"); return nullptr; }
     std::vector<int64_t> ids((size_t)nGaps);
     if (nGaps > 0 && !rd(fc.f, ids.data(), ids.size() * 8)) { *err = FileOpErr(filePath, PQA_FILE_LINE "Can't read the gaps."); return nullptr; }
     GapSet &gs = g == 0 ? eng->qGaps_ : eng->tGaps_;
@@ -1733,7 +1800,6 @@ Engine *Engine::LoadKB(const char *filePath, const CiB200Options &opts, PqaError
     return nullptr;
   }
   eng->SyncGapBits();
-  if (PqaError *e = eng->UploadKB(sA.data(), mD.data(), vB.data())) { *err = e; return nullptr; }
   eng->nQuestionsAsked_.store(asked, std::memory_order_relaxed);
   return eng.release();
 }

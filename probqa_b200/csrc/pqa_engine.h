@@ -160,6 +160,7 @@ class Engine {
   PqaError *CopyDTargets(int64_t iQuestion, int64_t maxTargets, double *pFreqs);
   PqaError *CopyBTargets(int64_t maxTargets, double *pFreqs);
   PqaError *SaveKB(const char *filePath);
+  PqaError *SaveKBShard(const char *filePath, bool writeFrame);   // sharded engines: every shard writes its cells into one file
   static Engine *LoadKB(const char *filePath, const CiB200Options &opts, PqaError **err);
 
   // --- maintenance mode (BaseEngine.cpp:640-779, CpuEngine.cpp:468-658) and id maps (BaseEngine.cpp:154-218) ---
@@ -244,6 +245,7 @@ class Engine {
   PqaError *ValidateRecordAnswer(int64_t n, const int64_t *pQuizIds, const int64_t *pAnswers) const;
   PqaError *FinishNextQuestion(int64_t m, const std::vector<int64_t> &valid, const std::vector<int64_t> &where,
                                int64_t *pQuestions, void **ppErrors, PqaError *firstErr);
+  PqaError *WriteKBFile(FILE *f, const char *filePath, bool frame);
   PqaError *WrongMode(const char *what) const;          // regular-only operation called in maintenance mode
   void SyncGapBits();                                    // host gap trackers -> device bitmaps read by the kernels
   void ResizeKB(int64_t newQ, int64_t newT);             // grows sA/mD/vB on the device, keeps the old cells

@@ -102,6 +102,8 @@ SIGNATURES = {
     "PqaEngine_SetLogger": (_vp, [_vp, _vp]),
     # ---- PqaB200Ext.h
     "PqaB200_CreateEngine": (_vp, [_pvp, C.POINTER(CiEngineDefinition), C.POINTER(CiB200Options)]),
+    "PqaB200_LoadEngine": (_vp, [_pvp, C.c_char_p, C.POINTER(CiB200Options)]),
+    "PqaB200_SaveKBShard": (_vp, [_vp, C.c_char_p, C.c_int32]),
     "PqaB200_GetEmulatedWorkers": (C.c_int32, [_vp]),
     "PqaB200_GetDevice": (C.c_int32, [_vp]),
     "PqaB200_BuildInfo": (C.c_char_p, []),
@@ -442,6 +444,10 @@ class PqaEngine:
     def quiz_comp_from_perm(self, ids):
         return self._map_ids(self._lib.PqaEngine_QuizCompFromPerm, ids)
 
+    def save_kb_shard(self, file_path: str, write_frame: bool, throw: bool = True):
+        """Sharded engines: this shard's cells into a file shared by all shards (the frame writer goes first)."""
+        return _raise_or_return(self._lib.PqaB200_SaveKBShard(self.c_engine, file_path.encode(), 1 if write_frame else 0), throw)
+
     def shutdown(self, save_file_path: str = None, throw: bool = True):
         p = save_file_path.encode() if save_file_path else None
         return _raise_or_return(self._lib.PqaEngine_Shutdown(self.c_engine, p), throw)
@@ -743,6 +749,18 @@ class PqaEngineFactory:
                              question_shard_count, target_shard_first, target_shard_count)
         e = C.c_void_p()
         c_engine = self._lib.PqaB200_CreateEngine(C.byref(e), C.byref(c_def), C.byref(opts))
+        if not c_engine:
+            raise PqaException(PqaError.factor(e.value))
+        return PqaEngine(c_engine)
+
+    def load_b200_engine(self, file_path: str, device: int = -1, emulated_workers: int = 0, rng_seed: int = 0,
+                         initial_quiz_capacity: int = 0, question_shard_first: int = 0, question_shard_count: int = 0,
+                         target_shard_first: int = 0, target_shard_count: int = 0) -> PqaEngine:
+        """LoadCpuEngine with explicit options; a sharded engine reads only its rows / columns of the file."""
+        opts = CiB200Options(device, emulated_workers, rng_seed, initial_quiz_capacity, question_shard_first,
+                             question_shard_count, target_shard_first, target_shard_count)
+        e = C.c_void_p()
+        c_engine = self._lib.PqaB200_LoadEngine(C.byref(e), file_path.encode(), C.byref(opts))
         if not c_engine:
             raise PqaException(PqaError.factor(e.value))
         return PqaEngine(c_engine)

@@ -219,6 +219,24 @@ class QuestionShardedEngine:
     def copy_quiz_priors(self, quiz):
         return self.shards[0].copy_quiz_priors(quiz)
 
+    def save_kb(self, file_path: str):
+        """One KB file in the reference's layout out of all shards: the first shard writes the frame (header, vB, id maps)
+        and its cells, then every other shard writes its cells in place. Load it back per shard with
+        PqaEngineFactory.load_b200_engine(path, question_shard_... / target_shard_...)."""
+        rank = 0
+        if self.group is not None:
+            import torch.distributed as dist
+            rank = dist.get_rank(self.group)
+        if rank == 0:
+            self.shards[0].engine.save_kb_shard(file_path, True)
+        if self.group is not None:
+            dist.barrier(group=self.group)
+        for x, s in enumerate(self.shards):
+            if not (rank == 0 and x == 0):
+                s.engine.save_kb_shard(file_path, False)
+        if self.group is not None:
+            dist.barrier(group=self.group)
+
 
 class B200TargetShard:
     """Shard port over a PqaEngine created with a target shard (probqa_b200.engine): the columns

@@ -313,3 +313,46 @@ def test_target_shards_exact_order_pipeline(kbname, dims, n_shards, n, chunk):
             e.record_answer_batch(ids, answers)
     assert worst_exact < 2e-12, worst_exact
     print("max relative priority difference vs the single engine: exact-order %.3g, summed partials %.3g" % (worst_exact, worst_plain))
+
+
+@pytest.mark.parametrize("axis,dims,n_shards", [("questions", (23, 4, 101), 3), ("targets", (17, 5, 203), 3), ("targets", (9, 3, 64), 2)])
+def test_sharded_kb_file_save_and_load(axis, dims, n_shards, tmp_path):
+    """Sharded engines save into ONE file in the reference's layout (frame writer first, then every shard in place) and
+    load their own rows / columns back out of a file; both must equal what a single engine writes / holds, byte for byte."""
+    from probqa_b200 import engine as pqa
+    Q, K, T = dims
+    kb = synth.gamma_kb(Q, K, T, INIT)
+    fac = pqa.PqaEngineFactory()
+    edef = pqa.EngineDefinition(K, Q, T, init_amount=INIT)
+    full = fac.create_b200_engine(edef, emulated_workers=4, rng_seed=5)
+    full.upload_kb(*kb)
+    ranges = sharded.shard_ranges(Q, n_shards) if axis == "questions" else sharded.target_shard_ranges(T, n_shards)
+    key = "question_shard" if axis == "questions" else "target_shard"
+    shards = []
+    for f, c in ranges:
+        e = fac.create_b200_engine(edef, emulated_workers=4, rng_seed=5, **{key + "_first": f, key + "_count": c})
+        e.upload_kb(*kb)
+        shards.append(sharded.B200Shard(e) if axis == "questions" else sharded.B200TargetShard(e))
+    se = (sharded.QuestionShardedEngine if axis == "questions" else sharded.TargetShardedEngine)(shards)
+    # train a little so that the file is not the uploaded KB, identically on both sides
+    aqs = [pqa.AnsweredQuestion(1, 2), pqa.AnsweredQuestion(3, 0), pqa.AnsweredQuestion(1, 1)]
+    full.train(aqs, 5, 0.75)
+    se.train(aqs, 5, 0.75)
+    p_full, p_shards = str(tmp_path / "full.kb"), str(tmp_path / "shards.kb")
+    full.save_kb(p_full)
+    se.save_kb(p_shards)
+    assert open(p_full, "rb").read() == open(p_shards, "rb").read()
+    want = full.download_kb()
+    gA, gD = np.full_like(want[0], np.nan), np.full_like(want[1], np.nan)
+    for f, c in ranges:
+        e = fac.load_b200_engine(p_shards, emulated_workers=4, **{key + "_first": f, key + "_count": c})
+        a, d, b = e.download_kb()
+        if axis == "questions":
+            gA[f:f + c], gD[f:f + c] = a[f:f + c], d[f:f + c]
+        else:
+            gA[:, :, f:f + c], gD[:, f:f + c] = a[:, :, f:f + c], d[:, f:f + c]
+        assert np.array_equal(bits(b), bits(want[2])) and e.get_total_questions_asked() == full.get_total_questions_asked()
+    assert np.array_equal(bits(gA), bits(want[0])) and np.array_equal(bits(gD), bits(want[1]))
+    one = fac.load_b200_engine(p_shards, emulated_workers=4)               # and as a single engine, streamed
+    for g, w in zip(one.download_kb(), want):
+        assert np.array_equal(bits(g), bits(w))
