@@ -5,7 +5,11 @@
 #    copy under a mktemp dir that is deleted afterwards; nothing of the reference is copied into the repo;
 #  * Win32-bound shell headers (thread pool, mem pool, logger, engine/quiz shells) are replaced by the
 #    stubs in refshim/stubs/ -- none of them contains arithmetic;
-#  * flags follow SURVEY.md 8(c): -O2 -mavx2 -mfma -mbmi -mbmi2 -ffp-contract=off.
+#  * flags follow SURVEY.md 8(c): -O2 -mavx2 -mfma -mbmi -mbmi2 -ffp-contract=off, plus -fno-strict-aliasing: the
+#    reference reads vector lanes through MSVC's union members (x.m128i_i64[i]), which the shim turns into pointer casts;
+#    MSVC never applies type-based alias analysis, and g++ with it on dropped the store behind such a read in
+#    SRSimd::FullHorizMaxI64 (ResumeQuiz then normalised with a wrong common exponent -- invisible in the priors, which
+#    are scale-invariant, but visible as -0.0 in removed-target lanes; found by tests/golden, round 1).
 # Only the .so lands in oracle/_ref/ (git-ignored, travels to the GPU box).
 set -euo pipefail
 HERE="$(cd "$(dirname "$0")" && pwd)"
@@ -30,7 +34,7 @@ cp "$HERE/ref_harness_prims.cpp" "$HERE/ref_harness_engine.cpp" "$TMP/ProbQA/har
 cp "$HERE/refshim/stubs/PqaCore/stdafx.h" "$TMP/ProbQA/harness/stdafx.h"
 
 CXX="${CXX:-g++}"
-FLAGS="-std=c++17 -O2 -fPIC -mavx2 -mfma -mbmi -mbmi2 -ffp-contract=off -fno-fast-math -fpermissive -w -pthread -include $HERE/refshim/compat.h -I $TMP/ProbQA/PqaCore"
+FLAGS="-std=c++17 -O2 -fPIC -mavx2 -mfma -mbmi -mbmi2 -ffp-contract=off -fno-fast-math -fno-strict-aliasing -fpermissive -w -pthread -include $HERE/refshim/compat.h -I $TMP/ProbQA/PqaCore"
 OBJS=""
 for f in $SR_CPP; do $CXX $FLAGS -c "$TMP/ProbQA/SRPlatform/$f" -o "$TMP/sr_${f%.cpp}.o"; OBJS="$OBJS $TMP/sr_${f%.cpp}.o"; done
 for f in $PQA_CPP; do $CXX $FLAGS -c "$TMP/ProbQA/PqaCore/$f" -o "$TMP/pqa_${f%.cpp}.o"; OBJS="$OBJS $TMP/pqa_${f%.cpp}.o"; done

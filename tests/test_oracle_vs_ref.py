@@ -212,3 +212,13 @@ def test_resume_quiz_bit_exact_vs_reference(ora, ref):
                 assert np.array_equal(bits(got), bits(want)), (Q, K, T, W, n)
                 assert abs(got.sum() - 1.0) < 1e-12
             eng.close()
+            # removed targets: their lanes must come out as +0.0 on both sides (this is what caught a strict-aliasing
+            # miscompile of the reference's FullHorizMaxI64 in the harness build, see oracle/build_ref.sh)
+            tg = np.zeros(T, dtype=bool); tg[rng.choice(T, size=max(2, T // 10), replace=False)] = True
+            eng = ref.RefEngine(sA, mD, vB, nWorkers=W, tgaps=tg)
+            for n in (1, 2, 5):
+                aqs = [(int(q), int(rng.integers(0, K))) for q in rng.choice(Q, size=n, replace=False)]
+                want = eng.resume_quiz(aqs)
+                got = ora.resume_quiz(sA, mD, vB, aqs, W, tgaps=tg)
+                assert np.array_equal(bits(got), bits(want)) and not np.signbit(want[tg]).any(), (Q, K, T, W, n)
+            eng.close()
