@@ -30,11 +30,33 @@ typedef struct {
   int64_t _targetShardFirst;
   int64_t _targetShardCount;
 } CiB200Options;
+/* One engine over several GPUs of a box in ONE process (PqaB200_CreateShardedEngine): the KB is split over _nShards shard
+ * engines, their kernels exchange over NVLink peer memory, and the returned handle answers every entry point of
+ * PqaCInterop.h and the batch entry points below like a single engine does. */
+typedef struct {
+  int32_t _axis;             /* 0 = questions (rows of sA/mD; results bit-identical to one engine), 1 = targets (columns;
+                              * BASELINE config 4) */
+  int32_t _nShards;          /* 1..8 */
+  int32_t _devices[8];       /* CUDA device of each shard; all -1 = devices 0.._nShards-1 modulo the visible device count */
+  int32_t _exactOrder;       /* targets only: hand the Kahan lanes from shard to shard (PqaB200_P2PSetExactOrder) */
+  int64_t _maxBatch;         /* quizzes per exchanged call (inbox size); 0 = 256; longer batches are cut into slices */
+} CiB200GroupOptions;
 #pragma pack(pop)
 
 #ifdef __cplusplus
 extern "C" {
 #endif
+
+/* A sharded engine group behind the ordinary engine handle. pOpts: as for PqaB200_CreateEngine (shard fields ignored).
+ * Environment shortcut for unmodified clients of the reference ABI: with PQA_B200_SHARDS=N set,
+ * PqaEngineFactory_CreateCpuEngine / LoadCpuEngine return such a group (PQA_B200_SHARD_AXIS=questions|targets, default
+ * targets; PQA_B200_SHARD_DEVICES=0,1,..; PQA_B200_SHARD_EXACT=1). */
+PQACORE_API void *PqaB200_CreateShardedEngine(void **ppError, const CiEngineDefinition *pEngDef, const CiB200Options *pOpts,
+                                              const CiB200GroupOptions *pGroupOpts);
+PQACORE_API void *PqaB200_LoadShardedEngine(void **ppError, const char *filePath, const CiB200Options *pOpts,
+                                            const CiB200GroupOptions *pGroupOpts);
+/* Number of shard engines behind the handle (1 for a plain engine). */
+PQACORE_API int32_t PqaB200_GetShardCount(void *pvEngine);
 
 /* Same contract as PqaEngineFactory_CreateCpuEngine, with explicit options. */
 PQACORE_API void *PqaB200_CreateEngine(void **ppError, const CiEngineDefinition *pEngDef, const CiB200Options *pOpts);

@@ -11,8 +11,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_DIR = os.path.join(_HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libPqaCore.so")
-SOURCES = ["pqa_kernels.cu", "pqa_eval_staged.cu", "pqa_train_sort.cu", "pqa_engine.cu", "pqa_maint.cu", "pqa_cabi.cu", "pqa_errors.cpp"]
-HEADERS = ["pqa_kernels.cuh", "pqa_device.cuh", "pqa_engine.h", "pqa_errors.h",
+SOURCES = ["pqa_kernels.cu", "pqa_eval_staged.cu", "pqa_train_sort.cu", "pqa_engine.cu", "pqa_maint.cu", "pqa_group.cu", "pqa_cabi.cu", "pqa_errors.cpp"]
+HEADERS = ["pqa_kernels.cuh", "pqa_device.cuh", "pqa_engine.h", "pqa_group.h", "pqa_errors.h",
            os.path.join("..", "..", "include", "PqaCInterop.h"), os.path.join("..", "..", "include", "PqaB200Ext.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-fmad=false",
               "-Xcompiler", "-fPIC,-fvisibility=hidden,-O2", "-Xptxas", "-v"]

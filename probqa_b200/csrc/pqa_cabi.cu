@@ -9,6 +9,10 @@
 
 #include "../../include/PqaB200Ext.h"
 #include "pqa_engine.h"
+#include "pqa_group.h"
+
+#include <cstdlib>
+#include <string>
 
 using namespace pqa;
 
@@ -51,6 +55,44 @@ PqaError *CreateEngineImpl(const CiEngineDefinition *pEngDef, const CiB200Option
   return Guard([&]() -> PqaError * { *out = new Engine(*pEngDef, opts); return nullptr; });
 }
 
+// PQA_B200_SHARDS=N (with PQA_B200_SHARD_AXIS / _DEVICES / _EXACT / PQA_B200_SHARD_MAX_BATCH): the reference's factory
+// entry points hand out a sharded engine group, so that an unmodified client of the reference ABI runs on N GPUs.
+bool EnvGroupOptions(CiB200GroupOptions *g) {
+  const char *n = std::getenv("PQA_B200_SHARDS");
+  if (!n || std::atoi(n) < 2) return false;
+  std::memset(g, 0, sizeof(*g));
+  g->_nShards = std::atoi(n);
+  const char *axis = std::getenv("PQA_B200_SHARD_AXIS");
+  g->_axis = (axis && std::string(axis) == "questions") ? 0 : 1;
+  for (int r = 0; r < 8; r++) g->_devices[r] = -1;
+  if (const char *d = std::getenv("PQA_B200_SHARD_DEVICES")) {
+    int r = 0;
+    for (const char *p = d; *p && r < 8; r++) {
+      g->_devices[r] = std::atoi(p);
+      while (*p && *p != ',') p++;
+      if (*p == ',') p++;
+    }
+  }
+  const char *ex = std::getenv("PQA_B200_SHARD_EXACT");
+  g->_exactOrder = ex && std::atoi(ex) != 0;
+  const char *mb = std::getenv("PQA_B200_SHARD_MAX_BATCH");
+  g->_maxBatch = mb ? std::atoll(mb) : 0;
+  return true;
+}
+
+PqaError *CreateGroupImpl(const CiEngineDefinition *pEngDef, const CiB200Options *pOpts, const CiB200GroupOptions *pG, Engine **out) {
+  *out = nullptr;
+  if (!pEngDef || !pG) return MakeError(ErrCode::NullArgument, "pEngDef / pGroupOpts is NULL");
+  if (pEngDef->_precType != 3)
+    return ErrNotImplemented("B200 engine on precision type other than double (precType must be 3).");
+  if (pEngDef->_nAnswers < 2 || pEngDef->_nQuestions < 1 || pEngDef->_nTargets < 2)
+    return ErrInsufficientDims(pEngDef->_nAnswers, pEngDef->_nQuestions, pEngDef->_nTargets);
+  CiB200Options opts;
+  if (pOpts) opts = *pOpts;
+  else { std::memset(&opts, 0, sizeof(opts)); opts._device = -1; }
+  return Guard([&]() -> PqaError * { *out = new ShardGroup(*pEngDef, opts, *pG); return nullptr; });
+}
+
 } // namespace
 
 extern "C" {
@@ -70,8 +112,33 @@ PQACORE_API void *CiGetPqaEngineFactory(void) { return &g_factory; }
 PQACORE_API void *PqaEngineFactory_CreateCpuEngine(void *pvFactory, void **ppError, const CiEngineDefinition *pEngDef) {
   (void)pvFactory;
   Engine *eng = nullptr;
-  Assign(ppError, CreateEngineImpl(pEngDef, nullptr, &eng));
+  CiB200GroupOptions g;
+  if (EnvGroupOptions(&g)) Assign(ppError, CreateGroupImpl(pEngDef, nullptr, &g, &eng));
+  else Assign(ppError, CreateEngineImpl(pEngDef, nullptr, &eng));
   return eng;
+}
+PQACORE_API void *PqaB200_CreateShardedEngine(void **ppError, const CiEngineDefinition *pEngDef, const CiB200Options *pOpts,
+                                              const CiB200GroupOptions *pGroupOpts) {
+  Engine *eng = nullptr;
+  Assign(ppError, CreateGroupImpl(pEngDef, pOpts, pGroupOpts, &eng));
+  return eng;
+}
+PQACORE_API void *PqaB200_LoadShardedEngine(void **ppError, const char *filePath, const CiB200Options *pOpts,
+                                            const CiB200GroupOptions *pGroupOpts) {
+  if (!pGroupOpts) { Assign(ppError, MakeError(ErrCode::NullArgument, "pGroupOpts is NULL")); return nullptr; }
+  CiB200Options opts;
+  if (pOpts) opts = *pOpts;
+  else { std::memset(&opts, 0, sizeof(opts)); opts._device = -1; }
+  PqaError *err = nullptr;
+  Engine *eng = nullptr;
+  PqaError *g = Guard([&]() -> PqaError * { eng = ShardGroup::LoadKBGroup(filePath, opts, *pGroupOpts, &err); return nullptr; });
+  Assign(ppError, g ? g : err);
+  return eng;
+}
+PQACORE_API int32_t PqaB200_GetShardCount(void *pvEngine) {
+  if (!pvEngine) return 0;
+  const ShardGroup *g = dynamic_cast<ShardGroup *>(E(pvEngine));
+  return g ? g->shardCount() : 1;
 }
 PQACORE_API void *PqaB200_CreateEngine(void **ppError, const CiEngineDefinition *pEngDef, const CiB200Options *pOpts) {
   Engine *eng = nullptr;
@@ -84,7 +151,12 @@ PQACORE_API void *PqaEngineFactory_LoadCpuEngine(void *pvFactory, void **ppError
   CiB200Options opts; std::memset(&opts, 0, sizeof(opts)); opts._device = -1;
   PqaError *err = nullptr;
   Engine *eng = nullptr;
-  PqaError *g = Guard([&]() -> PqaError * { eng = Engine::LoadKB(filePath, opts, &err); return nullptr; });
+  CiB200GroupOptions go;
+  const bool grouped = EnvGroupOptions(&go);
+  PqaError *g = Guard([&]() -> PqaError * {
+    eng = grouped ? static_cast<Engine *>(ShardGroup::LoadKBGroup(filePath, opts, go, &err)) : Engine::LoadKB(filePath, opts, &err);
+    return nullptr;
+  });
   Assign(ppError, g ? g : err);
   return eng;
 }

@@ -101,6 +101,27 @@ Engine::Engine(const CiEngineDefinition &def, const CiB200Options &opts) {
   PQA_CU(cudaStreamSynchronize(stream_));
 }
 
+Engine::Engine(const CiEngineDefinition &def, const CiB200Options &opts, ShellTag) {
+  Q_ = def._nQuestions; K_ = def._nAnswers; T_ = def._nTargets;
+  Tp_ = (T_ + 3) & ~3ll; TpL_ = Tp_;
+  askedWords_ = (Q_ + 63) >> 6;
+  initAmount_ = def._initAmount;
+  precMantissa_ = def._precMantissa; precExponent_ = def._precExponent;
+  qFirst_ = 0; qLocal_ = Q_; tFirst_ = 0; tLocal_ = T_;
+  qGaps_.GrowTo(Q_); tGaps_.GrowTo(T_);
+  pimQ_.GrowTo(Q_); pimT_.GrowTo(T_);
+  device_ = opts._device;
+  W_ = opts._emulatedWorkers;
+  if (W_ <= 0) W_ = env_int("PQA_B200_EMULATED_WORKERS", 0);
+  if (W_ <= 0) W_ = (int)std::thread::hardware_concurrency();
+  if (W_ <= 0) W_ = 1;
+  uint64_t seed = opts._rngSeed;
+  if (seed == 0) { std::random_device rd; seed = ((uint64_t)rd() << 32) ^ rd(); }
+  rng_[0] = seed * 0x9E3779B97F4A7C15ull + 0xD1B54A32D192ED03ull;
+  rng_[1] = (seed ^ 0xBF58476D1CE4E5B9ull) * 0x94D049BB133111EBull + 1;
+  if (!rng_[0] && !rng_[1]) rng_[1] = 1;
+}
+
 Engine::~Engine() {
   if (stream_) cudaStreamSynchronize(stream_);
   if (env_int("PQA_B200_STATS", 0) && statBatches_ > 0) {

@@ -141,12 +141,12 @@ struct CallSlot {
 class Engine {
  public:
   Engine(const CiEngineDefinition &def, const CiB200Options &opts);
-  ~Engine();
+  virtual ~Engine();
 
   // --- IPqaEngine mirror (one quiz per call) ---
-  PqaError *Train(int64_t nQuestions, const CiAnsweredQuestion *pAQs, int64_t iTarget, double amount);
+  virtual PqaError *Train(int64_t nQuestions, const CiAnsweredQuestion *pAQs, int64_t iTarget, double amount);
   int64_t StartQuiz(PqaError **err);
-  int64_t ResumeQuiz(PqaError **err, int64_t nAnswered, const CiAnsweredQuestion *pAQs);
+  virtual int64_t ResumeQuiz(PqaError **err, int64_t nAnswered, const CiAnsweredQuestion *pAQs);
   int64_t NextQuestion(PqaError **err, int64_t iQuiz);
   PqaError *RecordAnswer(int64_t iQuiz, int64_t iAnswer);
   int64_t GetActiveQuestionId(PqaError **err, int64_t iQuiz);
@@ -156,89 +156,93 @@ class Engine {
   PqaError *ReleaseQuiz(int64_t iQuiz);
   uint64_t GetTotalQuestionsAsked() const { return nQuestionsAsked_.load(std::memory_order_relaxed); }
   CiEngineDimensions CopyDims() const { return CiEngineDimensions{K_, Q_, T_}; }
-  PqaError *CopyATargets(int64_t iQuestion, int64_t iAnswer, int64_t maxTargets, double *pFreqs);
-  PqaError *CopyDTargets(int64_t iQuestion, int64_t maxTargets, double *pFreqs);
-  PqaError *CopyBTargets(int64_t maxTargets, double *pFreqs);
-  PqaError *SaveKB(const char *filePath);
-  PqaError *SaveKBShard(const char *filePath, bool writeFrame);   // sharded engines: every shard writes its cells into one file
+  virtual PqaError *CopyATargets(int64_t iQuestion, int64_t iAnswer, int64_t maxTargets, double *pFreqs);
+  virtual PqaError *CopyDTargets(int64_t iQuestion, int64_t maxTargets, double *pFreqs);
+  virtual PqaError *CopyBTargets(int64_t maxTargets, double *pFreqs);
+  virtual PqaError *SaveKB(const char *filePath);
+  virtual PqaError *SaveKBShard(const char *filePath, bool writeFrame);   // sharded engines: every shard writes its cells into one file
   static Engine *LoadKB(const char *filePath, const CiB200Options &opts, PqaError **err);
 
   // --- maintenance mode (BaseEngine.cpp:640-779, CpuEngine.cpp:468-658) and id maps (BaseEngine.cpp:154-218) ---
-  PqaError *ClearOldQuizzes(int64_t maxCount, double maxAgeSec);   // BaseEngine.cpp:814-872
-  PqaError *StartMaintenance(bool forceQuizzes);
-  PqaError *FinishMaintenance();
-  PqaError *AddQsTs(int64_t nQuestions, CiAddQorTParam *pAqps, int64_t nTargets, CiAddQorTParam *pAtps);
-  PqaError *RemoveQuestions(int64_t nQuestions, const int64_t *pQIds);
-  PqaError *RemoveTargets(int64_t nTargets, const int64_t *pTIds);
-  PqaError *Compact(int64_t *pnQuestions, const int64_t **ppOldQuestions, int64_t *pnTargets, const int64_t **ppOldTargets);
+  virtual PqaError *ClearOldQuizzes(int64_t maxCount, double maxAgeSec);   // BaseEngine.cpp:814-872
+  virtual PqaError *StartMaintenance(bool forceQuizzes);
+  virtual PqaError *FinishMaintenance();
+  virtual PqaError *AddQsTs(int64_t nQuestions, CiAddQorTParam *pAqps, int64_t nTargets, CiAddQorTParam *pAtps);
+  virtual PqaError *RemoveQuestions(int64_t nQuestions, const int64_t *pQIds);
+  virtual PqaError *RemoveTargets(int64_t nTargets, const int64_t *pTIds);
+  virtual PqaError *Compact(int64_t *pnQuestions, const int64_t **ppOldQuestions, int64_t *pnTargets, const int64_t **ppOldTargets);
   bool MapIds(int kind, bool permFromComp, int64_t count, int64_t *pIds);   // kind: 0 questions, 1 targets, 2 quizzes
   bool EnsurePermQuizGreater(int64_t bound);
   bool RemapQuizPermId(int64_t srcPermId, int64_t destPermId);
 
   // --- batches of concurrent quizzes ---
-  PqaError *StartQuizBatch(int64_t n, int64_t *pQuizIds);
-  PqaError *ResumeQuizBatch(int64_t n, const int64_t *pCounts, const CiAnsweredQuestion *pAQs, int64_t *pQuizIds);
-  PqaError *NextQuestionBatch(int64_t n, const int64_t *pQuizIds, const uint64_t *pRandoms, int64_t *pQuestions,
+  virtual PqaError *StartQuizBatch(int64_t n, int64_t *pQuizIds);
+  virtual PqaError *ResumeQuizBatch(int64_t n, const int64_t *pCounts, const CiAnsweredQuestion *pAQs, int64_t *pQuizIds);
+  virtual PqaError *NextQuestionBatch(int64_t n, const int64_t *pQuizIds, const uint64_t *pRandoms, int64_t *pQuestions,
                               void **ppErrors);
-  PqaError *RecordAnswerBatch(int64_t n, const int64_t *pQuizIds, const int64_t *pAnswers);
-  PqaError *SetActiveQuestionBatch(int64_t n, const int64_t *pQuizIds, const int64_t *pQuestions);
-  PqaError *ListTopTargetsBatch(int64_t n, const int64_t *pQuizIds, int64_t maxCount, CiRatedTarget *pDest,
+  virtual PqaError *RecordAnswerBatch(int64_t n, const int64_t *pQuizIds, const int64_t *pAnswers);
+  virtual PqaError *SetActiveQuestionBatch(int64_t n, const int64_t *pQuizIds, const int64_t *pQuestions);
+  virtual PqaError *ListTopTargetsBatch(int64_t n, const int64_t *pQuizIds, int64_t maxCount, CiRatedTarget *pDest,
                                 int64_t *pCounts);
-  PqaError *RecordQuizTargetBatch(int64_t n, const int64_t *pQuizIds, const int64_t *pTargets, const double *pAmounts);
-  PqaError *ReleaseQuizBatch(int64_t n, const int64_t *pQuizIds);
+  virtual PqaError *RecordQuizTargetBatch(int64_t n, const int64_t *pQuizIds, const int64_t *pTargets, const double *pAmounts);
+  virtual PqaError *ReleaseQuizBatch(int64_t n, const int64_t *pQuizIds);
 
   // --- KB transfer / inspection ---
-  PqaError *UploadKB(const double *sA, const double *mD, const double *vB);
-  PqaError *DownloadKB(double *sA, double *mD, double *vB);
-  PqaError *CopyQuizPriors(int64_t iQuiz, double *pPriors);
-  PqaError *SetQuizPriors(int64_t iQuiz, const double *pPriors);
-  PqaError *EvalQuestions(int64_t n, const int64_t *pQuizIds, double *pPriorities, double *pRunLength,
+  virtual PqaError *UploadKB(const double *sA, const double *mD, const double *vB);
+  virtual PqaError *DownloadKB(double *sA, double *mD, double *vB);
+  virtual PqaError *CopyQuizPriors(int64_t iQuiz, double *pPriors);
+  virtual PqaError *SetQuizPriors(int64_t iQuiz, const double *pPriors);
+  virtual PqaError *EvalQuestions(int64_t n, const int64_t *pQuizIds, double *pPriorities, double *pRunLength,
                           double *pGrandTotals, int64_t *pnChunks);
-  PqaError *EvalQuestionsDetailed(int64_t iQuiz, double *pW, double *pH, double *pV, double *pLack, double *pPriorities);
-  PqaError *SetEvalKernel(int32_t which, int64_t chunkTargets, int64_t quizzesPerCta, int32_t kahanLanesPerThread);
+  virtual PqaError *EvalQuestionsDetailed(int64_t iQuiz, double *pW, double *pH, double *pV, double *pLack, double *pPriorities);
+  virtual PqaError *SetEvalKernel(int32_t which, int64_t chunkTargets, int64_t quizzesPerCta, int32_t kahanLanesPerThread);
 
   // --- question-sharded operation (PqaB200Ext.h) ---
-  PqaError *ShardEval(int64_t n, const int64_t *pQuizIds);
-  PqaError *ShardSelect(int64_t n, const int64_t *pQuizIds, const uint64_t *pRandoms, int64_t *pQuestions, void **ppErrors);
-  PqaError *ShardRecordAnswerBegin(int64_t n, const int64_t *pQuizIds, const int64_t *pAnswers);
-  PqaError *ShardRecordAnswerEnd(int64_t n, const int64_t *pQuizIds);
-  PqaError *ShardBuffer(int32_t which, void **ppDevice, int64_t *pCount);
+  virtual PqaError *ShardEval(int64_t n, const int64_t *pQuizIds);
+  virtual PqaError *ShardSelect(int64_t n, const int64_t *pQuizIds, const uint64_t *pRandoms, int64_t *pQuestions, void **ppErrors);
+  virtual PqaError *ShardRecordAnswerBegin(int64_t n, const int64_t *pQuizIds, const int64_t *pAnswers);
+  virtual PqaError *ShardRecordAnswerEnd(int64_t n, const int64_t *pQuizIds);
+  virtual PqaError *ShardBuffer(int32_t which, void **ppDevice, int64_t *pCount);
   int64_t questionShardFirst() const { return qFirst_; }
   int64_t questionShardCount() const { return qLocal_; }
 
   // --- target-sharded operation (PqaB200Ext.h) ---
-  PqaError *TShardEvalW(int64_t n, const int64_t *pQuizIds);
-  PqaError *TShardEvalHVL(int64_t n, const int64_t *pQuizIds);
-  PqaError *TShardPriority(int64_t n, const int64_t *pQuizIds);
+  virtual PqaError *TShardEvalW(int64_t n, const int64_t *pQuizIds);
+  virtual PqaError *TShardEvalHVL(int64_t n, const int64_t *pQuizIds);
+  virtual PqaError *TShardPriority(int64_t n, const int64_t *pQuizIds);
   int64_t targetShardFirst() const { return tFirst_; }
   int64_t targetShardCount() const { return tLocal_; }
   bool IsTargetSharded() const { return tLocal_ != T_; }
   bool IsSharded() const { return qLocal_ != Q_ || tLocal_ != T_; }
   // --- shard exchange over peer memory (PqaB200Ext.h "P2P" entry points); works for question and target shards ---
-  PqaError *P2PInit(int32_t rank, int32_t nRanks, int64_t maxQuizzes, void **ppBase, int64_t *pBytes);
-  PqaError *P2PExportHandle(uint8_t *pHandle64);
-  PqaError *P2POpenHandle(const uint8_t *pHandle64, void **ppPeerBase);
-  PqaError *P2PConnect(void *const *pBases);
-  PqaError *P2PNextQuestionBegin(int64_t n, const int64_t *pQuizIds, const uint64_t *pRandoms);
-  PqaError *P2PNextQuestionEnd(int64_t n, const int64_t *pQuizIds, int64_t *pQuestions, void **ppErrors);
-  PqaError *P2PRecordAnswerBegin(int64_t n, const int64_t *pQuizIds, const int64_t *pAnswers);
-  PqaError *P2PRecordAnswerEnd();
-  PqaError *P2PSetExactOrder(int32_t on);   // target shards: hand the Kahan lanes from shard to shard (W_k bit-exact)
+  virtual PqaError *P2PInit(int32_t rank, int32_t nRanks, int64_t maxQuizzes, void **ppBase, int64_t *pBytes);
+  virtual PqaError *P2PExportHandle(uint8_t *pHandle64);
+  virtual PqaError *P2POpenHandle(const uint8_t *pHandle64, void **ppPeerBase);
+  virtual PqaError *P2PConnect(void *const *pBases);
+  virtual PqaError *P2PNextQuestionBegin(int64_t n, const int64_t *pQuizIds, const uint64_t *pRandoms);
+  virtual PqaError *P2PNextQuestionEnd(int64_t n, const int64_t *pQuizIds, int64_t *pQuestions, void **ppErrors);
+  virtual PqaError *P2PRecordAnswerBegin(int64_t n, const int64_t *pQuizIds, const int64_t *pAnswers);
+  virtual PqaError *P2PRecordAnswerEnd();
+  virtual PqaError *P2PSetExactOrder(int32_t on);   // target shards: hand the Kahan lanes from shard to shard (W_k bit-exact)
   // closed-form synthetic KB of SURVEY.md 8d written on the device (this engine's shard of it)
-  PqaError *FillBinarySearchKB(double rounds);
+  virtual PqaError *FillBinarySearchKB(double rounds);
 
   // --- device-resident stepping ---
-  PqaError *ResidentBind(int64_t n, const int64_t *pQuizIds, const uint64_t *pRandoms);
-  PqaError *ResidentStep();
-  PqaError *ResidentFetch(int64_t *pQuestions);
-  double ResidentLastEvalMs();   // device time of the evaluation kernel of the most recent ResidentStep (-1 on error)
-  PqaError *Synchronize();
-  PqaError *FlushL2();
+  virtual PqaError *ResidentBind(int64_t n, const int64_t *pQuizIds, const uint64_t *pRandoms);
+  virtual PqaError *ResidentStep();
+  virtual PqaError *ResidentFetch(int64_t *pQuestions);
+  virtual double ResidentLastEvalMs();   // device time of the evaluation kernel of the most recent ResidentStep (-1 on error)
+  virtual PqaError *Synchronize();
+  virtual PqaError *FlushL2();
   cudaStream_t stream() const { return stream_; }
   int device() const { return device_; }
   int emulatedWorkers() const { return W_; }
 
- private:
+ protected:
+  // A shell without device state: the host-side quiz registry, id maps and the call combiner of an engine whose KB lives
+  // in other engines (ShardGroup, pqa_group.h).
+  struct ShellTag {};
+  Engine(const CiEngineDefinition &def, const CiB200Options &opts, ShellTag);
   void Submit(CallSlot &slot);                           // flat combining of concurrent one-quiz calls
   void RunCombined(const std::vector<CallSlot *> &batch);
   PqaError *CheckQuiz(int64_t iQuiz) const;              // BaseEngine::UseQuiz, BaseEngine.cpp:399-419

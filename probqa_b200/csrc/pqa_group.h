@@ -1,0 +1,90 @@
+// probqa_b200: one engine over several GPUs of a box, in ONE process, behind the reference's C ABI.
+// A ShardGroup owns N shard engines (question shards or target shards, pqa_engine.h), one per device, wires their
+// peer-memory inboxes together (PqaB200_P2P*: the kernels exchange over NVLink, no host round trip, no NCCL) and
+// presents the IPqaEngine method set: StartQuiz / NextQuestion / RecordAnswer / ListTopTargets / RecordQuizTarget / Train /
+// ReleaseQuiz / SaveKB ... and their batch forms. It is itself an Engine *shell*: the quiz registry, id validation, error
+// objects and the combiner of concurrent one-quiz calls are the base class's; only the device work is fanned out.
+#pragma once
+#include <memory>
+#include <vector>
+
+#include "pqa_engine.h"
+
+namespace pqa {
+
+class ShardGroup : public Engine {
+ public:
+  ShardGroup(const CiEngineDefinition &def, const CiB200Options &opts, const CiB200GroupOptions &gopts);
+  ~ShardGroup() override;
+  static ShardGroup *LoadKBGroup(const char *filePath, const CiB200Options &opts, const CiB200GroupOptions &gopts, PqaError **err);
+
+  PqaError *Train(int64_t nQuestions, const CiAnsweredQuestion *pAQs, int64_t iTarget, double amount) override;
+  PqaError *StartQuizBatch(int64_t n, int64_t *pQuizIds) override;
+  PqaError *NextQuestionBatch(int64_t n, const int64_t *pQuizIds, const uint64_t *pRandoms, int64_t *pQuestions,
+                              void **ppErrors) override;
+  PqaError *RecordAnswerBatch(int64_t n, const int64_t *pQuizIds, const int64_t *pAnswers) override;
+  PqaError *SetActiveQuestionBatch(int64_t n, const int64_t *pQuizIds, const int64_t *pQuestions) override;
+  PqaError *ListTopTargetsBatch(int64_t n, const int64_t *pQuizIds, int64_t maxCount, CiRatedTarget *pDest,
+                                int64_t *pCounts) override;
+  PqaError *RecordQuizTargetBatch(int64_t n, const int64_t *pQuizIds, const int64_t *pTargets, const double *pAmounts) override;
+  PqaError *ReleaseQuizBatch(int64_t n, const int64_t *pQuizIds) override;
+  PqaError *CopyATargets(int64_t iQuestion, int64_t iAnswer, int64_t maxTargets, double *pFreqs) override;
+  PqaError *CopyDTargets(int64_t iQuestion, int64_t maxTargets, double *pFreqs) override;
+  PqaError *CopyBTargets(int64_t maxTargets, double *pFreqs) override;
+  PqaError *SaveKB(const char *filePath) override;
+  PqaError *UploadKB(const double *sA, const double *mD, const double *vB) override;
+  PqaError *DownloadKB(double *sA, double *mD, double *vB) override;
+  PqaError *CopyQuizPriors(int64_t iQuiz, double *pPriors) override;
+  PqaError *FillBinarySearchKB(double rounds) override;
+  PqaError *Synchronize() override;
+  PqaError *SetEvalKernel(int32_t which, int64_t chunkTargets, int64_t quizzesPerCta, int32_t kahanLanesPerThread) override;
+
+  // single-engine features a group does not offer
+  PqaError *ResumeQuizBatch(int64_t, const int64_t *, const CiAnsweredQuestion *, int64_t *) override { return No("ResumeQuiz"); }
+  PqaError *SaveKBShard(const char *, bool) override { return No("SaveKBShard (use SaveKB)"); }
+  PqaError *ClearOldQuizzes(int64_t, double) override { return No("ClearOldQuizzes"); }
+  PqaError *StartMaintenance(bool) override { return No("maintenance mode"); }
+  PqaError *FinishMaintenance() override { return No("maintenance mode"); }
+  PqaError *AddQsTs(int64_t, CiAddQorTParam *, int64_t, CiAddQorTParam *) override { return No("maintenance mode"); }
+  PqaError *RemoveQuestions(int64_t, const int64_t *) override { return No("maintenance mode"); }
+  PqaError *RemoveTargets(int64_t, const int64_t *) override { return No("maintenance mode"); }
+  PqaError *Compact(int64_t *, const int64_t **, int64_t *, const int64_t **) override { return No("maintenance mode"); }
+  PqaError *SetQuizPriors(int64_t, const double *) override { return No("SetQuizPriors"); }
+  PqaError *EvalQuestions(int64_t, const int64_t *, double *, double *, double *, int64_t *) override { return No("EvalQuestions"); }
+  PqaError *EvalQuestionsDetailed(int64_t, double *, double *, double *, double *, double *) override { return No("EvalQuestionsDetailed"); }
+  PqaError *ShardEval(int64_t, const int64_t *) override { return No("Shard* protocol (the group drives its shards itself)"); }
+  PqaError *ShardSelect(int64_t, const int64_t *, const uint64_t *, int64_t *, void **) override { return No("Shard* protocol"); }
+  PqaError *ShardRecordAnswerBegin(int64_t, const int64_t *, const int64_t *) override { return No("Shard* protocol"); }
+  PqaError *ShardRecordAnswerEnd(int64_t, const int64_t *) override { return No("Shard* protocol"); }
+  PqaError *ShardBuffer(int32_t, void **, int64_t *) override { return No("Shard* protocol"); }
+  PqaError *TShardEvalW(int64_t, const int64_t *) override { return No("TShard* protocol"); }
+  PqaError *TShardEvalHVL(int64_t, const int64_t *) override { return No("TShard* protocol"); }
+  PqaError *TShardPriority(int64_t, const int64_t *) override { return No("TShard* protocol"); }
+  PqaError *P2PInit(int32_t, int32_t, int64_t, void **, int64_t *) override { return No("P2P* protocol"); }
+  PqaError *P2PExportHandle(uint8_t *) override { return No("P2P* protocol"); }
+  PqaError *P2POpenHandle(const uint8_t *, void **) override { return No("P2P* protocol"); }
+  PqaError *P2PConnect(void *const *) override { return No("P2P* protocol"); }
+  PqaError *P2PNextQuestionBegin(int64_t, const int64_t *, const uint64_t *) override { return No("P2P* protocol"); }
+  PqaError *P2PNextQuestionEnd(int64_t, const int64_t *, int64_t *, void **) override { return No("P2P* protocol"); }
+  PqaError *P2PRecordAnswerBegin(int64_t, const int64_t *, const int64_t *) override { return No("P2P* protocol"); }
+  PqaError *P2PRecordAnswerEnd() override { return No("P2P* protocol"); }
+  PqaError *P2PSetExactOrder(int32_t) override { return No("P2P* protocol (CiB200GroupOptions::_exactOrder)"); }
+  PqaError *ResidentBind(int64_t, const int64_t *, const uint64_t *) override { return No("resident stepping"); }
+  PqaError *ResidentStep() override { return No("resident stepping"); }
+  PqaError *ResidentFetch(int64_t *) override { return No("resident stepping"); }
+  double ResidentLastEvalMs() override { return -1.0; }
+  PqaError *FlushL2() override { return No("FlushL2"); }
+
+  int shardCount() const { return (int)shards_.size(); }
+
+ private:
+  ShardGroup(const CiEngineDefinition &def, const CiB200Options &opts) : Engine(def, opts, ShellTag{}) {}   // shards added by LoadKBGroup
+  static PqaError *No(const char *what) { return ErrNotImplemented(std::string("sharded engine group: ") + what); }
+  void Connect(const CiB200GroupOptions &gopts);
+  static std::vector<CiB200Options> ShardOptions(const CiEngineDefinition &def, const CiB200Options &opts,
+                                                 const CiB200GroupOptions &gopts);
+  std::vector<std::unique_ptr<Engine>> shards_;
+  int64_t cap_ = 256;          // quizzes per exchanged call (inbox size); longer batches are cut into slices
+};
+
+} // namespace pqa

@@ -45,6 +45,12 @@ class CiAddQorTParam(C.Structure):  # :37-40
     _fields_ = [("index", C.c_int64), ("initAmount", C.c_double)]
 
 
+class CiB200GroupOptions(C.Structure):  # PqaB200Ext.h
+    _pack_ = 8
+    _fields_ = [("axis", C.c_int32), ("nShards", C.c_int32), ("devices", C.c_int32 * 8), ("exactOrder", C.c_int32),
+                ("maxBatch", C.c_int64)]
+
+
 class CiB200Options(C.Structure):  # PqaB200Ext.h
     _pack_ = 8
     _fields_ = [("device", C.c_int32), ("emulatedWorkers", C.c_int32), ("rngSeed", C.c_uint64),
@@ -103,6 +109,9 @@ SIGNATURES = {
     # ---- PqaB200Ext.h
     "PqaB200_CreateEngine": (_vp, [_pvp, C.POINTER(CiEngineDefinition), C.POINTER(CiB200Options)]),
     "PqaB200_LoadEngine": (_vp, [_pvp, C.c_char_p, C.POINTER(CiB200Options)]),
+    "PqaB200_CreateShardedEngine": (_vp, [_pvp, C.POINTER(CiEngineDefinition), C.POINTER(CiB200Options), C.POINTER(CiB200GroupOptions)]),
+    "PqaB200_LoadShardedEngine": (_vp, [_pvp, C.c_char_p, C.POINTER(CiB200Options), C.POINTER(CiB200GroupOptions)]),
+    "PqaB200_GetShardCount": (C.c_int32, [_vp]),
     "PqaB200_SaveKBShard": (_vp, [_vp, C.c_char_p, C.c_int32]),
     "PqaB200_GetEmulatedWorkers": (C.c_int32, [_vp]),
     "PqaB200_GetDevice": (C.c_int32, [_vp]),
@@ -694,6 +703,9 @@ class PqaEngine:
     def flush_l2(self):
         _raise_or_return(self._lib.PqaB200_FlushL2(self.c_engine))
 
+    def shard_count(self) -> int:
+        return int(self._lib.PqaB200_GetShardCount(self.c_engine))
+
     def kernel_launch_count(self) -> int:
         return self._lib.PqaB200_KernelLaunchCount(self.c_engine)
 
@@ -749,6 +761,40 @@ class PqaEngineFactory:
                              question_shard_count, target_shard_first, target_shard_count)
         e = C.c_void_p()
         c_engine = self._lib.PqaB200_CreateEngine(C.byref(e), C.byref(c_def), C.byref(opts))
+        if not c_engine:
+            raise PqaException(PqaError.factor(e.value))
+        return PqaEngine(c_engine)
+
+    @staticmethod
+    def _group_options(axis, n_shards, devices, exact_order, max_batch):
+        g = CiB200GroupOptions()
+        g.axis = {"questions": 0, "targets": 1}[axis]
+        g.nShards = n_shards
+        for r in range(8):
+            g.devices[r] = devices[r] if devices is not None and r < len(devices) else -1
+        g.exactOrder = 1 if exact_order else 0
+        g.maxBatch = max_batch
+        return g
+
+    def create_sharded_engine(self, eng_def: EngineDefinition, axis: str, n_shards: int, devices=None, exact_order: bool = False,
+                              max_batch: int = 0, emulated_workers: int = 0, rng_seed: int = 0, initial_quiz_capacity: int = 0) -> PqaEngine:
+        """One engine handle over n_shards shard engines of THIS process (one per listed device; several shards may share
+        a device), exchanging over peer memory. The handle serves the reference ABI and the batch calls like one engine."""
+        c_def = eng_def.to_c()
+        opts = CiB200Options(-1, emulated_workers, rng_seed, initial_quiz_capacity, 0, 0, 0, 0)
+        g = self._group_options(axis, n_shards, devices, exact_order, max_batch)
+        e = C.c_void_p()
+        c_engine = self._lib.PqaB200_CreateShardedEngine(C.byref(e), C.byref(c_def), C.byref(opts), C.byref(g))
+        if not c_engine:
+            raise PqaException(PqaError.factor(e.value))
+        return PqaEngine(c_engine)
+
+    def load_sharded_engine(self, file_path: str, axis: str, n_shards: int, devices=None, exact_order: bool = False,
+                            max_batch: int = 0, emulated_workers: int = 0, rng_seed: int = 0) -> PqaEngine:
+        opts = CiB200Options(-1, emulated_workers, rng_seed, 0, 0, 0, 0, 0)
+        g = self._group_options(axis, n_shards, devices, exact_order, max_batch)
+        e = C.c_void_p()
+        c_engine = self._lib.PqaB200_LoadShardedEngine(C.byref(e), file_path.encode(), C.byref(opts), C.byref(g))
         if not c_engine:
             raise PqaException(PqaError.factor(e.value))
         return PqaEngine(c_engine)

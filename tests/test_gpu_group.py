@@ -1,0 +1,151 @@
+"""A sharded engine group (PqaB200_CreateShardedEngine): N shard engines of one process behind ONE engine handle that
+serves the reference's C ABI. Run here with all shards on one GPU (on a multi-GPU box pass devices=[0, 1, ...]); the
+results must be those of a single engine."""
+import json
+import os
+import subprocess
+import threading
+
+import numpy as np
+import pytest
+
+from probqa_b200 import synth
+
+pytestmark = pytest.mark.gpu
+INIT = 0.1
+
+
+def bits(a):
+    return np.ascontiguousarray(a, dtype=np.float64).view(np.uint64)
+
+
+def devices(n):
+    import torch
+    have = torch.cuda.device_count()
+    return [r % have for r in range(n)]
+
+
+@pytest.mark.parametrize("axis,dims,n_shards,exact", [("questions", (40, 5, 203), 3, False), ("targets", (36, 5, 1000), 2, True),
+                                                      ("targets", (25, 4, 96), 4, False)])
+def test_group_behaves_like_one_engine(axis, dims, n_shards, exact, tmp_path):
+    from probqa_b200 import engine as pqa
+    Q, K, T = dims
+    W = 6
+    kb = synth.gamma_kb(Q, K, T, INIT)
+    fac = pqa.PqaEngineFactory()
+    edef = pqa.EngineDefinition(K, Q, T, init_amount=INIT)
+    one = fac.create_b200_engine(edef, emulated_workers=W, rng_seed=5)
+    grp = fac.create_sharded_engine(edef, axis, n_shards, devices=devices(n_shards), exact_order=exact, max_batch=16,
+                                    emulated_workers=W, rng_seed=5)
+    assert grp.shard_count() == n_shards and one.shard_count() == 1
+    one.upload_kb(*kb); grp.upload_kb(*kb)
+    n = 37                                                   # more than max_batch: the group cuts the batch into slices
+    ids = one.start_quiz_batch(n)
+    assert np.array_equal(ids, grp.start_quiz_batch(n))
+    rng = np.random.default_rng(82)
+    for step in range(3):
+        randoms = rng.integers(0, 2 ** 64, size=n, dtype=np.uint64)
+        c_one = one.next_question_batch(ids, randoms)
+        c_grp = grp.next_question_batch(ids, randoms)
+        if axis == "questions":
+            assert np.array_equal(c_one, c_grp)             # bit-identical priorities -> identical choices
+        else:
+            one.set_active_question_batch(ids, c_grp)       # target shards: tolerance-level priorities, follow the group
+        assert grp.get_active_question_id(int(ids[3])) == c_grp[3]
+        answers = [(int(c) * 7 + step) % K for c in c_grp]
+        one.record_answer_batch(ids, answers)
+        grp.record_answer_batch(ids, answers)
+        for q in ids[:6]:
+            assert np.array_equal(bits(grp.copy_quiz_priors(int(q))), bits(one.copy_quiz_priors(int(q))))
+        a, ca = grp.list_top_targets_batch(ids, 10)
+        b, cb = one.list_top_targets_batch(ids, 10)
+        assert np.array_equal(ca, cb) and a.tobytes() == b.tobytes()
+    # the reference's one-quiz entry points on the group handle
+    q1 = grp.start_quiz(); q1b = one.start_quiz()
+    assert q1 == q1b
+    nq = grp.next_question(q1)
+    one.next_question(q1b)                                   # (counts as a question asked on both sides)
+    one.set_active_question(q1b, nq)
+    grp.record_answer(q1, 2); one.record_answer(q1b, 2)
+    assert [(r.i_target, r.prob) for r in grp.list_top_targets(q1, 5)] == [(r.i_target, r.prob) for r in one.list_top_targets(q1b, 5)]
+    grp.record_quiz_target(q1, 7, 1.5); one.record_quiz_target(q1b, 7, 1.5)
+    grp.release_quiz(q1); one.release_quiz(q1b)
+    with pytest.raises(pqa.PqaException):
+        grp.next_question(q1)
+    # training and the KB
+    targets = rng.integers(0, T, size=n)
+    grp.record_quiz_target_batch(ids, targets); one.record_quiz_target_batch(ids, targets)
+    aqs = [pqa.AnsweredQuestion(1, 2), pqa.AnsweredQuestion(3, 0), pqa.AnsweredQuestion(1, 1)]
+    grp.train(aqs, 5, 0.75); one.train(aqs, 5, 0.75)
+    assert grp.train([pqa.AnsweredQuestion(Q, 0)], 1, 1.0, throw=False) is not None
+    for g, w in zip(grp.download_kb(), one.download_kb()):
+        assert np.array_equal(bits(g), bits(w))
+    assert np.array_equal(bits(grp.copy_a_targets(2, 1)), bits(one.copy_a_targets(2, 1)))
+    assert np.array_equal(bits(grp.copy_d_targets(2)), bits(one.copy_d_targets(2)))
+    assert grp.get_total_questions_asked() == one.get_total_questions_asked()
+    pg, po = str(tmp_path / "g.kb"), str(tmp_path / "o.kb")
+    grp.save_kb(pg); one.save_kb(po)
+    assert open(pg, "rb").read() == open(po, "rb").read()
+    again = fac.load_sharded_engine(pg, axis, n_shards, devices=devices(n_shards), emulated_workers=W)
+    for g, w in zip(again.download_kb(), one.download_kb()):
+        assert np.array_equal(bits(g), bits(w))
+    quiz = again.start_quiz()
+    assert 0 <= again.next_question(quiz) < Q
+    assert grp.start_maintenance(True, throw=False) is not None      # single-engine feature
+
+
+def test_group_serves_concurrent_one_quiz_clients():
+    """Client threads call the reference's one-quiz entry points on a group handle; the shell's combiner turns them into
+    exchanged batch launches on all shards. Every quiz must end with the posterior a single engine computes for the same
+    (question, answer) sequence."""
+    from probqa_b200 import engine as pqa
+    Q, K, T, W = 48, 5, 400, 4
+    kb = synth.binary_search_kb(Q, K, T, INIT, 3)
+    fac = pqa.PqaEngineFactory()
+    edef = pqa.EngineDefinition(K, Q, T, init_amount=INIT)
+    grp = fac.create_sharded_engine(edef, "targets", 2, devices=devices(2), exact_order=True, emulated_workers=W, rng_seed=9)
+    one = fac.create_b200_engine(edef, emulated_workers=W, rng_seed=9)
+    grp.upload_kb(*kb); one.upload_kb(*kb)
+    logs, errors = {}, []
+
+    def client(x):
+        try:
+            quiz = grp.start_quiz()
+            seq = []
+            for step in range(5):
+                q = grp.next_question(quiz)
+                a = (q + x + step) % K
+                grp.record_answer(quiz, a)
+                seq.append((q, a))
+                grp.list_top_targets(quiz, 3)
+            logs[x] = (quiz, seq)
+        except Exception as ex:          # noqa: BLE001
+            errors.append(repr(ex))
+
+    threads = [threading.Thread(target=client, args=(x,)) for x in range(12)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    for x, (quiz, seq) in logs.items():
+        ref_quiz = one.start_quiz()
+        for q, a in seq:
+            one.set_active_question(ref_quiz, q)
+            one.record_answer(ref_quiz, a)
+        assert np.array_equal(bits(grp.copy_quiz_priors(quiz)), bits(one.copy_quiz_priors(ref_quiz)))
+
+
+def test_reference_client_loop_on_a_group(tmp_path):
+    """The reference's own client program, unmodified, on a two-shard group: PQA_B200_SHARDS makes the reference factory
+    call hand out the group."""
+    from probqa_b200 import build
+    exe = build.build_client()
+    env = dict(os.environ, PQA_B200_SHARDS="2", PQA_B200_SHARD_AXIS="targets", PQA_B200_SHARD_DEVICES=",".join(map(str, devices(2))),
+               PQA_B200_SHARD_EXACT="1")
+    out = subprocess.run([exe, "--trainings", "3000", "--learners", "32", "--report-every", "1024", "--progress", str(tmp_path / "p.txt")],
+                         capture_output=True, text=True, timeout=600, env=env)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["failed"] is False and line["questions_asked"] > 3000
+    print("pqa_client on a 2-shard group:", json.dumps(line))
