@@ -317,6 +317,61 @@ def bench_sharded(args, cfg, pqa, dist, rank, world, local_rank, cores, barrier,
         dist.destroy_process_group()
 
 
+def bench_group(args, cfg, pqa, cores):
+    """One process, one engine handle over --group GPUs (ShardGroup): the same NextQuestion batch through the ordinary
+    PqaEngine_NextQuestionBatch call. Strong scaling; value == e2e (host buffers, wall clock)."""
+    import torch
+    Q, K, T, B = cfg["Q"], cfg["K"], cfg["T"], cfg["B"]
+    axis = args.shard if args.shard in ("questions", "targets") else "targets"
+    have = torch.cuda.device_count()
+    eng = pqa.PqaEngineFactory().create_sharded_engine(pqa.EngineDefinition(K, Q, T, init_amount=INIT), axis, args.group,
+                                                       devices=[r % have for r in range(args.group)], exact_order=args.exact_order,
+                                                       max_batch=B, emulated_workers=cores, rng_seed=1234, initial_quiz_capacity=B)
+    eng.fill_binary_search_kb(3)
+    states = quiz_states(cfg, 0, B)
+    quizzes = eng.start_quiz_batch(B)
+    for s in range(max(DEPTHS)):
+        sel = [x for x in range(B) if len(states[x]) > s]
+        if not sel:
+            break
+        eng.set_active_question_batch(quizzes[sel], [states[x][s][0] for x in sel])
+        eng.record_answer_batch(quizzes[sel], [states[x][s][1] for x in sel])
+    qevals_step = int(sum(Q - len(pf) for pf in states))
+    randoms = np.random.default_rng(99).integers(0, 2 ** 64, size=B, dtype=np.uint64)
+    for _ in range(args.warmup):
+        chosen = eng.next_question_batch(quizzes, randoms)
+    sampler = ClockSampler(0)
+    sampler.start()
+    launches0 = eng.kernel_launch_count()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        chosen = eng.next_question_batch(quizzes, randoms)
+    dt = time.perf_counter() - t0
+    launches = eng.kernel_launch_count() - launches0
+    clocks = sampler.stop()
+    assert np.all((chosen >= 0) & (chosen < Q))
+    value = qevals_step * args.steps / dt
+    peak, peak_src = measured_peak()
+    per_gpu = qevals_step * (K + 1) * T * 8 / (dt / args.steps) / 1e9 / min(args.group, have)
+    line = {
+        "metric": METRIC, "value": value, "unit": "questions/s", "n_gpus": min(args.group, have), "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": args.workload, "Q": Q, "A": K, "T": T, "batch_total": B, "quiz_depths": list(DEPTHS),
+                   "kb": "binary_search_kb(init=0.1, rounds=3), filled on the device",
+                   "parallelism": "ONE process, one engine handle (ShardGroup) over %d shards on %d GPU(s), %s sharded, peer-memory exchange%s"
+                                  % (args.group, min(args.group, have), axis, ", exact-order pipeline" if args.exact_order and axis == "targets" else ""),
+                   "timing": "wall clock around PqaEngine_NextQuestionBatch on the group handle (host buffers)",
+                   "chosen_checksum": int(np.sum(chosen * (np.arange(B) + 1)) % 1000000007)},
+        "e2e": {"value": value, "unit": "questions/s", "h2d_bytes_per_step": int(B * 16 * args.group), "d2h_bytes_per_step": int(B * 8 * args.group),
+                "api": "PqaEngine_NextQuestionBatch (group handle)"},
+        "gpu_launches": int(launches), "clocks": clocks,
+        "roofline": {"bound": "hbm", "achieved": per_gpu, "peak": peak, "unit": "GB/s", "frac": per_gpu / peak, "traffic": None,
+                     "peak_source": peak_src, "note": "per GPU, whole step, algorithmic bytes"},
+    }
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -329,6 +384,8 @@ def main():
     ap.add_argument("--chunk-targets", type=int, default=0)
     ap.add_argument("--lanes", type=int, default=0, help="Kahan lanes per thread of the staged kernel: 0 auto, 1, 4")
     ap.add_argument("--ref-quizzes", type=int, default=8, help="quizzes per step of the reference arm")
+    ap.add_argument("--group", type=int, default=0,
+                    help="single process: one sharded engine group over this many GPUs (PqaB200_CreateShardedEngine), axis = --shard")
     ap.add_argument("--exact-order", action="store_true",
                     help="--shard targets --exchange p2p: hand the Kahan lanes from shard to shard (W_k bit-exact across shards)")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
@@ -382,6 +439,8 @@ def main():
     from probqa_b200 import engine as pqa
     Q, K, T, B = cfg["Q"], cfg["K"], cfg["T"], cfg["B"]
     cores = host_cores()
+    if args.group > 1:
+        return bench_group(args, cfg, pqa, cores)
     if args.shard in ("questions", "targets") and world > 1:
         return bench_sharded(args, cfg, pqa, dist, rank, world, local_rank, cores, barrier, max_over_ranks)
     eng = pqa.PqaEngineFactory().create_b200_engine(pqa.EngineDefinition(K, Q, T, init_amount=INIT), device=local_rank,

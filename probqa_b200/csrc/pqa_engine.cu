@@ -123,6 +123,7 @@ Engine::Engine(const CiEngineDefinition &def, const CiB200Options &opts, ShellTa
 }
 
 Engine::~Engine() {
+  DeviceScope devScope(stream_ ? device_ : -1);
   if (stream_) cudaStreamSynchronize(stream_);
   if (env_int("PQA_B200_STATS", 0) && statBatches_ > 0) {
     static const char *names[6] = {"NextQuestion", "RecordAnswer", "ListTopTargets", "StartQuiz", "RecordQuizTarget", "ReleaseQuiz"};
@@ -239,7 +240,7 @@ PqaError *Engine::StartQuizBatch(int64_t n, int64_t *pQuizIds) {
   if (n == 0) return nullptr;
   if (!pQuizIds) return MakeError(ErrCode::NullArgument, PQA_FILE_LINE "pQuizIds");
   if (maintenance_) return WrongMode("Start/Resume quiz");
-  std::lock_guard<std::mutex> lk(mu_);
+  std::lock_guard<std::mutex> lk(mu_); DeviceScope devScope(device_);
   PQA_TRY
   for (int64_t x = 0; x < n; x++) pQuizIds[x] = AssignQuizId();
   EnsureQuizCapacity((int64_t)quizzes_.size());
@@ -286,7 +287,7 @@ PqaError *Engine::ResumeQuizBatch(int64_t n, const int64_t *pCounts, const CiAns
       return agg;
     }
   }
-  std::lock_guard<std::mutex> lk(mu_);
+  std::lock_guard<std::mutex> lk(mu_); DeviceScope devScope(device_);
   PQA_TRY
   for (int64_t x = 0; x < n; x++) pQuizIds[x] = AssignQuizId();
   EnsureQuizCapacity((int64_t)quizzes_.size());
@@ -355,7 +356,7 @@ PqaError *Engine::NextQuestionBatch(int64_t n, const int64_t *pQuizIds, const ui
   if (!pQuizIds || !pQuestions) return MakeError(ErrCode::NullArgument, PQA_FILE_LINE "pQuizIds/pQuestions");
   if (IsSharded()) return ErrNotImplemented("NextQuestion on a sharded engine: use the PqaB200_Shard* protocol");
   if (maintenance_) return WrongMode("compute next question");
-  std::lock_guard<std::mutex> lk(mu_);
+  std::lock_guard<std::mutex> lk(mu_); DeviceScope devScope(device_);
   PQA_TRY
   // validate; quizzes that fail validation get their own error and are left out of the launch
   std::vector<int64_t> valid; valid.reserve(n);
@@ -515,7 +516,7 @@ void Engine::RunCombined(const std::vector<CallSlot *> &batch) {
   ids.clear(); who.clear();
   for (CallSlot *c : batch) if (c->kind == 1) {
     PqaError *e;
-    { std::lock_guard<std::mutex> lk(mu_); e = ValidateRecordAnswer(1, &c->quiz, &c->arg); }
+    { std::lock_guard<std::mutex> lk(mu_); DeviceScope devScope(device_); e = ValidateRecordAnswer(1, &c->quiz, &c->arg); }
     if (e) { c->err = e; continue; }
     ids.push_back(c->quiz); args.push_back(c->arg); who.push_back(c);
   }
@@ -528,7 +529,7 @@ void Engine::RunCombined(const std::vector<CallSlot *> &batch) {
   for (CallSlot *c : batch) if (c->kind == 2) {
     PqaError *e = nullptr;
     if (c->arg < 0) e = ErrNegativeCount(c->arg, PQA_FILE_LINE "|maxCount| must be non-negative.");
-    else { std::lock_guard<std::mutex> lk(mu_); e = CheckQuiz(c->quiz); }
+    else { std::lock_guard<std::mutex> lk(mu_); DeviceScope devScope(device_); e = CheckQuiz(c->quiz); }
     if (e) { c->err = e; c->result = -1; continue; }
     tops.push_back(c);
   }
@@ -554,7 +555,7 @@ void Engine::RunCombined(const std::vector<CallSlot *> &batch) {
   for (CallSlot *c : batch) if (c->kind == 4) {
     PqaError *e = nullptr;
     {
-      std::lock_guard<std::mutex> lk(mu_);
+      std::lock_guard<std::mutex> lk(mu_); DeviceScope devScope(device_);
       if (c->arg < 0 || c->arg >= T_) e = ErrIndexOutOfRange(c->arg, 0, T_ - 1, PQA_FILE_LINE "Target index is not in KB range.");
       else if (tGaps_.IsGap(c->arg)) e = ErrAbsentId(c->arg, PQA_FILE_LINE "Target index is not in KB (but rather at a gap).");
       else e = CheckQuiz(c->quiz);
@@ -587,7 +588,7 @@ PqaError *Engine::RecordAnswerBatch(int64_t n, const int64_t *pQuizIds, const in
   if (!pQuizIds || !pAnswers) return MakeError(ErrCode::NullArgument, PQA_FILE_LINE "pQuizIds/pAnswers");
   if (IsSharded()) return ErrNotImplemented("RecordAnswer on a sharded engine: use PqaB200_ShardRecordAnswerBegin / End");
   if (maintenance_) return WrongMode("record an answer");
-  std::lock_guard<std::mutex> lk(mu_);
+  std::lock_guard<std::mutex> lk(mu_); DeviceScope devScope(device_);
   PQA_TRY
   if (PqaError *e = ValidateRecordAnswer(n, pQuizIds, pAnswers)) return e;
   UploadIds(n, pQuizIds);
@@ -636,7 +637,7 @@ PqaError *Engine::ValidateRecordAnswer(int64_t n, const int64_t *pQuizIds, const
 PqaError *Engine::ShardEval(int64_t n, const int64_t *pQuizIds) {
   if (n <= 0) return ErrNegativeCount(n, PQA_FILE_LINE "|n| must be positive.");
   if (IsTargetSharded()) return ErrNotImplemented("ShardEval on a target-sharded engine: use PqaB200_TShardEvalW / EvalHVL / Priority");
-  std::lock_guard<std::mutex> lk(mu_);
+  std::lock_guard<std::mutex> lk(mu_); DeviceScope devScope(device_);
   for (int64_t x = 0; x < n; x++)
     if (PqaError *e = CheckQuiz(pQuizIds[x])) return e;
   PQA_TRY
@@ -656,7 +657,7 @@ PqaError *Engine::ShardSelect(int64_t n, const int64_t *pQuizIds, const uint64_t
   if (n <= 0) return ErrNegativeCount(n, PQA_FILE_LINE "|n| must be positive.");
   if (!pQuizIds || !pQuestions || !pRandoms)
     return MakeError(ErrCode::NullArgument, PQA_FILE_LINE "pQuizIds/pQuestions/pRandoms (every shard must use the same draws)");
-  std::lock_guard<std::mutex> lk(mu_);
+  std::lock_guard<std::mutex> lk(mu_); DeviceScope devScope(device_);
   if (shardPriorityCount_ != n * Q_) return MakeError(ErrCode::NotInitialized, PQA_FILE_LINE "ShardSelect without a matching ShardEval");
   for (int64_t x = 0; x < n; x++)
     if (PqaError *e = CheckQuiz(pQuizIds[x])) return e;
@@ -694,7 +695,7 @@ PqaError *Engine::ShardSelect(int64_t n, const int64_t *pQuizIds, const uint64_t
 PqaError *Engine::ShardRecordAnswerBegin(int64_t n, const int64_t *pQuizIds, const int64_t *pAnswers) {
   if (n <= 0) return ErrNegativeCount(n, PQA_FILE_LINE "|n| must be positive.");
   if (!pQuizIds || !pAnswers) return MakeError(ErrCode::NullArgument, PQA_FILE_LINE "pQuizIds/pAnswers");
-  std::lock_guard<std::mutex> lk(mu_);
+  std::lock_guard<std::mutex> lk(mu_); DeviceScope devScope(device_);
   PQA_TRY
   if (PqaError *e = ValidateRecordAnswer(n, pQuizIds, pAnswers)) return e;
   UploadIds(n, pQuizIds);
@@ -725,7 +726,7 @@ PqaError *Engine::ShardRecordAnswerBegin(int64_t n, const int64_t *pQuizIds, con
 
 PqaError *Engine::ShardRecordAnswerEnd(int64_t n, const int64_t *pQuizIds) {
   if (n <= 0) return ErrNegativeCount(n, PQA_FILE_LINE "|n| must be positive.");
-  std::lock_guard<std::mutex> lk(mu_);
+  std::lock_guard<std::mutex> lk(mu_); DeviceScope devScope(device_);
   if (shardPriorsCount_ != n * Tp_) return MakeError(ErrCode::NotInitialized, PQA_FILE_LINE "ShardRecordAnswerEnd without a matching Begin");
   for (int64_t x = 0; x < n; x++)
     if (PqaError *e = CheckQuiz(pQuizIds[x])) return e;
@@ -741,7 +742,7 @@ PqaError *Engine::ShardRecordAnswerEnd(int64_t n, const int64_t *pQuizIds) {
 }
 
 PqaError *Engine::ShardBuffer(int32_t which, void **ppDevice, int64_t *pCount) {
-  std::lock_guard<std::mutex> lk(mu_);
+  std::lock_guard<std::mutex> lk(mu_); DeviceScope devScope(device_);
   if (!ppDevice || !pCount) return MakeError(ErrCode::NullArgument, PQA_FILE_LINE "ppDevice/pCount");
   if (which == 0) { *ppDevice = p2pLastPriority_ ? p2pLastPriority_ : dShardPriority_.get(); *pCount = shardPriorityCount_; }
   else if (which == 1) { *ppDevice = dShardPriors_.get(); *pCount = shardPriorsCount_; }
@@ -753,7 +754,7 @@ PqaError *Engine::ShardBuffer(int32_t which, void **ppDevice, int64_t *pCount) {
 
 int64_t Engine::GetActiveQuestionId(PqaError **err, int64_t iQuiz) {
   if (maintenance_) { *err = WrongMode("get active question ID for a quiz"); return -1; }
-  std::lock_guard<std::mutex> lk(mu_);
+  std::lock_guard<std::mutex> lk(mu_); DeviceScope devScope(device_);
   *err = CheckQuiz(iQuiz);
   return *err ? -1 : quizzes_[iQuiz].activeQuestion;
 }
@@ -763,7 +764,7 @@ PqaError *Engine::SetActiveQuestionBatch(int64_t n, const int64_t *pQuizIds, con
   if (n == 0) return nullptr;
   if (!pQuizIds || !pQuestions) return MakeError(ErrCode::NullArgument, PQA_FILE_LINE "pQuizIds/pQuestions");
   if (maintenance_) return WrongMode("get active question ID for a quiz");   // sic, BaseEngine.cpp:491-493
-  std::lock_guard<std::mutex> lk(mu_);
+  std::lock_guard<std::mutex> lk(mu_); DeviceScope devScope(device_);
   PQA_TRY
   for (int64_t x = 0; x < n; x++)
     if (PqaError *e = CheckQuiz(pQuizIds[x])) return e;
@@ -794,7 +795,7 @@ PqaError *Engine::ListTopTargetsBatch(int64_t n, const int64_t *pQuizIds, int64_
   if (!pQuizIds || !pCounts || (maxCount > 0 && !pDest))
     return MakeError(ErrCode::NullArgument, PQA_FILE_LINE "pQuizIds/pDest/pCounts");
   if (maintenance_) return WrongMode("compute next question");   // sic, BaseEngine.cpp:514-516
-  std::lock_guard<std::mutex> lk(mu_);
+  std::lock_guard<std::mutex> lk(mu_); DeviceScope devScope(device_);
   PQA_TRY
   for (int64_t x = 0; x < n; x++)
     if (PqaError *e = CheckQuiz(pQuizIds[x])) return e;
@@ -926,7 +927,7 @@ PqaError *Engine::RecordQuizTargetBatch(int64_t n, const int64_t *pQuizIds, cons
     for (int64_t x = 0; x < n; x++)
       if (!(pAmounts[x] > 0)) return ErrNonPositiveAmount(pAmounts[x], PQA_FILE_LINE "|amount| must be positive.");
   if (maintenance_) return WrongMode("record quiz target");
-  std::lock_guard<std::mutex> lk(mu_);
+  std::lock_guard<std::mutex> lk(mu_); DeviceScope devScope(device_);
   std::vector<TrainOp> ops;
   std::vector<int64_t> targets(n);
   std::vector<double> amounts(n);
@@ -963,7 +964,7 @@ PqaError *Engine::Train(int64_t nQuestions, const CiAnsweredQuestion *pAQs, int6
   if (nQuestions < 0) return ErrNegativeCount(nQuestions, "|nQuestions| must be non-negative.");
   if (!(amount > 0)) return ErrNonPositiveAmount(amount, PQA_FILE_LINE "|amount| must be positive.");
   if (nQuestions > 0 && !pAQs) return MakeError(ErrCode::NullArgument, PQA_FILE_LINE "pAQs");
-  std::lock_guard<std::mutex> lk(mu_);
+  std::lock_guard<std::mutex> lk(mu_); DeviceScope devScope(device_);
   if (iTarget < 0 || iTarget >= T_) return ErrIndexOutOfRange(iTarget, 0, T_ - 1, "Target index is not in KB range.");
   if (tGaps_.IsGap(iTarget)) return ErrAbsentId(iTarget, PQA_FILE_LINE "Target index is not in KB (but rather at a gap).");   // CpuEngine.cpp:148-152
   for (int64_t x = 0; x < nQuestions; x++) {  // CETrainSubtaskDistrib.h:24-43
@@ -1006,7 +1007,7 @@ PqaError *Engine::ReleaseQuizBatch(int64_t n, const int64_t *pQuizIds) {
   if (n < 0) return ErrNegativeCount(n, PQA_FILE_LINE "|n| must be non-negative.");
   if (n > 0 && !pQuizIds) return MakeError(ErrCode::NullArgument, PQA_FILE_LINE "pQuizIds");
   if (maintenance_) return WrongMode("release quiz");
-  std::lock_guard<std::mutex> lk(mu_);
+  std::lock_guard<std::mutex> lk(mu_); DeviceScope devScope(device_);
   for (int64_t x = 0; x < n; x++) {
     if (PqaError *e = CheckQuiz(pQuizIds[x])) return e;
     HostQuiz &q = quizzes_[pQuizIds[x]];
@@ -1028,7 +1029,7 @@ PqaError *Engine::ReleaseQuiz(int64_t iQuiz) {
 // ---------------------------------------------------------------------------------------------------------
 // IPqaEngine::CopyATargets / CopyDTargets / CopyBTargets (Interface/IPqaEngine.h:36-39, CpuEngine.cpp:690-709)
 PqaError *Engine::CopyATargets(int64_t iQuestion, int64_t iAnswer, int64_t maxTargets, double *pFreqs) {
-  std::lock_guard<std::mutex> lk(mu_);
+  std::lock_guard<std::mutex> lk(mu_); DeviceScope devScope(device_);
   if (iQuestion < 0 || iQuestion >= Q_) return ErrIndexOutOfRange(iQuestion, 0, Q_ - 1, PQA_FILE_LINE "Question index is not in KB range.");
   if (iAnswer < 0 || iAnswer >= K_) return ErrIndexOutOfRange(iAnswer, 0, K_ - 1, PQA_FILE_LINE "Answer index is not in KB range.");
   if (!OwnsQuestion(iQuestion)) return ErrIndexOutOfRange(iQuestion, qFirst_, qFirst_ + qLocal_ - 1, PQA_FILE_LINE "Question is not in this engine's shard.");
@@ -1040,7 +1041,7 @@ PqaError *Engine::CopyATargets(int64_t iQuestion, int64_t iAnswer, int64_t maxTa
   PQA_CATCH_RETURN_ERR
 }
 PqaError *Engine::CopyDTargets(int64_t iQuestion, int64_t maxTargets, double *pFreqs) {
-  std::lock_guard<std::mutex> lk(mu_);
+  std::lock_guard<std::mutex> lk(mu_); DeviceScope devScope(device_);
   if (iQuestion < 0 || iQuestion >= Q_) return ErrIndexOutOfRange(iQuestion, 0, Q_ - 1, PQA_FILE_LINE "Question index is not in KB range.");
   if (!OwnsQuestion(iQuestion)) return ErrIndexOutOfRange(iQuestion, qFirst_, qFirst_ + qLocal_ - 1, PQA_FILE_LINE "Question is not in this engine's shard.");
   PQA_TRY
@@ -1050,7 +1051,7 @@ PqaError *Engine::CopyDTargets(int64_t iQuestion, int64_t maxTargets, double *pF
   PQA_CATCH_RETURN_ERR
 }
 PqaError *Engine::CopyBTargets(int64_t maxTargets, double *pFreqs) {
-  std::lock_guard<std::mutex> lk(mu_);
+  std::lock_guard<std::mutex> lk(mu_); DeviceScope devScope(device_);
   PQA_TRY
   const int64_t cnt = std::min(maxTargets, T_);
   if (cnt > 0) PQA_CU(cudaMemcpy(pFreqs, dVB_, sizeof(double) * (size_t)cnt, cudaMemcpyDeviceToHost));
@@ -1061,7 +1062,7 @@ PqaError *Engine::CopyBTargets(int64_t maxTargets, double *pFreqs) {
 // Whole-KB transfer in the reference's file layout (CpuEngine.cpp:664-688): rows of T doubles, no padding.
 PqaError *Engine::UploadKB(const double *sA, const double *mD, const double *vB) {
   if (!sA || !mD || !vB) return MakeError(ErrCode::NullArgument, PQA_FILE_LINE "sA/mD/vB");
-  std::lock_guard<std::mutex> lk(mu_);
+  std::lock_guard<std::mutex> lk(mu_); DeviceScope devScope(device_);
   PQA_TRY
   // the host arrays always describe the whole KB; a question-sharded engine takes its rows out of them, a
   // target-sharded engine its columns
@@ -1096,7 +1097,7 @@ PqaError *Engine::UploadKB(const double *sA, const double *mD, const double *vB)
 }
 
 PqaError *Engine::DownloadKB(double *sA, double *mD, double *vB) {
-  std::lock_guard<std::mutex> lk(mu_);
+  std::lock_guard<std::mutex> lk(mu_); DeviceScope devScope(device_);
   PQA_TRY
   // whole-KB host arrays; a question-sharded engine fills its rows only, a target-sharded engine its columns only
   if (sA) sA += qFirst_ * K_ * T_ + tFirst_;
@@ -1121,7 +1122,7 @@ PqaError *Engine::DownloadKB(double *sA, double *mD, double *vB) {
 }
 
 PqaError *Engine::CopyQuizPriors(int64_t iQuiz, double *pPriors) {
-  std::lock_guard<std::mutex> lk(mu_);
+  std::lock_guard<std::mutex> lk(mu_); DeviceScope devScope(device_);
   if (PqaError *e = CheckQuiz(iQuiz)) return e;
   PQA_TRY
   PQA_CU(cudaMemcpyAsync(pPriors, dPriors_ + iQuiz * Tp_, sizeof(double) * (size_t)T_, cudaMemcpyDeviceToHost, stream_));
@@ -1130,7 +1131,7 @@ PqaError *Engine::CopyQuizPriors(int64_t iQuiz, double *pPriors) {
   PQA_CATCH_RETURN_ERR
 }
 PqaError *Engine::SetQuizPriors(int64_t iQuiz, const double *pPriors) {
-  std::lock_guard<std::mutex> lk(mu_);
+  std::lock_guard<std::mutex> lk(mu_); DeviceScope devScope(device_);
   if (PqaError *e = CheckQuiz(iQuiz)) return e;
   PQA_TRY
   PQA_CU(cudaMemcpyAsync(dPriors_ + iQuiz * Tp_, pPriors, sizeof(double) * (size_t)T_, cudaMemcpyHostToDevice, stream_));
@@ -1143,7 +1144,7 @@ PqaError *Engine::SetQuizPriors(int64_t iQuiz, const double *pPriors) {
 
 PqaError *Engine::SetEvalKernel(int32_t which, int64_t chunkTargets, int64_t quizzesPerCta, int32_t kahanLanesPerThread) {
   if (which < 0 || which > 2) return ErrIndexOutOfRange(which, 0, 2, PQA_FILE_LINE "which");
-  std::lock_guard<std::mutex> lk(mu_);
+  std::lock_guard<std::mutex> lk(mu_); DeviceScope devScope(device_);
   if (kahanLanesPerThread != 0 && kahanLanesPerThread != 1 && kahanLanesPerThread != 2 && kahanLanesPerThread != 4)
     return ErrIndexOutOfRange(kahanLanesPerThread, 0, 4, PQA_FILE_LINE "kahanLanesPerThread must be 0, 1 or 4");
   evalCfg_.which = which; evalCfg_.chunkTargets = chunkTargets; evalCfg_.quizzesPerCta = quizzesPerCta;
@@ -1155,7 +1156,7 @@ PqaError *Engine::EvalQuestions(int64_t n, const int64_t *pQuizIds, double *pPri
                                 double *pGrandTotals, int64_t *pnChunks) {
   if (n <= 0) return ErrNegativeCount(n, PQA_FILE_LINE "|n| must be positive.");
   if (IsTargetSharded()) return ErrNotImplemented("EvalQuestions on a target-sharded engine: use the PqaB200_TShard* protocol");
-  std::lock_guard<std::mutex> lk(mu_);
+  std::lock_guard<std::mutex> lk(mu_); DeviceScope devScope(device_);
   for (int64_t x = 0; x < n; x++)
     if (PqaError *e = CheckQuiz(pQuizIds[x])) return e;
   PQA_TRY
@@ -1179,7 +1180,7 @@ PqaError *Engine::EvalQuestions(int64_t n, const int64_t *pQuizIds, double *pPri
 PqaError *Engine::EvalQuestionsDetailed(int64_t iQuiz, double *pW, double *pH, double *pV, double *pLack,
                                         double *pPriorities) {
   if (IsTargetSharded()) return ErrNotImplemented("EvalQuestionsDetailed on a target-sharded engine");
-  std::lock_guard<std::mutex> lk(mu_);
+  std::lock_guard<std::mutex> lk(mu_); DeviceScope devScope(device_);
   if (PqaError *e = CheckQuiz(iQuiz)) return e;
   PQA_TRY
   UploadIds(1, &iQuiz);
@@ -1204,7 +1205,7 @@ PqaError *Engine::EvalQuestionsDetailed(int64_t iQuiz, double *pW, double *pH, d
 PqaError *Engine::ResidentBind(int64_t n, const int64_t *pQuizIds, const uint64_t *pRandoms) {
   if (n <= 0) return ErrNegativeCount(n, PQA_FILE_LINE "|n| must be positive.");
   if (IsTargetSharded()) return ErrNotImplemented("resident stepping on a target-sharded engine");
-  std::lock_guard<std::mutex> lk(mu_);
+  std::lock_guard<std::mutex> lk(mu_); DeviceScope devScope(device_);
   for (int64_t x = 0; x < n; x++)
     if (PqaError *e = CheckQuiz(pQuizIds[x])) return e;
   PQA_TRY
@@ -1220,7 +1221,7 @@ PqaError *Engine::ResidentBind(int64_t n, const int64_t *pQuizIds, const uint64_
   PQA_CATCH_RETURN_ERR
 }
 PqaError *Engine::ResidentStep() {
-  std::lock_guard<std::mutex> lk(mu_);
+  std::lock_guard<std::mutex> lk(mu_); DeviceScope devScope(device_);
   if (residentN_ <= 0) return MakeError(ErrCode::NotInitialized, PQA_FILE_LINE "no resident batch is bound");
   PQA_TRY
   EvalDetail det{nullptr, nullptr, nullptr, nullptr};
@@ -1235,7 +1236,7 @@ PqaError *Engine::ResidentStep() {
   PQA_CATCH_RETURN_ERR
 }
 PqaError *Engine::ResidentFetch(int64_t *pQuestions) {
-  std::lock_guard<std::mutex> lk(mu_);
+  std::lock_guard<std::mutex> lk(mu_); DeviceScope devScope(device_);
   if (residentN_ <= 0) return MakeError(ErrCode::NotInitialized, PQA_FILE_LINE "no resident batch is bound");
   PQA_TRY
   PQA_CU(cudaMemcpyAsync(pQuestions, dResQuestions_.get(), sizeof(int64_t) * (size_t)residentN_, cudaMemcpyDeviceToHost, stream_));
@@ -1244,7 +1245,7 @@ PqaError *Engine::ResidentFetch(int64_t *pQuestions) {
   PQA_CATCH_RETURN_ERR
 }
 double Engine::ResidentLastEvalMs() {
-  std::lock_guard<std::mutex> lk(mu_);
+  std::lock_guard<std::mutex> lk(mu_); DeviceScope devScope(device_);
   if (!evEvalStart_) return -1.0;
   float ms = -1.f;
   if (cudaEventSynchronize(evEvalStop_) != cudaSuccess) return -1.0;
@@ -1252,6 +1253,7 @@ double Engine::ResidentLastEvalMs() {
   return (double)ms;
 }
 PqaError *Engine::Synchronize() {
+  DeviceScope devScope(device_);
   PQA_TRY
   PQA_CU(cudaStreamSynchronize(stream_));
   PQA_CU(cudaGetLastError());
@@ -1259,7 +1261,7 @@ PqaError *Engine::Synchronize() {
   PQA_CATCH_RETURN_ERR
 }
 PqaError *Engine::FlushL2() {
-  std::lock_guard<std::mutex> lk(mu_);
+  std::lock_guard<std::mutex> lk(mu_); DeviceScope devScope(device_);
   PQA_TRY
   if (!flushBuf_) {
     flushBytes_ = 256ull << 20;  // > 126 MB L2
@@ -1276,7 +1278,7 @@ PqaError *Engine::FlushL2() {
 PqaError *Engine::TShardEvalW(int64_t n, const int64_t *pQuizIds) {
   if (n <= 0) return ErrNegativeCount(n, PQA_FILE_LINE "|n| must be positive.");
   if (!IsTargetSharded()) return ErrNotImplemented("TShardEvalW on an engine without a target shard");
-  std::lock_guard<std::mutex> lk(mu_);
+  std::lock_guard<std::mutex> lk(mu_); DeviceScope devScope(device_);
   for (int64_t x = 0; x < n; x++)
     if (PqaError *e = CheckQuiz(pQuizIds[x])) return e;
   PQA_TRY
@@ -1293,7 +1295,7 @@ PqaError *Engine::TShardEvalW(int64_t n, const int64_t *pQuizIds) {
 
 PqaError *Engine::TShardEvalHVL(int64_t n, const int64_t *pQuizIds) {
   if (n <= 0) return ErrNegativeCount(n, PQA_FILE_LINE "|n| must be positive.");
-  std::lock_guard<std::mutex> lk(mu_);
+  std::lock_guard<std::mutex> lk(mu_); DeviceScope devScope(device_);
   if (shardWCount_ != n * Q_ * K_) return MakeError(ErrCode::NotInitialized, PQA_FILE_LINE "TShardEvalHVL without a matching TShardEvalW");
   for (int64_t x = 0; x < n; x++)
     if (PqaError *e = CheckQuiz(pQuizIds[x])) return e;
@@ -1311,7 +1313,7 @@ PqaError *Engine::TShardEvalHVL(int64_t n, const int64_t *pQuizIds) {
 
 PqaError *Engine::TShardPriority(int64_t n, const int64_t *pQuizIds) {
   if (n <= 0) return ErrNegativeCount(n, PQA_FILE_LINE "|n| must be positive.");
-  std::lock_guard<std::mutex> lk(mu_);
+  std::lock_guard<std::mutex> lk(mu_); DeviceScope devScope(device_);
   if (shardWCount_ != n * Q_ * K_ || shardHVLCount_ != n * Q_ * (2 * K_ + 1))
     return MakeError(ErrCode::NotInitialized, PQA_FILE_LINE "TShardPriority without matching TShardEvalW / TShardEvalHVL");
   for (int64_t x = 0; x < n; x++)
@@ -1343,7 +1345,7 @@ static const int64_t kP2PMaxTiles = 1920;                         // 15 KB of fl
 static const size_t kP2PHeaderBytes = 32768, kP2POffHandOver = 1024, kP2POffWReady = 16384;
 
 PqaError *Engine::P2PSetExactOrder(int32_t on) {
-  std::lock_guard<std::mutex> lk(mu_);
+  std::lock_guard<std::mutex> lk(mu_); DeviceScope devScope(device_);
   if (!IsTargetSharded()) return ErrNotImplemented("exact-order pipeline on an engine without a target shard (question shards are exact already)");
   if (p2pPending_) return MakeError(ErrCode::WrongMode, PQA_FILE_LINE "a P2P operation is pending");
   p2pExactOrder_ = on != 0;
@@ -1355,7 +1357,7 @@ PqaError *Engine::P2PInit(int32_t rank, int32_t nRanks, int64_t maxQuizzes, void
   if (rank < 0 || rank >= nRanks) return ErrIndexOutOfRange(rank, 0, nRanks - 1, PQA_FILE_LINE "rank");
   if (maxQuizzes <= 0) return ErrNegativeCount(maxQuizzes, PQA_FILE_LINE "|maxQuizzes| must be positive.");
   if (!IsSharded()) return ErrNotImplemented("P2PInit on an engine without a question or target shard");
-  std::lock_guard<std::mutex> lk(mu_);
+  std::lock_guard<std::mutex> lk(mu_); DeviceScope devScope(device_);
   if (p2pInbox_) return MakeError(ErrCode::WrongMode, PQA_FILE_LINE "the peer-memory inbox exists already");
   PQA_TRY
   PQA_CU(cudaSetDevice(device_));
@@ -1399,7 +1401,7 @@ PqaError *Engine::P2PInit(int32_t rank, int32_t nRanks, int64_t maxQuizzes, void
 PqaError *Engine::P2PExportHandle(uint8_t *pHandle64) {
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
   if (!pHandle64) return MakeError(ErrCode::NullArgument, PQA_FILE_LINE "pHandle64");
-  std::lock_guard<std::mutex> lk(mu_);
+  std::lock_guard<std::mutex> lk(mu_); DeviceScope devScope(device_);
   if (!p2pInbox_) return MakeError(ErrCode::NotInitialized, PQA_FILE_LINE "P2PInit first");
   PQA_TRY
   cudaIpcMemHandle_t h;
@@ -1411,7 +1413,7 @@ PqaError *Engine::P2PExportHandle(uint8_t *pHandle64) {
 
 PqaError *Engine::P2POpenHandle(const uint8_t *pHandle64, void **ppPeerBase) {
   if (!pHandle64 || !ppPeerBase) return MakeError(ErrCode::NullArgument, PQA_FILE_LINE "pHandle64/ppPeerBase");
-  std::lock_guard<std::mutex> lk(mu_);
+  std::lock_guard<std::mutex> lk(mu_); DeviceScope devScope(device_);
   PQA_TRY
   PQA_CU(cudaSetDevice(device_));
   cudaIpcMemHandle_t h;
@@ -1423,7 +1425,7 @@ PqaError *Engine::P2POpenHandle(const uint8_t *pHandle64, void **ppPeerBase) {
 
 PqaError *Engine::P2PConnect(void *const *pBases) {
   if (!pBases) return MakeError(ErrCode::NullArgument, PQA_FILE_LINE "pBases");
-  std::lock_guard<std::mutex> lk(mu_);
+  std::lock_guard<std::mutex> lk(mu_); DeviceScope devScope(device_);
   if (!p2pInbox_) return MakeError(ErrCode::NotInitialized, PQA_FILE_LINE "P2PInit first");
   PQA_TRY
   for (int r = 0; r < p2pRanks_; r++) {
@@ -1472,7 +1474,7 @@ PqaError *Engine::P2PNextQuestionBegin(int64_t n, const int64_t *pQuizIds, const
   if (n <= 0) return ErrNegativeCount(n, PQA_FILE_LINE "|n| must be positive.");
   if (!pQuizIds || !pRandoms)
     return MakeError(ErrCode::NullArgument, PQA_FILE_LINE "pQuizIds/pRandoms (every shard must use the same draws)");
-  std::lock_guard<std::mutex> lk(mu_);
+  std::lock_guard<std::mutex> lk(mu_); DeviceScope devScope(device_);
   if (!p2pConnected_) return MakeError(ErrCode::NotInitialized, PQA_FILE_LINE "P2PInit / P2PConnect first");
   if (p2pPending_) return MakeError(ErrCode::WrongMode, PQA_FILE_LINE "a P2P operation is pending: call its End first");
   if (n > p2pCap_) return ErrIndexOutOfRange(n, 1, p2pCap_, PQA_FILE_LINE "more quizzes than the inbox was sized for");
@@ -1566,7 +1568,7 @@ PqaError *Engine::P2PNextQuestionBegin(int64_t n, const int64_t *pQuizIds, const
 PqaError *Engine::P2PNextQuestionEnd(int64_t n, const int64_t *pQuizIds, int64_t *pQuestions, void **ppErrors) {
   if (n <= 0) return ErrNegativeCount(n, PQA_FILE_LINE "|n| must be positive.");
   if (!pQuizIds || !pQuestions) return MakeError(ErrCode::NullArgument, PQA_FILE_LINE "pQuizIds/pQuestions");
-  std::lock_guard<std::mutex> lk(mu_);
+  std::lock_guard<std::mutex> lk(mu_); DeviceScope devScope(device_);
   if (!p2pPending_) return MakeError(ErrCode::NotInitialized, PQA_FILE_LINE "P2PNextQuestionEnd without a Begin");
   p2pPending_ = false;
   if (PqaError *e = P2PCheckError()) return e;
@@ -1593,7 +1595,7 @@ PqaError *Engine::P2PNextQuestionEnd(int64_t n, const int64_t *pQuizIds, int64_t
 PqaError *Engine::P2PRecordAnswerBegin(int64_t n, const int64_t *pQuizIds, const int64_t *pAnswers) {
   if (n <= 0) return ErrNegativeCount(n, PQA_FILE_LINE "|n| must be positive.");
   if (!pQuizIds || !pAnswers) return MakeError(ErrCode::NullArgument, PQA_FILE_LINE "pQuizIds/pAnswers");
-  std::lock_guard<std::mutex> lk(mu_);
+  std::lock_guard<std::mutex> lk(mu_); DeviceScope devScope(device_);
   if (!p2pConnected_) return MakeError(ErrCode::NotInitialized, PQA_FILE_LINE "P2PInit / P2PConnect first");
   if (p2pPending_) return MakeError(ErrCode::WrongMode, PQA_FILE_LINE "a P2P operation is pending: call its End first");
   if (n > p2pCap_) return ErrIndexOutOfRange(n, 1, p2pCap_, PQA_FILE_LINE "more quizzes than the inbox was sized for");
@@ -1636,14 +1638,14 @@ PqaError *Engine::P2PRecordAnswerBegin(int64_t n, const int64_t *pQuizIds, const
 }
 
 PqaError *Engine::P2PRecordAnswerEnd() {
-  std::lock_guard<std::mutex> lk(mu_);
+  std::lock_guard<std::mutex> lk(mu_); DeviceScope devScope(device_);
   if (!p2pPending_) return MakeError(ErrCode::NotInitialized, PQA_FILE_LINE "P2PRecordAnswerEnd without a Begin");
   p2pPending_ = false;
   return P2PCheckError();
 }
 
 PqaError *Engine::FillBinarySearchKB(double rounds) {
-  std::lock_guard<std::mutex> lk(mu_);
+  std::lock_guard<std::mutex> lk(mu_); DeviceScope devScope(device_);
   PQA_TRY
   launch_fill_binary_search_kb(kb(), tFirst_, T_, initAmount_, rounds, stream_);
   PQA_CU(cudaStreamSynchronize(stream_));
@@ -1727,7 +1729,7 @@ PqaError *Engine::WriteKBFile(FILE *f, const char *filePath, bool frame) {
 PqaError *Engine::SaveKB(const char *filePath) {
   if (!filePath) return MakeError(ErrCode::NullArgument, PQA_FILE_LINE "Nullptr is passed in place of KB file name.");
   if (IsSharded()) return ErrNotImplemented("SaveKB on a sharded engine: use PqaB200_SaveKBShard on every shard");
-  std::lock_guard<std::mutex> lk(mu_);   // the KB must not be trained while it is written (reference: shared lock)
+  std::lock_guard<std::mutex> lk(mu_); DeviceScope devScope(device_);   // the KB must not be trained while it is written (reference: shared lock)
   FileCloser fc{std::fopen(filePath, "wb")};
   if (!fc.f) return MakeError(ErrCode::CantOpenFile, PQA_FILE_LINE "Can't open the KB file to write.",
                               std::string("filePath=[") + filePath + "]");
@@ -1738,7 +1740,7 @@ PqaError *Engine::SaveKB(const char *filePath) {
 // file and writes header, vB and tail); the others then open the existing file and write their cells in place.
 PqaError *Engine::SaveKBShard(const char *filePath, bool writeFrame) {
   if (!filePath) return MakeError(ErrCode::NullArgument, PQA_FILE_LINE "Nullptr is passed in place of KB file name.");
-  std::lock_guard<std::mutex> lk(mu_);
+  std::lock_guard<std::mutex> lk(mu_); DeviceScope devScope(device_);
   FileCloser fc{std::fopen(filePath, writeFrame ? "wb" : "r+b")};
   if (!fc.f) return MakeError(ErrCode::CantOpenFile, PQA_FILE_LINE "Can't open the KB file to write.",
                               std::string("filePath=[") + filePath + "]");

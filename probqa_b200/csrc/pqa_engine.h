@@ -117,6 +117,20 @@ template <typename T> inline void PinBuf<T>::ensure(size_t n) {
 }
 
 
+// Makes an engine's device current for the scope of a call and restores the caller's: several engines of one process
+// may sit on different GPUs (ShardGroup, tests), and a client thread's current device is whatever it used last.
+struct DeviceScope {
+  int prev = -1;
+  bool switched = false;
+  explicit DeviceScope(int device) {
+    if (device < 0) return;
+    if (cudaGetDevice(&prev) == cudaSuccess && prev != device) switched = cudaSetDevice(device) == cudaSuccess;
+  }
+  ~DeviceScope() { if (switched) cudaSetDevice(prev); }
+  DeviceScope(const DeviceScope &) = delete;
+  DeviceScope &operator=(const DeviceScope &) = delete;
+};
+
 struct HostQuiz {                      // BaseQuiz.h:13-36 (host part); priors and asked bits live on the device
   bool present = false;
   int64_t activeQuestion = -1;

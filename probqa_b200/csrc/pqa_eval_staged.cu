@@ -31,6 +31,7 @@
 #include "pqa_kernels.cuh"
 #include "pqa_device.cuh"
 
+#include <atomic>
 #include <math.h>
 #include <stdio.h>
 #include <stdexcept>
@@ -718,11 +719,14 @@ template <int K, int PHASE>
 static void launch_tshard_k(TShardParams TP, size_t smem, cudaStream_t st) {
   // two threads per quiz; 128 quizzes per CTA pass (8 warps), or 64 (4 warps, twice the CTAs per SM) for small batches
   const bool wide = TP.S.n > 64;
-  static bool attrSet = false;
-  if (!attrSet) {
+  // function attributes are per device: several engines of one process may sit on different GPUs (ShardGroup)
+  static std::atomic<unsigned long long> attrDevices{0};
+  int attrDev = 0;
+  cudaGetDevice(&attrDev);
+  if (!((attrDevices.load(std::memory_order_relaxed) >> (attrDev & 63)) & 1ull)) {
     cudaFuncSetAttribute(k_eval_tshard<K, 2, 8, PHASE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(k_eval_tshard<K, 2, 4, PHASE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    attrSet = true;
+    attrDevices.fetch_or(1ull << (attrDev & 63), std::memory_order_relaxed);
   }
   const int64_t perPass = wide ? 128 : 64;
   TP.S.quizzesPerCta = perPass;
@@ -805,11 +809,14 @@ void launch_tshard_priority(const DeviceKB &kbLocal, const QuizPool &qp, int64_t
 
 template <int K>
 static void launch_small(StagedParams P, size_t smem, cudaStream_t st) {
-  static bool attrSet = false;
-  if (!attrSet) {
+  // function attributes are per device: several engines of one process may sit on different GPUs (ShardGroup)
+  static std::atomic<unsigned long long> attrDevices{0};
+  int attrDev = 0;
+  cudaGetDevice(&attrDev);
+  if (!((attrDevices.load(std::memory_order_relaxed) >> (attrDev & 63)) & 1ull)) {
     cudaFuncSetAttribute(k_eval_small<K, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(k_eval_small<K, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    attrSet = true;
+    attrDevices.fetch_or(1ull << (attrDev & 63), std::memory_order_relaxed);
   }
   if (P.n <= 2) {
     P.quizzesPerCta = 4;
@@ -827,10 +834,13 @@ static void launch_small(StagedParams P, size_t smem, cudaStream_t st) {
 
 template <int K, int KL, int WARPS>
 static void launch_cfg(StagedParams P, const EvalConfig &cfg, size_t smem, cudaStream_t st) {
-  static bool attrSet = false;
-  if (!attrSet) {
+  // function attributes are per device: several engines of one process may sit on different GPUs (ShardGroup)
+  static std::atomic<unsigned long long> attrDevices{0};
+  int attrDev = 0;
+  cudaGetDevice(&attrDev);
+  if (!((attrDevices.load(std::memory_order_relaxed) >> (attrDev & 63)) & 1ull)) {
     cudaFuncSetAttribute(k_eval_staged<K, KL, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    attrSet = true;
+    attrDevices.fetch_or(1ull << (attrDev & 63), std::memory_order_relaxed);
   }
   const int64_t perPass = (int64_t)WARPS * (32 / (4 / KL));   // quizzes one CTA evaluates concurrently
   if (P.nChunks > 1) {

@@ -873,10 +873,13 @@ void launch_list_top_targets(const DeviceKB &kb, const QuizPool &qp, int64_t n, 
   const size_t items = (size_t)kb.T * sizeof(Rated);
   const int useSmem = fixed + items <= 200 * 1024;
   const size_t smem = fixed + (useSmem ? items : 0);
-  static bool attrSet = false;
-  if (!attrSet) {
+  // function attributes are per device: several engines of one process may sit on different GPUs (ShardGroup)
+  static std::atomic<unsigned long long> attrDevices{0};
+  int attrDev = 0;
+  cudaGetDevice(&attrDev);
+  if (!((attrDevices.load(std::memory_order_relaxed) >> (attrDev & 63)) & 1ull)) {
     cudaFuncSetAttribute(k_list_top_targets, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-    attrSet = true;
+    attrDevices.fetch_or(1ull << (attrDev & 63), std::memory_order_relaxed);
   }
   int block = 32;
   while (block < W && block < 256) block <<= 1;

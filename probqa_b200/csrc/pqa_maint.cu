@@ -121,17 +121,17 @@ static PqaError *NotMaintenance(const char *what) {
 }
 
 bool Engine::MapIds(int kind, bool permFromComp, int64_t count, int64_t *pIds) {   // BaseEngine.cpp:154-206
-  std::lock_guard<std::mutex> lk(mu_);
+  std::lock_guard<std::mutex> lk(mu_); DeviceScope devScope(device_);
   const PermIds &pim = kind == 0 ? pimQ_ : kind == 1 ? pimT_ : pimQuiz_;
   for (int64_t i = 0; i < count; i++) pIds[i] = permFromComp ? pim.PermFromComp(pIds[i]) : pim.CompFromPerm(pIds[i]);
   return true;
 }
 bool Engine::EnsurePermQuizGreater(int64_t bound) {                                // :208-212
-  std::lock_guard<std::mutex> lk(mu_);
+  std::lock_guard<std::mutex> lk(mu_); DeviceScope devScope(device_);
   return pimQuiz_.EnsurePermIdGreater(bound);
 }
 bool Engine::RemapQuizPermId(int64_t srcPermId, int64_t destPermId) {              // :214-218
-  std::lock_guard<std::mutex> lk(mu_);
+  std::lock_guard<std::mutex> lk(mu_); DeviceScope devScope(device_);
   return pimQuiz_.RemapPermId(srcPermId, destPermId);
 }
 
@@ -166,7 +166,7 @@ void Engine::DropQuizPool() {
 PqaError *Engine::ClearOldQuizzes(int64_t maxCount, double maxAgeSec) {
   if (maxCount < 0) return ErrNegativeCount(maxCount, PQA_FILE_LINE "The number of quizzes to keep cannot be less than 0.");
   if (maintenance_) return nullptr;
-  std::lock_guard<std::mutex> lk(mu_);
+  std::lock_guard<std::mutex> lk(mu_); DeviceScope devScope(device_);
   struct QuizAge {
     int64_t iQuiz; double ageSec;
     bool operator<(const QuizAge &o) const { return ageSec < o.ageSec; }
@@ -201,7 +201,7 @@ PqaError *Engine::ClearOldQuizzes(int64_t maxCount, double maxAgeSec) {
 // (forceQuizzes) or refuses with QuizzesActive and stays in regular mode.
 PqaError *Engine::StartMaintenance(bool forceQuizzes) {
   if (IsSharded()) return ErrNotImplemented("maintenance mode on a sharded engine");
-  std::lock_guard<std::mutex> lk(mu_);
+  std::lock_guard<std::mutex> lk(mu_); DeviceScope devScope(device_);
   if (maintenance_) return MakeError(ErrCode::MaintenanceModeAlreadyThis, PQA_FILE_LINE "The engine is in maintenance mode already.",
                                      "activeMode=1");
   const int64_t nQuizzes = (int64_t)quizzes_.size() - (int64_t)quizGaps_.size();
@@ -224,7 +224,7 @@ PqaError *Engine::StartMaintenance(bool forceQuizzes) {
 
 // BaseEngine::FinishMaintenance (BaseEngine.cpp:685-702)
 PqaError *Engine::FinishMaintenance() {
-  std::lock_guard<std::mutex> lk(mu_);
+  std::lock_guard<std::mutex> lk(mu_); DeviceScope devScope(device_);
   if (!maintenance_) return MakeError(ErrCode::MaintenanceModeAlreadyThis, PQA_FILE_LINE "The engine is in regular mode already.",
                                       "activeMode=0");
   PQA_TRY
@@ -278,7 +278,7 @@ PqaError *Engine::AddQsTs(int64_t nQuestions, CiAddQorTParam *pAqps, int64_t nTa
   if (nQuestions < 0) return ErrNegativeCount(nQuestions, PQA_FILE_LINE "|nQuestions| must be non-negative.");
   if (nTargets < 0) return ErrNegativeCount(nTargets, PQA_FILE_LINE "|nTargets| must be non-negative.");
   if ((nQuestions > 0 && !pAqps) || (nTargets > 0 && !pAtps)) return MakeError(ErrCode::NullArgument, PQA_FILE_LINE "pAqps/pAtps");
-  std::lock_guard<std::mutex> lk(mu_);
+  std::lock_guard<std::mutex> lk(mu_); DeviceScope devScope(device_);
   PQA_TRY
   const int64_t nQReuse = std::min(nQuestions, qGaps_.GetNGaps());
   const int64_t nQNew = nQuestions - nQReuse, nQOld = Q_, totQ = nQOld + nQNew;
@@ -344,7 +344,7 @@ PqaError *Engine::AddQsTs(int64_t nQuestions, CiAddQorTParam *pAqps, int64_t nTa
 PqaError *Engine::RemoveQuestions(int64_t nQuestions, const int64_t *pQIds) {
   if (!maintenance_) return NotMaintenance("remove questions");
   if (nQuestions > 0 && !pQIds) return MakeError(ErrCode::NullArgument, PQA_FILE_LINE "pQIds");
-  std::lock_guard<std::mutex> lk(mu_);
+  std::lock_guard<std::mutex> lk(mu_); DeviceScope devScope(device_);
   for (int64_t i = 0; i < nQuestions; i++) {
     const int64_t q = pQIds[i];
     if (q < 0 || q >= Q_ || qGaps_.IsGap(q)) return ErrAbsentId(q, PQA_FILE_LINE "Question index is not in KB.");
@@ -356,7 +356,7 @@ PqaError *Engine::RemoveQuestions(int64_t nQuestions, const int64_t *pQIds) {
 PqaError *Engine::RemoveTargets(int64_t nTargets, const int64_t *pTIds) {
   if (!maintenance_) return NotMaintenance("remove targets");
   if (nTargets > 0 && !pTIds) return MakeError(ErrCode::NullArgument, PQA_FILE_LINE "pTIds");
-  std::lock_guard<std::mutex> lk(mu_);
+  std::lock_guard<std::mutex> lk(mu_); DeviceScope devScope(device_);
   for (int64_t i = 0; i < nTargets; i++) {
     const int64_t t = pTIds[i];
     if (t < 0 || t >= T_ || tGaps_.IsGap(t)) return ErrAbsentId(t, PQA_FILE_LINE "Target index is not in KB (but rather at a gap).");
@@ -381,7 +381,7 @@ PqaError *Engine::Compact(int64_t *pnQuestions, const int64_t **ppOldQuestions, 
   if (ppOldTargets) *ppOldTargets = nullptr;
   if (!maintenance_) return NotMaintenance("compact the KB");
   if (!pnQuestions || !ppOldQuestions || !pnTargets || !ppOldTargets) return MakeError(ErrCode::NullArgument, PQA_FILE_LINE "out-pointers");
-  std::lock_guard<std::mutex> lk(mu_);
+  std::lock_guard<std::mutex> lk(mu_); DeviceScope devScope(device_);
   PQA_TRY
   const int64_t nQ = Q_ - qGaps_.GetNGaps(), nT = T_ - tGaps_.GetNGaps();
   if (nQ < 1 || nT < 2) return ErrInsufficientDims(K_, nQ, nT);
