@@ -69,6 +69,9 @@ PQACORE_API void *PqaB200_SaveKBShard(void *pvEngine, const char *filePath, int3
 PQACORE_API int32_t PqaB200_GetEmulatedWorkers(void *pvEngine);
 PQACORE_API int32_t PqaB200_GetDevice(void *pvEngine);
 PQACORE_API const char *PqaB200_BuildInfo(void); /* static string: arch, build flags */
+/* Self test of the host-side bookkeeping that needs no device (gap sets, permanent ids, compaction plans): returns NULL
+ * when all is well, else a message to release with CiReleaseString. */
+PQACORE_API void *PqaB200_HostLogicSelfTest(void);
 
 /* C exports of IPqaEngine::CopyATargets/CopyDTargets/CopyBTargets (Interface/IPqaEngine.h:36-39; C++-only in the
  * reference). */

@@ -327,6 +327,13 @@ PQACORE_API int32_t PqaB200_GetDevice(void *pvEngine) { return pvEngine ? E(pvEn
 PQACORE_API const char *PqaB200_BuildInfo(void) {
   return "probqa_b200 libPqaCore: sm_100a, fp64, -fmad=false, built " __DATE__ " " __TIME__;
 }
+PQACORE_API void *PqaB200_HostLogicSelfTest(void) {
+  const std::string m = HostLogicSelfTest();
+  if (m.empty()) return nullptr;
+  char *out = new char[m.size() + 1];
+  std::memcpy(out, m.c_str(), m.size() + 1);
+  return out;
+}
 PQACORE_API void *PqaEngine_CopyATargets(void *pvEngine, int64_t iQuestion, int64_t iAnswer, int64_t maxTargets, double *pFreqs) {
   if (!pvEngine) return NullEngine();
   return Ret(E(pvEngine)->CopyATargets(iQuestion, iAnswer, maxTargets, pFreqs));

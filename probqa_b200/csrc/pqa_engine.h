@@ -131,6 +131,10 @@ struct DeviceScope {
   DeviceScope &operator=(const DeviceScope &) = delete;
 };
 
+void PlanCompactQuestions(const GapSet &gaps, int64_t n, int64_t *oldIds);   // CpuEngine.cpp:594-608
+void PlanCompactTargets(const GapSet &gaps, int64_t n, int64_t *oldIds);     // CpuEngine.cpp:616-641
+std::string HostLogicSelfTest();                                            // pqa_maint.cu; "" = ok
+
 struct HostQuiz {                      // BaseQuiz.h:13-36 (host part); priors and asked bits live on the device
   bool present = false;
   int64_t activeQuestion = -1;

@@ -366,6 +366,108 @@ PqaError *Engine::RemoveTargets(int64_t nTargets, const int64_t *pTIds) {
   return nullptr;
 }
 
+// The old-id arrays of CpuEngine::CompactSpec. Questions (CpuEngine.cpp:594-608): scanning from the front, every gap takes
+// the last non-gap question. Targets (:616-641): the same scan records the gap positions (ascending) and the moved targets
+// (descending) and pairs the g-th smallest gap with the g-th smallest moved target.
+void PlanCompactQuestions(const GapSet &gaps, int64_t n, int64_t *oldIds) {
+  int64_t iFirst, iLast;
+  for (iFirst = 0, iLast = n - 1; iFirst <= iLast; iFirst++) {
+    if (!gaps.IsGap(iFirst)) { oldIds[iFirst] = iFirst; continue; }
+    while (gaps.IsGap(iLast) && iLast > iFirst) iLast--;
+    if (iFirst == iLast) break;
+    oldIds[iFirst] = iLast;
+    iLast--;
+  }
+}
+void PlanCompactTargets(const GapSet &gaps, int64_t n, int64_t *oldIds) {
+  std::vector<int64_t> dests, srcs;
+  int64_t iFirst, iLast;
+  for (iFirst = 0, iLast = n - 1; iFirst <= iLast; iFirst++) {
+    if (!gaps.IsGap(iFirst)) { oldIds[iFirst] = iFirst; continue; }
+    while (gaps.IsGap(iLast) && iLast > iFirst) iLast--;
+    if (iFirst == iLast) break;
+    dests.push_back(iFirst);
+    srcs.push_back(iLast);
+    iLast--;
+  }
+  const size_t nMoves = dests.size();
+  for (size_t g = 0; g < nMoves; g++) oldIds[dests[g]] = srcs[nMoves - 1 - g];
+}
+
+// Host-logic self test (no device needed; called by the CPU test suite through PqaB200_HostLogicSelfTest): gap sets,
+// permanent ids and the compaction planners against brute-force expectations. Returns an empty string when all is well.
+std::string HostLogicSelfTest() {
+  auto fail = [](const char *what, int64_t a, int64_t b) { return std::string(what) + " (" + std::to_string(a) + " vs " + std::to_string(b) + ")"; };
+  uint64_t lcg = 88172645463325252ull;
+  auto rnd = [&](uint64_t m) { lcg ^= lcg << 13; lcg ^= lcg >> 7; lcg ^= lcg << 17; return (int64_t)(lcg % m); };
+  for (int trial = 0; trial < 200; trial++) {
+    const int64_t n = 2 + rnd(60);
+    GapSet gs; gs.GrowTo(n);
+    PermIds pim; pim.GrowTo(n);
+    std::vector<int64_t> removedOrder;
+    std::vector<uint8_t> gone((size_t)n, 0);
+    const int64_t nRemove = rnd((uint64_t)n);                 // at least one id survives
+    for (int64_t r = 0; r < nRemove; r++) {
+      const int64_t id = rnd((uint64_t)n);
+      if (gone[(size_t)id]) continue;
+      gone[(size_t)id] = 1; removedOrder.push_back(id);
+      gs.Release(id);
+      if (!pim.RemoveComp(id)) return "RemoveComp refused a live id";
+      if (pim.RemoveComp(id)) return "RemoveComp accepted a removed id";
+    }
+    if (gs.GetNGaps() != (int64_t)removedOrder.size()) return fail("gap count", gs.GetNGaps(), (int64_t)removedOrder.size());
+    for (int64_t i = 0; i < n; i++) {
+      if (gs.IsGap(i) != (gone[(size_t)i] != 0)) return fail("IsGap", i, gone[(size_t)i]);
+      if (pim.PermFromComp(i) != (gone[(size_t)i] ? -1 : i)) return fail("PermFromComp", i, pim.PermFromComp(i));
+      if (pim.CompFromPerm(i) != (gone[(size_t)i] ? -1 : i)) return fail("CompFromPerm", i, pim.CompFromPerm(i));
+    }
+    // compaction plans: a permutation of the survivors onto 0..nLive-1, fixed points stay, questions take the LAST
+    // survivor for the first gap, targets pair ascending gaps with ascending moved survivors
+    const int64_t nLive = n - gs.GetNGaps();
+    std::vector<int64_t> oq((size_t)n, -7), ot((size_t)n, -7);
+    PlanCompactQuestions(gs, n, oq.data());
+    PlanCompactTargets(gs, n, ot.data());
+    for (const std::vector<int64_t> *plan : {&oq, &ot}) {
+      std::vector<uint8_t> used((size_t)n, 0);
+      for (int64_t i = 0; i < nLive; i++) {
+        const int64_t o = (*plan)[(size_t)i];
+        if (o < 0 || o >= n || gone[(size_t)o] || used[(size_t)o]) return fail("compaction plan is not a permutation of the survivors", i, o);
+        used[(size_t)o] = 1;
+        if (!gone[(size_t)i] && o != i) return fail("a surviving id below the new size moved", i, o);
+        if (gone[(size_t)i] && o < nLive) return fail("a gap was filled from inside the new range", i, o);
+      }
+    }
+    int64_t prevQ = n, prevT = -1;
+    for (int64_t i = 0; i < nLive; i++) {
+      if (!gone[(size_t)i]) continue;
+      if (oq[(size_t)i] >= prevQ) return fail("questions: gaps must take survivors from the end downwards", i, oq[(size_t)i]);
+      if (ot[(size_t)i] <= prevT) return fail("targets: gaps must take moved survivors in ascending order", i, ot[(size_t)i]);
+      prevQ = oq[(size_t)i]; prevT = ot[(size_t)i];
+    }
+    // permanent ids follow their rows through the compaction; re-added ids get fresh permanent ids
+    PermIds pim2 = pim;
+    if (!pim2.OnCompact(nLive, oq.data())) return "OnCompact refused a valid plan";
+    for (int64_t i = 0; i < nLive; i++)
+      if (pim2.PermFromComp(i) != oq[(size_t)i] || pim2.CompFromPerm(oq[(size_t)i]) != i) return fail("OnCompact mapping", i, pim2.PermFromComp(i));
+    int64_t nextPerm = n;
+    while (gs.GetNGaps() > 0) {
+      const int64_t want = removedOrder.back(); removedOrder.pop_back();
+      const int64_t got = gs.Acquire();                        // LIFO reuse (GapTracker.h:38-49)
+      if (got != want) return fail("gap reuse order", got, want);
+      if (!pim.RenewComp(got) || pim.PermFromComp(got) != nextPerm) return fail("RenewComp permanent id", pim.PermFromComp(got), nextPerm);
+      nextPerm++;
+    }
+    if (gs.Acquire() != n) return "Acquire without gaps must append";
+  }
+  PermIds q;
+  q.GrowTo(3);
+  if (q.EnsurePermIdGreater(1) || !q.EnsurePermIdGreater(9)) return "EnsurePermIdGreater";
+  q.GrowTo(4);
+  if (q.PermFromComp(3) != 10) return "GrowTo after EnsurePermIdGreater";
+  if (q.RemapPermId(0, 10) || q.RemapPermId(0, 11) || !q.RemapPermId(0, 5) || q.CompFromPerm(5) != 0 || q.CompFromPerm(0) != -1) return "RemapPermId";
+  return "";
+}
+
 // BaseEngine::Compact (BaseEngine.cpp:768-779) -> CpuEngine::CompactSpec (CpuEngine.cpp:585-658).
 // Questions: scanning from the front, every gap takes the last non-gap question (rows swapped, :594-608).
 // Targets: the same scan records the gap positions in ascending order and the moved targets in descending order, and
@@ -386,30 +488,8 @@ PqaError *Engine::Compact(int64_t *pnQuestions, const int64_t **ppOldQuestions, 
   const int64_t nQ = Q_ - qGaps_.GetNGaps(), nT = T_ - tGaps_.GetNGaps();
   if (nQ < 1 || nT < 2) return ErrInsufficientDims(K_, nQ, nT);
   std::unique_ptr<int64_t[]> oldQ(new int64_t[(size_t)std::max<int64_t>(nQ, 1)]), oldT(new int64_t[(size_t)std::max<int64_t>(nT, 1)]);
-  {
-    int64_t iFirst, iLast;
-    for (iFirst = 0, iLast = Q_ - 1; iFirst <= iLast; iFirst++) {
-      if (!qGaps_.IsGap(iFirst)) { oldQ[(size_t)iFirst] = iFirst; continue; }
-      while (qGaps_.IsGap(iLast) && iLast > iFirst) iLast--;
-      if (iFirst == iLast) break;
-      oldQ[(size_t)iFirst] = iLast;
-      iLast--;
-    }
-  }
-  {
-    std::vector<int64_t> dests, srcs;
-    int64_t iFirst, iLast;
-    for (iFirst = 0, iLast = T_ - 1; iFirst <= iLast; iFirst++) {
-      if (!tGaps_.IsGap(iFirst)) { oldT[(size_t)iFirst] = iFirst; continue; }
-      while (tGaps_.IsGap(iLast) && iLast > iFirst) iLast--;
-      if (iFirst == iLast) break;
-      dests.push_back(iFirst);
-      srcs.push_back(iLast);
-      iLast--;
-    }
-    const size_t nMoves = dests.size();
-    for (size_t g = 0; g < nMoves; g++) oldT[(size_t)dests[g]] = srcs[nMoves - 1 - g];
-  }
+  PlanCompactQuestions(qGaps_, Q_, oldQ.get());
+  PlanCompactTargets(tGaps_, T_, oldT.get());
   const int64_t newTp = (nT + 3) & ~3ll;
   DevBuf<int64_t> dOldQ, dOldT, dZero;
   dOldQ.ensure((size_t)nQ, stream_); dOldT.ensure((size_t)nT, stream_); dZero.ensure(1, stream_);

@@ -112,6 +112,7 @@ SIGNATURES = {
     "PqaB200_CreateShardedEngine": (_vp, [_pvp, C.POINTER(CiEngineDefinition), C.POINTER(CiB200Options), C.POINTER(CiB200GroupOptions)]),
     "PqaB200_LoadShardedEngine": (_vp, [_pvp, C.c_char_p, C.POINTER(CiB200Options), C.POINTER(CiB200GroupOptions)]),
     "PqaB200_GetShardCount": (C.c_int32, [_vp]),
+    "PqaB200_HostLogicSelfTest": (_vp, []),
     "PqaB200_SaveKBShard": (_vp, [_vp, C.c_char_p, C.c_int32]),
     "PqaB200_GetEmulatedWorkers": (C.c_int32, [_vp]),
     "PqaB200_GetDevice": (C.c_int32, [_vp]),

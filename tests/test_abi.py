@@ -96,3 +96,15 @@ def test_product_does_not_touch_the_oracle():
                 code = "\n".join(l for l in src.splitlines() if not l.lstrip().startswith(("#", "//", "*", '"""')))
                 assert "import oracle" not in code and "from oracle" not in code and "libpqa_oracle" not in code \
                     and "libpqa_ref" not in code, os.path.join(dirpath, f)
+
+
+def test_host_logic_self_test_without_gpu(pqa):
+    """Gap sets (GapTracker.h), permanent ids (PermanentIdManager.cpp) and the compaction plans of CpuEngine::CompactSpec
+    (CpuEngine.cpp:594-641) checked inside the library against brute-force expectations -- host code, no device."""
+    import ctypes as C
+    lib = pqa.load_library()
+    msg = lib.PqaB200_HostLogicSelfTest()
+    if msg:
+        text = C.string_at(msg).decode()
+        lib.CiReleaseString(C.c_void_p(msg))
+        raise AssertionError(text)
