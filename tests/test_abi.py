@@ -108,3 +108,26 @@ def test_host_logic_self_test_without_gpu(pqa):
         text = C.string_at(msg).decode()
         lib.CiReleaseString(C.c_void_p(msg))
         raise AssertionError(text)
+
+
+def test_headers_are_plain_c_and_a_c_client_links(tmp_path):
+    """include/*.h must be consumable by a C compiler (the drop-in boundary is a C ABI: no C++ or torch types in the
+    signatures), and a C translation unit using both headers must link against libPqaCore.so."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "client.c"
+    src.write_text(
+        '#include "PqaCInterop.h"\n#include "PqaB200Ext.h"\n#include <stddef.h>\n'
+        'int main(void) {\n'
+        '  CiEngineDefinition def = {0}; CiB200Options o = {0}; CiB200GroupOptions g = {0};\n'
+        '  def._nAnswers = 5; o._device = -1; g._nShards = 2;\n'
+        '  /* never called without a GPU: only has to compile and link */\n'
+        '  if (def._nAnswers == 0) { void *err = NULL; void *e = PqaB200_CreateShardedEngine(&err, &def, &o, &g);\n'
+        '    PqaEngine_StartQuiz(e, &err); PqaEngine_NextQuestionBatch(e, 0, NULL, NULL, NULL, NULL); CiReleasePqaEngine(e); }\n'
+        '  return PqaB200_BuildInfo() == NULL;\n}\n')
+    from probqa_b200 import build
+    lib_dir = os.path.dirname(build.build())
+    exe = tmp_path / "client"
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(root, "include"), str(src),
+                           "-o", str(exe), "-L" + lib_dir, "-lPqaCore", "-Wl,-rpath," + lib_dir])
+    assert subprocess.run([str(exe)]).returncode == 0
