@@ -1,7 +1,8 @@
 // probqa_b200: one engine over several GPUs of a box, in ONE process, behind the reference's C ABI.
 // A ShardGroup owns N shard engines (question shards or target shards, pqa_engine.h), one per device, wires their
 // peer-memory inboxes together (PqaB200_P2P*: the kernels exchange over NVLink, no host round trip, no NCCL) and
-// presents the IPqaEngine method set: StartQuiz / NextQuestion / RecordAnswer / ListTopTargets / RecordQuizTarget / Train /
+// presents the IPqaEngine method set (PqaCore/Interface/IPqaEngine.h:13-114; validation order and error codes of
+// BaseEngine.cpp:399-603 through the inherited shell): StartQuiz / NextQuestion / RecordAnswer / ListTopTargets / RecordQuizTarget / Train /
 // ReleaseQuiz / SaveKB ... and their batch forms. It is itself an Engine *shell*: the quiz registry, id validation, error
 // objects and the combiner of concurrent one-quiz calls are the base class's; only the device work is fanned out.
 #pragma once
