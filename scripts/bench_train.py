@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """BASELINE config 5: 10^6 RecordQuizTarget cell updates = 125 000 quizzes x 8 answered questions on 1000Q x 5A x 1000T,
 B200 engine (one PqaEngine_RecordQuizTargetBatch call through the C ABI, host buffers) vs the CPU oracle applying the
-same quizzes one RecordQuizTarget at a time; the final sA/mD/vB are compared bit for bit. Prints one JSON line."""
+same quizzes one RecordQuizTarget at a time (the CPU-baseline leg of this bench: the only place it touches oracle/); the final
+sA/mD/vB are compared bit for bit. Prints one JSON line."""
 import argparse, json, os, sys, time
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Generates tests/golden/ref_vectors.npz from the REFERENCE'S OWN CODE (oracle/_ref/libpqa_ref.so = the subtask bodies of
+"""TEST INFRASTRUCTURE. Generates tests/golden/ref_vectors.npz from the REFERENCE'S OWN CODE (oracle/_ref/libpqa_ref.so = the subtask bodies of
 /root/reference/ProbQA compiled where they lie by oracle/build_ref.sh). Run in the build container, where /root/reference
 exists; the fixtures travel with the repo, so the oracle restatement (CPU tests) and the CUDA path (GPU tests) are checked
 against the reference's outputs even where neither /root/reference nor oracle/_ref is present (tests/test_golden.py).
@@ -17,7 +17,7 @@ import sys
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from oracle import ref  # noqa: E402
 from probqa_b200 import synth  # noqa: E402

@@ -1,4 +1,4 @@
-"""Golden vectors produced by the REFERENCE'S OWN compiled code (scripts/make_golden.py -> tests/golden/ref_vectors.npz):
+"""Golden vectors produced by the REFERENCE'S OWN compiled code (tests/golden/make_golden.py -> tests/golden/ref_vectors.npz):
 the CPU oracle must reproduce them bit for bit (-m "not gpu": this is what pins the oracle where neither /root/reference nor
 oracle/_ref exists), and the CUDA path, through the C ABI, must meet its parity bars against them (-m gpu)."""
 import os

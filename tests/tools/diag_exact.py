@@ -1,6 +1,6 @@
-"""Diagnostic: exact kernel vs oracle at full size, which component differs (GPU)."""
+"""TEST INFRASTRUCTURE. Diagnostic: exact kernel vs oracle at full size, which component differs (GPU)."""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 from probqa_b200 import engine as pqa, synth
 from oracle import oracle as ora
