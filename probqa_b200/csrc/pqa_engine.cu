@@ -98,7 +98,7 @@ Engine::Engine(const CiEngineDefinition &def, const CiB200Options &opts) {
   launch_fill_kb(kb(), initSqr, initSqr * (double)K_, initAmount_, stream_);
   if (IsTargetSharded()) launch_fill_kb(kbQuiz(), initSqr, initSqr * (double)K_, initAmount_, stream_);   // full-length vB
   EnsureQuizCapacity(opts._initialQuizCapacity > 0 ? opts._initialQuizCapacity : 256);
-  PQA_CU(cudaStreamSynchronize(stream_));
+  PQA_CU(cudaGetLastError()); PQA_CU(cudaStreamSynchronize(stream_));
 }
 
 Engine::Engine(const CiEngineDefinition &def, const CiB200Options &opts, ShellTag) {
@@ -182,7 +182,7 @@ void Engine::EnsureQuizCapacity(int64_t nSlots) {
     PQA_CU(cudaMemcpyAsync(nl, dLogPriors_, sizeof(double) * (size_t)(quizCap_ * Tp_), cudaMemcpyDeviceToDevice, stream_));
     PQA_CU(cudaMemcpyAsync(na, dAsked_, sizeof(uint64_t) * (size_t)(quizCap_ * askedWords_), cudaMemcpyDeviceToDevice, stream_));
     PQA_CU(cudaMemcpyAsync(nact, dActive_, sizeof(int64_t) * (size_t)quizCap_, cudaMemcpyDeviceToDevice, stream_));
-    PQA_CU(cudaStreamSynchronize(stream_));
+    PQA_CU(cudaGetLastError()); PQA_CU(cudaStreamSynchronize(stream_));
     cudaFree(dPriors_); cudaFree(dLogPriors_); cudaFree(dAsked_); cudaFree(dActive_);
   }
   dPriors_ = np; dLogPriors_ = nl; dAsked_ = na; dActive_ = nact;
@@ -246,7 +246,7 @@ PqaError *Engine::StartQuizBatch(int64_t n, int64_t *pQuizIds) {
   EnsureQuizCapacity((int64_t)quizzes_.size());
   UploadIds(n, pQuizIds);
   launch_start_quiz(kbQuiz(), pool(), n, dIds_.get(), W_, stream_);
-  PQA_CU(cudaStreamSynchronize(stream_));
+  PQA_CU(cudaGetLastError()); PQA_CU(cudaStreamSynchronize(stream_));
   return nullptr;
   PQA_CATCH_RETURN_ERR
 }
@@ -308,7 +308,7 @@ PqaError *Engine::ResumeQuizBatch(int64_t n, const int64_t *pCounts, const CiAns
   if (!startIds.empty()) {
     UploadIds((int64_t)startIds.size(), startIds.data());
     launch_start_quiz(kbQuiz(), pool(), (int64_t)startIds.size(), dIds_.get(), W_, stream_);
-    PQA_CU(cudaStreamSynchronize(stream_));
+    PQA_CU(cudaGetLastError()); PQA_CU(cudaStreamSynchronize(stream_));
   }
   PqaError *result = nullptr;
   if (!resumeIds.empty()) {
@@ -323,7 +323,7 @@ PqaError *Engine::ResumeQuizBatch(int64_t n, const int64_t *pCounts, const CiAns
                        reinterpret_cast<int *>(dCounts_.get()), stream_);
     std::vector<int> status((size_t)m);
     PQA_CU(cudaMemcpyAsync(status.data(), dCounts_.get(), sizeof(int) * (size_t)m, cudaMemcpyDeviceToHost, stream_));
-    PQA_CU(cudaStreamSynchronize(stream_));
+    PQA_CU(cudaGetLastError()); PQA_CU(cudaStreamSynchronize(stream_));
     for (int64_t x = 0; x < m; x++) {
       if (status[x] == 0) continue;
       // CpuEngine.cpp:316-319 -> CreateQuizInternal unassigns the quiz (:257-261)
@@ -387,7 +387,7 @@ PqaError *Engine::NextQuestionBatch(int64_t n, const int64_t *pQuizIds, const ui
     launch_select_question(kbQuiz(), pool(), m, dIds_.get(), dPriority_.get(), dRandoms_.get(), W_, dRunLength_.get(),
                            nullptr, dQuestions_.get(), 1, stream_);
     PQA_CU(cudaMemcpyAsync(hQuestions_.get(), dQuestions_.get(), sizeof(int64_t) * (size_t)m, cudaMemcpyDeviceToHost, stream_));
-    PQA_CU(cudaStreamSynchronize(stream_));
+    PQA_CU(cudaGetLastError()); PQA_CU(cudaStreamSynchronize(stream_));
     uint64_t nAsked = 0;
     for (int64_t x = 0; x < m; x++) {
       const int64_t qst = hQuestions_.get()[x];
@@ -602,7 +602,7 @@ PqaError *Engine::RecordAnswerBatch(int64_t n, const int64_t *pQuizIds, const in
     q.answers.push_back(CiAnsweredQuestion{q.activeQuestion, pAnswers[x]});  // CEQuiz.h:90
     q.activeQuestion = -1;                                                     // :92
   }
-  PQA_CU(cudaStreamSynchronize(stream_));
+  PQA_CU(cudaGetLastError()); PQA_CU(cudaStreamSynchronize(stream_));
   return nullptr;
   PQA_CATCH_RETURN_ERR
 }
@@ -647,7 +647,7 @@ PqaError *Engine::ShardEval(int64_t n, const int64_t *pQuizIds) {
   PQA_CU(cudaMemsetAsync(dShardPriority_.get(), 0, sizeof(double) * (size_t)shardPriorityCount_, stream_));  // +0.0
   EvalDetail det{nullptr, nullptr, nullptr, nullptr};
   launch_eval_questions(kb(), pool(), n, dIds_.get(), dShardPriority_.get(), det, evalCfg_, stream_);
-  PQA_CU(cudaStreamSynchronize(stream_));   // the caller's collective runs on another stream
+  PQA_CU(cudaGetLastError()); PQA_CU(cudaStreamSynchronize(stream_));   // the caller's collective runs on another stream
   return nullptr;
   PQA_CATCH_RETURN_ERR
 }
@@ -670,7 +670,7 @@ PqaError *Engine::ShardSelect(int64_t n, const int64_t *pQuizIds, const uint64_t
   launch_select_question(kbQuiz(), pool(), n, dIds_.get(), dShardPriority_.get(), dRandoms_.get(), W_, dRunLength_.get(),
                          nullptr, dQuestions_.get(), 1, stream_);
   PQA_CU(cudaMemcpyAsync(hQuestions_.get(), dQuestions_.get(), sizeof(int64_t) * (size_t)n, cudaMemcpyDeviceToHost, stream_));
-  PQA_CU(cudaStreamSynchronize(stream_));
+  PQA_CU(cudaGetLastError()); PQA_CU(cudaStreamSynchronize(stream_));
   PqaError *firstErr = nullptr;
   uint64_t nAsked = 0;
   for (int64_t x = 0; x < n; x++) {
@@ -719,7 +719,7 @@ PqaError *Engine::ShardRecordAnswerBegin(int64_t n, const int64_t *pQuizIds, con
     q.answers.push_back(CiAnsweredQuestion{q.activeQuestion, pAnswers[x]});
     q.activeQuestion = -1;
   }
-  PQA_CU(cudaStreamSynchronize(stream_));
+  PQA_CU(cudaGetLastError()); PQA_CU(cudaStreamSynchronize(stream_));
   return nullptr;
   PQA_CATCH_RETURN_ERR
 }
@@ -736,7 +736,7 @@ PqaError *Engine::ShardRecordAnswerEnd(int64_t n, const int64_t *pQuizIds) {
     launch_tshard_record_answer_finish(kbQuiz(), pool(), n, dIds_.get(), dShardPriors_.get(), std::max(1, W_ - 1), stream_);
   else
     launch_scatter_prior_rows(pool(), n, dIds_.get(), dShardPriors_.get(), stream_);
-  PQA_CU(cudaStreamSynchronize(stream_));
+  PQA_CU(cudaGetLastError()); PQA_CU(cudaStreamSynchronize(stream_));
   return nullptr;
   PQA_CATCH_RETURN_ERR
 }
@@ -774,7 +774,7 @@ PqaError *Engine::SetActiveQuestionBatch(int64_t n, const int64_t *pQuizIds, con
   PQA_CU(cudaMemcpyAsync(dQuestions_.get(), hQuestions_.get(), sizeof(int64_t) * (size_t)n, cudaMemcpyHostToDevice, stream_));
   launch_set_active(pool(), n, dIds_.get(), dQuestions_.get(), stream_);
   for (int64_t x = 0; x < n; x++) quizzes_[pQuizIds[x]].activeQuestion = pQuestions[x];  // BaseQuiz::SetActiveQuestion
-  PQA_CU(cudaStreamSynchronize(stream_));
+  PQA_CU(cudaGetLastError()); PQA_CU(cudaStreamSynchronize(stream_));
   return nullptr;
   PQA_CATCH_RETURN_ERR
 }
@@ -808,7 +808,7 @@ PqaError *Engine::ListTopTargetsBatch(int64_t n, const int64_t *pQuizIds, int64_
   launch_list_top_targets(kbQuiz(), pool(), n, dIds_.get(), W_, maxCount, dTopScratch_.get(), dTop_.get(), dCounts_.get(), stream_);
   PQA_CU(cudaMemcpyAsync(hTop_.get(), dTop_.get(), sizeof(CiRatedTarget) * nItems, cudaMemcpyDeviceToHost, stream_));
   PQA_CU(cudaMemcpyAsync(hCounts_.get(), dCounts_.get(), sizeof(int64_t) * (size_t)n, cudaMemcpyDeviceToHost, stream_));
-  PQA_CU(cudaStreamSynchronize(stream_));
+  PQA_CU(cudaGetLastError()); PQA_CU(cudaStreamSynchronize(stream_));
   for (int64_t x = 0; x < n; x++) {
     pCounts[x] = hCounts_.get()[x];
     std::memcpy(pDest + x * maxCount, hTop_.get() + x * maxCount, sizeof(CiRatedTarget) * (size_t)pCounts[x]);
@@ -873,7 +873,7 @@ PqaError *Engine::ApplyTrain(const std::vector<TrainOp> &opsAll, const std::vect
       PQA_CU(cudaMemcpyAsync(dAmounts_.get(), amounts.data(), sizeof(double) * (size_t)nT, cudaMemcpyHostToDevice, stream_));
       launch_add_vb_device_grouped(kbQuiz(), dTargets_.get(), dAmounts_.get(), nT, dSortScratch_.get(), dSortScratch_.size(), stream_);
     }
-    PQA_CU(cudaStreamSynchronize(stream_));   // the host vectors die at scope end
+    PQA_CU(cudaGetLastError()); PQA_CU(cudaStreamSynchronize(stream_));   // the host vectors die at scope end
     return nullptr;
   }
   if (nOps > 0) {
@@ -893,7 +893,7 @@ PqaError *Engine::ApplyTrain(const std::vector<TrainOp> &opsAll, const std::vect
     PQA_CU(cudaMemcpyAsync(dOps_.get(), sorted.data(), sizeof(TrainOp) * (size_t)nOps, cudaMemcpyHostToDevice, stream_));
     PQA_CU(cudaMemcpyAsync(dGroupStart_.get(), groupStart.data(), sizeof(int64_t) * groupStart.size(), cudaMemcpyHostToDevice, stream_));
     launch_train_ops(kb(), dOps_.get(), dGroupStart_.get(), nGroups, stream_);
-    PQA_CU(cudaStreamSynchronize(stream_));  // the staging vectors die at scope end
+    PQA_CU(cudaGetLastError()); PQA_CU(cudaStreamSynchronize(stream_));  // the staging vectors die at scope end
   }
   if (nT > 0) {
     std::vector<int64_t> order(nT);
@@ -912,7 +912,7 @@ PqaError *Engine::ApplyTrain(const std::vector<TrainOp> &opsAll, const std::vect
     PQA_CU(cudaMemcpyAsync(dAmounts_.get(), sa.data(), sizeof(double) * (size_t)nT, cudaMemcpyHostToDevice, stream_));
     PQA_CU(cudaMemcpyAsync(dGroupStart_.get(), groupStart.data(), sizeof(int64_t) * groupStart.size(), cudaMemcpyHostToDevice, stream_));
     launch_add_vb(kbQuiz(), dTargets_.get(), dAmounts_.get(), dGroupStart_.get(), nGroups, stream_);
-    PQA_CU(cudaStreamSynchronize(stream_));
+    PQA_CU(cudaGetLastError()); PQA_CU(cudaStreamSynchronize(stream_));
   }
   return nullptr;
   PQA_CATCH_RETURN_ERR
@@ -1091,7 +1091,7 @@ PqaError *Engine::UploadKB(const double *sA, const double *mD, const double *vB)
   }
   PQA_CU(cudaMemsetAsync(dVB_, 0, sizeof(double) * (size_t)Tp_, stream_));
   PQA_CU(cudaMemcpyAsync(dVB_, vB, sizeof(double) * (size_t)T_, cudaMemcpyHostToDevice, stream_));
-  PQA_CU(cudaStreamSynchronize(stream_));
+  PQA_CU(cudaGetLastError()); PQA_CU(cudaStreamSynchronize(stream_));
   return nullptr;
   PQA_CATCH_RETURN_ERR
 }
@@ -1116,7 +1116,7 @@ PqaError *Engine::DownloadKB(double *sA, double *mD, double *vB) {
                              cudaMemcpyDeviceToHost, stream_));
   }
   if (vB) PQA_CU(cudaMemcpyAsync(vB, dVB_, sizeof(double) * (size_t)T_, cudaMemcpyDeviceToHost, stream_));
-  PQA_CU(cudaStreamSynchronize(stream_));
+  PQA_CU(cudaGetLastError()); PQA_CU(cudaStreamSynchronize(stream_));
   return nullptr;
   PQA_CATCH_RETURN_ERR
 }
@@ -1126,7 +1126,7 @@ PqaError *Engine::CopyQuizPriors(int64_t iQuiz, double *pPriors) {
   if (PqaError *e = CheckQuiz(iQuiz)) return e;
   PQA_TRY
   PQA_CU(cudaMemcpyAsync(pPriors, dPriors_ + iQuiz * Tp_, sizeof(double) * (size_t)T_, cudaMemcpyDeviceToHost, stream_));
-  PQA_CU(cudaStreamSynchronize(stream_));
+  PQA_CU(cudaGetLastError()); PQA_CU(cudaStreamSynchronize(stream_));
   return nullptr;
   PQA_CATCH_RETURN_ERR
 }
@@ -1137,7 +1137,7 @@ PqaError *Engine::SetQuizPriors(int64_t iQuiz, const double *pPriors) {
   PQA_CU(cudaMemcpyAsync(dPriors_ + iQuiz * Tp_, pPriors, sizeof(double) * (size_t)T_, cudaMemcpyHostToDevice, stream_));
   UploadIds(1, &iQuiz);
   launch_refresh_log_priors(pool(), 1, dIds_.get(), stream_);
-  PQA_CU(cudaStreamSynchronize(stream_));
+  PQA_CU(cudaGetLastError()); PQA_CU(cudaStreamSynchronize(stream_));
   return nullptr;
   PQA_CATCH_RETURN_ERR
 }
@@ -1172,7 +1172,7 @@ PqaError *Engine::EvalQuestions(int64_t n, const int64_t *pQuizIds, double *pPri
   if (pPriorities) PQA_CU(cudaMemcpyAsync(pPriorities, dPriority_.get(), sizeof(double) * (size_t)(n * Q_), cudaMemcpyDeviceToHost, stream_));
   if (pRunLength) PQA_CU(cudaMemcpyAsync(pRunLength, dRunLength_.get(), sizeof(double) * (size_t)(n * Q_), cudaMemcpyDeviceToHost, stream_));
   if (pGrandTotals) PQA_CU(cudaMemcpyAsync(pGrandTotals, dGrand_.get(), sizeof(double) * (size_t)(n * nChunks), cudaMemcpyDeviceToHost, stream_));
-  PQA_CU(cudaStreamSynchronize(stream_));
+  PQA_CU(cudaGetLastError()); PQA_CU(cudaStreamSynchronize(stream_));
   return nullptr;
   PQA_CATCH_RETURN_ERR
 }
@@ -1194,7 +1194,7 @@ PqaError *Engine::EvalQuestionsDetailed(int64_t iQuiz, double *pW, double *pH, d
   if (pV) PQA_CU(cudaMemcpyAsync(pV, det.V, sizeof(double) * qk, cudaMemcpyDeviceToHost, stream_));
   if (pLack) PQA_CU(cudaMemcpyAsync(pLack, det.lack, sizeof(double) * (size_t)Q_, cudaMemcpyDeviceToHost, stream_));
   if (pPriorities) PQA_CU(cudaMemcpyAsync(pPriorities, dPriority_.get(), sizeof(double) * (size_t)Q_, cudaMemcpyDeviceToHost, stream_));
-  PQA_CU(cudaStreamSynchronize(stream_));
+  PQA_CU(cudaGetLastError()); PQA_CU(cudaStreamSynchronize(stream_));
   return nullptr;
   PQA_CATCH_RETURN_ERR
 }
@@ -1215,7 +1215,7 @@ PqaError *Engine::ResidentBind(int64_t n, const int64_t *pQuizIds, const uint64_
   for (int64_t x = 0; x < n; x++) rnd[x] = pRandoms ? pRandoms[x] : NextRandom();
   PQA_CU(cudaMemcpyAsync(dResIds_.get(), pQuizIds, sizeof(int64_t) * (size_t)n, cudaMemcpyHostToDevice, stream_));
   PQA_CU(cudaMemcpyAsync(dResRandoms_.get(), rnd.data(), sizeof(uint64_t) * (size_t)n, cudaMemcpyHostToDevice, stream_));
-  PQA_CU(cudaStreamSynchronize(stream_));
+  PQA_CU(cudaGetLastError()); PQA_CU(cudaStreamSynchronize(stream_));
   residentN_ = n;
   return nullptr;
   PQA_CATCH_RETURN_ERR
@@ -1240,7 +1240,7 @@ PqaError *Engine::ResidentFetch(int64_t *pQuestions) {
   if (residentN_ <= 0) return MakeError(ErrCode::NotInitialized, PQA_FILE_LINE "no resident batch is bound");
   PQA_TRY
   PQA_CU(cudaMemcpyAsync(pQuestions, dResQuestions_.get(), sizeof(int64_t) * (size_t)residentN_, cudaMemcpyDeviceToHost, stream_));
-  PQA_CU(cudaStreamSynchronize(stream_));
+  PQA_CU(cudaGetLastError()); PQA_CU(cudaStreamSynchronize(stream_));
   return nullptr;
   PQA_CATCH_RETURN_ERR
 }
@@ -1255,7 +1255,7 @@ double Engine::ResidentLastEvalMs() {
 PqaError *Engine::Synchronize() {
   DeviceScope devScope(device_);
   PQA_TRY
-  PQA_CU(cudaStreamSynchronize(stream_));
+  PQA_CU(cudaGetLastError()); PQA_CU(cudaStreamSynchronize(stream_));
   PQA_CU(cudaGetLastError());
   return nullptr;
   PQA_CATCH_RETURN_ERR
@@ -1288,7 +1288,7 @@ PqaError *Engine::TShardEvalW(int64_t n, const int64_t *pQuizIds) {
   PQA_CU(cudaMemsetAsync(dShardW_.get(), 0, sizeof(double) * (size_t)shardWCount_, stream_));   // asked questions: +0
   PeerBufs out; out.n = 1; out.p[0] = dShardW_.get();
   launch_eval_tshard_w(kb(), pool(), tFirst_, n, dIds_.get(), out, evalCfg_, stream_);
-  PQA_CU(cudaStreamSynchronize(stream_));
+  PQA_CU(cudaGetLastError()); PQA_CU(cudaStreamSynchronize(stream_));
   return nullptr;
   PQA_CATCH_RETURN_ERR
 }
@@ -1306,7 +1306,7 @@ PqaError *Engine::TShardEvalHVL(int64_t n, const int64_t *pQuizIds) {
   PQA_CU(cudaMemsetAsync(dShardHVL_.get(), 0, sizeof(double) * (size_t)shardHVLCount_, stream_));
   PeerBufs in, out; in.n = 1; in.p[0] = dShardW_.get(); out.n = 1; out.p[0] = dShardHVL_.get();
   launch_eval_tshard_hvl(kb(), pool(), tFirst_, n, dIds_.get(), in, out, evalCfg_, stream_);
-  PQA_CU(cudaStreamSynchronize(stream_));
+  PQA_CU(cudaGetLastError()); PQA_CU(cudaStreamSynchronize(stream_));
   return nullptr;
   PQA_CATCH_RETURN_ERR
 }
@@ -1325,7 +1325,7 @@ PqaError *Engine::TShardPriority(int64_t n, const int64_t *pQuizIds) {
   PeerBufs inW, inHVL; inW.n = 1; inW.p[0] = dShardW_.get(); inHVL.n = 1; inHVL.p[0] = dShardHVL_.get();
   EvalDetail det{nullptr, nullptr, nullptr, nullptr};
   launch_tshard_priority(kb(), pool(), n, dIds_.get(), inW, inHVL, dShardPriority_.get(), det, stream_);
-  PQA_CU(cudaStreamSynchronize(stream_));
+  PQA_CU(cudaGetLastError()); PQA_CU(cudaStreamSynchronize(stream_));
   return nullptr;
   PQA_CATCH_RETURN_ERR
 }
@@ -1389,7 +1389,7 @@ PqaError *Engine::P2PInit(int32_t rank, int32_t nRanks, int64_t maxQuizzes, void
   if (ts) dShardPriority_.ensure((size_t)(maxQuizzes * Q_), stream_);
   hIds_.ensure((size_t)maxQuizzes); hRandoms_.ensure((size_t)maxQuizzes); hAnswers_.ensure((size_t)maxQuizzes);
   hQuestions_.ensure((size_t)maxQuizzes);
-  PQA_CU(cudaStreamSynchronize(stream_));
+  PQA_CU(cudaGetLastError()); PQA_CU(cudaStreamSynchronize(stream_));
   p2pRank_ = rank; p2pRanks_ = nRanks; p2pCap_ = maxQuizzes;
   p2pPeer_[rank] = p2pInbox_;
   if (ppBase) *ppBase = p2pInbox_;
@@ -1460,7 +1460,7 @@ PqaError *Engine::P2PCheckError() {
   uint64_t flag = 0;
   PQA_TRY
   PQA_CU(cudaMemcpyAsync(&flag, p2pInbox_ + 64, 8, cudaMemcpyDeviceToHost, stream_));
-  PQA_CU(cudaStreamSynchronize(stream_));
+  PQA_CU(cudaGetLastError()); PQA_CU(cudaStreamSynchronize(stream_));
   if (flag != 0)
     return MakeError(ErrCode::Internal, PQA_FILE_LINE "peer-memory barrier timed out: a shard did not reach epoch " +
                      std::to_string(flag) + " (all shards must issue the same P2P calls in the same order)");
@@ -1560,6 +1560,7 @@ PqaError *Engine::P2PNextQuestionBegin(int64_t n, const int64_t *pQuizIds, const
   launch_select_question(kbQuiz(), pool(), n, dIds_.get(), priority, dRandoms_.get(), W_, dRunLength_.get(), nullptr,
                          dQuestions_.get(), 1, stream_);
   PQA_CU(cudaMemcpyAsync(hQuestions_.get(), dQuestions_.get(), sizeof(int64_t) * (size_t)n, cudaMemcpyDeviceToHost, stream_));
+  PQA_CU(cudaGetLastError());      // a kernel that failed to launch would leave the peers waiting at the barrier
   p2pPending_ = true;
   return nullptr;
   PQA_CATCH_RETURN_ERR
@@ -1632,6 +1633,7 @@ PqaError *Engine::P2PRecordAnswerBegin(int64_t n, const int64_t *pQuizIds, const
     q.answers.push_back(CiAnsweredQuestion{q.activeQuestion, pAnswers[x]});
     q.activeQuestion = -1;
   }
+  PQA_CU(cudaGetLastError());
   p2pPending_ = true;
   return nullptr;
   PQA_CATCH_RETURN_ERR
@@ -1648,7 +1650,7 @@ PqaError *Engine::FillBinarySearchKB(double rounds) {
   std::lock_guard<std::mutex> lk(mu_); DeviceScope devScope(device_);
   PQA_TRY
   launch_fill_binary_search_kb(kb(), tFirst_, T_, initAmount_, rounds, stream_);
-  PQA_CU(cudaStreamSynchronize(stream_));
+  PQA_CU(cudaGetLastError()); PQA_CU(cudaStreamSynchronize(stream_));
   return nullptr;
   PQA_CATCH_RETURN_ERR
 }
@@ -1694,7 +1696,7 @@ PqaError *Engine::WriteKBFile(FILE *f, const char *filePath, bool frame) {
       try {
         PQA_CU(cudaMemcpy2DAsync(slab.data(), (size_t)nCols * 8, dBase + r0 * stride, (size_t)stride * 8, (size_t)nCols * 8, (size_t)nr,
                                  cudaMemcpyDeviceToHost, stream_));
-        PQA_CU(cudaStreamSynchronize(stream_));
+        PQA_CU(cudaGetLastError()); PQA_CU(cudaStreamSynchronize(stream_));
       } catch (const CudaFail &cf) { return ErrCuda(cf.code, cf.what(), cf.file, cf.line); }
       if (nCols == fileRowDoubles) {            // whole rows: one contiguous write
         if (fseeko(f, (off_t)(fileOff + r0 * fileRowDoubles * 8), SEEK_SET) != 0 || !wr(f, slab.data(), (size_t)(nr * nCols) * 8))
