@@ -222,3 +222,49 @@ def test_resume_quiz_bit_exact_vs_reference(ora, ref):
                 got = ora.resume_quiz(sA, mD, vB, aqs, W, tgaps=tg)
                 assert np.array_equal(bits(got), bits(want)) and not np.signbit(want[tg]).any(), (Q, K, T, W, n)
             eng.close()
+
+
+def test_random_small_engines_vs_reference(ora, ref):
+    """Property test: random dimensions (ragged T), worker counts, KBs with zero cells, removed targets / questions and asked
+    sets -- every stage of the restatement against the reference's own code, bit for bit."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=30, deadline=None, derandomize=True)
+    @given(st.integers(2, 14), st.integers(2, 6), st.integers(2, 41), st.integers(1, 9), st.integers(0, 2 ** 31 - 1))
+    def run(Q, K, T, W, seed):
+        rng = np.random.default_rng(seed)
+        cnt = 0.1 + rng.gamma(0.5, 1.0, size=(Q, K, T)) * (rng.random((Q, K, T)) > 0.15)     # some cells stay at init
+        sA = cnt * cnt
+        mD = sA.sum(axis=1)
+        vB = 0.1 + rng.uniform(0, 5, size=T)
+        tg = rng.random(T) < 0.2
+        tg[rng.integers(0, T)] = False
+        tg[(rng.integers(0, T) + 1) % T] = False          # at least two live targets
+        qg = rng.random(Q) < 0.2
+        qg[rng.integers(0, Q)] = False
+        if tg.sum() == 0:
+            tg = None
+        if qg.sum() == 0:
+            qg = None
+        eng = ref.RefEngine(sA, mD, vB, W, qgaps=qg, tgaps=tg)
+        try:
+            p_ref, p_ora = eng.start_quiz(), ora.start_quiz(vB, W, tgaps=tg)
+            assert np.array_equal(bits(p_ref), bits(p_ora))
+            asked = np.zeros(Q, dtype=bool)
+            live_q = [i for i in range(Q) if qg is None or not qg[i]]
+            for q in rng.permutation(live_q)[:3]:
+                ev_r = eng.eval_questions(p_ref, asked)
+                ev_o = ora.eval_questions(sA, mD, p_ora, W, asked=asked, qgaps=qg, tgaps=tg)
+                assert np.array_equal(ev_r["bounds"], ev_o["bounds"])
+                assert np.array_equal(bits(ev_r["runLength"]), bits(ev_o["runLength"]))
+                assert np.array_equal(bits(ev_r["grand"]), bits(ev_o["grand"]))
+                assert eng.list_top_targets(p_ref, 5) == ora.list_top_targets(p_ora, W, 5, tgaps=tg)
+                a = int(rng.integers(0, K))
+                p_ref = eng.record_answer(p_ref, int(q), a)
+                p_ora = ora.record_answer(p_ora, sA[q, a], mD[q], max(1, W - 1), tgaps=tg)
+                assert np.array_equal(bits(p_ref), bits(p_ora))
+                asked[q] = True
+        finally:
+            eng.close()
+
+    run()
