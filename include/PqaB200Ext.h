@@ -114,6 +114,10 @@ PQACORE_API void *PqaB200_EvalQuestions(void *pvEngine, int64_t n, const int64_t
 /* Per-answer metrics of one quiz: pW/pH/pV [Q*K], pLack [Q] (CEEvalQsSubtaskConsider.cpp:88,129-132,201). */
 PQACORE_API void *PqaB200_EvalQuestionsDetailed(void *pvEngine, int64_t iQuiz, double *pW, double *pH, double *pV,
                                                 double *pLack, double *pPriorities);
+/* The same for a batch of n quizzes, evaluated by the kernel a NextQuestion batch of that size runs on: pW/pH/pV [n*Q*K],
+ * pLack / pPriorities [n*Q]. */
+PQACORE_API void *PqaB200_EvalQuestionsDetailedBatch(void *pvEngine, int64_t n, const int64_t *pQuizIds, double *pW, double *pH,
+                                                     double *pV, double *pLack, double *pPriorities);
 /* Selects which evaluation kernel the engine uses: 0 auto (= 2), 1 exact (every rounding of CpuEngine reproduced;
  * bit-identical W/H/V/lack), 2 staged (TMA + shared memory throughput kernel, tolerance-level parity). */
 PQACORE_API void *PqaB200_SetEvalKernel(void *pvEngine, int32_t which);

@@ -408,6 +408,11 @@ PQACORE_API void *PqaB200_EvalQuestionsDetailed(void *pvEngine, int64_t iQuiz, d
   if (!pvEngine) return NullEngine();
   return Ret(E(pvEngine)->EvalQuestionsDetailed(iQuiz, pW, pH, pV, pLack, pPriorities));
 }
+PQACORE_API void *PqaB200_EvalQuestionsDetailedBatch(void *pvEngine, int64_t n, const int64_t *pQuizIds, double *pW, double *pH,
+                                                     double *pV, double *pLack, double *pPriorities) {
+  if (!pvEngine) return NullEngine();
+  return Ret(E(pvEngine)->EvalQuestionsDetailedBatch(n, pQuizIds, pW, pH, pV, pLack, pPriorities));
+}
 PQACORE_API void *PqaB200_SetEvalKernel(void *pvEngine, int32_t which) {
   if (!pvEngine) return NullEngine();
   return Ret(E(pvEngine)->SetEvalKernel(which, 0, 0, 0));

@@ -1179,21 +1179,29 @@ PqaError *Engine::EvalQuestions(int64_t n, const int64_t *pQuizIds, double *pPri
 
 PqaError *Engine::EvalQuestionsDetailed(int64_t iQuiz, double *pW, double *pH, double *pV, double *pLack,
                                         double *pPriorities) {
+  return EvalQuestionsDetailedBatch(1, &iQuiz, pW, pH, pV, pLack, pPriorities);
+}
+// Per-answer metrics of a whole batch, evaluated by whichever kernel the batch size dispatches to (the parity tests use
+// this to hold the benched instantiation of the throughput kernel to the oracle: W_k bit for bit).
+PqaError *Engine::EvalQuestionsDetailedBatch(int64_t n, const int64_t *pQuizIds, double *pW, double *pH, double *pV,
+                                             double *pLack, double *pPriorities) {
+  if (n <= 0) return ErrNegativeCount(n, PQA_FILE_LINE "|n| must be positive.");
   if (IsTargetSharded()) return ErrNotImplemented("EvalQuestionsDetailed on a target-sharded engine");
   std::lock_guard<std::mutex> lk(mu_); DeviceScope devScope(device_);
-  if (PqaError *e = CheckQuiz(iQuiz)) return e;
+  for (int64_t x = 0; x < n; x++)
+    if (PqaError *e = CheckQuiz(pQuizIds[x])) return e;
   PQA_TRY
-  UploadIds(1, &iQuiz);
-  const size_t qk = (size_t)(Q_ * K_);
-  dDetail_.ensure(3 * qk + (size_t)Q_, stream_); dPriority_.ensure((size_t)Q_, stream_);
-  PQA_CU(cudaMemsetAsync(dDetail_.get(), 0xFF, sizeof(double) * (3 * qk + (size_t)Q_), stream_));  // NaN where not evaluated
+  UploadIds(n, pQuizIds);
+  const size_t nq = (size_t)(n * Q_), qk = nq * (size_t)K_;
+  dDetail_.ensure(3 * qk + nq, stream_); dPriority_.ensure(nq, stream_);
+  PQA_CU(cudaMemsetAsync(dDetail_.get(), 0xFF, sizeof(double) * (3 * qk + nq), stream_));  // NaN where not evaluated
   EvalDetail det{dDetail_.get(), dDetail_.get() + qk, dDetail_.get() + 2 * qk, dDetail_.get() + 3 * qk};
-  launch_eval_questions(kb(), pool(), 1, dIds_.get(), dPriority_.get(), det, evalCfg_, stream_);
+  launch_eval_questions(kb(), pool(), n, dIds_.get(), dPriority_.get(), det, evalCfg_, stream_);
   if (pW) PQA_CU(cudaMemcpyAsync(pW, det.W, sizeof(double) * qk, cudaMemcpyDeviceToHost, stream_));
   if (pH) PQA_CU(cudaMemcpyAsync(pH, det.H, sizeof(double) * qk, cudaMemcpyDeviceToHost, stream_));
   if (pV) PQA_CU(cudaMemcpyAsync(pV, det.V, sizeof(double) * qk, cudaMemcpyDeviceToHost, stream_));
-  if (pLack) PQA_CU(cudaMemcpyAsync(pLack, det.lack, sizeof(double) * (size_t)Q_, cudaMemcpyDeviceToHost, stream_));
-  if (pPriorities) PQA_CU(cudaMemcpyAsync(pPriorities, dPriority_.get(), sizeof(double) * (size_t)Q_, cudaMemcpyDeviceToHost, stream_));
+  if (pLack) PQA_CU(cudaMemcpyAsync(pLack, det.lack, sizeof(double) * nq, cudaMemcpyDeviceToHost, stream_));
+  if (pPriorities) PQA_CU(cudaMemcpyAsync(pPriorities, dPriority_.get(), sizeof(double) * nq, cudaMemcpyDeviceToHost, stream_));
   PQA_CU(cudaGetLastError()); PQA_CU(cudaStreamSynchronize(stream_));
   return nullptr;
   PQA_CATCH_RETURN_ERR

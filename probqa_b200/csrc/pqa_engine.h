@@ -213,6 +213,8 @@ class Engine {
   virtual PqaError *EvalQuestions(int64_t n, const int64_t *pQuizIds, double *pPriorities, double *pRunLength,
                           double *pGrandTotals, int64_t *pnChunks);
   virtual PqaError *EvalQuestionsDetailed(int64_t iQuiz, double *pW, double *pH, double *pV, double *pLack, double *pPriorities);
+  virtual PqaError *EvalQuestionsDetailedBatch(int64_t n, const int64_t *pQuizIds, double *pW, double *pH, double *pV, double *pLack,
+                                               double *pPriorities);
   virtual PqaError *SetEvalKernel(int32_t which, int64_t chunkTargets, int64_t quizzesPerCta, int32_t kahanLanesPerThread);
 
   // --- question-sharded operation (PqaB200Ext.h) ---

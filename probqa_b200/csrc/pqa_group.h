@@ -53,6 +53,7 @@ class ShardGroup : public Engine {
   PqaError *SetQuizPriors(int64_t, const double *) override { return No("SetQuizPriors"); }
   PqaError *EvalQuestions(int64_t, const int64_t *, double *, double *, double *, int64_t *) override { return No("EvalQuestions"); }
   PqaError *EvalQuestionsDetailed(int64_t, double *, double *, double *, double *, double *) override { return No("EvalQuestionsDetailed"); }
+  PqaError *EvalQuestionsDetailedBatch(int64_t, const int64_t *, double *, double *, double *, double *, double *) override { return No("EvalQuestionsDetailedBatch"); }
   PqaError *ShardEval(int64_t, const int64_t *) override { return No("Shard* protocol (the group drives its shards itself)"); }
   PqaError *ShardSelect(int64_t, const int64_t *, const uint64_t *, int64_t *, void **) override { return No("Shard* protocol"); }
   PqaError *ShardRecordAnswerBegin(int64_t, const int64_t *, const int64_t *) override { return No("Shard* protocol"); }

@@ -134,6 +134,7 @@ SIGNATURES = {
     "PqaB200_SetQuizPriors": (_vp, [_vp, _i64, _pd]),
     "PqaB200_EvalQuestions": (_vp, [_vp, _i64, _pi64, _pd, _pd, _pd, _pi64]),
     "PqaB200_EvalQuestionsDetailed": (_vp, [_vp, _i64, _pd, _pd, _pd, _pd, _pd]),
+    "PqaB200_EvalQuestionsDetailedBatch": (_vp, [_vp, _i64, _pi64, _pd, _pd, _pd, _pd, _pd]),
     "PqaB200_SetEvalKernel": (_vp, [_vp, C.c_int32]),
     "PqaB200_SetEvalTuning": (_vp, [_vp, C.c_int32, _i64, _i64, C.c_int32]),
     "PqaB200_ShardEval": (_vp, [_vp, _i64, _pi64]),
@@ -577,6 +578,16 @@ class PqaEngine:
         lack, pri = np.empty(Q), np.empty(Q)
         _raise_or_return(self._lib.PqaB200_EvalQuestionsDetailed(self.c_engine, i_quiz, _p(W, _pd), _p(H, _pd), _p(V, _pd),
                                                                  _p(lack, _pd), _p(pri, _pd)))
+        return dict(W=W, H=H, V=V, lack=lack, priority=pri)
+
+    def eval_questions_detailed_batch(self, quiz_ids):
+        """dict(W, H, V [n,Q,K], lack, priority [n,Q]) from the kernel a NextQuestion batch of this size runs on."""
+        ids = _i64arr(quiz_ids)
+        n, Q, K = ids.size, self.n_questions, self.n_answers
+        W, H, V = np.empty((n, Q, K)), np.empty((n, Q, K)), np.empty((n, Q, K))
+        lack, pri = np.empty((n, Q)), np.empty((n, Q))
+        _raise_or_return(self._lib.PqaB200_EvalQuestionsDetailedBatch(self.c_engine, n, _p(ids, _pi64), _p(W, _pd), _p(H, _pd),
+                                                                      _p(V, _pd), _p(lack, _pd), _p(pri, _pd)))
         return dict(W=W, H=H, V=V, lack=lack, priority=pri)
 
     def set_eval_kernel(self, which: int, chunk_targets: int = 0, quizzes_per_cta: int = 0, kahan_lanes_per_thread: int = 0):

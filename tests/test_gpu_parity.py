@@ -423,6 +423,61 @@ def test_full_size_staged_vs_exact_and_oracle(pqa, ora, depth):
         assert [(int(t), float(p)) for t, p in items[x][:counts[x]]] == want
 
 
+def bench_batch(eng, Q, K, T, B, depths=(0, 3, 8)):
+    """The batch bench.py times (bench.py quiz_states): quiz b has depth depths[b % 3] and synth.quiz_prefix(b, depth)."""
+    quizzes = eng.start_quiz_batch(B)
+    states = [synth.quiz_prefix(b, min(depths[b % len(depths)], Q - 1), Q, T, K) for b in range(B)]
+    for s in range(max(len(pf) for pf in states)):
+        sel = [x for x in range(B) if len(states[x]) > s]
+        eng.set_active_question_batch(quizzes[sel], [states[x][s][0] for x in sel])
+        eng.record_answer_batch(quizzes[sel], [states[x][s][1] for x in sel])
+    return quizzes, states
+
+
+@pytest.mark.parametrize("dims,B,W,sample", [
+    ((1000, 5, 1000), 256, 8, (0, 1, 2, 127, 128, 129, 254, 255)),   # BASELINE config 2 as bench.py runs it: two CTA tiles of 128 quizzes
+    ((300, 5, 999), 200, 8, (0, 64, 130, 199)),                      # ragged T (padding lanes), second tile partly filled
+    ((200, 3, 1400), 65, 4, (0, 31, 32, 64)),                        # smallest batch that takes the 8-warp / two-threads-per-quiz shape
+])
+def test_benched_instantiation_vs_oracle(pqa, ora, dims, B, W, sample):
+    """The instantiation behind every BENCH / SCALE number -- default tuning, batch > 64, whole slab in shared memory
+    (k_eval_staged<K,2,8>) -- against the oracle (CEEvalQsSubtaskConsider.cpp:41-217): priorities 2e-12 flat, W_k bit for
+    bit, H_k / V_k / lack 1e-12, run-lengths and the selected question for the same 64-bit draw."""
+    Q, K, T = dims
+    kb = synth.binary_search_kb(Q, K, T, INIT, 3)
+    eng = make_engine(pqa, Q, K, T, W, kb)
+    eng.set_eval_kernel(0)
+    quizzes, states = bench_batch(eng, Q, K, T, B)
+    det = eng.eval_questions_detailed_batch(quizzes)
+    ev = eng.eval_questions(quizzes)
+    assert np.array_equal(bits(det["priority"]), bits(ev["priority"]))   # the same kernel, run twice: deterministic
+    rng = np.random.default_rng(5)
+    randoms = rng.integers(0, 2 ** 64, size=B, dtype=np.uint64)
+    chosen = eng.next_question_batch(quizzes, randoms)
+    bounds = ora.calc_split(Q, 8 * W)
+    for x in range(B):      # cheap checks on every quiz of the batch
+        asked = np.zeros(Q, dtype=bool)
+        asked[[q for q, _ in states[x]]] = True
+        assert np.array_equal(np.isnan(ev["priority"][x]), asked), x
+        e1 = dict(runLength=ev["runLength"][x], grand=ev["grand"][x], bounds=bounds)
+        assert chosen[x] == ora.select_question(e1, Q, int(randoms[x]), asked=asked), x
+    for x in sample:        # the oracle on a sample covering every depth and both quiz tiles
+        prior = eng.copy_quiz_priors(int(quizzes[x]))
+        asked = np.isnan(ev["priority"][x])
+        ok = ~asked
+        oev = oracle_eval_all(ora, kb, prior, W, asked)
+        rel = np.abs(ev["priority"][x][ok] - oev["priority"][ok]) / np.abs(oev["priority"][ok])
+        assert rel.max() <= TOL_STAGED, (x, float(rel.max()))
+        assert np.allclose(ev["runLength"][x], oev["runLength"], rtol=4 * TOL_STAGED, atol=0)
+        assert np.allclose(ev["grand"][x], oev["grand"], rtol=4 * TOL_STAGED, atol=0)
+        for i in np.flatnonzero(ok)[::max(1, Q // 120)]:
+            o = ora.eval_question(kb[0][i], kb[1][i], prior)
+            assert np.array_equal(bits(det["W"][x, i]), bits(o["W"])), (x, i)
+            assert np.allclose(det["H"][x, i], o["H"], rtol=1e-12, atol=0)
+            assert np.allclose(det["V"][x, i], o["V"], rtol=1e-12, atol=0)
+            assert abs(det["lack"][x, i] - o["lack"]) <= 1e-12 * abs(o["lack"])
+
+
 def test_kb_file_roundtrip_in_reference_layout(pqa, tmp_path):
     """SaveKB / LoadCpuEngine in the reference's byte layout (BaseEngine.cpp:323-385, CpuEngine.cpp:664-688,
     PermanentIdManager.cpp:27-39): header, sA rows, mD rows, vB, empty gap lists, identity id maps."""
