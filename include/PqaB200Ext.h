@@ -188,6 +188,9 @@ PQACORE_API void *PqaB200_P2PNextQuestionBegin(void *pvEngine, int64_t n, const 
 PQACORE_API void *PqaB200_P2PNextQuestionEnd(void *pvEngine, int64_t n, const int64_t *pQuizIds, int64_t *pQuestions, void **ppErrors);
 PQACORE_API void *PqaB200_P2PRecordAnswerBegin(void *pvEngine, int64_t n, const int64_t *pQuizIds, const int64_t *pAnswers);
 PQACORE_API void *PqaB200_P2PRecordAnswerEnd(void *pvEngine);
+/* Target shards: device time (ms, CUDA events on the engine's stream) of the five stages of the most recent
+ * P2PNextQuestion -- phase 1, exchange barrier, phase 2, exchange barrier, epilogue + selection. Call after its End. */
+PQACORE_API void *PqaB200_P2PLastPhaseMs(void *pvEngine, double *pMs5);
 /* Target shards only. on != 0: the evaluation's first phase becomes a pipeline in target order -- the 4-lane Kahan state of
  * every (quiz, question, answer) is handed from shard to shard through the inboxes, tile of questions by tile, and the
  * last shard finishes the reference's own sum and publishes W_k to all shards. W_k is then bit-identical to a single

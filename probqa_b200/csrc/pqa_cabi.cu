@@ -503,6 +503,11 @@ PQACORE_API void *PqaB200_P2PRecordAnswerEnd(void *pvEngine) {
   if (!pvEngine) return NullEngine();
   return Ret(E(pvEngine)->P2PRecordAnswerEnd());
 }
+PQACORE_API void *PqaB200_P2PLastPhaseMs(void *pvEngine, double *pMs5) {
+  if (!pvEngine) return NullEngine();
+  if (!pMs5) return Ret(MakeError(ErrCode::NullArgument, "pMs5"));
+  return Ret(E(pvEngine)->P2PLastPhaseMs(pMs5));
+}
 PQACORE_API void *PqaB200_P2PSetExactOrder(void *pvEngine, int32_t on) {
   if (!pvEngine) return NullEngine();
   return Ret(E(pvEngine)->P2PSetExactOrder(on));

@@ -136,17 +136,20 @@ Engine::~Engine() {
                 (double)statCalls_[k] / (double)statKindLaunches_[k]);
   }
   cudaFree(dSA_); cudaFree(dMD_); cudaFree(dVB_); cudaFree(dLog2Tbl_);
+  cudaFree(dDerR_); cudaFree(dDerL_);
   cudaFree(dPriors_); cudaFree(dLogPriors_); cudaFree(dAsked_); cudaFree(dActive_);
   for (int r = 0; r < kMaxPeers; r++) if (p2pOpened_[r]) cudaIpcCloseMemHandle(p2pPeer_[r]);
   if (p2pInbox_) cudaFree(p2pInbox_);
   if (flushBuf_) cudaFree(flushBuf_);
   if (evEvalStart_) { cudaEventDestroy(evEvalStart_); cudaEventDestroy(evEvalStop_); }
+  for (cudaEvent_t e : p2pEv_) if (e) cudaEventDestroy(e);
   if (stream_) cudaStreamDestroy(stream_);
 }
 
 DeviceKB Engine::kb() const {
   DeviceKB k;
   k.sA = dSA_; k.mD = dMD_; k.vB = dVB_; k.log2tbl = dLog2Tbl_;
+  k.dR = dDerR_; k.dL = dDerL_;
   // gap bitmaps exist only while something is removed (RemoveTargets / RemoveQuestions without a Compact yet)
   k.tgaps = tGaps_.GetNGaps() > 0 ? dTGapBits_.get() : nullptr;
   k.qgaps = qGaps_.GetNGaps() > 0 ? dQGapBits_.get() : nullptr;
@@ -159,8 +162,52 @@ DeviceKB Engine::kb() const {
 // Identical to kb() unless the engine is target-sharded, in which case it carries no sA/mD rows at all.
 DeviceKB Engine::kbQuiz() const {
   DeviceKB k = kb();
-  if (IsTargetSharded()) { k.sA = nullptr; k.mD = nullptr; k.qCount = 0; k.T = T_; k.Tp = Tp_; }
+  if (IsTargetSharded()) { k.sA = nullptr; k.mD = nullptr; k.dR = nullptr; k.dL = nullptr; k.qCount = 0; k.T = T_; k.Tp = Tp_; }
   return k;
+}
+// caller holds mu_ and has this engine's device current
+DeviceKB Engine::kbEval() {
+  if (K_ > 8) return kb();      // served by the exact kernel, which reads sA / mD
+  size_t nR = 0, nL = 0;
+  derived_kb_doubles(kb(), &nR, &nL);
+  if (nR > derCapR_ || nL > derCapL_ || !dDerR_) {
+    PQA_CU(cudaStreamSynchronize(stream_));
+    if (dDerR_) cudaFree(dDerR_);
+    if (dDerL_) cudaFree(dDerL_);
+    dDerR_ = dDerL_ = nullptr; derCapR_ = derCapL_ = 0;
+    PQA_CU(cudaMalloc(&dDerR_, sizeof(double) * nR));
+    PQA_CU(cudaMalloc(&dDerL_, sizeof(double) * nL));
+    derCapR_ = nR; derCapL_ = nL;
+    derAllDirty_ = true;
+  }
+  if (derAllDirty_) {
+    launch_build_derived(kb(), nullptr, 0, stream_);
+  } else if (!derDirtyList_.empty()) {
+    const int64_t nd = (int64_t)derDirtyList_.size();
+    // the previous rebuild may still be reading the list: stream order protects the device buffer, the copy below is from
+    // pageable host memory and therefore staged before cudaMemcpyAsync returns
+    dDerList_.ensure((size_t)nd, stream_);
+    PQA_CU(cudaMemcpyAsync(dDerList_.get(), derDirtyList_.data(), sizeof(int64_t) * (size_t)nd, cudaMemcpyHostToDevice, stream_));
+    launch_build_derived(kb(), dDerList_.get(), nd, stream_);
+  }
+  for (int64_t q : derDirtyList_) derDirtyMark_[(size_t)q] = 0;
+  derDirtyList_.clear();
+  derAllDirty_ = false;
+  return kb();
+}
+void Engine::MarkQuestionsChanged(const std::vector<TrainOp> &ops) {
+  if (derAllDirty_) return;
+  if ((int64_t)derDirtyMark_.size() != qLocal_) derDirtyMark_.assign((size_t)qLocal_, 0);
+  for (const TrainOp &o : ops) {
+    const int64_t ql = o.q - qFirst_;
+    if (ql < 0 || ql >= qLocal_ || derDirtyMark_[(size_t)ql]) continue;
+    derDirtyMark_[(size_t)ql] = 1;
+    derDirtyList_.push_back(ql);
+  }
+  if ((int64_t)derDirtyList_.size() * 2 > qLocal_) {      // most questions touched: rebuild everything in one sweep
+    for (int64_t q : derDirtyList_) derDirtyMark_[(size_t)q] = 0;
+    MarkKBChanged();
+  }
 }
 QuizPool Engine::pool() const {
   QuizPool p;
@@ -173,8 +220,11 @@ void Engine::EnsureQuizCapacity(int64_t nSlots) {
   if (nSlots <= quizCap_) return;
   const int64_t cap = std::max<int64_t>(std::max<int64_t>(nSlots, quizCap_ * 2), 64);
   double *np = nullptr, *nl = nullptr; uint64_t *na = nullptr; int64_t *nact = nullptr;
-  PQA_CU(cudaMalloc(&np, sizeof(double) * (size_t)(cap * Tp_)));
-  PQA_CU(cudaMalloc(&nl, sizeof(double) * (size_t)(cap * Tp_)));
+  // + one vector: the evaluation kernels prefetch the priors one 4-target vector ahead, also past a row's end
+  PQA_CU(cudaMalloc(&np, sizeof(double) * (size_t)(cap * Tp_ + 4)));
+  PQA_CU(cudaMalloc(&nl, sizeof(double) * (size_t)(cap * Tp_ + 4)));
+  PQA_CU(cudaMemsetAsync(np + cap * Tp_, 0, sizeof(double) * 4, stream_));
+  PQA_CU(cudaMemsetAsync(nl + cap * Tp_, 0, sizeof(double) * 4, stream_));
   PQA_CU(cudaMalloc(&na, sizeof(uint64_t) * (size_t)(cap * askedWords_)));
   PQA_CU(cudaMalloc(&nact, sizeof(int64_t) * (size_t)cap));
   if (quizCap_ > 0) {
@@ -383,7 +433,7 @@ PqaError *Engine::NextQuestionBatch(int64_t n, const int64_t *pQuizIds, const ui
     dPriority_.ensure((size_t)(m * Q_), stream_); dRunLength_.ensure((size_t)(m * Q_), stream_);
     dQuestions_.ensure(m, stream_); hQuestions_.ensure(m);
     EvalDetail det{nullptr, nullptr, nullptr, nullptr};
-    launch_eval_questions(kb(), pool(), m, dIds_.get(), dPriority_.get(), det, evalCfg_, stream_);
+    launch_eval_questions(kbEval(), pool(), m, dIds_.get(), dPriority_.get(), det, evalCfg_, stream_);
     launch_select_question(kbQuiz(), pool(), m, dIds_.get(), dPriority_.get(), dRandoms_.get(), W_, dRunLength_.get(),
                            nullptr, dQuestions_.get(), 1, stream_);
     PQA_CU(cudaMemcpyAsync(hQuestions_.get(), dQuestions_.get(), sizeof(int64_t) * (size_t)m, cudaMemcpyDeviceToHost, stream_));
@@ -646,7 +696,7 @@ PqaError *Engine::ShardEval(int64_t n, const int64_t *pQuizIds) {
   dShardPriority_.ensure((size_t)shardPriorityCount_, stream_);
   PQA_CU(cudaMemsetAsync(dShardPriority_.get(), 0, sizeof(double) * (size_t)shardPriorityCount_, stream_));  // +0.0
   EvalDetail det{nullptr, nullptr, nullptr, nullptr};
-  launch_eval_questions(kb(), pool(), n, dIds_.get(), dShardPriority_.get(), det, evalCfg_, stream_);
+  launch_eval_questions(kbEval(), pool(), n, dIds_.get(), dShardPriority_.get(), det, evalCfg_, stream_);
   PQA_CU(cudaGetLastError()); PQA_CU(cudaStreamSynchronize(stream_));   // the caller's collective runs on another stream
   return nullptr;
   PQA_CATCH_RETURN_ERR
@@ -858,6 +908,7 @@ PqaError *Engine::ApplyTrain(const std::vector<TrainOp> &opsAll, const std::vect
       if (o.target >= tFirst_ && o.target < tFirst_ + tLocal_) { owned.push_back(o); owned.back().target -= tFirst_; }
   }
   const std::vector<TrainOp> &ops = IsSharded() ? owned : opsAll;
+  MarkQuestionsChanged(ops);
   const int64_t nOps = (int64_t)ops.size();
   const int64_t nT = (int64_t)targets.size();
   const int64_t kDeviceGrouping = 8192;   // from here on the grouping by cell is a device radix sort (pqa_train_sort.cu)
@@ -1067,6 +1118,7 @@ PqaError *Engine::UploadKB(const double *sA, const double *mD, const double *vB)
   // the host arrays always describe the whole KB; a question-sharded engine takes its rows out of them, a
   // target-sharded engine its columns
   sA += qFirst_ * K_ * T_ + tFirst_; mD += qFirst_ * T_ + tFirst_;
+  MarkKBChanged();
   const int64_t Q_ = qLocal_;   // rows handled below
   if (Tp_ == T_ && !IsTargetSharded()) {
     PQA_CU(cudaMemcpyAsync(dSA_, sA, sizeof(double) * (size_t)(Q_ * K_ * T_), cudaMemcpyHostToDevice, stream_));
@@ -1166,7 +1218,7 @@ PqaError *Engine::EvalQuestions(int64_t n, const int64_t *pQuizIds, double *pPri
   dPriority_.ensure((size_t)(n * Q_), stream_); dRunLength_.ensure((size_t)(n * Q_), stream_);
   dGrand_.ensure((size_t)(n * nChunks), stream_);
   EvalDetail det{nullptr, nullptr, nullptr, nullptr};
-  launch_eval_questions(kb(), pool(), n, dIds_.get(), dPriority_.get(), det, evalCfg_, stream_);
+  launch_eval_questions(kbEval(), pool(), n, dIds_.get(), dPriority_.get(), det, evalCfg_, stream_);
   launch_select_question(kbQuiz(), pool(), n, dIds_.get(), dPriority_.get(), nullptr, W_, dRunLength_.get(), dGrand_.get(),
                          nullptr, 0, stream_);
   if (pPriorities) PQA_CU(cudaMemcpyAsync(pPriorities, dPriority_.get(), sizeof(double) * (size_t)(n * Q_), cudaMemcpyDeviceToHost, stream_));
@@ -1196,7 +1248,7 @@ PqaError *Engine::EvalQuestionsDetailedBatch(int64_t n, const int64_t *pQuizIds,
   dDetail_.ensure(3 * qk + nq, stream_); dPriority_.ensure(nq, stream_);
   PQA_CU(cudaMemsetAsync(dDetail_.get(), 0xFF, sizeof(double) * (3 * qk + nq), stream_));  // NaN where not evaluated
   EvalDetail det{dDetail_.get(), dDetail_.get() + qk, dDetail_.get() + 2 * qk, dDetail_.get() + 3 * qk};
-  launch_eval_questions(kb(), pool(), n, dIds_.get(), dPriority_.get(), det, evalCfg_, stream_);
+  launch_eval_questions(kbEval(), pool(), n, dIds_.get(), dPriority_.get(), det, evalCfg_, stream_);
   if (pW) PQA_CU(cudaMemcpyAsync(pW, det.W, sizeof(double) * qk, cudaMemcpyDeviceToHost, stream_));
   if (pH) PQA_CU(cudaMemcpyAsync(pH, det.H, sizeof(double) * qk, cudaMemcpyDeviceToHost, stream_));
   if (pV) PQA_CU(cudaMemcpyAsync(pV, det.V, sizeof(double) * qk, cudaMemcpyDeviceToHost, stream_));
@@ -1235,7 +1287,7 @@ PqaError *Engine::ResidentStep() {
   EvalDetail det{nullptr, nullptr, nullptr, nullptr};
   if (!evEvalStart_) { PQA_CU(cudaEventCreate(&evEvalStart_)); PQA_CU(cudaEventCreate(&evEvalStop_)); }
   PQA_CU(cudaEventRecord(evEvalStart_, stream_));
-  launch_eval_questions(kb(), pool(), residentN_, dResIds_.get(), dResPriority_.get(), det, evalCfg_, stream_);
+  launch_eval_questions(kbEval(), pool(), residentN_, dResIds_.get(), dResPriority_.get(), det, evalCfg_, stream_);
   PQA_CU(cudaEventRecord(evEvalStop_, stream_));
   launch_select_question(kbQuiz(), pool(), residentN_, dResIds_.get(), dResPriority_.get(), dResRandoms_.get(), W_,
                          dResRunLength_.get(), nullptr, dResQuestions_.get(), 0, stream_);
@@ -1295,7 +1347,7 @@ PqaError *Engine::TShardEvalW(int64_t n, const int64_t *pQuizIds) {
   dShardW_.ensure((size_t)shardWCount_, stream_);
   PQA_CU(cudaMemsetAsync(dShardW_.get(), 0, sizeof(double) * (size_t)shardWCount_, stream_));   // asked questions: +0
   PeerBufs out; out.n = 1; out.p[0] = dShardW_.get();
-  launch_eval_tshard_w(kb(), pool(), tFirst_, n, dIds_.get(), out, evalCfg_, stream_);
+  launch_eval_tshard_w(kbEval(), pool(), tFirst_, n, dIds_.get(), out, evalCfg_, stream_);
   PQA_CU(cudaGetLastError()); PQA_CU(cudaStreamSynchronize(stream_));
   return nullptr;
   PQA_CATCH_RETURN_ERR
@@ -1313,7 +1365,7 @@ PqaError *Engine::TShardEvalHVL(int64_t n, const int64_t *pQuizIds) {
   dShardHVL_.ensure((size_t)shardHVLCount_, stream_);
   PQA_CU(cudaMemsetAsync(dShardHVL_.get(), 0, sizeof(double) * (size_t)shardHVLCount_, stream_));
   PeerBufs in, out; in.n = 1; in.p[0] = dShardW_.get(); out.n = 1; out.p[0] = dShardHVL_.get();
-  launch_eval_tshard_hvl(kb(), pool(), tFirst_, n, dIds_.get(), in, out, evalCfg_, stream_);
+  launch_eval_tshard_hvl(kbEval(), pool(), tFirst_, n, dIds_.get(), in, out, evalCfg_, stream_);
   PQA_CU(cudaGetLastError()); PQA_CU(cudaStreamSynchronize(stream_));
   return nullptr;
   PQA_CATCH_RETURN_ERR
@@ -1507,10 +1559,15 @@ PqaError *Engine::P2PNextQuestionBegin(int64_t n, const int64_t *pQuizIds, const
       outHVL.p[r] = (double *)(p2pPeer_[r] + p2pOffHVL_ + (par * p2pRanks_ + p2pRank_) * p2pSzHVL_);
       inHVL.p[r] = (double *)(p2pInbox_ + p2pOffHVL_ + (par * p2pRanks_ + r) * p2pSzHVL_);
     }
+    const DeviceKB kbE = kbEval();       // brings the derived KB up to date before the first timed phase
+    if (!p2pEv_[0]) for (cudaEvent_t &e : p2pEv_) PQA_CU(cudaEventCreate(&e));
+    PQA_CU(cudaEventRecord(p2pEv_[0], stream_));
     if (!p2pExactOrder_ || p2pRanks_ == 1) {
-      launch_eval_tshard_w(kb(), pool(), tFirst_, n, dIds_.get(), outW, evalCfg_, stream_);   // partial W_k -> every inbox
+      launch_eval_tshard_w(kbE, pool(), tFirst_, n, dIds_.get(), outW, evalCfg_, stream_);   // partial W_k -> every inbox
+      PQA_CU(cudaEventRecord(p2pEv_[1], stream_));
       launch_p2p_barrier(flags, ++p2pEpoch_, kP2PTimeoutNs, stream_);
-      launch_eval_tshard_hvl(kb(), pool(), tFirst_, n, dIds_.get(), inW, outHVL, evalCfg_, stream_);
+      PQA_CU(cudaEventRecord(p2pEv_[2], stream_));
+      launch_eval_tshard_hvl(kbE, pool(), tFirst_, n, dIds_.get(), inW, outHVL, evalCfg_, stream_);
     } else {
       // Exact-order pipeline: the Kahan lanes travel shard 0 -> 1 -> ... -> N-1 tile by tile (tiles of consecutive
       // questions, about two waves of CTAs each); shard N-1 finishes the reference's own sum and publishes W_k to every
@@ -1533,7 +1590,8 @@ PqaError *Engine::P2PNextQuestionBegin(int64_t n, const int64_t *pQuizIds, const
       double *outState = last ? nullptr : (double *)(p2pPeer_[p2pRank_ + 1] + p2pOffState_ + par * p2pSzState_);
       PeerBufs wAll;                                        // the complete W_k lives in slot 0 of every inbox
       if (last) { wAll.n = p2pRanks_; for (int r = 0; r < p2pRanks_; r++) wAll.p[r] = (double *)(p2pPeer_[r] + p2pOffW_ + (par * p2pRanks_) * p2pSzW_); }
-      launch_eval_tshard_w(kb(), pool(), tFirst_, n, dIds_.get(), wAll, evalCfg_, stream_, inState, outState, &p1);
+      launch_eval_tshard_w(kbE, pool(), tFirst_, n, dIds_.get(), wAll, evalCfg_, stream_, inState, outState, &p1);
+      PQA_CU(cudaEventRecord(p2pEv_[1], stream_));
       PipeCtl p2;
       p2.tileQ = tileQ; p2.epoch = opEpoch; p2.timeoutNs = kP2PTimeoutNs; p2.errFlag = p1.errFlag;
       p2.waitFlags = (const uint64_t *)(p2pInbox_ + kP2POffWReady);
@@ -1545,9 +1603,12 @@ PqaError *Engine::P2PNextQuestionBegin(int64_t n, const int64_t *pQuizIds, const
         launch_p2p_wait(p2.waitFlags, (int)nTiles, opEpoch, p1.errFlag, kP2PTimeoutNs, stream_);
         p2.waitFlags = nullptr;
       }
-      launch_eval_tshard_hvl(kb(), pool(), tFirst_, n, dIds_.get(), inW, outHVL, evalCfg_, stream_, &p2);
+      PQA_CU(cudaEventRecord(p2pEv_[2], stream_));
+      launch_eval_tshard_hvl(kbE, pool(), tFirst_, n, dIds_.get(), inW, outHVL, evalCfg_, stream_, &p2);
     }
+    PQA_CU(cudaEventRecord(p2pEv_[3], stream_));
     launch_p2p_barrier(flags, ++p2pEpoch_, kP2PTimeoutNs, stream_);
+    PQA_CU(cudaEventRecord(p2pEv_[4], stream_));
     dShardPriority_.ensure((size_t)(n * Q_), stream_);
     priority = dShardPriority_.get();
     EvalDetail det{nullptr, nullptr, nullptr, nullptr};
@@ -1560,13 +1621,15 @@ PqaError *Engine::P2PNextQuestionBegin(int64_t n, const int64_t *pQuizIds, const
     for (int r = 0; r < p2pRanks_; r++)
       if (r != p2pRank_) cfg.mirror.p[cfg.mirror.n++] = (double *)(p2pPeer_[r] + p2pOffPri_ + par * p2pSzPri_);
     EvalDetail det{nullptr, nullptr, nullptr, nullptr};
-    launch_eval_questions(kb(), pool(), n, dIds_.get(), priority, det, cfg, stream_);   // own columns -> every inbox
+    launch_eval_questions(kbEval(), pool(), n, dIds_.get(), priority, det, cfg, stream_);   // own columns -> every inbox
     launch_p2p_barrier(flags, ++p2pEpoch_, kP2PTimeoutNs, stream_);
     p2pLastPriority_ = priority;
   }
   shardPriorityCount_ = n * Q_;
   launch_select_question(kbQuiz(), pool(), n, dIds_.get(), priority, dRandoms_.get(), W_, dRunLength_.get(), nullptr,
                          dQuestions_.get(), 1, stream_);
+  if (IsTargetSharded()) PQA_CU(cudaEventRecord(p2pEv_[5], stream_));
+  p2pPhasesValid_ = IsTargetSharded();
   PQA_CU(cudaMemcpyAsync(hQuestions_.get(), dQuestions_.get(), sizeof(int64_t) * (size_t)n, cudaMemcpyDeviceToHost, stream_));
   PQA_CU(cudaGetLastError());      // a kernel that failed to launch would leave the peers waiting at the barrier
   p2pPending_ = true;
@@ -1599,6 +1662,23 @@ PqaError *Engine::P2PNextQuestionEnd(int64_t n, const int64_t *pQuizIds, int64_t
   }
   nQuestionsAsked_.fetch_add(nAsked, std::memory_order_relaxed);
   return firstErr;
+}
+
+// Device time (ms) of the five stages of the most recent target-sharded P2PNextQuestion: phase 1 (W_k partials), the
+// exchange barrier, phase 2 (H/V/lack partials; with the exact-order pipeline it includes waiting for the tiles' W_k), the
+// second barrier, epilogue + selection. From CUDA events on this engine's stream; call after the End.
+PqaError *Engine::P2PLastPhaseMs(double *pMs5) {
+  std::lock_guard<std::mutex> lk(mu_); DeviceScope devScope(device_);
+  if (!p2pPhasesValid_ || p2pPending_) return MakeError(ErrCode::NotInitialized, PQA_FILE_LINE "no finished target-sharded P2PNextQuestion");
+  PQA_TRY
+  PQA_CU(cudaEventSynchronize(p2pEv_[5]));
+  for (int x = 0; x < 5; x++) {
+    float ms = 0.f;
+    PQA_CU(cudaEventElapsedTime(&ms, p2pEv_[x], p2pEv_[x + 1]));
+    pMs5[x] = (double)ms;
+  }
+  return nullptr;
+  PQA_CATCH_RETURN_ERR
 }
 
 PqaError *Engine::P2PRecordAnswerBegin(int64_t n, const int64_t *pQuizIds, const int64_t *pAnswers) {
@@ -1657,6 +1737,7 @@ PqaError *Engine::P2PRecordAnswerEnd() {
 PqaError *Engine::FillBinarySearchKB(double rounds) {
   std::lock_guard<std::mutex> lk(mu_); DeviceScope devScope(device_);
   PQA_TRY
+  MarkKBChanged();
   launch_fill_binary_search_kb(kb(), tFirst_, T_, initAmount_, rounds, stream_);
   PQA_CU(cudaGetLastError()); PQA_CU(cudaStreamSynchronize(stream_));
   return nullptr;

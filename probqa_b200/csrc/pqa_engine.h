@@ -243,6 +243,7 @@ class Engine {
   virtual PqaError *P2PNextQuestionEnd(int64_t n, const int64_t *pQuizIds, int64_t *pQuestions, void **ppErrors);
   virtual PqaError *P2PRecordAnswerBegin(int64_t n, const int64_t *pQuizIds, const int64_t *pAnswers);
   virtual PqaError *P2PRecordAnswerEnd();
+  virtual PqaError *P2PLastPhaseMs(double *pMs5);   // device time of the stages of the last target-sharded P2PNextQuestion
   virtual PqaError *P2PSetExactOrder(int32_t on);   // target shards: hand the Kahan lanes from shard to shard (W_k bit-exact)
   // closed-form synthetic KB of SURVEY.md 8d written on the device (this engine's shard of it)
   virtual PqaError *FillBinarySearchKB(double rounds);
@@ -282,6 +283,11 @@ class Engine {
   uint64_t NextRandom();
   DeviceKB kb() const;
   DeviceKB kbQuiz() const;
+  // kb() for an evaluation launch: first brings the derived KB (pqa_eval_staged.cu) up to date with sA / mD -- all of it
+  // after an upload / fill / load / resize / gap change, the touched questions after a Train / RecordQuizTarget.
+  DeviceKB kbEval();
+  void MarkKBChanged() { derAllDirty_ = true; derDirtyList_.clear(); }
+  void MarkQuestionsChanged(const std::vector<TrainOp> &ops);
   QuizPool pool() const;
   PqaError *ApplyTrain(const std::vector<TrainOp> &ops, const std::vector<int64_t> &targets,
                        const std::vector<double> &amounts);
@@ -316,6 +322,8 @@ class Engine {
   bool p2pConnected_ = false, p2pPending_ = false;
   uint64_t p2pEpoch_ = 0, p2pOps_ = 0;
   double *p2pLastPriority_ = nullptr;
+  cudaEvent_t p2pEv_[6] = {};
+  bool p2pPhasesValid_ = false;
   P2PFlags p2pFlags() const;
   PqaError *P2PCheckError();
   std::atomic<bool> maintenance_{false};                           // MaintenanceSwitch mode (MaintenanceSwitch.h): Regular / Maintenance
@@ -328,6 +336,13 @@ class Engine {
   EvalConfig evalCfg_;
 
   double *dSA_ = nullptr, *dMD_ = nullptr, *dVB_ = nullptr, *dLog2Tbl_ = nullptr;
+  // derived KB: allocated at the first evaluation, rebuilt lazily (kbEval)
+  double *dDerR_ = nullptr, *dDerL_ = nullptr;
+  size_t derCapR_ = 0, derCapL_ = 0;
+  bool derAllDirty_ = true;
+  std::vector<int64_t> derDirtyList_;      // local question indices touched since the last rebuild (unique)
+  std::vector<uint8_t> derDirtyMark_;
+  DevBuf<int64_t> dDerList_;
   // quiz pool
   int64_t quizCap_ = 0;
   double *dPriors_ = nullptr, *dLogPriors_ = nullptr;

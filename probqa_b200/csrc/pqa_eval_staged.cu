@@ -1,33 +1,39 @@
-// probqa_b200: the throughput question-evaluation kernel (sm_100a).
+// probqa_b200: the throughput question-evaluation kernels (sm_100a) and the derived KB they stream.
 //
-// Computes what CEEvalQsSubtaskConsider<SRDoubleNumber>::Run (CEEvalQsSubtaskConsider.cpp:41-217) computes for
+// They compute what CEEvalQsSubtaskConsider<SRDoubleNumber>::Run (CEEvalQsSubtaskConsider.cpp:41-217) computes for
 // every (quiz, question) pair of a batch of concurrent quizzes, restructured for the GPU:
 //
-//  * One CTA owns one question i and a tile of quizzes. The question's slab -- K rows of sA[i][k][.] and the row
-//    mD[i][.] -- is staged into shared memory with 1-D bulk-async copies (TMA engine, cp.async.bulk + mbarrier) and
-//    transformed in place once per CTA: invD = 1/mD, r[k][j] = sA*invD (the reference's per-target likelihood factor,
-//    :72-81), lr[k][j] = log2 r, id2[j] = invD^2 (the numerator of the "lack" term, :116-117). Every quiz of the tile
-//    then reuses the staged slab, so HBM/L2 sees the slab once per CTA instead of once per quiz.
+//  * Derived KB. Everything the reference derives from sA / mD per question before it touches a quiz -- invD = 1/mD,
+//    the likelihood factor r[k][j] = sA*invD (:72-81, same roundings), lr = log2 r, id2 = invD^2 (numerator of the
+//    "lack" term, :116-117) -- is kept in HBM next to the KB, in the order the kernels consume it: per question and
+//    per 4-target vector v, dR[v][k][lane] and dL[v][{lr_0..lr_{K-1}, id2}][lane] (lane = j % 4 = the reference's
+//    AVX lane). k_build_derived writes it; the engine rebuilds the questions a Train / RecordQuizTarget touched (and
+//    everything after an upload / resize / gap change) before the next evaluation.
+//  * One CTA owns one question i and a tile of quizzes. The question's derived slab goes to shared memory with two 1-D
+//    bulk-async copies (TMA engine, cp.async.bulk + mbarrier): R first, L behind it, so pass 1 starts while L is still in
+//    flight. No transform, no index arithmetic: a thread walks the slab with one running shared-memory pointer and
+//    immediate offsets. Every quiz of the tile reuses the staged slab.
 //  * The reference sums with a 4-lane AVX2 Kahan accumulator: target j goes to lane j%4, lanes advance in vector
-//    order (SRAccumVectDbl256.h:40-46). A GPU thread here owns KL of those 4 Kahan lanes of ONE quiz (KL = 4: one
-//    thread per quiz, 32 quizzes per warp, used for big batches; KL = 1: four threads per quiz, 8 quizzes per warp,
-//    used for small batches) and walks the 4-target vectors in order, so pass 1 reproduces the reference's normaliser
-//    W_k BIT FOR BIT (4-lane Kahan sum + PreciseSum, :81-88), hence its posteriors post = lik * (1/W_k) (:91,:97)
-//    and the differences post - prior of the velocity term (:119) bit for bit. This matters: for a question that
-//    is uninformative under the current posterior, sum (post - prior)^2 is pure rounding noise and the reference's
-//    priority depends on it. All threads of a warp read the same r/lr/id2 vector: shared-memory loads are 128-bit
-//    warp broadcasts. A thread carries KL*K independent dependency chains, which is what keeps the fp64 pipe busy.
-//  * Pass 2 needs log2(posterior) per element (:106): instead of the reference's Log2Hot (one IEEE divide + series)
-//    it uses log2(post) = lr[k][j] + log2(prior[j]) - log2(W_k) (two adds; log2 prior is kept per quiz), and falls
-//    back to the bit-faithful Log2Hot for the elements where that split would lose accuracy or where Log2Hot's edge
-//    semantics matter: post >= 0.5 (cancellation; also Log2Hot(1) = -6.56e-20 != 0) and post < 2^-1022 (Log2Hot(0) =
-//    -1023, subnormals). The lack term's divide is a MUFU seed + 3 DFMA reciprocal. The entropy / lack / velocity
-//    sums are plain sums (the reference uses Kahan sums): their terms are same-signed, so this costs ~1e-14
-//    relative. Net: W_k bit-exact, H_k / V_k / lack / priority within the tolerance stated in DESIGN.md and enforced
-//    by tests/test_gpu_parity.py; the fully bit-level path is k_eval_exact in pqa_kernels.cu.
-//  * When a slab does not fit in shared memory (large T) the targets are processed in chunks; pass 1 runs over all
-//    chunks (the Kahan state lives in registers across chunks), then pass 2 re-stages them (sA/mD are then read twice
-//    per CTA, from L2 when resident).
+//    order (SRAccumVectDbl256.h:40-46). A GPU thread owns KL of those 4 Kahan lanes of ONE quiz (KL = 2: two threads per
+//    quiz, 16 quizzes per warp -- the throughput shape) and walks the vectors in order, so pass 1 reproduces the
+//    reference's normaliser W_k BIT FOR BIT (4-lane Kahan sum + PreciseSum, :81-88), hence its posteriors
+//    post = lik * (1/W_k) (:91,:97) and the differences post - prior of the velocity term (:119) bit for bit. This
+//    matters: for a question that is uninformative under the current posterior, sum (post - prior)^2 is pure rounding
+//    noise and the reference's priority depends on it. All threads of a warp read the same slab vector: shared-memory
+//    loads are 128-bit warp broadcasts.
+//  * Pass 2 needs log2(posterior) per element (:106): instead of the reference's Log2Hot (one IEEE divide + series) it
+//    uses log2(post) = lr[k][j] + log2(prior[j]) - log2(W_k) (two adds; log2 prior is kept per quiz), and falls back to
+//    the bit-faithful Log2Hot for the elements where that split would lose accuracy or where Log2Hot's edge semantics
+//    matter: post >= 0.5 (cancellation; also Log2Hot(1) = -6.56e-20 != 0) and post < 2^-1022 (Log2Hot(0) = -1023,
+//    subnormals). The range test is two 3-input integer min / max trees over the high words of the step's posteriors.
+//    The lack term sum_k id2 / log2(post_k) of one target is ONE division: the K reciprocals are folded into a single
+//    fraction n/d (2(K-1) multiply-adds: n/d + 1/l = (n*l + d)/(d*l); all terms same-signed, |d| <= 1022^K) and d is
+//    inverted with a MUFU seed + one Newton step. The entropy / lack / velocity sums are plain sums (the reference uses
+//    Kahan sums): their terms are same-signed. Net: W_k bit-exact, H_k / V_k / lack / priority within the tolerance
+//    stated in DESIGN.md and enforced by tests/; the fully bit-level path is k_eval_exact in pqa_kernels.cu.
+//  * When a slab does not fit in shared memory (large T) the targets stream through a two-stage ring of chunks filled by
+//    bulk copies one chunk ahead of the arithmetic: pass 1 over all chunks (R only; the Kahan state lives in registers
+//    across chunks), then pass 2 (R and L).
 #include "pqa_kernels.cuh"
 #include "pqa_device.cuh"
 
@@ -39,6 +45,70 @@
 namespace pqa {
 void count_launch();
 
+// ---------------------------------------------------------------------------------------------------------
+// Derived KB builder: one CTA row per question (all questions, or the listed local question indices), threads over
+// targets. Gap / padding lanes: r = 0, id2 = 0 (the +0 of the reference's gap masks), lr = -inf (never used: a zero
+// posterior takes the Log2Hot path).
+template <int K>
+__global__ void __launch_bounds__(256) k_build_derived(const DeviceKB kb, const int64_t *__restrict__ list) {
+  const int64_t iLocal = list ? list[blockIdx.x] : (int64_t)blockIdx.x;
+  const int64_t Tp = kb.Tp, T = kb.T, nV = Tp >> 2;
+  const double *__restrict__ mD = kb.mD + iLocal * Tp;
+  const double *__restrict__ sA = kb.sA + iLocal * K * Tp;
+  double *oR = kb.dR + iLocal * nV * (K * 4);
+  double *oL = kb.dL + iLocal * nV * ((K + 1) * 4);
+  for (int64_t j = (int64_t)blockIdx.y * blockDim.x + threadIdx.x; j < Tp; j += (int64_t)gridDim.y * blockDim.x) {
+    const bool gap = j >= T || bit32(kb.tgaps, j);
+    const double invD = __ddiv_rn(1.0, mD[j]);                            // CEEvalQsSubtaskConsider.cpp:72-76
+    const int64_t v = j >> 2, l = j & 3;
+    oL[(v * (K + 1) + K) * 4 + l] = gap ? 0.0 : __dmul_rn(invD, invD);    // :116
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+      const double r = gap ? 0.0 : __dmul_rn(sA[k * Tp + j], invD);       // :81
+      oR[(v * K + k) * 4 + l] = r;
+      oL[(v * (K + 1) + k) * 4 + l] = log2(r);
+    }
+  }
+}
+
+#define PQA_K_SWITCH(K_, CALL)                                  \
+  switch (K_) {                                                 \
+    case 2: { constexpr int KK = 2; CALL; } break;              \
+    case 3: { constexpr int KK = 3; CALL; } break;              \
+    case 4: { constexpr int KK = 4; CALL; } break;              \
+    case 5: { constexpr int KK = 5; CALL; } break;              \
+    case 6: { constexpr int KK = 6; CALL; } break;              \
+    case 7: { constexpr int KK = 7; CALL; } break;              \
+    case 8: { constexpr int KK = 8; CALL; } break;              \
+    default: throw std::runtime_error("probqa_b200: the staged evaluation supports 2..8 answer options"); \
+  }
+
+void derived_kb_doubles(const DeviceKB &kb, size_t *nR, size_t *nL) {
+  const size_t nV = (size_t)(kb.Tp >> 2);
+  *nR = (size_t)kb.qCount * nV * (size_t)(kb.K * 4);
+  *nL = (size_t)kb.qCount * nV * (size_t)((kb.K + 1) * 4);
+}
+void launch_build_derived(const DeviceKB &kb, const int64_t *dList, int64_t nList, cudaStream_t st) {
+  if (kb.K > 8) return;    // the exact kernel serves K > 8 and reads sA / mD directly
+  const int64_t rows = dList ? nList : kb.qCount;
+  if (rows <= 0) return;
+  int64_t gy = (kb.Tp + 255) / 256;
+  if (gy > 64) gy = 64;
+  for (int64_t r0 = 0; r0 < rows; r0 += 32768) {
+    const int64_t nr = rows - r0 < 32768 ? rows - r0 : 32768;
+    DeviceKB part = kb;
+    const int64_t *lst = dList ? dList + r0 : nullptr;
+    if (!dList) {   // all questions: shift the views instead of passing a list
+      part.sA += r0 * kb.K * kb.Tp; part.mD += r0 * kb.Tp;
+      part.dR += r0 * (kb.Tp >> 2) * (kb.K * 4); part.dL += r0 * (kb.Tp >> 2) * ((kb.K + 1) * 4);
+    }
+    dim3 grid((unsigned)nr, (unsigned)gy);
+    PQA_K_SWITCH(kb.K, (k_build_derived<KK><<<grid, 256, 0, st>>>(part, lst)))
+    count_launch();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 struct StagedParams {
   DeviceKB kb;
   QuizPool qp;
@@ -46,7 +116,7 @@ struct StagedParams {
   const int64_t *slots;
   double *priority;
   EvalDetail det;
-  int64_t Jc;             // targets per shared-memory chunk (multiple of 4)
+  int64_t Vc;             // 4-target vectors per shared-memory chunk
   int64_t nChunks;
   int64_t quizzesPerCta;  // == quizzes per pass of one CTA when nChunks > 1
   PeerBufs mirror;        // EvalConfig::mirror
@@ -87,63 +157,40 @@ template <int KL> __device__ __forceinline__ VecD<KL> ldg_vec(const double *p) {
   return o;
 }
 
-template <int K, int THREADS>
-__device__ __forceinline__ void stage_chunk(const StagedParams &P, int64_t iLocal, int64_t c, bool withLog, double *sR,
-                                            double *sLR, double *sID2, uint64_t *bar, uint32_t &parity) {
-  const int64_t Jc = P.Jc, Tp = P.kb.Tp, T = P.kb.T;
-  const int64_t j0 = c * Jc;
-  const int64_t cnt = (Tp - j0 < Jc) ? (Tp - j0) : Jc;  // multiple of 4 doubles = 32 bytes
-  if (threadIdx.x == 0) {
-    fence_proxy_async_smem();  // earlier generic-proxy accesses of the buffers (all threads, ordered by the CTA
-                               // barrier before this call) precede the async-proxy writes below
-    const uint32_t bytes = (uint32_t)(cnt * sizeof(double));
-    mbar_arrive_expect_tx(bar, bytes * (K + 1));
-#pragma unroll
-    for (int k = 0; k < K; k++) bulk_g2s(sR + k * Jc, P.kb.sA + (iLocal * K + k) * Tp + j0, bytes, bar);
-    bulk_g2s(sID2, P.kb.mD + iLocal * Tp + j0, bytes, bar);
-  }
-  mbar_wait(bar, parity);
-  parity ^= 1u;
-  for (int64_t j = threadIdx.x; j < cnt; j += THREADS) {
-    const int64_t gj = j0 + j;
-    const bool gap = gj >= T || bit32(P.kb.tgaps, gj);
-    const double invD = __ddiv_rn(1.0, sID2[j]);                         // :72-76
-    sID2[j] = gap ? 0.0 : __dmul_rn(invD, invD);
-#pragma unroll
-    for (int k = 0; k < K; k++) {
-      const double r = gap ? 0.0 : __dmul_rn(sR[k * Jc + j], invD);     // :81
-      sR[k * Jc + j] = r;
-      if (withLog) sLR[k * Jc + j] = log2(r);
-    }
-  }
-  __syncthreads();
+// Thread 0: bulk copies of chunk c of question iLocal's derived slab into one stage (R, and L when pass 2 needs it),
+// completing on `bar`. Sizes and addresses are multiples of 32 bytes.
+template <int K>
+__device__ __forceinline__ void issue_chunk(const StagedParams &P, int64_t iLocal, int64_t c, bool withL, double *sR,
+                                            double *sL, uint64_t *bar) {
+  const int64_t nV = P.kb.Tp >> 2;
+  const int64_t v0 = c * P.Vc;
+  const int64_t nv = (nV - v0 < P.Vc) ? (nV - v0) : P.Vc;
+  const uint32_t bytesR = (uint32_t)(nv * (K * 32)), bytesL = (uint32_t)(nv * ((K + 1) * 32));
+  mbar_arrive_expect_tx(bar, withL ? bytesR + bytesL : bytesR);
+  bulk_g2s(sR, P.kb.dR + (iLocal * nV + v0) * (K * 4), bytesR, bar);
+  if (withL) bulk_g2s(sL, P.kb.dL + (iLocal * nV + v0) * ((K + 1) * 4), bytesL, bar);
 }
 
-// Pass 1 over one chunk: thread owns Kahan lanes l0 .. l0+KL-1 of its quiz. Padding / gap lanes hold prior = +0 and
-// r = 0, which add +0 exactly as the reference's masked lanes do.
+// Pass 1 over one chunk: the thread owns Kahan lanes l0 .. l0+KL-1 of its quiz. Padding / gap lanes hold prior = +0 and
+// r = 0, which add +0 exactly as the reference's masked lanes do. sR: the chunk's [v][k][lane]; prc: the quiz' priors
+// at (first target of the chunk) + l0. The priors come from L2 (every quiz has its own row) one vector ahead; the read
+// past the chunk's last vector stays inside the quiz pool (rows are contiguous, the pool has a vector of slack).
 template <int K, int KL>
-__device__ __forceinline__ void pass1_chunk(const double *__restrict__ sR, int64_t Jc, int nVects, int64_t j0,
-                                            const double *__restrict__ pr, int l0, Kahan (&kw)[KL][K]) {
-  const double *prc = pr + j0 + l0;
-  // the priors come from L2 (every quiz has its own row: no reuse in L1) and are fetched PF vectors ahead. Measured at
-  // 1000x5x1000, B=256: PF = 1 1.50e8 q-evals/s, PF = 3 1.45e8 (and -18 % on the chunked 4-warp shape): deeper prefetch
-  // costs more than the long-scoreboard stalls it removes.
-  constexpr int PF = 1;
-  VecD<KL> pq[PF];
-#pragma unroll
-  for (int d = 0; d < PF; d++) pq[d] = ldg_vec<KL>(prc + 4 * (d < nVects ? d : 0));
+__device__ __forceinline__ void pass1_chunk(const double *__restrict__ sR, int nVects, const double *__restrict__ prc,
+                                            int l0, Kahan (&kw)[KL][K]) {
+  const double *rp = sR + l0;
+  VecD<KL> pn = ldg_vec<KL>(prc);
+#pragma unroll 2
   for (int v = 0; v < nVects; v++) {
-    const VecD<KL> p = pq[0];
-#pragma unroll
-    for (int d = 0; d + 1 < PF; d++) pq[d] = pq[d + 1];
-    if (v + PF < nVects) pq[PF - 1] = ldg_vec<KL>(prc + 4 * (v + PF));
-    const int j = 4 * v + l0;
+    const VecD<KL> p = pn;
+    pn = ldg_vec<KL>(prc + 4 * (v + 1));
 #pragma unroll
     for (int k = 0; k < K; k++) {
-      const VecD<KL> r = lds_vec<KL>(sR + k * Jc + j);
+      const VecD<KL> r = lds_vec<KL>(rp + k * 4);
 #pragma unroll
       for (int e = 0; e < KL; e++) kw[e][k].add(__dmul_rn(r.v[e], p.v[e]));   // :81-86
     }
+    rp += 4 * K;
   }
 }
 
@@ -156,68 +203,147 @@ __device__ __noinline__ double slow_log2(double post, const double *__restrict__
 }
 
 // high word of post in [0x00100000, 0x3FE00000) <=> 2^-1022 <= post < 0.5 (positive, normal): the split log is accurate
-__device__ __forceinline__ unsigned fast_range_key(double post) { return (unsigned)__double2hiint(post) - 0x00100000u; }
-constexpr unsigned kFastRangeLimit = 0x3FE00000u - 0x00100000u;
+constexpr int kFastLo = 0x00100000, kFastHi = 0x3FE00000;
+__device__ __forceinline__ bool in_fast_range(double post) {
+  return (unsigned)__double2hiint(post) - (unsigned)kFastLo < (unsigned)(kFastHi - kFastLo);
+}
+template <int N> __device__ __forceinline__ int max_tree(const int (&h)[N]) {
+  if constexpr (N == 1) return h[0];
+  else if constexpr (N == 2) return max(h[0], h[1]);
+  else {
+    constexpr int M = (N + 2) / 3;
+    int g[M];
+#pragma unroll
+    for (int i = 0; i < M; i++)
+      g[i] = (3 * i + 2 < N) ? __vimax3_s32(h[3 * i], h[(3 * i + 1) % N], h[(3 * i + 2) % N])
+                             : (3 * i + 1 < N) ? max(h[3 * i], h[(3 * i + 1) % N]) : h[3 * i];
+    return max_tree<M>(g);
+  }
+}
+template <int N> __device__ __forceinline__ int min_tree(const int (&h)[N]) {
+  if constexpr (N == 1) return h[0];
+  else if constexpr (N == 2) return min(h[0], h[1]);
+  else {
+    constexpr int M = (N + 2) / 3;
+    int g[M];
+#pragma unroll
+    for (int i = 0; i < M; i++)
+      g[i] = (3 * i + 2 < N) ? __vimin3_s32(h[3 * i], h[(3 * i + 1) % N], h[(3 * i + 2) % N])
+                             : (3 * i + 1 < N) ? min(h[3 * i], h[(3 * i + 1) % N]) : h[3 * i];
+    return min_tree<M>(g);
+  }
+}
 
-template <int K, int KL>
-__device__ __forceinline__ void pass2_chunk(const double *__restrict__ sR, const double *__restrict__ sLR,
-                                            const double *__restrict__ sID2, int64_t Jc, int nVects, int64_t j0,
-                                            const double *__restrict__ pr, const double *__restrict__ lpr,
-                                            const double *__restrict__ tbl, int l0, const double (&iW)[K],
-                                            const double (&lW)[K], double (&H)[K], double (&V)[K], double (&L)[KL]) {
-  const double *prc = pr + j0 + l0, *lprc = lpr + j0 + l0;
-  VecD<KL> pn = ldg_vec<KL>(prc), lpn = ldg_vec<KL>(lprc);
-  for (int v = 0; v < nVects; v++) {
-    const VecD<KL> p = pn, lp = lpn;
-    if (v + 1 < nVects) { pn = ldg_vec<KL>(prc + 4 * (v + 1)); lpn = ldg_vec<KL>(lprc + 4 * (v + 1)); }
-    const int j = 4 * v + l0;
-    const VecD<KL> id2 = lds_vec<KL>(sID2 + j);
-    // posteriors of the K*KL elements of this vector step, and whether all of them are in the fast range
-    double post[K][KL];
-    unsigned worst = 0;
+// One vector step of pass 2 with every element classified on its own: the split logarithm where the posterior is in the
+// fast range, the reference's Log2Hot (and an IEEE reciprocal) elsewhere. Only for the rare steps that hold an element
+// outside the fast range.
+template <int K, int KL, bool WITH_V>
+__device__ __forceinline__ void pass2_careful_step(const double *__restrict__ rp, const double *__restrict__ lp_s,
+                                                   const double *__restrict__ prv, const double *__restrict__ lprv,
+                                                   const double *__restrict__ tbl, const double (&iW)[K], const double (&lW)[K],
+                                                   double (&H)[K], double (&V)[K], double (&L)[KL]) {
+  const VecD<KL> p = ldg_vec<KL>(prv), lp = ldg_vec<KL>(lprv);
+  const VecD<KL> id2 = lds_vec<KL>(lp_s + K * 4);
 #pragma unroll
-    for (int k = 0; k < K; k++) {
-      const VecD<KL> r = lds_vec<KL>(sR + k * Jc + j);
+  for (int k = 0; k < K; k++) {
+    const VecD<KL> r = lds_vec<KL>(rp + k * 4), lr = lds_vec<KL>(lp_s + k * 4);
 #pragma unroll
-      for (int e = 0; e < KL; e++) {
-        post[k][e] = __dmul_rn(__dmul_rn(r.v[e], p.v[e]), iW[k]);       // :81-82, :97
-        worst = max(worst, fast_range_key(post[k][e]));
+    for (int e = 0; e < KL; e++) {
+      const double post = __dmul_rn(__dmul_rn(r.v[e], p.v[e]), iW[k]);  // :81-82, :97
+      double l2, rl2;
+      if (in_fast_range(post)) {
+        l2 = __dsub_rn(__dadd_rn(lr.v[e], lp.v[e]), lW[k]);
+        rl2 = fast_rcp(l2);
+      } else {
+        l2 = slow_log2(post, tbl, &rl2);
+      }
+      H[k] = __fma_rn(post, l2, H[k]);
+      L[e] = __fma_rn(id2.v[e], rl2, L[e]);
+      if (WITH_V) {
+        const double d = __dsub_rn(post, p.v[e]);
+        V[k] = __fma_rn(d, d, V[k]);
       }
     }
-    if (worst < kFastRangeLimit) {
-      // common case: no masks, no selects
+  }
+}
+
+// Pass 2 over one chunk. sR / sL: the chunk's [v][k][lane] and [v][{lr_k, id2}][lane]; prc / lprc as in pass 1.
+// A step whose K*KL posteriors are all in the fast range runs the branch-free common path. The others (on a trained KB
+// typically one step per quiz and question: the target the question is "about") are only noted -- up to six step numbers
+// packed into one 64-bit register -- and evaluated when the list is full or the chunk ends: a thread with an exception
+// idles for one step instead of holding its warp for the length of the careful path, and the careful steps of a warp's
+// quizzes run side by side.
+constexpr int kDeferBits = 10, kMaxDeferred = 6;     // chunks hold fewer than 2^10 vectors (slab_geometry)
+template <int K, int KL>
+__device__ __forceinline__ void pass2_chunk(const double *__restrict__ sR, const double *__restrict__ sL, int nVects,
+                                            const double *__restrict__ prc, const double *__restrict__ lprc,
+                                            const double *__restrict__ tbl, int l0, const double (&iW)[K],
+                                            const double (&lW)[K], double (&H)[K], double (&V)[K], double (&L)[KL]) {
+  const double *rp = sR + l0, *lp_s = sL + l0;
+  int v = 0;
+  for (;;) {
+    unsigned long long deferred = 0ull;
+    int nDeferred = 0;
+    VecD<KL> pn = ldg_vec<KL>(prc + 4 * v), lpn = ldg_vec<KL>(lprc + 4 * v);
+#pragma unroll 1
+    for (; v < nVects; v++) {
+      const VecD<KL> p = pn, lp = lpn;
+      pn = ldg_vec<KL>(prc + 4 * (v + 1)); lpn = ldg_vec<KL>(lprc + 4 * (v + 1));
+      // Everything that does not depend on the range test comes before it, so that the test's latency is covered: the
+      // posteriors, a = log2 r + log2 prior, and the velocity term (the same on both paths).
+      double post[K][KL], a[K][KL];
+      int hi[K * KL];
 #pragma unroll
       for (int k = 0; k < K; k++) {
-        const VecD<KL> lr = lds_vec<KL>(sLR + k * Jc + j);
+        const VecD<KL> r = lds_vec<KL>(rp + k * 4);
+        const VecD<KL> lr = lds_vec<KL>(lp_s + k * 4);
 #pragma unroll
         for (int e = 0; e < KL; e++) {
-          const double l2 = __dsub_rn(__dadd_rn(lr.v[e], lp.v[e]), lW[k]);
-          H[k] = __fma_rn(post[k][e], l2, H[k]);                        // :113-114
-          L[e] = __fma_rn(id2.v[e], fast_rcp46(l2), L[e]);              // :116-117 (id2 = 0 on gap / padding lanes)
+          post[k][e] = __dmul_rn(__dmul_rn(r.v[e], p.v[e]), iW[k]);     // :81-82, :97
+          hi[k * KL + e] = __double2hiint(post[k][e]);
+          a[k][e] = __dadd_rn(lr.v[e], lp.v[e]);
           const double d = __dsub_rn(post[k][e], p.v[e]);               // :119
           V[k] = __fma_rn(d, d, V[k]);                                  // :126-127
         }
       }
-    } else {
+      const VecD<KL> id2 = lds_vec<KL>(lp_s + K * 4);
+      rp += 4 * K; lp_s += 4 * (K + 1);
+#if defined(PQA_EXP_NOCHECK)
+      const bool allFast = true;
+#else
+      const bool allFast = (min_tree<K * KL>(hi) >= kFastLo) & (max_tree<K * KL>(hi) < kFastHi);   // one branch, not two
+#endif
+      if (allFast) {
+        // common case: no masks, no selects
+        double l2[K][KL];
 #pragma unroll
-      for (int k = 0; k < K; k++) {
-        const VecD<KL> lr = lds_vec<KL>(sLR + k * Jc + j);
+        for (int k = 0; k < K; k++) {
+#pragma unroll
+          for (int e = 0; e < KL; e++) {
+            l2[k][e] = __dsub_rn(a[k][e], lW[k]);
+            H[k] = __fma_rn(post[k][e], l2[k][e], H[k]);                // :113-114
+          }
+        }
 #pragma unroll
         for (int e = 0; e < KL; e++) {
-          double l2, rl2;
-          if (fast_range_key(post[k][e]) < kFastRangeLimit) {
-            l2 = __dsub_rn(__dadd_rn(lr.v[e], lp.v[e]), lW[k]);
-            rl2 = fast_rcp(l2);
-          } else {
-            l2 = slow_log2(post[k][e], tbl, &rl2);
-          }
-          H[k] = __fma_rn(post[k][e], l2, H[k]);
-          L[e] = __fma_rn(id2.v[e], rl2, L[e]);
-          const double d = __dsub_rn(post[k][e], p.v[e]);
-          V[k] = __fma_rn(d, d, V[k]);
+          // sum_k 1/l2[k] as one fraction nn/dd (:116-117 divides K times)
+          double nn = __dadd_rn(l2[0][e], l2[1][e]), dd = __dmul_rn(l2[0][e], l2[1][e]);
+#pragma unroll
+          for (int k = 2; k < K; k++) { nn = __fma_rn(nn, l2[k][e], dd); dd = __dmul_rn(dd, l2[k][e]); }
+          L[e] = __fma_rn(id2.v[e], __dmul_rn(nn, fast_rcp(dd)), L[e]);
         }
+      } else {
+        deferred = (deferred << kDeferBits) | (unsigned)v;
+        if (++nDeferred == kMaxDeferred) { v++; break; }
       }
     }
+#pragma unroll 1
+    for (; nDeferred > 0; nDeferred--, deferred >>= kDeferBits) {
+      const int dv = (int)(deferred & ((1u << kDeferBits) - 1u));
+      pass2_careful_step<K, KL, false>(sR + l0 + dv * (4 * K), sL + l0 + dv * (4 * (K + 1)), prc + 4 * dv, lprc + 4 * dv, tbl,
+                                       iW, lW, H, V, L);
+    }
+    if (v >= nVects) break;
   }
 }
 
@@ -289,6 +415,37 @@ __device__ __forceinline__ void finish_pass2(const StagedParams &P, int64_t i, i
   write_priority<K>(P, i, b, W, H, V, L);
 }
 
+constexpr int kStages = 2;   // ring depth of the streamed (large T) shape
+
+// Two-level summation for the streamed shape. The entropy / velocity / lack sums of pass 2 are plain sums; over tens of
+// thousands of (often identical: a trained KB has long runs of equal cells) same-signed terms a single accumulator drifts
+// by a fraction of an ulp of the running total per term. Each thread therefore sums one chunk in registers and adds that
+// to totals kept in shared memory ([value][thread], conflict-free), so that the per-term rounding is relative to a chunk's
+// sum, not to the whole row's.
+template <int K, int KL, int THREADS>
+__device__ __forceinline__ void flush_chunk_sums(double *sTotals, double (&H)[K], double (&V)[K], double (&L)[KL]) {
+  double *o = sTotals + threadIdx.x;
+#pragma unroll
+  for (int k = 0; k < K; k++) {
+    o[k * THREADS] = __dadd_rn(o[k * THREADS], H[k]); H[k] = 0.0;
+    o[(K + k) * THREADS] = __dadd_rn(o[(K + k) * THREADS], V[k]); V[k] = 0.0;
+  }
+#pragma unroll
+  for (int e = 0; e < KL; e++) { o[(2 * K + e) * THREADS] = __dadd_rn(o[(2 * K + e) * THREADS], L[e]); L[e] = 0.0; }
+}
+template <int K, int KL, int THREADS>
+__device__ __forceinline__ void load_chunk_sums(const double *sTotals, double (&H)[K], double (&V)[K], double (&L)[KL]) {
+  const double *o = sTotals + threadIdx.x;
+#pragma unroll
+  for (int k = 0; k < K; k++) { H[k] = o[k * THREADS]; V[k] = o[(K + k) * THREADS]; }
+#pragma unroll
+  for (int e = 0; e < KL; e++) L[e] = o[(2 * K + e) * THREADS];
+}
+template <int K, int KL, int THREADS> __device__ __forceinline__ void zero_chunk_sums(double *sTotals) {
+#pragma unroll
+  for (int x = 0; x < 2 * K + KL; x++) sTotals[x * THREADS + threadIdx.x] = 0.0;
+}
+
 // WARPS = 8: 256 threads, two CTAs per SM (slab budget 100 KB); WARPS = 4: 128 threads, four CTAs per SM (50 KB), used
 // when the batch has at most 64 quizzes so that no warp of a CTA pass is idle.
 template <int K, int KL, int WARPS>
@@ -297,12 +454,9 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 4 ? 4 : 2) k_eval_staged(
   constexpr int LPQ = 4 / KL;              // threads per quiz
   constexpr int QPW = 32 / LPQ;            // quizzes per warp
   extern __shared__ __align__(128) unsigned char smRaw[];
-  __shared__ uint64_t bar;
-  double *sR = (double *)smRaw;        // [K][Jc]  sA, then r = sA/mD
-  double *sLR = sR + K * P.Jc;         // [K][Jc]  log2 r
-  double *sID2 = sLR + K * P.Jc;       // [Jc]     mD, then 1/mD^2
+  __shared__ uint64_t bars[kStages];
 
-  const int64_t iLocal = blockIdx.x, i = P.kb.qFirst + iLocal, Q = P.kb.Q, Tp = P.kb.Tp;
+  const int64_t iLocal = blockIdx.x, i = P.kb.qFirst + iLocal, Q = P.kb.Q, Tp = P.kb.Tp, nV = Tp >> 2;
   const int64_t tileFirst = (int64_t)blockIdx.y * P.quizzesPerCta;
   const int64_t tileLimit = (tileFirst + P.quizzesPerCta < P.n) ? tileFirst + P.quizzesPerCta : P.n;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -313,14 +467,26 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 4 ? 4 : 2) k_eval_staged(
     for (int64_t b = tileFirst + threadIdx.x; b < tileLimit; b += THREADS) store_priority(P, b * Q + i, qnan);
     return;
   }
-  if (threadIdx.x == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < kStages; s++) mbar_init(&bars[s], 1);
+    mbar_fence_init();
+  }
   __syncthreads();
-  uint32_t parity = 0;
   const double *__restrict__ tbl = P.kb.log2tbl;
 
   if (P.nChunks == 1) {
-    stage_chunk<K, THREADS>(P, iLocal, 0, true, sR, sLR, sID2, &bar, parity);
-    const int nVects = (int)(Tp >> 2);
+    // resident shape: the whole slab stays in shared memory for every quiz group of the tile; R completes on bars[0],
+    // L (needed by pass 2 only) on bars[1]
+    double *sR = (double *)smRaw, *sL = sR + nV * (K * 4);
+    if (threadIdx.x == 0) {
+      const uint32_t bytesR = (uint32_t)(nV * (K * 32)), bytesL = (uint32_t)(nV * ((K + 1) * 32));
+      mbar_arrive_expect_tx(&bars[0], bytesR);
+      bulk_g2s(sR, P.kb.dR + iLocal * nV * (K * 4), bytesR, &bars[0]);
+      mbar_arrive_expect_tx(&bars[1], bytesL);
+      bulk_g2s(sL, P.kb.dL + iLocal * nV * ((K + 1) * 4), bytesL, &bars[1]);
+    }
+    const int nVects = (int)nV;
     for (int64_t g0 = tileFirst + (int64_t)warp * QPW; g0 < tileLimit; g0 += (int64_t)WARPS * QPW) {
       const int64_t b = g0 + qw;
       bool live = b < tileLimit;
@@ -330,7 +496,7 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 4 ? 4 : 2) k_eval_staged(
         live = false;
       }
       if (!live) continue;             // all threads of this quiz leave together
-      const double *pr = P.qp.priors + slot * Tp, *lpr = P.qp.logPriors + slot * Tp;
+      const double *pr = P.qp.priors + slot * Tp + l0, *lpr = P.qp.logPriors + slot * Tp + l0;
       double W[K], iW[K], lW[K], H[K], V[K], L[KL];
       {
         Kahan kw[KL][K];
@@ -338,18 +504,31 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 4 ? 4 : 2) k_eval_staged(
         for (int e = 0; e < KL; e++)
 #pragma unroll
           for (int k = 0; k < K; k++) kw[e][k].init();
-        pass1_chunk<K, KL>(sR, P.Jc, nVects, 0, pr, l0, kw);
+        mbar_wait(&bars[0], 0);
+#if !defined(PQA_EXP_NOPASS1)
+        pass1_chunk<K, KL>(sR, nVects, pr, l0, kw);
+#else
+        for (int e = 0; e < KL; e++) for (int k = 0; k < K; k++) kw[e][k].init(0.05);
+#endif
         finish_pass1<K, KL>(kw, W, iW, lW);
       }
 #pragma unroll
       for (int k = 0; k < K; k++) { H[k] = 0.0; V[k] = 0.0; }
 #pragma unroll
       for (int e = 0; e < KL; e++) L[e] = 0.0;
-      pass2_chunk<K, KL>(sR, sLR, sID2, P.Jc, nVects, 0, pr, lpr, tbl, l0, iW, lW, H, V, L);
+      mbar_wait(&bars[1], 0);
+#if !defined(PQA_EXP_NOPASS2)
+      pass2_chunk<K, KL>(sR, sL, nVects, pr, lpr, tbl, l0, iW, lW, H, V, L);
+#endif
       finish_pass2<K, KL>(P, i, b, l0, W, H, V, L);
     }
   } else {
-    // chunked targets: this thread keeps its quiz for the whole question
+    // streamed shape: this thread keeps its quiz for the whole question; 2 * nChunks ring items (pass 1: R chunks,
+    // pass 2: R + L chunks), item g lives in stage g % kStages and is issued when item g - kStages has been consumed
+    const int64_t stageDoubles = P.Vc * ((2 * K + 1) * 4);
+    double *const ring = (double *)smRaw;
+    double *const sTotals = ring + kStages * stageDoubles;     // [2K + KL][THREADS] (flush_chunk_sums)
+    zero_chunk_sums<K, KL, THREADS>(sTotals);
     const int64_t b = tileFirst + (int64_t)warp * QPW + qw;
     bool live = b < tileLimit;
     const int64_t slot = P.slots[live ? b : tileLimit - 1];
@@ -357,61 +536,82 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 4 ? 4 : 2) k_eval_staged(
       if (l0 == 0) store_priority(P, b * Q + i, qnan);
       live = false;
     }
-    const double *pr = P.qp.priors + slot * Tp, *lpr = P.qp.logPriors + slot * Tp;
-    double W[K], iW[K], lW[K], H[K], V[K], L[KL];
-    Kahan kw[KL][K];
-#pragma unroll
-    for (int k = 0; k < K; k++) { H[k] = 0.0; V[k] = 0.0; W[k] = 0.0; iW[k] = 0.0; lW[k] = 0.0; }
-#pragma unroll
-    for (int e = 0; e < KL; e++) {
-      L[e] = 0.0;
-#pragma unroll
-      for (int k = 0; k < K; k++) kw[e][k].init();
+    const double *pr = P.qp.priors + slot * Tp + l0, *lpr = P.qp.logPriors + slot * Tp + l0;
+    const int64_t total = 2 * P.nChunks;
+    if (threadIdx.x == 0) {
+      for (int64_t g = 0; g < kStages && g < total; g++) {
+        double *sR = ring + (g % kStages) * stageDoubles;
+        issue_chunk<K>(P, iLocal, g % P.nChunks, g >= P.nChunks, sR, sR + P.Vc * (K * 4), &bars[g % kStages]);
+      }
     }
-    for (int64_t c = 0; c < P.nChunks; c++) {
-      stage_chunk<K, THREADS>(P, iLocal, c, false, sR, sLR, sID2, &bar, parity);
-      const int64_t j0 = c * P.Jc;
-      const int nVects = (int)(((Tp - j0 < P.Jc) ? (Tp - j0) : P.Jc) >> 2);
-      if (live) pass1_chunk<K, KL>(sR, P.Jc, nVects, j0, pr, l0, kw);
-      __syncthreads();  // everyone is done with the buffers before the next stage overwrites them
+    // consumes ring item g (its stage is free afterwards) and issues item g + kStages into the same stage
+    auto next_item = [&](int64_t g) {
+      __syncthreads();  // everyone is done with the stage before the next copy overwrites it
+      if (threadIdx.x == 0 && g + kStages < total) {
+        fence_proxy_async_smem();
+        const int64_t gn = g + kStages;
+        double *dR = ring + (g % kStages) * stageDoubles;
+        issue_chunk<K>(P, iLocal, gn % P.nChunks, gn >= P.nChunks, dR, dR + P.Vc * (K * 4), &bars[g % kStages]);
+      }
+    };
+    double W[K], iW[K], lW[K];
+#pragma unroll
+    for (int k = 0; k < K; k++) { W[k] = 0.0; iW[k] = 0.0; lW[k] = 0.0; }
+    {
+      Kahan kw[KL][K];
+#pragma unroll
+      for (int e = 0; e < KL; e++)
+#pragma unroll
+        for (int k = 0; k < K; k++) kw[e][k].init();
+      for (int64_t g = 0; g < P.nChunks; g++) {
+        const double *sR = ring + (g % kStages) * stageDoubles;
+        const int64_t v0 = g * P.Vc;
+        const int nVects = (int)((nV - v0 < P.Vc) ? (nV - v0) : P.Vc);
+        mbar_wait(&bars[g % kStages], (uint32_t)((g / kStages) & 1));
+        if (live) pass1_chunk<K, KL>(sR, nVects, pr + 4 * v0, l0, kw);
+        next_item(g);
+      }
+      if (live) finish_pass1<K, KL>(kw, W, iW, lW);
     }
-    if (live) finish_pass1<K, KL>(kw, W, iW, lW);
-    for (int64_t c = 0; c < P.nChunks; c++) {
-      stage_chunk<K, THREADS>(P, iLocal, c, true, sR, sLR, sID2, &bar, parity);
-      const int64_t j0 = c * P.Jc;
-      const int nVects = (int)(((Tp - j0 < P.Jc) ? (Tp - j0) : P.Jc) >> 2);
-      if (live) pass2_chunk<K, KL>(sR, sLR, sID2, P.Jc, nVects, j0, pr, lpr, tbl, l0, iW, lW, H, V, L);
-      __syncthreads();
+    double H[K], V[K], L[KL];
+#pragma unroll
+    for (int k = 0; k < K; k++) { H[k] = 0.0; V[k] = 0.0; }
+#pragma unroll
+    for (int e = 0; e < KL; e++) L[e] = 0.0;
+    for (int64_t g = P.nChunks; g < total; g++) {
+      const double *sR = ring + (g % kStages) * stageDoubles, *sL = sR + P.Vc * (K * 4);
+      const int64_t v0 = (g - P.nChunks) * P.Vc;
+      const int nVects = (int)((nV - v0 < P.Vc) ? (nV - v0) : P.Vc);
+      mbar_wait(&bars[g % kStages], (uint32_t)((g / kStages) & 1));
+      if (live) {
+        pass2_chunk<K, KL>(sR, sL, nVects, pr + 4 * v0, lpr + 4 * v0, tbl, l0, iW, lW, H, V, L);
+        flush_chunk_sums<K, KL, THREADS>(sTotals, H, V, L);
+      }
+      next_item(g);
     }
+    if (live) load_chunk_sums<K, KL, THREADS>(sTotals, H, V, L);
     if (live) finish_pass2<K, KL>(P, i, b, l0, W, H, V, L);
   }
 }
 
 // ---------------------------------------------------------------------------------------------------------
 // Small batches (fewer quizzes than one warp of the kernel above would hold): latency matters more than throughput.
-// One CTA per question handles 8 quizzes per round. Pass 1 cannot be spread over targets (the reference's Kahan order is
-// a serial dependency per (answer, Kahan lane)): warp w runs the 4K chains of quiz w on lanes 4k + l -- W_k stays
-// bit-exact. Pass 2 has no such dependency: for every quiz of the round ALL threads of the CTA stride over the targets,
-// warp butterflies leave per-warp partial sums in shared memory, and warp w finishes quiz w. Single chunk only.
-// With few quizzes per slab, staging log2 r would cost as much as it saves, so pass 2 evaluates the reference's
-// Log2Hot and an IEEE divide for every element (entropy and lack TERMS are then the reference's bits; only the
-// summation order differs) and the slab is just (K+1) rows: 48 KB at 1000x5x1000, four CTAs per SM.
-// Two shapes. <K, 4, false>: one or two quizzes -- (K+1)-row slab, four CTAs per SM, pass 2 with the reference's Log2Hot and
-// IEEE divide per element as described above. <K, 8, true>: 3 .. 31 quizzes -- the slab also carries log2 r (staged once per
-// CTA, worth it from the third quiz on) and pass 2 uses the throughput kernel's split logarithm and reciprocal (15 instead
-// of ~70 fp64 instructions per element); eight warps = eight quizzes per round, one CTA per question takes all quizzes.
-template <int K, int SW, bool LOGSPLIT>
-__global__ void __launch_bounds__(SW * 32, LOGSPLIT ? 2 : 4) k_eval_small(const StagedParams P) {
-  constexpr int kSmallWarps = SW;
-  constexpr int THREADS = kSmallWarps * 32;
+// One CTA per question handles SW quizzes per round. Pass 1 cannot be spread over targets (the reference's Kahan order
+// is a serial dependency per (answer, Kahan lane)): warp w runs the 4K chains of quiz w on lanes 4k + l -- W_k stays
+// bit-exact. Pass 2 has no such dependency: for every quiz of the round ALL threads of the CTA stride over the targets
+// with the throughput kernel's split logarithm, warp butterflies leave per-warp partial sums in shared memory, and
+// warp w finishes quiz w. Whole slab in shared memory only.
+template <int K, int SW>
+__global__ void __launch_bounds__(SW * 32, 2) k_eval_small(const StagedParams P) {
+  constexpr int THREADS = SW * 32;
   constexpr int NV = 2 * K + 1;                       // H_k, V_k, L
   extern __shared__ __align__(128) unsigned char smRaw[];
-  __shared__ uint64_t bar;
-  __shared__ double sWk[kSmallWarps][3][K];           // per quiz of the round: W_k, 1/W_k, log2 W_k
-  __shared__ double sPart[kSmallWarps][kSmallWarps][NV];   // [quiz][warp][value] partial sums of pass 2
-  __shared__ int64_t sSlot[kSmallWarps];              // slot of the quiz, or -1 when absent / already asked
-  double *sR = (double *)smRaw, *sLR = sR + K * P.Jc, *sID2 = sR + (LOGSPLIT ? 2 * K : K) * P.Jc;
-  const int64_t iLocal = blockIdx.x, i = P.kb.qFirst + iLocal, Q = P.kb.Q, Tp = P.kb.Tp, T = P.kb.T, Jc = P.Jc;
+  __shared__ uint64_t bars[2];
+  __shared__ double sWk[SW][3][K];                    // per quiz of the round: W_k, 1/W_k, log2 W_k
+  __shared__ double sPart[SW][SW][NV];                // [quiz][warp][value] partial sums of pass 2
+  __shared__ int64_t sSlot[SW];                       // slot of the quiz, or -1 when absent / already asked
+  const int64_t iLocal = blockIdx.x, i = P.kb.qFirst + iLocal, Q = P.kb.Q, Tp = P.kb.Tp, T = P.kb.T, nV = Tp >> 2;
+  double *sR = (double *)smRaw, *sL = sR + nV * (K * 4);
   const int64_t tileFirst = (int64_t)blockIdx.y * P.quizzesPerCta;
   const int64_t tileLimit = (tileFirst + P.quizzesPerCta < P.n) ? tileFirst + P.quizzesPerCta : P.n;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -420,13 +620,18 @@ __global__ void __launch_bounds__(SW * 32, LOGSPLIT ? 2 : 4) k_eval_small(const 
     for (int64_t b = tileFirst + threadIdx.x; b < tileLimit; b += THREADS) store_priority(P, b * Q + i, qnan);
     return;
   }
-  if (threadIdx.x == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+  if (threadIdx.x == 0) {
+    mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init();
+    const uint32_t bytesR = (uint32_t)(nV * (K * 32)), bytesL = (uint32_t)(nV * ((K + 1) * 32));
+    mbar_arrive_expect_tx(&bars[0], bytesR);
+    bulk_g2s(sR, P.kb.dR + iLocal * nV * (K * 4), bytesR, &bars[0]);
+    mbar_arrive_expect_tx(&bars[1], bytesL);
+    bulk_g2s(sL, P.kb.dL + iLocal * nV * ((K + 1) * 4), bytesL, &bars[1]);
+  }
   __syncthreads();
-  uint32_t parity = 0;
-  stage_chunk<K, THREADS>(P, iLocal, 0, LOGSPLIT, sR, sLR, sID2, &bar, parity);
   const double *__restrict__ tbl = P.kb.log2tbl;
-  const int nVects = (int)(Tp >> 2);
-  for (int64_t b0 = tileFirst; b0 < tileLimit; b0 += kSmallWarps) {      // CTA-uniform
+  const int nVects = (int)nV;
+  for (int64_t b0 = tileFirst; b0 < tileLimit; b0 += SW) {      // CTA-uniform
     // ---- pass 1: warp w <-> quiz b0 + w
     {
       const int64_t b = b0 + warp;
@@ -439,20 +644,22 @@ __global__ void __launch_bounds__(SW * 32, LOGSPLIT ? 2 : 4) k_eval_small(const 
         }
       }
       if (lane == 0) sSlot[warp] = slot;
+      mbar_wait(&bars[0], 0);
       if (slot >= 0 && lane < 4 * K) {
         const int k = lane >> 2, l = lane & 3;
-        const double *rk = sR + k * Jc + l;
+        const double *rk = sR + k * 4 + l;
         const double *__restrict__ prl = P.qp.priors + slot * Tp + l;
         Kahan kw; kw.init();
 #pragma unroll 4
-        for (int v = 0; v < nVects; v++) kw.add(__dmul_rn(rk[4 * v], __ldg(prl + 4 * v)));   // :81-86
+        for (int v = 0; v < nVects; v++) kw.add(__dmul_rn(rk[v * (4 * K)], __ldg(prl + 4 * v)));   // :81-86
         const double w = group_precise_sum(kw);                          // :88
         if (l == 0) { sWk[warp][0][k] = w; sWk[warp][1][k] = __ddiv_rn(1.0, w); sWk[warp][2][k] = log2(w); }
       }
     }
     __syncthreads();
+    mbar_wait(&bars[1], 0);
     // ---- pass 2: every quiz of the round, all threads over the targets
-    for (int q = 0; q < kSmallWarps; q++) {
+    for (int q = 0; q < SW; q++) {
       const int64_t slot = sSlot[q];
       if (slot < 0) continue;                                            // CTA-uniform
       const double *__restrict__ pr = P.qp.priors + slot * Tp;
@@ -461,26 +668,21 @@ __global__ void __launch_bounds__(SW * 32, LOGSPLIT ? 2 : 4) k_eval_small(const 
 #pragma unroll
       for (int k = 0; k < K; k++) { iW[k] = sWk[q][1][k]; lW[k] = sWk[q][2][k]; H[k] = 0.0; V[k] = 0.0; }
       for (int j = threadIdx.x; j < (int)T; j += THREADS) {
-        const double p = __ldg(pr + j), id2 = sID2[j];
-        const double lp = LOGSPLIT ? __ldg(lpr + j) : 0.0;
+        const int vb = (j >> 2), l = j & 3;
+        const double *rj = sR + vb * (4 * K) + l, *lj = sL + vb * (4 * (K + 1)) + l;
+        const double p = __ldg(pr + j), id2 = lj[4 * K], lp = __ldg(lpr + j);
 #pragma unroll
         for (int k = 0; k < K; k++) {
-          const double post = __dmul_rn(__dmul_rn(sR[k * Jc + j], p), iW[k]);   // :81-82, :97
-          if (LOGSPLIT) {
-            double l2, rl2;
-            if (fast_range_key(post) < kFastRangeLimit) {               // the throughput kernel's split logarithm
-              l2 = __dsub_rn(__dadd_rn(sLR[k * Jc + j], lp), lW[k]);
-              rl2 = fast_rcp46(l2);
-            } else {
-              l2 = slow_log2(post, tbl, &rl2);
-            }
-            H[k] = __fma_rn(post, l2, H[k]);
-            L = __fma_rn(id2, rl2, L);
+          const double post = __dmul_rn(__dmul_rn(rj[4 * k], p), iW[k]);   // :81-82, :97
+          double l2, rl2;
+          if (in_fast_range(post)) {                                     // the throughput kernel's split logarithm
+            l2 = __dsub_rn(__dadd_rn(lj[4 * k], lp), lW[k]);
+            rl2 = fast_rcp46(l2);
           } else {
-            const double l2 = log2hot(post, tbl);                       // :106
-            H[k] = __fma_rn(post, l2, H[k]);                            // :113-114
-            L = __dadd_rn(L, __ddiv_rn(id2, l2));                       // :116-117
+            l2 = slow_log2(post, tbl, &rl2);
           }
+          H[k] = __fma_rn(post, l2, H[k]);                              // :113-114
+          L = __fma_rn(id2, rl2, L);                                    // :116-117
           const double d = __dsub_rn(post, p);                          // :119
           V[k] = __fma_rn(d, d, V[k]);                                  // :126-127
         }
@@ -499,7 +701,7 @@ __global__ void __launch_bounds__(SW * 32, LOGSPLIT ? 2 : 4) k_eval_small(const 
       double W[K], H[K], V[K], L = 0.0;
 #pragma unroll
       for (int k = 0; k < K; k++) { W[k] = sWk[warp][0][k]; H[k] = 0.0; V[k] = 0.0; }
-      for (int w = 0; w < kSmallWarps; w++) {
+      for (int w = 0; w < SW; w++) {
 #pragma unroll
         for (int k = 0; k < K; k++) { H[k] = __dadd_rn(H[k], sPart[warp][w][k]); V[k] = __dadd_rn(V[k], sPart[warp][w][K + k]); }
         L = __dadd_rn(L, sPart[warp][w][2 * K]);
@@ -512,8 +714,8 @@ __global__ void __launch_bounds__(SW * 32, LOGSPLIT ? 2 : 4) k_eval_small(const 
 
 // ---------------------------------------------------------------------------------------------------------
 // Target-sharded evaluation (SURVEY.md 8e "Targets"; pqa_kernels.cuh): this device holds the columns
-// [tFirst, tFirst + P.kb.T) of every row. Same CTA shape and chunk loop as the chunked branch of k_eval_staged, split at
-// the point where the reference needs the complete W_k (:88-91):
+// [tFirst, tFirst + P.kb.T) of every row (and the derived slabs of those columns). Same CTA shape and chunk ring as the
+// streamed shape of k_eval_staged, split at the point where the reference needs the complete W_k (:88-91):
 //   PHASE 1  pass 1 over the local targets -> partial W_k (the local 4 Kahan lanes + PreciseSum) into every peer slot
 //   PHASE 2  W_k = sum of the shards' partials in shard order (identical bits on every shard) -> pass 2 over the local
 //            targets -> partial H_k (sum post*log2 post), V_k, lack sum into every peer slot
@@ -562,33 +764,49 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 4 ? 4 : 2) k_eval_tshard(
   constexpr int NV = 2 * K + 1;
   const StagedParams &P = TP.S;
   extern __shared__ __align__(128) unsigned char smRaw[];
-  __shared__ uint64_t bar;
-  double *sR = (double *)smRaw;
-  double *sLR = sR + K * P.Jc;
-  double *sID2 = sLR + K * P.Jc;
-  const int64_t iLocal = blockIdx.x, i = P.kb.qFirst + iLocal, Q = P.kb.Q, TpL = P.kb.Tp;
+  __shared__ uint64_t bars[kStages];
+  const int64_t iLocal = blockIdx.x, i = P.kb.qFirst + iLocal, Q = P.kb.Q, nV = P.kb.Tp >> 2;
   if (bit32(P.kb.qgaps, i)) return;      // the epilogue writes the NaN
   const int64_t tileFirst = (int64_t)blockIdx.y * P.quizzesPerCta;
   const int64_t tileLimit = (tileFirst + P.quizzesPerCta < P.n) ? tileFirst + P.quizzesPerCta : P.n;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qw = lane / LPQ, l0 = (lane % LPQ) * KL;
-  if (threadIdx.x == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < kStages; s++) mbar_init(&bars[s], 1);
+    mbar_fence_init();
+  }
   __syncthreads();
-  uint32_t parity = 0;
+  const int64_t stageDoubles = P.Vc * ((2 * K + 1) * 4);
+  double *const ring = (double *)smRaw;
+  double *const sTotals = ring + (P.nChunks == 1 ? 1 : kStages) * stageDoubles;   // phase 2: [2K + KL][THREADS]
+  if (PHASE == 2) zero_chunk_sums<K, KL, THREADS>(sTotals);
+  const int64_t total = P.nChunks;
+  if (threadIdx.x == 0) {      // the slab does not depend on the other shards: start the copies before any waiting
+    for (int64_t g = 0; g < kStages && g < total; g++) {
+      double *sR = ring + g * stageDoubles;
+      issue_chunk<K>(P, iLocal, g, PHASE == 2, sR, sR + P.Vc * (K * 4), &bars[g]);
+    }
+  }
   const int64_t b = tileFirst + (int64_t)warp * QPW + qw;
   bool live = b < tileLimit;
   const int64_t slot = P.slots[live ? b : tileLimit - 1];
   if (live && bit64(P.qp.asked + slot * P.qp.askedWords, i)) live = false;
-  const double *pr = P.qp.priors + slot * P.qp.Tp + TP.tFirst, *lpr = P.qp.logPriors + slot * P.qp.Tp + TP.tFirst;
+  const double *pr = P.qp.priors + slot * P.qp.Tp + TP.tFirst + l0, *lpr = P.qp.logPriors + slot * P.qp.Tp + TP.tFirst + l0;
   const int64_t o = b * Q + i;
   const int64_t pipeTile = iLocal / TP.pipe.tileQ;
   pipe_wait(TP.pipe, pipeTile);          // phase 1: the previous shard's hand-over; phase 2: the complete W_k of this tile
+  double W[K], iW[K], lW[K], H[K], V[K], L[KL];
+  Kahan kw[KL][K];
+#pragma unroll
+  for (int k = 0; k < K; k++) { H[k] = 0.0; V[k] = 0.0; W[k] = 0.0; iW[k] = 0.0; lW[k] = 0.0; }
+#pragma unroll
+  for (int e = 0; e < KL; e++) {
+    L[e] = 0.0;
+#pragma unroll
+    for (int k = 0; k < K; k++) kw[e][k].init();
+  }
   if (PHASE == 1) {
-    Kahan kw[KL][K];
-#pragma unroll
-    for (int e = 0; e < KL; e++)
-#pragma unroll
-      for (int k = 0; k < K; k++) kw[e][k].init();
     if (live && TP.inState != nullptr) {                 // continue the previous shard's Kahan lanes
 #pragma unroll
       for (int e = 0; e < KL; e++)
@@ -598,13 +816,38 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 4 ? 4 : 2) k_eval_tshard(
           kw[e][k].s = sc.x; kw[e][k].c = sc.y;
         }
     }
-    for (int64_t c = 0; c < P.nChunks; c++) {
-      stage_chunk<K, THREADS>(P, iLocal, c, false, sR, sLR, sID2, &bar, parity);
-      const int64_t j0 = c * P.Jc;
-      const int nVects = (int)(((TpL - j0 < P.Jc) ? (TpL - j0) : P.Jc) >> 2);
-      if (live) pass1_chunk<K, KL>(sR, P.Jc, nVects, j0, pr, l0, kw);
-      __syncthreads();
+  } else if (live) {
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+      double w = TP.inW.p[0][o * K + k];
+      for (int r = 1; r < TP.inW.n; r++) w = __dadd_rn(w, TP.inW.p[r][o * K + k]);
+      W[k] = w;
+      iW[k] = __ddiv_rn(1.0, w);                                         // :91
+      lW[k] = log2(w);
     }
+  }
+  for (int64_t g = 0; g < total; g++) {
+    const int s = (int)(g % kStages);
+    const double *sR = ring + s * stageDoubles, *sL = sR + P.Vc * (K * 4);
+    const int64_t v0 = g * P.Vc;
+    const int nVects = (int)((nV - v0 < P.Vc) ? (nV - v0) : P.Vc);
+    mbar_wait(&bars[s], (uint32_t)((g / kStages) & 1));
+    if (live) {
+      if (PHASE == 1) {
+        pass1_chunk<K, KL>(sR, nVects, pr + 4 * v0, l0, kw);
+      } else {
+        pass2_chunk<K, KL>(sR, sL, nVects, pr + 4 * v0, lpr + 4 * v0, P.kb.log2tbl, l0, iW, lW, H, V, L);
+        flush_chunk_sums<K, KL, THREADS>(sTotals, H, V, L);
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && g + kStages < total) {
+      fence_proxy_async_smem();
+      double *dR = ring + s * stageDoubles;
+      issue_chunk<K>(P, iLocal, g + kStages, PHASE == 2, dR, dR + P.Vc * (K * 4), &bars[s]);
+    }
+  }
+  if (PHASE == 1) {
     if (live && TP.outState != nullptr) {                // hand the lanes over to the next shard
 #pragma unroll
       for (int e = 0; e < KL; e++)
@@ -612,7 +855,6 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 4 ? 4 : 2) k_eval_tshard(
         for (int k = 0; k < K; k++)
           *reinterpret_cast<double2 *>(TP.outState + (((o * K + k) * 4 + l0 + e) * 2)) = make_double2(kw[e][k].s, kw[e][k].c);
     } else if (live) {
-      double W[K], iW[K], lW[K];
       finish_pass1<K, KL>(kw, W, iW, lW);
       if (l0 == 0) {
         for (int r = 0; r < TP.outW.n; r++)
@@ -634,43 +876,20 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 4 ? 4 : 2) k_eval_tshard(
         }
       }
     }
-  } else {
-    double W[K], iW[K], lW[K], H[K], V[K], L[KL];
+  } else if (live) {
+    load_chunk_sums<K, KL, THREADS>(sTotals, H, V, L);
+    double Ls = L[0];
 #pragma unroll
-    for (int k = 0; k < K; k++) { H[k] = 0.0; V[k] = 0.0; W[k] = 0.0; iW[k] = 0.0; lW[k] = 0.0; }
+    for (int e = 1; e < KL; e++) Ls = __dadd_rn(Ls, L[e]);
 #pragma unroll
-    for (int e = 0; e < KL; e++) L[e] = 0.0;
-    if (live) {
+    for (int k = 0; k < K; k++) { H[k] = quiz_sum<KL>(H[k]); V[k] = quiz_sum<KL>(V[k]); }
+    Ls = quiz_sum<KL>(Ls);
+    if (l0 == 0) {
+      for (int r = 0; r < TP.outHVL.n; r++) {
+        double *dst = TP.outHVL.p[r] + o * NV;
 #pragma unroll
-      for (int k = 0; k < K; k++) {
-        double w = TP.inW.p[0][o * K + k];
-        for (int r = 1; r < TP.inW.n; r++) w = __dadd_rn(w, TP.inW.p[r][o * K + k]);
-        W[k] = w;
-        iW[k] = __ddiv_rn(1.0, w);                                         // :91
-        lW[k] = log2(w);
-      }
-    }
-    for (int64_t c = 0; c < P.nChunks; c++) {
-      stage_chunk<K, THREADS>(P, iLocal, c, true, sR, sLR, sID2, &bar, parity);
-      const int64_t j0 = c * P.Jc;
-      const int nVects = (int)(((TpL - j0 < P.Jc) ? (TpL - j0) : P.Jc) >> 2);
-      if (live) pass2_chunk<K, KL>(sR, sLR, sID2, P.Jc, nVects, j0, pr, lpr, P.kb.log2tbl, l0, iW, lW, H, V, L);
-      __syncthreads();
-    }
-    if (live) {
-      double Ls = L[0];
-#pragma unroll
-      for (int e = 1; e < KL; e++) Ls = __dadd_rn(Ls, L[e]);
-#pragma unroll
-      for (int k = 0; k < K; k++) { H[k] = quiz_sum<KL>(H[k]); V[k] = quiz_sum<KL>(V[k]); }
-      Ls = quiz_sum<KL>(Ls);
-      if (l0 == 0) {
-        for (int r = 0; r < TP.outHVL.n; r++) {
-          double *dst = TP.outHVL.p[r] + o * NV;
-#pragma unroll
-          for (int k = 0; k < K; k++) { dst[k] = H[k]; dst[K + k] = V[k]; }
-          dst[2 * K] = Ls;
-        }
+        for (int k = 0; k < K; k++) { dst[k] = H[k]; dst[K + k] = V[k]; }
+        dst[2 * K] = Ls;
       }
     }
   }
@@ -715,19 +934,23 @@ __global__ void __launch_bounds__(128) k_tshard_priority(const TShardEpiloguePar
 constexpr int64_t kSlabBudgetWide = 100 * 1024;    // two CTAs of 8 warps per SM
 constexpr int64_t kSlabBudgetNarrow = 50 * 1024;   // four CTAs of 4 warps per SM (batches of <= 64 quizzes)
 
+// function attributes are per device: several engines of one process may sit on different GPUs (ShardGroup)
+template <typename KernelT> static void allow_big_smem(KernelT kernel, std::atomic<unsigned long long> &devices) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!((devices.load(std::memory_order_relaxed) >> (dev & 63)) & 1ull)) {
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    devices.fetch_or(1ull << (dev & 63), std::memory_order_relaxed);
+  }
+}
+
 template <int K, int PHASE>
 static void launch_tshard_k(TShardParams TP, size_t smem, cudaStream_t st) {
   // two threads per quiz; 128 quizzes per CTA pass (8 warps), or 64 (4 warps, twice the CTAs per SM) for small batches
   const bool wide = TP.S.n > 64;
-  // function attributes are per device: several engines of one process may sit on different GPUs (ShardGroup)
-  static std::atomic<unsigned long long> attrDevices{0};
-  int attrDev = 0;
-  cudaGetDevice(&attrDev);
-  if (!((attrDevices.load(std::memory_order_relaxed) >> (attrDev & 63)) & 1ull)) {
-    cudaFuncSetAttribute(k_eval_tshard<K, 2, 8, PHASE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(k_eval_tshard<K, 2, 4, PHASE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    attrDevices.fetch_or(1ull << (attrDev & 63), std::memory_order_relaxed);
-  }
+  static std::atomic<unsigned long long> devWide{0}, devNarrow{0};
+  allow_big_smem(k_eval_tshard<K, 2, 8, PHASE>, devWide);
+  allow_big_smem(k_eval_tshard<K, 2, 4, PHASE>, devNarrow);
   const int64_t perPass = wide ? 128 : 64;
   TP.S.quizzesPerCta = perPass;
   dim3 grid((unsigned)TP.S.kb.qCount, (unsigned)((TP.S.n + perPass - 1) / perPass));
@@ -736,36 +959,40 @@ static void launch_tshard_k(TShardParams TP, size_t smem, cudaStream_t st) {
   count_launch();
 }
 
-// Chunk geometry: the whole local row when it fits the budget, else chunks of a multiple of 32 targets.
-static size_t slab_geometry(StagedParams &P, const EvalConfig &cfg, int64_t budget) {
-  const int64_t bytesPerTarget = (2 * P.kb.K + 1) * (int64_t)sizeof(double);
-  int64_t Jc = cfg.chunkTargets > 0 ? ((cfg.chunkTargets + 3) & ~3ll) : P.kb.Tp;
-  if (Jc > P.kb.Tp) Jc = P.kb.Tp;
-  if (Jc * bytesPerTarget > budget) Jc = (budget / bytesPerTarget) & ~31ll;
-  P.Jc = Jc;
-  P.nChunks = (P.kb.Tp + Jc - 1) / Jc;
+// Chunk geometry: the whole local slab when it fits the budget (one chunk, resident), else a ring of kStages chunks of a
+// multiple of 8 vectors (32 targets). Returns the dynamic shared memory of one CTA.
+// `totals` = shared memory the streamed shape needs besides the ring (flush_chunk_sums).
+static size_t slab_geometry(StagedParams &P, const EvalConfig &cfg, int64_t budget, int64_t totals) {
+  const int64_t bytesPerVector = (2 * P.kb.K + 1) * 32;
+  const int64_t nV = P.kb.Tp >> 2;
+  int64_t Vc = cfg.chunkTargets > 0 ? (cfg.chunkTargets + 3) / 4 : nV;
+  if (Vc > nV) Vc = nV;
+  int64_t ringVc = ((budget - totals) / (kStages * bytesPerVector)) & ~7ll;
+  if (ringVc > 1016) ringVc = 1016;                      // pass 2 packs step numbers into 10 bits
+  if (Vc == nV && nV * bytesPerVector > budget) Vc = ringVc;
+  if (Vc < nV && Vc > ringVc) Vc = ringVc;
+  P.Vc = Vc;
+  P.nChunks = (nV + Vc - 1) / Vc;
   P.quizzesPerCta = 0;
-  return (size_t)(Jc * bytesPerTarget);
+  return (size_t)((P.nChunks == 1 ? 1 : kStages) * Vc * bytesPerVector);
 }
+static int64_t totals_bytes(int64_t K, int KL, int threads) { return (2 * K + KL) * (int64_t)threads * 8; }
 int64_t tshard_quiz_tiles(int64_t n) {
   const int64_t perPass = n > 64 ? 128 : 64;
   return (n + perPass - 1) / perPass;
 }
+// the target-sharded kernels always carry the totals (phase 2), resident or streamed
 static size_t tshard_geometry(StagedParams &P, const EvalConfig &cfg) {
-  return slab_geometry(P, cfg, P.n > 64 ? kSlabBudgetWide : kSlabBudgetNarrow);
-}
-
-#define PQA_K_SWITCH(K_, CALL)                                  \
-  switch (K_) {                                                 \
-    case 2: { constexpr int KK = 2; CALL; } break;              \
-    case 3: { constexpr int KK = 3; CALL; } break;              \
-    case 4: { constexpr int KK = 4; CALL; } break;              \
-    case 5: { constexpr int KK = 5; CALL; } break;              \
-    case 6: { constexpr int KK = 6; CALL; } break;              \
-    case 7: { constexpr int KK = 7; CALL; } break;              \
-    case 8: { constexpr int KK = 8; CALL; } break;              \
-    default: throw std::runtime_error("probqa_b200: target-sharded evaluation supports 2..8 answer options"); \
+  const int64_t totals = totals_bytes(P.kb.K, 2, P.n > 64 ? 256 : 128);
+  const int64_t budget = P.n > 64 ? kSlabBudgetWide : kSlabBudgetNarrow;
+  size_t smem = slab_geometry(P, cfg, budget, totals);
+  if (P.nChunks == 1 && (int64_t)smem + totals > budget) {      // whole slab + totals do not fit: stream it
+    EvalConfig c2 = cfg;
+    c2.chunkTargets = 4 * (((budget - totals) / (kStages * (2 * P.kb.K + 1) * 32)) & ~7ll);
+    smem = slab_geometry(P, c2, budget, totals);
   }
+  return smem + (size_t)totals;
+}
 
 void launch_eval_tshard_w(const DeviceKB &kbLocal, const QuizPool &qp, int64_t tFirst, int64_t n, const int64_t *dSlots,
                           const PeerBufs &outW, const EvalConfig &cfg, cudaStream_t st, const double *inState,
@@ -798,7 +1025,7 @@ void launch_tshard_priority(const DeviceKB &kbLocal, const QuizPool &qp, int64_t
                             cudaStream_t st) {
   TShardEpilogueParams EP;
   EP.S.kb = kbLocal; EP.S.qp = qp; EP.S.n = n; EP.S.slots = dSlots; EP.S.priority = dPriority; EP.S.det = det;
-  EP.S.Jc = 0; EP.S.nChunks = 0; EP.S.quizzesPerCta = 0;
+  EP.S.Vc = 0; EP.S.nChunks = 0; EP.S.quizzesPerCta = 0;
   EP.inW = inW; EP.inHVL = inHVL;
   const int64_t total = n * kbLocal.Q;
   int64_t g = (total + 127) / 128;
@@ -809,41 +1036,21 @@ void launch_tshard_priority(const DeviceKB &kbLocal, const QuizPool &qp, int64_t
 
 template <int K>
 static void launch_small(StagedParams P, size_t smem, cudaStream_t st) {
-  // function attributes are per device: several engines of one process may sit on different GPUs (ShardGroup)
-  static std::atomic<unsigned long long> attrDevices{0};
-  int attrDev = 0;
-  cudaGetDevice(&attrDev);
-  if (!((attrDevices.load(std::memory_order_relaxed) >> (attrDev & 63)) & 1ull)) {
-    cudaFuncSetAttribute(k_eval_small<K, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(k_eval_small<K, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    attrDevices.fetch_or(1ull << (attrDev & 63), std::memory_order_relaxed);
-  }
-  if (P.n <= 2) {
-    P.quizzesPerCta = 4;
-    dim3 grid((unsigned)P.kb.qCount, (unsigned)((P.n + 3) / 4));
-    smem = (size_t)((K + 1) * P.Jc) * sizeof(double);
-    k_eval_small<K, 4, false><<<grid, 4 * 32, smem, st>>>(P);
-  } else {
-    P.quizzesPerCta = 32;                                    // one CTA per question, rounds of eight quizzes
-    dim3 grid((unsigned)P.kb.qCount, (unsigned)((P.n + 31) / 32));
-    smem = (size_t)((2 * K + 1) * P.Jc) * sizeof(double);
-    k_eval_small<K, 8, true><<<grid, 8 * 32, smem, st>>>(P);
-  }
+  static std::atomic<unsigned long long> dev{0};
+  allow_big_smem(k_eval_small<K, 8>, dev);
+  P.quizzesPerCta = 32;                                    // one CTA per question, rounds of eight quizzes
+  dim3 grid((unsigned)P.kb.qCount, (unsigned)((P.n + 31) / 32));
+  k_eval_small<K, 8><<<grid, 8 * 32, smem, st>>>(P);
   count_launch();
 }
 
 template <int K, int KL, int WARPS>
 static void launch_cfg(StagedParams P, const EvalConfig &cfg, size_t smem, cudaStream_t st) {
-  // function attributes are per device: several engines of one process may sit on different GPUs (ShardGroup)
-  static std::atomic<unsigned long long> attrDevices{0};
-  int attrDev = 0;
-  cudaGetDevice(&attrDev);
-  if (!((attrDevices.load(std::memory_order_relaxed) >> (attrDev & 63)) & 1ull)) {
-    cudaFuncSetAttribute(k_eval_staged<K, KL, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    attrDevices.fetch_or(1ull << (attrDev & 63), std::memory_order_relaxed);
-  }
+  static std::atomic<unsigned long long> dev{0};
+  allow_big_smem(k_eval_staged<K, KL, WARPS>, dev);
   const int64_t perPass = (int64_t)WARPS * (32 / (4 / KL));   // quizzes one CTA evaluates concurrently
   if (P.nChunks > 1) {
+    smem += (size_t)totals_bytes(K, KL, WARPS * 32);
     P.quizzesPerCta = perPass;
   } else if (cfg.quizzesPerCta > 0) {
     P.quizzesPerCta = ((cfg.quizzesPerCta + perPass - 1) / perPass) * perPass;
@@ -871,7 +1078,7 @@ static void launch_k(const StagedParams &P, const EvalConfig &cfg, size_t smem, 
   if (lanesPerThread == 4) launch_cfg<K, 4, 4>(P, cfg, smem, st);
   else if (lanesPerThread == 2 && P.n <= 64 && P.nChunks > 1) launch_cfg<K, 2, 4>(P, cfg, smem, st);   // 64 quizzes per CTA pass, 4 CTAs/SM
   else if (lanesPerThread == 2 && P.n <= 64 && cfg.kahanLanesPerThread == 0) launch_cfg<K, 1, 8>(P, cfg, smem, st);   // whole slab (2 CTAs/SM):
-                                                               // four threads per quiz fill all 8 warps (measured 0.58 vs 0.67 ms at B = 64)
+                                                               // four threads per quiz fill all 8 warps
   else if (lanesPerThread == 2) launch_cfg<K, 2, 8>(P, cfg, smem, st);
   else launch_cfg<K, 1, 8>(P, cfg, smem, st);
 }
@@ -886,29 +1093,21 @@ void launch_eval_staged(const DeviceKB &kb, const QuizPool &qp, int64_t n, const
   }
   StagedParams P;
   P.kb = kb; P.qp = qp; P.n = n; P.slots = dSlots; P.priority = dPriority; P.det = det; P.mirror = cfg.mirror;
-  // a slab that fits 100 KB is staged whole; a chunked one uses 50 KB chunks for batches of <= 64 quizzes, which run
+  // a slab that fits 100 KB is staged whole; a streamed one uses a 50 KB ring for batches of <= 64 quizzes, which run
   // four 4-warp CTAs per SM (launch_k)
-  size_t smem = slab_geometry(P, cfg, kSlabBudgetWide);
+  size_t smem = slab_geometry(P, cfg, kSlabBudgetWide, totals_bytes(kb.K, 4, 256));
   if (P.nChunks > 1 && n <= 64 && cfg.chunkTargets == 0 && (cfg.kahanLanesPerThread == 0 || cfg.kahanLanesPerThread == 2))
-    smem = slab_geometry(P, cfg, kSlabBudgetNarrow);
-  switch (kb.K) {
-    case 2: launch_k<2>(P, cfg, smem, st); break;
-    case 3: launch_k<3>(P, cfg, smem, st); break;
-    case 4: launch_k<4>(P, cfg, smem, st); break;
-    case 5: launch_k<5>(P, cfg, smem, st); break;
-    case 6: launch_k<6>(P, cfg, smem, st); break;
-    case 7: launch_k<7>(P, cfg, smem, st); break;
-    default: launch_k<8>(P, cfg, smem, st); break;
-  }
+    smem = slab_geometry(P, cfg, kSlabBudgetNarrow, totals_bytes(kb.K, 2, 128));
+  PQA_K_SWITCH(kb.K, (launch_k<KK>(P, cfg, smem, st)))
 }
 
 template <int K> static void preload_staged_k() {
   cudaFuncAttributes a;
+  cudaFuncGetAttributes(&a, k_build_derived<K>);
   cudaFuncGetAttributes(&a, k_eval_staged<K, 1, 8>);
   cudaFuncGetAttributes(&a, k_eval_staged<K, 2, 8>);
   cudaFuncGetAttributes(&a, k_eval_staged<K, 4, 4>);
-  cudaFuncGetAttributes(&a, k_eval_small<K, 4, false>);
-  cudaFuncGetAttributes(&a, k_eval_small<K, 8, true>);
+  cudaFuncGetAttributes(&a, k_eval_small<K, 8>);
   cudaFuncGetAttributes(&a, k_eval_staged<K, 2, 4>);
   cudaFuncGetAttributes(&a, k_eval_tshard<K, 2, 4, 1>);
   cudaFuncGetAttributes(&a, k_eval_tshard<K, 2, 8, 1>);

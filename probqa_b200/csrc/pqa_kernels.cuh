@@ -15,6 +15,11 @@ struct DeviceKB {
   double *sA;
   double *mD;
   double *vB;
+  // Derived KB streamed by the throughput evaluation kernels (pqa_eval_staged.cu), per local question i and 4-target
+  // vector v: dR[(i*nV + v)*K*4 + k*4 + lane] = sA/mD, dL[(i*nV + v)*(K+1)*4 + k*4 + lane] = log2(sA/mD) for k < K and
+  // 1/mD^2 for k = K (nV = Tp/4). nullptr for views that never evaluate (kbQuiz of a target shard, K > 8).
+  double *dR = nullptr;
+  double *dL = nullptr;
   const double *log2tbl;   // 1024-entry table of SRVectMath.cpp:30-44
   const uint32_t *tgaps;   // target gap bitmap (bit j of word j>>5) or nullptr
   const uint32_t *qgaps;   // question gap bitmap or nullptr
@@ -88,6 +93,10 @@ struct EvalConfig {
 };
 void launch_eval_questions(const DeviceKB &kb, const QuizPool &qp, int64_t n, const int64_t *dSlots,
                            double *dPriority, const EvalDetail &det, const EvalConfig &cfg, cudaStream_t st);
+// Derived KB (kb.dR / kb.dL): element counts for this view, and the builder -- all local questions (dList = nullptr) or
+// the nList local question indices in dList (the questions a Train / RecordQuizTarget touched).
+void derived_kb_doubles(const DeviceKB &kb, size_t *nR, size_t *nL);
+void launch_build_derived(const DeviceKB &kb, const int64_t *dList, int64_t nList, cudaStream_t st);
 // CpuEngine::NextQuestionSpec (CpuEngine.cpp:337-415) after the evaluation: chunk run-lengths, grand totals,
 // weighted draw with dRandoms[n], nearest unasked question; writes dQuestions[n] and the quiz' active question.
 // dRunLength[n*Q] / dGrand[n*nChunks] optional outputs. setActive=0 leaves the quiz untouched.

@@ -138,6 +138,7 @@ bool Engine::RemapQuizPermId(int64_t srcPermId, int64_t destPermId) {           
 // Bit j of word j>>5 = target j is a gap; same for questions. Uploaded only while gaps exist (kb() hands the kernels a
 // null bitmap otherwise, which costs them nothing).
 void Engine::SyncGapBits() {
+  MarkKBChanged();   // gap targets are +0 lanes of the derived KB; every maintenance change of sA / mD ends here too
   auto upload = [&](const GapSet &g, int64_t n, DevBuf<uint32_t> &buf) {
     if (g.GetNGaps() == 0) return;
     std::vector<uint32_t> words((size_t)((n + 31) >> 5) + 1, 0u);
@@ -237,6 +238,7 @@ PqaError *Engine::FinishMaintenance() {
 // New device arrays for newQ x K x newT, old cells kept; the cells of new rows / columns are written by the caller.
 // The quiz pool (sized by Tp and ceil(Q/64)) is dropped: maintenance mode has no quizzes.
 void Engine::ResizeKB(int64_t newQ, int64_t newT) {
+  MarkKBChanged();
   const int64_t newTp = (newT + 3) & ~3ll;
   double *nA = nullptr, *nD = nullptr, *nB = nullptr;
   PQA_CU(cudaMalloc(&nA, sizeof(double) * (size_t)(newQ * K_ * newTp)));

@@ -134,6 +134,7 @@ SIGNATURES = {
     "PqaB200_SetQuizPriors": (_vp, [_vp, _i64, _pd]),
     "PqaB200_EvalQuestions": (_vp, [_vp, _i64, _pi64, _pd, _pd, _pd, _pi64]),
     "PqaB200_EvalQuestionsDetailed": (_vp, [_vp, _i64, _pd, _pd, _pd, _pd, _pd]),
+    "PqaB200_P2PLastPhaseMs": (_vp, [_vp, _pd]),
     "PqaB200_EvalQuestionsDetailedBatch": (_vp, [_vp, _i64, _pi64, _pd, _pd, _pd, _pd, _pd]),
     "PqaB200_SetEvalKernel": (_vp, [_vp, C.c_int32]),
     "PqaB200_SetEvalTuning": (_vp, [_vp, C.c_int32, _i64, _i64, C.c_int32]),
@@ -684,6 +685,12 @@ class PqaEngine:
     def p2p_record_answer_begin(self, quiz_ids, answers):
         ids, ans = _i64arr(quiz_ids), _i64arr(answers)
         _raise_or_return(self._lib.PqaB200_P2PRecordAnswerBegin(self.c_engine, ids.size, _p(ids, _pi64), _p(ans, _pi64)))
+
+    def p2p_last_phase_ms(self) -> np.ndarray:
+        """[phase 1, barrier, phase 2, barrier, epilogue + selection] device ms of the last target-sharded P2PNextQuestion."""
+        out = np.zeros(5)
+        _raise_or_return(self._lib.PqaB200_P2PLastPhaseMs(self.c_engine, _p(out, _pd)))
+        return out
 
     def p2p_set_exact_order(self, on: bool):
         """Target shards: hand the Kahan lanes from shard to shard so that W_k is bit-identical to a single engine's."""

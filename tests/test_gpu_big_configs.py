@@ -71,13 +71,16 @@ def test_config3_chunked_wide_kernel_sampled_vs_oracle(ora):
     assert worst <= TOL_STAGED, worst
 
 
-@pytest.mark.parametrize("exact_order,tol", [(True, TOL_STAGED), (False, 1e-7)])
-def test_config4_eight_target_shards_sampled_vs_oracle(ora, exact_order, tol):
+@pytest.mark.parametrize("exact_order", [True, False])
+def test_config4_eight_target_shards_sampled_vs_oracle(ora, exact_order):
     """T = 100 000 targets split over 8 target shards (BASELINE config 4's partition; Q cut to 2000 so that the test takes
     seconds), peer-memory exchange, batch 70 (8-warp CTAs) in bench.py's shape. A few hundred (quiz, question) priorities
-    against the oracle: with the exact-order pipeline the single-engine bar (2e-12) holds; the summed-partials exchange
-    is held to its own bar on this KB (uninformative questions amplify the W_k rounding). Posteriors after
-    RecordAnswer are bit-exact either way."""
+    against the oracle. With the exact-order pipeline (the default of bench.py's sharded leg) the single-engine bar holds:
+    2e-12 relative per priority. The summed-partials exchange cannot reproduce the reference's W_k bits, and a question that
+    is uninformative under the current posterior has a priority that is rounding noise in ANY implementation (its
+    sum (post - prior)^2 is ~1e-32): there the two differ by percents of a value that is ~1e-8 of an
+    informative question's. Its bar is therefore on what selection sees: every priority within 1e-11 of the quiz' run
+    length (sum of its priorities). Posteriors after RecordAnswer are bit-exact either way."""
     from probqa_b200 import engine as pqa
     Q, K, T, W, B, NS = 2000, 5, 100000, 8, 70, 8
     fac = pqa.PqaEngineFactory()
@@ -113,7 +116,7 @@ def test_config4_eight_target_shards_sampled_vs_oracle(ora, exact_order, tol):
         other = s._view(0).cpu().numpy()[:B * Q].reshape(B, Q)
         assert np.array_equal(np.isnan(other), np.isnan(pri)) and np.array_equal(bits(other[~np.isnan(pri)]), bits(pri[~np.isnan(pri)]))
     sample_q = np.unique(np.concatenate([[0, Q - 1], rng.integers(0, Q, 70)]))
-    worst = 0.0
+    worst = worst_run = 0.0
     for i in sample_q:
         i = int(i)
         a_rows, d_row = np.empty((K, T)), np.empty(T)
@@ -129,5 +132,9 @@ def test_config4_eight_target_shards_sampled_vs_oracle(ora, exact_order, tol):
             prior = shards[0].copy_quiz_priors(int(quizzes[x]))
             o = ora.eval_question(a_rows, d_row, prior)
             worst = max(worst, abs(pri[x, i] - o["priority"]) / abs(o["priority"]))
-    print("8 target shards, T=100000, exact_order=%s: max relative priority difference vs the oracle %.3g" % (exact_order, worst))
-    assert worst <= tol, worst
+            worst_run = max(worst_run, abs(pri[x, i] - o["priority"]) / float(np.nansum(pri[x])))
+    print("8 target shards, T=100000, exact_order=%s: max priority difference vs the oracle: %.3g relative, %.3g of the run length"
+          % (exact_order, worst, worst_run))
+    if exact_order:
+        assert worst <= TOL_STAGED, worst
+    assert worst_run <= 1e-11, worst_run
