@@ -224,19 +224,203 @@ def cpu_baseline(cfg, budget_s=12.0):
                 n_calls, "/".join(map(str, DEPTHS)), dt, cores)}
 
 
-def bench_sharded(args, cfg, pqa, dist, rank, world, local_rank, cores, barrier, max_over_ranks):
-    """Strong scaling of ONE batch over N GPUs. --shard questions: every rank holds Q/N question rows of the KB, the
-    ranks' priority columns are exchanged, every rank selects (bit-identical to one engine). --shard targets (BASELINE
-    config 4's axis): every rank holds T/N target columns, two-phase evaluation with an exchange of the W_k partials and
-    of the H/V/lack partials. --exchange nccl: torch.distributed all-reduce on the engine's buffers (host sync on both
-    sides); --exchange p2p: the kernels store into the peers' inboxes over NVLink and a device-side barrier orders the
-    phases. The whole step goes through the public sharded API with host buffers, so value == e2e here."""
+def make_batch(eng, cfg, first_quiz, B):
+    """B quizzes in bench.py's shape on `eng` (anything with the batch API): depths DEPTHS cycled, prefixes from synth."""
+    states = quiz_states(cfg, first_quiz, B)
+    quizzes = eng.start_quiz_batch(B)
+    for s in range(max(DEPTHS)):
+        sel = [x for x in range(B) if len(states[x]) > s]
+        if not sel:
+            break
+        eng.set_active_question_batch(quizzes[sel], [states[x][s][0] for x in sel])
+        eng.record_answer_batch(quizzes[sel], [states[x][s][1] for x in sel])
+    return quizzes, states, int(sum(cfg["Q"] - len(pf) for pf in states))
+
+
+def resident_leg(pqa, eng, steps, warmup, flush, barrier=lambda: None):
+    """Device-resident stepping: per-step CUDA events on the engine's stream, L2 flushed between steps outside the events."""
+    for _ in range(warmup):
+        if flush:
+            eng.flush_l2()
+        eng.resident_step()
+    eng.synchronize()
+    launches0 = eng.kernel_launch_count()
+    ev = [(pqa.DeviceEvent(), pqa.DeviceEvent()) for _ in range(steps)]
+    eval_ms = []
+    barrier()
+    for k in range(steps):
+        if flush:
+            eng.flush_l2()
+        ev[k][0].record(eng)
+        eng.resident_step()
+        ev[k][1].record(eng)
+        eval_ms.append(eng.resident_last_eval_ms())
+    eng.synchronize()
+    barrier()
+    return dict(total_ms=sum(a.elapsed_ms(b) for a, b in ev), eval_ms=sum(eval_ms) / len(eval_ms),
+                launches=eng.kernel_launch_count() - launches0)
+
+
+def e2e_leg(eng, quizzes, randoms, steps, warmup, barrier=lambda: None):
+    for _ in range(warmup):
+        eng.next_question_batch(quizzes, randoms)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        out = eng.next_question_batch(quizzes, randoms)
+    return time.perf_counter() - t0, out
+
+
+def fp64_model(K):
+    """fp64 instructions per (quiz, question, answer, target) element of the staged kernel (pqa_eval_staged.cu): pass 1 =
+    1 DMUL + 4 Kahan adds; pass 2 = 2 DMUL (post) + 2 DADD (log2 post) + 1 DFMA (H) + DADD + DFMA (V) per element, plus per
+    target 2(K-1) (fraction) + 3 (reciprocal) + 2 (lack)."""
+    return 5.0 + 7.0 + (2.0 * (K - 1) + 5.0) / K
+
+
+def fp64_roofline(qevals, K, T, kernel_ms, sm_mhz, sm_count=148, measured_warp_instr=None):
+    per_elem = fp64_model(K)
+    warp_instr = measured_warp_instr if measured_warp_instr else qevals * K * T * per_elem / 32.0
+    peak = 0.5 * 4 * sm_count * (sm_mhz or 1965.0) * 1e6        # one fp64 warp instruction per 2 cycles per sub-partition
+    ach = warp_instr / (kernel_ms * 1e-3)
+    return {"instr_per_element": per_elem, "warp_instr_per_launch": warp_instr,
+            "warp_instr_source": "ncu sm__inst_executed_pipe_fp64.sum" if measured_warp_instr else "model (bench.py fp64_model)",
+            "achieved_warp_instr_per_s": ach, "peak_warp_instr_per_s": peak, "frac": ach / peak,
+            "peak_source": "0.5 warp-instr/cycle/sub-partition (scripts/microbench/fp64_pipe.cu) x 4 x %d SMs x %.0f MHz" % (sm_count, sm_mhz or 1965.0)}
+
+
+def measure_traffic(args):
+    """DRAM bytes and fp64 warp instructions of ONE launch of the evaluation kernel, from an ncu replay of this same
+    workload in a child process (`--traffic-child`: warm-up launches, then the profiled one). None when ncu is missing."""
+    import shutil
+    ncu = shutil.which("ncu") or "/usr/local/cuda/bin/ncu"
+    if not os.path.exists(ncu):
+        return None
+    cmd = [ncu, "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum,sm__inst_executed_pipe_fp64.sum,gpu__time_duration.sum",
+           "--clock-control", "none", "-k", "regex:k_eval_staged", "-s", "3", "-c", "1", "--csv",
+           sys.executable, os.path.abspath(__file__), "--traffic-child", "--workload", args.workload, "--kernel", str(args.kernel)]
+    try:
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=180, cwd=ROOT).stdout
+    except Exception:
+        return None
+    import csv
+    vals = {}
+    for row in csv.reader(out.splitlines()):
+        if len(row) >= 3 and row[-3].startswith(("dram__", "sm__inst", "gpu__time")):
+            try:
+                v = float(row[-1].replace(",", ""))
+            except ValueError:
+                continue
+            unit = row[-2].lower()
+            scale = {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(unit, 1)
+            vals[row[-3]] = v * scale
+    if "dram__bytes_read.sum" not in vals:
+        return None
+    return {"dram_bytes": vals["dram__bytes_read.sum"] + vals.get("dram__bytes_write.sum", 0.0),
+            "dram_bytes_read": vals["dram__bytes_read.sum"], "dram_bytes_write": vals.get("dram__bytes_write.sum"),
+            "fp64_warp_instr": vals.get("sm__inst_executed_pipe_fp64.sum"),
+            "how": "ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,sm__inst_executed_pipe_fp64.sum of one k_eval_staged "
+                   "launch of this workload (child process, after 3 warm-up launches; not a timed run)"}
+
+
+def traffic_child(args, cfg, pqa):
+    eng = pqa.PqaEngineFactory().create_b200_engine(pqa.EngineDefinition(cfg["K"], cfg["Q"], cfg["T"], init_amount=INIT),
+                                                    emulated_workers=host_cores(), rng_seed=1234, initial_quiz_capacity=cfg["B"])
+    eng.fill_binary_search_kb(3)
+    eng.set_eval_kernel(args.kernel, args.chunk_targets, args.quizzes_per_cta, args.lanes)
+    quizzes, _, _ = make_batch(eng, cfg, 0, cfg["B"])
+    eng.resident_bind(quizzes, np.arange(cfg["B"], dtype=np.uint64))
+    for _ in range(5):
+        eng.resident_step()
+    eng.synchronize()
+
+
+def extra_workload(pqa, name, cores, steps, warmup, device=0):
+    """One more BASELINE workload on one GPU, device-resident and through the host-buffer call; returns a dict for the line."""
+    cfg = WORKLOADS[name]
+    Q, K, T, B = cfg["Q"], cfg["K"], cfg["T"], cfg["B"]
+    t_build = time.perf_counter()
+    eng = pqa.PqaEngineFactory().create_b200_engine(pqa.EngineDefinition(K, Q, T, init_amount=INIT), device=device,
+                                                    emulated_workers=cores, rng_seed=1234, initial_quiz_capacity=B)
+    eng.fill_binary_search_kb(3)
+    quizzes, states, qevals = make_batch(eng, cfg, 0, B)
+    randoms = np.random.default_rng(99).integers(0, 2 ** 64, size=B, dtype=np.uint64)
+    eng.resident_bind(quizzes, randoms)
+    t_build = time.perf_counter() - t_build
+    r = resident_leg(pqa, eng, steps, warmup, flush=False)     # the KB is far larger than L2
+    t_e2e, chosen = e2e_leg(eng, quizzes, randoms, max(2, steps // 2), 1)
+    peak, _ = measured_peak()
+    alg = qevals * (K + 1) * T * 8
+    out = {"workload": name, "Q": Q, "A": K, "T": T, "batch": B, "kb_gb": Q * (K + 1) * T * 8 / 1e9,
+           "value": qevals * steps / (r["total_ms"] * 1e-3), "unit": "questions/s", "ms_per_step": r["total_ms"] / steps,
+           "steps": steps, "warmup": warmup, "kernel_ms": r["eval_ms"],
+           "e2e_value": qevals * max(2, steps // 2) / t_e2e,
+           "hbm_algorithmic_gbs": alg / (r["eval_ms"] * 1e-3) / 1e9, "hbm_frac": alg / (r["eval_ms"] * 1e-3) / 1e9 / peak,
+           "fp64_frac": fp64_roofline(qevals, K, T, r["eval_ms"], None)["frac"], "setup_s": t_build,
+           "l2": "inputs (KB %.1f GB) larger than L2" % (Q * (K + 1) * T * 8 / 1e9),
+           "chosen_checksum": int(np.sum(chosen * (np.arange(B) + 1)) % 1000000007)}
+    eng.close()
+    return out
+
+
+def train_workload(pqa, cores, cpu_sample_quizzes=4000):
+    """BASELINE config 5: 10^6 RecordQuizTarget cell updates = 125 000 quizzes x 8 answered questions on 1000x5x1000 in one
+    PqaEngine_RecordQuizTargetBatch call (host buffers), and the CPU port on a bounded sample of the same stream."""
+    Q, K, T = 1000, 5, 1000
+    n, d = 125000, 8
+    kb = synth.binary_search_kb(Q, K, T, INIT, 3)
+    eng = pqa.PqaEngineFactory().create_b200_engine(pqa.EngineDefinition(K, Q, T, init_amount=INIT), emulated_workers=cores,
+                                                    rng_seed=3, initial_quiz_capacity=n)
+    eng.upload_kb(*kb)
+    rng = np.random.default_rng(20171126)
+    targets = rng.integers(0, T, size=n)
+    qs = np.argsort(rng.random((n, 64)), axis=1)[:, :d] + rng.integers(0, Q - 64, size=(n, 1))
+    ans = synth.answer_rule(Q, T, K)[qs, targets[:, None]]
+    quizzes = eng.start_quiz_batch(n)
+    for s in range(d):
+        eng.set_active_question_batch(quizzes, qs[:, s])
+        eng.record_answer_batch(quizzes, ans[:, s])
+    eng.synchronize()
+    launches0 = eng.kernel_launch_count()
+    t0 = time.perf_counter()
+    eng.record_quiz_target_batch(quizzes, targets)
+    eng.synchronize()
+    t_gpu = time.perf_counter() - t0
+    out = {"workload": "train_1e6_updates_1000x5x1000", "updates": n * d, "quizzes": n, "value": n * d / t_gpu, "unit": "cell updates/s",
+           "seconds": t_gpu, "api": "PqaEngine_RecordQuizTargetBatch (host buffers, one call)",
+           "gpu_launches": int(eng.kernel_launch_count() - launches0)}
+    try:
+        from oracle import oracle as ora
+        m = min(cpu_sample_quizzes, n)
+        sA, mD, vB = [a.copy() for a in kb]
+        t0 = time.perf_counter()
+        for x in range(m):
+            ora.record_quiz_target(sA, mD, vB, list(zip(qs[x].tolist(), ans[x].tolist())), int(targets[x]), 1.0)
+        t_cpu = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": m * d / t_cpu, "unit": "cell updates/s", "cores": 1, "kind": "port",
+                               "sample": "first %d quizzes of the same stream, one RecordQuizTarget per call (as the reference does)" % m}
+    except Exception as ex:
+        out["cpu_baseline"] = {"value": None, "kind": "unavailable", "sample": repr(ex)}
+    eng.close()
+    return out
+
+
+def sharded_leg(args, wl_name, pqa, dist, rank, world, local_rank, cores, barrier, max_over_ranks, axis, exchange,
+                exact_modes, steps, warmup):
+    """Strong scaling of ONE batch over the N GPUs of the job (one process per GPU). axis "targets" (BASELINE config 4's
+    partition): every rank holds T/N target columns of every sA/mD row; two-phase evaluation with an exchange of the
+    [B][Q][K] W_k partials and of the [B][Q][2K+1] H/V/lack partials. axis "questions": every rank holds Q/N rows, the
+    [B][Q] priority columns are exchanged. exchange "p2p": the kernels store into the peers' inboxes over NVLink and a
+    device-side barrier orders the phases; "nccl": torch.distributed all-reduce on the engine's buffers. Returns one dict
+    per entry of exact_modes (target shards with p2p: False = summed partials, True = exact-order pipeline). Timing: wall
+    clock around the public sharded API (host buffers, result D2H inside every step), max over ranks."""
     import torch
     from probqa_b200 import sharded
+    cfg = WORKLOADS[wl_name]
     Q, K, T, B = cfg["Q"], cfg["K"], cfg["T"], cfg["B"]
     fac = pqa.PqaEngineFactory()
     edef = pqa.EngineDefinition(K, Q, T, init_amount=INIT)
-    if args.shard == "questions":
+    if axis == "questions":
         first, count = sharded.shard_ranges(Q, world)[rank]
         eng = fac.create_b200_engine(edef, device=local_rank, emulated_workers=cores, rng_seed=1234, initial_quiz_capacity=B,
                                      question_shard_first=first, question_shard_count=count)
@@ -249,70 +433,84 @@ def bench_sharded(args, cfg, pqa, dist, rank, world, local_rank, cores, barrier,
     eng.fill_binary_search_kb(3)       # this rank's shard of synth.binary_search_kb, written on the device
     eng.set_eval_kernel(args.kernel, args.chunk_targets, args.quizzes_per_cta, args.lanes)
     group = dist.group.WORLD if dist is not None else None
-    if args.shard == "questions":
-        se = sharded.QuestionShardedEngine([sharded.B200Shard(eng)], group=group)
-    else:
-        se = sharded.TargetShardedEngine([sharded.B200TargetShard(eng)], group=group)
-    if args.exchange == "p2p":
-        se.enable_p2p(B, exact_order=args.exact_order and args.shard == "targets")
-    states = quiz_states(cfg, 0, B)
-    quizzes = se.start_quiz_batch(B)
-    for s in range(max(DEPTHS)):
-        sel = [x for x in range(B) if len(states[x]) > s]
-        if not sel:
-            break
-        se.set_active_question_batch(quizzes[sel], [states[x][s][0] for x in sel])
-        se.record_answer_batch(quizzes[sel], [states[x][s][1] for x in sel])
-    qevals_step = int(sum(Q - len(pf) for pf in states))
+    se = (sharded.QuestionShardedEngine([sharded.B200Shard(eng)], group=group) if axis == "questions"
+          else sharded.TargetShardedEngine([sharded.B200TargetShard(eng)], group=group))
+    if exchange == "p2p":
+        se.enable_p2p(B, exact_order=False)
+    quizzes, states, qevals_step = make_batch(se, cfg, 0, B)
     randoms = np.random.default_rng(99).integers(0, 2 ** 64, size=B, dtype=np.uint64)
-    for _ in range(args.warmup):
-        chosen = se.next_question_batch(quizzes, randoms)
-    sampler = ClockSampler(local_rank)
+    results = []
+    for exact in exact_modes:
+        if exchange == "p2p" and axis == "targets":
+            eng.p2p_set_exact_order(bool(exact))
+        for _ in range(warmup):
+            chosen = se.next_question_batch(quizzes, randoms)
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+        launches0 = eng.kernel_launch_count()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            chosen = se.next_question_batch(quizzes, randoms)
+        torch.cuda.synchronize()
+        dt = max_over_ranks(time.perf_counter() - t0)
+        barrier()
+        launches = eng.kernel_launch_count() - launches0
+        clocks = sampler.stop() if rank == 0 else None
+        assert np.all((chosen >= 0) & (chosen < Q))
+        phases = None
+        if exchange == "p2p" and axis == "targets":
+            ph = eng.p2p_last_phase_ms()
+            names = ["phase1_W_partials", "barrier1", "phase2_HVL_partials", "barrier2", "epilogue_select"]
+            phases = {n_: max_over_ranks(float(v)) for n_, v in zip(names, ph)}
+            phases["rank0"] = {n_: float(v) for n_, v in zip(names, ph)}
+            phases["note"] = ("device ms of the last timed step, CUDA events on each rank's stream, max over ranks; with the "
+                              "exact-order pipeline phase 2 includes waiting for the last shard's W_k tiles and there is no barrier1")
+        value = qevals_step * steps / dt
+        peak, peak_src = measured_peak()
+        xbytes = int(B * Q * 8) if axis == "questions" else int(B * Q * (3 * K + 1) * 8)
+        if exact and axis == "targets":
+            xbytes = int(B * Q * (K * 8 * 8 + K * 8 + (2 * K + 1) * 8))       # Kahan lanes hand-over + complete W_k + H/V/lack partials
+        per_gpu = qevals_step * (K + 1) * T * 8 / (dt / steps) / 1e9 / world
+        results.append({
+            "workload": wl_name, "Q": Q, "A": K, "T": T, "batch_total": B, "n_gpus": world, "axis": axis, "scaling": "strong",
+            "exchange": ("NCCL all-reduce via torch.distributed" if exchange == "nccl" else
+                         "peer-memory stores from the kernel epilogues over NVLink + device-side barrier (no host round trip)"),
+            "exact_order_pipeline": bool(exact and axis == "targets" and exchange == "p2p"),
+            "value": value, "unit": "questions/s", "ms_per_step": 1e3 * dt / steps, "steps": steps, "warmup": warmup,
+            "exchange_bytes_per_step_per_gpu": xbytes, "kb_shard_gb": shard_bytes / 1e9,
+            "hbm_algorithmic_gbs_per_gpu": per_gpu, "hbm_frac_per_gpu": per_gpu / peak, "phases_ms": phases,
+            "gpu_launches_per_step_per_gpu": launches / steps, "clocks": clocks,
+            "timing": "wall clock around sharded.%s.next_question_batch (host buffers; result D2H + host sync inside every step), max over ranks"
+                      % type(se).__name__,
+            "chosen_checksum": int(np.sum(chosen * (np.arange(B) + 1)) % 1000000007)})
+    eng.close()
+    return results
+
+
+def bench_sharded(args, cfg, pqa, dist, rank, world, local_rank, cores, barrier, max_over_ranks):
+    """`--shard questions|targets` as the job's main line (scripts/run_multi_gpu.sh): value == e2e."""
+    res = sharded_leg(args, args.workload, pqa, dist, rank, world, local_rank, cores, barrier, max_over_ranks, args.shard,
+                      args.exchange, [args.exact_order], args.steps, args.warmup)[0]
     if rank == 0:
-        sampler.start()
-    launches0 = eng.kernel_launch_count()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        chosen = se.next_question_batch(quizzes, randoms)
-    torch.cuda.synchronize()
-    dt = max_over_ranks(time.perf_counter() - t0)
-    barrier()
-    launches = eng.kernel_launch_count() - launches0
-    clocks = sampler.stop() if rank == 0 else None
-    assert np.all((chosen >= 0) & (chosen < Q))
-    if rank != 0:
-        return
-    value = qevals_step * args.steps / dt
-    peak, peak_src = measured_peak()
-    if args.shard == "questions":
-        par = "questions sharded over %d GPUs (Q/N rows of sA/mD each), exchange of the [B][Q] priority columns" % world
-        xbytes = int(B * Q * 8)
-    else:
-        par = ("targets sharded over %d GPUs (T/N columns of every sA/mD row each), two-phase evaluation: exchange of the "
-               "[B][Q][K] W_k partials, then of the [B][Q][2K+1] H/V/lack partials" % world)
-        xbytes = int(B * Q * (3 * K + 1) * 8)
-    per_gpu = qevals_step * (K + 1) * T * 8 / (dt / args.steps) / 1e9 / world
-    line = {
-        "metric": METRIC, "value": value, "unit": "questions/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "strong",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": args.workload, "Q": Q, "A": K, "T": T, "batch_total": B, "quiz_depths": list(DEPTHS),
-                   "kb": "binary_search_kb(init=0.1, rounds=3), filled on the device", "parallelism": par,
-                   "exchange": ("NCCL all-reduce via torch.distributed (host sync on both sides)" if args.exchange == "nccl" else
-                                "peer-memory stores from the kernel epilogues + device-side barrier (no host round trip)" +
-                                ("; exact-order pipeline of the Kahan lanes (W_k bit-exact across shards)"
-                                 if args.exact_order and args.shard == "targets" else "")),
-                   "l2": "inputs re-read every step; KB shard %.1f MB per GPU" % (shard_bytes / 1e6),
-                   "timing": "wall clock around the public sharded API (result D2H + host sync inside every step), max over ranks",
-                   "chosen_checksum": int(np.sum(chosen * (np.arange(B) + 1)) % 1000000007)},
-        "e2e": {"value": value, "unit": "questions/s", "h2d_bytes_per_step": int(B * 16), "d2h_bytes_per_step": int(B * 8),
-                "api": "sharded.%s.next_question_batch" % type(se).__name__, "exchanged_bytes_per_step_per_gpu": xbytes},
-        "gpu_launches": int(launches), "clocks": clocks,
-        "roofline": {"bound": "hbm", "achieved": per_gpu, "peak": peak, "unit": "GB/s", "frac": per_gpu / peak, "traffic": None,
-                     "peak_source": peak_src, "note": "per GPU, whole step (evaluation + exchange + selection), algorithmic bytes"},
-    }
-    print(json.dumps(line), flush=True)
+        peak, peak_src = measured_peak()
+        line = {"metric": METRIC, "value": res["value"], "unit": "questions/s", "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": args.workload, "Q": cfg["Q"], "A": cfg["K"], "T": cfg["T"], "batch_total": cfg["B"],
+                           "quiz_depths": list(DEPTHS), "kb": "binary_search_kb(init=0.1, rounds=3), filled on the device",
+                           "parallelism": "%s sharded over %d GPUs" % (res["axis"], world), "exchange": res["exchange"],
+                           "exact_order_pipeline": res["exact_order_pipeline"], "timing": res["timing"],
+                           "chosen_checksum": res["chosen_checksum"]},
+                "e2e": {"value": res["value"], "unit": "questions/s", "h2d_bytes_per_step": int(cfg["B"] * 16),
+                        "d2h_bytes_per_step": int(cfg["B"] * 8), "exchanged_bytes_per_step_per_gpu": res["exchange_bytes_per_step_per_gpu"]},
+                "gpu_launches": int(res["gpu_launches_per_step_per_gpu"] * args.steps), "clocks": res["clocks"],
+                "phases_ms": res["phases_ms"],
+                "roofline": {"bound": "hbm", "achieved": res["hbm_algorithmic_gbs_per_gpu"], "peak": peak, "unit": "GB/s",
+                             "frac": res["hbm_frac_per_gpu"], "traffic": None, "peak_source": peak_src,
+                             "note": "per GPU, whole step (evaluation + exchange + selection), algorithmic bytes"}}
+        print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
 
@@ -328,15 +526,7 @@ def bench_group(args, cfg, pqa, cores):
                                                        devices=[r % have for r in range(args.group)], exact_order=args.exact_order,
                                                        max_batch=B, emulated_workers=cores, rng_seed=1234, initial_quiz_capacity=B)
     eng.fill_binary_search_kb(3)
-    states = quiz_states(cfg, 0, B)
-    quizzes = eng.start_quiz_batch(B)
-    for s in range(max(DEPTHS)):
-        sel = [x for x in range(B) if len(states[x]) > s]
-        if not sel:
-            break
-        eng.set_active_question_batch(quizzes[sel], [states[x][s][0] for x in sel])
-        eng.record_answer_batch(quizzes[sel], [states[x][s][1] for x in sel])
-    qevals_step = int(sum(Q - len(pf) for pf in states))
+    quizzes, states, qevals_step = make_batch(eng, cfg, 0, B)
     randoms = np.random.default_rng(99).integers(0, 2 ** 64, size=B, dtype=np.uint64)
     for _ in range(args.warmup):
         chosen = eng.next_question_batch(quizzes, randoms)
@@ -391,10 +581,13 @@ def main():
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="sharded modes: how the shards exchange partial results (peer memory from the kernels, or NCCL)")
     ap.add_argument("--shard", default="quizzes", choices=["quizzes", "questions", "targets"],
-                    help="N>1: quizzes = KB replicated, batch sharded, no collective; questions = each rank holds Q/N "
-                         "questions, NCCL all-reduce of the per-question priorities (probqa_b200/sharded.py)")
+                    help="N>1 main line: quizzes = KB replicated, batch sharded, no collective (default; the sharded BASELINE "
+                         "config 4 leg is then embedded under \"sharded\"); questions / targets = that split as the main line")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-flush", action="store_true")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the extra legs of the default line (BASELINE configs 3, 4, 5, ncu traffic, sharded config 4)")
+    ap.add_argument("--traffic-child", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -411,6 +604,10 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the B200 engine has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
+    from probqa_b200 import engine as pqa
+    if args.traffic_child:
+        traffic_child(args, cfg, pqa)
+        return
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -436,13 +633,13 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
-    from probqa_b200 import engine as pqa
     Q, K, T, B = cfg["Q"], cfg["K"], cfg["T"], cfg["B"]
     cores = host_cores()
     if args.group > 1:
         return bench_group(args, cfg, pqa, cores)
     if args.shard in ("questions", "targets") and world > 1:
         return bench_sharded(args, cfg, pqa, dist, rank, world, local_rank, cores, barrier, max_over_ranks)
+    extras = not args.no_extras and args.workload == "1000x5x1000_b256" and args.kernel != 1
     eng = pqa.PqaEngineFactory().create_b200_engine(pqa.EngineDefinition(K, Q, T, init_amount=INIT), device=local_rank,
                                                     emulated_workers=cores, rng_seed=1234 + rank, initial_quiz_capacity=B)
     if Q * K * T * 8 > (1 << 30):
@@ -451,15 +648,7 @@ def main():
         eng.upload_kb(*synth.binary_search_kb(Q, K, T, INIT, 3))
     eng.set_eval_kernel(args.kernel, args.chunk_targets, args.quizzes_per_cta, args.lanes)
     # this rank's shard of the batch: quizzes rank*B .. rank*B+B-1 (weak scaling: B per GPU)
-    states = quiz_states(cfg, rank * B, B)
-    quizzes = eng.start_quiz_batch(B)
-    for s in range(max(DEPTHS)):
-        sel = [x for x in range(B) if len(states[x]) > s]
-        if not sel:
-            break
-        eng.set_active_question_batch(quizzes[sel], [states[x][s][0] for x in sel])
-        eng.record_answer_batch(quizzes[sel], [states[x][s][1] for x in sel])
-    qevals_step = int(sum(Q - len(pf) for pf in states))
+    quizzes, states, qevals_step = make_batch(eng, cfg, rank * B, B)
     rng = np.random.default_rng(99 + rank)
     randoms = rng.integers(0, 2 ** 64, size=B, dtype=np.uint64)
 
@@ -468,43 +657,21 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()     # nvidia-smi needs ~100 ms per sample: it runs from the warm-up to the end of the timed steps
-    for _ in range(args.warmup):
-        if not args.no_flush:
-            eng.flush_l2()
-        eng.resident_step()
-    eng.synchronize()
-    launches0 = eng.kernel_launch_count()
-    ev = [(pqa.DeviceEvent(), pqa.DeviceEvent()) for _ in range(args.steps)]
-    eval_ms = []
-    barrier()
-    for k in range(args.steps):
-        if not args.no_flush:
-            eng.flush_l2()
-        ev[k][0].record(eng)
-        eng.resident_step()
-        ev[k][1].record(eng)
-        eval_ms.append(eng.resident_last_eval_ms())
-    eng.synchronize()
-    barrier()
-    launches = eng.kernel_launch_count() - launches0
-    step_ms = [a.elapsed_ms(b) for a, b in ev]
-    total_ms = max_over_ranks(sum(step_ms))
-    clocks = sampler.stop() if rank == 0 else None
+        time.sleep(0.4)
+    r = resident_leg(pqa, eng, args.steps, args.warmup, not args.no_flush, barrier)
+    total_ms = max_over_ranks(r["total_ms"])
+    launches = r["launches"]
     chosen = eng.resident_fetch()
     assert np.all((chosen >= 0) & (chosen < Q))
     total_qevals = sum_over_ranks(qevals_step)
     value = total_qevals * args.steps / (total_ms * 1e-3)
-    eval_ms_avg = max_over_ranks(sum(eval_ms) / len(eval_ms))
+    eval_ms_avg = max_over_ranks(r["eval_ms"])
 
     # ---------------- end-to-end leg through the C-ABI batch call with host buffers
-    for _ in range(args.warmup):
-        eng.next_question_batch(quizzes, randoms)
+    t_e2e, out = e2e_leg(eng, quizzes, randoms, args.steps, args.warmup, barrier)
+    t_e2e = max_over_ranks(t_e2e)
     barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        out = eng.next_question_batch(quizzes, randoms)
-    t_e2e = max_over_ranks(time.perf_counter() - t0)
-    barrier()
+    clocks = sampler.stop() if rank == 0 else None
     assert np.array_equal(out, chosen), "resident and host-buffer paths chose different questions"
     e2e_value = total_qevals * args.steps / t_e2e
 
@@ -519,8 +686,11 @@ def main():
         for _ in range(n_calls):
             eng.next_question(q1)
         dt1 = time.perf_counter() - t0
+        peak1, _ = measured_peak()
         single = {"api": "PqaEngine_NextQuestion (one quiz per call)", "calls_per_s": n_calls / dt1, "us_per_call": 1e6 * dt1 / n_calls,
-                  "questions_per_s": (Q - len(states[0])) * n_calls / dt1}
+                  "questions_per_s": (Q - len(states[0])) * n_calls / dt1,
+                  "hbm_frac": (Q - len(states[0])) * (K + 1) * T * 8 / (dt1 / n_calls) / 1e9 / peak1,
+                  "hbm_frac_note": "algorithmic bytes of one call ((K+1)*T*8 per unasked question) / wall time of the whole call / HBM peak"}
         # the same entry point from many client threads at once (the engine combines pending calls into one launch)
         import threading
         n_thr, per_thr = min(64, B), 100
@@ -537,19 +707,35 @@ def main():
         dtm = time.perf_counter() - t0
         single.update(threads=n_thr, threaded_calls_per_s=n_thr * per_thr / dtm,
                       threaded_questions_per_s=sum(Q - len(states[x]) for x in range(n_thr)) * per_thr / dtm)
+    eng.close()
 
+    # ---------------------------------------------------------------- extra legs (default line only)
+    sharded_res = config4_1gpu = None
+    if extras and world > 1:
+        # BASELINE config 4 as north_star partitions it: targets sharded over the job's GPUs, peer-memory exchange; the
+        # exact-order pipeline (single-engine parity bar) first, the summed-partials exchange beside it
+        sharded_res = sharded_leg(args, "10000x5x100000_b64", pqa, dist, rank, world, local_rank, cores, barrier, max_over_ranks,
+                                  "targets", "p2p", [True, False], 10, 5)
+    if extras and rank == 0:
+        # the same workload on ONE GPU (the whole 48 GB KB + its derived form on one B200): the strong-scaling base, measured
+        # in the same job on the same box
+        config4_1gpu = extra_workload(pqa, "10000x5x100000_b64", cores, 5, 3, device=local_rank)
+        if sharded_res:
+            for s_ in sharded_res:
+                s_["one_gpu_same_job"] = {"value": config4_1gpu["value"], "ms_per_step": config4_1gpu["ms_per_step"],
+                                          "e2e_value": config4_1gpu["e2e_value"]}
+                s_["speedup_vs_1gpu"] = s_["value"] / config4_1gpu["e2e_value"]
+                s_["speedup_note"] = "sharded value (host-buffer API, wall clock) / one-GPU e2e_value (host-buffer API) of the same workload, same job"
+    barrier()
     if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
         return
     peak, peak_src = measured_peak()
-    traffic = None   # physical DRAM bytes per launch from the committed ncu --set full capture of this workload
-    try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_eval_traffic.json")))
-        if tj["workload"] == args.workload and args.kernel != 1:
-            traffic = tj["dram_bytes_read_per_launch"] + tj["dram_bytes_write_per_launch"]
-    except Exception:
-        pass
+    traffic = measure_traffic(args) if (extras and world == 1) else None
     alg_bytes = qevals_step * (K + 1) * T * 8           # per launch of the evaluation kernel on one GPU
     achieved = alg_bytes / (eval_ms_avg * 1e-3) / 1e9
+    sm_mhz = (clocks or {}).get("sm_mhz")
     line = {
         "metric": METRIC, "value": value, "unit": "questions/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -565,14 +751,32 @@ def main():
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "kernel": "k_eval_staged" if args.kernel != 1 else "k_eval_exact",
+                     "traffic": traffic["dram_bytes"] if traffic else None,
+                     "traffic_detail": traffic,
+                     "kernel": "k_eval_staged" if args.kernel != 1 else "k_eval_exact",
                      "kernel_ms": eval_ms_avg, "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
+                     "fp64": fp64_roofline(qevals_step, K, T, eval_ms_avg, sm_mhz,
+                                           measured_warp_instr=(traffic or {}).get("fp64_warp_instr")) if args.kernel != 1 else None,
                      "note": "algorithmic bytes are counted per quiz ((K+1)*T*8 per evaluated question, SURVEY 8d); the slab is "
-                             "staged once per CTA and shared by its quizzes, so physical DRAM traffic is far lower and the "
-                             "kernel is bound by fp64 issue, see DESIGN.md"},
+                             "staged once per CTA and shared by its quizzes, so physical DRAM traffic (`traffic`, one ncu replay "
+                             "of this workload) is far lower and the kernel is bound by fp64 issue: `fp64` is the binding roofline"},
     }
     if single is not None:
         line["single_quiz"] = single
+    if sharded_res is not None:
+        line["sharded"] = sharded_res[0]
+        line["sharded_summed_partials"] = sharded_res[1]
+    if config4_1gpu is not None:
+        line["config4_1gpu"] = config4_1gpu
+    if extras and world == 1:
+        try:
+            line["config3"] = extra_workload(pqa, "10000x5x10000_b1024", cores, 5, 3)
+        except Exception as ex:
+            line["config3"] = {"error": repr(ex)}
+        try:
+            line["config5_train"] = train_workload(pqa, cores)
+        except Exception as ex:
+            line["config5_train"] = {"error": repr(ex)}
     if not args.no_cpu_baseline and world == 1:
         try:
             line["cpu_baseline"] = cpu_baseline(cfg)
