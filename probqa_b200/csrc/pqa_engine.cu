@@ -98,6 +98,14 @@ Engine::Engine(const CiEngineDefinition &def, const CiB200Options &opts) {
   launch_fill_kb(kb(), initSqr, initSqr * (double)K_, initAmount_, stream_);
   if (IsTargetSharded()) launch_fill_kb(kbQuiz(), initSqr, initSqr * (double)K_, initAmount_, stream_);   // full-length vB
   EnsureQuizCapacity(opts._initialQuizCapacity > 0 ? opts._initialQuizCapacity : 256);
+  if (K_ <= 8) {      // the derived KB of the throughput kernels (kbEval): allocated now, built at the first evaluation
+    size_t nR = 0, nL = 0;
+    derived_kb_doubles(kb(), &nR, &nL);
+    PQA_CU(cudaMalloc(&dDerR_, sizeof(double) * nR));
+    PQA_CU(cudaMalloc(&dDerL_, sizeof(double) * nL));
+    derCapR_ = nR; derCapL_ = nL;
+    dDerList_.ensure((size_t)qLocal_, stream_); hDerList_.ensure((size_t)qLocal_);
+  }
   PQA_CU(cudaGetLastError()); PQA_CU(cudaStreamSynchronize(stream_));
 }
 
@@ -137,6 +145,7 @@ Engine::~Engine() {
   }
   cudaFree(dSA_); cudaFree(dMD_); cudaFree(dVB_); cudaFree(dLog2Tbl_);
   cudaFree(dDerR_); cudaFree(dDerL_);
+  if (hFew_) cudaFreeHost((void *)hFew_);
   cudaFree(dPriors_); cudaFree(dLogPriors_); cudaFree(dAsked_); cudaFree(dActive_);
   for (int r = 0; r < kMaxPeers; r++) if (p2pOpened_[r]) cudaIpcCloseMemHandle(p2pPeer_[r]);
   if (p2pInbox_) cudaFree(p2pInbox_);
@@ -171,6 +180,9 @@ DeviceKB Engine::kbEval() {
   size_t nR = 0, nL = 0;
   derived_kb_doubles(kb(), &nR, &nL);
   if (nR > derCapR_ || nL > derCapL_ || !dDerR_) {
+    // Normally allocated by the constructor: allocations and frees synchronise the device, which must not happen while
+    // another shard engine of this process spins in an exchange barrier on the same GPU. Only a KB that grew in maintenance
+    // mode (single engines only) comes through here.
     PQA_CU(cudaStreamSynchronize(stream_));
     if (dDerR_) cudaFree(dDerR_);
     if (dDerL_) cudaFree(dDerL_);
@@ -178,16 +190,17 @@ DeviceKB Engine::kbEval() {
     PQA_CU(cudaMalloc(&dDerR_, sizeof(double) * nR));
     PQA_CU(cudaMalloc(&dDerL_, sizeof(double) * nL));
     derCapR_ = nR; derCapL_ = nL;
+    dDerList_.ensure((size_t)qLocal_, stream_); hDerList_.ensure((size_t)qLocal_);
     derAllDirty_ = true;
   }
   if (derAllDirty_) {
     launch_build_derived(kb(), nullptr, 0, stream_);
   } else if (!derDirtyList_.empty()) {
     const int64_t nd = (int64_t)derDirtyList_.size();
-    // the previous rebuild may still be reading the list: stream order protects the device buffer, the copy below is from
-    // pageable host memory and therefore staged before cudaMemcpyAsync returns
-    dDerList_.ensure((size_t)nd, stream_);
-    PQA_CU(cudaMemcpyAsync(dDerList_.get(), derDirtyList_.data(), sizeof(int64_t) * (size_t)nd, cudaMemcpyHostToDevice, stream_));
+    dDerList_.ensure((size_t)nd, stream_); hDerList_.ensure((size_t)nd);      // both sized for qLocal_ at creation
+    PQA_CU(cudaStreamSynchronize(stream_));      // an earlier rebuild may still be reading the pinned list
+    std::memcpy(hDerList_.get(), derDirtyList_.data(), sizeof(int64_t) * (size_t)nd);
+    PQA_CU(cudaMemcpyAsync(dDerList_.get(), hDerList_.get(), sizeof(int64_t) * (size_t)nd, cudaMemcpyHostToDevice, stream_));
     launch_build_derived(kb(), dDerList_.get(), nd, stream_);
   }
   for (int64_t q : derDirtyList_) derDirtyMark_[(size_t)q] = 0;
@@ -425,7 +438,44 @@ PqaError *Engine::NextQuestionBatch(int64_t n, const int64_t *pQuizIds, const ui
     valid.push_back(pQuizIds[x]); where.push_back(x);
   }
   const int64_t m = (int64_t)valid.size();
-  if (m > 0) {
+  if (m > 0 && UseFewPath(m)) {
+    // The reference ABI's shape (one quiz per call, or the handful a combiner round collects): one fused launch, ids and
+    // draws by value, results through mapped host memory (k_eval_few, pqa_eval_staged.cu).
+    EnsureFewResources();
+    uint64_t rnd[8];
+    for (int64_t x = 0; x < m; x++) rnd[x] = pRandoms ? pRandoms[where[x]] : NextRandom();
+    dPriority_.ensure((size_t)(m * Q_), stream_); dRunLength_.ensure((size_t)(m * Q_), stream_);
+    const uint64_t seq = ++fewSeq_;
+    launch_eval_few_select(kbEval(), pool(), (int)m, valid.data(), rnd, W_, dPriority_.get(), dRunLength_.get(),
+                           dFewTickets_.get(), (int64_t *)dFewHost_, (uint64_t *)dFewHost_ + 4, seq, nullptr, stream_);
+    PQA_CU(cudaGetLastError());
+    volatile uint64_t *seen = (volatile uint64_t *)hFew_ + 4;
+    for (uint64_t spins = 0; *seen != seq; spins++) {
+      if ((spins & 0xFFF) == 0xFFF) {          // every few microseconds: has the stream died or finished without an answer?
+        const cudaError_t qe = cudaStreamQuery(stream_);
+        if (qe == cudaSuccess) { if (*seen == seq) break; throw CudaFail((int)cudaErrorUnknown, "k_eval_few finished without publishing its result", __FILE__, __LINE__); }
+        if (qe != cudaErrorNotReady) PQA_CU(qe);
+      }
+#if defined(__x86_64__)
+      __builtin_ia32_pause();
+#endif
+    }
+    uint64_t nAsked = 0;
+    for (int64_t x = 0; x < m; x++) {
+      const int64_t qst = ((volatile int64_t *)hFew_)[x];
+      if (qst < 0) {  // CpuEngine.cpp:407-411
+        PqaError *e = MakeError(ErrCode::QuestionsExhausted, PQA_FILE_LINE "Found no unasked question that is not in a gap.");
+        if (ppErrors) ppErrors[where[x]] = e;
+        else if (!firstErr) firstErr = e;
+        else delete e;
+        continue;
+      }
+      pQuestions[where[x]] = qst;
+      quizzes_[valid[x]].activeQuestion = qst;  // :412
+      nAsked++;                                  // :413
+    }
+    nQuestionsAsked_.fetch_add(nAsked, std::memory_order_relaxed);
+  } else if (m > 0) {
     UploadIds(m, valid.data());
     hRandoms_.ensure(m); dRandoms_.ensure(m, stream_);
     for (int64_t x = 0; x < m; x++) hRandoms_.get()[x] = pRandoms ? pRandoms[where[x]] : NextRandom();
@@ -567,6 +617,9 @@ void Engine::RunCombined(const std::vector<CallSlot *> &batch) {
   for (CallSlot *c : batch) if (c->kind == 1) {
     PqaError *e;
     { std::lock_guard<std::mutex> lk(mu_); DeviceScope devScope(device_); e = ValidateRecordAnswer(1, &c->quiz, &c->arg); }
+    if (!e && std::find(ids.begin(), ids.end(), c->quiz) != ids.end())   // two clients answering one quiz at once: the second
+      e = ErrNoQuizActiveQuestion(c->arg, PQA_FILE_LINE "An attempt to record an answer in a quiz that doesn't"   // one loses, as serially
+                                          " have an active question");
     if (e) { c->err = e; continue; }
     ids.push_back(c->quiz); args.push_back(c->arg); who.push_back(c);
   }
@@ -677,6 +730,16 @@ PqaError *Engine::ValidateRecordAnswer(int64_t n, const int64_t *pQuizIds, const
     if (q.activeQuestion < 0 || q.activeQuestion >= Q_)
       return ErrNoQuizActiveQuestion(pAnswers[x], PQA_FILE_LINE "An attempt to record an answer in a quiz that has"
                                                   " invalid active question");
+  }
+  // The same quiz twice in one launch: the first answer consumes the active question (CEQuiz.h:92), so the second call
+  // is what the reference fails with NoQuizActiveQuestion -- and two CTAs must never update one quiz slot concurrently.
+  if (n > 1) {
+    std::vector<int64_t> sorted(pQuizIds, pQuizIds + n);
+    std::sort(sorted.begin(), sorted.end());
+    const auto dup = std::adjacent_find(sorted.begin(), sorted.end());
+    if (dup != sorted.end())
+      return ErrNoQuizActiveQuestion(*dup, PQA_FILE_LINE "An attempt to record an answer in a quiz that doesn't"
+                                           " have an active question (the same quiz appears twice in one batch)");
   }
   return nullptr;
 }
@@ -1204,6 +1267,19 @@ PqaError *Engine::SetEvalKernel(int32_t which, int64_t chunkTargets, int64_t qui
   return nullptr;
 }
 
+bool Engine::UseFewPath(int64_t n) const {
+  return n <= eval_few_max() && !IsSharded() && K_ <= 8 && evalCfg_.which != 1 && evalCfg_.kahanLanesPerThread == 0 &&
+         evalCfg_.chunkTargets == 0;
+}
+void Engine::EnsureFewResources() {
+  if (hFew_) return;
+  PQA_CU(cudaHostAlloc((void **)&hFew_, sizeof(int64_t) * 8, cudaHostAllocMapped));
+  std::memset((void *)hFew_, 0, sizeof(int64_t) * 8);
+  PQA_CU(cudaHostGetDevicePointer(&dFewHost_, (void *)hFew_, 0));
+  dFewTickets_.ensure((size_t)eval_few_ticket_count(), stream_);
+  PQA_CU(cudaMemsetAsync(dFewTickets_.get(), 0, sizeof(unsigned) * (size_t)eval_few_ticket_count(), stream_));
+}
+
 PqaError *Engine::EvalQuestions(int64_t n, const int64_t *pQuizIds, double *pPriorities, double *pRunLength,
                                 double *pGrandTotals, int64_t *pnChunks) {
   if (n <= 0) return ErrNegativeCount(n, PQA_FILE_LINE "|n| must be positive.");
@@ -1217,10 +1293,17 @@ PqaError *Engine::EvalQuestions(int64_t n, const int64_t *pQuizIds, double *pPri
   if (pnChunks) *pnChunks = nChunks;
   dPriority_.ensure((size_t)(n * Q_), stream_); dRunLength_.ensure((size_t)(n * Q_), stream_);
   dGrand_.ensure((size_t)(n * nChunks), stream_);
-  EvalDetail det{nullptr, nullptr, nullptr, nullptr};
-  launch_eval_questions(kbEval(), pool(), n, dIds_.get(), dPriority_.get(), det, evalCfg_, stream_);
-  launch_select_question(kbQuiz(), pool(), n, dIds_.get(), dPriority_.get(), nullptr, W_, dRunLength_.get(), dGrand_.get(),
-                         nullptr, 0, stream_);
+  if (UseFewPath(n)) {     // the kernel one-quiz NextQuestion calls run on, evaluation only
+    EnsureFewResources();
+    const uint64_t noDraws[8] = {};
+    launch_eval_few_select(kbEval(), pool(), (int)n, pQuizIds, noDraws, W_, dPriority_.get(), dRunLength_.get(),
+                           dFewTickets_.get(), nullptr, nullptr, 0, dGrand_.get(), stream_);
+  } else {
+    EvalDetail det{nullptr, nullptr, nullptr, nullptr};
+    launch_eval_questions(kbEval(), pool(), n, dIds_.get(), dPriority_.get(), det, evalCfg_, stream_);
+    launch_select_question(kbQuiz(), pool(), n, dIds_.get(), dPriority_.get(), nullptr, W_, dRunLength_.get(), dGrand_.get(),
+                           nullptr, 0, stream_);
+  }
   if (pPriorities) PQA_CU(cudaMemcpyAsync(pPriorities, dPriority_.get(), sizeof(double) * (size_t)(n * Q_), cudaMemcpyDeviceToHost, stream_));
   if (pRunLength) PQA_CU(cudaMemcpyAsync(pRunLength, dRunLength_.get(), sizeof(double) * (size_t)(n * Q_), cudaMemcpyDeviceToHost, stream_));
   if (pGrandTotals) PQA_CU(cudaMemcpyAsync(pGrandTotals, dGrand_.get(), sizeof(double) * (size_t)(n * nChunks), cudaMemcpyDeviceToHost, stream_));

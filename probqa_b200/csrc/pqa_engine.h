@@ -286,6 +286,8 @@ class Engine {
   // kb() for an evaluation launch: first brings the derived KB (pqa_eval_staged.cu) up to date with sA / mD -- all of it
   // after an upload / fill / load / resize / gap change, the touched questions after a Train / RecordQuizTarget.
   DeviceKB kbEval();
+  bool UseFewPath(int64_t n) const;       // the fused one-launch NextQuestion of 1 .. eval_few_max() quizzes applies
+  void EnsureFewResources();
   void MarkKBChanged() { derAllDirty_ = true; derDirtyList_.clear(); }
   void MarkQuestionsChanged(const std::vector<TrainOp> &ops);
   QuizPool pool() const;
@@ -343,6 +345,7 @@ class Engine {
   std::vector<int64_t> derDirtyList_;      // local question indices touched since the last rebuild (unique)
   std::vector<uint8_t> derDirtyMark_;
   DevBuf<int64_t> dDerList_;
+  PinBuf<int64_t> hDerList_;
   // quiz pool
   int64_t quizCap_ = 0;
   double *dPriors_ = nullptr, *dLogPriors_ = nullptr;
@@ -362,6 +365,12 @@ class Engine {
   PinBuf<uint64_t> hRandoms_;
   PinBuf<CiRatedTarget> hTop_;
   PinBuf<double> hRow_;
+
+  // one-quiz fused path: mapped host memory {int64 questions[4]; uint64 seq; ...}, ticket counters, call sequence number
+  volatile void *hFew_ = nullptr;
+  void *dFewHost_ = nullptr;
+  DevBuf<unsigned> dFewTickets_;
+  uint64_t fewSeq_ = 0;
 
   // resident batch
   int64_t residentN_ = 0;

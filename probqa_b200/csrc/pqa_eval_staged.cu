@@ -36,6 +36,7 @@
 //    across chunks), then pass 2 (R and L).
 #include "pqa_kernels.cuh"
 #include "pqa_device.cuh"
+#include "pqa_select.cuh"
 
 #include <atomic>
 #include <math.h>
@@ -369,28 +370,35 @@ __device__ __forceinline__ void finish_pass1(const Kahan (&kw)[KL][K], double (&
 // Per (quiz, question) epilogue: CEEvalQsSubtaskConsider.cpp:134-207. H holds sum post*log2 post (negative), L the
 // lack sum (negative), V the squared distances.
 template <int K>
-__device__ __forceinline__ void write_priority(const StagedParams &P, int64_t i, int64_t b, const double (&W)[K],
-                                               const double (&H)[K], const double (&V)[K], double L) {
-  const int64_t o = b * P.kb.Q + i;
+__device__ __forceinline__ double priority_value(int64_t nValidTargets, const double (&W)[K], const double (&H)[K],
+                                                 const double (&V)[K], double L) {
   double totW = 0.0, sumH = 0.0, sumV = 0.0;
 #pragma unroll
   for (int k = 0; k < K; k++) {
     totW += W[k];                                                       // :89,:134
     sumH = __fma_rn(W[k], -H[k], sumH);                                 // :148-172
     sumV = __fma_rn(W[k], sqrt(V[k]), sumV);
-    if (P.det.W) P.det.W[o * K + k] = W[k];
-    if (P.det.H) P.det.H[o * K + k] = -H[k];
-    if (P.det.V) P.det.V[o * K + k] = V[k];
   }
   const double avgH = sumH / totW, avgV = sumV / totW;                  // :176-177
   const double nExp = exp2(avgH);                                       // :181
   const double cLnMaxV = 0.34657359027997265470861606072909;            // SRMath::_cLnSqrt2
   const double lnV = (avgV == 0) ? -746.0 : log(avgV);                  // :27-29
-  const double n1 = (double)(P.kb.nValidTargets + 1);
+  const double n1 = (double)(nValidTargets + 1);
   const double vComp = 1.0 / (cLnMaxV - lnV + cLnMaxV / (n1 * n1));     // :30-33
-  const double lack = -L;                                               // :201
-  store_priority(P, o, lack * pow(vComp, 9.0) * pow(nExp, -2.0));       // :207
-  if (P.det.lack) P.det.lack[o] = lack;
+  return -L * pow(vComp, 9.0) * pow(nExp, -2.0);                        // :201, :207
+}
+template <int K>
+__device__ __forceinline__ void write_priority(const StagedParams &P, int64_t i, int64_t b, const double (&W)[K],
+                                               const double (&H)[K], const double (&V)[K], double L) {
+  const int64_t o = b * P.kb.Q + i;
+#pragma unroll
+  for (int k = 0; k < K; k++) {
+    if (P.det.W) P.det.W[o * K + k] = W[k];
+    if (P.det.H) P.det.H[o * K + k] = -H[k];
+    if (P.det.V) P.det.V[o * K + k] = V[k];
+  }
+  store_priority(P, o, priority_value<K>(P.kb.nValidTargets, W, H, V, L));
+  if (P.det.lack) P.det.lack[o] = -L;
 }
 
 template <int KL> __device__ __forceinline__ double quiz_sum(double v) {
@@ -709,6 +717,185 @@ __global__ void __launch_bounds__(SW * 32, 2) k_eval_small(const StagedParams P)
       write_priority<K>(P, i, b0 + warp, W, H, V, L);
     }
     __syncthreads();   // sWk / sPart / sSlot are rewritten by the next round
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// One to four quizzes per call -- the shape of the reference ABI's PqaEngine_NextQuestion -- is a latency problem: the
+// reference's W_k is a serial chain of T/4 Kahan steps per (answer, lane) (~4.6 us of dependent fp64 adds at T = 1000)
+// and nothing can shorten it, so everything else is arranged around it. One CTA per question, every question of the KB
+// in flight at once (no shared-memory slab: the derived KB streams from L2 with coalesced loads, eight CTAs per SM); warp
+// w runs the 4K chains of quiz w; then all threads take the elementwise pass of each quiz; the last CTA to finish a quiz
+// (a ticket counter) runs the selection of CpuEngine::NextQuestionSpec right there, and the chosen questions go to mapped
+// host memory followed by a sequence word the caller polls: ONE launch, no copy, no stream synchronisation.
+constexpr int kFewMax = 4;                 // quizzes per launch = warps per CTA
+constexpr int kFewGroups = 32;             // first-level ticket counters per quiz (1000 same-address atomics would serialise)
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+struct FewParams {
+  DeviceKB kb;
+  QuizPool qp;
+  int n;
+  int64_t slots[kFewMax];
+  uint64_t randoms[kFewMax];
+  double *priority;          // [n][Q]
+  double *runLength;         // [n][Q]
+  unsigned *tickets;         // [kFewMax][kFewGroups + 1] + 1 counters zeroed at creation; each is reset by its last incrementer
+  int64_t *hostQuestions;    // mapped pinned host memory [kFewMax]
+  uint64_t *hostSeq;         // mapped pinned host memory: receives `seq` after the questions
+  uint64_t seq;
+  int W;
+  int setActive;             // 1: NextQuestion (the quiz' active question is set); 0: evaluation only (inspection)
+  double *grandOut;          // optional [n][nChunks] grand totals (inspection)
+};
+
+template <int K>
+__global__ void __launch_bounds__(kFewMax * 32, 7) k_eval_few(const FewParams P) {
+  constexpr int THREADS = kFewMax * 32;
+  constexpr int NV = 2 * K + 1;
+  extern __shared__ double sGrand[];                      // selection scratch (nChunks doubles), last CTA of a quiz only
+  __shared__ double sW[kFewMax][3][K];                    // W_k, 1/W_k, log2 W_k per quiz
+  __shared__ double sPart[kFewMax][NV];                   // per-warp partial sums of the quiz in flight
+  __shared__ int sLast;
+  const int64_t iLocal = blockIdx.x, i = P.kb.qFirst + iLocal, Q = P.kb.Q, Tp = P.kb.Tp, T = P.kb.T, nV = Tp >> 2;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const double qnan = __longlong_as_double(0x7FF8000000000000ll);
+  const double *__restrict__ gR = P.kb.dR + iLocal * nV * (K * 4);
+  const double *__restrict__ gL = P.kb.dL + iLocal * nV * ((K + 1) * 4);
+  const bool qgap = bit32(P.kb.qgaps, i);
+  // ---- pass 1: warp w <-> quiz w, lane 4k + l <-> Kahan lane l of answer k
+  bool liveW = false;
+  if (warp < P.n && !qgap) {
+    const int64_t slot = P.slots[warp];
+    liveW = !bit64(P.qp.asked + slot * P.qp.askedWords, i);
+    if (liveW && lane < 4 * K) {
+      const int k = lane >> 2, l = lane & 3;
+      const double *rk = gR + k * 4 + l;
+      const double *__restrict__ prl = P.qp.priors + slot * Tp + l;
+      Kahan kw; kw.init();
+      // The chain advances one vector per ~36 cycles (4 dependent adds); an L2 hit takes ~250. Lines are therefore pulled
+      // into L1 kPf vectors ahead with prefetch instructions (no registers), and the loads proper hit L1.
+      constexpr int kPf = 24;
+      for (int v = 0; v < kPf && v < (int)nV; v++) prefetch_l1(rk + v * (4 * K));
+      int v = 0;
+      for (; v + 4 <= (int)nV; v += 4) {
+        double r[4], p[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          if (v + u + kPf < (int)nV) prefetch_l1(rk + (v + u + kPf) * (4 * K));   // the warp's 4K lanes cover the vector's lines
+          r[u] = __ldg(rk + (v + u) * (4 * K)); p[u] = __ldg(prl + 4 * (v + u));
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) kw.add(__dmul_rn(r[u], p[u]));       // :81-86
+      }
+      for (; v < (int)nV; v++) kw.add(__dmul_rn(__ldg(rk + v * (4 * K)), __ldg(prl + 4 * v)));
+      const double w = group_precise_sum(kw);                            // :88
+      if (l == 0) { sW[warp][0][k] = w; sW[warp][1][k] = __ddiv_rn(1.0, w); sW[warp][2][k] = log2(w); }
+    }
+  }
+  __syncthreads();
+  // ---- pass 2 and epilogue, quiz by quiz, all threads over the targets
+  for (int b = 0; b < P.n; b++) {
+    const int64_t slot = P.slots[b];
+    const int64_t o = (int64_t)b * Q + i;
+    const bool live = !qgap && !bit64(P.qp.asked + slot * P.qp.askedWords, i);     // CTA-uniform
+    if (live) {
+      const double *__restrict__ pr = P.qp.priors + slot * Tp;
+      const double *__restrict__ lpr = P.qp.logPriors + slot * Tp;
+      double H[K], V[K], L = 0.0;
+#pragma unroll
+      for (int k = 0; k < K; k++) { H[k] = 0.0; V[k] = 0.0; }
+      for (int j = threadIdx.x; j < (int)T; j += THREADS) {
+        const int vb = j >> 2, l = j & 3;
+        const double *rj = gR + vb * (4 * K) + l, *lj = gL + vb * (4 * (K + 1)) + l;
+        if (j + 2 * THREADS < (int)T && l == 0) {        // the slab lines of the iteration after next, one request per vector
+          const double *rn = rj + (2 * THREADS / 4) * (4 * K), *ln = lj + (2 * THREADS / 4) * (4 * (K + 1));
+          prefetch_l1(rn); prefetch_l1(rn + 16); if (K > 4) prefetch_l1(rn + 4 * K - 1);
+          prefetch_l1(ln); prefetch_l1(ln + 16); prefetch_l1(ln + 4 * (K + 1) - 1);
+        }
+        const double p = __ldg(pr + j), lp = __ldg(lpr + j), id2 = __ldg(lj + 4 * K);
+        double post[K], l2[K];
+        bool allFast = true;
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+          post[k] = __dmul_rn(__dmul_rn(__ldg(rj + 4 * k), p), sW[b][1][k]);   // :81-82, :97
+          l2[k] = __dsub_rn(__dadd_rn(__ldg(lj + 4 * k), lp), sW[b][2][k]);
+          allFast = allFast & in_fast_range(post[k]);
+          const double d = __dsub_rn(post[k], p);                        // :119
+          V[k] = __fma_rn(d, d, V[k]);                                   // :126-127
+        }
+        if (allFast) {
+          double nn = __dadd_rn(l2[0], l2[1]), dd = __dmul_rn(l2[0], l2[1]);
+#pragma unroll
+          for (int k = 0; k < K; k++) H[k] = __fma_rn(post[k], l2[k], H[k]);   // :113-114
+#pragma unroll
+          for (int k = 2; k < K; k++) { nn = __fma_rn(nn, l2[k], dd); dd = __dmul_rn(dd, l2[k]); }
+          L = __fma_rn(id2, __dmul_rn(nn, fast_rcp(dd)), L);             // :116-117
+        } else {
+#pragma unroll
+          for (int k = 0; k < K; k++) {
+            double x = l2[k], rx;
+            if (in_fast_range(post[k])) rx = fast_rcp(x);
+            else x = slow_log2(post[k], P.kb.log2tbl, &rx);
+            H[k] = __fma_rn(post[k], x, H[k]);
+            L = __fma_rn(id2, rx, L);
+          }
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < K; k++) {
+        const double h = warp_sum(H[k]), vv = warp_sum(V[k]);
+        if (lane == 0) { sPart[warp][k] = h; sPart[warp][K + k] = vv; }
+      }
+      L = warp_sum(L);
+      if (lane == 0) sPart[warp][2 * K] = L;
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        double W[K], Hs[K], Vs[K], Ls = 0.0;
+#pragma unroll
+        for (int k = 0; k < K; k++) { W[k] = sW[b][0][k]; Hs[k] = 0.0; Vs[k] = 0.0; }
+        for (int w = 0; w < kFewMax; w++) {
+#pragma unroll
+          for (int k = 0; k < K; k++) { Hs[k] = __dadd_rn(Hs[k], sPart[w][k]); Vs[k] = __dadd_rn(Vs[k], sPart[w][K + k]); }
+          Ls = __dadd_rn(Ls, sPart[w][2 * K]);
+        }
+        P.priority[o] = priority_value<K>(P.kb.nValidTargets, W, Hs, Vs, Ls);
+      }
+    } else if (threadIdx.x == 0) {
+      P.priority[o] = qnan;                                              // CEEvalQsSubtaskConsider.cpp:54-58
+    }
+    // ---- the last CTA of this quiz selects its question
+    if (threadIdx.x == 0) {
+      // two-level ticket: CTA x counts in group x % nG; the last of a group counts at the top; the last there is the last
+      __threadfence();
+      const unsigned nG = gridDim.x < (unsigned)kFewGroups ? gridDim.x : (unsigned)kFewGroups;
+      const unsigned g = blockIdx.x % nG, groupSize = (gridDim.x - g + nG - 1) / nG;
+      unsigned *cnt = P.tickets + b * (kFewGroups + 1);
+      int last = 0;
+      if (atomicAdd(cnt + g, 1u) + 1u == groupSize) {
+        cnt[g] = 0u;
+        __threadfence();
+        if (atomicAdd(cnt + kFewGroups, 1u) + 1u == nG) { cnt[kFewGroups] = 0u; last = 1; }
+      }
+      sLast = last;
+    }
+    __syncthreads();
+    if (sLast) {                                                         // CTA-uniform
+      __threadfence();
+      const int64_t nChunks = split_count(Q, (int64_t)P.W * 8);
+      const int64_t chosen = select_question_cta(P.kb, P.qp, slot, P.priority + (int64_t)b * Q, P.randoms[b], P.W,
+                                                 P.runLength + (int64_t)b * Q, P.grandOut ? P.grandOut + b * nChunks : nullptr,
+                                                 P.hostQuestions != nullptr, P.setActive, sGrand);
+      if (threadIdx.x == 0 && P.hostQuestions) {
+        P.hostQuestions[b] = chosen;
+        __threadfence_system();
+        unsigned *done = P.tickets + kFewMax * (kFewGroups + 1);
+        if (atomicAdd(done, 1u) + 1u == (unsigned)P.n) {                 // every quiz of the call has its question
+          *done = 0u;
+          *reinterpret_cast<volatile uint64_t *>(P.hostSeq) = P.seq;
+        }
+      }
+    }
+    __syncthreads();       // sPart / sLast / sGrand are reused by the next quiz
   }
 }
 
@@ -1083,6 +1270,21 @@ static void launch_k(const StagedParams &P, const EvalConfig &cfg, size_t smem, 
   else launch_cfg<K, 1, 8>(P, cfg, smem, st);
 }
 
+int eval_few_max() { return kFewMax; }
+int eval_few_ticket_count() { return kFewMax * (kFewGroups + 1) + 1; }
+void launch_eval_few_select(const DeviceKB &kb, const QuizPool &qp, int n, const int64_t *slots, const uint64_t *randoms, int W,
+                            double *dPriority, double *dRunLength, unsigned *dTickets, int64_t *hostQuestions,
+                            uint64_t *hostSeq, uint64_t seq, double *dGrand, cudaStream_t st) {
+  FewParams P;
+  P.kb = kb; P.qp = qp; P.n = n; P.priority = dPriority; P.runLength = dRunLength; P.tickets = dTickets;
+  P.hostQuestions = hostQuestions; P.hostSeq = hostSeq; P.seq = seq; P.W = W;
+  P.setActive = hostQuestions != nullptr; P.grandOut = dGrand;
+  for (int x = 0; x < kFewMax; x++) { P.slots[x] = x < n ? slots[x] : 0; P.randoms[x] = x < n ? randoms[x] : 0; }
+  const size_t smem = sizeof(double) * (size_t)select_chunk_count(kb.Q, W);
+  PQA_K_SWITCH(kb.K, (k_eval_few<KK><<<(unsigned)kb.qCount, kFewMax * 32, smem, st>>>(P)))
+  count_launch();
+}
+
 void launch_eval_staged(const DeviceKB &kb, const QuizPool &qp, int64_t n, const int64_t *dSlots, double *dPriority,
                         const EvalDetail &det, const EvalConfig &cfg, cudaStream_t st) {
   if (kb.K > 8) {  // more answer options than the register tile covers: use the exact kernel
@@ -1108,6 +1310,7 @@ template <int K> static void preload_staged_k() {
   cudaFuncGetAttributes(&a, k_eval_staged<K, 2, 8>);
   cudaFuncGetAttributes(&a, k_eval_staged<K, 4, 4>);
   cudaFuncGetAttributes(&a, k_eval_small<K, 8>);
+  cudaFuncGetAttributes(&a, k_eval_few<K>);
   cudaFuncGetAttributes(&a, k_eval_staged<K, 2, 4>);
   cudaFuncGetAttributes(&a, k_eval_tshard<K, 2, 4, 1>);
   cudaFuncGetAttributes(&a, k_eval_tshard<K, 2, 8, 1>);

@@ -4,6 +4,7 @@
 // Citations are relative to /root/reference/ProbQA/. Built with -fmad=false: every fused multiply-add is explicit.
 #include "pqa_kernels.cuh"
 #include "pqa_device.cuh"
+#include "pqa_select.cuh"
 
 #include <atomic>
 #include <limits.h>
@@ -118,6 +119,7 @@ __global__ void __launch_bounds__(256) k_update_priors(DeviceKB kb, QuizPool qp,
   int64_t q = -1;
   if (MODE == 1) {
     q = qp.active[slot];
+    if (q < 0) return;      // no active question: the host validation never lets this through; never touch the slot
     if (q < kb.qFirst || q >= kb.qFirst + kb.qCount) {
       // question-sharded engine, question owned by another device: contribute zeros to the all-reduce of the
       // updated priors (x + 0 is exact), keep the bookkeeping of CEQuiz.h:90-92 identical on every device
@@ -633,62 +635,6 @@ void launch_eval_questions(const DeviceKB &kb, const QuizPool &qp, int64_t n, co
 //   upper_bound inside the chunk (:380-400); asked/gap -> nearest available question (BaseEngine.cpp:60-124).
 int64_t select_chunk_count(int64_t Q, int W) { return split_count(Q, (int64_t)W * 8); }
 
-__device__ __forceinline__ uint64_t avail_word(const DeviceKB &kb, const uint64_t *asked, int64_t w) {
-  // bits of (qgaps | asked) for questions 64w..64w+63, complemented; questions >= Q read as gaps (GapTracker.h:12-15)
-  uint64_t g = 0;
-  if (kb.qgaps) g = (uint64_t)kb.qgaps[2 * w] | ((uint64_t)kb.qgaps[2 * w + 1] << 32);
-  const int64_t rem = kb.Q - 64 * w;
-  if (rem < 64) g |= ~0ull << rem;
-  return ~(g | asked[w]);
-}
-
-__device__ int64_t find_nearest_question(const DeviceKB &kb, const uint64_t *asked, int64_t iMiddle) {
-  const uint32_t dInf = 200;
-  const int64_t iPack = iMiddle >> 6;
-  const uint32_t iWithin = (uint32_t)(iMiddle & 63);
-  const uint64_t available = avail_word(kb, asked, iPack);
-  if (available != 0) {
-    const uint64_t baseMask = (1ull << iWithin) - 1;
-    const uint64_t higher = available & ~baseMask, lower = available & baseMask;
-    const uint32_t dHigher = higher ? (uint32_t)(__ffsll((long long)higher) - 1) - iWithin : dInf;
-    const uint32_t dLower = lower ? iWithin - (uint32_t)(63 - __clzll((long long)lower)) : dInf;
-    if (dHigher < dLower) return iMiddle + dHigher;
-    return iMiddle - dLower;
-  }
-  const int64_t limPack = (kb.Q + 63) >> 6;
-  int64_t i = 1;
-  while (iPack >= i && iPack + i < limPack) {
-    const uint64_t availLeft = avail_word(kb, asked, iPack - i), availRight = avail_word(kb, asked, iPack + i);
-    if ((availLeft | availRight) == 0) { i++; continue; }
-    const uint32_t dHigher = availRight ? (uint32_t)(__ffsll((long long)availRight) - 1) + 64 - iWithin : dInf;
-    const uint32_t dLower = availLeft ? iWithin + 64 - (uint32_t)(63 - __clzll((long long)availLeft)) : dInf;
-    if (dHigher < dLower) return iMiddle + dHigher + ((i - 1) << 6);
-    return iMiddle - dLower - ((i - 1) << 6);
-  }
-  while (iPack >= i) {
-    const uint64_t availLeft = avail_word(kb, asked, iPack - i);
-    if (!availLeft) { i++; continue; }
-    const uint32_t dLower = iWithin + 64 - (uint32_t)(63 - __clzll((long long)availLeft));
-    return iMiddle - dLower - ((i - 1) << 6);
-  }
-  while (iPack + i < limPack) {
-    const uint64_t availRight = avail_word(kb, asked, iPack + i);
-    if (!availRight) { i++; continue; }
-    const uint32_t dHigher = (uint32_t)(__ffsll((long long)availRight) - 1) + 64 - iWithin;
-    return iMiddle + dHigher + ((i - 1) << 6);
-  }
-  return -1;
-}
-
-__device__ __forceinline__ int64_t upper_bound_d(const double *a, int64_t n, double v) {
-  int64_t lo = 0, len = n;
-  while (len > 0) {
-    const int64_t half = len >> 1;
-    if (!(v < a[lo + half])) { lo += half + 1; len -= half + 1; } else len = half;
-  }
-  return lo;
-}
-
 // Shared memory: nChunks grand totals. runLength[n*Q] is required (the in-chunk binary search reads it back).
 __global__ void __launch_bounds__(256) k_select_question(DeviceKB kb, QuizPool qp, const int64_t *__restrict__ slots,
                                                          const double *__restrict__ priority,
@@ -696,44 +642,12 @@ __global__ void __launch_bounds__(256) k_select_question(DeviceKB kb, QuizPool q
                                                          double *__restrict__ runLength, double *__restrict__ grandOut,
                                                          int64_t *__restrict__ questions, int setActive) {
   extern __shared__ double sGrand[];
-  const int64_t b = blockIdx.x, slot = slots[b], Q = kb.Q;
-  const uint64_t *asked = qp.asked + slot * qp.askedWords;
-  const double *pri = priority + b * Q;
-  const int64_t nW = (int64_t)W * 8, nChunks = split_count(Q, nW);
-  for (int64_t c = threadIdx.x; c < nChunks; c += blockDim.x) {
-    const int64_t first = split_start(Q, nW, c), limit = split_start(Q, nW, c + 1);
-    Kahan run; run.init(0.0);
-    for (int64_t i = first; i < limit; i++) {
-      if (!(bit32(kb.qgaps, i) || bit64(asked, i))) run.add(pri[i]);
-      runLength[b * Q + i] = run.get();
-    }
-    sGrand[c] = run.get();
-  }
-  __syncthreads();
-  if (threadIdx.x != 0) return;
-  Kahan tot; tot.init(0.0);
-  for (int64_t c = 0; c < nChunks; c++) {  // CpuEngine.cpp:362-374
-    tot.add(sGrand[c]);
-    sGrand[c] = tot.get();
-    if (grandOut) grandOut[b * nChunks + c] = sGrand[c];
-  }
-  if (!questions) return;
-  const double totG = sGrand[nChunks - 1];
-  // SRDoubleNumber::MakeRandom: upper * rnd / max (left to right, both factors converted to double)
-  const double sel = __ddiv_rn(__dmul_rn(totG, __ull2double_rn(randoms[b])), __ull2double_rn(~0ull));
-  const int64_t iWorker = upper_bound_d(sGrand, nChunks, sel);
-  int64_t chosen;
-  if (iWorker >= nChunks) {
-    chosen = Q - 1;                                                       // :382-386
-  } else {
-    const double inWorker = __dsub_rn(sel, iWorker == 0 ? 0.0 : sGrand[iWorker - 1]);  // :388
-    const int64_t first = split_start(Q, nW, iWorker), limit = split_start(Q, nW, iWorker + 1);
-    chosen = first + upper_bound_d(runLength + b * Q + first, limit - first, inWorker);               // :391
-    if (chosen >= limit) chosen = limit - 1;                              // :392-400
-  }
-  if (bit32(kb.qgaps, chosen) || bit64(asked, chosen)) chosen = find_nearest_question(kb, asked, chosen);  // :404-406
-  questions[b] = chosen;
-  if (setActive && chosen >= 0) qp.active[slot] = chosen;                 // :412
+  const int64_t b = blockIdx.x, Q = kb.Q;
+  const int64_t nChunks = split_count(Q, (int64_t)W * 8);
+  const int64_t chosen = select_question_cta(kb, qp, slots[b], priority + b * Q, questions ? randoms[b] : 0ull, W,
+                                             runLength + b * Q, grandOut ? grandOut + b * nChunks : nullptr, questions != nullptr,
+                                             setActive, sGrand);
+  if (threadIdx.x == 0 && questions) questions[b] = chosen;
 }
 
 void launch_select_question(const DeviceKB &kb, const QuizPool &qp, int64_t n, const int64_t *dSlots,

@@ -255,6 +255,50 @@ def test_next_question_selection(pqa, ora, which):
         assert eng.get_active_question_id(int(quizzes[x])) == chosen[x]
 
 
+@pytest.mark.parametrize("dims,W", [((96, 5, 300), 4), ((1000, 5, 1000), 16), ((40, 3, 203), 2)])
+def test_one_quiz_fused_launch(pqa, ora, dims, W):
+    """The reference ABI's call shape -- PqaEngine_NextQuestion, one quiz per call (and the 2..4 a combiner round may
+    collect) -- runs as ONE fused launch (k_eval_few: evaluation from the derived KB, selection by the last CTA, result in
+    mapped host memory). Its priorities (W_k bit-exact inside) against the oracle at the staged bar, its chosen question
+    against the oracle's selection for the same draw, and the quiz state it leaves."""
+    Q, K, T = dims
+    kb = synth.binary_search_kb(Q, K, T, INIT, 3)
+    eng = make_engine(pqa, Q, K, T, W, kb)
+    rng = np.random.default_rng(17)
+    quizzes, priors, askeds = [], [], []
+    for b, depth in enumerate((0, 3, 8, 5)):
+        quiz = eng.start_quiz()
+        prefix = synth.quiz_prefix(b, min(depth, Q - 1), Q, T, K)
+        priors.append(drive_quiz(eng, ora, kb, W, quiz, prefix, check_top=False))
+        asked = np.zeros(Q, dtype=bool)
+        asked[[q for q, _ in prefix]] = True
+        askeds.append(asked)
+        quizzes.append(quiz)
+    bounds = ora.calc_split(Q, 8 * W)
+    for n in (1, 2, 4):
+        ev = eng.eval_questions(quizzes[:n])               # the same kernel, evaluation only
+        randoms = rng.integers(0, 2 ** 64, size=n, dtype=np.uint64)
+        before = eng.get_total_questions_asked()
+        chosen = eng.next_question_batch(quizzes[:n], randoms)
+        assert eng.get_total_questions_asked() == before + n
+        for x in range(n):
+            oev = oracle_eval_all(ora, kb, priors[x], W, askeds[x])
+            ok = ~askeds[x]
+            assert np.array_equal(np.isnan(ev["priority"][x]), askeds[x])
+            rel = np.abs(ev["priority"][x][ok] - oev["priority"][ok]) / np.abs(oev["priority"][ok])
+            assert rel.max() <= TOL_STAGED, (n, x, float(rel.max()))
+            assert np.allclose(ev["runLength"][x], oev["runLength"], rtol=4 * TOL_STAGED, atol=0)
+            assert np.allclose(ev["grand"][x], oev["grand"], rtol=4 * TOL_STAGED, atol=0)
+            e1 = dict(runLength=ev["runLength"][x], grand=ev["grand"][x], bounds=bounds)
+            assert chosen[x] == ora.select_question(e1, Q, int(randoms[x]), asked=askeds[x]), (n, x)
+            assert chosen[x] == ora.select_question(oev, Q, int(randoms[x]), asked=askeds[x]), (n, x)
+            assert eng.get_active_question_id(int(quizzes[x])) == chosen[x] and not askeds[x][chosen[x]]
+    q1 = eng.next_question(int(quizzes[3]))                  # the one-quiz entry point itself
+    assert 0 <= q1 < Q and not askeds[3][q1] and eng.get_active_question_id(int(quizzes[3])) == q1
+    # priors are untouched by NextQuestion
+    assert np.array_equal(bits(eng.copy_quiz_priors(int(quizzes[0]))), bits(priors[0]))
+
+
 def test_selection_skips_to_nearest_unasked(pqa, ora):
     Q, K, T, W = 130, 5, 64, 1
     kb = synth.uniform_kb(Q, K, T, INIT)
@@ -381,6 +425,16 @@ def test_error_contract(pqa):
     assert "[The amount is not positive]" in str(ei.value)
     with pytest.raises(pqa.PqaException):
         pqa.PqaEngineFactory().create_cpu_engine(pqa.EngineDefinition(1, 1, 1))
+    # the same quiz twice in one RecordAnswer launch: the second answer has no active question left (CEQuiz.h:78-92); the
+    # whole batch is refused before any quiz is touched
+    a, b = eng.start_quiz_batch(2)
+    eng.next_question_batch([a, b], np.array([1, 2], dtype=np.uint64))
+    before = eng.copy_quiz_priors(int(a))
+    with pytest.raises(pqa.PqaException) as ei:
+        eng.record_answer_batch([a, b, a], [0, 1, 2])
+    assert "[No active question in the quiz]" in str(ei.value)
+    assert np.array_equal(bits(eng.copy_quiz_priors(int(a))), bits(before)) and eng.get_active_question_id(int(a)) >= 0
+    eng.record_answer_batch([a, b], [0, 1])
 
 
 @pytest.mark.parametrize("depth", [0, 3, 8])
