@@ -72,6 +72,21 @@ def build_client(force=False):
     return CLIENT_PATH
 
 
+LAUNCHER_SRC = os.path.join(os.path.dirname(_HERE), "clients", "pqa_shard_launcher.cpp")
+LAUNCHER_PATH = os.path.join(LIB_DIR, "pqa_shard_launcher")
+
+
+def build_launcher(force=False):
+    """clients/pqa_shard_launcher.cpp (one process per GPU over the C ABI, no Python / torch) -> probqa_b200/lib/."""
+    build()
+    hdrs = [os.path.join(os.path.dirname(_HERE), "include", h) for h in ("PqaCInterop.h", "PqaB200Ext.h")]
+    if force or _stale(LAUNCHER_PATH, [LAUNCHER_SRC, LIB_PATH] + hdrs):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-Wall", LAUNCHER_SRC, "-o", LAUNCHER_PATH, "-L" + LIB_DIR, "-lPqaCore",
+                               "-Wl,-rpath,$ORIGIN", "-lpthread"])
+    return LAUNCHER_PATH
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
     print(build_client(force="--force" in sys.argv))
+    print(build_launcher(force="--force" in sys.argv))

@@ -101,8 +101,8 @@ Engine::Engine(const CiEngineDefinition &def, const CiB200Options &opts) {
   if (K_ <= 8) {      // the derived KB of the throughput kernels (kbEval): allocated now, built at the first evaluation
     size_t nR = 0, nL = 0;
     derived_kb_doubles(kb(), &nR, &nL);
-    PQA_CU(cudaMalloc(&dDerR_, sizeof(double) * nR));
-    PQA_CU(cudaMalloc(&dDerL_, sizeof(double) * nL));
+    PQA_CU(cudaMalloc(&dDerR_, sizeof(double) * (nR + nL)));     // one range: R, then L
+    dDerL_ = dDerR_ + nR;
     derCapR_ = nR; derCapL_ = nL;
     dDerList_.ensure((size_t)qLocal_, stream_); hDerList_.ensure((size_t)qLocal_);
   }
@@ -144,7 +144,7 @@ Engine::~Engine() {
                 (double)statCalls_[k] / (double)statKindLaunches_[k]);
   }
   cudaFree(dSA_); cudaFree(dMD_); cudaFree(dVB_); cudaFree(dLog2Tbl_);
-  cudaFree(dDerR_); cudaFree(dDerL_);
+  cudaFree(dDerR_);
   if (hFew_) cudaFreeHost((void *)hFew_);
   cudaFree(dPriors_); cudaFree(dLogPriors_); cudaFree(dAsked_); cudaFree(dActive_);
   for (int r = 0; r < kMaxPeers; r++) if (p2pOpened_[r]) cudaIpcCloseMemHandle(p2pPeer_[r]);
@@ -179,17 +179,17 @@ DeviceKB Engine::kbEval() {
   if (K_ > 8) return kb();      // served by the exact kernel, which reads sA / mD
   size_t nR = 0, nL = 0;
   derived_kb_doubles(kb(), &nR, &nL);
-  if (nR > derCapR_ || nL > derCapL_ || !dDerR_) {
+  if (nR != derCapR_ || nL != derCapL_ || !dDerR_) {
     // Normally allocated by the constructor: allocations and frees synchronise the device, which must not happen while
     // another shard engine of this process spins in an exchange barrier on the same GPU. Only a KB that grew in maintenance
     // mode (single engines only) comes through here.
     PQA_CU(cudaStreamSynchronize(stream_));
     if (dDerR_) cudaFree(dDerR_);
-    if (dDerL_) cudaFree(dDerL_);
     dDerR_ = dDerL_ = nullptr; derCapR_ = derCapL_ = 0;
-    PQA_CU(cudaMalloc(&dDerR_, sizeof(double) * nR));
-    PQA_CU(cudaMalloc(&dDerL_, sizeof(double) * nL));
+    PQA_CU(cudaMalloc(&dDerR_, sizeof(double) * (nR + nL)));
+    dDerL_ = dDerR_ + nR;
     derCapR_ = nR; derCapL_ = nL;
+
     dDerList_.ensure((size_t)qLocal_, stream_); hDerList_.ensure((size_t)qLocal_);
     derAllDirty_ = true;
   }
@@ -327,11 +327,21 @@ int64_t Engine::StartQuiz(PqaError **err) {
 // CreateQuizInternal (:185-270: index validation, asked bits, answers) -> CECreateQuizResume::UpdateLikelihoods.
 // pCounts[x] answered questions of quiz x are taken from pAQs in order. A quiz with zero answers is a StartQuiz (:392-394).
 PqaError *Engine::ResumeQuizBatch(int64_t n, const int64_t *pCounts, const CiAnsweredQuestion *pAQs, int64_t *pQuizIds) {
+  if (IsSharded()) return ErrNotImplemented("ResumeQuiz on a sharded engine (a ShardGroup resumes quizzes for its shards)");
+  return ResumeQuizBatchEx(n, pCounts, pAQs, pQuizIds, nullptr, nullptr, nullptr);
+}
+
+// ResumeQuiz for one engine (src = nullptr), or as one member of a ShardGroup: the leader (src / pools given) runs the
+// kernel once over the cells of all shards and stores the finished rows into every shard's quiz pool; a follower
+// (followStatus given: the leader's per-resumed-quiz status) only keeps its registry in step and starts the quizzes that
+// have no answers. outStatus (leader): receives that status array.
+PqaError *Engine::ResumeQuizBatchEx(int64_t n, const int64_t *pCounts, const CiAnsweredQuestion *pAQs, int64_t *pQuizIds,
+                                    const ResumeSource *src, const PoolList *pools, std::vector<int> *status) {
   if (n < 0) return ErrNegativeCount(n, PQA_FILE_LINE "|n| must be non-negative.");
   if (n == 0) return nullptr;
   if (!pCounts || !pQuizIds) return MakeError(ErrCode::NullArgument, PQA_FILE_LINE "pCounts/pQuizIds");
-  if (IsSharded()) return ErrNotImplemented("ResumeQuiz on a sharded engine");
   if (maintenance_) return WrongMode("Start/Resume quiz");
+  const bool follower = src == nullptr && status != nullptr;
   int64_t total = 0;
   for (int64_t x = 0; x < n; x++) {
     if (pCounts[x] < 0) return ErrNegativeCount(pCounts[x], "|nAnswered| must be non-negative.");
@@ -376,19 +386,31 @@ PqaError *Engine::ResumeQuizBatch(int64_t n, const int64_t *pCounts, const CiAns
   PqaError *result = nullptr;
   if (!resumeIds.empty()) {
     const int64_t m = (int64_t)resumeIds.size();
-    UploadIds(m, resumeIds.data());
-    dGroupStart_.ensure(aqStart.size(), stream_); dTargets_.ensure(aqQ.size(), stream_); dAnswers_.ensure(aqA.size(), stream_);
-    dCounts_.ensure((size_t)m, stream_);   // reused as the int status array (m ints fit in m int64 slots)
-    PQA_CU(cudaMemcpyAsync(dGroupStart_.get(), aqStart.data(), sizeof(int64_t) * aqStart.size(), cudaMemcpyHostToDevice, stream_));
-    PQA_CU(cudaMemcpyAsync(dTargets_.get(), aqQ.data(), sizeof(int64_t) * aqQ.size(), cudaMemcpyHostToDevice, stream_));
-    PQA_CU(cudaMemcpyAsync(dAnswers_.get(), aqA.data(), sizeof(int64_t) * aqA.size(), cudaMemcpyHostToDevice, stream_));
-    launch_resume_quiz(kb(), pool(), m, dIds_.get(), dGroupStart_.get(), dTargets_.get(), dAnswers_.get(), W_,
-                       reinterpret_cast<int *>(dCounts_.get()), stream_);
-    std::vector<int> status((size_t)m);
-    PQA_CU(cudaMemcpyAsync(status.data(), dCounts_.get(), sizeof(int) * (size_t)m, cudaMemcpyDeviceToHost, stream_));
-    PQA_CU(cudaGetLastError()); PQA_CU(cudaStreamSynchronize(stream_));
+    std::vector<int> st((size_t)m, 0);
+    if (follower) {
+      if ((int64_t)status->size() != m) return MakeError(ErrCode::Internal, PQA_FILE_LINE "the shards' resume batches have diverged");
+      st = *status;
+    } else {
+      UploadIds(m, resumeIds.data());
+      dGroupStart_.ensure(aqStart.size(), stream_); dTargets_.ensure(aqQ.size(), stream_); dAnswers_.ensure(aqA.size(), stream_);
+      dCounts_.ensure((size_t)m, stream_);   // reused as the int status array (m ints fit in m int64 slots)
+      PQA_CU(cudaMemcpyAsync(dGroupStart_.get(), aqStart.data(), sizeof(int64_t) * aqStart.size(), cudaMemcpyHostToDevice, stream_));
+      PQA_CU(cudaMemcpyAsync(dTargets_.get(), aqQ.data(), sizeof(int64_t) * aqQ.size(), cudaMemcpyHostToDevice, stream_));
+      PQA_CU(cudaMemcpyAsync(dAnswers_.get(), aqA.data(), sizeof(int64_t) * aqA.size(), cudaMemcpyHostToDevice, stream_));
+      if (src) {
+        const DeviceKB kq = kbQuiz();
+        launch_resume_quiz_multi(*src, *pools, kq.vB, kq.tgaps, T_, m, dIds_.get(), dGroupStart_.get(), dTargets_.get(),
+                                 dAnswers_.get(), W_, reinterpret_cast<int *>(dCounts_.get()), stream_);
+      } else {
+        launch_resume_quiz(kb(), pool(), m, dIds_.get(), dGroupStart_.get(), dTargets_.get(), dAnswers_.get(), W_,
+                           reinterpret_cast<int *>(dCounts_.get()), stream_);
+      }
+      PQA_CU(cudaMemcpyAsync(st.data(), dCounts_.get(), sizeof(int) * (size_t)m, cudaMemcpyDeviceToHost, stream_));
+      PQA_CU(cudaGetLastError()); PQA_CU(cudaStreamSynchronize(stream_));
+      if (status) *status = st;
+    }
     for (int64_t x = 0; x < m; x++) {
-      if (status[x] == 0) continue;
+      if (st[(size_t)x] == 0) continue;
       // CpuEngine.cpp:316-319 -> CreateQuizInternal unassigns the quiz (:257-261)
       HostQuiz &q = quizzes_[resumeIds[x]];
       q.present = false; q.answers.clear(); q.activeQuestion = -1;
@@ -1673,6 +1695,13 @@ PqaError *Engine::P2PNextQuestionBegin(int64_t n, const int64_t *pQuizIds, const
       double *outState = last ? nullptr : (double *)(p2pPeer_[p2pRank_ + 1] + p2pOffState_ + par * p2pSzState_);
       PeerBufs wAll;                                        // the complete W_k lives in slot 0 of every inbox
       if (last) { wAll.n = p2pRanks_; for (int r = 0; r < p2pRanks_; r++) wAll.p[r] = (double *)(p2pPeer_[r] + p2pOffW_ + (par * p2pRanks_) * p2pSzW_); }
+      if (p2pSameDevicePeer_ && !first) {
+        // several shard engines share this GPU (tests): phase-1 CTAs that spin for the previous shard's hand-over could fill
+        // every SM slot before that shard's own CTAs are resident, so a one-CTA kernel waits for all tiles instead
+        const int64_t nTiles = (Q_ + tileQ - 1) / tileQ;
+        launch_p2p_wait(p1.waitFlags, (int)nTiles, opEpoch, p1.errFlag, kP2PTimeoutNs, stream_);
+        p1.waitFlags = nullptr;
+      }
       launch_eval_tshard_w(kbE, pool(), tFirst_, n, dIds_.get(), wAll, evalCfg_, stream_, inState, outState, &p1);
       PQA_CU(cudaEventRecord(p2pEv_[1], stream_));
       PipeCtl p2;

@@ -156,7 +156,9 @@ struct CallSlot {
   std::condition_variable cv;        // signalled for this call only (with Engine::combineMu_)
 };
 
+class ShardGroup;
 class Engine {
+  friend class ShardGroup;   // a group reads its shards' device views (kb(), pool()) to wire kernels across them
  public:
   Engine(const CiEngineDefinition &def, const CiB200Options &opts);
   virtual ~Engine();
@@ -196,6 +198,8 @@ class Engine {
   // --- batches of concurrent quizzes ---
   virtual PqaError *StartQuizBatch(int64_t n, int64_t *pQuizIds);
   virtual PqaError *ResumeQuizBatch(int64_t n, const int64_t *pCounts, const CiAnsweredQuestion *pAQs, int64_t *pQuizIds);
+  PqaError *ResumeQuizBatchEx(int64_t n, const int64_t *pCounts, const CiAnsweredQuestion *pAQs, int64_t *pQuizIds,
+                              const ResumeSource *src, const PoolList *pools, std::vector<int> *status);
   virtual PqaError *NextQuestionBatch(int64_t n, const int64_t *pQuizIds, const uint64_t *pRandoms, int64_t *pQuestions,
                               void **ppErrors);
   virtual PqaError *RecordAnswerBatch(int64_t n, const int64_t *pQuizIds, const int64_t *pAnswers);

@@ -730,7 +730,6 @@ __global__ void __launch_bounds__(SW * 32, 2) k_eval_small(const StagedParams P)
 // host memory followed by a sequence word the caller polls: ONE launch, no copy, no stream synchronisation.
 constexpr int kFewMax = 4;                 // quizzes per launch = warps per CTA
 constexpr int kFewGroups = 32;             // first-level ticket counters per quiz (1000 same-address atomics would serialise)
-__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 struct FewParams {
   DeviceKB kb;
   QuizPool qp;
@@ -763,29 +762,23 @@ __global__ void __launch_bounds__(kFewMax * 32, 7) k_eval_few(const FewParams P)
   const double *__restrict__ gL = P.kb.dL + iLocal * nV * ((K + 1) * 4);
   const bool qgap = bit32(P.kb.qgaps, i);
   // ---- pass 1: warp w <-> quiz w, lane 4k + l <-> Kahan lane l of answer k
-  bool liveW = false;
   if (warp < P.n && !qgap) {
     const int64_t slot = P.slots[warp];
-    liveW = !bit64(P.qp.asked + slot * P.qp.askedWords, i);
-    if (liveW && lane < 4 * K) {
+    if (!bit64(P.qp.asked + slot * P.qp.askedWords, i) && lane < 4 * K) {
       const int k = lane >> 2, l = lane & 3;
       const double *rk = gR + k * 4 + l;
       const double *__restrict__ prl = P.qp.priors + slot * Tp + l;
       Kahan kw; kw.init();
-      // The chain advances one vector per ~36 cycles (4 dependent adds); an L2 hit takes ~250. Lines are therefore pulled
-      // into L1 kPf vectors ahead with prefetch instructions (no registers), and the loads proper hit L1.
-      constexpr int kPf = 24;
-      for (int v = 0; v < kPf && v < (int)nV; v++) prefetch_l1(rk + v * (4 * K));
+      // The chain advances one vector per ~36 cycles (4 dependent adds); an L2 hit takes ~250: sixteen independent loads
+      // are in flight ahead of the dependent adds.
+      constexpr int kB = 16;
       int v = 0;
-      for (; v + 4 <= (int)nV; v += 4) {
-        double r[4], p[4];
+      for (; v + kB <= (int)nV; v += kB) {
+        double r[kB], p[kB];
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
-          if (v + u + kPf < (int)nV) prefetch_l1(rk + (v + u + kPf) * (4 * K));   // the warp's 4K lanes cover the vector's lines
-          r[u] = __ldg(rk + (v + u) * (4 * K)); p[u] = __ldg(prl + 4 * (v + u));
-        }
+        for (int u = 0; u < kB; u++) { r[u] = __ldg(rk + (v + u) * (4 * K)); p[u] = __ldg(prl + 4 * (v + u)); }
 #pragma unroll
-        for (int u = 0; u < 4; u++) kw.add(__dmul_rn(r[u], p[u]));       // :81-86
+        for (int u = 0; u < kB; u++) kw.add(__dmul_rn(r[u], p[u]));      // :81-86
       }
       for (; v < (int)nV; v++) kw.add(__dmul_rn(__ldg(rk + v * (4 * K)), __ldg(prl + 4 * v)));
       const double w = group_precise_sum(kw);                            // :88
@@ -807,11 +800,6 @@ __global__ void __launch_bounds__(kFewMax * 32, 7) k_eval_few(const FewParams P)
       for (int j = threadIdx.x; j < (int)T; j += THREADS) {
         const int vb = j >> 2, l = j & 3;
         const double *rj = gR + vb * (4 * K) + l, *lj = gL + vb * (4 * (K + 1)) + l;
-        if (j + 2 * THREADS < (int)T && l == 0) {        // the slab lines of the iteration after next, one request per vector
-          const double *rn = rj + (2 * THREADS / 4) * (4 * K), *ln = lj + (2 * THREADS / 4) * (4 * (K + 1));
-          prefetch_l1(rn); prefetch_l1(rn + 16); if (K > 4) prefetch_l1(rn + 4 * K - 1);
-          prefetch_l1(ln); prefetch_l1(ln + 16); prefetch_l1(ln + 4 * (K + 1) - 1);
-        }
         const double p = __ldg(pr + j), lp = __ldg(lpr + j), id2 = __ldg(lj + 4 * K);
         double post[K], l2[K];
         bool allFast = true;
@@ -881,9 +869,9 @@ __global__ void __launch_bounds__(kFewMax * 32, 7) k_eval_few(const FewParams P)
     __syncthreads();
     if (sLast) {                                                         // CTA-uniform
       __threadfence();
-      const int64_t nChunks = split_count(Q, (int64_t)P.W * 8);
+      const int64_t nSel = split_count(Q, (int64_t)P.W * 8);
       const int64_t chosen = select_question_cta(P.kb, P.qp, slot, P.priority + (int64_t)b * Q, P.randoms[b], P.W,
-                                                 P.runLength + (int64_t)b * Q, P.grandOut ? P.grandOut + b * nChunks : nullptr,
+                                                 P.runLength + (int64_t)b * Q, P.grandOut ? P.grandOut + b * nSel : nullptr,
                                                  P.hostQuestions != nullptr, P.setActive, sGrand);
       if (threadIdx.x == 0 && P.hostQuestions) {
         P.hostQuestions[b] = chosen;

@@ -137,6 +137,95 @@ PqaError *ShardGroup::StartQuizBatch(int64_t n, int64_t *pQuizIds) {
   return err;
 }
 
+// ResumeQuiz (CpuEngine.cpp:277-282, CECreateQuizOperation.cpp:55-83): the likelihood product over the answered questions is
+// elementwise per target, but its cells are spread over the shards (rows of some questions, or columns of all). Shard 0
+// runs the single-engine kernel once with a cell view over ALL shards (peer pointers; the devices of a group have peer
+// access) and stores the finished rows into every shard's replica of the quiz; the other shards only keep their
+// registries in step. Bit-identical to one engine by construction: it is the same kernel on the same cells.
+PqaError *ShardGroup::ResumeQuizBatch(int64_t n, const int64_t *pCounts, const CiAnsweredQuestion *pAQs, int64_t *pQuizIds) {
+  if (n < 0) return ErrNegativeCount(n, PQA_FILE_LINE "|n| must be non-negative.");
+  if (n == 0) return nullptr;
+  if (!pCounts || !pQuizIds) return MakeError(ErrCode::NullArgument, PQA_FILE_LINE "pCounts/pQuizIds");
+  if (shards_.size() == 1) {
+    std::lock_guard<std::mutex> lk(mu_);
+    PqaError *e = (cudaSetDevice(shards_[0]->device()), shards_[0]->ResumeQuizBatchEx(n, pCounts, pAQs, pQuizIds, nullptr, nullptr, nullptr));
+    MirrorResumed(n, pCounts, pAQs, pQuizIds);
+    return e;
+  }
+  std::lock_guard<std::mutex> lk(mu_);
+  ResumeSource src;
+  PoolList pools;
+  src.nShards = pools.n = (int)shards_.size();
+  src.K = K_;
+  for (size_t r = 0; r < shards_.size(); r++) {
+    const DeviceKB k = shards_[r]->kb();
+    src.sA[r] = k.sA; src.mD[r] = k.mD; src.qFirst[r] = k.qFirst; src.qCount[r] = k.qCount;
+    src.tFirst[r] = shards_[r]->targetShardFirst(); src.TpL[r] = k.Tp;
+    pools.p[r] = shards_[r]->pool();
+  }
+  // every shard grows its quiz pool first: the leader's kernel writes into all of them
+  std::vector<int> status;
+  std::vector<int64_t> ids((size_t)n, -1);
+  cudaSetDevice(shards_[0]->device());
+  for (size_t r = 1; r < shards_.size(); r++) {     // pools of the followers must hold the new slots before the kernel runs
+    cudaSetDevice(shards_[r]->device());
+    std::lock_guard<std::mutex> lkS(shards_[r]->mu_);
+    shards_[r]->EnsureQuizCapacity((int64_t)shards_[r]->quizzes_.size() + n);
+    pools.p[r] = shards_[r]->pool();
+  }
+  cudaSetDevice(shards_[0]->device());
+  {
+    std::lock_guard<std::mutex> lkS(shards_[0]->mu_);
+    shards_[0]->EnsureQuizCapacity((int64_t)shards_[0]->quizzes_.size() + n);
+    pools.p[0] = shards_[0]->pool();
+  }
+  PqaError *err = shards_[0]->ResumeQuizBatchEx(n, pCounts, pAQs, pQuizIds, &src, &pools, &status);
+  if (err && err->code != ErrCode::I64Underflow) return err;      // validation failure: nothing was assigned anywhere
+  for (size_t r = 1; r < shards_.size(); r++) {
+    cudaSetDevice(shards_[r]->device());
+    std::vector<int> st = status;
+    PqaError *e = shards_[r]->ResumeQuizBatchEx(n, pCounts, pAQs, ids.data(), nullptr, nullptr, &st);
+    if (e && e->code == ErrCode::I64Underflow) { delete e; e = nullptr; }       // reported once, by the leader
+    if (!e && !std::equal(ids.begin(), ids.end(), pQuizIds)) e = MakeError(ErrCode::Internal, PQA_FILE_LINE "the shards' quiz registries have diverged");
+    if (e) { delete err; return e; }
+  }
+  MirrorResumed(n, pCounts, pAQs, pQuizIds);
+  return err;
+}
+
+// the shell's own registry follows the shards': same ids in the same order (failed quizzes are assigned and released again)
+void ShardGroup::MirrorResumed(int64_t n, const int64_t *pCounts, const CiAnsweredQuestion *pAQs, const int64_t *pQuizIds) {
+  std::vector<int64_t> mine((size_t)n);
+  for (int64_t x = 0; x < n; x++) mine[(size_t)x] = AssignQuizId();
+  int64_t off = 0;
+  for (int64_t x = 0; x < n; x++) {
+    HostQuiz &q = quizzes_[(size_t)mine[(size_t)x]];
+    for (int64_t y = 0; y < pCounts[x]; y++) q.answers.push_back(pAQs[off + y]);
+    off += pCounts[x];
+  }
+  for (int64_t x = 0; x < n; x++) {
+    if (pQuizIds[x] >= 0) continue;                    // the reference's I64Underflow: the quiz was unassigned again
+    HostQuiz &q = quizzes_[(size_t)mine[(size_t)x]];
+    q.present = false; q.answers.clear(); q.activeQuestion = -1;
+    quizGaps_.push_back(mine[(size_t)x]);
+    pimQuiz_.RemoveComp(mine[(size_t)x]);
+  }
+}
+
+// BaseEngine::ClearOldQuizzes (BaseEngine.cpp:814-872) is registry work: the shell decides with its own usage times which
+// quizzes go (the base class's algorithm), and the shards release exactly those, in the same order.
+PqaError *ShardGroup::ClearOldQuizzes(int64_t maxCount, double maxAgeSec) {
+  size_t before;
+  { std::lock_guard<std::mutex> lk(mu_); before = quizGaps_.size(); }
+  if (PqaError *e = Engine::ClearOldQuizzes(maxCount, maxAgeSec)) return e;
+  std::vector<int64_t> released;
+  { std::lock_guard<std::mutex> lk(mu_); released.assign(quizGaps_.begin() + (std::ptrdiff_t)before, quizGaps_.end()); }
+  PqaError *err = nullptr;
+  if (!released.empty())
+    for (auto &s : shards_) { cudaSetDevice(s->device()); err = Keep(err, s->ReleaseQuizBatch((int64_t)released.size(), released.data())); }
+  return err;
+}
+
 PqaError *ShardGroup::NextQuestionBatch(int64_t n, const int64_t *pQuizIds, const uint64_t *pRandoms, int64_t *pQuestions,
                                         void **ppErrors) {
   if (n < 0) return ErrNegativeCount(n, PQA_FILE_LINE "|n| must be non-negative.");

@@ -40,10 +40,11 @@ class ShardGroup : public Engine {
   PqaError *Synchronize() override;
   PqaError *SetEvalKernel(int32_t which, int64_t chunkTargets, int64_t quizzesPerCta, int32_t kahanLanesPerThread) override;
 
+  PqaError *ResumeQuizBatch(int64_t n, const int64_t *pCounts, const CiAnsweredQuestion *pAQs, int64_t *pQuizIds) override;
+  PqaError *ClearOldQuizzes(int64_t maxCount, double maxAgeSec) override;
+
   // single-engine features a group does not offer
-  PqaError *ResumeQuizBatch(int64_t, const int64_t *, const CiAnsweredQuestion *, int64_t *) override { return No("ResumeQuiz"); }
   PqaError *SaveKBShard(const char *, bool) override { return No("SaveKBShard (use SaveKB)"); }
-  PqaError *ClearOldQuizzes(int64_t, double) override { return No("ClearOldQuizzes"); }
   PqaError *StartMaintenance(bool) override { return No("maintenance mode"); }
   PqaError *FinishMaintenance() override { return No("maintenance mode"); }
   PqaError *AddQsTs(int64_t, CiAddQorTParam *, int64_t, CiAddQorTParam *) override { return No("maintenance mode"); }
@@ -84,6 +85,7 @@ class ShardGroup : public Engine {
   ShardGroup(const CiEngineDefinition &def, const CiB200Options &opts) : Engine(def, opts, ShellTag{}) {}   // shards added by LoadKBGroup
   static PqaError *No(const char *what) { return ErrNotImplemented(std::string("sharded engine group: ") + what); }
   void Connect(const CiB200GroupOptions &gopts);
+  void MirrorResumed(int64_t n, const int64_t *pCounts, const CiAnsweredQuestion *pAQs, const int64_t *pQuizIds);
   static std::vector<CiB200Options> ShardOptions(const CiEngineDefinition &def, const CiB200Options &opts,
                                                  const CiB200GroupOptions &gopts);
   std::vector<std::unique_ptr<Engine>> shards_;

@@ -258,25 +258,38 @@ void launch_fill_binary_search_kb(const DeviceKB &kbLocal, int64_t tFirst, int64
 // kept as a mantissa in [1,2) plus an integer sum of biased exponents so that it cannot underflow; the reference
 // multiplies by vB[j % 4] (it loads the FIRST vector of vB for every target vector, :48) and that is reproduced.
 // status[b] = 1 reports the reference's I64Underflow (:316-319). The log-prior row doubles as the exponent scratch.
-__global__ void __launch_bounds__(256) k_resume_quiz(DeviceKB kb, QuizPool qp, const int64_t *__restrict__ slots,
+// Generalised over where the cells live (ResumeSource): one engine, or the shard engines of a group in one process read
+// through peer pointers; the finished row is stored into every pool of the list (replicated quiz state of a group).
+__device__ __forceinline__ double resume_ratio(const ResumeSource &S, int64_t q, int64_t a, int64_t j) {
+  for (int r = 0; r < S.nShards; r++) {
+    if (q < S.qFirst[r] || q >= S.qFirst[r] + S.qCount[r]) continue;
+    if (j < S.tFirst[r] || j >= S.tFirst[r] + S.TpL[r]) continue;       // TpL: the shard's padded column count
+    const int64_t ql = q - S.qFirst[r], jl = j - S.tFirst[r];
+    return __ddiv_rn(S.sA[r][(ql * S.K + a) * S.TpL[r] + jl], S.mD[r][ql * S.TpL[r] + jl]);   // padding lanes: 0 / 1
+  }
+  return 0.0;
+}
+__global__ void __launch_bounds__(256) k_resume_quiz(ResumeSource S, PoolList pools, const double *__restrict__ vB,
+                                                     const uint32_t *__restrict__ tgaps, int64_t T,
+                                                     const int64_t *__restrict__ slots,
                                                      const int64_t *__restrict__ aqStart, const int64_t *__restrict__ aqQ,
                                                      const int64_t *__restrict__ aqA, int W, int *__restrict__ status) {
   extern __shared__ double sm[];
   __shared__ long long sMax[256];
+  const QuizPool &qp = pools.p[0];
   const int64_t slot = slots[blockIdx.x];
   double *prior = qp.priors + slot * qp.Tp;
   double *lprior = qp.logPriors + slot * qp.Tp;
   long long *totExp = reinterpret_cast<long long *>(lprior);
-  const int64_t T = kb.T, Tp = kb.Tp, first = aqStart[blockIdx.x], limit = aqStart[blockIdx.x + 1];
+  const int64_t Tp = qp.Tp, first = aqStart[blockIdx.x], limit = aqStart[blockIdx.x + 1];
   const unsigned long long EXPMASK = 0x7FF0000000000000ull, EXP0 = 0x3FF0000000000000ull;
   long long myMax = LLONG_MIN;
   for (int64_t j = threadIdx.x; j < Tp; j += blockDim.x) {
     double m = 0.0;
     long long e = 0;
     for (int64_t x = first; x < limit; x++) {
-      const int64_t q = aqQ[x] - kb.qFirst, a = aqA[x];
-      const double P = __ddiv_rn(kb.sA[(q * kb.K + a) * Tp + j], kb.mD[q * Tp + j]);   // padding lanes: 0 / 1
-      const double old = (x == first) ? kb.vB[j & 3] : m;
+      const double P = resume_ratio(S, aqQ[x], aqA[x], j);
+      const double old = (x == first) ? vB[j & 3] : m;
       const unsigned long long pb = (unsigned long long)__double_as_longlong(__dmul_rn(old, P));
       m = __longlong_as_double((long long)((pb & ~EXPMASK) | EXP0));                   // MakeExponent0
       const long long pe = (long long)((pb & EXPMASK) >> 52);                          // ExtractExponents64<false>
@@ -285,7 +298,7 @@ __global__ void __launch_bounds__(256) k_resume_quiz(DeviceKB kb, QuizPool qp, c
     const long long tot = e + 1023;   // + exponent field of the mantissa, which MakeExponent0 just set to 1023
     prior[j] = m;
     totExp[j] = tot;
-    if (j < T && !bit32(kb.tgaps, j)) myMax = max(myMax, tot);
+    if (j < T && !bit32(tgaps, j)) myMax = max(myMax, tot);
   }
   sMax[threadIdx.x] = myMax;
   __syncthreads();
@@ -305,23 +318,44 @@ __global__ void __launch_bounds__(256) k_resume_quiz(DeviceKB kb, QuizPool qp, c
   for (int64_t j = threadIdx.x; j < Tp; j += blockDim.x) {                             // CENormPriorsSubtaskCorrSum.cpp:24-41
     const unsigned long long mb = (unsigned long long)__double_as_longlong(prior[j]);
     const long long normExp = totExp[j] + corr;
-    const bool zero = normExp < 1 || j >= T || bit32(kb.tgaps, j);
+    const bool zero = normExp < 1 || j >= T || bit32(tgaps, j);
     prior[j] = zero ? 0.0 : __longlong_as_double((long long)((mb & ~EXPMASK) | ((unsigned long long)normExp << 52)));
   }
   if (threadIdx.x == 0) {
     status[blockIdx.x] = 0;
-    for (int64_t w = 0; w < qp.askedWords; w++) qp.asked[slot * qp.askedWords + w] = 0;
-    for (int64_t x = first; x < limit; x++) qp.asked[slot * qp.askedWords + (aqQ[x] >> 6)] |= 1ull << (aqQ[x] & 63);
-    qp.active[slot] = -1;
+    for (int r = 0; r < pools.n; r++) {
+      const QuizPool &pr = pools.p[r];
+      for (int64_t w = 0; w < pr.askedWords; w++) pr.asked[slot * pr.askedWords + w] = 0;
+      for (int64_t x = first; x < limit; x++) pr.asked[slot * pr.askedWords + (aqQ[x] >> 6)] |= 1ull << (aqQ[x] & 63);
+      pr.active[slot] = -1;
+    }
   }
   __syncthreads();
   kahan_normalise(prior, lprior, T, Tp, W, sm);
+  if (pools.n > 1) {         // the other shards' replicas of the quiz (peer memory)
+    __syncthreads();
+    for (int64_t j = threadIdx.x; j < Tp; j += blockDim.x) {
+      const double v = prior[j], lv = lprior[j];
+      for (int r = 1; r < pools.n; r++) { pools.p[r].priors[slot * Tp + j] = v; pools.p[r].logPriors[slot * Tp + j] = lv; }
+    }
+    __threadfence_system();
+  }
+}
+void launch_resume_quiz_multi(const ResumeSource &src, const PoolList &pools, const double *dVB, const uint32_t *dTGaps, int64_t T,
+                              int64_t n, const int64_t *dSlots, const int64_t *dAqStart, const int64_t *dAqQ, const int64_t *dAqA,
+                              int W, int *dStatus, cudaStream_t st) {
+  if (n <= 0) return;
+  k_resume_quiz<<<(unsigned)n, 256, priors_smem(W), st>>>(src, pools, dVB, dTGaps, T, dSlots, dAqStart, dAqQ, dAqA, W, dStatus);
+  count_launch();
 }
 void launch_resume_quiz(const DeviceKB &kb, const QuizPool &qp, int64_t n, const int64_t *dSlots, const int64_t *dAqStart,
                         const int64_t *dAqQ, const int64_t *dAqA, int W, int *dStatus, cudaStream_t st) {
-  if (n <= 0) return;
-  k_resume_quiz<<<(unsigned)n, 256, priors_smem(W), st>>>(kb, qp, dSlots, dAqStart, dAqQ, dAqA, W, dStatus);
-  count_launch();
+  ResumeSource S;
+  S.nShards = 1; S.K = kb.K;
+  S.sA[0] = kb.sA; S.mD[0] = kb.mD; S.qFirst[0] = kb.qFirst; S.qCount[0] = kb.qCount; S.tFirst[0] = 0; S.TpL[0] = kb.Tp;
+  PoolList pools;
+  pools.n = 1; pools.p[0] = qp;
+  launch_resume_quiz_multi(S, pools, kb.vB, kb.tgaps, kb.T, n, dSlots, dAqStart, dAqQ, dAqA, W, dStatus, st);
 }
 
 __global__ void k_refresh_log_priors(QuizPool qp, const int64_t *__restrict__ slots) {

@@ -30,6 +30,8 @@ struct DeviceKB {
   int64_t qFirst, qCount;
 };
 
+constexpr int kMaxPeers = 8;   // shard engines of one box
+
 // Per-quiz state resident in HBM, addressed by quiz slot.
 struct QuizPool {
   double *priors;          // [slot][Tp]  normalised posterior (CEQuiz.decl.h _pPriorMants); padding = +0
@@ -40,7 +42,6 @@ struct QuizPool {
   int64_t Tp;
 };
 
-constexpr int kMaxPeers = 8;
 struct PeerBufs {           // where a result goes / comes from when several devices cooperate
   int n = 0;                // 1 = this device's own buffer only (the caller sums across shards);
                             // N = one buffer per shard: as output, p[r] is this shard's slot in shard r's inbox (peer
@@ -69,6 +70,22 @@ void launch_record_answer(const DeviceKB &kb, const QuizPool &qp, int64_t n, con
 // questions dAqQ[dAqStart[b] .. dAqStart[b+1]) with dAqA; dStatus[b] = 1 on the reference's I64Underflow.
 void launch_resume_quiz(const DeviceKB &kb, const QuizPool &qp, int64_t n, const int64_t *dSlots, const int64_t *dAqStart,
                         const int64_t *dAqQ, const int64_t *dAqA, int W, int *dStatus, cudaStream_t st);
+// The same over the shard engines of one process (ShardGroup): the cells of an answered question are read from whichever
+// shard holds them (peer pointers), the finished row goes into every shard's replica of the quiz.
+struct ResumeSource {
+  int nShards = 0;
+  int64_t K = 0;
+  const double *sA[kMaxPeers] = {}, *mD[kMaxPeers] = {};
+  int64_t qFirst[kMaxPeers] = {}, qCount[kMaxPeers] = {};   // questions held by shard r
+  int64_t tFirst[kMaxPeers] = {}, TpL[kMaxPeers] = {};      // first target and padded column count (row stride) of shard r
+};
+struct PoolList {
+  int n = 0;
+  QuizPool p[kMaxPeers];
+};
+void launch_resume_quiz_multi(const ResumeSource &src, const PoolList &pools, const double *dVB, const uint32_t *dTGaps, int64_t T,
+                              int64_t n, const int64_t *dSlots, const int64_t *dAqStart, const int64_t *dAqQ, const int64_t *dAqA,
+                              int W, int *dStatus, cudaStream_t st);
 // Renormalisation-free refresh of logPriors after priors were overwritten from the host.
 void launch_refresh_log_priors(const QuizPool &qp, int64_t n, const int64_t *dSlots, cudaStream_t st);
 

@@ -94,6 +94,63 @@ def test_group_behaves_like_one_engine(axis, dims, n_shards, exact, tmp_path):
     assert grp.start_maintenance(True, throw=False) is not None      # single-engine feature
 
 
+@pytest.mark.parametrize("axis,dims,n_shards", [("questions", (40, 5, 203), 3), ("targets", (36, 5, 1000), 2), ("targets", (25, 4, 96), 4)])
+def test_group_resume_quiz_and_clear_old_quizzes(axis, dims, n_shards):
+    """ResumeQuiz (CpuEngine.cpp:277-282) and ClearOldQuizzes (BaseEngine.cpp:814-872) on a group handle: priors after a
+    resume are bit-identical to one engine's (and hence to the oracle's, test_resume_quiz_bit_exact), on every shard; the
+    resumed quizzes then continue like any other; ClearOldQuizzes releases the same quizzes on both sides."""
+    from probqa_b200 import engine as pqa
+    Q, K, T = dims
+    W = 6
+    kb = synth.gamma_kb(Q, K, T, INIT)
+    fac = pqa.PqaEngineFactory()
+    edef = pqa.EngineDefinition(K, Q, T, init_amount=INIT)
+    one = fac.create_b200_engine(edef, emulated_workers=W, rng_seed=5)
+    grp = fac.create_sharded_engine(edef, axis, n_shards, devices=devices(n_shards), exact_order=True, max_batch=16,
+                                    emulated_workers=W, rng_seed=5)
+    one.upload_kb(*kb); grp.upload_kb(*kb)
+    rng = np.random.default_rng(83)
+    lists = []
+    for n_ans in (0, 1, 7, min(Q - 2, 30), 3, 0, 12):
+        qs = rng.permutation(Q)[:n_ans]
+        lists.append([pqa.AnsweredQuestion(int(q), int(rng.integers(0, K))) for q in qs])
+    ids_one = one.resume_quiz_batch(lists)
+    ids_grp = grp.resume_quiz_batch(lists)
+    assert np.array_equal(ids_one, ids_grp) and np.all(ids_grp >= 0)
+    for q in ids_grp:
+        assert np.array_equal(bits(grp.copy_quiz_priors(int(q))), bits(one.copy_quiz_priors(int(q))))
+    single = grp.resume_quiz(lists[2]); single_one = one.resume_quiz(lists[2])
+    assert single == single_one
+    assert np.array_equal(bits(grp.copy_quiz_priors(single)), bits(one.copy_quiz_priors(single_one)))
+    # the resumed quizzes go on: the asked bits were installed on every shard (an asked question is never chosen again)
+    randoms = rng.integers(0, 2 ** 64, size=len(ids_grp), dtype=np.uint64)
+    chosen = grp.next_question_batch(ids_grp, randoms)
+    for x, c in enumerate(chosen):
+        assert c not in {aq.i_question for aq in lists[x]}
+    one.set_active_question_batch(ids_one, chosen)
+    answers = [int(c) % K for c in chosen]
+    grp.record_answer_batch(ids_grp, answers); one.record_answer_batch(ids_one, answers)
+    for q in ids_grp:
+        assert np.array_equal(bits(grp.copy_quiz_priors(int(q))), bits(one.copy_quiz_priors(int(q))))
+    a, ca = grp.list_top_targets_batch(ids_grp, 10)
+    b, cb = one.list_top_targets_batch(ids_one, 10)
+    assert np.array_equal(ca, cb) and a.tobytes() == b.tobytes()
+    # ClearOldQuizzes: keep at most 3 quizzes (all have the same age here: the heap order decides, identically on both sides)
+    grp.clear_old_quizzes(3, 3600.0); one.clear_old_quizzes(3, 3600.0)
+    def alive(eng, q):
+        try:
+            eng.get_active_question_id(int(q))
+            return True
+        except pqa.PqaException:
+            return False
+    alive_g = [int(q) for q in list(ids_grp) + [single] if alive(grp, q)]
+    alive_o = [int(q) for q in list(ids_one) + [single_one] if alive(one, q)]
+    assert alive_g == alive_o and len(alive_g) == 3
+    assert grp.start_quiz() == one.start_quiz()            # released ids are reused in the same (LIFO) order
+    grp.clear_old_quizzes(0, -1.0); one.clear_old_quizzes(0, -1.0)
+    assert grp.start_quiz() == one.start_quiz()
+
+
 def test_group_serves_concurrent_one_quiz_clients():
     """Client threads call the reference's one-quiz entry points on a group handle; the shell's combiner turns them into
     exchanged batch launches on all shards. Every quiz must end with the posterior a single engine computes for the same
