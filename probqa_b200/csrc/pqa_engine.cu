@@ -1498,7 +1498,7 @@ PqaError *Engine::TShardPriority(int64_t n, const int64_t *pQuizIds) {
 // ---------------------------------------------------------------------------------------------------------
 // Shard exchange over peer memory. Inbox layout (identical on every shard; [2] = parity of the operation counter, so a
 // shard that runs ahead into the next operation never overwrites what a slower shard is still reading):
-//   0    flags[kMaxPeers] u64 (last epoch published by each rank)    64   error flag
+//   0    flags[kMaxPeers] u64 (last epoch published by each rank)    64   error flag    128  UUID of the owning GPU (16 bytes)
 //   1024 hand-over flags [kP2PMaxTiles] u64 (exact-order pipeline: the previous shard finished tile t of operation e)
 //   16384 W-ready flags  [kP2PMaxTiles] u64 (the last shard published the complete W_k of tile t)
 //   state [2][cap*Q*K*8]             Kahan lanes handed over by the previous shard               (target shards)
@@ -1545,6 +1545,11 @@ PqaError *Engine::P2PInit(int32_t rank, int32_t nRanks, int64_t maxQuizzes, void
   }
   PQA_CU(cudaMalloc(&p2pInbox_, p2pBytes_));
   PQA_CU(cudaMemsetAsync(p2pInbox_, 0, p2pBytes_, stream_));
+  {   // which physical GPU this inbox lives on: peers compare it with their own (P2PConnect)
+    cudaDeviceProp prop;
+    PQA_CU(cudaGetDeviceProperties(&prop, device_));
+    PQA_CU(cudaMemcpyAsync(p2pInbox_ + 128, &prop.uuid, 16, cudaMemcpyHostToDevice, stream_));
+  }
   preload_exchange_kernels((int)K_);
   // size every scratch buffer of the P2P calls now: growing one later would cudaFree, which waits for the whole device
   // -- including another engine's barrier kernel that is waiting for THIS engine (several engines in one process)
@@ -1600,7 +1605,15 @@ PqaError *Engine::P2PConnect(void *const *pBases) {
     // inboxes of other devices in this process need peer access; IPC-opened ones got it when they were opened
     cudaPointerAttributes at;
     PQA_CU(cudaPointerGetAttributes(&at, pBases[r]));
-    if (at.device == device_) p2pSameDevicePeer_ = true;
+    // A peer on the same physical GPU (tests; several processes or engines per GPU) changes how the exact-order pipeline
+    // waits. The pointer's device ordinal does not tell for an inbox opened through cudaIpc, the GPU's UUID in its header does.
+    {
+      cudaDeviceProp prop;
+      PQA_CU(cudaGetDeviceProperties(&prop, device_));
+      char peerUuid[16];
+      PQA_CU(cudaMemcpy(peerUuid, (const char *)pBases[r] + 128, 16, cudaMemcpyDeviceToHost));
+      if (std::memcmp(peerUuid, &prop.uuid, 16) == 0) p2pSameDevicePeer_ = true;
+    }
     if (at.device != device_) {
       PQA_CU(cudaSetDevice(device_));
       const cudaError_t e = cudaDeviceEnablePeerAccess(at.device, 0);
