@@ -1693,6 +1693,7 @@ PqaError *Engine::P2PNextQuestionBegin(int64_t n, const int64_t *pQuizIds, const
       const uint64_t opEpoch = p2pOps_;                      // identical on all shards, grows with every operation
       const int64_t gridY = tshard_quiz_tiles(n);
       int64_t tileQ = std::max<int64_t>(1, (2 * (int64_t)smCount_ + gridY - 1) / gridY);
+      if (const int64_t forced = env_int("PQA_B200_PIPE_TILE", 0)) tileQ = forced;      // experiments: questions per pipeline tile
       if ((Q_ + tileQ - 1) / tileQ > kP2PMaxTiles) tileQ = (Q_ + kP2PMaxTiles - 1) / kP2PMaxTiles;
       const bool first = p2pRank_ == 0, last = p2pRank_ == p2pRanks_ - 1;
       PipeCtl p1;

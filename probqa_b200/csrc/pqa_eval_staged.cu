@@ -902,7 +902,9 @@ struct TShardParams {
   PeerBufs outW, inW, outHVL;
   // Exact-order pipeline (phase 1 only): the 4-lane Kahan state (s, c) of every (quiz, question, answer) is handed from
   // shard to shard in target order, so the LAST shard finishes the reference's own sum: W_k bit-exact across shards.
-  // Layout [((b*Q + i)*K + k)*4 + lane]*2 + {s, c}. inState = the previous shard's hand-over (nullptr on the first
+  // Layout [((i*K + k)*4 + lane)*n + b]*2 + {s, c}: for one (question, answer, lane) the quizzes of the batch are contiguous,
+  // so a warp's store of one lane state is two runs of 256 bytes -- NVLink-sized writes into the next shard's inbox instead
+  // of sixteen 32-byte ones. inState = the previous shard's hand-over (nullptr on the first
   // shard), outState = the next shard's inbox (nullptr on the last shard, which writes W_k to outW instead).
   const double *inState;
   double *outState;
@@ -987,7 +989,7 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 4 ? 4 : 2) k_eval_tshard(
       for (int e = 0; e < KL; e++)
 #pragma unroll
         for (int k = 0; k < K; k++) {
-          const double2 sc = *reinterpret_cast<const double2 *>(TP.inState + (((o * K + k) * 4 + l0 + e) * 2));
+          const double2 sc = *reinterpret_cast<const double2 *>(TP.inState + ((((i * K + k) * 4 + l0 + e) * P.n + b) * 2));
           kw[e][k].s = sc.x; kw[e][k].c = sc.y;
         }
     }
@@ -1028,7 +1030,7 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 4 ? 4 : 2) k_eval_tshard(
       for (int e = 0; e < KL; e++)
 #pragma unroll
         for (int k = 0; k < K; k++)
-          *reinterpret_cast<double2 *>(TP.outState + (((o * K + k) * 4 + l0 + e) * 2)) = make_double2(kw[e][k].s, kw[e][k].c);
+          *reinterpret_cast<double2 *>(TP.outState + ((((i * K + k) * 4 + l0 + e) * P.n + b) * 2)) = make_double2(kw[e][k].s, kw[e][k].c);
     } else if (live) {
       finish_pass1<K, KL>(kw, W, iW, lW);
       if (l0 == 0) {

@@ -164,7 +164,7 @@ void launch_add_vb(const DeviceKB &kb, const int64_t *dTargets, const double *dA
 // W_k is needed before phase 2 because log2(lik/W_k) sits in the denominator of the lack term.
 // phase 1: outW.p[*][(b*Q + i)*K + k]
 // inState / outState (optional): exact-order pipeline -- the Kahan lanes (s, c) per (quiz, question, answer, lane),
-// [((b*Q + i)*K + k)*4 + lane]*2 doubles, continue from the previous shard's hand-over and go to the next shard instead
+// [((i*K + k)*4 + lane)*n + b]*2 doubles, continue from the previous shard's hand-over and go to the next shard instead
 // of being summed; the shard without outState finishes the reference's sum and writes the complete W_k to outW.
 // kbLocal.qFirst / qCount (with sA/mD pointing at row qFirst) select the questions of one pipeline tile.
 // In-kernel control of the exact-order pipeline. Questions are grouped into tiles of tileQ consecutive questions. A CTA
