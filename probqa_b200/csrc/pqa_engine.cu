@@ -146,7 +146,7 @@ Engine::~Engine() {
   cudaFree(dSA_); cudaFree(dMD_); cudaFree(dVB_); cudaFree(dLog2Tbl_);
   cudaFree(dDerR_);
   if (hFew_) cudaFreeHost((void *)hFew_);
-  cudaFree(dPriors_); cudaFree(dLogPriors_); cudaFree(dAsked_); cudaFree(dActive_);
+  cudaFree(dPriors_); cudaFree(dLogPriors_); cudaFree(dAsked_); cudaFree(dActive_); cudaFree(dNormS_);
   for (int r = 0; r < kMaxPeers; r++) if (p2pOpened_[r]) cudaIpcCloseMemHandle(p2pPeer_[r]);
   if (p2pInbox_) cudaFree(p2pInbox_);
   if (flushBuf_) cudaFree(flushBuf_);
@@ -224,7 +224,7 @@ void Engine::MarkQuestionsChanged(const std::vector<TrainOp> &ops) {
 }
 QuizPool Engine::pool() const {
   QuizPool p;
-  p.priors = dPriors_; p.logPriors = dLogPriors_; p.asked = dAsked_; p.active = dActive_;
+  p.priors = dPriors_; p.logPriors = dLogPriors_; p.asked = dAsked_; p.active = dActive_; p.normS = dNormS_;
   p.askedWords = askedWords_; p.Tp = Tp_;
   return p;
 }
@@ -232,7 +232,7 @@ QuizPool Engine::pool() const {
 void Engine::EnsureQuizCapacity(int64_t nSlots) {
   if (nSlots <= quizCap_) return;
   const int64_t cap = std::max<int64_t>(std::max<int64_t>(nSlots, quizCap_ * 2), 64);
-  double *np = nullptr, *nl = nullptr; uint64_t *na = nullptr; int64_t *nact = nullptr;
+  double *np = nullptr, *nl = nullptr, *ns = nullptr; uint64_t *na = nullptr; int64_t *nact = nullptr;
   // + one vector: the evaluation kernels prefetch the priors one 4-target vector ahead, also past a row's end
   PQA_CU(cudaMalloc(&np, sizeof(double) * (size_t)(cap * Tp_ + 4)));
   PQA_CU(cudaMalloc(&nl, sizeof(double) * (size_t)(cap * Tp_ + 4)));
@@ -240,15 +240,16 @@ void Engine::EnsureQuizCapacity(int64_t nSlots) {
   PQA_CU(cudaMemsetAsync(nl + cap * Tp_, 0, sizeof(double) * 4, stream_));
   PQA_CU(cudaMalloc(&na, sizeof(uint64_t) * (size_t)(cap * askedWords_)));
   PQA_CU(cudaMalloc(&nact, sizeof(int64_t) * (size_t)cap));
+  PQA_CU(cudaMalloc(&ns, sizeof(double) * (size_t)cap));
   if (quizCap_ > 0) {
     PQA_CU(cudaMemcpyAsync(np, dPriors_, sizeof(double) * (size_t)(quizCap_ * Tp_), cudaMemcpyDeviceToDevice, stream_));
     PQA_CU(cudaMemcpyAsync(nl, dLogPriors_, sizeof(double) * (size_t)(quizCap_ * Tp_), cudaMemcpyDeviceToDevice, stream_));
     PQA_CU(cudaMemcpyAsync(na, dAsked_, sizeof(uint64_t) * (size_t)(quizCap_ * askedWords_), cudaMemcpyDeviceToDevice, stream_));
     PQA_CU(cudaMemcpyAsync(nact, dActive_, sizeof(int64_t) * (size_t)quizCap_, cudaMemcpyDeviceToDevice, stream_));
     PQA_CU(cudaGetLastError()); PQA_CU(cudaStreamSynchronize(stream_));
-    cudaFree(dPriors_); cudaFree(dLogPriors_); cudaFree(dAsked_); cudaFree(dActive_);
+    cudaFree(dPriors_); cudaFree(dLogPriors_); cudaFree(dAsked_); cudaFree(dActive_); cudaFree(dNormS_);
   }
-  dPriors_ = np; dLogPriors_ = nl; dAsked_ = na; dActive_ = nact;
+  dPriors_ = np; dLogPriors_ = nl; dAsked_ = na; dActive_ = nact; dNormS_ = ns;
   quizCap_ = cap;
 }
 

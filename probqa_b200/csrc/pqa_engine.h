@@ -352,7 +352,7 @@ class Engine {
   PinBuf<int64_t> hDerList_;
   // quiz pool
   int64_t quizCap_ = 0;
-  double *dPriors_ = nullptr, *dLogPriors_ = nullptr;
+  double *dPriors_ = nullptr, *dLogPriors_ = nullptr, *dNormS_ = nullptr;
   uint64_t *dAsked_ = nullptr;
   int64_t *dActive_ = nullptr;
   std::vector<HostQuiz> quizzes_;

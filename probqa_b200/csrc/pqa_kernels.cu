@@ -157,15 +157,153 @@ __global__ void __launch_bounds__(256) k_update_priors(DeviceKB kb, QuizPool qp,
 
 static size_t priors_smem(int W) { return sizeof(double) * (size_t)(9 * W + 1); }
 
+// ---- long rows (T >= kLongRow): the same arithmetic spread over the chip. One CTA per quiz cannot feed a row of 10^5
+// targets: its 4W Kahan chains wait an L2 round trip per step and the divide / log2 sweep has 256 threads. Here
+//   k_update_lanes   one thread per (piece, AVX lane) chain of the reference's sum: it forms m[j] for its own elements
+//                    (so the row is read once), eight elements ahead of the dependent adds, stores the un-normalised row,
+//                    and the CTA finishes PreciseSum / the Kahan sum over the pieces -> S per quiz (qp.normS[slot])
+//   k_normalise_rows grid over (quiz, row chunks): prior = m / S, log2 prior
+// Operation for operation what k_update_priors / k_tshard_ra_finish do, hence the same bits.
+constexpr int64_t kLongRow = 8192;
+template <int MODE>  // 0 = StartQuiz, 1 = RecordAnswer, 2 = rows[] holds the complete un-normalised row (target shards)
+__global__ void __launch_bounds__(256) k_update_lanes(DeviceKB kb, QuizPool qp, const int64_t *__restrict__ slots,
+                                                       const int64_t *__restrict__ answers, const double *__restrict__ rows,
+                                                       int W) {
+  extern __shared__ double sm[];
+  double *laneS = sm, *laneC = sm + 4 * W, *pieceSum = sm + 8 * W;
+  const int64_t slot = slots[blockIdx.x];
+  double *prior = qp.priors + slot * qp.Tp;
+  const int64_t T = kb.T, Tp = kb.Tp;
+  const double *rowA = nullptr, *rowD = nullptr, *rowM = nullptr;
+  int64_t q = -1;
+  if (MODE != 0) q = qp.active[slot];
+  if (MODE == 1) {
+    if (q < 0) return;
+    if (q < kb.qFirst || q >= kb.qFirst + kb.qCount) {     // question owned by another shard: see k_update_priors
+      for (int64_t j = threadIdx.x; j < Tp; j += blockDim.x) prior[j] = 0.0;
+      if (threadIdx.x == 0) {
+        qp.asked[slot * qp.askedWords + (q >> 6)] |= 1ull << (q & 63);
+        qp.active[slot] = -1;
+        qp.normS[slot] = __longlong_as_double(0x7FF8000000000000ll);      // tells k_normalise_rows to leave the zeros alone
+      }
+      return;
+    }
+    const int64_t a = answers[blockIdx.x];
+    rowA = kb.sA + ((q - kb.qFirst) * kb.K + a) * Tp;
+    rowD = kb.mD + (q - kb.qFirst) * Tp;
+  }
+  if (MODE == 2) rowM = rows + (int64_t)blockIdx.x * qp.Tp;
+  const int64_t nVects = Tp >> 2;
+  const int64_t nPieces = split_count(nVects, W);
+  // rows are padded to Tp: every load below is unconditional (so that the eight steps' loads are all in flight before the
+  // first divide), the gap / padding mask is applied to the value
+  const double *src = MODE == 0 ? kb.vB : MODE == 1 ? prior : rowM;
+  auto value = [&](int64_t j, double x, double a, double d) -> double {
+    if (j >= T || bit32(kb.tgaps, j)) return 0.0;
+    return MODE == 1 ? __dmul_rn(x, __ddiv_rn(a, d)) : x;
+  };
+  const int64_t t = threadIdx.x;
+  if (t < nPieces * 4) {
+    const int64_t p = t >> 2, lane = t & 3;
+    const int64_t first = split_start(nVects, W, p), limit = split_start(nVects, W, p + 1);
+    Kahan k; k.init();
+    int64_t v = first;
+    // two batches of eight steps in flight: the loads of the next batch are issued before the dependent adds of this one
+    struct Batch { double x[8], a[8], d[8]; };
+    auto load = [&](Batch &bt, int64_t v0) {
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        const int64_t j = 4 * (v0 + u) + lane;
+        bt.x[u] = src[j];
+        bt.a[u] = MODE == 1 ? rowA[j] : 0.0;
+        bt.d[u] = MODE == 1 ? rowD[j] : 1.0;
+      }
+    };
+    auto process = [&](const Batch &bt, int64_t v0) {
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        const int64_t j = 4 * (v0 + u) + lane;
+        const double m = value(j, bt.x[u], bt.a[u], bt.d[u]);
+        prior[j] = m;
+        k.add(m);
+      }
+    };
+    Batch A, B;
+    if (v + 8 <= limit) {
+      load(A, v);
+      for (;;) {
+        if (v + 16 > limit) { process(A, v); v += 8; break; }
+        load(B, v + 8);
+        process(A, v); v += 8;
+        if (v + 16 > limit) { process(B, v); v += 8; break; }
+        load(A, v + 8);
+        process(B, v); v += 8;
+      }
+    }
+    for (; v < limit; v++) {
+      const int64_t j = 4 * v + lane;
+      const double m = value(j, src[j], MODE == 1 ? rowA[j] : 0.0, MODE == 1 ? rowD[j] : 1.0);
+      prior[j] = m;
+      k.add(m);
+    }
+    laneS[t] = k.s; laneC[t] = k.c;
+  }
+  __syncthreads();
+  for (int64_t p = threadIdx.x; p < nPieces; p += blockDim.x)
+    pieceSum[p] = precise_sum4(laneS[4 * p], laneS[4 * p + 1], laneS[4 * p + 2], laneS[4 * p + 3],
+                               laneC[4 * p], laneC[4 * p + 1], laneC[4 * p + 2], laneC[4 * p + 3]);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    Kahan k; k.init(0.0);
+    for (int64_t p = 0; p < nPieces; p++) k.add(pieceSum[p]);
+    qp.normS[slot] = k.get();
+    if (MODE == 0) {
+      for (int64_t w = 0; w < qp.askedWords; w++) qp.asked[slot * qp.askedWords + w] = 0;
+      qp.active[slot] = -1;
+    } else {
+      qp.asked[slot * qp.askedWords + (q >> 6)] |= 1ull << (q & 63);  // CEQuiz.h:91
+      qp.active[slot] = -1;                                           // CEQuiz.h:92
+    }
+  }
+}
+__global__ void __launch_bounds__(256) k_normalise_rows(QuizPool qp, const int64_t *__restrict__ slots, int64_t T) {
+  const int64_t slot = slots[blockIdx.y];
+  const double S = qp.normS[slot];
+  if (S != S) return;                                       // foreign-shard question: the row stays zero
+  double *prior = qp.priors + slot * qp.Tp, *lprior = qp.logPriors + slot * qp.Tp;
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < qp.Tp; j += (int64_t)gridDim.x * blockDim.x) {
+    const double v = j < T ? __ddiv_rn(prior[j], S) : 0.0;  // CEDivTargPriorsSubtask.h:16-21
+    prior[j] = v;
+    lprior[j] = log2(v);
+  }
+}
+static bool long_row_path(const QuizPool &qp, int64_t Tp, int W) {
+  return Tp >= kLongRow && qp.normS != nullptr && 4 * split_count(Tp >> 2, W) <= 256;
+}
+template <int MODE>
+static void launch_update_long(const DeviceKB &kb, const QuizPool &qp, int64_t n, const int64_t *dSlots, const int64_t *dAnswers,
+                               const double *dRows, int W, cudaStream_t st) {
+  const int threads = (int)((4 * split_count(kb.Tp >> 2, W) + 31) / 32 * 32);
+  k_update_lanes<MODE><<<(unsigned)n, threads, priors_smem(W), st>>>(kb, qp, dSlots, dAnswers, dRows, W);
+  count_launch();
+  int64_t gx = (kb.Tp + 255) / 256;
+  if (gx > 64) gx = 64;
+  k_normalise_rows<<<dim3((unsigned)gx, (unsigned)n), 256, 0, st>>>(qp, dSlots, kb.T);
+  count_launch();
+}
+
+
 void launch_start_quiz(const DeviceKB &kb, const QuizPool &qp, int64_t n, const int64_t *dSlots, int W,
                        cudaStream_t st) {
   if (n <= 0) return;
+  if (long_row_path(qp, kb.Tp, W)) { launch_update_long<0>(kb, qp, n, dSlots, nullptr, nullptr, W, st); return; }
   k_update_priors<0><<<(unsigned)n, 256, priors_smem(W), st>>>(kb, qp, dSlots, nullptr, W);
   count_launch();
 }
 void launch_record_answer(const DeviceKB &kb, const QuizPool &qp, int64_t n, const int64_t *dSlots,
                           const int64_t *dAnswers, int W, cudaStream_t st) {
   if (n <= 0) return;
+  if (long_row_path(qp, kb.Tp, W)) { launch_update_long<1>(kb, qp, n, dSlots, dAnswers, nullptr, W, st); return; }
   k_update_priors<1><<<(unsigned)n, 256, priors_smem(W), st>>>(kb, qp, dSlots, dAnswers, W);
   count_launch();
 }
@@ -214,6 +352,7 @@ __global__ void __launch_bounds__(256) k_tshard_ra_finish(DeviceKB kb, QuizPool 
 void launch_tshard_record_answer_finish(const DeviceKB &kbFull, const QuizPool &qp, int64_t n, const int64_t *dSlots,
                                         const double *dRows, int W, cudaStream_t st) {
   if (n <= 0) return;
+  if (long_row_path(qp, kbFull.Tp, W)) { launch_update_long<2>(kbFull, qp, n, dSlots, nullptr, dRows, W, st); return; }
   k_tshard_ra_finish<<<(unsigned)n, 256, priors_smem(W), st>>>(kbFull, qp, dSlots, dRows, W);
   count_launch();
 }
@@ -766,6 +905,11 @@ __device__ void head_down(HeadItem *first, int64_t len) {  // SRHeapHelper::Down
 }
 
 // Shared memory: W head items, W starts, W limits, then (if useSmem) T Rated items.
+// The piece heaps are built by the whole CTA. Compaction of a piece (CEHeapifyPriorsSubtaskMake.cpp:42-53) is a stable
+// filter: one warp per piece, ballot prefix. std::make_heap (:85-86) is a sequence of sift-downs from the last parent to
+// the root; the sift-downs of nodes on one tree level touch disjoint subtrees and every deeper level comes first in that
+// sequence, so running level by level -- all nodes of a level (of all pieces) in parallel, a barrier between levels --
+// leaves exactly the heap the sequential loop leaves, ties included. The k pops of the merge stay sequential (thread 0).
 __global__ void __launch_bounds__(256) k_list_top_targets(DeviceKB kb, QuizPool qp, const int64_t *__restrict__ slots,
                                                           int W, int64_t maxCount, Rated *__restrict__ scratch,
                                                           int useSmem, Rated *__restrict__ dest,
@@ -775,22 +919,49 @@ __global__ void __launch_bounds__(256) k_list_top_targets(DeviceKB kb, QuizPool 
   int64_t *starts = (int64_t *)(head + W);
   int64_t *limits = starts + W;
   Rated *ratings = useSmem ? (Rated *)(limits + W) : scratch + (int64_t)blockIdx.x * kb.T;
+  __shared__ int sMaxLen;
   const int64_t b = blockIdx.x, slot = slots[b], T = kb.T;
   const double *prior = qp.priors + slot * qp.Tp;
   const int64_t nPieces = split_count(T, W);
-  for (int64_t p = threadIdx.x; p < nPieces; p += blockDim.x) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nWarps = blockDim.x >> 5;
+  if (threadIdx.x == 0) sMaxLen = 0;
+  __syncthreads();
+  for (int64_t p = warp; p < nPieces; p += nWarps) {      // CEHeapifyPriorsSubtaskMake.cpp:42-53
     const int64_t first = split_start(T, W, p), limit = split_start(T, W, p + 1);
     int64_t sel = first;
-    for (int64_t j = first; j < limit; j++) {            // CEHeapifyPriorsSubtaskMake.cpp:42-53
-      if (bit32(kb.tgaps, j)) continue;
-      const double prob = prior[j];
-      if (prob <= 0) continue;
-      ratings[sel].prob = prob; ratings[sel].iTarget = j; sel++;
+    for (int64_t base = first; base < limit; base += 32) {
+      const int64_t j = base + lane;
+      double prob = 0.0;
+      bool keep = false;
+      if (j < limit && !bit32(kb.tgaps, j)) { prob = prior[j]; keep = prob > 0; }
+      const unsigned mask = __ballot_sync(0xffffffffu, keep);
+      if (keep) {
+        const int64_t at = sel + __popc(mask & ((1u << lane) - 1u));
+        ratings[at].prob = prob; ratings[at].iTarget = j;
+      }
+      sel += __popc(mask);
     }
-    starts[p] = first; limits[p] = sel;
-    heap_make(ratings + first, sel - first);             // :85-86
+    if (lane == 0) { starts[p] = first; limits[p] = sel; atomicMax(&sMaxLen, (int)(sel - first)); }
   }
   __syncthreads();
+  // std::make_heap of every piece (:85-86), level by level from the deepest parents up
+  const int maxLen = sMaxLen;
+  if (maxLen >= 2) {
+    int depth = 0;
+    while ((2ll << depth) - 1 <= (maxLen - 2) / 2) depth++;          // deepest level that holds a parent
+    for (int d = depth; d >= 0; d--) {
+      const int64_t perPiece = 1ll << d, total = nPieces * perPiece;
+      for (int64_t x = threadIdx.x; x < total; x += blockDim.x) {
+        const int64_t p = x >> d, node = perPiece - 1 + (x & (perPiece - 1));
+        const int64_t len = limits[p] - starts[p];
+        if (len < 2 || node > (len - 2) / 2) continue;
+        Rated *first = ratings + starts[p];
+        const Rated value = first[node];
+        heap_adjust(first, node, len, value);
+      }
+      __syncthreads();
+    }
+  }
   if (threadIdx.x != 0) return;
   int64_t nHh = 0;
   for (int64_t p = 0; p < nPieces; p++) {                // CEListTopTargetsAlgorithm.cpp:57-66
@@ -829,8 +1000,7 @@ void launch_list_top_targets(const DeviceKB &kb, const QuizPool &qp, int64_t n, 
     cudaFuncSetAttribute(k_list_top_targets, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     attrDevices.fetch_or(1ull << (attrDev & 63), std::memory_order_relaxed);
   }
-  int block = 32;
-  while (block < W && block < 256) block <<= 1;
+  const int block = kb.T >= 4096 ? 256 : 128;     // the whole CTA builds the piece heaps level by level
   k_list_top_targets<<<(unsigned)n, block, smem, st>>>(kb, qp, dSlots, W, maxCount, (Rated *)dScratch, useSmem,
                                                        (Rated *)dDest, dCounts);
   count_launch();
@@ -904,6 +1074,10 @@ void preload_exchange_kernels(int K) {
   cudaFuncGetAttributes(&a, k_update_priors<1>);
   cudaFuncGetAttributes(&a, k_tshard_ra_partial);
   cudaFuncGetAttributes(&a, k_tshard_ra_finish);
+  cudaFuncGetAttributes(&a, k_update_lanes<0>);
+  cudaFuncGetAttributes(&a, k_update_lanes<1>);
+  cudaFuncGetAttributes(&a, k_update_lanes<2>);
+  cudaFuncGetAttributes(&a, k_normalise_rows);
   cudaFuncGetAttributes(&a, k_p2p_barrier);
   cudaFuncGetAttributes(&a, k_p2p_wait);
   cudaFuncGetAttributes(&a, k_p2p_signal);

@@ -38,6 +38,7 @@ struct QuizPool {
   double *logPriors;       // [slot][Tp]  log2 of priors (derived; rewritten whenever priors are)
   uint64_t *asked;         // [slot][askedWords]  bit i = question i already answered (CEBaseQuiz _isQAsked)
   int64_t *active;         // [slot] active question or -1 (BaseQuiz.h _activeQuestion)
+  double *normS = nullptr; // [slot] normaliser of the row being updated (long rows: two-kernel update, pqa_kernels.cu)
   int64_t askedWords;      // ceil(Q/64)
   int64_t Tp;
 };

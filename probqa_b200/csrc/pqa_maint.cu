@@ -155,8 +155,8 @@ void Engine::SyncGapBits() {
 void Engine::DropQuizPool() {
   if (quizCap_ > 0) {
     PQA_CU(cudaStreamSynchronize(stream_));
-    cudaFree(dPriors_); cudaFree(dLogPriors_); cudaFree(dAsked_); cudaFree(dActive_);
-    dPriors_ = dLogPriors_ = nullptr; dAsked_ = nullptr; dActive_ = nullptr;
+    cudaFree(dPriors_); cudaFree(dLogPriors_); cudaFree(dAsked_); cudaFree(dActive_); cudaFree(dNormS_);
+    dPriors_ = dLogPriors_ = dNormS_ = nullptr; dAsked_ = nullptr; dActive_ = nullptr;
     quizCap_ = 0;
   }
   residentN_ = 0;
