@@ -24,6 +24,14 @@ Factory g_factory;
 inline Engine *E(void *pv) { return static_cast<Engine *>(pv); }
 
 PqaError *NullEngine() { return MakeError(ErrCode::NullArgument, "pvEngine is NULL"); }
+// Every entry point that enters an engine passes here first: a NULL handle, or an engine after PqaEngine_Shutdown
+// (MaintenanceSwitch.h:138-141: operations on a shut-down engine fail with ObjectShutDown).
+PqaError *Gate(void *pvEngine) {
+  if (!pvEngine) return NullEngine();
+  if (static_cast<Engine *>(pvEngine)->IsShutDown())
+    return MakeError(ErrCode::ObjectShutDown, "The engine is shut down.", "MaintenanceSwitch::TryEnterSpecific()");
+  return nullptr;
+}
 
 // ReturnPqaError (PqaCInterop.cpp:56-61): NULL on success, owned error otherwise.
 inline void *Ret(PqaError *e) { return e; }
@@ -172,7 +180,7 @@ PQACORE_API void *PqaB200_LoadEngine(void **ppError, const char *filePath, const
   return eng;
 }
 PQACORE_API void *PqaB200_SaveKBShard(void *pvEngine, const char *filePath, int32_t writeFrame) {
-  if (!pvEngine) return NullEngine();
+  if (PqaError *g_ = Gate(pvEngine)) return g_;
   return Ret(Guard([&] { return E(pvEngine)->SaveKBShard(filePath, writeFrame != 0); }));
 }
 
@@ -188,13 +196,13 @@ PQACORE_API void CiReleasePqaEngine(void *pvEngine) { delete E(pvEngine); }
 
 PQACORE_API void *PqaEngine_Train(void *pvEngine, int64_t nQuestions, const CiAnsweredQuestion *const pAQs,
                                   const int64_t iTarget, const double amount) {
-  if (!pvEngine) return NullEngine();
+  if (PqaError *g_ = Gate(pvEngine)) return g_;
   return Ret(Guard([&] { return E(pvEngine)->Train(nQuestions, pAQs, iTarget, amount); }));
 }
 
 // Permanent <-> compact id maps (BaseEngine.cpp:154-218, PermanentIdManager.cpp); ids that do not map give -1.
 static uint8_t MapIds(void *pvEngine, int kind, bool permFromComp, int64_t count, int64_t *pIds) {
-  if (!pvEngine || (count > 0 && !pIds)) return 0;
+  if (!pvEngine || E(pvEngine)->IsShutDown() || (count > 0 && !pIds)) return 0;
   return E(pvEngine)->MapIds(kind, permFromComp, count, pIds) ? 1 : 0;
 }
 PQACORE_API uint8_t PqaEngine_QuestionPermFromComp(void *pvEngine, const int64_t count, int64_t *pIds) { return MapIds(pvEngine, 0, true, count, pIds); }
@@ -204,117 +212,126 @@ PQACORE_API uint8_t PqaEngine_TargetCompFromPerm(void *pvEngine, const int64_t c
 PQACORE_API uint8_t PqaEngine_QuizPermFromComp(void *pvEngine, const int64_t count, int64_t *pIds) { return MapIds(pvEngine, 2, true, count, pIds); }
 PQACORE_API uint8_t PqaEngine_QuizCompFromPerm(void *pvEngine, const int64_t count, int64_t *pIds) { return MapIds(pvEngine, 2, false, count, pIds); }
 PQACORE_API uint8_t PqaEngine_EnsurePermQuizGreater(void *pvEngine, const int64_t bound) {
-  return pvEngine && E(pvEngine)->EnsurePermQuizGreater(bound) ? 1 : 0;
+  return pvEngine && !E(pvEngine)->IsShutDown() && E(pvEngine)->EnsurePermQuizGreater(bound) ? 1 : 0;
 }
 PQACORE_API uint8_t PqaEngine_RemapQuizPermId(void *pvEngine, const int64_t srcPermId, const int64_t destPermId) {
-  return pvEngine && E(pvEngine)->RemapQuizPermId(srcPermId, destPermId) ? 1 : 0;
+  return pvEngine && !E(pvEngine)->IsShutDown() && E(pvEngine)->RemapQuizPermId(srcPermId, destPermId) ? 1 : 0;
 }
 
 PQACORE_API uint64_t PqaEngine_GetTotalQuestionsAsked(void *pvEngine, void **ppError) {
-  if (!pvEngine) { Assign(ppError, NullEngine()); return 0; }
+  if (PqaError *g_ = Gate(pvEngine)) { Assign(ppError, g_); return 0; }
   Assign(ppError, nullptr);
   return E(pvEngine)->GetTotalQuestionsAsked();
 }
 PQACORE_API uint8_t PqaEngine_CopyDims(void *pvEngine, CiEngineDimensions *pDims) {
   if (!pvEngine || !pDims) return 0;
-  *pDims = E(pvEngine)->CopyDims();
+  *pDims = E(pvEngine)->IsShutDown() ? CiEngineDimensions{0, 0, 0} : E(pvEngine)->CopyDims();   // BaseEngine.cpp:315
   return 1;
 }
 PQACORE_API int64_t PqaEngine_StartQuiz(void *pvEngine, void **ppError) {
-  if (!pvEngine) { Assign(ppError, NullEngine()); return -1; }
+  if (PqaError *g_ = Gate(pvEngine)) { Assign(ppError, g_); return -1; }
   PqaError *err = nullptr;
-  const int64_t id = E(pvEngine)->StartQuiz(&err);
+  int64_t id = -1;
+  PqaError *g = Guard([&]() -> PqaError * { id = E(pvEngine)->StartQuiz(&err); return nullptr; });
+  if (g) { delete err; err = g; id = -1; }
   Assign(ppError, err);
   return id;
 }
 PQACORE_API int64_t PqaEngine_ResumeQuiz(void *pvEngine, void **ppError, const int64_t nAnswered,
                                          const CiAnsweredQuestion *const pAQs) {
-  if (!pvEngine) { Assign(ppError, NullEngine()); return -1; }
+  if (PqaError *g_ = Gate(pvEngine)) { Assign(ppError, g_); return -1; }
   PqaError *err = nullptr;
-  const int64_t id = E(pvEngine)->ResumeQuiz(&err, nAnswered, pAQs);
+  int64_t id = -1;
+  PqaError *g = Guard([&]() -> PqaError * { id = E(pvEngine)->ResumeQuiz(&err, nAnswered, pAQs); return nullptr; });
+  if (g) { delete err; err = g; id = -1; }
   Assign(ppError, err);
   return id;
 }
 PQACORE_API int64_t PqaEngine_NextQuestion(void *pvEngine, void **ppError, const int64_t iQuiz) {
-  if (!pvEngine) { Assign(ppError, NullEngine()); return -1; }
+  if (PqaError *g_ = Gate(pvEngine)) { Assign(ppError, g_); return -1; }
   PqaError *err = nullptr;
-  const int64_t q = E(pvEngine)->NextQuestion(&err, iQuiz);
+  int64_t q = -1;
+  PqaError *g = Guard([&]() -> PqaError * { q = E(pvEngine)->NextQuestion(&err, iQuiz); return nullptr; });
+  if (g) { delete err; err = g; q = -1; }
   Assign(ppError, err);
   return q;
 }
 PQACORE_API void *PqaEngine_RecordAnswer(void *pvEngine, const int64_t iQuiz, const int64_t iAnswer) {
-  if (!pvEngine) return NullEngine();
-  return Ret(E(pvEngine)->RecordAnswer(iQuiz, iAnswer));
+  if (PqaError *g_ = Gate(pvEngine)) return g_;
+  return Ret(Guard([&] { return E(pvEngine)->RecordAnswer(iQuiz, iAnswer); }));
 }
 PQACORE_API void *PqaEngine_ClearOldQuizzes(void *pvEngine, const int64_t maxCount, const double maxAgeSec) {
-  if (!pvEngine) return NullEngine();
+  if (PqaError *g_ = Gate(pvEngine)) return g_;
   return Ret(Guard([&] { return E(pvEngine)->ClearOldQuizzes(maxCount, maxAgeSec); }));
 }
 PQACORE_API int64_t PqaEngine_GetActiveQuestionId(void *pvEngine, void **ppError, const int64_t iQuiz) {
-  if (!pvEngine) { Assign(ppError, NullEngine()); return -1; }
+  if (PqaError *g_ = Gate(pvEngine)) { Assign(ppError, g_); return -1; }
   PqaError *err = nullptr;
-  const int64_t q = E(pvEngine)->GetActiveQuestionId(&err, iQuiz);
+  int64_t q = -1;
+  PqaError *g = Guard([&]() -> PqaError * { q = E(pvEngine)->GetActiveQuestionId(&err, iQuiz); return nullptr; });
+  if (g) { delete err; err = g; q = -1; }
   Assign(ppError, err);
   return q;
 }
 PQACORE_API void *PqaEngine_SetActiveQuestion(void *pvEngine, const int64_t iQuiz, const int64_t iQuestion) {
-  if (!pvEngine) return NullEngine();
-  return Ret(E(pvEngine)->SetActiveQuestion(iQuiz, iQuestion));
+  if (PqaError *g_ = Gate(pvEngine)) return g_;
+  return Ret(Guard([&] { return E(pvEngine)->SetActiveQuestion(iQuiz, iQuestion); }));
 }
 PQACORE_API int64_t PqaEngine_ListTopTargets(void *pvEngine, void **ppError, const int64_t iQuiz,
                                              const int64_t maxCount, CiRatedTarget *pDest) {
-  if (!pvEngine) { Assign(ppError, NullEngine()); return -1; }
+  if (PqaError *g_ = Gate(pvEngine)) { Assign(ppError, g_); return -1; }
   PqaError *err = nullptr;
-  const int64_t n = E(pvEngine)->ListTopTargets(&err, iQuiz, maxCount, pDest);
+  int64_t n = -1;
+  PqaError *g = Guard([&]() -> PqaError * { n = E(pvEngine)->ListTopTargets(&err, iQuiz, maxCount, pDest); return nullptr; });
+  if (g) { delete err; err = g; n = -1; }
   Assign(ppError, err);
   return n;
 }
 PQACORE_API void *PqaEngine_RecordQuizTarget(void *pvEngine, const int64_t iQuiz, const int64_t iTarget,
                                              const double amount) {
-  if (!pvEngine) return NullEngine();
-  return Ret(E(pvEngine)->RecordQuizTarget(iQuiz, iTarget, amount));
+  if (PqaError *g_ = Gate(pvEngine)) return g_;
+  return Ret(Guard([&] { return E(pvEngine)->RecordQuizTarget(iQuiz, iTarget, amount); }));
 }
 PQACORE_API void *PqaEngine_ReleaseQuiz(void *pvEngine, const int64_t iQuiz) {
-  if (!pvEngine) return NullEngine();
-  return Ret(E(pvEngine)->ReleaseQuiz(iQuiz));
+  if (PqaError *g_ = Gate(pvEngine)) return g_;
+  return Ret(Guard([&] { return E(pvEngine)->ReleaseQuiz(iQuiz); }));
 }
 PQACORE_API void *PqaEngine_SaveKB(void *pvEngine, const char *const filePath, const uint8_t bDoubleBuffer) {
   (void)bDoubleBuffer;
-  if (!pvEngine) return NullEngine();
+  if (PqaError *g_ = Gate(pvEngine)) return g_;
   return Ret(Guard([&] { return E(pvEngine)->SaveKB(filePath); }));
 }
 
 PQACORE_API void *PqaEngine_StartMaintenance(void *pvEngine, const bool forceQuizzes) {
-  if (!pvEngine) return NullEngine();
+  if (PqaError *g_ = Gate(pvEngine)) return g_;
   return Ret(Guard([&] { return E(pvEngine)->StartMaintenance(forceQuizzes); }));
 }
 PQACORE_API void *PqaEngine_FinishMaintenance(void *pvEngine) {
-  if (!pvEngine) return NullEngine();
+  if (PqaError *g_ = Gate(pvEngine)) return g_;
   return Ret(Guard([&] { return E(pvEngine)->FinishMaintenance(); }));
 }
 PQACORE_API void *PqaEngine_AddQsTs(void *pvEngine, const int64_t nQuestions, CiAddQorTParam *pAddQuestionParams,
                                     const int64_t nTargets, CiAddQorTParam *pAddTargetParams) {
-  if (!pvEngine) return NullEngine();
+  if (PqaError *g_ = Gate(pvEngine)) return g_;
   return Ret(Guard([&] { return E(pvEngine)->AddQsTs(nQuestions, pAddQuestionParams, nTargets, pAddTargetParams); }));
 }
 PQACORE_API void *PqaEngine_RemoveQuestions(void *pvEngine, const int64_t nQuestions, const int64_t *pQIds) {
-  if (!pvEngine) return NullEngine();
+  if (PqaError *g_ = Gate(pvEngine)) return g_;
   return Ret(Guard([&] { return E(pvEngine)->RemoveQuestions(nQuestions, pQIds); }));
 }
 PQACORE_API void *PqaEngine_RemoveTargets(void *pvEngine, const int64_t nTargets, const int64_t *pTIds) {
-  if (!pvEngine) return NullEngine();
+  if (PqaError *g_ = Gate(pvEngine)) return g_;
   return Ret(Guard([&] { return E(pvEngine)->RemoveTargets(nTargets, pTIds); }));
 }
 PQACORE_API void *PqaEngine_Compact(void *pvEngine, int64_t *pnQuestions, int64_t const **const ppOldQuestions,
                                     int64_t *pnTargets, int64_t const **const ppOldTargets) {
-  if (!pvEngine) return NullEngine();
+  if (PqaError *g_ = Gate(pvEngine)) return g_;
   return Ret(Guard([&] { return E(pvEngine)->Compact(pnQuestions, ppOldQuestions, pnTargets, ppOldTargets); }));
 }
 PQACORE_API void CiReleaseCompaction(const int64_t *p) { delete[] p; }
 PQACORE_API void *PqaEngine_Shutdown(void *pvEngine, const char *const saveFilePath) {
   if (!pvEngine) return NullEngine();
-  if (saveFilePath && *saveFilePath) return Ret(Guard([&] { return E(pvEngine)->SaveKB(saveFilePath); }));
-  return Ret(E(pvEngine)->Synchronize());
+  return Ret(Guard([&] { return E(pvEngine)->Shutdown(saveFilePath); }));      // a second Shutdown answers ObjectShutDown itself
 }
 PQACORE_API void *PqaEngine_SetLogger(void *pvEngine, void *pSRLogger) {
   (void)pSRLogger;
@@ -335,199 +352,199 @@ PQACORE_API void *PqaB200_HostLogicSelfTest(void) {
   return out;
 }
 PQACORE_API void *PqaEngine_CopyATargets(void *pvEngine, int64_t iQuestion, int64_t iAnswer, int64_t maxTargets, double *pFreqs) {
-  if (!pvEngine) return NullEngine();
-  return Ret(E(pvEngine)->CopyATargets(iQuestion, iAnswer, maxTargets, pFreqs));
+  if (PqaError *g_ = Gate(pvEngine)) return g_;
+  return Ret(Guard([&] { return E(pvEngine)->CopyATargets(iQuestion, iAnswer, maxTargets, pFreqs); }));
 }
 PQACORE_API void *PqaEngine_CopyDTargets(void *pvEngine, int64_t iQuestion, int64_t maxTargets, double *pFreqs) {
-  if (!pvEngine) return NullEngine();
-  return Ret(E(pvEngine)->CopyDTargets(iQuestion, maxTargets, pFreqs));
+  if (PqaError *g_ = Gate(pvEngine)) return g_;
+  return Ret(Guard([&] { return E(pvEngine)->CopyDTargets(iQuestion, maxTargets, pFreqs); }));
 }
 PQACORE_API void *PqaEngine_CopyBTargets(void *pvEngine, int64_t maxTargets, double *pFreqs) {
-  if (!pvEngine) return NullEngine();
-  return Ret(E(pvEngine)->CopyBTargets(maxTargets, pFreqs));
+  if (PqaError *g_ = Gate(pvEngine)) return g_;
+  return Ret(Guard([&] { return E(pvEngine)->CopyBTargets(maxTargets, pFreqs); }));
 }
 PQACORE_API void *PqaB200_UploadKB(void *pvEngine, const double *sA, const double *mD, const double *vB) {
-  if (!pvEngine) return NullEngine();
-  return Ret(E(pvEngine)->UploadKB(sA, mD, vB));
+  if (PqaError *g_ = Gate(pvEngine)) return g_;
+  return Ret(Guard([&] { return E(pvEngine)->UploadKB(sA, mD, vB); }));
 }
 PQACORE_API void *PqaB200_DownloadKB(void *pvEngine, double *sA, double *mD, double *vB) {
-  if (!pvEngine) return NullEngine();
-  return Ret(E(pvEngine)->DownloadKB(sA, mD, vB));
+  if (PqaError *g_ = Gate(pvEngine)) return g_;
+  return Ret(Guard([&] { return E(pvEngine)->DownloadKB(sA, mD, vB); }));
 }
 PQACORE_API void *PqaEngine_StartQuizBatch(void *pvEngine, int64_t n, int64_t *pQuizIds) {
-  if (!pvEngine) return NullEngine();
-  return Ret(E(pvEngine)->StartQuizBatch(n, pQuizIds));
+  if (PqaError *g_ = Gate(pvEngine)) return g_;
+  return Ret(Guard([&] { return E(pvEngine)->StartQuizBatch(n, pQuizIds); }));
 }
 PQACORE_API void *PqaEngine_ResumeQuizBatch(void *pvEngine, int64_t n, const int64_t *pCounts, const CiAnsweredQuestion *pAQs,
                                             int64_t *pQuizIds) {
-  if (!pvEngine) return NullEngine();
+  if (PqaError *g_ = Gate(pvEngine)) return g_;
   return Ret(Guard([&] { return E(pvEngine)->ResumeQuizBatch(n, pCounts, pAQs, pQuizIds); }));
 }
 PQACORE_API void *PqaEngine_NextQuestionBatch(void *pvEngine, int64_t n, const int64_t *pQuizIds,
                                               const uint64_t *pRandoms, int64_t *pQuestions, void **ppErrors) {
-  if (!pvEngine) return NullEngine();
-  return Ret(E(pvEngine)->NextQuestionBatch(n, pQuizIds, pRandoms, pQuestions, ppErrors));
+  if (PqaError *g_ = Gate(pvEngine)) return g_;
+  return Ret(Guard([&] { return E(pvEngine)->NextQuestionBatch(n, pQuizIds, pRandoms, pQuestions, ppErrors); }));
 }
 PQACORE_API void *PqaEngine_RecordAnswerBatch(void *pvEngine, int64_t n, const int64_t *pQuizIds, const int64_t *pAnswers) {
-  if (!pvEngine) return NullEngine();
-  return Ret(E(pvEngine)->RecordAnswerBatch(n, pQuizIds, pAnswers));
+  if (PqaError *g_ = Gate(pvEngine)) return g_;
+  return Ret(Guard([&] { return E(pvEngine)->RecordAnswerBatch(n, pQuizIds, pAnswers); }));
 }
 PQACORE_API void *PqaEngine_SetActiveQuestionBatch(void *pvEngine, int64_t n, const int64_t *pQuizIds, const int64_t *pQuestions) {
-  if (!pvEngine) return NullEngine();
-  return Ret(E(pvEngine)->SetActiveQuestionBatch(n, pQuizIds, pQuestions));
+  if (PqaError *g_ = Gate(pvEngine)) return g_;
+  return Ret(Guard([&] { return E(pvEngine)->SetActiveQuestionBatch(n, pQuizIds, pQuestions); }));
 }
 PQACORE_API void *PqaEngine_ListTopTargetsBatch(void *pvEngine, int64_t n, const int64_t *pQuizIds, int64_t maxCount,
                                                 CiRatedTarget *pDest, int64_t *pCounts) {
-  if (!pvEngine) return NullEngine();
-  return Ret(E(pvEngine)->ListTopTargetsBatch(n, pQuizIds, maxCount, pDest, pCounts));
+  if (PqaError *g_ = Gate(pvEngine)) return g_;
+  return Ret(Guard([&] { return E(pvEngine)->ListTopTargetsBatch(n, pQuizIds, maxCount, pDest, pCounts); }));
 }
 PQACORE_API void *PqaEngine_RecordQuizTargetBatch(void *pvEngine, int64_t n, const int64_t *pQuizIds,
                                                   const int64_t *pTargets, const double *pAmounts) {
-  if (!pvEngine) return NullEngine();
+  if (PqaError *g_ = Gate(pvEngine)) return g_;
   return Ret(Guard([&] { return E(pvEngine)->RecordQuizTargetBatch(n, pQuizIds, pTargets, pAmounts); }));
 }
 PQACORE_API void *PqaEngine_ReleaseQuizBatch(void *pvEngine, int64_t n, const int64_t *pQuizIds) {
-  if (!pvEngine) return NullEngine();
-  return Ret(E(pvEngine)->ReleaseQuizBatch(n, pQuizIds));
+  if (PqaError *g_ = Gate(pvEngine)) return g_;
+  return Ret(Guard([&] { return E(pvEngine)->ReleaseQuizBatch(n, pQuizIds); }));
 }
 PQACORE_API void *PqaB200_CopyQuizPriors(void *pvEngine, int64_t iQuiz, double *pPriors) {
-  if (!pvEngine) return NullEngine();
-  return Ret(E(pvEngine)->CopyQuizPriors(iQuiz, pPriors));
+  if (PqaError *g_ = Gate(pvEngine)) return g_;
+  return Ret(Guard([&] { return E(pvEngine)->CopyQuizPriors(iQuiz, pPriors); }));
 }
 PQACORE_API void *PqaB200_SetQuizPriors(void *pvEngine, int64_t iQuiz, const double *pPriors) {
-  if (!pvEngine) return NullEngine();
-  return Ret(E(pvEngine)->SetQuizPriors(iQuiz, pPriors));
+  if (PqaError *g_ = Gate(pvEngine)) return g_;
+  return Ret(Guard([&] { return E(pvEngine)->SetQuizPriors(iQuiz, pPriors); }));
 }
 PQACORE_API void *PqaB200_EvalQuestions(void *pvEngine, int64_t n, const int64_t *pQuizIds, double *pPriorities,
                                         double *pRunLength, double *pGrandTotals, int64_t *pnChunks) {
-  if (!pvEngine) return NullEngine();
-  return Ret(E(pvEngine)->EvalQuestions(n, pQuizIds, pPriorities, pRunLength, pGrandTotals, pnChunks));
+  if (PqaError *g_ = Gate(pvEngine)) return g_;
+  return Ret(Guard([&] { return E(pvEngine)->EvalQuestions(n, pQuizIds, pPriorities, pRunLength, pGrandTotals, pnChunks); }));
 }
 PQACORE_API void *PqaB200_EvalQuestionsDetailed(void *pvEngine, int64_t iQuiz, double *pW, double *pH, double *pV,
                                                 double *pLack, double *pPriorities) {
-  if (!pvEngine) return NullEngine();
-  return Ret(E(pvEngine)->EvalQuestionsDetailed(iQuiz, pW, pH, pV, pLack, pPriorities));
+  if (PqaError *g_ = Gate(pvEngine)) return g_;
+  return Ret(Guard([&] { return E(pvEngine)->EvalQuestionsDetailed(iQuiz, pW, pH, pV, pLack, pPriorities); }));
 }
 PQACORE_API void *PqaB200_EvalQuestionsDetailedBatch(void *pvEngine, int64_t n, const int64_t *pQuizIds, double *pW, double *pH,
                                                      double *pV, double *pLack, double *pPriorities) {
-  if (!pvEngine) return NullEngine();
-  return Ret(E(pvEngine)->EvalQuestionsDetailedBatch(n, pQuizIds, pW, pH, pV, pLack, pPriorities));
+  if (PqaError *g_ = Gate(pvEngine)) return g_;
+  return Ret(Guard([&] { return E(pvEngine)->EvalQuestionsDetailedBatch(n, pQuizIds, pW, pH, pV, pLack, pPriorities); }));
 }
 PQACORE_API void *PqaB200_SetEvalKernel(void *pvEngine, int32_t which) {
-  if (!pvEngine) return NullEngine();
-  return Ret(E(pvEngine)->SetEvalKernel(which, 0, 0, 0));
+  if (PqaError *g_ = Gate(pvEngine)) return g_;
+  return Ret(Guard([&] { return E(pvEngine)->SetEvalKernel(which, 0, 0, 0); }));
 }
 PQACORE_API void *PqaB200_SetEvalTuning(void *pvEngine, int32_t which, int64_t chunkTargets, int64_t quizzesPerCta,
                                         int32_t kahanLanesPerThread) {
-  if (!pvEngine) return NullEngine();
-  return Ret(E(pvEngine)->SetEvalKernel(which, chunkTargets, quizzesPerCta, kahanLanesPerThread));
+  if (PqaError *g_ = Gate(pvEngine)) return g_;
+  return Ret(Guard([&] { return E(pvEngine)->SetEvalKernel(which, chunkTargets, quizzesPerCta, kahanLanesPerThread); }));
 }
 PQACORE_API void *PqaB200_ShardEval(void *pvEngine, int64_t n, const int64_t *pQuizIds) {
-  if (!pvEngine) return NullEngine();
-  return Ret(E(pvEngine)->ShardEval(n, pQuizIds));
+  if (PqaError *g_ = Gate(pvEngine)) return g_;
+  return Ret(Guard([&] { return E(pvEngine)->ShardEval(n, pQuizIds); }));
 }
 PQACORE_API void *PqaB200_ShardSelect(void *pvEngine, int64_t n, const int64_t *pQuizIds, const uint64_t *pRandoms,
                                       int64_t *pQuestions, void **ppErrors) {
-  if (!pvEngine) return NullEngine();
-  return Ret(E(pvEngine)->ShardSelect(n, pQuizIds, pRandoms, pQuestions, ppErrors));
+  if (PqaError *g_ = Gate(pvEngine)) return g_;
+  return Ret(Guard([&] { return E(pvEngine)->ShardSelect(n, pQuizIds, pRandoms, pQuestions, ppErrors); }));
 }
 PQACORE_API void *PqaB200_ShardRecordAnswerBegin(void *pvEngine, int64_t n, const int64_t *pQuizIds, const int64_t *pAnswers) {
-  if (!pvEngine) return NullEngine();
-  return Ret(E(pvEngine)->ShardRecordAnswerBegin(n, pQuizIds, pAnswers));
+  if (PqaError *g_ = Gate(pvEngine)) return g_;
+  return Ret(Guard([&] { return E(pvEngine)->ShardRecordAnswerBegin(n, pQuizIds, pAnswers); }));
 }
 PQACORE_API void *PqaB200_ShardRecordAnswerEnd(void *pvEngine, int64_t n, const int64_t *pQuizIds) {
-  if (!pvEngine) return NullEngine();
-  return Ret(E(pvEngine)->ShardRecordAnswerEnd(n, pQuizIds));
+  if (PqaError *g_ = Gate(pvEngine)) return g_;
+  return Ret(Guard([&] { return E(pvEngine)->ShardRecordAnswerEnd(n, pQuizIds); }));
 }
 PQACORE_API void *PqaB200_ShardBuffer(void *pvEngine, int32_t which, void **ppDevice, int64_t *pCount) {
-  if (!pvEngine) return NullEngine();
-  return Ret(E(pvEngine)->ShardBuffer(which, ppDevice, pCount));
+  if (PqaError *g_ = Gate(pvEngine)) return g_;
+  return Ret(Guard([&] { return E(pvEngine)->ShardBuffer(which, ppDevice, pCount); }));
 }
 PQACORE_API void *PqaB200_GetQuestionShard(void *pvEngine, int64_t *pFirst, int64_t *pCount) {
-  if (!pvEngine) return NullEngine();
+  if (PqaError *g_ = Gate(pvEngine)) return g_;
   if (pFirst) *pFirst = E(pvEngine)->questionShardFirst();
   if (pCount) *pCount = E(pvEngine)->questionShardCount();
   return nullptr;
 }
 PQACORE_API void *PqaB200_TShardEvalW(void *pvEngine, int64_t n, const int64_t *pQuizIds) {
-  if (!pvEngine) return NullEngine();
-  return Ret(E(pvEngine)->TShardEvalW(n, pQuizIds));
+  if (PqaError *g_ = Gate(pvEngine)) return g_;
+  return Ret(Guard([&] { return E(pvEngine)->TShardEvalW(n, pQuizIds); }));
 }
 PQACORE_API void *PqaB200_TShardEvalHVL(void *pvEngine, int64_t n, const int64_t *pQuizIds) {
-  if (!pvEngine) return NullEngine();
-  return Ret(E(pvEngine)->TShardEvalHVL(n, pQuizIds));
+  if (PqaError *g_ = Gate(pvEngine)) return g_;
+  return Ret(Guard([&] { return E(pvEngine)->TShardEvalHVL(n, pQuizIds); }));
 }
 PQACORE_API void *PqaB200_TShardPriority(void *pvEngine, int64_t n, const int64_t *pQuizIds) {
-  if (!pvEngine) return NullEngine();
-  return Ret(E(pvEngine)->TShardPriority(n, pQuizIds));
+  if (PqaError *g_ = Gate(pvEngine)) return g_;
+  return Ret(Guard([&] { return E(pvEngine)->TShardPriority(n, pQuizIds); }));
 }
 PQACORE_API void *PqaB200_GetTargetShard(void *pvEngine, int64_t *pFirst, int64_t *pCount) {
-  if (!pvEngine) return NullEngine();
+  if (PqaError *g_ = Gate(pvEngine)) return g_;
   if (pFirst) *pFirst = E(pvEngine)->targetShardFirst();
   if (pCount) *pCount = E(pvEngine)->targetShardCount();
   return nullptr;
 }
 PQACORE_API void *PqaB200_FillBinarySearchKB(void *pvEngine, double rounds) {
-  if (!pvEngine) return NullEngine();
-  return Ret(E(pvEngine)->FillBinarySearchKB(rounds));
+  if (PqaError *g_ = Gate(pvEngine)) return g_;
+  return Ret(Guard([&] { return E(pvEngine)->FillBinarySearchKB(rounds); }));
 }
 PQACORE_API void *PqaB200_P2PInit(void *pvEngine, int32_t rank, int32_t nRanks, int64_t maxQuizzes, void **ppBase, int64_t *pBytes) {
-  if (!pvEngine) return NullEngine();
-  return Ret(E(pvEngine)->P2PInit(rank, nRanks, maxQuizzes, ppBase, pBytes));
+  if (PqaError *g_ = Gate(pvEngine)) return g_;
+  return Ret(Guard([&] { return E(pvEngine)->P2PInit(rank, nRanks, maxQuizzes, ppBase, pBytes); }));
 }
 PQACORE_API void *PqaB200_P2PExportHandle(void *pvEngine, uint8_t *pHandle64) {
-  if (!pvEngine) return NullEngine();
-  return Ret(E(pvEngine)->P2PExportHandle(pHandle64));
+  if (PqaError *g_ = Gate(pvEngine)) return g_;
+  return Ret(Guard([&] { return E(pvEngine)->P2PExportHandle(pHandle64); }));
 }
 PQACORE_API void *PqaB200_P2POpenHandle(void *pvEngine, const uint8_t *pHandle64, void **ppPeerBase) {
-  if (!pvEngine) return NullEngine();
-  return Ret(E(pvEngine)->P2POpenHandle(pHandle64, ppPeerBase));
+  if (PqaError *g_ = Gate(pvEngine)) return g_;
+  return Ret(Guard([&] { return E(pvEngine)->P2POpenHandle(pHandle64, ppPeerBase); }));
 }
 PQACORE_API void *PqaB200_P2PConnect(void *pvEngine, void *const *pBases) {
-  if (!pvEngine) return NullEngine();
-  return Ret(E(pvEngine)->P2PConnect(pBases));
+  if (PqaError *g_ = Gate(pvEngine)) return g_;
+  return Ret(Guard([&] { return E(pvEngine)->P2PConnect(pBases); }));
 }
 PQACORE_API void *PqaB200_P2PNextQuestionBegin(void *pvEngine, int64_t n, const int64_t *pQuizIds, const uint64_t *pRandoms) {
-  if (!pvEngine) return NullEngine();
-  return Ret(E(pvEngine)->P2PNextQuestionBegin(n, pQuizIds, pRandoms));
+  if (PqaError *g_ = Gate(pvEngine)) return g_;
+  return Ret(Guard([&] { return E(pvEngine)->P2PNextQuestionBegin(n, pQuizIds, pRandoms); }));
 }
 PQACORE_API void *PqaB200_P2PNextQuestionEnd(void *pvEngine, int64_t n, const int64_t *pQuizIds, int64_t *pQuestions, void **ppErrors) {
-  if (!pvEngine) return NullEngine();
-  return Ret(E(pvEngine)->P2PNextQuestionEnd(n, pQuizIds, pQuestions, ppErrors));
+  if (PqaError *g_ = Gate(pvEngine)) return g_;
+  return Ret(Guard([&] { return E(pvEngine)->P2PNextQuestionEnd(n, pQuizIds, pQuestions, ppErrors); }));
 }
 PQACORE_API void *PqaB200_P2PRecordAnswerBegin(void *pvEngine, int64_t n, const int64_t *pQuizIds, const int64_t *pAnswers) {
-  if (!pvEngine) return NullEngine();
-  return Ret(E(pvEngine)->P2PRecordAnswerBegin(n, pQuizIds, pAnswers));
+  if (PqaError *g_ = Gate(pvEngine)) return g_;
+  return Ret(Guard([&] { return E(pvEngine)->P2PRecordAnswerBegin(n, pQuizIds, pAnswers); }));
 }
 PQACORE_API void *PqaB200_P2PRecordAnswerEnd(void *pvEngine) {
-  if (!pvEngine) return NullEngine();
-  return Ret(E(pvEngine)->P2PRecordAnswerEnd());
+  if (PqaError *g_ = Gate(pvEngine)) return g_;
+  return Ret(Guard([&] { return E(pvEngine)->P2PRecordAnswerEnd(); }));
 }
 PQACORE_API void *PqaB200_P2PLastPhaseMs(void *pvEngine, double *pMs5) {
-  if (!pvEngine) return NullEngine();
+  if (PqaError *g_ = Gate(pvEngine)) return g_;
   if (!pMs5) return Ret(MakeError(ErrCode::NullArgument, "pMs5"));
-  return Ret(E(pvEngine)->P2PLastPhaseMs(pMs5));
+  return Ret(Guard([&] { return E(pvEngine)->P2PLastPhaseMs(pMs5); }));
 }
 PQACORE_API void *PqaB200_P2PSetExactOrder(void *pvEngine, int32_t on) {
-  if (!pvEngine) return NullEngine();
-  return Ret(E(pvEngine)->P2PSetExactOrder(on));
+  if (PqaError *g_ = Gate(pvEngine)) return g_;
+  return Ret(Guard([&] { return E(pvEngine)->P2PSetExactOrder(on); }));
 }
 PQACORE_API void *PqaB200_ResidentBind(void *pvEngine, int64_t n, const int64_t *pQuizIds, const uint64_t *pRandoms) {
-  if (!pvEngine) return NullEngine();
-  return Ret(E(pvEngine)->ResidentBind(n, pQuizIds, pRandoms));
+  if (PqaError *g_ = Gate(pvEngine)) return g_;
+  return Ret(Guard([&] { return E(pvEngine)->ResidentBind(n, pQuizIds, pRandoms); }));
 }
 PQACORE_API void *PqaB200_ResidentStep(void *pvEngine) {
-  if (!pvEngine) return NullEngine();
-  return Ret(E(pvEngine)->ResidentStep());
+  if (PqaError *g_ = Gate(pvEngine)) return g_;
+  return Ret(Guard([&] { return E(pvEngine)->ResidentStep(); }));
 }
 PQACORE_API void *PqaB200_ResidentFetch(void *pvEngine, int64_t *pQuestions) {
-  if (!pvEngine) return NullEngine();
-  return Ret(E(pvEngine)->ResidentFetch(pQuestions));
+  if (PqaError *g_ = Gate(pvEngine)) return g_;
+  return Ret(Guard([&] { return E(pvEngine)->ResidentFetch(pQuestions); }));
 }
 PQACORE_API double PqaB200_ResidentLastEvalMs(void *pvEngine) { return pvEngine ? E(pvEngine)->ResidentLastEvalMs() : -1.0; }
 PQACORE_API void *PqaB200_Synchronize(void *pvEngine) {
-  if (!pvEngine) return NullEngine();
-  return Ret(E(pvEngine)->Synchronize());
+  if (PqaError *g_ = Gate(pvEngine)) return g_;
+  return Ret(Guard([&] { return E(pvEngine)->Synchronize(); }));
 }
 PQACORE_API void *PqaB200_EventCreate(void) {
   cudaEvent_t ev = nullptr;
@@ -536,7 +553,7 @@ PQACORE_API void *PqaB200_EventCreate(void) {
 }
 PQACORE_API void PqaB200_EventDestroy(void *pvEvent) { if (pvEvent) cudaEventDestroy((cudaEvent_t)pvEvent); }
 PQACORE_API void *PqaB200_EventRecord(void *pvEngine, void *pvEvent) {
-  if (!pvEngine) return NullEngine();
+  if (PqaError *g_ = Gate(pvEngine)) return g_;
   const cudaError_t e = cudaEventRecord((cudaEvent_t)pvEvent, E(pvEngine)->stream());
   return e == cudaSuccess ? nullptr : ErrCuda((int)e, "cudaEventRecord", __FILE__, __LINE__);
 }
@@ -551,8 +568,8 @@ PQACORE_API double PqaB200_EventElapsedMs(void *pvStart, void *pvStop) {
 }
 PQACORE_API uint64_t PqaB200_KernelLaunchCount(void *pvEngine) { (void)pvEngine; return kernel_launch_count(); }
 PQACORE_API void *PqaB200_FlushL2(void *pvEngine) {
-  if (!pvEngine) return NullEngine();
-  return Ret(E(pvEngine)->FlushL2());
+  if (PqaError *g_ = Gate(pvEngine)) return g_;
+  return Ret(Guard([&] { return E(pvEngine)->FlushL2(); }));
 }
 
 } // extern "C"

@@ -305,6 +305,7 @@ PqaError *Engine::StartQuizBatch(int64_t n, int64_t *pQuizIds) {
   if (!pQuizIds) return MakeError(ErrCode::NullArgument, PQA_FILE_LINE "pQuizIds");
   if (maintenance_) return WrongMode("Start/Resume quiz");
   std::lock_guard<std::mutex> lk(mu_); DeviceScope devScope(device_);
+  if (maintenance_) return WrongMode("Start/Resume quiz");   // re-checked under the lock: StartMaintenance may have completed meanwhile
   PQA_TRY
   for (int64_t x = 0; x < n; x++) pQuizIds[x] = AssignQuizId();
   EnsureQuizCapacity((int64_t)quizzes_.size());
@@ -443,6 +444,7 @@ PqaError *Engine::NextQuestionBatch(int64_t n, const int64_t *pQuizIds, const ui
   if (IsSharded()) return ErrNotImplemented("NextQuestion on a sharded engine: use the PqaB200_Shard* protocol");
   if (maintenance_) return WrongMode("compute next question");
   std::lock_guard<std::mutex> lk(mu_); DeviceScope devScope(device_);
+  if (maintenance_) return WrongMode("compute next question");   // re-checked under the lock: StartMaintenance may have completed meanwhile
   PQA_TRY
   // validate; quizzes that fail validation get their own error and are left out of the launch
   std::vector<int64_t> valid; valid.reserve(n);
@@ -715,6 +717,7 @@ PqaError *Engine::RecordAnswerBatch(int64_t n, const int64_t *pQuizIds, const in
   if (IsSharded()) return ErrNotImplemented("RecordAnswer on a sharded engine: use PqaB200_ShardRecordAnswerBegin / End");
   if (maintenance_) return WrongMode("record an answer");
   std::lock_guard<std::mutex> lk(mu_); DeviceScope devScope(device_);
+  if (maintenance_) return WrongMode("record an answer");   // re-checked under the lock: StartMaintenance may have completed meanwhile
   PQA_TRY
   if (PqaError *e = ValidateRecordAnswer(n, pQuizIds, pAnswers)) return e;
   UploadIds(n, pQuizIds);
@@ -901,6 +904,7 @@ PqaError *Engine::SetActiveQuestionBatch(int64_t n, const int64_t *pQuizIds, con
   if (!pQuizIds || !pQuestions) return MakeError(ErrCode::NullArgument, PQA_FILE_LINE "pQuizIds/pQuestions");
   if (maintenance_) return WrongMode("get active question ID for a quiz");   // sic, BaseEngine.cpp:491-493
   std::lock_guard<std::mutex> lk(mu_); DeviceScope devScope(device_);
+  if (maintenance_) return WrongMode("get active question ID for a quiz");   // re-checked under the lock: StartMaintenance may have completed meanwhile
   PQA_TRY
   for (int64_t x = 0; x < n; x++)
     if (PqaError *e = CheckQuiz(pQuizIds[x])) return e;
@@ -932,6 +936,7 @@ PqaError *Engine::ListTopTargetsBatch(int64_t n, const int64_t *pQuizIds, int64_
     return MakeError(ErrCode::NullArgument, PQA_FILE_LINE "pQuizIds/pDest/pCounts");
   if (maintenance_) return WrongMode("compute next question");   // sic, BaseEngine.cpp:514-516
   std::lock_guard<std::mutex> lk(mu_); DeviceScope devScope(device_);
+  if (maintenance_) return WrongMode("compute next question");   // re-checked under the lock: StartMaintenance may have completed meanwhile
   PQA_TRY
   for (int64_t x = 0; x < n; x++)
     if (PqaError *e = CheckQuiz(pQuizIds[x])) return e;
@@ -1065,6 +1070,7 @@ PqaError *Engine::RecordQuizTargetBatch(int64_t n, const int64_t *pQuizIds, cons
       if (!(pAmounts[x] > 0)) return ErrNonPositiveAmount(pAmounts[x], PQA_FILE_LINE "|amount| must be positive.");
   if (maintenance_) return WrongMode("record quiz target");
   std::lock_guard<std::mutex> lk(mu_); DeviceScope devScope(device_);
+  if (maintenance_) return WrongMode("record quiz target");   // re-checked under the lock: StartMaintenance may have completed meanwhile
   std::vector<TrainOp> ops;
   std::vector<int64_t> targets(n);
   std::vector<double> amounts(n);
@@ -1145,6 +1151,7 @@ PqaError *Engine::ReleaseQuizBatch(int64_t n, const int64_t *pQuizIds) {
   if (n > 0 && !pQuizIds) return MakeError(ErrCode::NullArgument, PQA_FILE_LINE "pQuizIds");
   if (maintenance_) return WrongMode("release quiz");
   std::lock_guard<std::mutex> lk(mu_); DeviceScope devScope(device_);
+  if (maintenance_) return WrongMode("release quiz");   // re-checked under the lock: StartMaintenance may have completed meanwhile
   for (int64_t x = 0; x < n; x++) {
     if (PqaError *e = CheckQuiz(pQuizIds[x])) return e;
     HostQuiz &q = quizzes_[pQuizIds[x]];
@@ -1640,9 +1647,11 @@ PqaError *Engine::P2PCheckError() {
   PQA_TRY
   PQA_CU(cudaMemcpyAsync(&flag, p2pInbox_ + 64, 8, cudaMemcpyDeviceToHost, stream_));
   PQA_CU(cudaGetLastError()); PQA_CU(cudaStreamSynchronize(stream_));
-  if (flag != 0)
+  if (flag != 0) {
+    PQA_CU(cudaMemsetAsync(p2pInbox_ + 64, 0, 8, stream_));        // reported once; the caller decides whether to go on
     return MakeError(ErrCode::Internal, PQA_FILE_LINE "peer-memory barrier timed out: a shard did not reach epoch " +
                      std::to_string(flag) + " (all shards must issue the same P2P calls in the same order)");
+  }
   return nullptr;
   PQA_CATCH_RETURN_ERR
 }
@@ -1952,6 +1961,29 @@ PqaError *Engine::SaveKB(const char *filePath) {
   if (!fc.f) return MakeError(ErrCode::CantOpenFile, PQA_FILE_LINE "Can't open the KB file to write.",
                               std::string("filePath=[") + filePath + "]");
   return WriteKBFile(fc.f, filePath, true);
+}
+
+PqaError *Engine::Shutdown(const char *saveFilePath) {
+  if (shutdown_.exchange(true, std::memory_order_acq_rel))          // MaintenanceSwitch::Shutdown (MaintenanceSwitch.cpp:82-90)
+    return MakeError(ErrCode::ObjectShutDown, std::string("MaintenanceSwitch seems already shut down.") +
+                     (saveFilePath ? std::string(" Not saving file: ") + saveFilePath : std::string()), "CpuEngine<taNumber>::Shutdown()");
+  PqaError *err = nullptr;
+  if (saveFilePath && *saveFilePath) err = IsSharded() ? SaveKBShard(saveFilePath, true) : SaveKB(saveFilePath);
+  std::lock_guard<std::mutex> lk(mu_); DeviceScope devScope(device_);
+  for (int64_t i = 0; i < (int64_t)quizzes_.size(); i++)           // BaseEngine.cpp:289-303
+    if (quizzes_[(size_t)i].present) pimQuiz_.RemoveComp(i);
+  quizzes_.clear(); quizGaps_.clear();
+  pimQuiz_.OnCompact(0, nullptr);
+  ReleaseDeviceState();                                            // :311 DestroyStatistics
+  return err;
+}
+void Engine::ReleaseDeviceState() {
+  if (stream_) cudaStreamSynchronize(stream_);
+  cudaFree(dSA_); cudaFree(dMD_); cudaFree(dVB_); cudaFree(dDerR_);
+  dSA_ = dMD_ = dVB_ = dDerR_ = dDerL_ = nullptr; derCapR_ = derCapL_ = 0;
+  cudaFree(dPriors_); cudaFree(dLogPriors_); cudaFree(dAsked_); cudaFree(dActive_); cudaFree(dNormS_);
+  dPriors_ = dLogPriors_ = dNormS_ = nullptr; dAsked_ = nullptr; dActive_ = nullptr;
+  quizCap_ = 0; residentN_ = 0;
 }
 
 // One shard's part of a KB file shared by all shards. The shard called with writeFrame != 0 goes first (it creates the

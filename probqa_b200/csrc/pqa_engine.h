@@ -180,6 +180,10 @@ class Engine {
   virtual PqaError *CopyDTargets(int64_t iQuestion, int64_t maxTargets, double *pFreqs);
   virtual PqaError *CopyBTargets(int64_t maxTargets, double *pFreqs);
   virtual PqaError *SaveKB(const char *filePath);
+  // BaseEngine::Shutdown (BaseEngine.cpp:260-322): no new operations, optional KB save, quizzes and KB released. Every later
+  // call through the C ABI answers ObjectShutDown (pqa_cabi.cu checks IsShutDown before it enters the engine).
+  virtual PqaError *Shutdown(const char *saveFilePath);
+  bool IsShutDown() const { return shutdown_.load(std::memory_order_acquire); }
   virtual PqaError *SaveKBShard(const char *filePath, bool writeFrame);   // sharded engines: every shard writes its cells into one file
   static Engine *LoadKB(const char *filePath, const CiB200Options &opts, PqaError **err);
 
@@ -332,6 +336,8 @@ class Engine {
   bool p2pPhasesValid_ = false;
   P2PFlags p2pFlags() const;
   PqaError *P2PCheckError();
+  std::atomic<bool> shutdown_{false};
+  void ReleaseDeviceState();                                       // frees the KB, the derived KB and the quiz pool (Shutdown)
   std::atomic<bool> maintenance_{false};                           // MaintenanceSwitch mode (MaintenanceSwitch.h): Regular / Maintenance
   GapSet qGaps_, tGaps_;                                 // removed questions / targets (BaseEngine _questionGaps, _targetGaps)
   PermIds pimQ_, pimT_, pimQuiz_;

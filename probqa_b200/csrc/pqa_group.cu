@@ -246,6 +246,7 @@ PqaError *ShardGroup::NextQuestionBatch(int64_t n, const int64_t *pQuizIds, cons
     valid.push_back(pQuizIds[x]); where.push_back(x);
     rnd.push_back(pRandoms ? pRandoms[x] : NextRandom());
   }
+  if (broken_) return Broken();
   uint64_t nAsked = 0;
   for (size_t s0 = 0; s0 < valid.size(); s0 += (size_t)cap_) {      // slices of the inbox capacity
     const int64_t m = (int64_t)std::min(valid.size() - s0, (size_t)cap_);
@@ -264,6 +265,7 @@ PqaError *ShardGroup::NextQuestionBatch(int64_t n, const int64_t *pQuizIds, cons
         if (!e && r != 0 && o2 != out) e = MakeError(ErrCode::Internal, PQA_FILE_LINE "the shards selected different questions");
         sliceErr = Keep(sliceErr, e);
       }
+      if (sliceErr && sliceErr->code != ErrCode::QuestionsExhausted) broken_ = true;   // a shard failed mid-exchange: no lockstep any more
     }
     for (int64_t x = 0; x < m; x++) {
       const int64_t at = where[s0 + (size_t)x];
@@ -290,6 +292,7 @@ PqaError *ShardGroup::RecordAnswerBatch(int64_t n, const int64_t *pQuizIds, cons
   std::lock_guard<std::mutex> lk(mu_);
   PQA_TRY
   if (PqaError *e = ValidateRecordAnswer(n, pQuizIds, pAnswers)) return e;
+  if (broken_) return Broken();
   PqaError *err = nullptr;
   for (int64_t s0 = 0; s0 < n && !err; s0 += cap_) {
     const int64_t m = std::min(cap_, n - s0);
@@ -298,6 +301,7 @@ PqaError *ShardGroup::RecordAnswerBatch(int64_t n, const int64_t *pQuizIds, cons
     } else {
       for (auto &s : shards_) { cudaSetDevice(s->device()); err = Keep(err, s->P2PRecordAnswerBegin(m, pQuizIds + s0, pAnswers + s0)); }
       for (auto &s : shards_) { cudaSetDevice(s->device()); err = Keep(err, s->P2PRecordAnswerEnd()); }
+      if (err) broken_ = true;       // the shards' posteriors and registries may differ now
     }
   }
   if (err) return err;
@@ -416,6 +420,18 @@ PqaError *ShardGroup::SaveKB(const char *filePath) {
   if (shards_.size() == 1) return (cudaSetDevice(shards_[0]->device()), shards_[0]->SaveKB(filePath));
   PqaError *err = (cudaSetDevice(shards_[0]->device()), shards_[0]->SaveKBShard(filePath, true));       // frame + its cells, then the others in place
   for (size_t r = 1; r < shards_.size() && !err; r++) { cudaSetDevice(shards_[r]->device()); err = shards_[r]->SaveKBShard(filePath, false); }
+  return err;
+}
+PqaError *ShardGroup::Shutdown(const char *saveFilePath) {
+  if (shutdown_.exchange(true, std::memory_order_acq_rel))
+    return MakeError(ErrCode::ObjectShutDown, std::string("MaintenanceSwitch seems already shut down.") +
+                     (saveFilePath ? std::string(" Not saving file: ") + saveFilePath : std::string()), "CpuEngine<taNumber>::Shutdown()");
+  PqaError *err = nullptr;
+  if (saveFilePath && *saveFilePath) err = SaveKB(saveFilePath);
+  for (auto &s : shards_) { cudaSetDevice(s->device()); err = Keep(err, s->Shutdown(nullptr)); }
+  std::lock_guard<std::mutex> lk(mu_);
+  quizzes_.clear(); quizGaps_.clear();
+  pimQuiz_.OnCompact(0, nullptr);
   return err;
 }
 PqaError *ShardGroup::FillBinarySearchKB(double rounds) {

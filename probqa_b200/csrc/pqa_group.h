@@ -33,6 +33,7 @@ class ShardGroup : public Engine {
   PqaError *CopyDTargets(int64_t iQuestion, int64_t maxTargets, double *pFreqs) override;
   PqaError *CopyBTargets(int64_t maxTargets, double *pFreqs) override;
   PqaError *SaveKB(const char *filePath) override;
+  PqaError *Shutdown(const char *saveFilePath) override;
   PqaError *UploadKB(const double *sA, const double *mD, const double *vB) override;
   PqaError *DownloadKB(double *sA, double *mD, double *vB) override;
   PqaError *CopyQuizPriors(int64_t iQuiz, double *pPriors) override;
@@ -88,6 +89,14 @@ class ShardGroup : public Engine {
   void MirrorResumed(int64_t n, const int64_t *pCounts, const CiAnsweredQuestion *pAQs, const int64_t *pQuizIds);
   static std::vector<CiB200Options> ShardOptions(const CiEngineDefinition &def, const CiB200Options &opts,
                                                  const CiB200GroupOptions &gopts);
+  // Everything is validated on the shell before any shard is touched, so an exchanged call can only fail asymmetrically on
+  // a device error (a CUDA failure or a barrier time-out on one shard). The shards are then out of lockstep -- epochs, inbox
+  // parities, possibly registries -- and the group refuses further exchanged calls instead of answering from diverged state.
+  bool broken_ = false;
+  static PqaError *Broken() {
+    return MakeError(ErrCode::Internal, "sharded engine group: an exchanged call failed on one shard earlier; the shards are out of "
+                                        "lockstep. Save the KB if needed and release the engine.");
+  }
   std::vector<std::unique_ptr<Engine>> shards_;
   int64_t cap_ = 256;          // quizzes per exchanged call (inbox size); longer batches are cut into slices
 };

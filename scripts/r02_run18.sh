@@ -1,0 +1,3 @@
+mkdir -p gpurun_out
+timeout 1500 python -m pytest tests -x -q -m gpu 2>&1 > gpurun_out/r02_tests_v14.log; tail -3 gpurun_out/r02_tests_v14.log
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1

@@ -437,6 +437,29 @@ def test_error_contract(pqa):
     eng.record_answer_batch([a, b], [0, 1])
 
 
+def test_shutdown_contract(pqa, tmp_path):
+    """PqaEngine_Shutdown (BaseEngine.cpp:260-322): the KB is saved when a path is given, then the engine is gone for every
+    later call (ObjectShutDown, MaintenanceSwitch.h:138-141), dimensions read 0, and a second Shutdown says so too."""
+    Q, K, T = 12, 3, 40
+    kb = synth.gamma_kb(Q, K, T, INIT)
+    eng = make_engine(pqa, Q, K, T, 2, kb)
+    quiz = eng.start_quiz()
+    eng.next_question(quiz)
+    path = str(tmp_path / "down.kb")
+    eng.shutdown(path)
+    again = pqa.PqaEngineFactory().load_b200_engine(path, emulated_workers=2)
+    for g, w in zip(again.download_kb(), kb):
+        assert np.array_equal(bits(g), bits(w))
+    for call in (lambda: eng.start_quiz(), lambda: eng.next_question(quiz), lambda: eng.record_answer(quiz, 0),
+                 lambda: eng.list_top_targets(quiz, 3), lambda: eng.train([pqa.AnsweredQuestion(0, 0)], 1),
+                 lambda: eng.save_kb(path), lambda: eng.download_kb(), lambda: eng.shutdown()):
+        with pytest.raises(pqa.PqaException) as ei:
+            call()
+        assert "[Object is shut(ting) down]" in str(ei.value)
+    d = eng.copy_dims()
+    assert (d.n_answers, d.n_questions, d.n_targets) == (0, 0, 0)
+
+
 @pytest.mark.parametrize("depth", [0, 3, 8])
 def test_full_size_staged_vs_exact_and_oracle(pqa, ora, depth):
     """BASELINE config 2 size (1000x5x1000): the staged kernel against the exact kernel for a batch of quizzes, and
