@@ -208,11 +208,11 @@ DeviceKB Engine::kbEval() {
   derAllDirty_ = false;
   return kb();
 }
-void Engine::MarkQuestionsChanged(const std::vector<TrainOp> &ops) {
+void Engine::MarkQuestionsChanged(const TrainOp *ops, int64_t nOps) {
   if (derAllDirty_) return;
   if ((int64_t)derDirtyMark_.size() != qLocal_) derDirtyMark_.assign((size_t)qLocal_, 0);
-  for (const TrainOp &o : ops) {
-    const int64_t ql = o.q - qFirst_;
+  for (int64_t x = 0; x < nOps; x++) {
+    const int64_t ql = ops[x].q - qFirst_;
     if (ql < 0 || ql >= qLocal_ || derDirtyMark_[(size_t)ql]) continue;
     derDirtyMark_[(size_t)ql] = 1;
     derDirtyList_.push_back(ql);
@@ -467,14 +467,21 @@ PqaError *Engine::NextQuestionBatch(int64_t n, const int64_t *pQuizIds, const ui
     // The reference ABI's shape (one quiz per call, or the handful a combiner round collects): one fused launch, ids and
     // draws by value, results through mapped host memory (k_eval_few, pqa_eval_staged.cu).
     EnsureFewResources();
-    uint64_t rnd[8];
+    hRandoms_.ensure(m);
+    uint64_t *rnd = hRandoms_.get();
     for (int64_t x = 0; x < m; x++) rnd[x] = pRandoms ? pRandoms[where[x]] : NextRandom();
     dPriority_.ensure((size_t)(m * Q_), stream_); dRunLength_.ensure((size_t)(m * Q_), stream_);
+    if (m > eval_few_inline()) {            // ids and draws of a larger batch go through device arrays
+      UploadIds(m, valid.data());
+      dRandoms_.ensure(m, stream_);
+      PQA_CU(cudaMemcpyAsync(dRandoms_.get(), rnd, sizeof(uint64_t) * (size_t)m, cudaMemcpyHostToDevice, stream_));
+    }
     const uint64_t seq = ++fewSeq_;
     launch_eval_few_select(kbEval(), pool(), (int)m, valid.data(), rnd, W_, dPriority_.get(), dRunLength_.get(),
-                           dFewTickets_.get(), (int64_t *)dFewHost_, (uint64_t *)dFewHost_ + 4, seq, nullptr, stream_);
+                           dFewTickets_.get(), (int64_t *)dFewHost_, (uint64_t *)dFewHost_ + kFewHostSlots, seq, nullptr,
+                           dIds_.get(), dRandoms_.get(), stream_);
     PQA_CU(cudaGetLastError());
-    volatile uint64_t *seen = (volatile uint64_t *)hFew_ + 4;
+    volatile uint64_t *seen = (volatile uint64_t *)hFew_ + kFewHostSlots;
     for (uint64_t spins = 0; *seen != seq; spins++) {
       if ((spins & 0xFFF) == 0xFFF) {          // every few microseconds: has the stream died or finished without an answer?
         const cudaError_t qe = cudaStreamQuery(stream_);
@@ -972,42 +979,43 @@ int64_t Engine::ListTopTargets(PqaError **err, int64_t iQuiz, int64_t maxCount, 
 // CETrainOperation.cpp:28-83); here every Perform2/Perform1 is split into per-cell operations (same-question pairs
 // stay fused because they share mD[q][t]) and grouped by (question, target) so that one device thread applies a
 // cell group's operations in the reference's sequence order.
-void Engine::AppendQuizOps(std::vector<TrainOp> &ops, const CiAnsweredQuestion *aqs, int64_t n, int64_t iTarget,
-                           double amount) {
-  int64_t x = 0;
+int64_t Engine::AppendQuizOps(TrainOp *dst, const CiAnsweredQuestion *aqs, int64_t n, int64_t iTarget, double amount) {
+  int64_t x = 0, w = 0;                    // writes at most n operations, returns how many
   for (; x + 1 < n; x += 2) {
     const CiAnsweredQuestion &f = aqs[x], &s = aqs[x + 1];
     if (f._iQuestion == s._iQuestion) {
-      ops.push_back(TrainOp{f._iQuestion, f._iAnswer, s._iAnswer, iTarget, amount});  // doubled step or 3-add form
+      dst[w++] = TrainOp{f._iQuestion, f._iAnswer, s._iAnswer, iTarget, amount};  // doubled step or 3-add form
     } else {
-      ops.push_back(TrainOp{f._iQuestion, f._iAnswer, -1, iTarget, amount});
-      ops.push_back(TrainOp{s._iQuestion, s._iAnswer, -1, iTarget, amount});
+      dst[w++] = TrainOp{f._iQuestion, f._iAnswer, -1, iTarget, amount};
+      dst[w++] = TrainOp{s._iQuestion, s._iAnswer, -1, iTarget, amount};
     }
   }
-  if (x < n) ops.push_back(TrainOp{aqs[x]._iQuestion, aqs[x]._iAnswer, -1, iTarget, amount});
+  if (x < n) dst[w++] = TrainOp{aqs[x]._iQuestion, aqs[x]._iAnswer, -1, iTarget, amount};
+  return w;
 }
 
-PqaError *Engine::ApplyTrain(const std::vector<TrainOp> &opsAll, const std::vector<int64_t> &targets,
+// opsAll may live in pinned memory (hOps_, big RecordQuizTarget batches): the upload is then a plain DMA.
+PqaError *Engine::ApplyTrain(const TrainOp *opsAll, int64_t nAll, const std::vector<int64_t> &targets,
                              const std::vector<double> &amounts) {
   // caller holds mu_
   PQA_TRY
   std::vector<TrainOp> owned;
   if (qLocal_ != Q_) {   // question-sharded engine: cells of other shards' questions are theirs to update
-    for (const TrainOp &o : opsAll) if (OwnsQuestion(o.q)) owned.push_back(o);
+    for (int64_t x = 0; x < nAll; x++) if (OwnsQuestion(opsAll[x].q)) owned.push_back(opsAll[x]);
   } else if (IsTargetSharded()) {   // target-sharded engine: only the cells of its own columns, addressed locally
-    for (const TrainOp &o : opsAll)
-      if (o.target >= tFirst_ && o.target < tFirst_ + tLocal_) { owned.push_back(o); owned.back().target -= tFirst_; }
+    for (int64_t x = 0; x < nAll; x++)
+      if (opsAll[x].target >= tFirst_ && opsAll[x].target < tFirst_ + tLocal_) { owned.push_back(opsAll[x]); owned.back().target -= tFirst_; }
   }
-  const std::vector<TrainOp> &ops = IsSharded() ? owned : opsAll;
-  MarkQuestionsChanged(ops);
-  const int64_t nOps = (int64_t)ops.size();
+  const TrainOp *ops = IsSharded() ? owned.data() : opsAll;
+  const int64_t nOps = IsSharded() ? (int64_t)owned.size() : nAll;
+  MarkQuestionsChanged(ops, nOps);
   const int64_t nT = (int64_t)targets.size();
   const int64_t kDeviceGrouping = 8192;   // from here on the grouping by cell is a device radix sort (pqa_train_sort.cu)
   if (nOps >= kDeviceGrouping) {
     const size_t need = std::max(train_sort_scratch_bytes(nOps), train_sort_scratch_bytes(nT));
     dSortScratch_.ensure(need, stream_);
     dOps_.ensure(nOps, stream_);
-    PQA_CU(cudaMemcpyAsync(dOps_.get(), ops.data(), sizeof(TrainOp) * (size_t)nOps, cudaMemcpyHostToDevice, stream_));
+    PQA_CU(cudaMemcpyAsync(dOps_.get(), ops, sizeof(TrainOp) * (size_t)nOps, cudaMemcpyHostToDevice, stream_));
     launch_train_ops_device_grouped(kb(), dOps_.get(), nOps, dSortScratch_.get(), dSortScratch_.size(), stream_);
     if (nT > 0) {
       dTargets_.ensure(nT, stream_); dAmounts_.ensure(nT, stream_);
@@ -1071,7 +1079,6 @@ PqaError *Engine::RecordQuizTargetBatch(int64_t n, const int64_t *pQuizIds, cons
   if (maintenance_) return WrongMode("record quiz target");
   std::lock_guard<std::mutex> lk(mu_); DeviceScope devScope(device_);
   if (maintenance_) return WrongMode("record quiz target");   // re-checked under the lock: StartMaintenance may have completed meanwhile
-  std::vector<TrainOp> ops;
   std::vector<int64_t> targets(n);
   std::vector<double> amounts(n);
   for (int64_t x = 0; x < n; x++) {  // BaseEngine::RecordQuizTarget, BaseEngine.cpp:529-566
@@ -1084,11 +1091,17 @@ PqaError *Engine::RecordQuizTargetBatch(int64_t n, const int64_t *pQuizIds, cons
     if (PqaError *e = CheckQuiz(pQuizIds[x])) return e;
     targets[x] = pTargets[x]; amounts[x] = amount;
   }
+  PQA_TRY
+  int64_t maxOps = 0;
+  for (int64_t x = 0; x < n; x++) maxOps += (int64_t)quizzes_[pQuizIds[x]].answers.size();
+  hOps_.ensure((size_t)std::max<int64_t>(maxOps, 1));      // pinned: the operation list is built where the DMA reads it
+  int64_t nOps = 0;
   for (int64_t x = 0; x < n; x++) {
     const HostQuiz &q = quizzes_[pQuizIds[x]];
-    AppendQuizOps(ops, q.answers.data(), (int64_t)q.answers.size(), targets[x], amounts[x]);
+    nOps += AppendQuizOps(hOps_.get() + nOps, q.answers.data(), (int64_t)q.answers.size(), targets[x], amounts[x]);
   }
-  return ApplyTrain(ops, targets, amounts);
+  return ApplyTrain(hOps_.get(), nOps, targets, amounts);
+  PQA_CATCH_RETURN_ERR
 }
 
 PqaError *Engine::RecordQuizTarget(int64_t iQuiz, int64_t iTarget, double amount) {
@@ -1140,7 +1153,7 @@ PqaError *Engine::Train(int64_t nQuestions, const CiAnsweredQuestion *pAQs, int6
       }
     }
   }
-  PqaError *e = ApplyTrain(ops, std::vector<int64_t>{iTarget}, std::vector<double>{amount});
+  PqaError *e = ApplyTrain(ops.data(), (int64_t)ops.size(), std::vector<int64_t>{iTarget}, std::vector<double>{amount});
   if (!e) nQuestionsAsked_.fetch_add((uint64_t)nQuestions, std::memory_order_relaxed);  // CpuEngine.cpp:179
   return e;
 }
@@ -1297,14 +1310,18 @@ PqaError *Engine::SetEvalKernel(int32_t which, int64_t chunkTargets, int64_t qui
   return nullptr;
 }
 
+// Measured at 1000x5x1000 (bench.py e2e, ms per NextQuestion batch): fused kernel 0.05 / 0.22 / 0.37 / 0.66 at 1 / 8 / 16 / 32
+// quizzes (it streams the derived KB from L2 once per four quizzes), shared-memory slab kernels 0.23 / 0.43 / 0.38 at 8 / 16 /
+// 32: the fused launch serves batches up to 16.
 bool Engine::UseFewPath(int64_t n) const {
-  return n <= eval_few_max() && !IsSharded() && K_ <= 8 && evalCfg_.which != 1 && evalCfg_.kahanLanesPerThread == 0 &&
+  static const int64_t limit = std::min<int64_t>(eval_few_max(), env_int("PQA_B200_FEW_MAX", 16));
+  return n <= limit && !IsSharded() && K_ <= 8 && evalCfg_.which != 1 && evalCfg_.kahanLanesPerThread == 0 &&
          evalCfg_.chunkTargets == 0;
 }
 void Engine::EnsureFewResources() {
   if (hFew_) return;
-  PQA_CU(cudaHostAlloc((void **)&hFew_, sizeof(int64_t) * 8, cudaHostAllocMapped));
-  std::memset((void *)hFew_, 0, sizeof(int64_t) * 8);
+  PQA_CU(cudaHostAlloc((void **)&hFew_, sizeof(int64_t) * (kFewHostSlots + 1), cudaHostAllocMapped));
+  std::memset((void *)hFew_, 0, sizeof(int64_t) * (kFewHostSlots + 1));
   PQA_CU(cudaHostGetDevicePointer(&dFewHost_, (void *)hFew_, 0));
   dFewTickets_.ensure((size_t)eval_few_ticket_count(), stream_);
   PQA_CU(cudaMemsetAsync(dFewTickets_.get(), 0, sizeof(unsigned) * (size_t)eval_few_ticket_count(), stream_));
@@ -1326,8 +1343,9 @@ PqaError *Engine::EvalQuestions(int64_t n, const int64_t *pQuizIds, double *pPri
   if (UseFewPath(n)) {     // the kernel one-quiz NextQuestion calls run on, evaluation only
     EnsureFewResources();
     const uint64_t noDraws[8] = {};
+    dRandoms_.ensure((size_t)n, stream_);     // never read: no question is chosen
     launch_eval_few_select(kbEval(), pool(), (int)n, pQuizIds, noDraws, W_, dPriority_.get(), dRunLength_.get(),
-                           dFewTickets_.get(), nullptr, nullptr, 0, dGrand_.get(), stream_);
+                           dFewTickets_.get(), nullptr, nullptr, 0, dGrand_.get(), dIds_.get(), dRandoms_.get(), stream_);
   } else {
     EvalDetail det{nullptr, nullptr, nullptr, nullptr};
     launch_eval_questions(kbEval(), pool(), n, dIds_.get(), dPriority_.get(), det, evalCfg_, stream_);

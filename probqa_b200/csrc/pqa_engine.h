@@ -297,12 +297,11 @@ class Engine {
   bool UseFewPath(int64_t n) const;       // the fused one-launch NextQuestion of 1 .. eval_few_max() quizzes applies
   void EnsureFewResources();
   void MarkKBChanged() { derAllDirty_ = true; derDirtyList_.clear(); }
-  void MarkQuestionsChanged(const std::vector<TrainOp> &ops);
+  void MarkQuestionsChanged(const TrainOp *ops, int64_t nOps);
   QuizPool pool() const;
-  PqaError *ApplyTrain(const std::vector<TrainOp> &ops, const std::vector<int64_t> &targets,
+  PqaError *ApplyTrain(const TrainOp *ops, int64_t nOps, const std::vector<int64_t> &targets,
                        const std::vector<double> &amounts);
-  static void AppendQuizOps(std::vector<TrainOp> &ops, const CiAnsweredQuestion *aqs, int64_t n, int64_t iTarget,
-                            double amount);
+  static int64_t AppendQuizOps(TrainOp *dst, const CiAnsweredQuestion *aqs, int64_t n, int64_t iTarget, double amount);
 
   mutable std::mutex mu_;
   std::mutex combineMu_;
@@ -375,8 +374,10 @@ class Engine {
   PinBuf<uint64_t> hRandoms_;
   PinBuf<CiRatedTarget> hTop_;
   PinBuf<double> hRow_;
+  PinBuf<TrainOp> hOps_;
 
-  // one-quiz fused path: mapped host memory {int64 questions[4]; uint64 seq; ...}, ticket counters, call sequence number
+  // fused small-batch path: mapped host memory {int64 questions[kFewHostSlots]; uint64 seq}, ticket counters, call sequence number
+  static constexpr int kFewHostSlots = 64;
   volatile void *hFew_ = nullptr;
   void *dFewHost_ = nullptr;
   DevBuf<unsigned> dFewTickets_;

@@ -728,18 +728,21 @@ __global__ void __launch_bounds__(SW * 32, 2) k_eval_small(const StagedParams P)
 // w runs the 4K chains of quiz w; then all threads take the elementwise pass of each quiz; the last CTA to finish a quiz
 // (a ticket counter) runs the selection of CpuEngine::NextQuestionSpec right there, and the chosen questions go to mapped
 // host memory followed by a sequence word the caller polls: ONE launch, no copy, no stream synchronisation.
-constexpr int kFewMax = 4;                 // quizzes per launch = warps per CTA
+constexpr int kFewMax = 4;                 // quizzes per CTA = warps per CTA
+constexpr int kFewBatchMax = 64;           // quizzes per launch (grid.y tiles of kFewMax quizzes)
 constexpr int kFewGroups = 32;             // first-level ticket counters per quiz (1000 same-address atomics would serialise)
 struct FewParams {
   DeviceKB kb;
   QuizPool qp;
   int n;
-  int64_t slots[kFewMax];
+  int64_t slots[kFewMax];    // n <= kFewMax: ids and draws travel in the launch parameters ...
   uint64_t randoms[kFewMax];
+  const int64_t *dSlots;     // ... larger batches: device arrays [n] (nullptr otherwise)
+  const uint64_t *dRandoms;
   double *priority;          // [n][Q]
   double *runLength;         // [n][Q]
-  unsigned *tickets;         // [kFewMax][kFewGroups + 1] + 1 counters zeroed at creation; each is reset by its last incrementer
-  int64_t *hostQuestions;    // mapped pinned host memory [kFewMax]
+  unsigned *tickets;         // [kFewBatchMax][kFewGroups + 1] + 1 counters zeroed at creation; each is reset by its last incrementer
+  int64_t *hostQuestions;    // mapped pinned host memory [kFewBatchMax]
   uint64_t *hostSeq;         // mapped pinned host memory: receives `seq` after the questions
   uint64_t seq;
   int W;
@@ -761,9 +764,12 @@ __global__ void __launch_bounds__(kFewMax * 32, 7) k_eval_few(const FewParams P)
   const double *__restrict__ gR = P.kb.dR + iLocal * nV * (K * 4);
   const double *__restrict__ gL = P.kb.dL + iLocal * nV * ((K + 1) * 4);
   const bool qgap = bit32(P.kb.qgaps, i);
+  const int b0 = blockIdx.y * kFewMax;                    // this CTA's quizzes: b0 .. b0 + nHere - 1 of the batch
+  const int nHere = P.n - b0 < kFewMax ? P.n - b0 : kFewMax;
+  auto slot_of = [&](int b) -> int64_t { return P.dSlots ? P.dSlots[b0 + b] : P.slots[b]; };
   // ---- pass 1: warp w <-> quiz w, lane 4k + l <-> Kahan lane l of answer k
-  if (warp < P.n && !qgap) {
-    const int64_t slot = P.slots[warp];
+  if (warp < nHere && !qgap) {
+    const int64_t slot = slot_of(warp);
     if (!bit64(P.qp.asked + slot * P.qp.askedWords, i) && lane < 4 * K) {
       const int k = lane >> 2, l = lane & 3;
       const double *rk = gR + k * 4 + l;
@@ -787,9 +793,9 @@ __global__ void __launch_bounds__(kFewMax * 32, 7) k_eval_few(const FewParams P)
   }
   __syncthreads();
   // ---- pass 2 and epilogue, quiz by quiz, all threads over the targets
-  for (int b = 0; b < P.n; b++) {
-    const int64_t slot = P.slots[b];
-    const int64_t o = (int64_t)b * Q + i;
+  for (int b = 0; b < nHere; b++) {
+    const int64_t slot = slot_of(b);
+    const int64_t o = (int64_t)(b0 + b) * Q + i;
     const bool live = !qgap && !bit64(P.qp.asked + slot * P.qp.askedWords, i);     // CTA-uniform
     if (live) {
       const double *__restrict__ pr = P.qp.priors + slot * Tp;
@@ -857,7 +863,7 @@ __global__ void __launch_bounds__(kFewMax * 32, 7) k_eval_few(const FewParams P)
       __threadfence();
       const unsigned nG = gridDim.x < (unsigned)kFewGroups ? gridDim.x : (unsigned)kFewGroups;
       const unsigned g = blockIdx.x % nG, groupSize = (gridDim.x - g + nG - 1) / nG;
-      unsigned *cnt = P.tickets + b * (kFewGroups + 1);
+      unsigned *cnt = P.tickets + (b0 + b) * (kFewGroups + 1);
       int last = 0;
       if (atomicAdd(cnt + g, 1u) + 1u == groupSize) {
         cnt[g] = 0u;
@@ -870,13 +876,15 @@ __global__ void __launch_bounds__(kFewMax * 32, 7) k_eval_few(const FewParams P)
     if (sLast) {                                                         // CTA-uniform
       __threadfence();
       const int64_t nSel = split_count(Q, (int64_t)P.W * 8);
-      const int64_t chosen = select_question_cta(P.kb, P.qp, slot, P.priority + (int64_t)b * Q, P.randoms[b], P.W,
-                                                 P.runLength + (int64_t)b * Q, P.grandOut ? P.grandOut + b * nSel : nullptr,
+      const uint64_t draw = P.dRandoms ? P.dRandoms[b0 + b] : P.randoms[b];
+      const int64_t chosen = select_question_cta(P.kb, P.qp, slot, P.priority + (int64_t)(b0 + b) * Q, draw, P.W,
+                                                 P.runLength + (int64_t)(b0 + b) * Q,
+                                                 P.grandOut ? P.grandOut + (b0 + b) * nSel : nullptr,
                                                  P.hostQuestions != nullptr, P.setActive, sGrand);
       if (threadIdx.x == 0 && P.hostQuestions) {
-        P.hostQuestions[b] = chosen;
+        P.hostQuestions[b0 + b] = chosen;
         __threadfence_system();
-        unsigned *done = P.tickets + kFewMax * (kFewGroups + 1);
+        unsigned *done = P.tickets + kFewBatchMax * (kFewGroups + 1);
         if (atomicAdd(done, 1u) + 1u == (unsigned)P.n) {                 // every quiz of the call has its question
           *done = 0u;
           *reinterpret_cast<volatile uint64_t *>(P.hostSeq) = P.seq;
@@ -1260,18 +1268,22 @@ static void launch_k(const StagedParams &P, const EvalConfig &cfg, size_t smem, 
   else launch_cfg<K, 1, 8>(P, cfg, smem, st);
 }
 
-int eval_few_max() { return kFewMax; }
-int eval_few_ticket_count() { return kFewMax * (kFewGroups + 1) + 1; }
+int eval_few_inline() { return kFewMax; }
+int eval_few_max() { return kFewBatchMax; }
+int eval_few_ticket_count() { return kFewBatchMax * (kFewGroups + 1) + 1; }
 void launch_eval_few_select(const DeviceKB &kb, const QuizPool &qp, int n, const int64_t *slots, const uint64_t *randoms, int W,
                             double *dPriority, double *dRunLength, unsigned *dTickets, int64_t *hostQuestions,
-                            uint64_t *hostSeq, uint64_t seq, double *dGrand, cudaStream_t st) {
+                            uint64_t *hostSeq, uint64_t seq, double *dGrand, const int64_t *dSlots, const uint64_t *dRandoms,
+                            cudaStream_t st) {
   FewParams P;
+  P.dSlots = n > kFewMax ? dSlots : nullptr; P.dRandoms = n > kFewMax ? dRandoms : nullptr;
   P.kb = kb; P.qp = qp; P.n = n; P.priority = dPriority; P.runLength = dRunLength; P.tickets = dTickets;
   P.hostQuestions = hostQuestions; P.hostSeq = hostSeq; P.seq = seq; P.W = W;
   P.setActive = hostQuestions != nullptr; P.grandOut = dGrand;
-  for (int x = 0; x < kFewMax; x++) { P.slots[x] = x < n ? slots[x] : 0; P.randoms[x] = x < n ? randoms[x] : 0; }
+  for (int x = 0; x < kFewMax; x++) { P.slots[x] = (x < n && n <= kFewMax) ? slots[x] : 0; P.randoms[x] = (x < n && n <= kFewMax) ? randoms[x] : 0; }
   const size_t smem = sizeof(double) * (size_t)select_chunk_count(kb.Q, W);
-  PQA_K_SWITCH(kb.K, (k_eval_few<KK><<<(unsigned)kb.qCount, kFewMax * 32, smem, st>>>(P)))
+  const dim3 grid((unsigned)kb.qCount, (unsigned)((n + kFewMax - 1) / kFewMax));
+  PQA_K_SWITCH(kb.K, (k_eval_few<KK><<<grid, kFewMax * 32, smem, st>>>(P)))
   count_launch();
 }
 

@@ -127,11 +127,13 @@ int64_t select_chunk_count(int64_t Q, int W);
 // host memory hostQuestions[n] and then `seq` to *hostSeq (the caller polls it). slots / randoms are host arrays passed by
 // value; dTickets: eval_few_ticket_count() zeroed counters owned by the engine. hostQuestions = nullptr: evaluation only (no
 // question is chosen, no quiz state changes); dGrand: optional [n][nChunks] grand totals.
-int eval_few_max();
+int eval_few_max();      // quizzes per launch
+int eval_few_inline();   // up to this many, ids and draws travel in the launch parameters (slots / randoms host arrays)
 int eval_few_ticket_count();
 void launch_eval_few_select(const DeviceKB &kb, const QuizPool &qp, int n, const int64_t *slots, const uint64_t *randoms, int W,
                             double *dPriority, double *dRunLength, unsigned *dTickets, int64_t *hostQuestions,
-                            uint64_t *hostSeq, uint64_t seq, double *dGrand, cudaStream_t st);
+                            uint64_t *hostSeq, uint64_t seq, double *dGrand, const int64_t *dSlots, const uint64_t *dRandoms,
+                            cudaStream_t st);
 // CEListTopTargetsAlgorithm::RunHeapifyBased (CEListTopTargetsAlgorithm.cpp:30-97). dScratch: n*T 16-byte items
 // (used only when T items do not fit in shared memory). dDest: n*maxCount {int64 iTarget; double prob}.
 void launch_list_top_targets(const DeviceKB &kb, const QuizPool &qp, int64_t n, const int64_t *dSlots, int W,

@@ -266,7 +266,7 @@ def test_one_quiz_fused_launch(pqa, ora, dims, W):
     eng = make_engine(pqa, Q, K, T, W, kb)
     rng = np.random.default_rng(17)
     quizzes, priors, askeds = [], [], []
-    for b, depth in enumerate((0, 3, 8, 5)):
+    for b, depth in enumerate((0, 3, 8, 5, 1, 2, 4, 6, 7, 0, 3)):
         quiz = eng.start_quiz()
         prefix = synth.quiz_prefix(b, min(depth, Q - 1), Q, T, K)
         priors.append(drive_quiz(eng, ora, kb, W, quiz, prefix, check_top=False))
@@ -275,7 +275,7 @@ def test_one_quiz_fused_launch(pqa, ora, dims, W):
         askeds.append(asked)
         quizzes.append(quiz)
     bounds = ora.calc_split(Q, 8 * W)
-    for n in (1, 2, 4):
+    for n in (1, 2, 4, 5, 11):                            # up to 4: ids in the launch parameters; beyond: device arrays, grid.y tiles
         ev = eng.eval_questions(quizzes[:n])               # the same kernel, evaluation only
         randoms = rng.integers(0, 2 ** 64, size=n, dtype=np.uint64)
         before = eng.get_total_questions_asked()
