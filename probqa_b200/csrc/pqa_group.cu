@@ -53,6 +53,7 @@ std::vector<CiB200Options> ShardGroup::ShardOptions(const CiEngineDefinition &de
 
 ShardGroup::ShardGroup(const CiEngineDefinition &def, const CiB200Options &opts, const CiB200GroupOptions &gopts)
     : Engine(def, opts, ShellTag{}) {
+  baseOpts_ = opts; groupOpts_ = gopts;
   const std::vector<CiB200Options> so = ShardOptions(def, opts, gopts);
   device_ = so[0]._device;
   for (const CiB200Options &o : so) shards_.emplace_back(new Engine(def, o));
@@ -86,6 +87,8 @@ ShardGroup *ShardGroup::LoadKBGroup(const char *filePath, const CiB200Options &o
     g->shards_.emplace_back(e);
   }
   g->nQuestionsAsked_.store(asked, std::memory_order_relaxed);
+  g->baseOpts_ = opts; g->groupOpts_ = gopts;
+  g->pimQ_ = g->shards_[0]->pimQ_; g->pimT_ = g->shards_[0]->pimT_; g->pimQuiz_ = g->shards_[0]->pimQuiz_;   // the id maps of the file
   g->Connect(gopts);
   return g.release();
 }
@@ -114,6 +117,10 @@ void ShardGroup::Connect(const CiB200GroupOptions &gopts) {
 }
 
 // first error wins, the rest are released
+static PqaError *NotMaintenanceGroup(const char *what) {
+  return MakeError(ErrCode::WrongMode, std::string("Can't perform maintenance-only mode operation - ") + what +
+                                           " - because current mode is not maintenance (but regular/shutdown?).");
+}
 static PqaError *Keep(PqaError *first, PqaError *next) {
   if (!first) return next;
   delete next;
@@ -121,6 +128,7 @@ static PqaError *Keep(PqaError *first, PqaError *next) {
 }
 
 PqaError *ShardGroup::StartQuizBatch(int64_t n, int64_t *pQuizIds) {
+  if (maintenance_) return WrongMode("Start/Resume quiz");
   if (n < 0) return ErrNegativeCount(n, PQA_FILE_LINE "|n| must be non-negative.");
   if (n == 0) return nullptr;
   if (!pQuizIds) return MakeError(ErrCode::NullArgument, PQA_FILE_LINE "pQuizIds");
@@ -143,6 +151,7 @@ PqaError *ShardGroup::StartQuizBatch(int64_t n, int64_t *pQuizIds) {
 // access) and stores the finished rows into every shard's replica of the quiz; the other shards only keep their
 // registries in step. Bit-identical to one engine by construction: it is the same kernel on the same cells.
 PqaError *ShardGroup::ResumeQuizBatch(int64_t n, const int64_t *pCounts, const CiAnsweredQuestion *pAQs, int64_t *pQuizIds) {
+  if (maintenance_) return WrongMode("Start/Resume quiz");
   if (n < 0) return ErrNegativeCount(n, PQA_FILE_LINE "|n| must be non-negative.");
   if (n == 0) return nullptr;
   if (!pCounts || !pQuizIds) return MakeError(ErrCode::NullArgument, PQA_FILE_LINE "pCounts/pQuizIds");
@@ -228,6 +237,7 @@ PqaError *ShardGroup::ClearOldQuizzes(int64_t maxCount, double maxAgeSec) {
 
 PqaError *ShardGroup::NextQuestionBatch(int64_t n, const int64_t *pQuizIds, const uint64_t *pRandoms, int64_t *pQuestions,
                                         void **ppErrors) {
+  if (maintenance_) return WrongMode("compute next question");
   if (n < 0) return ErrNegativeCount(n, PQA_FILE_LINE "|n| must be non-negative.");
   if (n == 0) return nullptr;
   if (!pQuizIds || !pQuestions) return MakeError(ErrCode::NullArgument, PQA_FILE_LINE "pQuizIds/pQuestions");
@@ -286,6 +296,7 @@ PqaError *ShardGroup::NextQuestionBatch(int64_t n, const int64_t *pQuizIds, cons
 }
 
 PqaError *ShardGroup::RecordAnswerBatch(int64_t n, const int64_t *pQuizIds, const int64_t *pAnswers) {
+  if (maintenance_) return WrongMode("record an answer");
   if (n < 0) return ErrNegativeCount(n, PQA_FILE_LINE "|n| must be non-negative.");
   if (n == 0) return nullptr;
   if (!pQuizIds || !pAnswers) return MakeError(ErrCode::NullArgument, PQA_FILE_LINE "pQuizIds/pAnswers");
@@ -315,6 +326,7 @@ PqaError *ShardGroup::RecordAnswerBatch(int64_t n, const int64_t *pQuizIds, cons
 }
 
 PqaError *ShardGroup::SetActiveQuestionBatch(int64_t n, const int64_t *pQuizIds, const int64_t *pQuestions) {
+  if (maintenance_) return WrongMode("set active question");
   if (n < 0) return ErrNegativeCount(n, PQA_FILE_LINE "|n| must be non-negative.");
   if (n == 0) return nullptr;
   if (!pQuizIds || !pQuestions) return MakeError(ErrCode::NullArgument, PQA_FILE_LINE "pQuizIds/pQuestions");
@@ -330,6 +342,7 @@ PqaError *ShardGroup::SetActiveQuestionBatch(int64_t n, const int64_t *pQuizIds,
 
 PqaError *ShardGroup::ListTopTargetsBatch(int64_t n, const int64_t *pQuizIds, int64_t maxCount, CiRatedTarget *pDest,
                                           int64_t *pCounts) {
+  if (maintenance_) return WrongMode("compute next question");
   if (n > 0 && pQuizIds) {
     std::lock_guard<std::mutex> lk(mu_);
     for (int64_t x = 0; x < n; x++)
@@ -339,6 +352,7 @@ PqaError *ShardGroup::ListTopTargetsBatch(int64_t n, const int64_t *pQuizIds, in
 }
 
 PqaError *ShardGroup::RecordQuizTargetBatch(int64_t n, const int64_t *pQuizIds, const int64_t *pTargets, const double *pAmounts) {
+  if (maintenance_) return WrongMode("record quiz target");
   if (n < 0) return ErrNegativeCount(n, PQA_FILE_LINE "|n| must be non-negative.");
   if (n == 0) return nullptr;
   if (!pQuizIds || !pTargets) return MakeError(ErrCode::NullArgument, PQA_FILE_LINE "pQuizIds/pTargets");
@@ -354,6 +368,7 @@ PqaError *ShardGroup::RecordQuizTargetBatch(int64_t n, const int64_t *pQuizIds, 
 }
 
 PqaError *ShardGroup::Train(int64_t nQuestions, const CiAnsweredQuestion *pAQs, int64_t iTarget, double amount) {
+  if (maintenance_) return WrongMode("train");
   // every shard validates the same arguments the same way: if the first one refuses, nothing was applied anywhere
   cudaSetDevice(shards_[0]->device());
   if (PqaError *e = shards_[0]->Train(nQuestions, pAQs, iTarget, amount)) return e;
@@ -364,6 +379,7 @@ PqaError *ShardGroup::Train(int64_t nQuestions, const CiAnsweredQuestion *pAQs, 
 }
 
 PqaError *ShardGroup::ReleaseQuizBatch(int64_t n, const int64_t *pQuizIds) {
+  if (maintenance_) return WrongMode("release quiz");
   if (n < 0) return ErrNegativeCount(n, PQA_FILE_LINE "|n| must be non-negative.");
   if (n > 0 && !pQuizIds) return MakeError(ErrCode::NullArgument, PQA_FILE_LINE "pQuizIds");
   std::lock_guard<std::mutex> lk(mu_);
@@ -381,13 +397,119 @@ PqaError *ShardGroup::ReleaseQuizBatch(int64_t n, const int64_t *pQuizIds) {
   return nullptr;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Maintenance mode on a group (pqa_group.h).
+void ShardGroup::MoveCells(Engine &whole, bool toWhole) {
+  for (auto &sp : shards_) {
+    Engine &s = *sp;
+    cudaSetDevice(s.device());
+    const int64_t rowsA = s.qLocal_ * K_, rowsD = s.qLocal_;
+    double *wA = whole.dSA_ + (s.qFirst_ * K_) * whole.TpL_ + s.tFirst_, *wD = whole.dMD_ + s.qFirst_ * whole.TpL_ + s.tFirst_;
+    const size_t wPitch = (size_t)whole.TpL_ * 8, sPitch = (size_t)s.TpL_ * 8, width = (size_t)s.tLocal_ * 8;
+    if (toWhole) {
+      PQA_CU(cudaMemcpy2D(wA, wPitch, s.dSA_, sPitch, width, (size_t)rowsA, cudaMemcpyDefault));
+      PQA_CU(cudaMemcpy2D(wD, wPitch, s.dMD_, sPitch, width, (size_t)rowsD, cudaMemcpyDefault));
+    } else {
+      PQA_CU(cudaMemcpy2D(s.dSA_, sPitch, wA, wPitch, width, (size_t)rowsA, cudaMemcpyDefault));
+      PQA_CU(cudaMemcpy2D(s.dMD_, sPitch, wD, wPitch, width, (size_t)rowsD, cudaMemcpyDefault));
+      PQA_CU(cudaMemcpy(s.dVB_, whole.dVB_, sizeof(double) * (size_t)whole.Tp_, cudaMemcpyDefault));
+      s.MarkKBChanged();
+    }
+  }
+  if (toWhole) {
+    cudaSetDevice(whole.device());
+    PQA_CU(cudaMemcpy(whole.dVB_, shards_[0]->dVB_, sizeof(double) * (size_t)whole.Tp_, cudaMemcpyDefault));
+    whole.MarkKBChanged();
+  }
+}
+
+void ShardGroup::MirrorMaintenanceState() {
+  Q_ = maint_->Q_; T_ = maint_->T_; Tp_ = maint_->Tp_; TpL_ = Tp_; qLocal_ = Q_; tLocal_ = T_;
+  askedWords_ = maint_->askedWords_;
+  qGaps_ = maint_->qGaps_; tGaps_ = maint_->tGaps_;
+  pimQ_ = maint_->pimQ_; pimT_ = maint_->pimT_;
+}
+
+PqaError *ShardGroup::StartMaintenance(bool forceQuizzes) {
+  if (broken_) return Broken();
+  PQA_TRY
+  if (PqaError *e = Engine::StartMaintenance(forceQuizzes)) return e;     // the shell: mode switch, quizzes (BaseEngine.cpp:640-683)
+  CiEngineDefinition def;
+  std::memset(&def, 0, sizeof(def));
+  def._nAnswers = K_; def._nQuestions = Q_; def._nTargets = T_; def._precType = 3;
+  def._precMantissa = precMantissa_; def._precExponent = precExponent_; def._initAmount = initAmount_;
+  CiB200Options o = baseOpts_;
+  o._device = shards_[0]->device(); o._emulatedWorkers = W_;
+  o._questionShardFirst = o._questionShardCount = o._targetShardFirst = o._targetShardCount = 0;
+  cudaSetDevice(o._device);
+  maint_.reset(new Engine(def, o));
+  maint_->pimQ_ = pimQ_; maint_->pimT_ = pimT_; maint_->pimQuiz_ = pimQuiz_; maint_->qGaps_ = qGaps_; maint_->tGaps_ = tGaps_;
+  maint_->nQuestionsAsked_.store(nQuestionsAsked_.load(std::memory_order_relaxed), std::memory_order_relaxed);
+  MoveCells(*maint_, true);
+  shards_.clear();                                                       // their device memory is free for the resized KB
+  if (PqaError *e = maint_->StartMaintenance(true)) return e;
+  return nullptr;
+  PQA_CATCH_RETURN_ERR
+}
+
+PqaError *ShardGroup::FinishMaintenance() {
+  if (!maintenance_ || !maint_) return MakeError(ErrCode::MaintenanceModeAlreadyThis, PQA_FILE_LINE "The engine is in regular mode already.", "activeMode=0");
+  if (maint_->qGaps_.GetNGaps() > 0 || maint_->tGaps_.GetNGaps() > 0)
+    return ErrNotImplemented("sharded engine group: removed questions / targets (gaps) on shards; call Compact before FinishMaintenance");
+  PQA_TRY
+  if (PqaError *e = maint_->FinishMaintenance()) return e;
+  MirrorMaintenanceState();
+  CiEngineDefinition def;
+  std::memset(&def, 0, sizeof(def));
+  def._nAnswers = K_; def._nQuestions = Q_; def._nTargets = T_; def._precType = 3;
+  def._precMantissa = precMantissa_; def._precExponent = precExponent_; def._initAmount = initAmount_;
+  CiB200Options o = baseOpts_;
+  o._emulatedWorkers = W_;
+  const std::vector<CiB200Options> so = ShardOptions(def, o, groupOpts_);
+  for (const CiB200Options &x : so) { cudaSetDevice(x._device); shards_.emplace_back(new Engine(def, x)); }
+  MoveCells(*maint_, false);
+  for (auto &s : shards_) { s->pimQ_ = pimQ_; s->pimT_ = pimT_; s->pimQuiz_ = pimQuiz_; s->nQuestionsAsked_.store(nQuestionsAsked_.load(std::memory_order_relaxed), std::memory_order_relaxed); }
+  maint_.reset();
+  Connect(groupOpts_);
+  maintenance_ = false;
+  return nullptr;
+  PQA_CATCH_RETURN_ERR
+}
+
+PqaError *ShardGroup::AddQsTs(int64_t nQuestions, CiAddQorTParam *pAqps, int64_t nTargets, CiAddQorTParam *pAtps) {
+  if (!maintenance_ || !maint_) return NotMaintenanceGroup("add questions/targets");
+  PqaError *e = (cudaSetDevice(maint_->device()), maint_->AddQsTs(nQuestions, pAqps, nTargets, pAtps));
+  MirrorMaintenanceState();
+  return e;
+}
+PqaError *ShardGroup::RemoveQuestions(int64_t nQuestions, const int64_t *pQIds) {
+  if (!maintenance_ || !maint_) return NotMaintenanceGroup("remove questions");
+  PqaError *e = (cudaSetDevice(maint_->device()), maint_->RemoveQuestions(nQuestions, pQIds));
+  MirrorMaintenanceState();
+  return e;
+}
+PqaError *ShardGroup::RemoveTargets(int64_t nTargets, const int64_t *pTIds) {
+  if (!maintenance_ || !maint_) return NotMaintenanceGroup("remove targets");
+  PqaError *e = (cudaSetDevice(maint_->device()), maint_->RemoveTargets(nTargets, pTIds));
+  MirrorMaintenanceState();
+  return e;
+}
+PqaError *ShardGroup::Compact(int64_t *pnQuestions, const int64_t **ppOldQuestions, int64_t *pnTargets, const int64_t **ppOldTargets) {
+  if (!maintenance_ || !maint_) return NotMaintenanceGroup("compact the KB");
+  PqaError *e = (cudaSetDevice(maint_->device()), maint_->Compact(pnQuestions, ppOldQuestions, pnTargets, ppOldTargets));
+  MirrorMaintenanceState();
+  return e;
+}
+
 // KB access: whole-KB host arrays, every shard fills / takes its own rows or columns of them
 PqaError *ShardGroup::UploadKB(const double *sA, const double *mD, const double *vB) {
+  if (maint_) return (cudaSetDevice(maint_->device()), maint_->UploadKB(sA, mD, vB));
   PqaError *err = nullptr;
   for (auto &s : shards_) { cudaSetDevice(s->device()); err = Keep(err, s->UploadKB(sA, mD, vB)); }
   return err;
 }
 PqaError *ShardGroup::DownloadKB(double *sA, double *mD, double *vB) {
+  if (maint_) return (cudaSetDevice(maint_->device()), maint_->DownloadKB(sA, mD, vB));
   PqaError *err = nullptr;
   for (auto &s : shards_) { cudaSetDevice(s->device()); err = Keep(err, s->DownloadKB(sA, mD, vB)); }
   return err;
@@ -395,6 +517,7 @@ PqaError *ShardGroup::DownloadKB(double *sA, double *mD, double *vB) {
 PqaError *ShardGroup::CopyATargets(int64_t iQuestion, int64_t iAnswer, int64_t maxTargets, double *pFreqs) {
   if (iQuestion < 0 || iQuestion >= Q_) return ErrIndexOutOfRange(iQuestion, 0, Q_ - 1, PQA_FILE_LINE "Question index is not in KB range.");
   if (iAnswer < 0 || iAnswer >= K_) return ErrIndexOutOfRange(iAnswer, 0, K_ - 1, PQA_FILE_LINE "Answer index is not in KB range.");
+  if (maint_) return (cudaSetDevice(maint_->device()), maint_->CopyATargets(iQuestion, iAnswer, maxTargets, pFreqs));
   PqaError *err = nullptr;
   for (auto &s : shards_) {
     cudaSetDevice(s->device());
@@ -405,6 +528,7 @@ PqaError *ShardGroup::CopyATargets(int64_t iQuestion, int64_t iAnswer, int64_t m
 }
 PqaError *ShardGroup::CopyDTargets(int64_t iQuestion, int64_t maxTargets, double *pFreqs) {
   if (iQuestion < 0 || iQuestion >= Q_) return ErrIndexOutOfRange(iQuestion, 0, Q_ - 1, PQA_FILE_LINE "Question index is not in KB range.");
+  if (maint_) return (cudaSetDevice(maint_->device()), maint_->CopyDTargets(iQuestion, maxTargets, pFreqs));
   PqaError *err = nullptr;
   for (auto &s : shards_) {
     cudaSetDevice(s->device());
@@ -413,10 +537,14 @@ PqaError *ShardGroup::CopyDTargets(int64_t iQuestion, int64_t maxTargets, double
   }
   return err;
 }
-PqaError *ShardGroup::CopyBTargets(int64_t maxTargets, double *pFreqs) { return (cudaSetDevice(shards_[0]->device()), shards_[0]->CopyBTargets(maxTargets, pFreqs)); }
-PqaError *ShardGroup::CopyQuizPriors(int64_t iQuiz, double *pPriors) { return (cudaSetDevice(shards_[0]->device()), shards_[0]->CopyQuizPriors(iQuiz, pPriors)); }
+PqaError *ShardGroup::CopyBTargets(int64_t maxTargets, double *pFreqs) {
+  Engine *e = maint_ ? maint_.get() : shards_[0].get();
+  return (cudaSetDevice(e->device()), e->CopyBTargets(maxTargets, pFreqs));
+}
+PqaError *ShardGroup::CopyQuizPriors(int64_t iQuiz, double *pPriors) { if (maint_) return WrongMode("copy quiz priors"); return (cudaSetDevice(shards_[0]->device()), shards_[0]->CopyQuizPriors(iQuiz, pPriors)); }
 
 PqaError *ShardGroup::SaveKB(const char *filePath) {
+  if (maint_) return (cudaSetDevice(maint_->device()), maint_->SaveKB(filePath));
   if (shards_.size() == 1) return (cudaSetDevice(shards_[0]->device()), shards_[0]->SaveKB(filePath));
   PqaError *err = (cudaSetDevice(shards_[0]->device()), shards_[0]->SaveKBShard(filePath, true));       // frame + its cells, then the others in place
   for (size_t r = 1; r < shards_.size() && !err; r++) { cudaSetDevice(shards_[r]->device()); err = shards_[r]->SaveKBShard(filePath, false); }
@@ -435,11 +563,13 @@ PqaError *ShardGroup::Shutdown(const char *saveFilePath) {
   return err;
 }
 PqaError *ShardGroup::FillBinarySearchKB(double rounds) {
+  if (maint_) return (cudaSetDevice(maint_->device()), maint_->FillBinarySearchKB(rounds));
   PqaError *err = nullptr;
   for (auto &s : shards_) { cudaSetDevice(s->device()); err = Keep(err, s->FillBinarySearchKB(rounds)); }
   return err;
 }
 PqaError *ShardGroup::Synchronize() {
+  if (maint_) return (cudaSetDevice(maint_->device()), maint_->Synchronize());
   PqaError *err = nullptr;
   for (auto &s : shards_) { cudaSetDevice(s->device()); err = Keep(err, s->Synchronize()); }
   return err;

@@ -44,14 +44,19 @@ class ShardGroup : public Engine {
   PqaError *ResumeQuizBatch(int64_t n, const int64_t *pCounts, const CiAnsweredQuestion *pAQs, int64_t *pQuizIds) override;
   PqaError *ClearOldQuizzes(int64_t maxCount, double maxAgeSec) override;
 
+  // Maintenance mode (BaseEngine.cpp:640-779): the KB is gathered from the shards into ONE un-sharded engine on the first
+  // shard's device (device-to-device copies over NVLink), every maintenance call runs there, and FinishMaintenance splits the
+  // -- possibly resized -- KB over freshly created shards. Shards hold no gaps, so a KB with removed questions / targets must
+  // be compacted before FinishMaintenance.
+  PqaError *StartMaintenance(bool forceQuizzes) override;
+  PqaError *FinishMaintenance() override;
+  PqaError *AddQsTs(int64_t nQuestions, CiAddQorTParam *pAqps, int64_t nTargets, CiAddQorTParam *pAtps) override;
+  PqaError *RemoveQuestions(int64_t nQuestions, const int64_t *pQIds) override;
+  PqaError *RemoveTargets(int64_t nTargets, const int64_t *pTIds) override;
+  PqaError *Compact(int64_t *pnQuestions, const int64_t **ppOldQuestions, int64_t *pnTargets, const int64_t **ppOldTargets) override;
+
   // single-engine features a group does not offer
   PqaError *SaveKBShard(const char *, bool) override { return No("SaveKBShard (use SaveKB)"); }
-  PqaError *StartMaintenance(bool) override { return No("maintenance mode"); }
-  PqaError *FinishMaintenance() override { return No("maintenance mode"); }
-  PqaError *AddQsTs(int64_t, CiAddQorTParam *, int64_t, CiAddQorTParam *) override { return No("maintenance mode"); }
-  PqaError *RemoveQuestions(int64_t, const int64_t *) override { return No("maintenance mode"); }
-  PqaError *RemoveTargets(int64_t, const int64_t *) override { return No("maintenance mode"); }
-  PqaError *Compact(int64_t *, const int64_t **, int64_t *, const int64_t **) override { return No("maintenance mode"); }
   PqaError *SetQuizPriors(int64_t, const double *) override { return No("SetQuizPriors"); }
   PqaError *EvalQuestions(int64_t, const int64_t *, double *, double *, double *, int64_t *) override { return No("EvalQuestions"); }
   PqaError *EvalQuestionsDetailed(int64_t, double *, double *, double *, double *, double *) override { return No("EvalQuestionsDetailed"); }
@@ -86,6 +91,11 @@ class ShardGroup : public Engine {
   ShardGroup(const CiEngineDefinition &def, const CiB200Options &opts) : Engine(def, opts, ShellTag{}) {}   // shards added by LoadKBGroup
   static PqaError *No(const char *what) { return ErrNotImplemented(std::string("sharded engine group: ") + what); }
   void Connect(const CiB200GroupOptions &gopts);
+  void MirrorMaintenanceState();      // dimensions, gap sets and id maps of the maintenance engine -> the shell
+  void MoveCells(Engine &whole, bool toWhole);   // shards <-> the un-sharded maintenance engine, device to device
+  std::unique_ptr<Engine> maint_;     // exists in maintenance mode only
+  CiB200Options baseOpts_;
+  CiB200GroupOptions groupOpts_;
   void MirrorResumed(int64_t n, const int64_t *pCounts, const CiAnsweredQuestion *pAQs, const int64_t *pQuizIds);
   static std::vector<CiB200Options> ShardOptions(const CiEngineDefinition &def, const CiB200Options &opts,
                                                  const CiB200GroupOptions &gopts);

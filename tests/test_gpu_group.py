@@ -91,7 +91,6 @@ def test_group_behaves_like_one_engine(axis, dims, n_shards, exact, tmp_path):
         assert np.array_equal(bits(g), bits(w))
     quiz = again.start_quiz()
     assert 0 <= again.next_question(quiz) < Q
-    assert grp.start_maintenance(True, throw=False) is not None      # single-engine feature
 
 
 @pytest.mark.parametrize("axis,dims,n_shards", [("questions", (40, 5, 203), 3), ("targets", (36, 5, 1000), 2), ("targets", (25, 4, 96), 4)])
@@ -149,6 +148,71 @@ def test_group_resume_quiz_and_clear_old_quizzes(axis, dims, n_shards):
     assert grp.start_quiz() == one.start_quiz()            # released ids are reused in the same (LIFO) order
     grp.clear_old_quizzes(0, -1.0); one.clear_old_quizzes(0, -1.0)
     assert grp.start_quiz() == one.start_quiz()
+
+
+@pytest.mark.parametrize("axis,dims,n_shards", [("questions", (12, 4, 50), 3), ("targets", (10, 5, 203), 2), ("targets", (9, 3, 64), 4)])
+def test_group_maintenance_mode(axis, dims, n_shards, tmp_path):
+    """Maintenance mode on a group handle (BaseEngine.cpp:640-779): the KB is gathered into one engine, resized / trimmed /
+    compacted there and split over new shards at FinishMaintenance. Every step against one un-sharded engine doing the same:
+    dimensions, id maps, the KB bit for bit, the mode contract; afterwards quizzes run on the re-sharded KB with posteriors
+    bit-identical to the single engine's."""
+    from probqa_b200 import engine as pqa
+    Q, K, T = dims
+    W = 4
+    kb = synth.gamma_kb(Q, K, T, INIT)
+    fac = pqa.PqaEngineFactory()
+    edef = pqa.EngineDefinition(K, Q, T, init_amount=INIT)
+    one = fac.create_b200_engine(edef, emulated_workers=W, rng_seed=5)
+    grp = fac.create_sharded_engine(edef, axis, n_shards, devices=devices(n_shards), exact_order=True, emulated_workers=W, rng_seed=5)
+    one.upload_kb(*kb); grp.upload_kb(*kb)
+    quiz = grp.start_quiz(); one.start_quiz()
+    assert grp.add_qs_ts([1.0], [], throw=False) is not None                       # maintenance-only call in regular mode
+    assert grp.start_maintenance(False, throw=False) is not None                   # QuizzesActive unless forced (BaseEngine.cpp:646-655)
+    grp.start_maintenance(True); one.start_maintenance(True)                       # destroys the quizzes
+    with pytest.raises(pqa.PqaException):
+        grp.start_quiz()
+    def same_kb():
+        for g, w in zip(grp.download_kb(), one.download_kb()):
+            assert np.array_equal(bits(g), bits(w))
+    same_kb()
+    # grow: 3 questions, 5 targets; then remove some of each; ids and cells must follow the single engine
+    for e in (grp, one):
+        e.add_qs_ts([0.5, 1.5, 2.5], [0.25, 0.5, 0.75, 1.0, 1.25])
+    dg, do = grp.copy_dims(), one.copy_dims()
+    assert (dg.n_questions, dg.n_targets) == (do.n_questions, do.n_targets) == (Q + 3, T + 5)
+    grp._refresh_dims(); one._refresh_dims()
+    same_kb()
+    for e in (grp, one):
+        e.remove_questions([1, Q + 1]); e.remove_targets([0, 7, T + 2])
+    assert np.array_equal(grp.question_perm_from_comp(np.arange(Q + 3)), one.question_perm_from_comp(np.arange(Q + 3)))
+    assert np.array_equal(grp.target_perm_from_comp(np.arange(T + 5)), one.target_perm_from_comp(np.arange(T + 5)))
+    assert grp.finish_maintenance(throw=False) is not None                         # shards hold no gaps: compact first
+    cg, co = grp.compact(), one.compact()
+    assert np.array_equal(cg[0], co[0]) and np.array_equal(cg[1], co[1])
+    grp._refresh_dims(); one._refresh_dims()
+    same_kb()
+    p = str(tmp_path / "maint.kb")
+    grp.save_kb(p)                                                                  # still in maintenance: the gathered KB is saved
+    grp.finish_maintenance(); one.finish_maintenance()
+    dg = grp.copy_dims()
+    assert (dg.n_questions, dg.n_targets) == (Q + 1, T + 2) and grp.shard_count() == n_shards
+    same_kb()
+    p1 = str(tmp_path / "one.kb")
+    one.save_kb(p1)
+    assert open(p, "rb").read() == open(p1, "rb").read()
+    assert np.array_equal(grp.target_comp_from_perm(np.arange(T + 5)), one.target_comp_from_perm(np.arange(T + 5)))
+    # the re-sharded KB serves quizzes like the single engine
+    ids_g, ids_o = grp.start_quiz_batch(6), one.start_quiz_batch(6)
+    assert np.array_equal(ids_g, ids_o)
+    rng = np.random.default_rng(3)
+    for step in range(2):
+        randoms = rng.integers(0, 2 ** 64, size=6, dtype=np.uint64)
+        chosen = grp.next_question_batch(ids_g, randoms)
+        one.set_active_question_batch(ids_o, chosen)
+        answers = [int(c) % K for c in chosen]
+        grp.record_answer_batch(ids_g, answers); one.record_answer_batch(ids_o, answers)
+        for q in ids_g:
+            assert np.array_equal(bits(grp.copy_quiz_priors(int(q))), bits(one.copy_quiz_priors(int(q))))
 
 
 def test_group_serves_concurrent_one_quiz_clients():
