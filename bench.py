@@ -38,7 +38,12 @@ WORKLOADS = {
     "10000x5x100000_b64": dict(Q=10000, K=5, T=100000, B=64),
     "10000x5x100000_b256": dict(Q=10000, K=5, T=100000, B=256),
     "2000x5x20000_b64": dict(Q=2000, K=5, T=20000, B=64),
+    "1000x5x1000_b4": dict(Q=1000, K=5, T=1000, B=4),
+    "1000x5x1000_b6": dict(Q=1000, K=5, T=1000, B=6),
     "1000x5x1000_b8": dict(Q=1000, K=5, T=1000, B=8),
+    "1000x5x1000_b12": dict(Q=1000, K=5, T=1000, B=12),
+    "1000x5x1000_b24": dict(Q=1000, K=5, T=1000, B=24),
+    "1000x5x1000_b48": dict(Q=1000, K=5, T=1000, B=48),
     "1000x5x1000_b16": dict(Q=1000, K=5, T=1000, B=16),
     "1000x5x1000_b32": dict(Q=1000, K=5, T=1000, B=32),
     "1000x5x1000_b64": dict(Q=1000, K=5, T=1000, B=64),

@@ -188,6 +188,11 @@ PQACORE_API void *PqaB200_P2PNextQuestionBegin(void *pvEngine, int64_t n, const 
 PQACORE_API void *PqaB200_P2PNextQuestionEnd(void *pvEngine, int64_t n, const int64_t *pQuizIds, int64_t *pQuestions, void **ppErrors);
 PQACORE_API void *PqaB200_P2PRecordAnswerBegin(void *pvEngine, int64_t n, const int64_t *pQuizIds, const int64_t *pAnswers);
 PQACORE_API void *PqaB200_P2PRecordAnswerEnd(void *pvEngine);
+/* The reference's question evaluation only WARNS (through its logger) about a priority that is <= 0 or not finite
+ * (CEEvalQsSubtaskConsider.cpp:209-211), about non-finite running totals (CpuEngine.cpp:368-371) and about a grand total
+ * <= 0 (CpuEngine.cpp:375-377), and carries on; so does this engine. pCounts3 receives how often each of the three has
+ * been seen by NextQuestion since the engine was created; a growing count is also reported on stderr. */
+PQACORE_API void *PqaB200_AnomalyCounts(void *pvEngine, uint64_t *pCounts3);
 /* Target shards: device time (ms, CUDA events on the engine's stream) of the five stages of the most recent
  * P2PNextQuestion -- phase 1, exchange barrier, phase 2, exchange barrier, epilogue + selection. Call after its End. */
 PQACORE_API void *PqaB200_P2PLastPhaseMs(void *pvEngine, double *pMs5);

@@ -525,6 +525,11 @@ PQACORE_API void *PqaB200_P2PLastPhaseMs(void *pvEngine, double *pMs5) {
   if (!pMs5) return Ret(MakeError(ErrCode::NullArgument, "pMs5"));
   return Ret(Guard([&] { return E(pvEngine)->P2PLastPhaseMs(pMs5); }));
 }
+PQACORE_API void *PqaB200_AnomalyCounts(void *pvEngine, uint64_t *pCounts3) {
+  if (PqaError *g_ = Gate(pvEngine)) return g_;
+  if (!pCounts3) return Ret(MakeError(ErrCode::NullArgument, "pCounts3"));
+  return Ret(Guard([&] { return E(pvEngine)->AnomalyCounts(pCounts3); }));
+}
 PQACORE_API void *PqaB200_P2PSetExactOrder(void *pvEngine, int32_t on) {
   if (PqaError *g_ = Gate(pvEngine)) return g_;
   return Ret(Guard([&] { return E(pvEngine)->P2PSetExactOrder(on); }));

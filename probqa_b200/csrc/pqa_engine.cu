@@ -98,6 +98,10 @@ Engine::Engine(const CiEngineDefinition &def, const CiB200Options &opts) {
   launch_fill_kb(kb(), initSqr, initSqr * (double)K_, initAmount_, stream_);
   if (IsTargetSharded()) launch_fill_kb(kbQuiz(), initSqr, initSqr * (double)K_, initAmount_, stream_);   // full-length vB
   EnsureQuizCapacity(opts._initialQuizCapacity > 0 ? opts._initialQuizCapacity : 256);
+  PQA_CU(cudaMalloc(&dAnom_, sizeof(unsigned long long) * kAnomalyKinds));
+  PQA_CU(cudaMemsetAsync(dAnom_, 0, sizeof(unsigned long long) * kAnomalyKinds, stream_));
+  PQA_CU(cudaHostAlloc((void **)&hAnom_, sizeof(uint64_t) * kAnomalyKinds, cudaHostAllocDefault));
+  std::memset(hAnom_, 0, sizeof(uint64_t) * kAnomalyKinds);
   if (K_ <= 8) {      // the derived KB of the throughput kernels (kbEval): allocated now, built at the first evaluation
     size_t nR = 0, nL = 0;
     derived_kb_doubles(kb(), &nR, &nL);
@@ -146,6 +150,8 @@ Engine::~Engine() {
   cudaFree(dSA_); cudaFree(dMD_); cudaFree(dVB_); cudaFree(dLog2Tbl_);
   cudaFree(dDerR_);
   if (hFew_) cudaFreeHost((void *)hFew_);
+  if (hAnom_) cudaFreeHost(hAnom_);
+  if (dAnom_) cudaFree(dAnom_);
   cudaFree(dPriors_); cudaFree(dLogPriors_); cudaFree(dAsked_); cudaFree(dActive_); cudaFree(dNormS_);
   for (int r = 0; r < kMaxPeers; r++) if (p2pOpened_[r]) cudaIpcCloseMemHandle(p2pPeer_[r]);
   if (p2pInbox_) cudaFree(p2pInbox_);
@@ -165,6 +171,7 @@ DeviceKB Engine::kb() const {
   k.Q = Q_; k.K = K_; k.T = tLocal_; k.Tp = TpL_;   // a target-sharded engine sees its own columns here
   k.nValidTargets = T_ - tGaps_.GetNGaps();  // CpuEngine.cpp:351
   k.qFirst = qFirst_; k.qCount = qLocal_;
+  k.anomalies = dAnom_;
   return k;
 }
 // The view the quiz-level kernels use (StartQuiz, selection, ListTopTargets, vB updates): whole-length vB / priors.
@@ -492,6 +499,7 @@ PqaError *Engine::NextQuestionBatch(int64_t n, const int64_t *pQuizIds, const ui
       __builtin_ia32_pause();
 #endif
     }
+    ReportAnomalies((const volatile uint64_t *)hFew_ + kFewHostSlots + 1);
     uint64_t nAsked = 0;
     for (int64_t x = 0; x < m; x++) {
       const int64_t qst = ((volatile int64_t *)hFew_)[x];
@@ -519,7 +527,9 @@ PqaError *Engine::NextQuestionBatch(int64_t n, const int64_t *pQuizIds, const ui
     launch_select_question(kbQuiz(), pool(), m, dIds_.get(), dPriority_.get(), dRandoms_.get(), W_, dRunLength_.get(),
                            nullptr, dQuestions_.get(), 1, stream_);
     PQA_CU(cudaMemcpyAsync(hQuestions_.get(), dQuestions_.get(), sizeof(int64_t) * (size_t)m, cudaMemcpyDeviceToHost, stream_));
+    QueueAnomalyCopy();
     PQA_CU(cudaGetLastError()); PQA_CU(cudaStreamSynchronize(stream_));
+    ReportAnomalies(hAnom_);
     uint64_t nAsked = 0;
     for (int64_t x = 0; x < m; x++) {
       const int64_t qst = hQuestions_.get()[x];
@@ -816,7 +826,9 @@ PqaError *Engine::ShardSelect(int64_t n, const int64_t *pQuizIds, const uint64_t
   launch_select_question(kbQuiz(), pool(), n, dIds_.get(), dShardPriority_.get(), dRandoms_.get(), W_, dRunLength_.get(),
                          nullptr, dQuestions_.get(), 1, stream_);
   PQA_CU(cudaMemcpyAsync(hQuestions_.get(), dQuestions_.get(), sizeof(int64_t) * (size_t)n, cudaMemcpyDeviceToHost, stream_));
+  QueueAnomalyCopy();
   PQA_CU(cudaGetLastError()); PQA_CU(cudaStreamSynchronize(stream_));
+  ReportAnomalies(hAnom_);
   PqaError *firstErr = nullptr;
   uint64_t nAsked = 0;
   for (int64_t x = 0; x < n; x++) {
@@ -1310,18 +1322,51 @@ PqaError *Engine::SetEvalKernel(int32_t which, int64_t chunkTargets, int64_t qui
   return nullptr;
 }
 
-// Measured at 1000x5x1000 (bench.py e2e, ms per NextQuestion batch): fused kernel 0.05 / 0.22 / 0.37 / 0.66 at 1 / 8 / 16 / 32
-// quizzes (it streams the derived KB from L2 once per four quizzes), shared-memory slab kernels 0.23 / 0.43 / 0.38 at 8 / 16 /
-// 32: the fused launch serves batches up to 16.
+void Engine::QueueAnomalyCopy() {
+  if (dAnom_) cudaMemcpyAsync(hAnom_, dAnom_, sizeof(uint64_t) * kAnomalyKinds, cudaMemcpyDeviceToHost, stream_);
+}
+// caller holds mu_; `now` = counters read after the stream was synchronised (or published by the fused kernel)
+void Engine::ReportAnomalies(const volatile uint64_t *now) {
+  static const char *const what[kAnomalyKinds] = {
+      "question priorities <= 0 or not finite (CEEvalQsSubtaskConsider.cpp:209-211)",
+      "non-finite running totals of the priorities: overflow or underflow in the question evaluation (CpuEngine.cpp:368-371)",
+      "grand totals of the priorities <= 0 (CpuEngine.cpp:375-377)"};
+  for (int a = 0; a < kAnomalyKinds; a++) {
+    const uint64_t v = now[a];
+    if (v <= anomSeen_[a]) continue;
+    const uint64_t delta = v - anomSeen_[a];
+    anomSeen_[a] = v;
+    // warn like the reference's logger, but not for every call of a loop: the first 8, then at powers of two
+    anomWarnings_++;
+    if (anomWarnings_ <= 8 || (anomWarnings_ & (anomWarnings_ - 1)) == 0)
+      std::fprintf(stderr, "[probqa_b200] warning: NextQuestion saw %llu %s; %llu so far\n", (unsigned long long)delta,
+                   what[a], (unsigned long long)v);
+  }
+}
+PqaError *Engine::AnomalyCounts(uint64_t *pCounts3) {
+  std::lock_guard<std::mutex> lk(mu_); DeviceScope devScope(device_);
+  PQA_TRY
+  if (!dAnom_) { for (int a = 0; a < kAnomalyKinds; a++) pCounts3[a] = 0; return nullptr; }
+  QueueAnomalyCopy();
+  PQA_CU(cudaStreamSynchronize(stream_));
+  for (int a = 0; a < kAnomalyKinds; a++) pCounts3[a] = hAnom_[a];
+  return nullptr;
+  PQA_CATCH_RETURN_ERR
+}
+
+// Measured at 1000x5x1000 (bench.py e2e, ms per NextQuestion batch): fused kernel 0.05 / 0.16 / 0.18 / 0.24 / 0.38 at 1 / 4 /
+// 6 / 8 / 16 quizzes (it streams the derived KB from L2 once per four quizzes); medium-batch kernel + selection + copy
+// 0.15 / 0.15 / 0.18 / 0.27 at 6 / 8 / 16 / 32: the fused launch serves batches up to 4 (one tile of it).
 bool Engine::UseFewPath(int64_t n) const {
-  static const int64_t limit = std::min<int64_t>(eval_few_max(), env_int("PQA_B200_FEW_MAX", 16));
+  static const int64_t limit = std::min<int64_t>(eval_few_max(), env_int("PQA_B200_FEW_MAX", 4));
   return n <= limit && !IsSharded() && K_ <= 8 && evalCfg_.which != 1 && evalCfg_.kahanLanesPerThread == 0 &&
          evalCfg_.chunkTargets == 0;
 }
 void Engine::EnsureFewResources() {
   if (hFew_) return;
-  PQA_CU(cudaHostAlloc((void **)&hFew_, sizeof(int64_t) * (kFewHostSlots + 1), cudaHostAllocMapped));
-  std::memset((void *)hFew_, 0, sizeof(int64_t) * (kFewHostSlots + 1));
+  // {questions[kFewHostSlots], sequence word, anomaly counters}
+  PQA_CU(cudaHostAlloc((void **)&hFew_, sizeof(int64_t) * (kFewHostSlots + 1 + kAnomalyKinds), cudaHostAllocMapped));
+  std::memset((void *)hFew_, 0, sizeof(int64_t) * (kFewHostSlots + 1 + kAnomalyKinds));
   PQA_CU(cudaHostGetDevicePointer(&dFewHost_, (void *)hFew_, 0));
   dFewTickets_.ensure((size_t)eval_few_ticket_count(), stream_);
   PQA_CU(cudaMemsetAsync(dFewTickets_.get(), 0, sizeof(unsigned) * (size_t)eval_few_ticket_count(), stream_));
@@ -1785,6 +1830,7 @@ PqaError *Engine::P2PNextQuestionBegin(int64_t n, const int64_t *pQuizIds, const
   if (IsTargetSharded()) PQA_CU(cudaEventRecord(p2pEv_[5], stream_));
   p2pPhasesValid_ = IsTargetSharded();
   PQA_CU(cudaMemcpyAsync(hQuestions_.get(), dQuestions_.get(), sizeof(int64_t) * (size_t)n, cudaMemcpyDeviceToHost, stream_));
+  QueueAnomalyCopy();
   PQA_CU(cudaGetLastError());      // a kernel that failed to launch would leave the peers waiting at the barrier
   p2pPending_ = true;
   return nullptr;
@@ -1798,6 +1844,7 @@ PqaError *Engine::P2PNextQuestionEnd(int64_t n, const int64_t *pQuizIds, int64_t
   if (!p2pPending_) return MakeError(ErrCode::NotInitialized, PQA_FILE_LINE "P2PNextQuestionEnd without a Begin");
   p2pPending_ = false;
   if (PqaError *e = P2PCheckError()) return e;
+  if (p2pRank_ == 0) ReportAnomalies(hAnom_);      // every shard counts the same; one of them speaks
   PqaError *firstErr = nullptr;
   uint64_t nAsked = 0;
   for (int64_t x = 0; x < n; x++) {

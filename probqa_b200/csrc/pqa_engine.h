@@ -251,6 +251,9 @@ class Engine {
   virtual PqaError *P2PNextQuestionEnd(int64_t n, const int64_t *pQuizIds, int64_t *pQuestions, void **ppErrors);
   virtual PqaError *P2PRecordAnswerBegin(int64_t n, const int64_t *pQuizIds, const int64_t *pAnswers);
   virtual PqaError *P2PRecordAnswerEnd();
+  // Warn-only conditions of the reference's evaluation counted by the selection kernels (DeviceKB::anomalies); a growing
+  // counter is also reported on stderr, as the reference's logger does.
+  virtual PqaError *AnomalyCounts(uint64_t *pCounts3);
   virtual PqaError *P2PLastPhaseMs(double *pMs5);   // device time of the stages of the last target-sharded P2PNextQuestion
   virtual PqaError *P2PSetExactOrder(int32_t on);   // target shards: hand the Kahan lanes from shard to shard (W_k bit-exact)
   // closed-form synthetic KB of SURVEY.md 8d written on the device (this engine's shard of it)
@@ -381,6 +384,12 @@ class Engine {
   volatile void *hFew_ = nullptr;
   void *dFewHost_ = nullptr;
   DevBuf<unsigned> dFewTickets_;
+  unsigned long long *dAnom_ = nullptr;      // DeviceKB::anomalies
+  uint64_t *hAnom_ = nullptr;                // pinned copy read after the batch paths' synchronisation
+  uint64_t anomSeen_[kAnomalyKinds] = {};
+  uint64_t anomWarnings_ = 0;
+  void QueueAnomalyCopy();
+  void ReportAnomalies(const volatile uint64_t *now);
   uint64_t fewSeq_ = 0;
 
   // resident batch

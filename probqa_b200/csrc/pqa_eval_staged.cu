@@ -39,6 +39,7 @@
 #include "pqa_select.cuh"
 
 #include <atomic>
+#include <cstdlib>
 #include <math.h>
 #include <stdio.h>
 #include <stdexcept>
@@ -603,6 +604,105 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 4 ? 4 : 2) k_eval_staged(
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Medium batches (5 ... 64 quizzes, a slab that would fit shared memory whole). One question per CTA would leave most of
+// the CTA's warps without a quiz, and the shared memory of an SM holds only two whole slabs. Here a CTA takes
+// PLACES / G consecutive questions (G = quiz places per question, P.quizzesPerCta; PLACES = 256 threads / threads per
+// quiz) and streams their slabs through the two-stage ring in chunks of P.Vc vectors; thread group p serves quiz p % G of
+// question p / G for the whole launch, with the arithmetic of the throughput kernel (KL Kahan lanes per thread, W_k
+// bit-exact, pass 1 over all chunks, then pass 2). All 8 warps work whatever the batch size, and the grid shrinks with
+// it. KL = 2 (two threads per quiz) for 17 ... 64 quizzes; KL = 1 (four threads per quiz: half the serial work per
+// thread) up to 16, where there are too few quizzes to fill the SMs and the length of a thread's chain is what counts.
+template <int K, int KL>
+__global__ void __launch_bounds__(256, 2) k_eval_multi(const StagedParams P) {
+  constexpr int THREADS = 256, LPQ = 4 / KL, PLACES = THREADS / LPQ;
+  extern __shared__ __align__(128) unsigned char smRaw[];
+  __shared__ uint64_t bars[kStages];
+  const int G = (int)P.quizzesPerCta, qpc = PLACES / G;
+  const int64_t Q = P.kb.Q, Tp = P.kb.Tp, nV = Tp >> 2;
+  const int pair = threadIdx.x / LPQ, l0 = (threadIdx.x % LPQ) * KL;
+  const int qs = pair / G;
+  const int64_t b = pair % G;
+  const int64_t iFirst = (int64_t)blockIdx.x * qpc;                     // first local question of this CTA
+  const int nQuestions = (int)((P.kb.qCount - iFirst < qpc) ? (P.kb.qCount - iFirst) : qpc);
+  const int64_t iLocal = iFirst + qs, i = P.kb.qFirst + iLocal;
+  const double qnan = __longlong_as_double(0x7FF8000000000000ll);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < kStages; s++) mbar_init(&bars[s], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  bool live = qs < nQuestions && b < P.n;
+  const int64_t slot = P.slots[b < P.n ? b : P.n - 1];
+  if (live && (bit32(P.kb.qgaps, i) || bit64(P.qp.asked + slot * P.qp.askedWords, i))) {   // CEEvalQsSubtaskConsider.cpp:54-58
+    if (l0 == 0) store_priority(P, b * Q + i, qnan);
+    live = false;
+  }
+  const double *pr = P.qp.priors + slot * Tp + l0, *lpr = P.qp.logPriors + slot * Tp + l0;
+  const int64_t perQuestion = P.Vc * ((2 * K + 1) * 4);                  // doubles of one question's chunk: R, then L
+  const int64_t stageDoubles = perQuestion * qpc;
+  double *const ring = (double *)smRaw;
+  const int64_t total = 2 * P.nChunks;
+  // thread 0: ring item g (pass 1: chunk g of R; pass 2: chunk g - nChunks of R and L) of every question of the CTA
+  auto issue_item = [&](int64_t g) {
+    const int64_t c = g % P.nChunks, v0 = c * P.Vc;
+    const bool withL = g >= P.nChunks;
+    const int64_t nv = (nV - v0 < P.Vc) ? (nV - v0) : P.Vc;
+    const uint32_t bytesR = (uint32_t)(nv * (K * 32)), bytesL = (uint32_t)(nv * ((K + 1) * 32));
+    uint64_t *bar = &bars[g % kStages];
+    double *stage = ring + (g % kStages) * stageDoubles;
+    mbar_arrive_expect_tx(bar, (uint32_t)nQuestions * (withL ? bytesR + bytesL : bytesR));
+    for (int q = 0; q < nQuestions; q++) {
+      double *sR = stage + q * perQuestion;
+      bulk_g2s(sR, P.kb.dR + ((iFirst + q) * nV + v0) * (K * 4), bytesR, bar);
+      if (withL) bulk_g2s(sR + P.Vc * (K * 4), P.kb.dL + ((iFirst + q) * nV + v0) * ((K + 1) * 4), bytesL, bar);
+    }
+  };
+  if (threadIdx.x == 0)
+    for (int64_t g = 0; g < kStages && g < total; g++) issue_item(g);
+  auto next_item = [&](int64_t g) {
+    __syncthreads();  // everyone is done with the stage before the next copy overwrites it
+    if (threadIdx.x == 0 && g + kStages < total) {
+      fence_proxy_async_smem();
+      issue_item(g + kStages);
+    }
+  };
+  double W[K], iW[K], lW[K];
+#pragma unroll
+  for (int k = 0; k < K; k++) { W[k] = 0.0; iW[k] = 0.0; lW[k] = 0.0; }
+  {
+    Kahan kw[KL][K];
+#pragma unroll
+    for (int e = 0; e < KL; e++)
+#pragma unroll
+      for (int k = 0; k < K; k++) kw[e][k].init();
+    for (int64_t g = 0; g < P.nChunks; g++) {
+      const double *sR = ring + (g % kStages) * stageDoubles + qs * perQuestion;
+      const int64_t v0 = g * P.Vc;
+      const int nVects = (int)((nV - v0 < P.Vc) ? (nV - v0) : P.Vc);
+      mbar_wait(&bars[g % kStages], (uint32_t)((g / kStages) & 1));
+      if (live) pass1_chunk<K, KL>(sR, nVects, pr + 4 * v0, l0, kw);
+      next_item(g);
+    }
+    if (live) finish_pass1<K, KL>(kw, W, iW, lW);      // the threads of a quiz are live together
+  }
+  double H[K], V[K], L[KL];
+#pragma unroll
+  for (int k = 0; k < K; k++) { H[k] = 0.0; V[k] = 0.0; }
+#pragma unroll
+  for (int e = 0; e < KL; e++) L[e] = 0.0;
+  for (int64_t g = P.nChunks; g < total; g++) {
+    const double *sR = ring + (g % kStages) * stageDoubles + qs * perQuestion, *sL = sR + P.Vc * (K * 4);
+    const int64_t v0 = (g - P.nChunks) * P.Vc;
+    const int nVects = (int)((nV - v0 < P.Vc) ? (nV - v0) : P.Vc);
+    mbar_wait(&bars[g % kStages], (uint32_t)((g / kStages) & 1));
+    if (live) pass2_chunk<K, KL>(sR, sL, nVects, pr + 4 * v0, lpr + 4 * v0, P.kb.log2tbl, l0, iW, lW, H, V, L);
+    next_item(g);
+  }
+  if (live) finish_pass2<K, KL>(P, i, b, l0, W, H, V, L);
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // Small batches (fewer quizzes than one warp of the kernel above would hold): latency matters more than throughput.
 // One CTA per question handles SW quizzes per round. Pass 1 cannot be spread over targets (the reference's Kahan order
 // is a serial dependency per (answer, Kahan lane)): warp w runs the 4K chains of quiz w on lanes 4k + l -- W_k stays
@@ -877,12 +977,16 @@ __global__ void __launch_bounds__(kFewMax * 32, 7) k_eval_few(const FewParams P)
       __threadfence();
       const int64_t nSel = split_count(Q, (int64_t)P.W * 8);
       const uint64_t draw = P.dRandoms ? P.dRandoms[b0 + b] : P.randoms[b];
+      bool anomaly = false;
       const int64_t chosen = select_question_cta(P.kb, P.qp, slot, P.priority + (int64_t)(b0 + b) * Q, draw, P.W,
                                                  P.runLength + (int64_t)(b0 + b) * Q,
                                                  P.grandOut ? P.grandOut + (b0 + b) * nSel : nullptr,
-                                                 P.hostQuestions != nullptr, P.setActive, sGrand);
+                                                 P.hostQuestions != nullptr, P.setActive, sGrand, &anomaly);
       if (threadIdx.x == 0 && P.hostQuestions) {
         P.hostQuestions[b0 + b] = chosen;
+        if (anomaly && P.kb.anomalies)       // the CTA that saw one publishes the counters beside the sequence word
+          for (int a = 0; a < kAnomalyKinds; a++)
+            reinterpret_cast<volatile uint64_t *>(P.hostSeq)[1 + a] = atomicAdd(P.kb.anomalies + a, 0ull);
         __threadfence_system();
         unsigned *done = P.tickets + kFewBatchMax * (kFewGroups + 1);
         if (atomicAdd(done, 1u) + 1u == (unsigned)P.n) {                 // every quiz of the call has its question
@@ -1229,6 +1333,37 @@ static void launch_small(StagedParams P, size_t smem, cudaStream_t st) {
   count_launch();
 }
 
+// Medium batches: geometry and launch of k_eval_multi (see there). Only for slabs that would be resident.
+constexpr int64_t kMultiRingBudget = 100 * 1024;
+static bool multi_applies(const StagedParams &P, const EvalConfig &cfg) {
+  return P.n > 0 && P.n <= 64 && P.nChunks == 1 && cfg.kahanLanesPerThread == 0 && cfg.chunkTargets == 0 &&
+         cfg.quizzesPerCta == 0 && cfg.which != 1;
+}
+static int multi_min() {     // batches of this many ... 64 quizzes go to k_eval_multi (PQA_B200_MULTI_MIN: experiments)
+  static const int v = [] { const char *e = std::getenv("PQA_B200_MULTI_MIN"); return e && *e ? std::atoi(e) : 5; }();
+  return v;
+}
+template <int K, int KL>
+static void launch_multi_kl(StagedParams P, int64_t G, cudaStream_t st) {
+  static std::atomic<unsigned long long> dev{0};
+  allow_big_smem(k_eval_multi<K, KL>, dev);
+  const int64_t places = 256 / (4 / KL), qpc = places / G, nV = P.kb.Tp >> 2;
+  int64_t Vc = (kMultiRingBudget / (kStages * qpc * (2 * K + 1) * 32)) & ~7ll;
+  if (Vc > 1016) Vc = 1016;                                   // pass 2 packs step numbers into 10 bits
+  if (Vc > nV) Vc = nV;
+  P.Vc = Vc; P.nChunks = (nV + Vc - 1) / Vc; P.quizzesPerCta = G;
+  const size_t smem = (size_t)(kStages * qpc * Vc * (2 * K + 1) * 32);
+  const unsigned grid = (unsigned)((P.kb.qCount + qpc - 1) / qpc);
+  k_eval_multi<K, KL><<<grid, 256, smem, st>>>(P);
+  count_launch();
+}
+template <int K>
+static void launch_multi(const StagedParams &P, cudaStream_t st) {
+  static const int kl1Max = [] { const char *e = std::getenv("PQA_B200_MULTI_KL1_MAX"); return e && *e ? std::atoi(e) : 16; }();
+  if (P.n <= kl1Max && P.n <= 64) launch_multi_kl<K, 1>(P, P.n <= 8 ? 8 : P.n <= 16 ? 16 : P.n <= 32 ? 32 : 64, st);
+  else launch_multi_kl<K, 2>(P, P.n <= 16 ? 16 : P.n <= 32 ? 32 : 64, st);
+}
+
 template <int K, int KL, int WARPS>
 static void launch_cfg(StagedParams P, const EvalConfig &cfg, size_t smem, cudaStream_t st) {
   static std::atomic<unsigned long long> dev{0};
@@ -1256,6 +1391,7 @@ static void launch_cfg(StagedParams P, const EvalConfig &cfg, size_t smem, cudaS
 
 template <int K>
 static void launch_k(const StagedParams &P, const EvalConfig &cfg, size_t smem, cudaStream_t st) {
+  if (multi_applies(P, cfg) && P.n >= multi_min()) { launch_multi<K>(P, st); return; }
   if (cfg.kahanLanesPerThread == 0 && P.n < 32 && P.nChunks == 1 && cfg.chunkTargets == 0) { launch_small<K>(P, smem, st); return; }
   // batches >= 32: two threads per quiz (16 quizzes per warp, 16 warps per SM; measured fastest); small batches: four
   // threads per quiz; one thread per quiz (4 lanes, 4 warps per CTA) is kept selectable for experiments
@@ -1312,6 +1448,8 @@ template <int K> static void preload_staged_k() {
   cudaFuncGetAttributes(&a, k_eval_staged<K, 2, 8>);
   cudaFuncGetAttributes(&a, k_eval_staged<K, 4, 4>);
   cudaFuncGetAttributes(&a, k_eval_small<K, 8>);
+  cudaFuncGetAttributes(&a, k_eval_multi<K, 1>);
+  cudaFuncGetAttributes(&a, k_eval_multi<K, 2>);
   cudaFuncGetAttributes(&a, k_eval_few<K>);
   cudaFuncGetAttributes(&a, k_eval_staged<K, 2, 4>);
   cudaFuncGetAttributes(&a, k_eval_tshard<K, 2, 4, 1>);

@@ -580,4 +580,12 @@ PqaError *ShardGroup::SetEvalKernel(int32_t which, int64_t chunkTargets, int64_t
   return err;
 }
 
+// every shard runs the same selection on the same priorities: the first shard's counters are the group's
+PqaError *ShardGroup::AnomalyCounts(uint64_t *pCounts3) {
+  if (maint_) return maint_->AnomalyCounts(pCounts3);
+  if (shards_.empty()) { for (int a = 0; a < kAnomalyKinds; a++) pCounts3[a] = 0; return nullptr; }
+  cudaSetDevice(shards_[0]->device());
+  return shards_[0]->AnomalyCounts(pCounts3);
+}
+
 } // namespace pqa

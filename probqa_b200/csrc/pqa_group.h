@@ -78,6 +78,7 @@ class ShardGroup : public Engine {
   PqaError *P2PRecordAnswerBegin(int64_t, const int64_t *, const int64_t *) override { return No("P2P* protocol"); }
   PqaError *P2PRecordAnswerEnd() override { return No("P2P* protocol"); }
   PqaError *P2PLastPhaseMs(double *) override { return No("P2P* protocol"); }
+  PqaError *AnomalyCounts(uint64_t *pCounts3) override;
   PqaError *P2PSetExactOrder(int32_t) override { return No("P2P* protocol (CiB200GroupOptions::_exactOrder)"); }
   PqaError *ResidentBind(int64_t, const int64_t *, const uint64_t *) override { return No("resident stepping"); }
   PqaError *ResidentStep() override { return No("resident stepping"); }

@@ -28,7 +28,12 @@ struct DeviceKB {
   // Question shard held by this device: rows of questions qFirst .. qFirst+qCount-1 (sA/mD are indexed by i - qFirst).
   // A single-device engine has qFirst = 0, qCount = Q.
   int64_t qFirst, qCount;
+  // Warn-only anomaly counters the selection maintains (the reference logs these conditions and carries on):
+  // [0] priorities of available questions that are <= 0 or not finite (CEEvalQsSubtaskConsider.cpp:209-211),
+  // [1] non-finite chunk totals (CpuEngine.cpp:368-371), [2] grand totals <= 0 (:375-377). nullptr = not counted.
+  unsigned long long *anomalies = nullptr;
 };
+constexpr int kAnomalyKinds = 3;
 
 constexpr int kMaxPeers = 8;   // shard engines of one box
 

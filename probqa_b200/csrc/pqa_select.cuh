@@ -72,20 +72,28 @@ __device__ __forceinline__ int64_t upper_bound_d(const double *a, int64_t n, dou
 // Returns (to thread 0 only) the chosen question or -1; other threads return -2.
 __device__ __forceinline__ int64_t select_question_cta(const DeviceKB &kb, const QuizPool &qp, int64_t slot, const double *pri,
                                                        uint64_t random, int W, double *runLength, double *grandOut,
-                                                       bool wantQuestion, int setActive, double *sGrand) {
+                                                       bool wantQuestion, int setActive, double *sGrand,
+                                                       bool *sawAnomaly = nullptr) {
   const int64_t Q = kb.Q;
   const uint64_t *asked = qp.asked + slot * qp.askedWords;
   const int64_t nW = (int64_t)W * 8, nChunks = split_count(Q, nW);
+  unsigned bad = 0;      // priorities of available questions that are <= 0 or not finite: :209-211 warns and adds them anyway
   for (int64_t c = threadIdx.x; c < nChunks; c += blockDim.x) {
     const int64_t first = split_start(Q, nW, c), limit = split_start(Q, nW, c + 1);
     Kahan run; run.init(0.0);
     for (int64_t i = first; i < limit; i++) {
-      if (!(bit32(kb.qgaps, i) || bit64(asked, i))) run.add(pri[i]);
+      if (!(bit32(kb.qgaps, i) || bit64(asked, i))) {
+        const double v = pri[i];
+        const long long vb = __double_as_longlong(v);                     // positive and finite <=> 0 < bits < those of +inf
+        bad += !(vb > 0ll && vb < 0x7FF0000000000000ll);
+        run.add(v);
+      }
       runLength[i] = run.get();
     }
     sGrand[c] = run.get();
   }
-  __syncthreads();
+  if (bad && kb.anomalies) atomicAdd(kb.anomalies + 0, (unsigned long long)bad);
+  bool anomaly = __syncthreads_or(bad != 0) != 0;
   if (threadIdx.x != 0) return -2;
   Kahan tot; tot.init(0.0);
   for (int64_t c = 0; c < nChunks; c++) {  // CpuEngine.cpp:362-374
@@ -93,8 +101,12 @@ __device__ __forceinline__ int64_t select_question_cta(const DeviceKB &kb, const
     sGrand[c] = tot.get();
     if (grandOut) grandOut[c] = sGrand[c];
   }
-  if (!wantQuestion) return -2;
   const double totG = sGrand[nChunks - 1];
+  // running totals, once not finite, stay so: the last one tells (CpuEngine.cpp:368-371 checks each and carries on)
+  if (!(fabs(totG) < __longlong_as_double(0x7FF0000000000000ll))) { anomaly = true; if (kb.anomalies) atomicAdd(kb.anomalies + 1, 1ull); }
+  if (wantQuestion && !(totG > 0.0)) { anomaly = true; if (kb.anomalies) atomicAdd(kb.anomalies + 2, 1ull); }   // :375-377
+  if (sawAnomaly) *sawAnomaly = anomaly;
+  if (!wantQuestion) return -2;
   // SRDoubleNumber::MakeRandom: upper * rnd / max (left to right, both factors converted to double)
   const double sel = __ddiv_rn(__dmul_rn(totG, __ull2double_rn(random)), __ull2double_rn(~0ull));
   const int64_t iWorker = upper_bound_d(sGrand, nChunks, sel);

@@ -135,6 +135,7 @@ SIGNATURES = {
     "PqaB200_EvalQuestions": (_vp, [_vp, _i64, _pi64, _pd, _pd, _pd, _pi64]),
     "PqaB200_EvalQuestionsDetailed": (_vp, [_vp, _i64, _pd, _pd, _pd, _pd, _pd]),
     "PqaB200_P2PLastPhaseMs": (_vp, [_vp, _pd]),
+    "PqaB200_AnomalyCounts": (_vp, [_vp, _pu64]),
     "PqaB200_EvalQuestionsDetailedBatch": (_vp, [_vp, _i64, _pi64, _pd, _pd, _pd, _pd, _pd]),
     "PqaB200_SetEvalKernel": (_vp, [_vp, C.c_int32]),
     "PqaB200_SetEvalTuning": (_vp, [_vp, C.c_int32, _i64, _i64, C.c_int32]),
@@ -685,6 +686,13 @@ class PqaEngine:
     def p2p_record_answer_begin(self, quiz_ids, answers):
         ids, ans = _i64arr(quiz_ids), _i64arr(answers)
         _raise_or_return(self._lib.PqaB200_P2PRecordAnswerBegin(self.c_engine, ids.size, _p(ids, _pi64), _p(ans, _pi64)))
+
+    def anomaly_counts(self) -> np.ndarray:
+        """[priorities <= 0 or non-finite, non-finite running totals, grand totals <= 0] seen by NextQuestion so far (the
+        reference logs warnings for these and carries on: CEEvalQsSubtaskConsider.cpp:209-211, CpuEngine.cpp:368-377)."""
+        out = np.zeros(3, dtype=np.uint64)
+        _raise_or_return(self._lib.PqaB200_AnomalyCounts(self.c_engine, _p(out, _pu64)))
+        return out
 
     def p2p_last_phase_ms(self) -> np.ndarray:
         """[phase 1, barrier, phase 2, barrier, epilogue + selection] device ms of the last target-sharded P2PNextQuestion."""

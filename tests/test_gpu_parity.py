@@ -395,6 +395,34 @@ def test_initial_kb_and_dims(pqa):
     assert np.all(sA == INIT * INIT) and np.all(mD == K * (INIT * INIT)) and np.all(vB == INIT)
 
 
+@pytest.mark.parametrize("n", [1, 40])
+def test_degenerate_priorities_are_counted_not_fatal(pqa, ora, n):
+    """CEEvalQsSubtaskConsider.cpp:209-211 and CpuEngine.cpp:368-377 only WARN about a priority <= 0, a non-finite running
+    total and a grand total <= 0, and NextQuestion still answers. Cells of 1e300 make 1/mD^2 underflow: lack = 0, every
+    priority = 0 (the oracle agrees), the grand total is 0. The engine counts the three conditions (fused launch and batch
+    path) and keeps answering."""
+    Q, K, T, W = 24, 3, 16, 2
+    eng = pqa.PqaEngineFactory().create_b200_engine(pqa.EngineDefinition(K, Q, T, init_amount=1e150), emulated_workers=W,
+                                                    rng_seed=9)
+    assert np.array_equal(eng.anomaly_counts(), [0, 0, 0])
+    quizzes = eng.start_quiz_batch(n)
+    sA = np.full((Q, K, T), 1e300); mD = np.full((Q, T), K * 1e300)
+    prior = ora.start_quiz(np.full(T, 1e150), W)
+    assert np.all(oracle_eval_all(ora, (sA, mD, None), prior, W)["priority"] == 0.0)
+    got = eng.eval_questions(quizzes)
+    assert np.all(got["priority"] == 0.0)
+    before = eng.anomaly_counts()
+    chosen = eng.next_question_batch(quizzes, np.arange(n, dtype=np.uint64) * 977)
+    assert np.all((chosen >= 0) & (chosen < Q))
+    after = eng.anomaly_counts()
+    assert after[0] - before[0] == n * Q and after[1] == before[1] and after[2] - before[2] == n
+    # a healthy engine counts nothing
+    eng2 = make_engine(pqa, 16, 3, 32, 2)
+    q2 = eng2.start_quiz_batch(5)
+    eng2.next_question_batch(q2, np.arange(5, dtype=np.uint64))
+    assert np.array_equal(eng2.anomaly_counts(), [0, 0, 0])
+
+
 def test_error_contract(pqa):
     Q, K, T = 8, 3, 16
     eng = make_engine(pqa, Q, K, T, 2)
@@ -515,6 +543,14 @@ def bench_batch(eng, Q, K, T, B, depths=(0, 3, 8)):
     ((1000, 5, 1000), 256, 8, (0, 1, 2, 127, 128, 129, 254, 255)),   # BASELINE config 2 as bench.py runs it: two CTA tiles of 128 quizzes
     ((300, 5, 999), 200, 8, (0, 64, 130, 199)),                      # ragged T (padding lanes), second tile partly filled
     ((200, 3, 1400), 65, 4, (0, 31, 32, 64)),                        # smallest batch that takes the 8-warp / two-threads-per-quiz shape
+    # medium batches (k_eval_multi: 128 / G questions per CTA, slabs streamed in chunks)
+    ((1000, 5, 1000), 40, 8, (0, 1, 2, 39)),                         # G = 64, two questions per CTA
+    ((61, 5, 203), 33, 3, (0, 16, 32)),                              # odd question count: the last CTA holds one question; ragged T
+    ((45, 5, 999), 20, 3, (0, 10, 19)),                              # G = 32, four questions per CTA, last CTA holds one
+    ((130, 4, 600), 64, 4, (0, 33, 63)),                             # every quiz place of G = 64 taken
+    ((90, 2, 2100), 17, 2, (0, 8, 16)),                              # two answers, several chunks per question
+    ((77, 8, 300), 12, 2, (0, 5, 11)),                               # four threads per quiz, G = 16, four questions per CTA, K = 8
+    ((50, 5, 1000), 9, 8, (0, 4, 8)),                                # smallest batch of the medium kernel
 ])
 def test_benched_instantiation_vs_oracle(pqa, ora, dims, B, W, sample):
     """The instantiation behind every BENCH / SCALE number -- default tuning, batch > 64, whole slab in shared memory
