@@ -386,13 +386,20 @@ def train_workload(pqa, cores, cpu_sample_quizzes=4000):
         eng.set_active_question_batch(quizzes, qs[:, s])
         eng.record_answer_batch(quizzes, ans[:, s])
     eng.synchronize()
+    # the first call of this size also allocates the engine's pinned operation list (40 MB) and sort scratch: it is timed
+    # and reported, the value is the second call (same quizzes, same 10^6 updates; RecordQuizTarget leaves the quizzes alive)
+    t0 = time.perf_counter()
+    eng.record_quiz_target_batch(quizzes, targets)
+    eng.synchronize()
+    t_first = time.perf_counter() - t0
     launches0 = eng.kernel_launch_count()
     t0 = time.perf_counter()
     eng.record_quiz_target_batch(quizzes, targets)
     eng.synchronize()
     t_gpu = time.perf_counter() - t0
     out = {"workload": "train_1e6_updates_1000x5x1000", "updates": n * d, "quizzes": n, "value": n * d / t_gpu, "unit": "cell updates/s",
-           "seconds": t_gpu, "api": "PqaEngine_RecordQuizTargetBatch (host buffers, one call)",
+           "seconds": t_gpu, "first_call_seconds": t_first,
+           "api": "PqaEngine_RecordQuizTargetBatch (host buffers, one call; second call of the size, the first one allocates)",
            "gpu_launches": int(eng.kernel_launch_count() - launches0)}
     try:
         from oracle import oracle as ora

@@ -23,4 +23,9 @@ PY
 bash scripts/profile_hot.sh r02_eval_final > /dev/null 2>&1
 cuobjdump -sass -fun '_ZN3pqa13k_eval_stagedILi5ELi2ELi8EEEvNS_12StagedParamsE' probqa_b200/lib/libPqaCore.so > /tmp/prof/hot.sass 2>/dev/null
 python scripts/sass_loops.py /tmp/prof/hot.sass > gpurun_out/r02_hot_loops.txt 2>/dev/null
-tail -3 gpurun_out/r02_launches.txt; tail -12 gpurun_out/r02_eval_final.txt
+bash scripts/profile_others.sh > /dev/null 2>&1
+bash scripts/profile_multi.sh "8 32" > /dev/null 2>&1
+rm -f gpurun_out/*.ncu-rep
+bash scripts/client_loop.sh > /dev/null 2>&1
+bash scripts/sweep_mid_batches.sh > gpurun_out/r02_mid_batches.txt 2>&1
+tail -3 gpurun_out/r02_launches.txt; tail -12 gpurun_out/r02_eval_final.txt; tail -12 gpurun_out/r02_mid_batches.txt

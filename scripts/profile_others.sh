@@ -30,7 +30,7 @@ for s in range(d):
     eng.set_active_question_batch(ids, qs[:, s]); eng.record_answer_batch(ids, rng.integers(0, K, size=n))
 eng.record_quiz_target_batch(ids, rng.integers(0, T, size=n))
 PY
-ncu --set full --clock-control none -k regex:"k_update_priors|k_list_top_targets|k_select_question|k_train|k_add_vb|k_build_derived|DeviceRadixSort" -c 60 -o /tmp/prof/others -f python /tmp/others.py > gpurun_out/r02_others_ncu.log 2>&1
+ncu --set full --clock-control none -k regex:"k_update_priors|k_update_lanes|k_normalise_rows|k_list_top_targets|k_select_question|k_train|k_add_vb|k_build_derived|DeviceRadixSort" -c 80 -o /tmp/prof/others -f python /tmp/others.py > gpurun_out/r02_others_ncu.log 2>&1
 python scripts/ncu_summary.py /tmp/prof/others.ncu-rep > gpurun_out/r02_other_kernels_full.txt 2>&1
 python - <<'PY'
 import re
