@@ -1,17 +1,118 @@
 // probqa_b200: large RecordQuizTarget / Train batches (BASELINE config 5). The reference applies a quiz' answers in
 // sequence (CETrainOperation.cpp:15-83); operations on different (question, target) cells commute, operations on the same
 // cell must keep their sequence order. For big batches the grouping by cell is done on the device: a stable radix sort of
-// (cell key, sequence number) pairs (CUB, part of the CUDA toolkit), then one thread per sorted position -- the thread that
+// (cell key, sequence number) pairs (radix_sort_pairs below), then one thread per sorted position -- the thread that
 // sits at the head of a run of equal keys applies the whole run in sequence order with the same arithmetic as k_train_ops.
 // Results are bit-identical to the host-grouped path (tests/test_gpu_parity.py::test_record_quiz_target_and_train_bit_exact
 // runs both).
-#include <cub/device/device_radix_sort.cuh>
-
 #include "pqa_kernels.cuh"
 #include "pqa_device.cuh"
 
+#include <stdexcept>
+
 namespace pqa {
 void count_launch();
+
+// ---------------------------------------------------------------------------------------------------------
+// Stable least-significant-digit radix sort of (key, value) pairs, 8 bits per pass. A block owns a tile of kSortTile
+// consecutive elements. Per pass: k_rs_hist counts the tile's digits into hist[digit][block]; k_rs_scan turns the table
+// (read digit-major) into exclusive prefix sums = the first output position of every (digit, block); k_rs_scatter walks
+// its tile in order, 256 elements at a time, and places every element at (position of its digit for this block) + (number
+// of elements with the same digit earlier in the tile): earlier chunks are in the running offsets, earlier warps of the
+// chunk in the per-warp counts, earlier lanes of the warp come from __match_any_sync. Equal keys therefore keep their order.
+constexpr int kSortTile = 4096, kSortThreads = 256, kSortWarps = kSortThreads / 32;
+
+__global__ void __launch_bounds__(kSortThreads) k_rs_hist(const int64_t *__restrict__ keys, int64_t n, int shift,
+                                                          unsigned *__restrict__ hist, int nBlocks) {
+  __shared__ unsigned sHist[256];
+  sHist[threadIdx.x] = 0u;
+  __syncthreads();
+  const int64_t first = (int64_t)blockIdx.x * kSortTile;
+  const int64_t limit = (first + kSortTile < n) ? first + kSortTile : n;
+  for (int64_t x = first + threadIdx.x; x < limit; x += kSortThreads)
+    atomicAdd(&sHist[(unsigned)((uint64_t)keys[x] >> shift) & 255u], 1u);
+  __syncthreads();
+  hist[(size_t)threadIdx.x * nBlocks + blockIdx.x] = sHist[threadIdx.x];
+}
+
+// one block: exclusive prefix sums over m entries in place
+__global__ void __launch_bounds__(1024) k_rs_scan(unsigned *__restrict__ a, int64_t m) {
+  __shared__ unsigned sPart[1024];
+  const int64_t per = (m + 1023) / 1024;
+  const int64_t first = (int64_t)threadIdx.x * per;
+  const int64_t limit = (first + per < m) ? first + per : m;
+  unsigned sum = 0u;
+  for (int64_t x = first; x < limit; x++) sum += a[x];
+  sPart[threadIdx.x] = sum;
+  __syncthreads();
+  for (int d = 1; d < 1024; d <<= 1) {          // inclusive scan of the 1024 partial sums
+    const unsigned v = (threadIdx.x >= (unsigned)d) ? sPart[threadIdx.x - d] : 0u;
+    __syncthreads();
+    sPart[threadIdx.x] += v;
+    __syncthreads();
+  }
+  unsigned run = sPart[threadIdx.x] - sum;      // exclusive
+  for (int64_t x = first; x < limit; x++) { const unsigned v = a[x]; a[x] = run; run += v; }
+}
+
+__global__ void __launch_bounds__(kSortThreads) k_rs_scatter(const int64_t *__restrict__ keysIn, const int64_t *__restrict__ valsIn,
+                                                             int64_t *__restrict__ keysOut, int64_t *__restrict__ valsOut,
+                                                             int64_t n, int shift, const unsigned *__restrict__ offsets,
+                                                             int nBlocks) {
+  __shared__ unsigned sOff[256];                     // next output position of every digit for this block
+  __shared__ unsigned sWarp[kSortWarps][256];        // per chunk: how many elements with the digit every warp holds
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  sOff[threadIdx.x] = offsets[(size_t)threadIdx.x * nBlocks + blockIdx.x];
+  const int64_t first = (int64_t)blockIdx.x * kSortTile;
+  const int64_t limit = (first + kSortTile < n) ? first + kSortTile : n;
+  for (int64_t c0 = first; c0 < limit; c0 += kSortThreads) {
+#pragma unroll
+    for (int w = 0; w < kSortWarps; w++) sWarp[w][threadIdx.x] = 0u;
+    __syncthreads();                                 // also orders the previous chunk's update of sOff before its use below
+    const int64_t x = c0 + threadIdx.x;
+    const bool valid = x < limit;
+    int64_t key = 0, val = 0;
+    if (valid) { key = keysIn[x]; val = valsIn[x]; }
+    const unsigned digit = valid ? ((unsigned)((uint64_t)key >> shift) & 255u) : 256u + (unsigned)lane;   // invalid lanes match nobody
+    const unsigned peers = __match_any_sync(0xFFFFFFFFu, digit);
+    const unsigned rankInWarp = __popc(peers & ((1u << lane) - 1u));
+    if (valid && rankInWarp == 0) sWarp[warp][digit] = __popc(peers);
+    __syncthreads();
+    if (valid) {
+      unsigned before = 0u;
+      for (int w = 0; w < warp; w++) before += sWarp[w][digit];
+      const unsigned pos = sOff[digit] + before + rankInWarp;
+      keysOut[pos] = key;
+      valsOut[pos] = val;
+    }
+    __syncthreads();
+    unsigned total = 0u;
+#pragma unroll
+    for (int w = 0; w < kSortWarps; w++) total += sWarp[w][threadIdx.x];
+    sOff[threadIdx.x] += total;
+  }
+}
+
+static int64_t sort_blocks(int64_t n) { return (n + kSortTile - 1) / kSortTile; }
+static size_t sort_hist_bytes(int64_t n) { return sizeof(unsigned) * 256 * (size_t)sort_blocks(n); }
+
+// Sorts n pairs by the low `bits` bits of the keys. srcKeys / srcVals are only read; (aKeys, aVals) and (bKeys, bVals) are
+// work buffers distinct from the source and from each other; the sorted pairs end in (bKeys, bVals).
+static void radix_sort_pairs(const int64_t *srcKeys, const int64_t *srcVals, int64_t *aKeys, int64_t *aVals, int64_t *bKeys,
+                             int64_t *bVals, unsigned *hist, int64_t n, int bits, cudaStream_t st) {
+  const int passes = (bits + 7) / 8;
+  const int nBlocks = (int)sort_blocks(n);
+  const int64_t *inK = srcKeys, *inV = srcVals;
+  for (int p = 0; p < passes; p++) {
+    const bool toB = ((passes - 1 - p) & 1) == 0;      // the last pass writes b, the one before it a, ...
+    int64_t *outK = toB ? bKeys : aKeys, *outV = toB ? bVals : aVals;
+    k_rs_hist<<<nBlocks, kSortThreads, 0, st>>>(inK, n, 8 * p, hist, nBlocks);
+    k_rs_scan<<<1, 1024, 0, st>>>(hist, (int64_t)256 * nBlocks);
+    k_rs_scatter<<<nBlocks, kSortThreads, 0, st>>>(inK, inV, outK, outV, n, 8 * p, hist, nBlocks);
+    count_launch(); count_launch(); count_launch();
+    inK = outK; inV = outV;
+  }
+}
 
 __global__ void k_train_keys(const TrainOp *__restrict__ ops, int64_t nOps, int64_t T, int64_t *__restrict__ keys,
                              int64_t *__restrict__ seq) {
@@ -77,11 +178,8 @@ static int bits_for(int64_t maxKey) {
 }
 
 size_t train_sort_scratch_bytes(int64_t n) {
-  size_t tmp = 0;
-  cub::DeviceRadixSort::SortPairs(nullptr, tmp, (const int64_t *)nullptr, (int64_t *)nullptr, (const int64_t *)nullptr,
-                                  (int64_t *)nullptr, (int)n, 0, 63);
-  // layout: keysIn | seqIn | keysOut | seqOut | cub temp
-  return sizeof(int64_t) * 4 * (size_t)n + tmp + 256;
+  // layout: keysIn | seqIn | keysA | seqA | keysOut | seqOut | digit table
+  return sizeof(int64_t) * 6 * (size_t)n + sort_hist_bytes(n) + 256;
 }
 
 // dOps: nOps operations in sequence order (questions owned by this device, targets local); dScratch from
@@ -89,31 +187,29 @@ size_t train_sort_scratch_bytes(int64_t n) {
 void launch_train_ops_device_grouped(const DeviceKB &kb, const TrainOp *dOps, int64_t nOps, void *dScratch,
                                      size_t scratchBytes, cudaStream_t st) {
   if (nOps <= 0) return;
-  int64_t *keysIn = (int64_t *)dScratch, *seqIn = keysIn + nOps, *keysOut = seqIn + nOps, *seqOut = keysOut + nOps;
-  void *tmp = (void *)(((uintptr_t)(seqOut + nOps) + 255) & ~(uintptr_t)255);
-  size_t tmpBytes = scratchBytes - ((char *)tmp - (char *)dScratch);
+  if (scratchBytes < train_sort_scratch_bytes(nOps)) throw std::runtime_error("train sort scratch too small");
+  int64_t *keysIn = (int64_t *)dScratch, *seqIn = keysIn + nOps, *keysA = seqIn + nOps, *seqA = keysA + nOps,
+          *keysOut = seqA + nOps, *seqOut = keysOut + nOps;
+  unsigned *hist = (unsigned *)(((uintptr_t)(seqOut + nOps) + 255) & ~(uintptr_t)255);
   const unsigned grid = (unsigned)((nOps + 255) / 256);
   k_train_keys<<<grid, 256, 0, st>>>(dOps, nOps, kb.T, keysIn, seqIn);
   count_launch();
-  cub::DeviceRadixSort::SortPairs(tmp, tmpBytes, keysIn, keysOut, seqIn, seqOut, (int)nOps, 0,
-                                  bits_for(kb.Q * kb.T), st);   // stable: equal cells keep their sequence order
-  count_launch();
+  radix_sort_pairs(keysIn, seqIn, keysA, seqA, keysOut, seqOut, hist, nOps, bits_for(kb.Q * kb.T), st);   // stable: equal cells keep their sequence order
   k_train_ops_sorted<<<grid, 256, 0, st>>>(kb, dOps, keysOut, seqOut, nOps);
   count_launch();
 }
 
-// vB[target] += amount for n (target, amount) pairs in sequence order; dTargets doubles as the key input.
+// vB[target] += amount for n (target, amount) pairs in sequence order; dTargets is the key input.
 void launch_add_vb_device_grouped(const DeviceKB &kb, const int64_t *dTargets, const double *dAmounts, int64_t n,
                                   void *dScratch, size_t scratchBytes, cudaStream_t st) {
   if (n <= 0) return;
-  int64_t *seqIn = (int64_t *)dScratch + n, *keysOut = seqIn + n, *seqOut = keysOut + n;
-  void *tmp = (void *)(((uintptr_t)(seqOut + n) + 255) & ~(uintptr_t)255);
-  size_t tmpBytes = scratchBytes - ((char *)tmp - (char *)dScratch);
+  if (scratchBytes < train_sort_scratch_bytes(n)) throw std::runtime_error("train sort scratch too small");
+  int64_t *seqIn = (int64_t *)dScratch + n, *keysA = seqIn + n, *seqA = keysA + n, *keysOut = seqA + n, *seqOut = keysOut + n;
+  unsigned *hist = (unsigned *)(((uintptr_t)(seqOut + n) + 255) & ~(uintptr_t)255);
   const unsigned grid = (unsigned)((n + 255) / 256);
   k_vb_keys<<<grid, 256, 0, st>>>(dTargets, n, seqIn);
   count_launch();
-  cub::DeviceRadixSort::SortPairs(tmp, tmpBytes, dTargets, keysOut, seqIn, seqOut, (int)n, 0, bits_for(kb.T), st);
-  count_launch();
+  radix_sort_pairs(dTargets, seqIn, keysA, seqA, keysOut, seqOut, hist, n, bits_for(kb.T), st);
   k_add_vb_sorted<<<grid, 256, 0, st>>>(kb, keysOut, seqOut, dAmounts, n);
   count_launch();
 }
